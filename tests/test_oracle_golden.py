@@ -1,0 +1,55 @@
+"""Pin the CPU oracle (oracle/pinn_oracle.py) against golden vectors produced by
+executing the reference itself (tests/golden/make_golden.py)."""
+import numpy as np
+import pytest
+import torch
+
+from tests import golden_util as gu
+from oracle import pinn_oracle as po
+
+# param name in the reference's state dict -> (layer index, key in oracle grads)
+_KEY = {"weight": "W", "weight_g": "g", "weight_v": "v", "bias": "b"}
+
+
+def _check(name, dtype, tag, tol):
+    problem, flat = gu.load(name)
+    want = {d["name"]: [k for k in gu.ref_domain(flat, tag, d["name"])] for d in problem["domains"]}
+    res = po.training_step(problem, dtype=dtype, want=want)
+    # every variable the reference graph computed (outputs, derivative symbols, residuals)
+    for d in problem["domains"]:
+        ref = gu.ref_domain(flat, tag, d["name"])
+        for k, v in ref.items():
+            err = gu.normwise(res["domains"][d["name"]][k], v)
+            assert err <= tol, f"{name}/{d['name']}/{k}: {err:.3e}"
+    # per-domain and total loss
+    for k, v in gu.ref_components(flat, tag).items():
+        dom = k[: -len("_loss")]
+        assert abs(res["loss_components"][dom] - v) <= tol * max(abs(v), 1e-30) * 10, k
+    ref_loss = float(flat[f"{tag}/loss"])
+    assert abs(res["loss"] - ref_loss) <= 10 * tol * abs(ref_loss)
+    # parameter gradients (raw parameters, i.e. weight_g / weight_v / bias under weight-norm)
+    for pname, g in gu.ref_grads(flat, tag).items():
+        net, rest = pname.split("/", 1)
+        parts = rest.split(".")  # layers.mlp_<i>.<param>
+        li = int(parts[1].split("_")[1])
+        og = res["grads"][net][li][_KEY[parts[2]]]
+        assert og is not None, pname
+        err = gu.normwise(og.reshape(g.shape), g)
+        assert err <= tol * 20, f"{name}/{pname}: {err:.3e}"
+    # parameters the reference leaves without gradient stay without gradient
+    import json
+    for pname in json.loads(str(flat[f"{tag}/grad_none"])):
+        net, rest = pname.split("/", 1)
+        parts = rest.split(".")
+        li = int(parts[1].split("_")[1])
+        assert res["grads"][net][li][_KEY[parts[2]]] is None, pname
+
+
+@pytest.mark.parametrize("name", gu.CONFIGS)
+def test_oracle_matches_reference_fp32(name):
+    _check(name, torch.float32, "ref32", 2e-6)
+
+
+@pytest.mark.parametrize("name", gu.CONFIGS)
+def test_oracle_matches_reference_fp64(name):
+    _check(name, torch.float64, "ref64", 1e-12)
