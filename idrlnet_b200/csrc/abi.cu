@@ -1,0 +1,334 @@
+// extern "C" entry points of libpinn_b200.so (see include/pinn_b200.h).
+#include <cuda_runtime.h>
+#include <stdio.h>
+#include <stdarg.h>
+#include <string.h>
+
+#include <atomic>
+#include <mutex>
+
+#include "narrow_kernel.cuh"
+#include "wide.cuh"
+
+namespace pinn {
+
+static thread_local char g_err[512] = "";
+static std::atomic<int64_t> g_launches{0};
+
+static int fail(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return code;
+}
+static int cuda_fail(cudaError_t e, const char* what) {
+  snprintf(g_err, sizeof(g_err), "%s: %s", what, cudaGetErrorString(e));
+  return (int)e;
+}
+void count_launch(int n) { g_launches += n; }
+
+static int padded_width(int H) { return H <= 20 ? 20 : (H <= 32 ? 32 : 0); }
+
+static const NarrowKernelInfo* narrow_lookup(const pinn_mlp* m, const pinn_jets* j) {
+  const int Hp = padded_width(m->width);
+  if (!Hp) return nullptr;
+  if (Hp == 20) {
+    if (m->act == PINN_ACT_TANH) return narrow_table_h20_tanh(j->n_first, j->n_second);
+    if (m->act == PINN_ACT_SILU) return narrow_table_h20_silu(j->n_first, j->n_second);
+    if (m->act == PINN_ACT_SIN) return narrow_table_h20_sin(j->n_first, j->n_second);
+  } else {
+    if (m->act == PINN_ACT_TANH) return narrow_table_h32_tanh(j->n_first, j->n_second);
+    if (m->act == PINN_ACT_SILU) return narrow_table_h32_silu(j->n_first, j->n_second);
+    if (m->act == PINN_ACT_SIN) return narrow_table_h32_sin(j->n_first, j->n_second);
+  }
+  return nullptr;
+}
+
+static int check_mlp(const pinn_mlp* m, const pinn_jets* j) {
+  if (!m || !j) return fail(PINN_E_INVALID, "null descriptor");
+  if (m->n_in < 1 || m->n_in > PINN_MAX_IN) return fail(PINN_E_INVALID, "n_in=%d out of range", m->n_in);
+  if (m->n_out < 1 || m->n_out > PINN_MAX_OUT) return fail(PINN_E_INVALID, "n_out=%d out of range", m->n_out);
+  if (m->n_hidden < 1 || m->n_hidden + 1 > PINN_MAX_LAYERS) return fail(PINN_E_INVALID, "n_hidden=%d out of range", m->n_hidden);
+  if (m->width < 1) return fail(PINN_E_INVALID, "width=%d", m->width);
+  if (m->act < 0 || m->act > PINN_ACT_SIN) return fail(PINN_E_INVALID, "act=%d", m->act);
+  if (j->n_first < 0 || j->n_first > 3 || j->n_second < 0 || j->n_second > j->n_first)
+    return fail(PINN_E_UNSUPPORTED, "jet plan (%d first, %d second) not supported", j->n_first, j->n_second);
+  for (int i = 0; i < j->n_first; ++i)
+    if (j->first_in[i] < 0 || j->first_in[i] >= m->n_in) return fail(PINN_E_INVALID, "first_in[%d]=%d", i, j->first_in[i]);
+  for (int l = 0; l <= m->n_hidden; ++l)
+    if (!m->W[l] || !m->b[l]) return fail(PINN_E_INVALID, "layer %d has null weights", l);
+  return 0;
+}
+
+struct DeviceInfo {
+  int sm_count = 0;
+  int max_smem_optin = 0;
+  int cc_major = 0;
+  bool ok = false;
+};
+static DeviceInfo& device_info() {
+  static thread_local int cached_dev = -1;
+  static thread_local DeviceInfo info;
+  int dev = -1;
+  if (cudaGetDevice(&dev) != cudaSuccess) {
+    info.ok = false;
+    return info;
+  }
+  if (dev != cached_dev) {
+    cudaDeviceGetAttribute(&info.sm_count, cudaDevAttrMultiProcessorCount, dev);
+    cudaDeviceGetAttribute(&info.max_smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+    cudaDeviceGetAttribute(&info.cc_major, cudaDevAttrComputeCapabilityMajor, dev);
+    info.ok = true;
+    cached_dev = dev;
+  }
+  return info;
+}
+
+// ----------------------------------------------------------------------------
+// workspace layout (floats): [gpart: MAX_CTA * PP][lpart: n_domains * MAX_CTA]
+// ----------------------------------------------------------------------------
+static const int kMaxCta = 148 * 2;
+
+struct NarrowPlan {
+  const NarrowKernelInfo* k;
+  int Hp, L, PP, n_warps, smem_bytes, n_cta_cap;
+};
+
+static int narrow_plan(const pinn_mlp* m, const pinn_jets* j, NarrowPlan* pl, bool need_device) {
+  pl->k = narrow_lookup(m, j);
+  if (!pl->k) return fail(PINN_E_UNSUPPORTED, "no narrow kernel for width %d", m->width);
+  pl->Hp = pl->k->H;
+  pl->L = m->n_hidden;
+  const Layout lay(pl->Hp, pl->L);
+  pl->PP = lay.size();
+  const int wf = pl->k->warp_floats(pl->L);
+  int max_smem = 232448;  // 227 KB
+  int sms = 148;
+  if (need_device) {
+    DeviceInfo& di = device_info();
+    if (!di.ok) return fail(PINN_E_NO_DEVICE, "no CUDA device");
+    max_smem = di.max_smem_optin;
+    sms = di.sm_count;
+  }
+  int nw = (max_smem - lay.size() * 4) / (wf * 4);
+  if (nw > 8) nw = 8;
+  if (nw < 1) return fail(PINN_E_UNSUPPORTED, "net too deep for the narrow kernel (smem)");
+  pl->n_warps = nw;
+  pl->smem_bytes = (lay.size() + nw * wf) * 4;
+  pl->n_cta_cap = sms < kMaxCta ? sms : kMaxCta;
+  return 0;
+}
+
+__global__ void finalize_kernel(const float* gpart, const float* lpart, int max_cta, int PP, int n_in, int n_out,
+                                int Hreal, int Hp, int L, int64_t n_params, float* flat_grad, int add, float* losses,
+                                int n_dom) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n_params) {
+    const Layout lay(Hp, L);
+    const int idx = flat_to_layout(n_in, n_out, Hreal, lay, i);
+    float s = 0.f;
+    for (int c = 0; c < max_cta; ++c) s += gpart[(size_t)c * PP + idx];
+    flat_grad[i] = add ? flat_grad[i] + s : s;
+  }
+  if (blockIdx.x == 0 && threadIdx.x < n_dom && losses) {
+    float s = 0.f;
+    for (int c = 0; c < max_cta; ++c) s += lpart[(size_t)threadIdx.x * max_cta + c];
+    losses[threadIdx.x] = s;
+  }
+}
+
+static int launch_narrow(const pinn_mlp* m, const pinn_jets* j, NarrowParams& p, const NarrowPlan& pl, cudaStream_t st) {
+  static std::mutex mu;
+  {
+    std::lock_guard<std::mutex> lk(mu);
+    cudaError_t e = cudaFuncSetAttribute((const void*)pl.k->fn, cudaFuncAttributeMaxDynamicSharedMemorySize, pl.smem_bytes);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(narrow)");
+  }
+  p.n_warps = pl.n_warps;
+  const int64_t tiles = (p.n_points + 31) / 32;
+  p.n_tiles = (int32_t)tiles;
+  int64_t ctas = (tiles + pl.n_warps - 1) / pl.n_warps;
+  if (ctas > pl.n_cta_cap) ctas = pl.n_cta_cap;
+  if (ctas < 1) ctas = 1;
+  narrow_kernel_t fn = pl.k->fn;
+  fn<<<(unsigned)ctas, pl.n_warps * 32, pl.smem_bytes, st>>>(p, m->width);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return cuda_fail(e, "narrow kernel launch");
+  count_launch(1);
+  return 0;
+}
+
+static void fill_net(NarrowParams& p, const pinn_mlp* m, const pinn_jets* j) {
+  memset(&p, 0, sizeof(p));
+  p.n_in = m->n_in;
+  p.n_out = m->n_out;
+  p.n_hidden = m->n_hidden;
+  for (int l = 0; l <= m->n_hidden; ++l) {
+    p.W[l] = m->W[l];
+    p.b[l] = m->b[l];
+  }
+  p.jets = *j;
+  p.max_cta = kMaxCta;
+}
+
+}  // namespace pinn
+
+using namespace pinn;
+
+extern "C" {
+
+int pinn_abi_version(void) { return PINN_ABI_VERSION; }
+const char* pinn_last_error(void) { return g_err; }
+int64_t pinn_launch_count(void) { return g_launches.load(); }
+
+int64_t pinn_param_count(const pinn_mlp* m) {
+  if (!m) return 0;
+  int64_t n = (int64_t)m->width * m->n_in + m->width;
+  n += (int64_t)(m->n_hidden - 1) * ((int64_t)m->width * m->width + m->width);
+  n += (int64_t)m->n_out * m->width + m->n_out;
+  return n;
+}
+
+int pinn_supported(const pinn_mlp* m, const pinn_jets* j) {
+  if (!m || !j) return 0;
+  if (narrow_lookup(m, j)) {
+    NarrowPlan pl;
+    return narrow_plan(m, j, &pl, false) == 0 ? 1 : 0;
+  }
+  return wide_supported(m, j) ? 1 : 0;
+}
+
+int64_t pinn_workspace_bytes(const pinn_mlp* m, const pinn_jets* j, int32_t n_domains) {
+  if (!m || !j || n_domains < 1) return 0;
+  if (narrow_lookup(m, j)) {
+    NarrowPlan pl;
+    if (narrow_plan(m, j, &pl, false)) return 0;
+    return ((int64_t)kMaxCta * pl.PP + (int64_t)n_domains * kMaxCta) * 4;
+  }
+  return wide_workspace_bytes(m, j, n_domains);
+}
+
+static int narrow_step_common(const pinn_mlp* m, const pinn_jets* j, NarrowParams& p, void* ws, int64_t ws_bytes,
+                              int n_slots_needed, int accumulate, cudaStream_t st) {
+  NarrowPlan pl;
+  int rc = narrow_plan(m, j, &pl, true);
+  if (rc) return rc;
+  const int64_t gbytes = (int64_t)kMaxCta * pl.PP * 4;
+  if (!ws || ws_bytes < gbytes + (int64_t)n_slots_needed * kMaxCta * 4)
+    return fail(PINN_E_WORKSPACE, "workspace too small: %lld bytes", (long long)ws_bytes);
+  p.gpart = (float*)ws;
+  p.lpart = (float*)((char*)ws + gbytes);
+  if (!accumulate) {
+    cudaError_t e = cudaMemsetAsync(ws, 0, (size_t)ws_bytes, st);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaMemsetAsync(workspace)");
+  }
+  return launch_narrow(m, j, p, pl, st);
+}
+
+int pinn_step_fused(const pinn_mlp* m, const pinn_jets* j, const pinn_domain* dom, void* ws, int64_t ws_bytes,
+                    int32_t domain_slot, int32_t accumulate, void* stream) {
+  int rc = check_mlp(m, j);
+  if (rc) return rc;
+  if (!dom) return fail(PINN_E_INVALID, "null domain");
+  if (dom->n_points < 0 || dom->n_eq < 0 || dom->n_eq > PINN_MAX_EQ || dom->n_terms < 0 ||
+      dom->n_terms > PINN_MAX_TERMS || dom->n_aux < 0 || dom->n_aux > PINN_MAX_AUX || domain_slot < 0)
+    return fail(PINN_E_INVALID, "malformed domain descriptor");
+  for (int d = 0; d < m->n_in; ++d)
+    if (!dom->coords[d] && dom->n_points > 0) return fail(PINN_E_INVALID, "null coordinate column %d", d);
+  for (int e = 0; e < dom->n_eq; ++e) {
+    const pinn_equation& q = dom->eq[e];
+    if (q.term_begin < 0 || q.term_end < q.term_begin || q.term_end > dom->n_terms)
+      return fail(PINN_E_INVALID, "equation %d term range", e);
+    for (int t = q.term_begin; t < q.term_end; ++t) {
+      if (dom->terms[t].n_fac > PINN_MAX_FACTORS) return fail(PINN_E_INVALID, "term %d has too many factors", t);
+      for (int f = 0; f < dom->terms[t].n_fac; ++f)
+        if (dom->terms[t].fac[f] >= PINN_SYM_COUNT) return fail(PINN_E_INVALID, "term %d symbol id", t);
+    }
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  if (narrow_lookup(m, j)) {
+    NarrowParams p;
+    fill_net(p, m, j);
+    p.mode = MODE_FUSED;
+    p.n_points = dom->n_points;
+    for (int d = 0; d < m->n_in; ++d) p.coords[d] = dom->coords[d];
+    p.dom = *dom;
+    p.domain_slot = domain_slot;
+    return narrow_step_common(m, j, p, ws, ws_bytes, domain_slot + 1, accumulate, st);
+  }
+  if (wide_supported(m, j)) return wide_step_fused(m, j, dom, ws, ws_bytes, domain_slot, accumulate, st);
+  return fail(PINN_E_UNSUPPORTED, "no fused kernel for width %d / act %d", m->width, m->act);
+}
+
+int pinn_step_finalize(const pinn_mlp* m, const pinn_jets* j, void* ws, int64_t ws_bytes, int32_t n_domains,
+                       float* flat_grad, int32_t add_to_grad, float* losses, void* stream) {
+  int rc = check_mlp(m, j);
+  if (rc) return rc;
+  if (!flat_grad) return fail(PINN_E_INVALID, "null flat_grad");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (narrow_lookup(m, j)) {
+    NarrowPlan pl;
+    rc = narrow_plan(m, j, &pl, true);
+    if (rc) return rc;
+    const int64_t gbytes = (int64_t)kMaxCta * pl.PP * 4;
+    if (!ws || ws_bytes < gbytes + (int64_t)n_domains * kMaxCta * 4) return fail(PINN_E_WORKSPACE, "workspace too small");
+    if (n_domains > 256) return fail(PINN_E_INVALID, "too many domains");
+    const int64_t np = pinn_param_count(m);
+    const int threads = 256;
+    const int blocks = (int)((np + threads - 1) / threads);
+    finalize_kernel<<<blocks, threads, 0, st>>>((const float*)ws, (const float*)((char*)ws + gbytes), kMaxCta, pl.PP,
+                                                m->n_in, m->n_out, m->width, pl.Hp, pl.L, np, flat_grad, add_to_grad,
+                                                losses, n_domains);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return cuda_fail(e, "finalize launch");
+    count_launch(1);
+    return 0;
+  }
+  if (wide_supported(m, j)) return wide_step_finalize(m, j, ws, ws_bytes, n_domains, flat_grad, add_to_grad, losses, st);
+  return fail(PINN_E_UNSUPPORTED, "no fused kernel for width %d", m->width);
+}
+
+int pinn_jet_forward(const pinn_mlp* m, const pinn_jets* j, int64_t n_points, const float* const* coords, float* out,
+                     void* stream) {
+  int rc = check_mlp(m, j);
+  if (rc) return rc;
+  if (!coords || !out || n_points < 0) return fail(PINN_E_INVALID, "null argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (n_points == 0) return 0;
+  if (narrow_lookup(m, j)) {
+    NarrowPlan pl;
+    rc = narrow_plan(m, j, &pl, true);
+    if (rc) return rc;
+    NarrowParams p;
+    fill_net(p, m, j);
+    p.mode = MODE_FWD;
+    p.n_points = n_points;
+    for (int d = 0; d < m->n_in; ++d) p.coords[d] = coords[d];
+    p.jets_out = out;
+    return launch_narrow(m, j, p, pl, st);
+  }
+  if (wide_supported(m, j)) return wide_jet_forward(m, j, n_points, coords, out, st);
+  return fail(PINN_E_UNSUPPORTED, "no kernel for width %d", m->width);
+}
+
+int pinn_jet_backward(const pinn_mlp* m, const pinn_jets* j, int64_t n_points, const float* const* coords,
+                      const float* out_bar, void* ws, int64_t ws_bytes, int32_t accumulate, void* stream) {
+  int rc = check_mlp(m, j);
+  if (rc) return rc;
+  if (!coords || !out_bar || n_points < 0) return fail(PINN_E_INVALID, "null argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (narrow_lookup(m, j)) {
+    NarrowParams p;
+    fill_net(p, m, j);
+    p.mode = MODE_BWD;
+    p.n_points = n_points;
+    for (int d = 0; d < m->n_in; ++d) p.coords[d] = coords[d];
+    p.jets_bar = out_bar;
+    return narrow_step_common(m, j, p, ws, ws_bytes, 1, accumulate, st);
+  }
+  if (wide_supported(m, j)) return wide_jet_backward(m, j, n_points, coords, out_bar, ws, ws_bytes, accumulate, st);
+  return fail(PINN_E_UNSUPPORTED, "no kernel for width %d", m->width);
+}
+
+}  // extern "C"

@@ -1,0 +1,5 @@
+// Narrow fused-step kernels: hidden width <= 20, activation sin.
+#include "narrow_kernel.cuh"
+namespace pinn {
+PINN_NARROW_TABLE(narrow_table_h20_sin, 20, PINN_ACT_SIN)
+}

@@ -1,0 +1,97 @@
+// __global__ wrapper around the warp programs of narrow_warp.h and the
+// per-translation-unit lookup tables.
+#pragma once
+#include <cuda_runtime.h>
+
+#include "narrow_warp.h"
+
+namespace pinn {
+
+typedef void (*narrow_kernel_t)(const NarrowParams, int);
+
+struct NarrowKernelInfo {
+  narrow_kernel_t fn;
+  int H, C;
+  int (*warp_floats)(int L);
+};
+
+template <class NW>
+__global__ void __launch_bounds__(256, 1) narrow_kernel(const __grid_constant__ NarrowParams p, int Hreal) {
+  extern __shared__ __align__(16) float smem[];
+  const int L = p.n_hidden;
+  const Layout lay(NW::H, L);
+  const int tid = threadIdx.x;
+  const int warp = tid >> 5, lane = tid & 31;
+  const int nwarps = blockDim.x >> 5;
+  const int wf = NW::warp_floats(L);
+  float* wm = smem + lay.size() + warp * wf;
+
+  for (int i = tid; i < lay.size(); i += blockDim.x) smem[i] = stage_weight(p, Hreal, lay, i);
+  {
+    float* g = wm + NW::off_gacc(L);
+    for (int i = lane; i < lay.size(); i += 32) g[i] = 0.f;
+  }
+  __syncthreads();
+
+  typename NW::Lane ln;
+  ln.loss = 0.f;
+  for (int64_t tile = (int64_t)blockIdx.x * nwarps + warp; tile < p.n_tiles; tile += (int64_t)gridDim.x * nwarps) {
+    NW::phase_forward(p, smem, wm, lane, tile, ln);
+    if (p.mode == MODE_FWD) continue;
+    __syncwarp();
+    NW::phase_gemm_out(p, wm, lane);
+    __syncwarp();
+    for (int l = L; l >= 2; --l) {
+      NW::phase_backward_layer(p, smem, wm, lane, l);
+      __syncwarp();
+      NW::phase_gemm_hidden(p, wm, lane, l);
+      __syncwarp();
+    }
+    NW::phase_gemm_first(p, wm, lane);
+    __syncwarp();
+  }
+  if (p.mode == MODE_FWD) return;
+
+  wm[NW::off_xs(L) + lane] = ln.loss;
+  __syncthreads();
+  // per-CTA partial = sum over the CTA's warps, in warp order (deterministic)
+  float* gp = p.gpart + (size_t)blockIdx.x * lay.size();
+  for (int i = tid; i < lay.size(); i += blockDim.x) {
+    float s = 0.f;
+    for (int w = 0; w < nwarps; ++w) s += smem[lay.size() + w * wf + NW::off_gacc(L) + i];
+    gp[i] += s;
+  }
+  if (p.mode == MODE_FUSED && tid == 0) {
+    float s = 0.f;
+    for (int w = 0; w < nwarps; ++w) {
+      float sw_ = 0.f;
+      for (int l2 = 0; l2 < 32; ++l2) sw_ += smem[lay.size() + w * wf + NW::off_xs(L) + l2];
+      s += sw_;
+    }
+    p.lpart[(size_t)p.domain_slot * p.max_cta + blockIdx.x] += s;
+  }
+}
+
+// One table per (H, ACT) translation unit: entries for every (NF, NS).
+#define PINN_NARROW_ENTRY(H, NF, NS, ACT) \
+  { narrow_kernel<NarrowWarp<H, NF, NS, ACT>>, H, 1 + NF + NS, &NarrowWarp<H, NF, NS, ACT>::warp_floats }
+
+#define PINN_NARROW_TABLE(NAME, H, ACT)                                          \
+  const NarrowKernelInfo* NAME(int nf, int ns) {                                 \
+    static const NarrowKernelInfo t[4][4] = {                                    \
+        {PINN_NARROW_ENTRY(H, 0, 0, ACT), {0, 0, 0, 0}, {0, 0, 0, 0}, {0, 0, 0, 0}}, \
+        {PINN_NARROW_ENTRY(H, 1, 0, ACT), PINN_NARROW_ENTRY(H, 1, 1, ACT), {0, 0, 0, 0}, {0, 0, 0, 0}}, \
+        {PINN_NARROW_ENTRY(H, 2, 0, ACT), PINN_NARROW_ENTRY(H, 2, 1, ACT), PINN_NARROW_ENTRY(H, 2, 2, ACT), {0, 0, 0, 0}}, \
+        {PINN_NARROW_ENTRY(H, 3, 0, ACT), PINN_NARROW_ENTRY(H, 3, 1, ACT), PINN_NARROW_ENTRY(H, 3, 2, ACT), PINN_NARROW_ENTRY(H, 3, 3, ACT)}}; \
+    if (nf < 0 || nf > 3 || ns < 0 || ns > nf) return nullptr;                   \
+    return t[nf][ns].fn ? &t[nf][ns] : nullptr;                                  \
+  }
+
+const NarrowKernelInfo* narrow_table_h20_tanh(int nf, int ns);
+const NarrowKernelInfo* narrow_table_h20_silu(int nf, int ns);
+const NarrowKernelInfo* narrow_table_h20_sin(int nf, int ns);
+const NarrowKernelInfo* narrow_table_h32_tanh(int nf, int ns);
+const NarrowKernelInfo* narrow_table_h32_silu(int nf, int ns);
+const NarrowKernelInfo* narrow_table_h32_sin(int nf, int ns);
+
+}  // namespace pinn

@@ -1,0 +1,595 @@
+// Fused PINN step for NARROW nets (hidden width H <= 32): FP32 FMA, one warp
+// owns a tile of 32 collocation points from the forward pass through the
+// reverse pass; one lane = one point.
+//
+// Replaces idrlnet/net.py:14-36 + idrlnet/variable.py:161-208 (forward Taylor
+// jets instead of nested autograd.grad), idrlnet/node.py:105-109 (residual),
+// idrlnet/variable.py:40-80 (weighted loss) and loss.backward()
+// (idrlnet/solver.py:338).  Math: SURVEY.md section 8(a) "Jet mathematics".
+//
+// Data flow per warp tile (all on chip; HBM traffic = the coordinate columns,
+// targets/lambda/area in, nothing per point out):
+//   * the lane's layer-input jet h[c][k] lives in registers (C*H values);
+//   * the (transposed) weights Wt[k][j] are shared by the CTA in smem and read
+//     as warp-broadcast float4 -> 4*C FMAs per LDS.128;
+//   * pre-activation jets z of layers 2..L are stashed in per-warp smem rows
+//     (row stride chosen so float4 accesses are conflict free) and are the only
+//     forward state kept for the reverse pass (activations are recomputed);
+//   * the reverse pass overwrites each z with its adjoint zbar in place;
+//   * dW_l = sum over the 32 points and C channels of zbar_l^T h_{l-1} is a
+//     small warp-local GEMM from smem in 4x4 register tiles, accumulated in a
+//     per-warp smem copy of the gradient -> no atomics, deterministic;
+//   * warps never synchronise with each other inside the tile loop.
+//
+// The code below is written as per-lane "phase" functions separated by
+// __syncwarp(); tests/emu runs the same functions lane by lane on the CPU.
+#pragma once
+#include "pinn_common.h"
+
+namespace pinn {
+
+enum { MODE_FUSED = 0, MODE_FWD = 1, MODE_BWD = 2 };
+
+struct NarrowParams {
+  // network
+  int32_t n_in, n_out, n_hidden, mode;  // mode: MODE_*
+  const float* W[PINN_MAX_LAYERS];
+  const float* b[PINN_MAX_LAYERS];
+  pinn_jets jets;
+  // points
+  int64_t n_points;
+  const float* coords[PINN_MAX_IN];
+  // fused mode
+  pinn_domain dom;
+  // generic modes
+  float* jets_out;        // MODE_FWD : [(c*n_out+o)*N + n]
+  const float* jets_bar;  // MODE_BWD : same layout
+  // results
+  float* gpart;  // [max_cta][PP] gradient partials (padded layout, see Layout)
+  float* lpart;  // [n_slots][max_cta] loss partials
+  int32_t max_cta, domain_slot;
+  int32_t n_warps, n_tiles;
+};
+
+// Padded, transposed parameter layout used in smem for the weights, for the
+// per-warp gradient accumulators and for the per-CTA gradient partials.
+struct Layout {
+  int H, L;
+  PINN_HD Layout(int h, int l) : H(h), L(l) {}
+  PINN_HD int w1() const { return 0; }                    // W1t[d][j]   4*H
+  PINN_HD int b1() const { return 4 * H; }                 // b1[j]       H
+  PINN_HD int wh(int l) const { return 5 * H + (l - 2) * (H * H + H); }  // Wt_l[k][j], l = 2..L
+  PINN_HD int bh(int l) const { return wh(l) + H * H; }
+  PINN_HD int wo() const { return 5 * H + (L - 1) * (H * H + H); }      // Woutt[k][o4]  4*H
+  PINN_HD int bo() const { return wo() + 4 * H; }          // bout[4]
+  PINN_HD int size() const { return bo() + 4; }
+};
+
+template <int H_, int NF_, int NS_, int ACT_>
+struct NarrowWarp {
+  static constexpr int H = H_, NF = NF_, NS = NS_, ACT = ACT_;
+  static constexpr int C = 1 + NF + NS;
+  static constexpr int H4 = H / 4;
+  static_assert(H % 4 == 0, "hidden width must be a multiple of 4");
+  static_assert(NS <= NF, "second-order channels need their first-order channel");
+
+  // ---- per-warp shared memory carve-up (in floats) -----------------------
+  PINN_HD static int S() { return row_stride(C * H); }
+  PINN_HD static int YS() { return row_stride(C * 4); }
+  PINN_HD static int nbuf(int L) { return L <= 2 ? L + 1 : L; }
+  PINN_HD static int hb_index(int L) { return L - 1; }
+  PINN_HD static int x_index(int L) { return L >= 3 ? 1 : L; }
+  PINN_HD static int off_ybar(int L) { return nbuf(L) * 32 * S(); }
+  PINN_HD static int off_xs(int L) { return off_ybar(L) + 32 * YS(); }
+  PINN_HD static int off_gacc(int L) { return off_xs(L) + 32 * 4; }
+  PINN_HD static int warp_floats(int L) { return off_gacc(L) + Layout(H, L).size(); }
+
+  struct Lane {      // lane-private state that survives across tiles
+    float loss;
+  };
+
+  // ---- small pieces -------------------------------------------------------
+  PINN_HD static void unit_fwd(const float (&z)[C], float (&h)[C]) {
+    float s0, s1, s2, s3;
+    act_derivs<ACT>(z[0], s0, s1, s2, s3);
+    h[0] = s0;
+#pragma unroll
+    for (int i = 0; i < NF; ++i) h[1 + i] = s1 * z[1 + i];
+#pragma unroll
+    for (int s = 0; s < NS; ++s) h[1 + NF + s] = s2 * z[1 + s] * z[1 + s] + s1 * z[1 + NF + s];
+  }
+
+  PINN_HD static void unit_bwd(const float (&z)[C], const float (&hb)[C], float (&h)[C], float (&zb)[C]) {
+    float s0, s1, s2, s3;
+    act_derivs<ACT>(z[0], s0, s1, s2, s3);
+    h[0] = s0;
+    float zv = hb[0] * s1;
+#pragma unroll
+    for (int i = 0; i < NF; ++i) {
+      h[1 + i] = s1 * z[1 + i];
+      zv += hb[1 + i] * s2 * z[1 + i];
+      zb[1 + i] = hb[1 + i] * s1;
+    }
+#pragma unroll
+    for (int s = 0; s < NS; ++s) {
+      const float zi = z[1 + s], zii = z[1 + NF + s], hbs = hb[1 + NF + s];
+      h[1 + NF + s] = s2 * zi * zi + s1 * zii;
+      zv += hbs * (s3 * zi * zi + s2 * zii);
+      zb[1 + s] += 2.0f * hbs * s2 * zi;
+      zb[1 + NF + s] = hbs * s1;
+    }
+    zb[0] = zv;
+  }
+
+  // pre-activation jet of hidden layer 1 for units k4*4..k4*4+3 (never stashed:
+  // z_val = b1 + W1 x, z_i = W1[:, first_in[i]], z_ii = 0)
+  PINN_HD static void layer1_tile(const float* sw, const Layout& lay, const NarrowParams& p, const float (&x)[4],
+                                  int k4, f4 (&zt)[C]) {
+    f4 w[4];
+#pragma unroll
+    for (int d = 0; d < 4; ++d) w[d] = ld4(sw + lay.w1() + d * H + k4 * 4);
+    f4 b = ld4(sw + lay.b1() + k4 * 4);
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      float v = f4_at(b, e);
+#pragma unroll
+      for (int d = 0; d < 4; ++d) v += f4_at(w[d], e) * x[d];
+      f4_at(zt[0], e) = v;
+    }
+#pragma unroll
+    for (int i = 0; i < NF; ++i) {
+      const int d = p.jets.first_in[i];
+      // select without dynamic register indexing
+      f4 r = w[0];
+      if (d == 1) r = w[1];
+      if (d == 2) r = w[2];
+      if (d == 3) r = w[3];
+      zt[1 + i] = r;
+    }
+#pragma unroll
+    for (int s = 0; s < NS; ++s) zt[1 + NF + s] = f4{0.f, 0.f, 0.f, 0.f};
+  }
+
+  PINN_HD static void load_ztile(const float* row, int k4, f4 (&zt)[C]) {
+#pragma unroll
+    for (int c = 0; c < C; ++c) zt[c] = ld4(row + c * H + k4 * 4);
+  }
+  PINN_HD static void store_tile(float* row, int k4, const f4 (&t)[C]) {
+#pragma unroll
+    for (int c = 0; c < C; ++c) st4(row + c * H + k4 * 4, t[c]);
+  }
+
+  // hin[c][k] <- activation jet of the z tile
+  PINN_HD static void act_tile_fwd(const f4 (&zt)[C], int k4, float (&hin)[C][H]) {
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      float z[C], h[C];
+#pragma unroll
+      for (int c = 0; c < C; ++c) z[c] = (&zt[c].x)[e];
+      unit_fwd(z, h);
+#pragma unroll
+      for (int c = 0; c < C; ++c) hin[c][k4 * 4 + e] = h[c];
+    }
+  }
+
+  // given z tile and hbar (adjoint of the layer output) -> h tile, zbar tile
+  PINN_HD static void act_tile_bwd(const f4 (&zt)[C], int k4, const float (&hbar)[C][H], f4 (&ht)[C], f4 (&zbt)[C]) {
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      float z[C], hb[C], h[C], zb[C];
+#pragma unroll
+      for (int c = 0; c < C; ++c) {
+        z[c] = (&zt[c].x)[e];
+        hb[c] = hbar[c][k4 * 4 + e];
+        zb[c] = 0.f;
+      }
+      unit_bwd(z, hb, h, zb);
+#pragma unroll
+      for (int c = 0; c < C; ++c) {
+        (&ht[c].x)[e] = h[c];
+        (&zbt[c].x)[e] = zb[c];
+      }
+    }
+  }
+
+  // ---- residual, loss and its seed adjoint (FUSED mode) -------------------
+  // y[c][o] are the output jets of this lane's point; returns ybar[c][o] =
+  // d(sigma * loss)/dy and adds the point's un-weighted loss to lane.loss.
+  PINN_HD static void residual_loss(const NarrowParams& p, int64_t n, bool valid, const float (&x)[4],
+                                    const f4 (&y)[C], f4 (&yb)[C], Lane& lane) {
+    const pinn_domain& dm = p.dom;
+    float sym[PINN_SYM_COUNT];
+    float sg[PINN_SYM_COORD0];
+#pragma unroll
+    for (int i = 0; i < PINN_SYM_COUNT; ++i) sym[i] = 0.f;
+#pragma unroll
+    for (int i = 0; i < PINN_SYM_COORD0; ++i) sg[i] = 0.f;
+#pragma unroll
+    for (int c = 0; c < C; ++c) {
+      sym[c * 4 + 0] = y[c].x; sym[c * 4 + 1] = y[c].y; sym[c * 4 + 2] = y[c].z; sym[c * 4 + 3] = y[c].w;
+    }
+#pragma unroll
+    for (int d = 0; d < 4; ++d) sym[PINN_SYM_COORD0 + d] = x[d];
+    for (int a = 0; a < dm.n_aux; ++a) sym[PINN_SYM_AUX0 + a] = valid ? dm.aux[a][n] : 0.f;
+    const float area = valid ? (dm.area ? dm.area[n] : dm.area_const) : 0.f;
+    float loss = 0.f;
+    for (int e = 0; e < dm.n_eq; ++e) {
+      const pinn_equation& q = dm.eq[e];
+      float r = 0.f;
+      for (int t = q.term_begin; t < q.term_end; ++t) {
+        const pinn_term& tm = dm.terms[t];
+        float prod = tm.coef;
+        for (int f = 0; f < tm.n_fac; ++f) prod *= sym[tm.fac[f]];
+        r += prod;
+      }
+      const float tgt = q.target ? (valid ? q.target[n] : 0.f) : q.target_const;
+      const float lam = q.lambda ? (valid ? q.lambda[n] : 0.f) : q.lambda_const;
+      const float diff = r - tgt;
+      const float w = lam * area;
+      float f0, f1;
+      if (dm.loss_kind == PINN_LOSS_SQUARE) {
+        f0 = diff * diff; f1 = 2.0f * diff;
+      } else if (dm.loss_kind == PINN_LOSS_L1) {
+        f0 = fabsf(diff); f1 = (diff > 0.f) ? 1.0f : ((diff < 0.f) ? -1.0f : 0.f);
+      } else {
+        f0 = diff; f1 = 1.0f;
+      }
+      loss += f0 * w;
+      const float g = f1 * w * dm.sigma;
+      for (int t = q.term_begin; t < q.term_end; ++t) {
+        const pinn_term& tm = dm.terms[t];
+        for (int f = 0; f < tm.n_fac; ++f) {
+          const int id = tm.fac[f];
+          if (id >= PINN_SYM_COORD0) continue;  // only net outputs carry gradient
+          float prod = tm.coef * g;
+          for (int f2 = 0; f2 < tm.n_fac; ++f2)
+            if (f2 != f) prod *= sym[tm.fac[f2]];
+          sg[id] += prod;
+        }
+      }
+    }
+    lane.loss += loss;
+#pragma unroll
+    for (int c = 0; c < C; ++c) yb[c] = f4{sg[c * 4 + 0], sg[c * 4 + 1], sg[c * 4 + 2], sg[c * 4 + 3]};
+  }
+
+  // ---- phase P0: forward, residual/loss, output-layer backward ------------
+  // sw: CTA weights, wm: this warp's smem region.  Returns nothing; all state
+  // for later phases is in smem.
+  PINN_HD static void phase_forward(const NarrowParams& p, const float* sw, float* wm, int lane_id, int64_t tile,
+                                    Lane& lane) {
+    const int L = p.n_hidden;
+    const Layout lay(H, L);
+    const int s = S();
+    const int64_t n = tile * 32 + lane_id;
+    const bool valid = n < p.n_points;
+    float x[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int d = 0; d < 4; ++d)
+      if (d < p.n_in && valid) x[d] = p.coords[d][n];
+    st4(wm + off_xs(L) + lane_id * 4, f4{x[0], x[1], x[2], x[3]});
+
+    float hin[C][H];
+    // hidden layer 1
+#pragma unroll
+    for (int k4 = 0; k4 < H4; ++k4) {
+      f4 zt[C];
+      layer1_tile(sw, lay, p, x, k4, zt);
+      act_tile_fwd(zt, k4, hin);
+    }
+    // hidden layers 2..L
+    for (int l = 2; l <= L; ++l) {
+      const float* Wt = sw + lay.wh(l);
+      const float* bl = sw + lay.bh(l);
+      float* row = wm + (l - 2) * 32 * s + lane_id * s;
+#if defined(__CUDA_ARCH__)
+#pragma unroll 1
+#endif
+      for (int j4 = 0; j4 < H4; ++j4) {
+        f4 acc[C];
+        acc[0] = ld4(bl + j4 * 4);
+#pragma unroll
+        for (int c = 1; c < C; ++c) acc[c] = f4{0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+        for (int k = 0; k < H; ++k) {
+          const f4 w = ld4(Wt + k * H + j4 * 4);
+#pragma unroll
+          for (int c = 0; c < C; ++c) {
+            const float hv = hin[c][k];
+            acc[c].x += w.x * hv; acc[c].y += w.y * hv; acc[c].z += w.z * hv; acc[c].w += w.w * hv;
+          }
+        }
+        store_tile(row, j4, acc);
+      }
+#pragma unroll
+      for (int k4 = 0; k4 < H4; ++k4) {
+        f4 zt[C];
+        load_ztile(row, k4, zt);
+        act_tile_fwd(zt, k4, hin);
+      }
+    }
+    // output layer: y[c][o] = sum_k Woutt[k][o] * h[c][k] (+ bout)
+    f4 y[C];
+    y[0] = ld4(sw + lay.bo());
+#pragma unroll
+    for (int c = 1; c < C; ++c) y[c] = f4{0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int k = 0; k < H; ++k) {
+      const f4 w = ld4(sw + lay.wo() + k * 4);
+#pragma unroll
+      for (int c = 0; c < C; ++c) {
+        const float hv = hin[c][k];
+        y[c].x += w.x * hv; y[c].y += w.y * hv; y[c].z += w.z * hv; y[c].w += w.w * hv;
+      }
+    }
+
+    if (p.mode == MODE_FWD) {
+      if (valid) {
+#pragma unroll
+        for (int c = 0; c < C; ++c)
+#pragma unroll
+          for (int o = 0; o < 4; ++o)
+            if (o < p.n_out) p.jets_out[(int64_t)(c * p.n_out + o) * p.n_points + n] = (&y[c].x)[o];
+      }
+      return;
+    }
+
+    f4 yb[C];
+    if (p.mode == MODE_FUSED) {
+      residual_loss(p, n, valid, x, y, yb, lane);
+    } else {
+#pragma unroll
+      for (int c = 0; c < C; ++c) {
+        yb[c] = f4{0.f, 0.f, 0.f, 0.f};
+        if (valid) {
+#pragma unroll
+          for (int o = 0; o < 4; ++o)
+            if (o < p.n_out) (&yb[c].x)[o] = p.jets_bar[(int64_t)(c * p.n_out + o) * p.n_points + n];
+        }
+      }
+    }
+    {
+      float* yrow = wm + off_ybar(L) + lane_id * YS();
+#pragma unroll
+      for (int c = 0; c < C; ++c) st4(yrow + c * 4, yb[c]);
+    }
+    // adjoint of h_L, then through the last activation
+    float (&hbar)[C][H] = hin;  // forward jet is dead: reuse its registers
+#pragma unroll
+    for (int k = 0; k < H; ++k) {
+      const f4 w = ld4(sw + lay.wo() + k * 4);
+#pragma unroll
+      for (int c = 0; c < C; ++c) hbar[c][k] = w.x * yb[c].x + w.y * yb[c].y + w.z * yb[c].z + w.w * yb[c].w;
+    }
+    act_backward_all(p, sw, wm, lane_id, L, hbar);
+  }
+
+  // hbar = adjoint of h_l (all units).  Reads z_l (stash, or recomputed for
+  // l == 1), writes h_l to the HB buffer and zbar_l over z_l (or to the X
+  // buffer for l == 1).
+  PINN_HD static void act_backward_all(const NarrowParams& p, const float* sw, float* wm, int lane_id, int l,
+                                       const float (&hbar)[C][H]) {
+    const int L = p.n_hidden;
+    const Layout lay(H, L);
+    const int s = S();
+    float* hb_row = wm + hb_index(L) * 32 * s + lane_id * s;
+    float* z_row = (l >= 2) ? wm + (l - 2) * 32 * s + lane_id * s : wm + x_index(L) * 32 * s + lane_id * s;
+    float x[4];
+    {
+      const f4 xv = ld4(wm + off_xs(L) + lane_id * 4);
+      x[0] = xv.x; x[1] = xv.y; x[2] = xv.z; x[3] = xv.w;
+    }
+#pragma unroll
+    for (int k4 = 0; k4 < H4; ++k4) {
+      f4 zt[C], ht[C], zbt[C];
+      if (l >= 2) load_ztile(z_row, k4, zt);
+      else layer1_tile(sw, lay, p, x, k4, zt);
+      act_tile_bwd(zt, k4, hbar, ht, zbt);
+      store_tile(hb_row, k4, ht);
+      store_tile(z_row, k4, zbt);
+    }
+  }
+
+  // ---- phase P_l (l = L..2): hbar_{l-1} = W_l^T zbar_l, then activation l-1 --
+  PINN_HD static void phase_backward_layer(const NarrowParams& p, const float* sw, float* wm, int lane_id, int l) {
+    const int L = p.n_hidden;
+    const Layout lay(H, L);
+    const int s = S();
+    const float* Wt = sw + lay.wh(l);
+    const float* zb_row = wm + (l - 2) * 32 * s + lane_id * s;
+    float hbar[C][H];
+#pragma unroll
+    for (int c = 0; c < C; ++c)
+#pragma unroll
+      for (int k = 0; k < H; ++k) hbar[c][k] = 0.f;
+#if defined(__CUDA_ARCH__)
+#pragma unroll 1
+#endif
+    for (int j4 = 0; j4 < H4; ++j4) {
+      f4 zb[C];
+      load_ztile(zb_row, j4, zb);
+#pragma unroll
+      for (int k = 0; k < H; ++k) {
+        const f4 w = ld4(Wt + k * H + j4 * 4);
+#pragma unroll
+        for (int c = 0; c < C; ++c)
+          hbar[c][k] += w.x * zb[c].x + w.y * zb[c].y + w.z * zb[c].z + w.w * zb[c].w;
+      }
+    }
+    act_backward_all(p, sw, wm, lane_id, l - 1, hbar);
+  }
+
+  // ---- GEMM phases (cross-lane; run after __syncwarp) ----------------------
+  // dWout[o][k] += sum_{n,c} ybar[n][c][o] * h_L[n][c][k];  dbout[o] += sum_n ybar[n][0][o]
+  PINN_HD static void phase_gemm_out(const NarrowParams& p, float* wm, int lane_id) {
+    const int L = p.n_hidden;
+    const Layout lay(H, L);
+    const int s = S(), ys = YS();
+    const float* hb = wm + hb_index(L) * 32 * s;
+    const float* yb = wm + off_ybar(L);
+    float* g = wm + off_gacc(L);
+    const int T = p.n_out * H4;
+    for (int t = lane_id; t < T; t += 32) {
+      const int o = t / H4, kb = t % H4;
+      f4 acc = f4{0.f, 0.f, 0.f, 0.f};
+      for (int n = 0; n < 32; ++n) {
+#pragma unroll
+        for (int c = 0; c < C; ++c) {
+          const float a = yb[n * ys + c * 4 + o];
+          const f4 b = ld4(hb + n * s + c * H + kb * 4);
+          acc.x += a * b.x; acc.y += a * b.y; acc.z += a * b.z; acc.w += a * b.w;
+        }
+      }
+      float* gw = g + lay.wo() + (kb * 4) * 4 + o;
+      gw[0] += acc.x; gw[4] += acc.y; gw[8] += acc.z; gw[12] += acc.w;
+    }
+    if (lane_id < p.n_out) {
+      float a = 0.f;
+      for (int n = 0; n < 32; ++n) a += yb[n * ys + lane_id];
+      g[lay.bo() + lane_id] += a;
+    }
+  }
+
+  // dW_l[j][k] += sum_{n,c} zbar_l[n][c][j] * h_{l-1}[n][c][k];  db_l[j] += sum_n zbar_l[n][0][j]
+  PINN_HD static void phase_gemm_hidden(const NarrowParams& p, float* wm, int lane_id, int l) {
+    const int L = p.n_hidden;
+    const Layout lay(H, L);
+    const int s = S();
+    const float* A = wm + (l - 2) * 32 * s;       // zbar_l
+    const float* B = wm + hb_index(L) * 32 * s;   // h_{l-1}
+    float* g = wm + off_gacc(L);
+    for (int t = lane_id; t < H4 * H4; t += 32) {
+      const int ja = t / H4, kb = t % H4;
+      f4 acc[4];  // acc[kk] = (j0..j3) for k = kb*4+kk
+#pragma unroll
+      for (int kk = 0; kk < 4; ++kk) acc[kk] = f4{0.f, 0.f, 0.f, 0.f};
+#if defined(__CUDA_ARCH__)
+#pragma unroll 2
+#endif
+      for (int n = 0; n < 32; ++n) {
+#pragma unroll
+        for (int c = 0; c < C; ++c) {
+          const f4 a = ld4(A + n * s + c * H + ja * 4);
+          const f4 b = ld4(B + n * s + c * H + kb * 4);
+#pragma unroll
+          for (int kk = 0; kk < 4; ++kk) {
+            const float bv = (&b.x)[kk];
+            acc[kk].x += a.x * bv; acc[kk].y += a.y * bv; acc[kk].z += a.z * bv; acc[kk].w += a.w * bv;
+          }
+        }
+      }
+#pragma unroll
+      for (int kk = 0; kk < 4; ++kk) {
+        float* gp = g + lay.wh(l) + (kb * 4 + kk) * H + ja * 4;
+        f4 v = ld4(gp);
+        v.x += acc[kk].x; v.y += acc[kk].y; v.z += acc[kk].z; v.w += acc[kk].w;
+        st4(gp, v);
+      }
+    }
+    for (int t = lane_id; t < H4; t += 32) {
+      f4 a = f4{0.f, 0.f, 0.f, 0.f};
+      for (int n = 0; n < 32; ++n) {
+        const f4 v = ld4(A + n * s + t * 4);
+        a.x += v.x; a.y += v.y; a.z += v.z; a.w += v.w;
+      }
+      float* gp = g + lay.bh(l) + t * 4;
+      f4 v = ld4(gp);
+      v.x += a.x; v.y += a.y; v.z += a.z; v.w += a.w;
+      st4(gp, v);
+    }
+  }
+
+  // dW1[j][d] += sum_n zbar_val[n][j] x_d[n] + [d == first_in[i]] sum_n zbar_i[n][j];  db1[j] += sum_n zbar_val[n][j]
+  PINN_HD static void phase_gemm_first(const NarrowParams& p, float* wm, int lane_id) {
+    const int L = p.n_hidden;
+    const Layout lay(H, L);
+    const int s = S();
+    const float* X = wm + x_index(L) * 32 * s;  // zbar_1
+    const float* xs = wm + off_xs(L);
+    float* g = wm + off_gacc(L);
+    for (int j = lane_id; j < H; j += 32) {
+      float ad[4] = {0.f, 0.f, 0.f, 0.f};
+      float af[NF > 0 ? NF : 1];
+#pragma unroll
+      for (int i = 0; i < NF; ++i) af[i] = 0.f;
+      float ab = 0.f;
+      for (int n = 0; n < 32; ++n) {
+        const float zv = X[n * s + j];
+        const f4 xv = ld4(xs + n * 4);
+        ad[0] += zv * xv.x; ad[1] += zv * xv.y; ad[2] += zv * xv.z; ad[3] += zv * xv.w;
+        ab += zv;
+#pragma unroll
+        for (int i = 0; i < NF; ++i) af[i] += X[n * s + (1 + i) * H + j];
+      }
+#pragma unroll
+      for (int d = 0; d < 4; ++d) g[lay.w1() + d * H + j] += ad[d];
+#pragma unroll
+      for (int i = 0; i < NF; ++i) g[lay.w1() + p.jets.first_in[i] * H + j] += af[i];
+      g[lay.b1() + j] += ab;
+    }
+  }
+};
+
+// Weight staging: global (row-major [out,in]) -> smem padded/transposed Layout.
+// idx is an index into the Layout; returns the value to store there.
+PINN_HD float stage_weight(const NarrowParams& p, int Hreal, const Layout& lay, int idx) {
+  const int H = lay.H, L = lay.L;
+  if (idx < lay.b1()) {  // W1t[d][j]
+    const int d = idx / H, j = idx % H;
+    return (d < p.n_in && j < Hreal) ? p.W[0][j * p.n_in + d] : 0.f;
+  }
+  if (idx < lay.wh(2)) {  // b1
+    const int j = idx - lay.b1();
+    return j < Hreal ? p.b[0][j] : 0.f;
+  }
+  if (idx < lay.wo()) {
+    const int r = idx - lay.wh(2);
+    const int l = 2 + r / (H * H + H);
+    const int q = r % (H * H + H);
+    if (q < H * H) {  // Wt_l[k][j] = W_l[j][k]
+      const int k = q / H, j = q % H;
+      return (k < Hreal && j < Hreal) ? p.W[l - 1][j * Hreal + k] : 0.f;
+    }
+    const int j = q - H * H;
+    return j < Hreal ? p.b[l - 1][j] : 0.f;
+  }
+  if (idx < lay.bo()) {  // Woutt[k][o]
+    const int q = idx - lay.wo();
+    const int k = q / 4, o = q % 4;
+    return (k < Hreal && o < p.n_out) ? p.W[L][o * Hreal + k] : 0.f;
+  }
+  const int o = idx - lay.bo();
+  return o < p.n_out ? p.b[L][o] : 0.f;
+}
+
+// Inverse map for the gradient: flat torch index (layer order, W row-major
+// [out,in] then b) -> index into the padded Layout.
+PINN_HD int flat_to_layout(int n_in, int n_out, int Hreal, const Layout& lay, int64_t flat) {
+  const int H = lay.H, L = lay.L;
+  int64_t r = flat;
+  // layer 0
+  if (r < (int64_t)Hreal * n_in) {
+    const int j = (int)(r / n_in), d = (int)(r % n_in);
+    return lay.w1() + d * H + j;
+  }
+  r -= (int64_t)Hreal * n_in;
+  if (r < Hreal) return lay.b1() + (int)r;
+  r -= Hreal;
+  for (int l = 2; l <= L; ++l) {
+    if (r < (int64_t)Hreal * Hreal) {
+      const int j = (int)(r / Hreal), k = (int)(r % Hreal);
+      return lay.wh(l) + k * H + j;
+    }
+    r -= (int64_t)Hreal * Hreal;
+    if (r < Hreal) return lay.bh(l) + (int)r;
+    r -= Hreal;
+  }
+  if (r < (int64_t)n_out * Hreal) {
+    const int o = (int)(r / Hreal), k = (int)(r % Hreal);
+    return lay.wo() + k * 4 + o;
+  }
+  r -= (int64_t)n_out * Hreal;
+  return lay.bo() + (int)r;
+}
+
+}  // namespace pinn

@@ -1,0 +1,131 @@
+// Parameter-sized helpers and the on-device sampler (see include/pinn_b200.h).
+#include <cuda_runtime.h>
+#include <stdio.h>
+
+#include "pinn_common.h"
+#include "philox.h"
+
+namespace pinn {
+void count_launch(int n);
+
+// one warp per output row: W[j,:] = g[j] * v[j,:] / ||v[j,:]||
+__global__ void weight_norm_fwd_kernel(const float* __restrict__ g, const float* __restrict__ v, float* __restrict__ W,
+                                       int out_dim, int in_dim) {
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= out_dim) return;
+  const float* vr = v + (size_t)row * in_dim;
+  float ss = 0.f;
+  for (int k = lane; k < in_dim; k += 32) ss += vr[k] * vr[k];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+  const float scale = g[row] / sqrtf(ss);
+  for (int k = lane; k < in_dim; k += 32) W[(size_t)row * in_dim + k] = vr[k] * scale;
+}
+
+// dg[j] = <dW_j, v_j>/||v_j|| ; dv[j,:] = g_j/||v_j|| * (dW_j - <dW_j, v_j>/||v_j||^2 * v_j)
+__global__ void weight_norm_bwd_kernel(const float* __restrict__ g, const float* __restrict__ v,
+                                       const float* __restrict__ dW, float* __restrict__ dg, float* __restrict__ dv,
+                                       int out_dim, int in_dim) {
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= out_dim) return;
+  const float* vr = v + (size_t)row * in_dim;
+  const float* dr = dW + (size_t)row * in_dim;
+  float ss = 0.f, dot = 0.f;
+  for (int k = lane; k < in_dim; k += 32) {
+    ss += vr[k] * vr[k];
+    dot += dr[k] * vr[k];
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    ss += __shfl_xor_sync(0xffffffffu, ss, o);
+    dot += __shfl_xor_sync(0xffffffffu, dot, o);
+  }
+  const float inv = rsqrtf(ss);
+  if (lane == 0) dg[row] = dot * inv;
+  const float a = g[row] * inv, b = dot / ss;
+  for (int k = lane; k < in_dim; k += 32) dv[(size_t)row * in_dim + k] = a * (dr[k] - b * vr[k]);
+}
+
+struct SampleArgs {
+  float* col[PINN_MAX_IN];
+  float lo[PINN_MAX_IN], hi[PINN_MAX_IN];
+  float* sdf;
+  int n_dims, sdf_dims;
+  int64_t n;
+  uint64_t seed, stream_id, offset;
+};
+
+__global__ void sample_box_kernel(const SampleArgs a) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < a.n; i += (int64_t)gridDim.x * blockDim.x) {
+    uint32_t r[4];
+    philox4x32_10(a.seed, a.stream_id, a.offset + (uint64_t)i, r);
+    float xs[PINN_MAX_IN];
+#pragma unroll
+    for (int d = 0; d < PINN_MAX_IN; ++d) {
+      if (d < a.n_dims) {
+        xs[d] = box_point(r[d], a.lo[d], a.hi[d]);
+        a.col[d][i] = xs[d];
+      }
+    }
+    if (a.sdf) a.sdf[i] = box_sdf(xs, a.lo, a.hi, a.sdf_dims);
+  }
+}
+
+}  // namespace pinn
+
+using namespace pinn;
+
+extern "C" {
+
+int pinn_weight_norm_forward(const float* g, const float* v, float* W, int32_t out_dim, int32_t in_dim, void* stream) {
+  if (!g || !v || !W || out_dim < 1 || in_dim < 1) return PINN_E_INVALID;
+  const int wpb = 4;
+  weight_norm_fwd_kernel<<<(out_dim + wpb - 1) / wpb, wpb * 32, 0, (cudaStream_t)stream>>>(g, v, W, out_dim, in_dim);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return (int)e;
+  count_launch(1);
+  return 0;
+}
+
+int pinn_weight_norm_backward(const float* g, const float* v, const float* dW, float* dg, float* dv, int32_t out_dim,
+                              int32_t in_dim, void* stream) {
+  if (!g || !v || !dW || !dg || !dv || out_dim < 1 || in_dim < 1) return PINN_E_INVALID;
+  const int wpb = 4;
+  weight_norm_bwd_kernel<<<(out_dim + wpb - 1) / wpb, wpb * 32, 0, (cudaStream_t)stream>>>(g, v, dW, dg, dv, out_dim, in_dim);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return (int)e;
+  count_launch(1);
+  return 0;
+}
+
+int pinn_sample_box(float* const* columns, int32_t n_dims, const float* lo, const float* hi, int64_t n_points,
+                    uint64_t seed, uint64_t stream_id, uint64_t offset, float* sdf, int32_t sdf_dims, void* stream) {
+  if (!columns || !lo || !hi || n_dims < 1 || n_dims > PINN_MAX_IN || n_points < 0 || sdf_dims < 0 || sdf_dims > n_dims)
+    return PINN_E_INVALID;
+  if (n_points == 0) return 0;
+  SampleArgs a;
+  for (int d = 0; d < PINN_MAX_IN; ++d) {
+    a.col[d] = d < n_dims ? columns[d] : nullptr;
+    a.lo[d] = d < n_dims ? lo[d] : 0.f;
+    a.hi[d] = d < n_dims ? hi[d] : 0.f;
+    if (d < n_dims && !columns[d]) return PINN_E_INVALID;
+  }
+  a.sdf = sdf;
+  a.n_dims = n_dims;
+  a.sdf_dims = sdf_dims;
+  a.n = n_points;
+  a.seed = seed;
+  a.stream_id = stream_id;
+  a.offset = offset;
+  int64_t blocks = (n_points + 255) / 256;
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  sample_box_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(a);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return (int)e;
+  count_launch(1);
+  return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,196 @@
+/*
+ * pinn_b200.h -- C ABI of libpinn_b200.so: the B200 (sm_100a) implementation of the
+ * IDRLnet PINN training step.
+ *
+ * The reference (idrl-lab/idrlnet v2.0.0) is pure Python and has no FFI; the seam
+ * this library plugs into is its node protocol (idrlnet/node.py:11-66,
+ * idrlnet/graph.py:95-121,170-180).  Each entry point below names the reference
+ * code whose work it replaces.  All pointers are DEVICE pointers to FP32 unless
+ * stated otherwise; every buffer is owned by the caller (PyTorch tensors in the
+ * Python host layer); the library allocates nothing persistent, never
+ * synchronises the host, and is stream-ordered on the `stream` argument
+ * (a cudaStream_t passed as void*).
+ *
+ * Return value of every function: 0 = ok, <0 = PINN_E_* (invalid / unsupported
+ * configuration -- the caller raises or takes the generic torch path),
+ * >0 = a cudaError_t.  Nothing throws across the ABI, nothing calls exit().
+ */
+#ifndef PINN_B200_H
+#define PINN_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PINN_ABI_VERSION 1
+
+#if defined(__GNUC__)
+#define PINN_API __attribute__((visibility("default")))
+#else
+#define PINN_API
+#endif
+
+#define PINN_MAX_LAYERS 16 /* linear layers: hidden + output */
+#define PINN_MAX_IN 4      /* network inputs (x, y, z, t / parameters) */
+#define PINN_MAX_OUT 4     /* network outputs */
+#define PINN_MAX_FIRST 4   /* first-order jet channels */
+#define PINN_MAX_AUX 8     /* extra per-point symbols (normal_x, sdf, ...) */
+#define PINN_MAX_EQ 8      /* equations (loss terms) per sampling domain */
+#define PINN_MAX_TERMS 64  /* monomials over all equations of a domain */
+#define PINN_MAX_FACTORS 7 /* factors per monomial */
+
+/* symbol ids used by the residual monomials */
+#define PINN_SYM_JET(c, o) ((c) * PINN_MAX_OUT + (o)) /* channel c of output o  */
+#define PINN_SYM_COORD0 28                            /* + input index          */
+#define PINN_SYM_AUX0 32                              /* + aux index            */
+#define PINN_SYM_COUNT 40
+
+enum { PINN_ACT_TANH = 0, PINN_ACT_SILU = 1, PINN_ACT_SIN = 2 };
+enum { PINN_LOSS_SQUARE = 0, PINN_LOSS_L1 = 1, PINN_LOSS_IDENTITY = 2 };
+enum {
+  PINN_E_INVALID = -1,     /* malformed descriptor                        */
+  PINN_E_UNSUPPORTED = -2, /* valid but no kernel for it (width, channels) */
+  PINN_E_WORKSPACE = -3,   /* workspace too small                          */
+  PINN_E_NO_DEVICE = -4    /* no sm_100 device / kernel image not loadable */
+};
+
+/* The MLP of a NetNode: idrlnet/architecture/mlp.py:18-76 (Linear + activation
+ * stack, last layer linear), evaluated as idrlnet/net.py:14-36 does (inputs
+ * concatenated in NetNode.inputs order).  W[l] is the EFFECTIVE weight of linear
+ * layer l, row-major [out, in] as torch.nn.Linear stores it (for weight-norm
+ * layers, idrlnet/architecture/layer.py:42-43, the caller passes g*v/||v||). */
+typedef struct pinn_mlp {
+  int32_t n_in;     /* d                                                   */
+  int32_t n_out;    /* o                                                   */
+  int32_t n_hidden; /* L >= 1 hidden layers, all `width` wide              */
+  int32_t width;    /* H                                                   */
+  int32_t act;      /* PINN_ACT_*                                          */
+  int32_t _pad;
+  const float* W[PINN_MAX_LAYERS]; /* L+1 pointers                         */
+  const float* b[PINN_MAX_LAYERS];
+} pinn_mlp;
+
+/* Which input-derivative "jet" channels to propagate.  Replaces the nested
+ * torch.autograd.grad calls of idrlnet/variable.py:161-208: channel 0 is the
+ * value, channel 1+i is d/d(input first_in[i]), channel 1+n_first+s is
+ * d2/d(input first_in[s])^2  (s < n_second <= n_first). */
+typedef struct pinn_jets {
+  int32_t n_first;
+  int32_t n_second;
+  int32_t first_in[PINN_MAX_FIRST];
+} pinn_jets;
+
+/* A residual is a polynomial in the symbols (what idrlnet/pde.py:65-79 +
+ * idrlnet/torch_util.py:25-39 lambdify; every PDE of idrlnet/pde_op/equations.py
+ * is of this form): sum over terms of coef * prod(sym[fac[i]]). */
+typedef struct pinn_term {
+  float coef;
+  uint8_t n_fac;
+  uint8_t fac[PINN_MAX_FACTORS];
+} pinn_term;
+
+typedef struct pinn_equation {
+  int32_t term_begin, term_end; /* range in pinn_domain.terms               */
+  const float* target;          /* [N] or NULL -> target_const              */
+  const float* lambda;          /* [N] or NULL -> lambda_const              */
+  float target_const;
+  float lambda_const;           /* 1.0 when the domain has no lambda_<name> */
+} pinn_equation;
+
+/* One sampling domain (idrlnet/data.py:15-129) and its share of the loss
+ * (idrlnet/solver.py:353-408, idrlnet/variable.py:40-80):
+ *   loss_d = sum_eq sum_n f(r_eq[n] - target[n]) * lambda_eq[n] * area[n]
+ * and the step differentiates sigma * loss_d. */
+typedef struct pinn_domain {
+  int64_t n_points;
+  const float* coords[PINN_MAX_IN]; /* one [N] column per net input (SoA)   */
+  const float* aux[PINN_MAX_AUX];
+  const float* area; /* [N] or NULL -> area_const                           */
+  float area_const;
+  float sigma;
+  int32_t n_aux;
+  int32_t loss_kind; /* PINN_LOSS_*                                          */
+  int32_t n_eq;
+  int32_t n_terms;
+  pinn_equation eq[PINN_MAX_EQ];
+  pinn_term terms[PINN_MAX_TERMS];
+} pinn_domain;
+
+/* ---- queries ---------------------------------------------------------- */
+PINN_API int pinn_abi_version(void);
+/* Number of floats of the flat gradient: sum over layers of out*in + out,
+ * in layer order, W (row-major [out,in]) then b -- the order of
+ * torch.nn.Module.parameters() for a plain Linear stack. */
+PINN_API int64_t pinn_param_count(const pinn_mlp* mlp);
+/* Bytes of scratch the step functions need for this net (per-CTA gradient and
+ * loss partials).  `n_domains` = how many pinn_step_* calls are accumulated
+ * before pinn_step_finalize. */
+PINN_API int64_t pinn_workspace_bytes(const pinn_mlp* mlp, const pinn_jets* jets, int32_t n_domains);
+/* 1 if a fused kernel exists for (mlp, jets); 0 otherwise. */
+PINN_API int pinn_supported(const pinn_mlp* mlp, const pinn_jets* jets);
+/* Kernels launched by this library in this process (bench.py "gpu_launches"). */
+PINN_API int64_t pinn_launch_count(void);
+PINN_API const char* pinn_last_error(void);
+
+/* ---- the fused training step ------------------------------------------ */
+/* Forward jets + residual + weighted loss + reverse pass for ONE domain, no
+ * autograd graph materialised.  Replaces, for that domain,
+ * VertexTaskPipeline.forward_pipeline (idrlnet/graph.py:170-193: WrapEvaluate,
+ * Variables.differentiate_, PdeEvaluate), Solver.compute_loss
+ * (idrlnet/solver.py:353-408) and loss.backward() (idrlnet/solver.py:338).
+ * Results go to per-CTA partials inside `workspace`; `domain_slot` selects the
+ * loss slot, `accumulate` != 0 adds the gradient partials to those of earlier
+ * calls (several domains sharing the net).  Call pinn_step_finalize afterwards. */
+PINN_API int pinn_step_fused(const pinn_mlp* mlp, const pinn_jets* jets, const pinn_domain* dom,
+                    void* workspace, int64_t workspace_bytes, int32_t domain_slot,
+                    int32_t accumulate, void* stream);
+
+/* Deterministic reduction of the per-CTA partials:
+ *   flat_grad[pinn_param_count] (+)= d(sum_d sigma_d*loss_d)/d(W,b)   (add_to_grad != 0 adds)
+ *   losses[n_domains]            = loss_d (un-weighted by sigma, as
+ *                                  solver.loss_component holds it)      */
+PINN_API int pinn_step_finalize(const pinn_mlp* mlp, const pinn_jets* jets, void* workspace,
+                       int64_t workspace_bytes, int32_t n_domains, float* flat_grad,
+                       int32_t add_to_grad, float* losses, void* stream);
+
+/* ---- the generic path (residual evaluated by the caller) --------------- */
+/* Jets only: out[(c*n_out + o)*N + n] = channel c of output o at point n.
+ * Replaces WrapEvaluate + Variables.differentiate_ for names such as u__x__x
+ * when the residual is not a polynomial (idrlnet/graph.py:172-175), and serves
+ * Solver.infer_step (idrlnet/solver.py:410-420). */
+PINN_API int pinn_jet_forward(const pinn_mlp* mlp, const pinn_jets* jets, int64_t n_points,
+                     const float* const* coords, float* out, void* stream);
+
+/* Reverse pass for caller-supplied adjoints out_bar (same layout as `out`):
+ * gradient partials into workspace as pinn_step_fused does. */
+PINN_API int pinn_jet_backward(const pinn_mlp* mlp, const pinn_jets* jets, int64_t n_points,
+                      const float* const* coords, const float* out_bar, void* workspace,
+                      int64_t workspace_bytes, int32_t accumulate, void* stream);
+
+/* ---- parameter-sized helpers ------------------------------------------- */
+/* W[j,:] = g[j] * v[j,:] / ||v[j,:]||  (torch.nn.utils.weight_norm, dim=0;
+ * idrlnet/architecture/layer.py:42-43). */
+PINN_API int pinn_weight_norm_forward(const float* g, const float* v, float* W, int32_t out_dim,
+                             int32_t in_dim, void* stream);
+/* (dg, dv) from dW. */
+PINN_API int pinn_weight_norm_backward(const float* g, const float* v, const float* dW, float* dg,
+                              float* dv, int32_t out_dim, int32_t in_dim, void* stream);
+
+/* ---- on-device sampling ------------------------------------------------ */
+/* Uniform points in an axis-aligned box (idrlnet/geo_utils/geo.py:316-343
+ * `_ranged_sample`; the docs' "future versions will sample on GPU"), Philox4x32-10
+ * keyed by (seed, stream_id), counter = point index + offset: columns[d][n] in
+ * [lo[d], hi[d]).  Also writes the rectangle / interval signed distance
+ * (idrlnet/geo_utils/geo_obj.py:30-41,109-167) over the first `sdf_dims`
+ * columns into `sdf` when it is non-NULL. */
+PINN_API int pinn_sample_box(float* const* columns, int32_t n_dims, const float* lo, const float* hi,
+                    int64_t n_points, uint64_t seed, uint64_t stream_id, uint64_t offset,
+                    float* sdf, int32_t sdf_dims, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PINN_B200_H */

@@ -1,0 +1,143 @@
+// CPU emulation of the narrow warp programs (idrlnet_b200/csrc/narrow_warp.h).
+// TEST INFRASTRUCTURE ONLY: lets the CPU-only test tier execute the very same
+// per-lane phase functions the CUDA kernel runs (lane by lane, phase by phase)
+// and compare them with the oracle.  The product library never links this.
+#include <stdlib.h>
+#include <string.h>
+
+#include <vector>
+
+#include "../../idrlnet_b200/csrc/narrow_warp.h"
+
+using namespace pinn;
+
+namespace {
+
+struct Runner {
+  virtual ~Runner() {}
+  virtual int H() const = 0;
+  virtual int warp_floats(int L) const = 0;
+  virtual void run_cta(const NarrowParams& p, int Hreal, int cta, int n_cta, int n_warps, float* gpart_cta,
+                       float* lpart_cta) const = 0;
+};
+
+template <class NW>
+struct RunnerT : Runner {
+  int H() const override { return NW::H; }
+  int warp_floats(int L) const override { return NW::warp_floats(L); }
+  void run_cta(const NarrowParams& p, int Hreal, int cta, int n_cta, int n_warps, float* gpart_cta,
+               float* lpart_cta) const override {
+    const int L = p.n_hidden;
+    const Layout lay(NW::H, L);
+    const int wf = NW::warp_floats(L);
+    std::vector<float> smem(lay.size() + (size_t)n_warps * wf, 0.f);
+    for (int i = 0; i < lay.size(); ++i) smem[i] = stage_weight(p, Hreal, lay, i);
+    std::vector<typename NW::Lane> lanes((size_t)n_warps * 32);
+    for (auto& l : lanes) l.loss = 0.f;
+    for (int warp = 0; warp < n_warps; ++warp) {
+      float* wm = smem.data() + lay.size() + (size_t)warp * wf;
+      typename NW::Lane* ln = &lanes[(size_t)warp * 32];
+      for (int64_t tile = (int64_t)cta * n_warps + warp; tile < p.n_tiles; tile += (int64_t)n_cta * n_warps) {
+        for (int lane = 0; lane < 32; ++lane) NW::phase_forward(p, smem.data(), wm, lane, tile, ln[lane]);
+        if (p.mode == MODE_FWD) continue;
+        for (int lane = 0; lane < 32; ++lane) NW::phase_gemm_out(p, wm, lane);
+        for (int l = L; l >= 2; --l) {
+          for (int lane = 0; lane < 32; ++lane) NW::phase_backward_layer(p, smem.data(), wm, lane, l);
+          for (int lane = 0; lane < 32; ++lane) NW::phase_gemm_hidden(p, wm, lane, l);
+        }
+        for (int lane = 0; lane < 32; ++lane) NW::phase_gemm_first(p, wm, lane);
+      }
+    }
+    if (p.mode == MODE_FWD) return;
+    for (int i = 0; i < lay.size(); ++i) {
+      float s = 0.f;
+      for (int w = 0; w < n_warps; ++w) s += smem[lay.size() + (size_t)w * wf + NW::off_gacc(L) + i];
+      gpart_cta[i] += s;
+    }
+    if (p.mode == MODE_FUSED) {
+      float s = 0.f;
+      for (int w = 0; w < n_warps; ++w) {
+        float sw = 0.f;
+        for (int l2 = 0; l2 < 32; ++l2) sw += lanes[(size_t)w * 32 + l2].loss;
+        s += sw;
+      }
+      *lpart_cta += s;
+    }
+  }
+};
+
+#define ROW(H, A)                                                                                         \
+  {{new RunnerT<NarrowWarp<H, 0, 0, A>>, nullptr, nullptr, nullptr},                                      \
+   {new RunnerT<NarrowWarp<H, 1, 0, A>>, new RunnerT<NarrowWarp<H, 1, 1, A>>, nullptr, nullptr},          \
+   {new RunnerT<NarrowWarp<H, 2, 0, A>>, new RunnerT<NarrowWarp<H, 2, 1, A>>, new RunnerT<NarrowWarp<H, 2, 2, A>>, nullptr}, \
+   {new RunnerT<NarrowWarp<H, 3, 0, A>>, new RunnerT<NarrowWarp<H, 3, 1, A>>, new RunnerT<NarrowWarp<H, 3, 2, A>>, new RunnerT<NarrowWarp<H, 3, 3, A>>}}
+
+const Runner* lookup(int width, int act, int nf, int ns) {
+  static const Runner* t20[3][4][4] = {ROW(20, PINN_ACT_TANH), ROW(20, PINN_ACT_SILU), ROW(20, PINN_ACT_SIN)};
+  static const Runner* t32[3][4][4] = {ROW(32, PINN_ACT_TANH), ROW(32, PINN_ACT_SILU), ROW(32, PINN_ACT_SIN)};
+  if (act < 0 || act > 2 || nf < 0 || nf > 3 || ns < 0 || ns > nf) return nullptr;
+  if (width <= 20) return t20[act][nf][ns];
+  if (width <= 32) return t32[act][nf][ns];
+  return nullptr;
+}
+
+int64_t param_count(const pinn_mlp* m) {
+  int64_t n = (int64_t)m->width * m->n_in + m->width;
+  n += (int64_t)(m->n_hidden - 1) * ((int64_t)m->width * m->width + m->width);
+  n += (int64_t)m->n_out * m->width + m->n_out;
+  return n;
+}
+
+void fill(NarrowParams& p, const pinn_mlp* m, const pinn_jets* j) {
+  memset(&p, 0, sizeof(p));
+  p.n_in = m->n_in; p.n_out = m->n_out; p.n_hidden = m->n_hidden;
+  for (int l = 0; l <= m->n_hidden; ++l) { p.W[l] = m->W[l]; p.b[l] = m->b[l]; }
+  p.jets = *j;
+}
+
+}  // namespace
+
+extern "C" {
+
+// mode 0: fused (dom, flat_grad += , loss_out +=); mode 1: jets_out; mode 2: jets_bar -> flat_grad +=
+__attribute__((visibility("default"))) int pinn_emu_run(const pinn_mlp* m, const pinn_jets* j, int mode,
+                                                        const pinn_domain* dom, int64_t n_points,
+                                                        const float* const* coords, float* jets_out,
+                                                        const float* jets_bar, float* flat_grad, float* loss_out,
+                                                        int n_cta, int n_warps) {
+  const Runner* r = lookup(m->width, m->act, j->n_first, j->n_second);
+  if (!r) return PINN_E_UNSUPPORTED;
+  NarrowParams p;
+  fill(p, m, j);
+  p.mode = mode;
+  if (mode == MODE_FUSED) {
+    p.dom = *dom;
+    n_points = dom->n_points;
+    for (int d = 0; d < m->n_in; ++d) p.coords[d] = dom->coords[d];
+  } else {
+    for (int d = 0; d < m->n_in; ++d) p.coords[d] = coords[d];
+  }
+  p.n_points = n_points;
+  p.jets_out = jets_out;
+  p.jets_bar = jets_bar;
+  p.n_tiles = (int32_t)((n_points + 31) / 32);
+  p.n_warps = n_warps;
+  const Layout lay(r->H(), m->n_hidden);
+  std::vector<float> gpart((size_t)n_cta * lay.size(), 0.f), lpart(n_cta, 0.f);
+  for (int c = 0; c < n_cta; ++c) r->run_cta(p, m->width, c, n_cta, n_warps, &gpart[(size_t)c * lay.size()], &lpart[c]);
+  if (mode == MODE_FWD) return 0;
+  const int64_t np = param_count(m);
+  for (int64_t i = 0; i < np; ++i) {
+    const int idx = flat_to_layout(m->n_in, m->n_out, m->width, lay, i);
+    float s = 0.f;
+    for (int c = 0; c < n_cta; ++c) s += gpart[(size_t)c * lay.size() + idx];
+    flat_grad[i] += s;
+  }
+  if (mode == MODE_FUSED && loss_out) {
+    float s = 0.f;
+    for (int c = 0; c < n_cta; ++c) s += lpart[c];
+    *loss_out += s;
+  }
+  return 0;
+}
+}

@@ -1,0 +1,162 @@
+"""Test helpers: run an oracle-format problem (see oracle/pinn_oracle.py)
+through the kernels' descriptors -- on the CPU emulator (tests/emu, host
+pointers) -- and build random problems."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+from idrlnet_b200 import compiler as cp
+from idrlnet_b200 import native as nv
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+EMU_DIR = os.path.join(ROOT, "tests", "emu")
+_EMU = None
+
+
+def emu_lib():
+    global _EMU
+    if _EMU is None:
+        so = os.path.join(EMU_DIR, "libpinn_emu.so")
+        src = os.path.join(EMU_DIR, "emu.cpp")
+        deps = [src, os.path.join(ROOT, "include", "pinn_b200.h")] + [
+            os.path.join(ROOT, "idrlnet_b200", "csrc", f) for f in ("narrow_warp.h", "pinn_common.h")]
+        if not os.path.exists(so) or any(os.path.getmtime(d) > os.path.getmtime(so) for d in deps):
+            subprocess.check_call(["g++", "-O1", "-std=c++17", "-fPIC", "-shared", "-DPINN_EMU",
+                                   "-fvisibility=hidden", "-o", so, src])
+        h = C.CDLL(so)
+        h.pinn_emu_run.restype = C.c_int
+        h.pinn_emu_run.argtypes = [C.POINTER(nv.PinnMlp), C.POINTER(nv.PinnJets), C.c_int, C.POINTER(nv.PinnDomain),
+                                   C.c_int64, C.POINTER(C.c_void_p), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                   C.c_int, C.c_int]
+        _EMU = h
+    return _EMU
+
+
+def effective_layers(net):
+    """[(W, b)] float32 effective weights of an oracle-format net."""
+    out = []
+    for lay in net["layers"]:
+        if "g" in lay:
+            v = np.asarray(lay["v"], np.float64)
+            g = np.asarray(lay["g"], np.float64).reshape(-1, 1)
+            W = (g * v / np.linalg.norm(v, axis=1, keepdims=True)).astype(np.float32)
+        else:
+            W = np.asarray(lay["W"], np.float32)
+        out.append((np.ascontiguousarray(W), np.ascontiguousarray(np.asarray(lay["b"], np.float32))))
+    return out
+
+
+def net_specs(problem):
+    return [cp.NetSpec(n["name"], tuple(n["inputs"]), tuple(n["outputs"])) for n in problem["nets"]]
+
+
+def owner_net(problem, name):
+    n = next(n for n in problem["nets"] if n["name"] == name)
+    if n.get("shares"):
+        n = next(m for m in problem["nets"] if m["name"] == n["shares"])
+    return n
+
+
+def flat_grad_from_oracle(res, net_name):
+    """Oracle W_eff/b grads of a net, one entry per flat-layout segment (None = no grad)."""
+    parts = []
+    for g in res["grads"][net_name]:
+        W = g["W_eff"] if g.get("W_eff") is not None else g.get("W")
+        parts.append(None if W is None else W.ravel())
+        parts.append(g["b"].ravel() if g["b"] is not None else None)
+    return parts
+
+
+def flat_layout_sizes(layers):
+    return [a.size for Wb in layers for a in Wb]
+
+
+def mlp_struct(layers, n_in, n_out, act, ptr):
+    width = layers[0][0].shape[0]
+    n_hidden = len(layers) - 1
+    for W, _ in layers[1:-1]:
+        assert W.shape == (width, width)
+    return nv.make_mlp(n_in, n_out, n_hidden, width, act, [ptr(W) for W, _ in layers], [ptr(b) for _, b in layers])
+
+
+def domain_columns(dom):
+    """float32 contiguous [N] columns of everything sampled on the domain."""
+    return {k: np.ascontiguousarray(np.asarray(v, np.float32).reshape(-1)) for k, v in dom["points"].items()}
+
+
+def compile_problem_domain(problem, dom):
+    cols = domain_columns(dom)
+    return cp.compile_domain(list(dom["targets"].keys()), problem.get("exprs", {}), net_specs(problem), list(cols))
+
+
+def run_emu_fused(problem, n_cta=3, n_warps=2):
+    """Every fusable domain through the emulator.  Returns
+    {net: flat grad}, {domain: loss}, [names of domains that were not fusable]."""
+    lib = emu_lib()
+    grads, losses, skipped = {}, {}, []
+    keep = []
+    for dom in problem["domains"]:
+        if not dom.get("targets"):
+            continue
+        try:
+            cd = compile_problem_domain(problem, dom)
+        except cp.NotFusable:
+            skipped.append(dom["name"])
+            continue
+        cols = domain_columns(dom)
+        n = len(next(iter(cols.values())))
+        net = owner_net(problem, cd.net.name)
+        layers = effective_layers(net)
+        keep.append(layers)
+        mlp = mlp_struct(layers, len(cd.net.inputs), len(cd.net.outputs), net["act"], lambda a: a.ctypes.data)
+        jets = nv.make_jets(cd.plan.first_in, cd.plan.n_second)
+
+        def val(v):
+            if np.ndim(v) == 0:
+                return float(v)
+            a = np.ascontiguousarray(np.asarray(v, np.float32).reshape(-1))
+            keep.append(a)
+            return cp.Ptr(a.ctypes.data)
+
+        targets = {k: val(v) for k, v in dom["targets"].items()}
+        lambdas = {k: val(v) for k, v in dom.get("lambdas", {}).items()}
+        for k in dom["targets"]:
+            if k not in lambdas and ("lambda_" + k) in cols:
+                lambdas[k] = cp.Ptr(cols["lambda_" + k].ctypes.data)
+        d = cp.build_domain_struct(cd, n, lambda k: cols[k].ctypes.data, targets, lambdas,
+                                   cp.Ptr(cols["area"].ctypes.data), dom.get("loss", "square"),
+                                   float(dom.get("sigma", 1.0)))
+        owner = net["name"]
+        if owner not in grads:
+            grads[owner] = np.zeros(sum(flat_layout_sizes(layers)), np.float32)
+        loss = np.zeros(1, np.float32)
+        rc = lib.pinn_emu_run(C.byref(mlp), C.byref(jets), 0, C.byref(d), n, None, None, None,
+                              grads[owner].ctypes.data, loss.ctypes.data, n_cta, n_warps)
+        assert rc == 0, rc
+        losses[dom["name"]] = float(loss[0])
+    return grads, losses, skipped
+
+
+def random_problem(rng, n_in=2, n_out=1, width=20, n_hidden=3, act="tanh", n_points=100, weight_norm=False,
+                   equation="u*u__x + u__t - 0.01*u__x__x", inputs=("x", "t"), outputs=("u",), loss="square",
+                   target=0.0, with_lambda=False, sigma=1.0, scale=1.0):
+    dims = [n_in] + [width] * n_hidden + [n_out]
+    layers = []
+    for i in range(len(dims) - 1):
+        W = (rng.standard_normal((dims[i + 1], dims[i])) * scale / np.sqrt(dims[i])).astype(np.float32)
+        b = (rng.standard_normal(dims[i + 1]) * 0.1).astype(np.float32)
+        if weight_norm:
+            g = (np.linalg.norm(W, axis=1, keepdims=True) * rng.uniform(0.5, 1.5, (dims[i + 1], 1))).astype(np.float32)
+            layers.append({"g": g, "v": W, "b": b})
+        else:
+            layers.append({"W": W, "b": b})
+    pts = {k: rng.uniform(-1, 1, (n_points, 1)).astype(np.float32) for k in inputs}
+    pts["area"] = rng.uniform(0.5, 1.5, (n_points, 1)).astype(np.float32) / max(n_points, 1)
+    dom = {"name": "dom", "points": pts, "targets": {"eq": target}, "lambdas": {}, "loss": loss, "sigma": sigma}
+    if with_lambda:
+        dom["lambdas"]["eq"] = rng.uniform(0.0, 2.0, (n_points, 1)).astype(np.float32)
+    return {"nets": [{"name": "net", "inputs": list(inputs), "outputs": list(outputs), "act": act,
+                      "layers": layers, "shares": None}],
+            "exprs": {"eq": equation}, "domains": [dom]}
