@@ -48,6 +48,23 @@ __global__ void weight_norm_bwd_kernel(const float* __restrict__ g, const float*
   for (int k = lane; k < in_dim; k += 32) dv[(size_t)row * in_dim + k] = a * (dr[k] - b * vr[k]);
 }
 
+// FP32 FMA throughput probe: 16 independent chains per thread (roofline denominator
+// for the narrow kernels; MEASURED_PEAKS.json only carries HBM and bf16 numbers).
+__global__ void fma_probe_kernel(int iters, float* out) {
+  float a[16];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) a[i] = 1.0f + 1e-3f * (threadIdx.x + i);
+  const float m = 1.0f - 1e-7f * (threadIdx.x & 3), c = 1e-9f * blockIdx.x;
+  for (int it = 0; it < iters; ++it) {
+#pragma unroll
+    for (int i = 0; i < 16; ++i) a[i] = a[i] * m + c;
+  }
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < 16; ++i) s += a[i];
+  if (s == 12345.678f) out[0] = s;  // keep the chains alive
+}
+
 struct SampleArgs {
   float* col[PINN_MAX_IN];
   float lo[PINN_MAX_IN], hi[PINN_MAX_IN];
@@ -98,6 +115,14 @@ int pinn_weight_norm_backward(const float* g, const float* v, const float* dW, f
   if (e != cudaSuccess) return (int)e;
   count_launch(1);
   return 0;
+}
+
+int64_t pinn_fp32_fma_probe(int32_t iters, int32_t blocks, float* scratch, void* stream) {
+  if (iters < 1 || blocks < 1 || !scratch) return PINN_E_INVALID;
+  fma_probe_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(iters, scratch);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return -(int64_t)e;
+  return (int64_t)2 * 16 * iters * 256 * blocks;  // flops issued
 }
 
 int pinn_sample_box(float* const* columns, int32_t n_dims, const float* lo, const float* hi, int64_t n_points,

@@ -1,0 +1,344 @@
+"""Torch-facing host layer over the C ABI (include/pinn_b200.h).
+
+PyTorch is used here for device memory, streams and (multi-GPU)
+`torch.distributed`; all per-point arithmetic happens in libpinn_b200.so.
+
+* `NetPack`      -- the parameters of one MLP (`idrlnet/architecture/mlp.py:18-76`)
+                    as the kernels see them: effective W/b per layer (weight-norm
+                    resolved by a kernel), one flat gradient buffer.
+* `JetFunction`  -- autograd op "MLP + input-derivative jets" for the generic
+                    path (replaces `idrlnet/net.py:14-36` +
+                    `idrlnet/variable.py:161-208` when a residual cannot be fused).
+* `FusedDomain`  -- one sampling domain compiled for `pinn_step_fused`.
+* `StepEngine`   -- one training step over several domains sharing a net:
+                    forward jets + residual + loss + reverse pass + gradient
+                    reduction (replaces `idrlnet/solver.py:329-338`).
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Dict, List, Mapping, Optional, Sequence, Tuple, Union
+
+import torch
+
+from . import compiler as cp
+from . import native as nv
+
+
+def _stream_ptr() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _require_cuda(t: torch.Tensor, what: str) -> None:
+    if not t.is_cuda:
+        raise RuntimeError(f"idrlnet_b200: {what} must be a CUDA tensor (there is no CPU path)")
+    if t.dtype != torch.float32:
+        raise RuntimeError(f"idrlnet_b200: {what} must be float32, got {t.dtype}")
+
+
+def _linear_layers(module: torch.nn.Module) -> List[torch.nn.Module]:
+    lins = [m for m in module.modules() if isinstance(m, torch.nn.Linear)]
+    if not lins:
+        raise cp.NotFusable("net has no Linear layers")
+    return lins
+
+
+def _activation_name(module: torch.nn.Module) -> str:
+    """Name of the single activation used between the Linear layers."""
+    names = set()
+    for m in module.modules():
+        n = type(m).__name__.lower()
+        if n in ("tanh",):
+            names.add("tanh")
+        elif n in ("silu", "swish"):
+            names.add("silu")
+        elif n in ("sin",):
+            names.add("sin")
+        elif n in ("relu", "selu", "sigmoid", "poly", "leaky_relu", "leakyrelu", "gelu", "elu", "softplus"):
+            names.add(n)
+    if len(names) != 1:
+        raise cp.NotFusable(f"net must use exactly one activation kind, found {sorted(names)}")
+    act = names.pop()
+    if act not in nv.ACT:
+        raise cp.NotFusable(f"activation {act} has no fused kernel")
+    return act
+
+
+class NetPack:
+    """Kernel view of an MLP: Linear stack, uniform hidden width, one activation."""
+
+    def __init__(self, module: torch.nn.Module, act: Optional[str] = None):
+        self.module = module
+        self.layers = _linear_layers(module)
+        self.act = act or _activation_name(module)
+        if len(self.layers) < 2:
+            raise cp.NotFusable("need at least one hidden layer")
+        self.n_in = self.layers[0].in_features
+        self.n_out = self.layers[-1].out_features
+        self.width = self.layers[0].out_features
+        self.n_hidden = len(self.layers) - 1
+        for i, lay in enumerate(self.layers):
+            want_in = self.n_in if i == 0 else self.width
+            want_out = self.n_out if i == self.n_hidden else self.width
+            if lay.in_features != want_in or lay.out_features != want_out:
+                raise cp.NotFusable("hidden layers must all have the same width")
+            if lay.bias is None:
+                raise cp.NotFusable("Linear layers without bias are not supported")
+        if self.n_in > nv.MAX_IN or self.n_out > nv.MAX_OUT or len(self.layers) > nv.MAX_LAYERS:
+            raise cp.NotFusable("net too large for the descriptors")
+        self.weight_norm = [hasattr(l, "weight_g") and hasattr(l, "weight_v") for l in self.layers]
+        dev = self.layers[0].bias.device
+        if dev.type != "cuda":
+            raise RuntimeError("idrlnet_b200: the net must live on a CUDA device (there is no CPU path)")
+        self.device = dev
+        self.sizes = []
+        for l in self.layers:
+            self.sizes += [l.out_features * l.in_features, l.out_features]
+        self.n_params = sum(self.sizes)
+        # effective-weight buffers for weight-norm layers (plain layers are read in place)
+        self._w_eff = [torch.empty(l.out_features, l.in_features, device=dev, dtype=torch.float32) if wn else None
+                       for l, wn in zip(self.layers, self.weight_norm)]
+        self._grad_wn: Dict[int, Tuple[torch.Tensor, torch.Tensor]] = {}
+        self._mlp = None
+        self._mlp_key = None
+
+    # -- parameters ---------------------------------------------------------
+    def raw_params(self, i: int):
+        l = self.layers[i]
+        if self.weight_norm[i]:
+            return l.weight_g, l.weight_v, l.bias
+        return l.weight, l.bias
+
+    def effective(self, i: int) -> Tuple[torch.Tensor, torch.Tensor]:
+        l = self.layers[i]
+        return (self._w_eff[i] if self.weight_norm[i] else l.weight.data), l.bias.data
+
+    def refresh_effective(self) -> None:
+        """W = g * v / ||v|| for the weight-norm layers (one small kernel each)."""
+        lib = nv.lib()
+        st = _stream_ptr()
+        for i, l in enumerate(self.layers):
+            if self.weight_norm[i]:
+                g, v = l.weight_g.data, l.weight_v.data
+                nv.check(lib.pinn_weight_norm_forward(g.data_ptr(), v.data_ptr(), self._w_eff[i].data_ptr(),
+                                                      l.out_features, l.in_features, st))
+
+    def mlp_struct(self) -> nv.PinnMlp:
+        ptrs = tuple(t.data_ptr() for i in range(len(self.layers)) for t in self.effective(i))
+        if self._mlp is None or self._mlp_key != ptrs:
+            for i in range(len(self.layers)):
+                for t in self.effective(i):
+                    _require_cuda(t, "net parameter")
+                    if not t.is_contiguous():
+                        raise RuntimeError("idrlnet_b200: net parameters must be contiguous")
+            self._mlp = nv.make_mlp(self.n_in, self.n_out, self.n_hidden, self.width, self.act, ptrs[0::2], ptrs[1::2])
+            self._mlp_key = ptrs
+        return self._mlp
+
+    # -- gradients ----------------------------------------------------------
+    def scatter_grad(self, flat: torch.Tensor, accumulate: bool = False) -> None:
+        """flat = d loss / d(effective W, b) in pinn_param_count order -> `.grad`
+        of the module's own parameters (through weight-norm where present)."""
+        lib = nv.lib()
+        st = _stream_ptr()
+        off = 0
+        for i, l in enumerate(self.layers):
+            nW, nb = self.sizes[2 * i], self.sizes[2 * i + 1]
+            dW = flat[off:off + nW].view(l.out_features, l.in_features)
+            db = flat[off + nW:off + nW + nb]
+            off += nW + nb
+            if self.weight_norm[i]:
+                if i not in self._grad_wn:
+                    self._grad_wn[i] = (torch.empty_like(l.weight_g.data), torch.empty_like(l.weight_v.data))
+                dg, dv = self._grad_wn[i]
+                nv.check(lib.pinn_weight_norm_backward(l.weight_g.data.data_ptr(), l.weight_v.data.data_ptr(),
+                                                       dW.data_ptr(), dg.data_ptr(), dv.data_ptr(), l.out_features,
+                                                       l.in_features, st))
+                _set_grad(l.weight_g, dg, accumulate)
+                _set_grad(l.weight_v, dv, accumulate)
+            else:
+                _set_grad(l.weight, dW, accumulate)
+            _set_grad(l.bias, db, accumulate)
+
+
+def _set_grad(p: torch.nn.Parameter, g: torch.Tensor, accumulate: bool) -> None:
+    if accumulate and p.grad is not None:
+        p.grad.add_(g)
+    else:
+        p.grad = g.clone() if accumulate else g
+
+
+# --------------------------------------------------------------------------- #
+class JetFunction(torch.autograd.Function):
+    """jets[c*n_out + o, n] of an MLP given as effective (W, b) tensors.
+
+    Differentiable w.r.t. the weights (not w.r.t. the coordinates: the input
+    derivatives ARE the jet channels)."""
+
+    @staticmethod
+    def forward(ctx, plan: cp.JetPlan, act: str, coords: Tuple[torch.Tensor, ...], *wb: torch.Tensor):
+        lib = nv.lib()
+        n_layers = len(wb) // 2
+        Ws, bs = wb[0::2], wb[1::2]
+        for t in list(coords) + list(wb):
+            _require_cuda(t, "JetFunction argument")
+        n = coords[0].numel()
+        cols = [c.detach().reshape(-1).contiguous() for c in coords]
+        wbc = [t.detach().contiguous() for t in wb]
+        mlp = nv.make_mlp(len(cols), Ws[-1].shape[0], n_layers - 1, Ws[0].shape[0], act,
+                          [t.data_ptr() for t in wbc[0::2]], [t.data_ptr() for t in wbc[1::2]])
+        jets = nv.make_jets(plan.first_in, plan.n_second)
+        out = torch.empty(plan.n_channels * Ws[-1].shape[0], n, device=cols[0].device, dtype=torch.float32)
+        nv.check(lib.pinn_jet_forward(C.byref(mlp), C.byref(jets), n, nv.ptr_array([c.data_ptr() for c in cols]),
+                                      out.data_ptr(), _stream_ptr()))
+        ctx.plan, ctx.act, ctx.cols, ctx.wbc = plan, act, cols, wbc
+        return out
+
+    @staticmethod
+    def backward(ctx, out_bar: torch.Tensor):
+        lib = nv.lib()
+        wbc, cols, plan = ctx.wbc, ctx.cols, ctx.plan
+        Ws = wbc[0::2]
+        n = cols[0].numel()
+        mlp = nv.make_mlp(len(cols), Ws[-1].shape[0], len(Ws) - 1, Ws[0].shape[0], ctx.act,
+                          [t.data_ptr() for t in wbc[0::2]], [t.data_ptr() for t in wbc[1::2]])
+        jets = nv.make_jets(plan.first_in, plan.n_second)
+        ws_bytes = lib.pinn_workspace_bytes(C.byref(mlp), C.byref(jets), 1)
+        ws = torch.empty(ws_bytes // 4, device=cols[0].device, dtype=torch.float32)
+        ob = out_bar.contiguous()
+        st = _stream_ptr()
+        nv.check(lib.pinn_jet_backward(C.byref(mlp), C.byref(jets), n, nv.ptr_array([c.data_ptr() for c in cols]),
+                                       ob.data_ptr(), ws.data_ptr(), ws_bytes, 0, st))
+        flat = torch.empty(lib.pinn_param_count(C.byref(mlp)), device=ob.device, dtype=torch.float32)
+        nv.check(lib.pinn_step_finalize(C.byref(mlp), C.byref(jets), ws.data_ptr(), ws_bytes, 1, flat.data_ptr(), 0,
+                                        None, st))
+        grads, off = [], 0
+        for t in wbc:
+            grads.append(flat[off:off + t.numel()].view_as(t))
+            off += t.numel()
+        return (None, None, None, *grads)
+
+
+def jet_mlp(plan: cp.JetPlan, act: str, coords: Sequence[torch.Tensor], weights_and_biases: Sequence[torch.Tensor]):
+    return JetFunction.apply(plan, act, tuple(coords), *weights_and_biases)
+
+
+# --------------------------------------------------------------------------- #
+Value = Union[torch.Tensor, float, int, None]
+
+
+class FusedDomain:
+    """A sampling domain bound to device columns, ready for `pinn_step_fused`."""
+
+    def __init__(self, name: str, compiled: cp.CompiledDomain, loss: str = "square", sigma: float = 1.0):
+        self.name = name
+        self.compiled = compiled
+        self.loss = loss
+        self.sigma = float(sigma)
+        self.jets = nv.make_jets(compiled.plan.first_in, compiled.plan.n_second)
+        self._struct: Optional[nv.PinnDomain] = None
+        self._keep: List[torch.Tensor] = []
+        self.n_points = 0
+
+    def bind(self, columns: Mapping[str, torch.Tensor], targets: Mapping[str, Value],
+             lambdas: Mapping[str, Value], area: Value) -> None:
+        """columns[key] = sampled [N,1] / [N] tensors (coords and aux symbols)."""
+        keep: List[torch.Tensor] = []
+
+        def col(t: torch.Tensor) -> torch.Tensor:
+            _require_cuda(t, f"domain {self.name} column")
+            t = t.detach().reshape(-1)
+            if not t.is_contiguous():
+                t = t.contiguous()
+            keep.append(t)
+            return t
+
+        cd = self.compiled
+        need = list(cd.net.inputs) + list(cd.aux_keys)
+        cols = {k: col(columns[k]) for k in need}
+        n = cols[cd.net.inputs[0]].numel()
+        for k, t in cols.items():
+            if t.numel() != n:
+                raise RuntimeError(f"domain {self.name}: column {k} has {t.numel()} points, expected {n}")
+
+        def val(v: Value, what: str):
+            if isinstance(v, torch.Tensor):
+                if v.numel() == 1 and n != 1:
+                    return float(v)
+                t = col(v)
+                if t.numel() != n:
+                    raise RuntimeError(f"domain {self.name}: {what} has {t.numel()} points, expected {n}")
+                return cp.Ptr(t.data_ptr())
+            return v if v is None else float(v)
+
+        tg = {e.name: val(targets[e.name], f"target {e.name}") for e in cd.equations}
+        lm = {e.name: val(lambdas.get(e.name), f"lambda_{e.name}") for e in cd.equations}
+        ar = val(area, "area")
+        if ar is None:
+            raise RuntimeError(f"domain {self.name}: no `area` (idrlnet/solver.py:369 requires it)")
+        self._struct = cp.build_domain_struct(cd, n, lambda k: cols[k].data_ptr(), tg, lm, ar, self.loss, self.sigma)
+        self._keep = keep
+        self.n_points = n
+
+    @property
+    def struct(self) -> nv.PinnDomain:
+        if self._struct is None:
+            raise RuntimeError(f"domain {self.name} is not bound to data")
+        return self._struct
+
+
+class StepEngine:
+    """One net, several fused domains: gradient of sum_d sigma_d * loss_d."""
+
+    def __init__(self, pack: NetPack, domains: Sequence[FusedDomain]):
+        self.pack = pack
+        self.domains = list(domains)
+        lib = nv.lib()
+        pack.refresh_effective()
+        mlp = pack.mlp_struct()
+        self.ws_bytes = 0
+        for d in self.domains:
+            if not lib.pinn_supported(C.byref(mlp), C.byref(d.jets)):
+                raise cp.NotFusable(f"no fused kernel for net width {pack.width} / jets of domain {d.name}")
+            self.ws_bytes = max(self.ws_bytes, lib.pinn_workspace_bytes(C.byref(mlp), C.byref(d.jets), len(self.domains)))
+        self.ws = torch.empty(max(self.ws_bytes // 4, 1), device=pack.device, dtype=torch.float32)
+        # flat gradient with the per-domain losses appended: ONE buffer to all-reduce
+        self.flat = torch.zeros(pack.n_params + len(self.domains), device=pack.device, dtype=torch.float32)
+        self.sigmas = torch.tensor([d.sigma for d in self.domains], device=pack.device, dtype=torch.float32)
+
+    @property
+    def grad(self) -> torch.Tensor:
+        return self.flat[: self.pack.n_params]
+
+    @property
+    def losses(self) -> torch.Tensor:
+        return self.flat[self.pack.n_params:]
+
+    def launch(self, timed: Optional[Tuple[int, "torch.cuda.Event", "torch.cuda.Event"]] = None) -> None:
+        """Enqueue the step kernels on the current stream (no host sync).
+        `timed=(i, start, stop)` brackets domain i's kernel with CUDA events."""
+        lib = nv.lib()
+        st = _stream_ptr()
+        pack = self.pack
+        pack.refresh_effective()
+        mlp = pack.mlp_struct()
+        for i, d in enumerate(self.domains):
+            if timed is not None and timed[0] == i:
+                timed[1].record()
+            nv.check(lib.pinn_step_fused(C.byref(mlp), C.byref(d.jets), C.byref(d.struct), self.ws.data_ptr(),
+                                         self.ws_bytes, i, 1 if i else 0, st))
+            if timed is not None and timed[0] == i:
+                timed[2].record()
+        nv.check(lib.pinn_step_finalize(C.byref(mlp), C.byref(self.domains[0].jets), self.ws.data_ptr(), self.ws_bytes,
+                                        len(self.domains), self.flat.data_ptr(), 0, self.losses.data_ptr(), st))
+
+    def total_loss(self) -> torch.Tensor:
+        return torch.dot(self.losses, self.sigmas)
+
+    def step(self, scatter: bool = True) -> torch.Tensor:
+        """launch + (optional) write `.grad` of the module parameters; returns the
+        total loss as a 0-d device tensor."""
+        self.launch()
+        if scatter:
+            self.pack.scatter_grad(self.grad)
+        return self.total_loss()

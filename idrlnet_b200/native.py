@@ -102,6 +102,7 @@ _SIGNATURES = {
                                             C.c_int32, C.c_void_p]),
     "pinn_sample_box": (C.c_int, [C.POINTER(_fp), C.c_int32, C.POINTER(C.c_float), C.POINTER(C.c_float), C.c_int64,
                                   C.c_uint64, C.c_uint64, C.c_uint64, C.c_void_p, C.c_int32, C.c_void_p]),
+    "pinn_fp32_fma_probe": (C.c_int64, [C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]),
 }
 EXPORTS = tuple(_SIGNATURES)
 

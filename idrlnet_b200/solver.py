@@ -1,0 +1,421 @@
+"""Solver (mirror of idrlnet/solver.py) with the fused CUDA training step behind it.
+
+Public surface kept: constructor arguments, `solve`, `train_pipe`, `compute_loss`,
+`infer_step`, `forward_through_all_graph`, `generate_in_out_dict`,
+`sample_variables_from_domains`, `set_domain_parameter` / `get_domain_parameter`,
+`register_receiver`, `sample_domains` (setter rebuilds the graphs), `netnodes`,
+`global_step`, `loss_component`, `save` / `load` / `init_load` (same `model.ckpt`
+layout), the seven Signals.
+
+What changes underneath: at graph-build time every domain whose loss terms compile
+to polynomials over one supported net (`compiler.compile_domain`) is bound to the
+fused kernels; a training step for those domains is `pinn_step_fused` +
+`pinn_step_finalize` (forward jets, residual, loss and reverse pass in one kernel
+per domain) instead of forward graph + `compute_loss` + `loss.backward()`
+(idrlnet/solver.py:329-338).  Everything else runs the generic graph.  Under
+`torch.distributed` the points of every domain are sharded over the ranks and
+the flat gradient (+ loss scalars) is all-reduced once per step.
+
+Deviation, on purpose: the reference re-samples and re-evaluates the loss after
+the optimiser step only to return/log it (idrlnet/solver.py:341-344), doubling the
+cost; here `train_pipe` returns the loss of the step it just took unless
+`post_step_loss=True` is passed.
+"""
+from __future__ import annotations
+
+import os
+import pathlib
+from typing import Callable, Dict, List, Optional, Tuple, Union
+
+import torch
+
+from . import compiler as cp
+from .data import DataNode, SampleDomain
+from .graph import VertexTaskPipeline
+from .header import logger
+from .net import NetNode
+from .optim import Optimizable
+from .pde import PdeNode
+from .receivers import Notifier, Receiver, Signal
+from .variable import DomainVariables, Variables
+
+__all__ = ["Solver"]
+
+
+def _dist():
+    d = torch.distributed
+    if d.is_available() and d.is_initialized() and d.get_world_size() > 1:
+        return d
+    return None
+
+
+class Solver(Notifier, Optimizable):
+    def __init__(self, sample_domains: Tuple[Union[DataNode, SampleDomain], ...], netnodes: List[NetNode],
+                 pdes: Optional[List] = None, network_dir: str = "./network_dir", summary_dir: Optional[str] = None,
+                 max_iter: int = 1000, save_freq: int = 100, print_freq: int = 10, loading: bool = True,
+                 init_network_dirs: Optional[List[str]] = None, opt_config: Dict = None, schedule_config: Dict = None,
+                 result_dir="train_domain/results", fused: Optional[bool] = None, post_step_loss: bool = False,
+                 **kwargs):
+        from . import callbacks
+        self.network_dir = network_dir
+        self.domain_losses = {d.name: d.loss_fn for d in sample_domains}
+        self.netnodes: List[NetNode] = netnodes
+        self.fused_enabled = fused
+        self.post_step_loss = post_step_loss
+        self._move_nets_to_device()
+        self.init_network_dirs = init_network_dirs if init_network_dirs else []
+        self.init_load()
+        self.pdes: List = [] if pdes is None else pdes
+        pathlib.Path(self.network_dir).mkdir(parents=True, exist_ok=True)
+        self.global_step = 0
+        self.max_iter, self.save_freq, self.print_freq = max_iter, save_freq, print_freq
+        try:
+            self.parse_configure(**({"opt_config": opt_config} if opt_config is not None else {}),
+                                 **({"schedule_config": schedule_config} if schedule_config is not None else {}))
+        except Exception:
+            logger.error("Optimizer configuration failed")
+            raise
+        if loading:
+            try:
+                self.load()
+            except Exception:
+                pass  # idrlnet/solver.py:116-120
+        self._receivers: List[Receiver] = []
+        self.sample_domains = sample_domains
+        self.summary_dir = self.network_dir if summary_dir is None else summary_dir
+        self.receivers = [callbacks.SummaryReceiver(self.summary_dir), callbacks.HandleResultReceiver(result_dir)]
+
+    # ------------------------------------------------------------------ setup
+    def _move_nets_to_device(self):
+        from . import DEVICE
+        for nn in self.netnodes:
+            nn.net.to(DEVICE)
+
+    @property
+    def network_dir(self):
+        return self._network_dir
+
+    @network_dir.setter
+    def network_dir(self, network_dir):
+        self._network_dir = network_dir
+
+    @property
+    def sample_domains(self):
+        return self._sample_domains
+
+    @sample_domains.setter
+    def sample_domains(self, sample_domains):
+        self._sample_domains = sample_domains
+        self.domain_losses = {d.name: d.loss_fn for d in sample_domains}
+        self._generate_dict_index()
+        self.generate_computation_pipeline()
+
+    @property
+    def trainable_parameters(self):
+        groups = [{"params": list(nn.net.parameters())} for nn in self.netnodes
+                  if not nn.is_reference and not nn.fixed]
+        if not groups:
+            logger.warning("No trainable parameters found!")
+            return [torch.nn.parameter.Parameter(torch.tensor([0.0]), requires_grad=True)]
+        return groups
+
+    @property
+    def summary_receiver(self):
+        return self.receivers[0]
+
+    def __str__(self):
+        return ("nets: \n" + "".join(str(n) for n in self.netnodes) + "domains: \n"
+                + "".join(str(d) for d in self.sample_domains) + "\noptimizer config:\n" + Optimizable.__str__(self))
+
+    def set_param_ranges(self, param_ranges: Dict):
+        for domain in self.sample_domains:
+            domain.sample_fn.param_ranges = param_ranges
+
+    def set_domain_parameter(self, domain_name: str, parameter_dict: dict):
+        domain = self.get_sample_domain(domain_name)
+        for key, value in parameter_dict.items():
+            domain.sample_fn.__dict__[key] = value
+
+    def get_domain_parameter(self, domain_name: str, parameter: str):
+        return self.get_sample_domain(domain_name).sample_fn.__dict__[parameter]
+
+    def get_sample_domain(self, name: str) -> DataNode:
+        for d in self.sample_domains:
+            if d.name == name:
+                return d
+        raise KeyError(f"domain {name} not exist!")
+
+    def append_sample_domain(self, datanode):
+        self.sample_domains = tuple(self.sample_domains) + (datanode,)
+
+    def _generate_dict_index(self) -> None:
+        self.invar_dict_index = {d.name: d.inputs for d in self.sample_domains}
+        self.outvar_dict_index = {d.name: d.outputs for d in self.sample_domains}
+        self.lambda_dict_index = {d.name: d.lambda_outputs for d in self.sample_domains}
+
+    # ------------------------------------------------------- graph + fusion
+    def generate_computation_pipeline(self):
+        """One graph per domain (idrlnet/solver.py:214-228) and, where possible,
+        one fused-kernel binding per domain."""
+        samples = self.sample_variables_from_domains()
+        in_var, _, _ = self.generate_in_out_dict(samples)
+        self.vertex_pipelines = {}
+        for name, var in in_var.items():
+            logger.debug(f"Constructing computation graph for domain <{name}>")
+            self.vertex_pipelines[name] = VertexTaskPipeline(self.netnodes + self.pdes, var, self.outvar_dict_index[name])
+        self._plan_fusion(in_var)
+
+    def _plan_fusion(self, in_var: DomainVariables) -> None:
+        from . import DEVICE, fused
+        self._fused_domains: Dict[str, "fused.FusedDomain"] = {}
+        self._fused_owner: Dict[str, NetNode] = {}
+        self._engines: Dict[int, "fused.StepEngine"] = {}
+        self._packs = getattr(self, "_packs", {})
+        want = self.fused_enabled
+        if want is False or DEVICE.type != "cuda":
+            if want:
+                raise RuntimeError("Solver(fused=True) needs a CUDA device: the fused step has no CPU implementation")
+            return
+        exprs = {}
+        for pde in self.pdes:
+            if isinstance(pde, PdeNode):
+                for sub in pde.sub_nodes:
+                    exprs[sub.name] = sub.evaluate.tf_eq
+        specs = [cp.NetSpec(nn.name, tuple(nn.inputs), tuple(nn.outputs)) for nn in self.netnodes]
+        by_name = {nn.name: nn for nn in self.netnodes}
+        for dom in self.sample_domains:
+            if not dom.outputs:
+                continue
+            try:
+                cd = cp.compile_domain(list(dom.outputs), exprs, specs, list(in_var[dom.name].keys()))
+                nn = by_name[cd.net.name]
+                if nn.fixed or nn.require_no_grad:
+                    raise cp.NotFusable("fixed / no-grad net")
+                key = id(nn.net)
+                if key not in self._packs:
+                    self._packs[key] = fused.NetPack(nn.net)
+                pack = self._packs[key]
+                if pack.n_in != len(nn.inputs) or pack.n_out < len(nn.outputs):
+                    raise cp.NotFusable("net shape does not match the node's inputs/outputs")
+                fd = fused.FusedDomain(dom.name, cd, dom.loss_fn if isinstance(dom.loss_fn, str) else dom.loss_fn.name,
+                                       float(dom.sigma))
+                import ctypes as C
+                from . import native as nv
+                pack.refresh_effective()
+                if not nv.lib().pinn_supported(C.byref(pack.mlp_struct()), C.byref(fd.jets)):
+                    raise cp.NotFusable("no kernel for this net width / jet plan")
+                self._fused_domains[dom.name] = fd
+                self._fused_owner[dom.name] = nn
+            except cp.NotFusable as e:
+                logger.info(f"domain <{dom.name}>: generic path ({e})")
+        if want and len(self._fused_domains) == 0:
+            raise RuntimeError("Solver(fused=True): no domain could be fused")
+        if self._fused_domains:
+            logger.info("fused CUDA step for domains: " + ", ".join(self._fused_domains))
+
+    # --------------------------------------------------------------- forward
+    def forward_through_all_graph(self, invar_dict: DomainVariables,
+                                  req_outvar_dict_index: Dict[str, List[str]]) -> DomainVariables:
+        return {key: self.vertex_pipelines[key].forward_pipeline(invar_dict[key], req)
+                for key, req in req_outvar_dict_index.items()}
+
+    def generate_in_out_dict(self, samples: DomainVariables):
+        def pick(index):
+            return {d: Variables({k: v for k, v in var.items() if k in index[d]}) for d, var in samples.items()}
+        return pick(self.invar_dict_index), pick(self.outvar_dict_index), pick(self.lambda_dict_index)
+
+    def sample_variables_from_domains(self) -> DomainVariables:
+        return {d.name: d.sample() for d in self.sample_domains}
+
+    # ------------------------------------------------------------------ train
+    def solve(self):
+        self.notify(self, message={Signal.SOLVE_START: "default"})
+        while self.global_step < self.max_iter:
+            loss = self.train_pipe()
+            if self.global_step % self.print_freq == 0:
+                logger.info("Iteration: {}, Loss: {}".format(self.global_step, float(loss)))
+            if self.global_step % self.save_freq == 0:
+                self.save()
+        logger.info("Training Stage Ends")
+        self.notify(self, message={Signal.SOLVE_END: "default"})
+
+    def train_pipe(self):
+        """Sample once, loss + gradients once, optimiser step once."""
+        self.notify(self, message={Signal.TRAIN_PIPE_START: "defaults"})
+        loss = None
+        for opt in self.optimizers:
+            if self.optimizer_config["optimizer"] == "LBFGS":
+                def closure():
+                    opt.zero_grad()
+                    return self._loss_and_grads()
+                loss = opt.step(closure)
+            else:
+                opt.zero_grad()
+                loss = self._loss_and_grads()
+                opt.step()
+        if self.post_step_loss:
+            loss = self._loss_and_grads(grads=False)  # idrlnet/solver.py:341-344
+        self.global_step += 1
+        for scheduler in self.schedulers:
+            scheduler.step(self.global_step)
+        self.notify(self, message={Signal.TRAIN_PIPE_END: "defaults"})
+        return loss
+
+    def _shard(self, samples: DomainVariables) -> DomainVariables:
+        d = _dist()
+        if d is None:
+            return samples
+        r, w = d.get_rank(), d.get_world_size()
+        return {name: Variables({k: (v[r::w] if isinstance(v, torch.Tensor) and v.dim() > 0 and v.shape[0] > 1 else v)
+                                 for k, v in var.items()}) for name, var in samples.items()}
+
+    def _loss_and_grads(self, grads: bool = True) -> torch.Tensor:
+        samples = self._shard(self.sample_variables_from_domains())
+        in_var, true_out, lambda_out = self.generate_in_out_dict(samples)
+        fused_names = [n for n in self._fused_domains if len(true_out[n]) > 0]
+        generic = {n: idx for n, idx in self.outvar_dict_index.items() if n not in fused_names and len(true_out[n]) > 0}
+        comps: Dict[str, torch.Tensor] = {}
+        gen_loss = None
+        # -- generic domains: graph forward + torch loss ------------------------
+        if generic:
+            pred = self.forward_through_all_graph(in_var, generic)
+            comps.update(self._loss_components(in_var, pred, {n: true_out[n] for n in generic},
+                                               {n: lambda_out[n] for n in generic}))
+        # -- fused domains: one kernel per domain --------------------------------
+        engines = self._bind_fused(fused_names, in_var, true_out, lambda_out)
+        dist = _dist()
+        for eng in engines:
+            eng.launch()
+            if dist is not None:
+                dist.all_reduce(eng.flat)
+            for fd, l in zip(eng.domains, eng.losses):
+                comps[f"{fd.name}_loss"] = l
+        ordered = {f"{d.name}_loss": comps[f"{d.name}_loss"] for d in self.sample_domains if f"{d.name}_loss" in comps}
+        self.loss_component = Variables(ordered)
+        self.notify(self, message={Signal.BEFORE_COMPUTE_LOSS: {**self.loss_component}})
+        loss = sum(self.get_sample_domain(k[:-5]).sigma.to(v.device) * v for k, v in ordered.items())
+        self.notify(self, message={Signal.AFTER_COMPUTE_LOSS: {**self.loss_component, **{"total_loss": loss}}})
+        if not grads:
+            return loss.detach() if isinstance(loss, torch.Tensor) else loss
+        self.notify(self, message={Signal.BEFORE_BACKWARD: "defaults"})
+        if generic:
+            gen_loss = sum(self.get_sample_domain(n).sigma.to(comps[f"{n}_loss"].device) * comps[f"{n}_loss"]
+                           for n in generic)
+            if isinstance(gen_loss, torch.Tensor) and gen_loss.requires_grad:
+                gen_loss.backward()
+                if dist is not None:
+                    for nn in self.netnodes:
+                        for p in nn.net.parameters():
+                            if p.grad is not None:
+                                dist.all_reduce(p.grad)
+        for eng in engines:
+            eng.pack.scatter_grad(eng.grad, accumulate=bool(generic) or len(engines) > 1)
+        return loss.detach() if isinstance(loss, torch.Tensor) else loss
+
+    def _bind_fused(self, names, in_var, true_out, lambda_out):
+        from . import fused
+        groups: Dict[int, List] = {}
+        for n in names:
+            fd = self._fused_domains[n]
+            pts = in_var[n]
+            lambdas = {k[len("lambda_"):]: v for k, v in lambda_out[n].items()}
+            for k in list(true_out[n].keys()):
+                if k not in lambdas and ("lambda_" + k) in pts:  # idrlnet/solver.py:371-378
+                    lambdas[k] = pts["lambda_" + k]
+            fd.bind(pts, {k: v for k, v in true_out[n].to_torch_tensor_().items()}, lambdas, pts.get("area"))
+            groups.setdefault(id(self._fused_owner[n].net), []).append(fd)
+        engines = []
+        for key, fds in groups.items():
+            sig = tuple(fd.name for fd in fds)
+            eng = self._engines.get(key)
+            if eng is None or getattr(eng, "_sig", None) != sig:
+                eng = fused.StepEngine(self._packs[key], fds)
+                eng._sig = sig
+                self._engines[key] = eng
+            else:
+                eng.domains = fds
+            engines.append(eng)
+        return engines
+
+    def _loss_components(self, in_var, pred_out_sample, true_out, lambda_out) -> Dict[str, torch.Tensor]:
+        """Per-domain weighted losses of the generic path (idrlnet/solver.py:362-390)."""
+        comps = {}
+        for name, tgt in true_out.items():
+            if len(tgt) == 0:
+                continue
+            diff = pred_out_sample[name] - tgt.to_torch_tensor_()
+            diff.update(lambda_out[name])
+            diff.update(area=in_var[name]["area"])
+            for k in list(diff.keys()):
+                if "lambda_" + k in in_var[name]:
+                    diff["lambda_" + k] = in_var[name]["lambda_" + k]
+            comps.update(diff.weighted_loss(f"{name}_loss", loss_function=self.domain_losses[name]))
+        return comps
+
+    def compute_loss(self, in_var: DomainVariables, pred_out_sample: DomainVariables, true_out: DomainVariables,
+                     lambda_out: DomainVariables) -> torch.Tensor:
+        """Total loss of already-forwarded domains (idrlnet/solver.py:353-408)."""
+        comps = self._loss_components(in_var, pred_out_sample, true_out, lambda_out)
+        self.loss_component = Variables(comps)
+        self.notify(self, message={Signal.BEFORE_COMPUTE_LOSS: {**self.loss_component}})
+        loss = sum(self.get_sample_domain(k[:-5]).sigma.to(v.device) * v for k, v in comps.items())
+        self.notify(self, message={Signal.AFTER_COMPUTE_LOSS: {**self.loss_component, **{"total_loss": loss}}})
+        return loss
+
+    def infer_step(self, domain_attr: Dict[str, List[str]]) -> DomainVariables:
+        samples = self.sample_variables_from_domains()
+        in_var, _, _ = self.generate_in_out_dict(samples)
+        return self.forward_through_all_graph(in_var, domain_attr)
+
+    # ------------------------------------------------------------- checkpoint
+    def save(self):
+        """`model.ckpt`: {<net>_dict, optimizer_<i>_dict, global_step} (idrlnet/solver.py:425-436)."""
+        d = _dist()
+        if d is not None and d.get_rank() != 0:
+            return
+        path = os.path.join(self.network_dir, "model.ckpt")
+        logger.info("save to path: {}".format(os.path.abspath(path)))
+        save_dict = {f"{nn.name}_dict": nn.state_dict() for nn in self.netnodes if not nn.is_reference}
+        for i, opt in enumerate(self.optimizers):
+            save_dict[f"optimizer_{i}_dict"] = opt.state_dict()
+        save_dict["global_step"] = self.global_step
+        torch.save(save_dict, path)
+
+    def init_load(self):
+        from . import DEVICE
+        for network_dir in self.init_network_dirs:
+            save_dict = torch.load(os.path.join(network_dir, "model.ckpt"), map_location=DEVICE)
+            for nn in self.netnodes:
+                if f"{nn.name}_dict" in save_dict and not nn.is_reference:
+                    nn.load_state_dict(save_dict[f"{nn.name}_dict"])
+                    logger.info(f"Successfully loading initialization {nn.name}.")
+
+    def load(self):
+        from . import DEVICE
+        save_dict = torch.load(os.path.join(self.network_dir, "model.ckpt"), map_location=DEVICE)
+        for i, opt in enumerate(self.optimizers):
+            opt.load_state_dict(save_dict[f"optimizer_{i}_dict"])
+        self.global_step = save_dict["global_step"]
+        for nn in self.netnodes:
+            if f"{nn.name}_dict" in save_dict and not nn.is_reference:
+                nn.load_state_dict(save_dict[f"{nn.name}_dict"])
+                logger.info(f"Successfully loading {nn.name}.")
+
+    def configure_optimizers(self):
+        opt = self.optimizer_config["optimizer"]
+        if isinstance(opt, str) and opt in Optimizable.OPTIMIZER_MAP:
+            opt = Optimizable.OPTIMIZER_MAP[opt](self.trainable_parameters,
+                                                 **{k: v for k, v in self.optimizer_config.items() if k != "optimizer"})
+        elif not isinstance(opt, Callable):
+            raise NotImplementedError("The optimizer is not implemented. You may use one of the following optimizer:\n"
+                                      + "\n".join(Optimizable.OPTIMIZER_MAP.keys())
+                                      + '\n Example: opt_config=dict(optimizer="Adam", lr=1e-3)')
+        sch = self.schedule_config["scheduler"]
+        if isinstance(sch, str) and sch in Optimizable.SCHEDULE_MAP:
+            sch = Optimizable.SCHEDULE_MAP[sch](opt, **{k: v for k, v in self.schedule_config.items() if k != "scheduler"})
+        elif not isinstance(sch, Callable):
+            raise NotImplementedError("The scheduler is not implemented. You may use one of the following scheduler:\n"
+                                      + "\n".join(Optimizable.SCHEDULE_MAP.keys())
+                                      + '\n Example: schedule_config=dict(scheduler="ExponentialLR", gamma=0.999')
+        self.optimizers = [opt]
+        self.schedulers = [sch]

@@ -190,6 +190,12 @@ PINN_API int pinn_sample_box(float* const* columns, int32_t n_dims, const float*
                     int64_t n_points, uint64_t seed, uint64_t stream_id, uint64_t offset,
                     float* sdf, int32_t sdf_dims, void* stream);
 
+/* ---- measurement helper ------------------------------------------------- */
+/* Launches `blocks` x 256 threads each running 16 independent FP32 FMA chains of
+ * `iters` steps; returns the number of flops issued (time it with CUDA events to
+ * get the FP32-pipe roofline denominator), or a negative cudaError_t. */
+PINN_API int64_t pinn_fp32_fma_probe(int32_t iters, int32_t blocks, float* scratch, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -141,3 +141,23 @@ __attribute__((visibility("default"))) int pinn_emu_run(const pinn_mlp* m, const
   return 0;
 }
 }
+
+// Host evaluation of the sampler maps (idrlnet_b200/csrc/philox.h) so the device
+// sampler can be checked bit for bit.
+#include "../../idrlnet_b200/csrc/philox.h"
+extern "C" __attribute__((visibility("default"))) void pinn_emu_sample_box(float* const* columns, int n_dims,
+                                                                          const float* lo, const float* hi,
+                                                                          int64_t n_points, uint64_t seed,
+                                                                          uint64_t stream_id, uint64_t offset,
+                                                                          float* sdf, int sdf_dims) {
+  for (int64_t i = 0; i < n_points; ++i) {
+    uint32_t r[4];
+    pinn::philox4x32_10(seed, stream_id, offset + (uint64_t)i, r);
+    float xs[PINN_MAX_IN];
+    for (int d = 0; d < n_dims; ++d) {
+      xs[d] = pinn::box_point(r[d], lo[d], hi[d]);
+      columns[d][i] = xs[d];
+    }
+    if (sdf) sdf[i] = pinn::box_sdf(xs, lo, hi, sdf_dims);
+  }
+}

@@ -21,7 +21,7 @@ def emu_lib():
         so = os.path.join(EMU_DIR, "libpinn_emu.so")
         src = os.path.join(EMU_DIR, "emu.cpp")
         deps = [src, os.path.join(ROOT, "include", "pinn_b200.h")] + [
-            os.path.join(ROOT, "idrlnet_b200", "csrc", f) for f in ("narrow_warp.h", "pinn_common.h")]
+            os.path.join(ROOT, "idrlnet_b200", "csrc", f) for f in ("narrow_warp.h", "pinn_common.h", "philox.h")]
         if not os.path.exists(so) or any(os.path.getmtime(d) > os.path.getmtime(so) for d in deps):
             subprocess.check_call(["g++", "-O1", "-std=c++17", "-fPIC", "-shared", "-DPINN_EMU",
                                    "-fvisibility=hidden", "-o", so, src])
@@ -30,6 +30,9 @@ def emu_lib():
         h.pinn_emu_run.argtypes = [C.POINTER(nv.PinnMlp), C.POINTER(nv.PinnJets), C.c_int, C.POINTER(nv.PinnDomain),
                                    C.c_int64, C.POINTER(C.c_void_p), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                    C.c_int, C.c_int]
+        h.pinn_emu_sample_box.restype = None
+        h.pinn_emu_sample_box.argtypes = [C.POINTER(C.c_void_p), C.c_int, C.POINTER(C.c_float), C.POINTER(C.c_float),
+                                          C.c_int64, C.c_uint64, C.c_uint64, C.c_uint64, C.c_void_p, C.c_int]
         _EMU = h
     return _EMU
 
@@ -160,3 +163,71 @@ def random_problem(rng, n_in=2, n_out=1, width=20, n_hidden=3, act="tanh", n_poi
     return {"nets": [{"name": "net", "inputs": list(inputs), "outputs": list(outputs), "act": act,
                       "layers": layers, "shares": None}],
             "exprs": {"eq": equation}, "domains": [dom]}
+
+
+# --------------------------------------------------------------------------- #
+# CUDA side: oracle-format problem -> torch modules -> idrlnet_b200.fused
+# --------------------------------------------------------------------------- #
+def torch_module_from_net(net, device):
+    """An idrlnet_b200.architecture.MLP holding the oracle-format net's parameters."""
+    import torch
+    from idrlnet_b200 import architecture as arch
+    layers = net["layers"]
+    wn = "g" in layers[0]
+    first = layers[0]["v"] if wn else layers[0]["W"]
+    seq = [np.asarray(first).shape[1]] + [np.asarray(l["b"]).shape[0] for l in layers]
+    act = {"tanh": arch.Activation.tanh, "silu": arch.Activation.silu, "sin": arch.Activation.sin}[net["act"]]
+    m = arch.MLP(seq, activation=act, weight_norm=wn)
+    lins = [l for k, l in m.layers.items() if not k.endswith("_activation")]
+    with torch.no_grad():
+        for lin, lay in zip(lins, layers):
+            lin.bias.copy_(torch.as_tensor(np.asarray(lay["b"], np.float32)))
+            if wn:
+                lin.weight_g.copy_(torch.as_tensor(np.asarray(lay["g"], np.float32)).reshape(lin.weight_g.shape))
+                lin.weight_v.copy_(torch.as_tensor(np.asarray(lay["v"], np.float32)))
+            else:
+                lin.weight.copy_(torch.as_tensor(np.asarray(lay["W"], np.float32)))
+    return m.to(device)
+
+
+def run_cuda_fused(problem, device="cuda:0"):
+    """All fusable domains through fused.StepEngine (the C ABI).  Returns
+    ({net: flat eff grad (numpy)}, {domain: loss}, skipped, {net: module})."""
+    import torch
+    from idrlnet_b200 import fused
+    modules, packs, per_net = {}, {}, {}
+    skipped = []
+    for dom in problem["domains"]:
+        if not dom.get("targets"):
+            continue
+        try:
+            cd = compile_problem_domain(problem, dom)
+        except cp.NotFusable:
+            skipped.append(dom["name"])
+            continue
+        owner = owner_net(problem, cd.net.name)
+        if owner["name"] not in modules:
+            modules[owner["name"]] = torch_module_from_net(owner, device)
+            packs[owner["name"]] = fused.NetPack(modules[owner["name"]], act=owner["act"])
+        cols = {k: torch.as_tensor(v, device=device) for k, v in domain_columns(dom).items()}
+
+        def val(v):
+            return float(v) if np.ndim(v) == 0 else torch.as_tensor(np.asarray(v, np.float32).reshape(-1), device=device)
+
+        targets = {k: val(v) for k, v in dom["targets"].items()}
+        lambdas = {k: val(v) for k, v in dom.get("lambdas", {}).items()}
+        for k in dom["targets"]:
+            if k not in lambdas and ("lambda_" + k) in cols:
+                lambdas[k] = cols["lambda_" + k]
+        fd = fused.FusedDomain(dom["name"], cd, dom.get("loss", "square"), float(dom.get("sigma", 1.0)))
+        fd.bind(cols, targets, lambdas, cols["area"])
+        per_net.setdefault(owner["name"], []).append(fd)
+    grads, losses = {}, {}
+    for name, doms in per_net.items():
+        eng = fused.StepEngine(packs[name], doms)
+        eng.step(scatter=True)
+        torch.cuda.synchronize()
+        grads[name] = eng.grad.detach().cpu().numpy().copy()
+        for d, l in zip(doms, eng.losses.detach().cpu().numpy()):
+            losses[d.name] = float(l)
+    return grads, losses, skipped, modules
