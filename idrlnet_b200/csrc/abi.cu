@@ -87,12 +87,17 @@ static DeviceInfo& device_info() {
 
 // ----------------------------------------------------------------------------
 // workspace layout (floats): [gpart: MAX_CTA * PP][lpart: n_domains * MAX_CTA]
+//                            [stash: MAX_CTA * 8 warps * stash_floats]
 // ----------------------------------------------------------------------------
-static const int kMaxCta = 148 * 2;
+static const int kMaxCta = 160;  // >= SM count of a B200 (148); one persistent CTA per SM
+static const int kMaxWarps = 8;
 
 struct NarrowPlan {
   const NarrowKernelInfo* k;
   int Hp, L, PP, n_warps, smem_bytes, n_cta_cap;
+  int64_t stash_floats_warp;
+  int64_t head_bytes(int n_slots) const { return ((int64_t)kMaxCta * PP + (int64_t)n_slots * kMaxCta) * 4; }
+  int64_t stash_bytes() const { return (int64_t)kMaxCta * kMaxWarps * stash_floats_warp * 4; }
 };
 
 static int narrow_plan(const pinn_mlp* m, const pinn_jets* j, NarrowPlan* pl, bool need_device) {
@@ -112,11 +117,12 @@ static int narrow_plan(const pinn_mlp* m, const pinn_jets* j, NarrowPlan* pl, bo
     sms = di.sm_count;
   }
   int nw = (max_smem - lay.size() * 4) / (wf * 4);
-  if (nw > 8) nw = 8;
+  if (nw > kMaxWarps) nw = kMaxWarps;
   if (nw < 1) return fail(PINN_E_UNSUPPORTED, "net too deep for the narrow kernel (smem)");
   pl->n_warps = nw;
   pl->smem_bytes = (lay.size() + nw * wf) * 4;
   pl->n_cta_cap = sms < kMaxCta ? sms : kMaxCta;
+  pl->stash_floats_warp = pl->k->stash_floats(pl->L);
   return 0;
 }
 
@@ -204,7 +210,7 @@ int64_t pinn_workspace_bytes(const pinn_mlp* m, const pinn_jets* j, int32_t n_do
   if (narrow_lookup(m, j)) {
     NarrowPlan pl;
     if (narrow_plan(m, j, &pl, false)) return 0;
-    return ((int64_t)kMaxCta * pl.PP + (int64_t)n_domains * kMaxCta) * 4;
+    return pl.head_bytes(n_domains) + pl.stash_bytes();
   }
   return wide_workspace_bytes(m, j, n_domains);
 }
@@ -215,12 +221,14 @@ static int narrow_step_common(const pinn_mlp* m, const pinn_jets* j, NarrowParam
   int rc = narrow_plan(m, j, &pl, true);
   if (rc) return rc;
   const int64_t gbytes = (int64_t)kMaxCta * pl.PP * 4;
-  if (!ws || ws_bytes < gbytes + (int64_t)n_slots_needed * kMaxCta * 4)
+  // the stash sits at the END of the workspace so that its offset does not depend on the slot count
+  if (!ws || ws_bytes < pl.head_bytes(n_slots_needed) + pl.stash_bytes())
     return fail(PINN_E_WORKSPACE, "workspace too small: %lld bytes", (long long)ws_bytes);
   p.gpart = (float*)ws;
   p.lpart = (float*)((char*)ws + gbytes);
+  p.stash = (float*)((char*)ws + (ws_bytes - pl.stash_bytes()));
   if (!accumulate) {
-    cudaError_t e = cudaMemsetAsync(ws, 0, (size_t)ws_bytes, st);
+    cudaError_t e = cudaMemsetAsync(ws, 0, (size_t)(ws_bytes - pl.stash_bytes()), st);
     if (e != cudaSuccess) return cuda_fail(e, "cudaMemsetAsync(workspace)");
   }
   return launch_narrow(m, j, p, pl, st);
@@ -272,7 +280,7 @@ int pinn_step_finalize(const pinn_mlp* m, const pinn_jets* j, void* ws, int64_t 
     rc = narrow_plan(m, j, &pl, true);
     if (rc) return rc;
     const int64_t gbytes = (int64_t)kMaxCta * pl.PP * 4;
-    if (!ws || ws_bytes < gbytes + (int64_t)n_domains * kMaxCta * 4) return fail(PINN_E_WORKSPACE, "workspace too small");
+    if (!ws || ws_bytes < pl.head_bytes(n_domains)) return fail(PINN_E_WORKSPACE, "workspace too small");
     if (n_domains > 256) return fail(PINN_E_INVALID, "too many domains");
     const int64_t np = pinn_param_count(m);
     const int threads = 256;

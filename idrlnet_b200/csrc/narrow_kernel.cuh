@@ -13,6 +13,7 @@ struct NarrowKernelInfo {
   narrow_kernel_t fn;
   int H, C;
   int (*warp_floats)(int L);
+  int (*stash_floats)(int L);
 };
 
 template <class NW>
@@ -25,10 +26,11 @@ __global__ void __launch_bounds__(256, 1) narrow_kernel(const __grid_constant__ 
   const int nwarps = blockDim.x >> 5;
   const int wf = NW::warp_floats(L);
   float* wm = smem + lay.size() + warp * wf;
+  float* gs = p.stash + ((size_t)blockIdx.x * nwarps + warp) * NW::stash_floats(L);
 
   for (int i = tid; i < lay.size(); i += blockDim.x) smem[i] = stage_weight(p, Hreal, lay, i);
   {
-    float* g = wm + NW::off_gacc(L);
+    float* g = wm + NW::off_gacc();
     for (int i = lane; i < lay.size(); i += 32) g[i] = 0.f;
   }
   __syncthreads();
@@ -36,36 +38,36 @@ __global__ void __launch_bounds__(256, 1) narrow_kernel(const __grid_constant__ 
   typename NW::Lane ln;
   ln.loss = 0.f;
   for (int64_t tile = (int64_t)blockIdx.x * nwarps + warp; tile < p.n_tiles; tile += (int64_t)gridDim.x * nwarps) {
-    NW::phase_forward(p, smem, wm, lane, tile, ln);
+    NW::phase_forward(p, smem, wm, gs, lane, tile, ln);
     if (p.mode == MODE_FWD) continue;
-    __syncwarp();
-    NW::phase_gemm_out(p, wm, lane);
-    __syncwarp();
-    for (int l = L; l >= 2; --l) {
-      NW::phase_backward_layer(p, smem, wm, lane, l);
+    for (int l = L + 1; l >= 2; --l) {
+      NW::phase_backward(p, smem, wm, gs, lane, l, ln);
       __syncwarp();
-      NW::phase_gemm_hidden(p, wm, lane, l);
+      if (l == L + 1) NW::phase_gemm_out(p, wm, lane);
+      else NW::phase_gemm_hidden(p, wm, lane, l);
       __syncwarp();
+      NW::phase_store_zk(wm, lane, ln);
     }
+    __syncwarp();
     NW::phase_gemm_first(p, wm, lane);
     __syncwarp();
   }
   if (p.mode == MODE_FWD) return;
 
-  wm[NW::off_xs(L) + lane] = ln.loss;
+  wm[NW::off_xs() + lane] = ln.loss;
   __syncthreads();
   // per-CTA partial = sum over the CTA's warps, in warp order (deterministic)
   float* gp = p.gpart + (size_t)blockIdx.x * lay.size();
   for (int i = tid; i < lay.size(); i += blockDim.x) {
     float s = 0.f;
-    for (int w = 0; w < nwarps; ++w) s += smem[lay.size() + w * wf + NW::off_gacc(L) + i];
+    for (int w = 0; w < nwarps; ++w) s += smem[lay.size() + w * wf + NW::off_gacc() + i];
     gp[i] += s;
   }
   if (p.mode == MODE_FUSED && tid == 0) {
     float s = 0.f;
     for (int w = 0; w < nwarps; ++w) {
       float sw_ = 0.f;
-      for (int l2 = 0; l2 < 32; ++l2) sw_ += smem[lay.size() + w * wf + NW::off_xs(L) + l2];
+      for (int l2 = 0; l2 < 32; ++l2) sw_ += smem[lay.size() + w * wf + NW::off_xs() + l2];
       s += sw_;
     }
     p.lpart[(size_t)p.domain_slot * p.max_cta + blockIdx.x] += s;
@@ -74,14 +76,15 @@ __global__ void __launch_bounds__(256, 1) narrow_kernel(const __grid_constant__ 
 
 // One table per (H, ACT) translation unit: entries for every (NF, NS).
 #define PINN_NARROW_ENTRY(H, NF, NS, ACT) \
-  { narrow_kernel<NarrowWarp<H, NF, NS, ACT>>, H, 1 + NF + NS, &NarrowWarp<H, NF, NS, ACT>::warp_floats }
+  { narrow_kernel<NarrowWarp<H, NF, NS, ACT>>, H, 1 + NF + NS, &NarrowWarp<H, NF, NS, ACT>::warp_floats, \
+    &NarrowWarp<H, NF, NS, ACT>::stash_floats }
 
 #define PINN_NARROW_TABLE(NAME, H, ACT)                                          \
   const NarrowKernelInfo* NAME(int nf, int ns) {                                 \
     static const NarrowKernelInfo t[4][4] = {                                    \
-        {PINN_NARROW_ENTRY(H, 0, 0, ACT), {0, 0, 0, 0}, {0, 0, 0, 0}, {0, 0, 0, 0}}, \
-        {PINN_NARROW_ENTRY(H, 1, 0, ACT), PINN_NARROW_ENTRY(H, 1, 1, ACT), {0, 0, 0, 0}, {0, 0, 0, 0}}, \
-        {PINN_NARROW_ENTRY(H, 2, 0, ACT), PINN_NARROW_ENTRY(H, 2, 1, ACT), PINN_NARROW_ENTRY(H, 2, 2, ACT), {0, 0, 0, 0}}, \
+        {PINN_NARROW_ENTRY(H, 0, 0, ACT), {0, 0, 0, 0, 0}, {0, 0, 0, 0, 0}, {0, 0, 0, 0, 0}}, \
+        {PINN_NARROW_ENTRY(H, 1, 0, ACT), PINN_NARROW_ENTRY(H, 1, 1, ACT), {0, 0, 0, 0, 0}, {0, 0, 0, 0, 0}}, \
+        {PINN_NARROW_ENTRY(H, 2, 0, ACT), PINN_NARROW_ENTRY(H, 2, 1, ACT), PINN_NARROW_ENTRY(H, 2, 2, ACT), {0, 0, 0, 0, 0}}, \
         {PINN_NARROW_ENTRY(H, 3, 0, ACT), PINN_NARROW_ENTRY(H, 3, 1, ACT), PINN_NARROW_ENTRY(H, 3, 2, ACT), PINN_NARROW_ENTRY(H, 3, 3, ACT)}}; \
     if (nf < 0 || nf > 3 || ns < 0 || ns > nf) return nullptr;                   \
     return t[nf][ns].fn ? &t[nf][ns] : nullptr;                                  \

@@ -12,13 +12,17 @@
 //   * the lane's layer-input jet h[c][k] lives in registers (C*H values);
 //   * the (transposed) weights Wt[k][j] are shared by the CTA in smem and read
 //     as warp-broadcast float4 -> 4*C FMAs per LDS.128;
-//   * pre-activation jets z of layers 2..L are stashed in per-warp smem rows
-//     (row stride chosen so float4 accesses are conflict free) and are the only
-//     forward state kept for the reverse pass (activations are recomputed);
-//   * the reverse pass overwrites each z with its adjoint zbar in place;
-//   * dW_l = sum over the 32 points and C channels of zbar_l^T h_{l-1} is a
-//     small warp-local GEMM from smem in 4x4 register tiles, accumulated in a
-//     per-warp smem copy of the gradient -> no atomics, deterministic;
+//   * pre-activation jets z of layers 2..L are the only forward state kept for
+//     the reverse pass (activations are recomputed).  They are stashed in a
+//     per-warp scratch region in GLOBAL memory that every tile overwrites, so it
+//     stays L2-resident (148 CTAs x 8 warps x 30 KB = 36 MB << 126 MB L2) and
+//     costs no shared memory: 8 warps per SM instead of 4;
+//   * per warp only two smem row buffers remain: A (zbar_l, or ybar) and
+//     B (h_{l-1}), the operands of the warp-local GEMM
+//     dW_l = sum over the 32 points and C channels of zbar_l^T h_{l-1}
+//     (4x4 register tiles, accumulated in a per-warp smem copy of the
+//     gradient -> no atomics, deterministic); row stride chosen so float4
+//     accesses are conflict free;
 //   * warps never synchronise with each other inside the tile loop.
 //
 // The code below is written as per-lane "phase" functions separated by
@@ -47,6 +51,7 @@ struct NarrowParams {
   // results
   float* gpart;  // [max_cta][PP] gradient partials (padded layout, see Layout)
   float* lpart;  // [n_slots][max_cta] loss partials
+  float* stash;  // [cta][warp][(L-1)*C*H*32] pre-activation jets of layers 2..L (L2-resident scratch)
   int32_t max_cta, domain_slot;
   int32_t n_warps, n_tiles;
 };
@@ -74,18 +79,20 @@ struct NarrowWarp {
   static_assert(NS <= NF, "second-order channels need their first-order channel");
 
   // ---- per-warp shared memory carve-up (in floats) -----------------------
+  // [A: 32 rows of S][B: 32 rows of S][xs: 32 x 4][gacc: Layout]
   PINN_HD static int S() { return row_stride(C * H); }
-  PINN_HD static int YS() { return row_stride(C * 4); }
-  PINN_HD static int nbuf(int L) { return L <= 2 ? L + 1 : L; }
-  PINN_HD static int hb_index(int L) { return L - 1; }
-  PINN_HD static int x_index(int L) { return L >= 3 ? 1 : L; }
-  PINN_HD static int off_ybar(int L) { return nbuf(L) * 32 * S(); }
-  PINN_HD static int off_xs(int L) { return off_ybar(L) + 32 * YS(); }
-  PINN_HD static int off_gacc(int L) { return off_xs(L) + 32 * 4; }
-  PINN_HD static int warp_floats(int L) { return off_gacc(L) + Layout(H, L).size(); }
+  PINN_HD static int off_a() { return 0; }
+  PINN_HD static int off_b() { return 32 * S(); }
+  PINN_HD static int off_xs() { return 2 * 32 * S(); }
+  PINN_HD static int off_gacc() { return off_xs() + 32 * 4; }
+  PINN_HD static int warp_floats(int L) { return off_gacc() + Layout(H, L).size(); }
+  // per-warp global stash (floats): [(l-2)][c][k4][lane][4]
+  PINN_HD static int stash_floats(int L) { return (L - 1) * C * H * 32; }
+  PINN_HD static int stash_off(int l, int c, int k4, int lane) { return (((l - 2) * C + c) * H4 + k4) * 128 + lane * 4; }
 
-  struct Lane {      // lane-private state that survives across tiles
-    float loss;
+  struct Lane {          // lane-private state crossing phase boundaries
+    float loss;          // running un-weighted loss of this lane's points
+    float zk[C][H];      // zbar of the layer just differentiated (registers on the GPU)
   };
 
   // ---- small pieces -------------------------------------------------------
@@ -139,8 +146,7 @@ struct NarrowWarp {
 #pragma unroll
     for (int i = 0; i < NF; ++i) {
       const int d = p.jets.first_in[i];
-      // select without dynamic register indexing
-      f4 r = w[0];
+      f4 r = w[0];  // select without dynamic register indexing
       if (d == 1) r = w[1];
       if (d == 2) r = w[2];
       if (d == 3) r = w[3];
@@ -150,11 +156,11 @@ struct NarrowWarp {
     for (int s = 0; s < NS; ++s) zt[1 + NF + s] = f4{0.f, 0.f, 0.f, 0.f};
   }
 
-  PINN_HD static void load_ztile(const float* row, int k4, f4 (&zt)[C]) {
+  PINN_HD static void load_row_tile(const float* row, int k4, f4 (&t)[C]) {
 #pragma unroll
-    for (int c = 0; c < C; ++c) zt[c] = ld4(row + c * H + k4 * 4);
+    for (int c = 0; c < C; ++c) t[c] = ld4(row + c * H + k4 * 4);
   }
-  PINN_HD static void store_tile(float* row, int k4, const f4 (&t)[C]) {
+  PINN_HD static void store_row_tile(float* row, int k4, const f4 (&t)[C]) {
 #pragma unroll
     for (int c = 0; c < C; ++c) st4(row + c * H + k4 * 4, t[c]);
   }
@@ -169,26 +175,6 @@ struct NarrowWarp {
       unit_fwd(z, h);
 #pragma unroll
       for (int c = 0; c < C; ++c) hin[c][k4 * 4 + e] = h[c];
-    }
-  }
-
-  // given z tile and hbar (adjoint of the layer output) -> h tile, zbar tile
-  PINN_HD static void act_tile_bwd(const f4 (&zt)[C], int k4, const float (&hbar)[C][H], f4 (&ht)[C], f4 (&zbt)[C]) {
-#pragma unroll
-    for (int e = 0; e < 4; ++e) {
-      float z[C], hb[C], h[C], zb[C];
-#pragma unroll
-      for (int c = 0; c < C; ++c) {
-        z[c] = (&zt[c].x)[e];
-        hb[c] = hbar[c][k4 * 4 + e];
-        zb[c] = 0.f;
-      }
-      unit_bwd(z, hb, h, zb);
-#pragma unroll
-      for (int c = 0; c < C; ++c) {
-        (&ht[c].x)[e] = h[c];
-        (&zbt[c].x)[e] = zb[c];
-      }
     }
   }
 
@@ -253,11 +239,10 @@ struct NarrowWarp {
     for (int c = 0; c < C; ++c) yb[c] = f4{sg[c * 4 + 0], sg[c * 4 + 1], sg[c * 4 + 2], sg[c * 4 + 3]};
   }
 
-  // ---- phase P0: forward, residual/loss, output-layer backward ------------
-  // sw: CTA weights, wm: this warp's smem region.  Returns nothing; all state
-  // for later phases is in smem.
-  PINN_HD static void phase_forward(const NarrowParams& p, const float* sw, float* wm, int lane_id, int64_t tile,
-                                    Lane& lane) {
+  // ---- phase F: forward, residual/loss; leaves ybar in this lane's A row ----
+  // sw: CTA weights, wm: this warp's smem region, gs: this warp's global stash.
+  PINN_HD static void phase_forward(const NarrowParams& p, const float* sw, float* wm, float* gs, int lane_id,
+                                    int64_t tile, Lane& lane) {
     const int L = p.n_hidden;
     const Layout lay(H, L);
     const int s = S();
@@ -267,21 +252,19 @@ struct NarrowWarp {
 #pragma unroll
     for (int d = 0; d < 4; ++d)
       if (d < p.n_in && valid) x[d] = p.coords[d][n];
-    st4(wm + off_xs(L) + lane_id * 4, f4{x[0], x[1], x[2], x[3]});
+    st4(wm + off_xs() + lane_id * 4, f4{x[0], x[1], x[2], x[3]});
+    float* a_row = wm + off_a() + lane_id * s;
 
     float hin[C][H];
-    // hidden layer 1
 #pragma unroll
-    for (int k4 = 0; k4 < H4; ++k4) {
+    for (int k4 = 0; k4 < H4; ++k4) {  // hidden layer 1
       f4 zt[C];
       layer1_tile(sw, lay, p, x, k4, zt);
       act_tile_fwd(zt, k4, hin);
     }
-    // hidden layers 2..L
-    for (int l = 2; l <= L; ++l) {
+    for (int l = 2; l <= L; ++l) {  // hidden layers 2..L
       const float* Wt = sw + lay.wh(l);
       const float* bl = sw + lay.bh(l);
-      float* row = wm + (l - 2) * 32 * s + lane_id * s;
 #if defined(__CUDA_ARCH__)
 #pragma unroll 1
 #endif
@@ -299,12 +282,16 @@ struct NarrowWarp {
             acc[c].x += w.x * hv; acc[c].y += w.y * hv; acc[c].z += w.z * hv; acc[c].w += w.w * hv;
           }
         }
-        store_tile(row, j4, acc);
+        store_row_tile(a_row, j4, acc);  // scratch for the reload below
+        if (p.mode != MODE_FWD) {
+#pragma unroll
+          for (int c = 0; c < C; ++c) st4(gs + stash_off(l, c, j4, lane_id), acc[c]);
+        }
       }
 #pragma unroll
       for (int k4 = 0; k4 < H4; ++k4) {
         f4 zt[C];
-        load_ztile(row, k4, zt);
+        load_row_tile(a_row, k4, zt);
         act_tile_fwd(zt, k4, hin);
       }
     }
@@ -348,75 +335,98 @@ struct NarrowWarp {
         }
       }
     }
-    {
-      float* yrow = wm + off_ybar(L) + lane_id * YS();
 #pragma unroll
-      for (int c = 0; c < C; ++c) st4(yrow + c * 4, yb[c]);
-    }
-    // adjoint of h_L, then through the last activation
-    float (&hbar)[C][H] = hin;  // forward jet is dead: reuse its registers
-#pragma unroll
-    for (int k = 0; k < H; ++k) {
-      const f4 w = ld4(sw + lay.wo() + k * 4);
-#pragma unroll
-      for (int c = 0; c < C; ++c) hbar[c][k] = w.x * yb[c].x + w.y * yb[c].y + w.z * yb[c].z + w.w * yb[c].w;
-    }
-    act_backward_all(p, sw, wm, lane_id, L, hbar);
+    for (int c = 0; c < C; ++c) st4(a_row + c * 4, yb[c]);  // A row now holds ybar[c][o4]
   }
 
-  // hbar = adjoint of h_l (all units).  Reads z_l (stash, or recomputed for
-  // l == 1), writes h_l to the HB buffer and zbar_l over z_l (or to the X
-  // buffer for l == 1).
-  PINN_HD static void act_backward_all(const NarrowParams& p, const float* sw, float* wm, int lane_id, int l,
-                                       const float (&hbar)[C][H]) {
+  // ---- phase B_l (l = L+1 .. 2): adjoint through linear layer l, then through
+  // activation l-1.  Reads this lane's A row (ybar for l == L+1, zbar_l
+  // otherwise) and z_{l-1} (global stash, or recomputed for l-1 == 1); writes
+  // h_{l-1} to this lane's B row and keeps zbar_{l-1} in lane.zk. ------------
+  PINN_HD static void phase_backward(const NarrowParams& p, const float* sw, float* wm, const float* gs, int lane_id,
+                                     int l, Lane& lane) {
     const int L = p.n_hidden;
     const Layout lay(H, L);
     const int s = S();
-    float* hb_row = wm + hb_index(L) * 32 * s + lane_id * s;
-    float* z_row = (l >= 2) ? wm + (l - 2) * 32 * s + lane_id * s : wm + x_index(L) * 32 * s + lane_id * s;
+    const float* a_row = wm + off_a() + lane_id * s;
+    float* b_row = wm + off_b() + lane_id * s;
+    float hbar[C][H];
+    if (l == L + 1) {
+      f4 yb[C];
+#pragma unroll
+      for (int c = 0; c < C; ++c) yb[c] = ld4(a_row + c * 4);
+#pragma unroll
+      for (int k = 0; k < H; ++k) {
+        const f4 w = ld4(sw + lay.wo() + k * 4);
+#pragma unroll
+        for (int c = 0; c < C; ++c) hbar[c][k] = w.x * yb[c].x + w.y * yb[c].y + w.z * yb[c].z + w.w * yb[c].w;
+      }
+    } else {
+      const float* Wt = sw + lay.wh(l);
+#pragma unroll
+      for (int c = 0; c < C; ++c)
+#pragma unroll
+        for (int k = 0; k < H; ++k) hbar[c][k] = 0.f;
+#if defined(__CUDA_ARCH__)
+#pragma unroll 1
+#endif
+      for (int j4 = 0; j4 < H4; ++j4) {
+        f4 zb[C];
+        load_row_tile(a_row, j4, zb);
+#pragma unroll
+        for (int k = 0; k < H; ++k) {
+          const f4 w = ld4(Wt + k * H + j4 * 4);
+#pragma unroll
+          for (int c = 0; c < C; ++c)
+            hbar[c][k] += w.x * zb[c].x + w.y * zb[c].y + w.z * zb[c].z + w.w * zb[c].w;
+        }
+      }
+    }
+    // through activation l-1
+    const int lm = l - 1;
     float x[4];
     {
-      const f4 xv = ld4(wm + off_xs(L) + lane_id * 4);
+      const f4 xv = ld4(wm + off_xs() + lane_id * 4);
       x[0] = xv.x; x[1] = xv.y; x[2] = xv.z; x[3] = xv.w;
     }
 #pragma unroll
     for (int k4 = 0; k4 < H4; ++k4) {
-      f4 zt[C], ht[C], zbt[C];
-      if (l >= 2) load_ztile(z_row, k4, zt);
-      else layer1_tile(sw, lay, p, x, k4, zt);
-      act_tile_bwd(zt, k4, hbar, ht, zbt);
-      store_tile(hb_row, k4, ht);
-      store_tile(z_row, k4, zbt);
+      f4 zt[C], ht[C];
+      if (lm >= 2) {
+#pragma unroll
+        for (int c = 0; c < C; ++c) zt[c] = ld4(gs + stash_off(lm, c, k4, lane_id));
+      } else {
+        layer1_tile(sw, lay, p, x, k4, zt);
+      }
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        float z[C], hb[C], h[C], zb[C];
+#pragma unroll
+        for (int c = 0; c < C; ++c) {
+          z[c] = (&zt[c].x)[e];
+          hb[c] = hbar[c][k4 * 4 + e];
+          zb[c] = 0.f;
+        }
+        unit_bwd(z, hb, h, zb);
+#pragma unroll
+        for (int c = 0; c < C; ++c) {
+          (&ht[c].x)[e] = h[c];
+          lane.zk[c][k4 * 4 + e] = zb[c];
+        }
+      }
+      store_row_tile(b_row, k4, ht);
     }
   }
 
-  // ---- phase P_l (l = L..2): hbar_{l-1} = W_l^T zbar_l, then activation l-1 --
-  PINN_HD static void phase_backward_layer(const NarrowParams& p, const float* sw, float* wm, int lane_id, int l) {
-    const int L = p.n_hidden;
-    const Layout lay(H, L);
-    const int s = S();
-    const float* Wt = sw + lay.wh(l);
-    const float* zb_row = wm + (l - 2) * 32 * s + lane_id * s;
-    float hbar[C][H];
+  // after the GEMM that consumed A: A row <- zbar kept in registers
+  PINN_HD static void phase_store_zk(float* wm, int lane_id, const Lane& lane) {
+    float* a_row = wm + off_a() + lane_id * S();
 #pragma unroll
-    for (int c = 0; c < C; ++c)
+    for (int k4 = 0; k4 < H4; ++k4)
 #pragma unroll
-      for (int k = 0; k < H; ++k) hbar[c][k] = 0.f;
-#if defined(__CUDA_ARCH__)
-#pragma unroll 1
-#endif
-    for (int j4 = 0; j4 < H4; ++j4) {
-      f4 zb[C];
-      load_ztile(zb_row, j4, zb);
-#pragma unroll
-      for (int k = 0; k < H; ++k) {
-        const f4 w = ld4(Wt + k * H + j4 * 4);
-#pragma unroll
-        for (int c = 0; c < C; ++c)
-          hbar[c][k] += w.x * zb[c].x + w.y * zb[c].y + w.z * zb[c].z + w.w * zb[c].w;
-      }
-    }
-    act_backward_all(p, sw, wm, lane_id, l - 1, hbar);
+      for (int c = 0; c < C; ++c)
+        st4(a_row + c * H + k4 * 4,
+            f4{lane.zk[c][k4 * 4], lane.zk[c][k4 * 4 + 1], lane.zk[c][k4 * 4 + 2], lane.zk[c][k4 * 4 + 3]});
   }
 
   // ---- GEMM phases (cross-lane; run after __syncwarp) ----------------------
@@ -424,10 +434,10 @@ struct NarrowWarp {
   PINN_HD static void phase_gemm_out(const NarrowParams& p, float* wm, int lane_id) {
     const int L = p.n_hidden;
     const Layout lay(H, L);
-    const int s = S(), ys = YS();
-    const float* hb = wm + hb_index(L) * 32 * s;
-    const float* yb = wm + off_ybar(L);
-    float* g = wm + off_gacc(L);
+    const int s = S();
+    const float* yb = wm + off_a();
+    const float* hb = wm + off_b();
+    float* g = wm + off_gacc();
     const int T = p.n_out * H4;
     for (int t = lane_id; t < T; t += 32) {
       const int o = t / H4, kb = t % H4;
@@ -435,7 +445,7 @@ struct NarrowWarp {
       for (int n = 0; n < 32; ++n) {
 #pragma unroll
         for (int c = 0; c < C; ++c) {
-          const float a = yb[n * ys + c * 4 + o];
+          const float a = yb[n * s + c * 4 + o];
           const f4 b = ld4(hb + n * s + c * H + kb * 4);
           acc.x += a * b.x; acc.y += a * b.y; acc.z += a * b.z; acc.w += a * b.w;
         }
@@ -445,7 +455,7 @@ struct NarrowWarp {
     }
     if (lane_id < p.n_out) {
       float a = 0.f;
-      for (int n = 0; n < 32; ++n) a += yb[n * ys + lane_id];
+      for (int n = 0; n < 32; ++n) a += yb[n * s + lane_id];
       g[lay.bo() + lane_id] += a;
     }
   }
@@ -455,9 +465,9 @@ struct NarrowWarp {
     const int L = p.n_hidden;
     const Layout lay(H, L);
     const int s = S();
-    const float* A = wm + (l - 2) * 32 * s;       // zbar_l
-    const float* B = wm + hb_index(L) * 32 * s;   // h_{l-1}
-    float* g = wm + off_gacc(L);
+    const float* A = wm + off_a();  // zbar_l
+    const float* B = wm + off_b();  // h_{l-1}
+    float* g = wm + off_gacc();
     for (int t = lane_id; t < H4 * H4; t += 32) {
       const int ja = t / H4, kb = t % H4;
       f4 acc[4];  // acc[kk] = (j0..j3) for k = kb*4+kk
@@ -504,9 +514,9 @@ struct NarrowWarp {
     const int L = p.n_hidden;
     const Layout lay(H, L);
     const int s = S();
-    const float* X = wm + x_index(L) * 32 * s;  // zbar_1
-    const float* xs = wm + off_xs(L);
-    float* g = wm + off_gacc(L);
+    const float* X = wm + off_a();  // zbar_1
+    const float* xs = wm + off_xs();
+    float* g = wm + off_gacc();
     for (int j = lane_id; j < H; j += 32) {
       float ad[4] = {0.f, 0.f, 0.f, 0.f};
       float af[NF > 0 ? NF : 1];

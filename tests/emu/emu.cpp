@@ -34,16 +34,21 @@ struct RunnerT : Runner {
     for (int i = 0; i < lay.size(); ++i) smem[i] = stage_weight(p, Hreal, lay, i);
     std::vector<typename NW::Lane> lanes((size_t)n_warps * 32);
     for (auto& l : lanes) l.loss = 0.f;
+    std::vector<float> stash((size_t)n_warps * NW::stash_floats(L) + 4, 0.f);
     for (int warp = 0; warp < n_warps; ++warp) {
       float* wm = smem.data() + lay.size() + (size_t)warp * wf;
+      float* gs = stash.data() + (size_t)warp * NW::stash_floats(L);
       typename NW::Lane* ln = &lanes[(size_t)warp * 32];
       for (int64_t tile = (int64_t)cta * n_warps + warp; tile < p.n_tiles; tile += (int64_t)n_cta * n_warps) {
-        for (int lane = 0; lane < 32; ++lane) NW::phase_forward(p, smem.data(), wm, lane, tile, ln[lane]);
+        for (int lane = 0; lane < 32; ++lane) NW::phase_forward(p, smem.data(), wm, gs, lane, tile, ln[lane]);
         if (p.mode == MODE_FWD) continue;
-        for (int lane = 0; lane < 32; ++lane) NW::phase_gemm_out(p, wm, lane);
-        for (int l = L; l >= 2; --l) {
-          for (int lane = 0; lane < 32; ++lane) NW::phase_backward_layer(p, smem.data(), wm, lane, l);
-          for (int lane = 0; lane < 32; ++lane) NW::phase_gemm_hidden(p, wm, lane, l);
+        for (int l = L + 1; l >= 2; --l) {
+          for (int lane = 0; lane < 32; ++lane) NW::phase_backward(p, smem.data(), wm, gs, lane, l, ln[lane]);
+          for (int lane = 0; lane < 32; ++lane) {
+            if (l == L + 1) NW::phase_gemm_out(p, wm, lane);
+            else NW::phase_gemm_hidden(p, wm, lane, l);
+          }
+          for (int lane = 0; lane < 32; ++lane) NW::phase_store_zk(wm, lane, ln[lane]);
         }
         for (int lane = 0; lane < 32; ++lane) NW::phase_gemm_first(p, wm, lane);
       }
@@ -51,7 +56,7 @@ struct RunnerT : Runner {
     if (p.mode == MODE_FWD) return;
     for (int i = 0; i < lay.size(); ++i) {
       float s = 0.f;
-      for (int w = 0; w < n_warps; ++w) s += smem[lay.size() + (size_t)w * wf + NW::off_gacc(L) + i];
+      for (int w = 0; w < n_warps; ++w) s += smem[lay.size() + (size_t)w * wf + NW::off_gacc() + i];
       gpart_cta[i] += s;
     }
     if (p.mode == MODE_FUSED) {
