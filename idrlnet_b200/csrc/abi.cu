@@ -265,7 +265,7 @@ int pinn_step_fused(const pinn_mlp* m, const pinn_jets* j, const pinn_domain* do
     p.domain_slot = domain_slot;
     return narrow_step_common(m, j, p, ws, ws_bytes, domain_slot + 1, accumulate, st);
   }
-  if (wide_supported(m, j)) return wide_step_fused(m, j, dom, ws, ws_bytes, domain_slot, accumulate, st);
+  if (wide_supported(m, j)) return wide_step_fused(m, j, dom, ws, ws_bytes, domain_slot + 1, domain_slot, accumulate, st);
   return fail(PINN_E_UNSUPPORTED, "no fused kernel for width %d / act %d", m->width, m->act);
 }
 
@@ -298,7 +298,7 @@ int pinn_step_finalize(const pinn_mlp* m, const pinn_jets* j, void* ws, int64_t 
 }
 
 int pinn_jet_forward(const pinn_mlp* m, const pinn_jets* j, int64_t n_points, const float* const* coords, float* out,
-                     void* stream) {
+                     void* ws, int64_t ws_bytes, void* stream) {
   int rc = check_mlp(m, j);
   if (rc) return rc;
   if (!coords || !out || n_points < 0) return fail(PINN_E_INVALID, "null argument");
@@ -316,7 +316,7 @@ int pinn_jet_forward(const pinn_mlp* m, const pinn_jets* j, int64_t n_points, co
     p.jets_out = out;
     return launch_narrow(m, j, p, pl, st);
   }
-  if (wide_supported(m, j)) return wide_jet_forward(m, j, n_points, coords, out, st);
+  if (wide_supported(m, j)) return wide_jet_forward(m, j, n_points, coords, out, ws, ws_bytes, st);
   return fail(PINN_E_UNSUPPORTED, "no kernel for width %d", m->width);
 }
 

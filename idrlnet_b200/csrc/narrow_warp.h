@@ -350,7 +350,7 @@ struct NarrowWarp {
     const int s = S();
     const float* a_row = wm + off_a() + lane_id * s;
     float* b_row = wm + off_b() + lane_id * s;
-    float hbar[C][H];
+    float (&hbar)[C][H] = lane.zk;  // adjoint of h_{l-1}; overwritten in place by zbar_{l-1}
     if (l == L + 1) {
       f4 yb[C];
 #pragma unroll
@@ -411,7 +411,7 @@ struct NarrowWarp {
 #pragma unroll
         for (int c = 0; c < C; ++c) {
           (&ht[c].x)[e] = h[c];
-          lane.zk[c][k4 * 4 + e] = zb[c];
+          hbar[c][k4 * 4 + e] = zb[c];
         }
       }
       store_row_tile(b_row, k4, ht);

@@ -48,7 +48,9 @@ PINN_HD float fast_exp(float x) {
 }
 PINN_HD float fast_rcp(float x) {
 #if defined(__CUDA_ARCH__)
-  return __frcp_rn(x);
+  float r;  // MUFU.RCP, <= 1 ulp; (__frcp_rn is a multi-instruction IEEE sequence with a branch)
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
 #else
   return 1.0f / x;
 #endif

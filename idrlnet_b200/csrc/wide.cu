@@ -1,11 +1,774 @@
-// Wide-net path: placeholder until the tiled kernels land (returns "unsupported"
-// so callers take the generic torch path; never a silent CPU fallback).
+// Wide-net path (hidden width > 32; configs C/D/E: 128, 100, 512), FP32.
+//
+// Same mathematics as the narrow path (forward Taylor jets, fused residual/loss,
+// reverse pass), organised as layer-streamed kernels over chunks
+// of points, because at these widths a layer's work IS a dense contraction
+// (rows = points x jet channels, K = N = H):
+//
+//   first_fwd                Z1 = W1 x + b1 (jets), H1 = act(Z1)
+//   gemm_fwd   (l = 2..L)    Z_l = H_{l-1} W_l^T + b_l ; H_l = act(Z_l)   (act fused in the epilogue)
+//   head                     y = H_L Wout^T + bout ; residual ; loss ; ybar ;
+//                            zbar_L = act'(Z_L; Wout^T ybar) ; dWout, dbout
+//   for l = L..2:
+//     gemm_dw                dW_l  = zbar_l^T H_{l-1}            (split over points, per-split partials)
+//     reduce_cols            db_l  = column sums of zbar_l (value channel)
+//     gemm_hbar              zbar_{l-1} = act'(Z_{l-1}; zbar_l W_l)       (act' fused in the epilogue, in place)
+//   reduce_cols              dW1, db1 from zbar_1 and the coordinates
+//
+// Jets live in a chunk workspace as channel planes [C][Mc][H] (Z_l, H_l for every
+// layer of the chunk; Z_l is overwritten by zbar_l).  All reductions go through
+// per-block / per-split partial slots that are summed in a fixed order by
+// wide_finalize -> deterministic, no atomics.
+//
+// This FP32-FMA implementation is the parity path (1e-5); it keeps the tensor
+// pipe idle.  See DESIGN.md for the tcgen05 plan that replaces the three GEMMs.
+#include <cuda_runtime.h>
+#include <stdio.h>
+#include <string.h>
+
 #include "wide.cuh"
+
 namespace pinn {
-bool wide_supported(const pinn_mlp*, const pinn_jets*) { return false; }
-int64_t wide_workspace_bytes(const pinn_mlp*, const pinn_jets*, int) { return 0; }
-int wide_step_fused(const pinn_mlp*, const pinn_jets*, const pinn_domain*, void*, int64_t, int, int, cudaStream_t) { return PINN_E_UNSUPPORTED; }
-int wide_step_finalize(const pinn_mlp*, const pinn_jets*, void*, int64_t, int, float*, int, float*, cudaStream_t) { return PINN_E_UNSUPPORTED; }
-int wide_jet_forward(const pinn_mlp*, const pinn_jets*, int64_t, const float* const*, float*, cudaStream_t) { return PINN_E_UNSUPPORTED; }
-int wide_jet_backward(const pinn_mlp*, const pinn_jets*, int64_t, const float* const*, const float*, void*, int64_t, int, cudaStream_t) { return PINN_E_UNSUPPORTED; }
+
+namespace {
+
+constexpr int kMaxC = 7;
+constexpr int kBlocks = 148;         // partial slots of the per-block reductions
+constexpr int kBM = 32;              // points per GEMM tile
+constexpr int kBN = 128;             // output columns per GEMM tile
+constexpr int kBK = 16;
+constexpr int64_t kChunkBudget = 96ll << 20;  // bytes of Z/H planes per chunk
+constexpr int kMaxDomains = 64;       // loss slots
+
+struct WNet {
+  int n_in, n_out, L, H, act, C, NF, NS;
+  int first_in[4];
+  const float* W[PINN_MAX_LAYERS];
+  const float* b[PINN_MAX_LAYERS];
+};
+
+// ---- activation jets with runtime channel counts ---------------------------
+template <int ACT>
+__device__ __forceinline__ void jet_fwd(int NF, int NS, const float* z, float* h) {
+  float s0, s1, s2, s3;
+  act_derivs<ACT>(z[0], s0, s1, s2, s3);
+  h[0] = s0;
+#pragma unroll
+  for (int i = 0; i < 3; ++i)
+    if (i < NF) h[1 + i] = s1 * z[1 + i];
+#pragma unroll
+  for (int s = 0; s < 3; ++s)
+    if (s < NS) h[1 + NF + s] = s2 * z[1 + s] * z[1 + s] + s1 * z[1 + NF + s];
+}
+
+template <int ACT>
+__device__ __forceinline__ void jet_bwd(int NF, int NS, const float* z, const float* hb, float* zb) {
+  float s0, s1, s2, s3;
+  act_derivs<ACT>(z[0], s0, s1, s2, s3);
+  float zv = hb[0] * s1;
+#pragma unroll
+  for (int i = 0; i < 3; ++i)
+    if (i < NF) {
+      zv += hb[1 + i] * s2 * z[1 + i];
+      zb[1 + i] = hb[1 + i] * s1;
+    }
+#pragma unroll
+  for (int s = 0; s < 3; ++s)
+    if (s < NS) {
+      const float zi = z[1 + s], zii = z[1 + NF + s], hbs = hb[1 + NF + s];
+      zv += hbs * (s3 * zi * zi + s2 * zii);
+      zb[1 + s] += 2.0f * hbs * s2 * zi;
+      zb[1 + NF + s] = hbs * s1;
+    }
+  zb[0] = zv;
+}
+
+#define ACT_SWITCH(act, CALL)                      \
+  do {                                             \
+    if ((act) == PINN_ACT_TANH) { CALL(PINN_ACT_TANH); } \
+    else if ((act) == PINN_ACT_SILU) { CALL(PINN_ACT_SILU); } \
+    else { CALL(PINN_ACT_SIN); }                   \
+  } while (0)
+
+// ---- first layer ------------------------------------------------------------
+struct Coords {
+  const float* p[PINN_MAX_IN];
+};
+
+template <int ACT>
+__global__ void first_fwd_kernel(WNet net, Coords xs, int64_t n0, int m, int Mc, float* __restrict__ Z, float* __restrict__ Hb) {
+  const int H = net.H;
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (int64_t)m * H) return;
+  const int n = (int)(idx / H), j = (int)(idx % H);
+  float z[kMaxC], h[kMaxC];
+  float v = net.b[0][j];
+  for (int d = 0; d < net.n_in; ++d) v += net.W[0][j * net.n_in + d] * xs.p[d][n0 + n];
+  z[0] = v;
+  for (int i = 0; i < net.NF; ++i) z[1 + i] = net.W[0][j * net.n_in + net.first_in[i]];
+  for (int s = 0; s < net.NS; ++s) z[1 + net.NF + s] = 0.f;
+  jet_fwd<ACT>(net.NF, net.NS, z, h);
+  const size_t plane = (size_t)Mc * H;
+  for (int c = 0; c < net.C; ++c) {
+    Z[c * plane + (size_t)n * H + j] = z[c];
+    Hb[c * plane + (size_t)n * H + j] = h[c];
+  }
+}
+
+// ---- GEMM with per-point channel epilogue -----------------------------------
+// out[(c,n)][j] = sum_k A[(c,n)][k] * Bop(k, j):   BT = true : B is W[j][k]  (forward, out = A W^T)
+//                                                   BT = false: B is W[k][j]  (reverse, out = A W)
+// tile: 32 points x C channels rows, 128 columns; 256 threads = 16 (cols) x 16 (points);
+// thread tile: C channels x 2 points x 8 columns.
+// EPI = 0: Zout = acc + bias ; Hout = act(Zout)                 (forward layer)
+// EPI = 1: Zio  = act'(Zio; acc)   (in place: reads z, writes zbar)   (reverse layer)
+template <int C, int ACT, bool BT, int EPI>
+__global__ void __launch_bounds__(256) gemm_rows_kernel(WNet net, const float* __restrict__ A, const float* __restrict__ Wl,
+                                                        const float* __restrict__ bias, float* __restrict__ Zio,
+                                                        float* __restrict__ Hout, int m, int Mc) {
+  const int H = net.H;
+  __shared__ float As[kBK][C * kBM + 4];
+  __shared__ __align__(16) float Bs[kBK][kBN + 4];
+  const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+  const int n0 = blockIdx.x * kBM, j0 = blockIdx.y * kBN;
+  const size_t plane = (size_t)Mc * H;
+  float acc[C][2][8];
+#pragma unroll
+  for (int c = 0; c < C; ++c)
+#pragma unroll
+    for (int r = 0; r < 2; ++r)
+#pragma unroll
+      for (int t = 0; t < 8; ++t) acc[c][r][t] = 0.f;
+
+  for (int k0 = 0; k0 < H; k0 += kBK) {
+    // A tile: rows (c, p), 16 k's each, loaded as float4 along k and stored transposed
+    for (int i = tid; i < C * kBM * 4; i += 256) {
+      const int row = i >> 2, kq = (i & 3) * 4;
+      const int c = row / kBM, p = row % kBM;
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (n0 + p < m && k0 + kq < H) v = *reinterpret_cast<const float4*>(A + c * plane + (size_t)(n0 + p) * H + k0 + kq);
+      As[kq + 0][row] = v.x; As[kq + 1][row] = v.y; As[kq + 2][row] = v.z; As[kq + 3][row] = v.w;
+    }
+    if (BT) {  // B tile from W[j][k]: 128 j rows x 16 k, transposed into Bs[k][j]
+      for (int i = tid; i < kBN * 4; i += 256) {
+        const int j = i >> 2, kq = (i & 3) * 4;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (j0 + j < H && k0 + kq < H) v = *reinterpret_cast<const float4*>(Wl + (size_t)(j0 + j) * H + k0 + kq);
+        Bs[kq + 0][j] = v.x; Bs[kq + 1][j] = v.y; Bs[kq + 2][j] = v.z; Bs[kq + 3][j] = v.w;
+      }
+    } else {  // B tile from W[k][j]: 16 k rows x 128 j, direct
+      for (int i = tid; i < kBK * (kBN / 4); i += 256) {
+        const int kk = i / (kBN / 4), jq = (i % (kBN / 4)) * 4;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (k0 + kk < H && j0 + jq < H) v = *reinterpret_cast<const float4*>(Wl + (size_t)(k0 + kk) * H + j0 + jq);
+        *reinterpret_cast<float4*>(&Bs[kk][jq]) = v;
+      }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int kk = 0; kk < kBK; ++kk) {
+      const float4 b0 = *reinterpret_cast<const float4*>(&Bs[kk][tx * 8]);
+      const float4 b1 = *reinterpret_cast<const float4*>(&Bs[kk][tx * 8 + 4]);
+      const float bv[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+      for (int c = 0; c < C; ++c) {
+        const float2 a = *reinterpret_cast<const float2*>(&As[kk][c * kBM + ty * 2]);
+#pragma unroll
+        for (int t = 0; t < 8; ++t) {
+          acc[c][0][t] += a.x * bv[t];
+          acc[c][1][t] += a.y * bv[t];
+        }
+      }
+    }
+    __syncthreads();
+  }
+  // epilogue: all C channels of a (point, column) are in this thread
+#pragma unroll
+  for (int r = 0; r < 2; ++r) {
+    const int n = n0 + ty * 2 + r;
+    if (n >= m) continue;
+#pragma unroll
+    for (int tq = 0; tq < 2; ++tq) {
+      const int j = j0 + tx * 8 + tq * 4;
+      if (j >= H) continue;
+      float4 outz[C], outh[C];
+      float4 zin[C];
+      if (EPI == 1) {
+#pragma unroll
+        for (int c = 0; c < C; ++c) zin[c] = *reinterpret_cast<const float4*>(Zio + c * plane + (size_t)n * H + j);
+      }
+      float4 bj = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (EPI == 0) bj = *reinterpret_cast<const float4*>(bias + j);
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        float v[kMaxC], w[kMaxC], o[kMaxC];
+#pragma unroll
+        for (int c = 0; c < C; ++c) v[c] = acc[c][r][tq * 4 + e];
+        if (EPI == 0) {
+          v[0] += (&bj.x)[e];
+          jet_fwd<ACT>(net.NF, net.NS, v, o);
+#pragma unroll
+          for (int c = 0; c < C; ++c) {
+            (&outz[c].x)[e] = v[c];
+            (&outh[c].x)[e] = o[c];
+          }
+        } else {
+#pragma unroll
+          for (int c = 0; c < C; ++c) {
+            w[c] = (&zin[c].x)[e];
+            o[c] = 0.f;
+          }
+          jet_bwd<ACT>(net.NF, net.NS, w, v, o);
+#pragma unroll
+          for (int c = 0; c < C; ++c) (&outz[c].x)[e] = o[c];
+        }
+      }
+#pragma unroll
+      for (int c = 0; c < C; ++c) {
+        *reinterpret_cast<float4*>(Zio + c * plane + (size_t)n * H + j) = outz[c];
+        if (EPI == 0) *reinterpret_cast<float4*>(Hout + c * plane + (size_t)n * H + j) = outh[c];
+      }
+    }
+  }
+}
+
+// ---- dW_l[j][k] (+)= sum over rows (c,n) of zbar[(c,n)][j] * h[(c,n)][k] ----------
+// grid (tiles_j * tiles_k, n_splits); 128 x 128 tile, thread tile 8 x 8.
+__global__ void __launch_bounds__(256) gemm_dw_kernel(const float* __restrict__ Zb, const float* __restrict__ Hb, int H, int C,
+                                                      int m, int Mc, float* __restrict__ part, int tiles_k) {
+  __shared__ __align__(16) float As[kBK][kBN + 4];
+  __shared__ __align__(16) float Bs[kBK][kBN + 4];
+  const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+  const int j0 = (blockIdx.x / tiles_k) * kBN, k0 = (blockIdx.x % tiles_k) * kBN;
+  const int split = blockIdx.y, n_splits = gridDim.y;
+  const size_t plane = (size_t)Mc * H;
+  const int64_t rows = (int64_t)C * m;
+  int64_t per = (rows + n_splits - 1) / n_splits;
+  per = (per + kBK - 1) / kBK * kBK;
+  const int64_t r_begin = split * per, r_end = (r_begin + per < rows) ? r_begin + per : rows;
+  float acc[8][8];
+#pragma unroll
+  for (int a = 0; a < 8; ++a)
+#pragma unroll
+    for (int b = 0; b < 8; ++b) acc[a][b] = 0.f;
+  for (int64_t r0 = r_begin; r0 < r_end; r0 += kBK) {
+    for (int i = tid; i < kBK * (kBN / 4); i += 256) {
+      const int kk = i / (kBN / 4), q = (i % (kBN / 4)) * 4;
+      const int64_t r = r0 + kk;
+      float4 va = make_float4(0.f, 0.f, 0.f, 0.f), vb = va;
+      if (r < r_end) {
+        const int c = (int)(r / m), n = (int)(r % m);
+        const size_t base = c * plane + (size_t)n * H;
+        if (j0 + q < H) va = *reinterpret_cast<const float4*>(Zb + base + j0 + q);
+        if (k0 + q < H) vb = *reinterpret_cast<const float4*>(Hb + base + k0 + q);
+      }
+      *reinterpret_cast<float4*>(&As[kk][q]) = va;
+      *reinterpret_cast<float4*>(&Bs[kk][q]) = vb;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int kk = 0; kk < kBK; ++kk) {
+      const float4 a0 = *reinterpret_cast<const float4*>(&As[kk][ty * 8]);
+      const float4 a1 = *reinterpret_cast<const float4*>(&As[kk][ty * 8 + 4]);
+      const float4 b0 = *reinterpret_cast<const float4*>(&Bs[kk][tx * 8]);
+      const float4 b1 = *reinterpret_cast<const float4*>(&Bs[kk][tx * 8 + 4]);
+      const float av[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+      const float bv[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+      for (int a = 0; a < 8; ++a)
+#pragma unroll
+        for (int b = 0; b < 8; ++b) acc[a][b] += av[a] * bv[b];
+    }
+    __syncthreads();
+  }
+  float* out = part + (size_t)split * H * H;
+#pragma unroll
+  for (int a = 0; a < 8; ++a) {
+    const int j = j0 + ty * 8 + a;
+    if (j >= H) continue;
+#pragma unroll
+    for (int b = 0; b < 8; ++b) {
+      const int k = k0 + tx * 8 + b;
+      if (k < H) out[(size_t)j * H + k] += acc[a][b];
+    }
+  }
+}
+
+// ---- column reductions: part[block][slot_q][j] += sum_n src[plane_q][n][j] * (w_q ? w_q[n0+n] : 1)
+// (several terms may target the same slot, so the slot layout does not depend on the jet plan)
+struct RedSpec {
+  int nq;
+  int plane[8];
+  int slot[8];
+  const float* w[8];
+};
+__global__ void reduce_cols_kernel(const float* __restrict__ src, RedSpec rs, int H, int64_t n0, int m, int Mc,
+                                   float* __restrict__ part) {
+  const size_t plane = (size_t)Mc * H;
+  const int per = (m + gridDim.x - 1) / gridDim.x;
+  const int nb = blockIdx.x * per, ne = (nb + per < m) ? nb + per : m;
+  for (int j = threadIdx.x; j < H; j += blockDim.x) {
+    float a[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    for (int n = nb; n < ne; ++n) {
+#pragma unroll
+      for (int q = 0; q < 8; ++q)
+        if (q < rs.nq) {
+          const float v = src[rs.plane[q] * plane + (size_t)n * H + j];
+          a[q] += rs.w[q] ? v * rs.w[q][n0 + n] : v;
+        }
+    }
+    float o[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int q = 0; q < 8; ++q)
+      if (q < rs.nq) {
+#pragma unroll
+        for (int t = 0; t < 8; ++t)
+          if (rs.slot[q] == t) o[t] += a[q];
+      }
+#pragma unroll
+    for (int t = 0; t < 8; ++t)
+      if (o[t] != 0.f) part[((size_t)blockIdx.x * 8 + t) * H + j] += o[t];
+  }
+}
+
+// ---- head: output layer, residual, loss, seeds of the reverse pass --------------------
+struct HeadArgs {
+  int mode;  // MODE_*
+  pinn_domain dom;
+  Coords xs;
+  int64_t n0, n_total;
+  float* jets_out;
+  const float* jets_bar;
+  float* part;  // [block][O*H + O + 1]  (dWout, dbout, loss)
+};
+enum { W_MODE_FUSED = 0, W_MODE_FWD = 1, W_MODE_BWD = 2 };
+
+__device__ __forceinline__ void residual_loss_rt(const pinn_domain& dm, int C, int64_t n, const float* x, const float (*y)[4],
+                                                 float (*yb)[4], float& loss_acc) {
+  float sym[PINN_SYM_COUNT];
+  float sg[PINN_SYM_COORD0];
+  for (int i = 0; i < PINN_SYM_COUNT; ++i) sym[i] = 0.f;
+  for (int i = 0; i < PINN_SYM_COORD0; ++i) sg[i] = 0.f;
+  for (int c = 0; c < C; ++c)
+    for (int o = 0; o < 4; ++o) sym[c * 4 + o] = y[c][o];
+  for (int d = 0; d < 4; ++d) sym[PINN_SYM_COORD0 + d] = x[d];
+  for (int a = 0; a < dm.n_aux; ++a) sym[PINN_SYM_AUX0 + a] = dm.aux[a][n];
+  const float area = dm.area ? dm.area[n] : dm.area_const;
+  float loss = 0.f;
+  for (int e = 0; e < dm.n_eq; ++e) {
+    const pinn_equation& q = dm.eq[e];
+    float r = 0.f;
+    for (int t = q.term_begin; t < q.term_end; ++t) {
+      const pinn_term& tm = dm.terms[t];
+      float prod = tm.coef;
+      for (int f = 0; f < tm.n_fac; ++f) prod *= sym[tm.fac[f]];
+      r += prod;
+    }
+    const float tgt = q.target ? q.target[n] : q.target_const;
+    const float lam = q.lambda ? q.lambda[n] : q.lambda_const;
+    const float diff = r - tgt, w = lam * area;
+    float f0, f1;
+    if (dm.loss_kind == PINN_LOSS_SQUARE) { f0 = diff * diff; f1 = 2.0f * diff; }
+    else if (dm.loss_kind == PINN_LOSS_L1) { f0 = fabsf(diff); f1 = (diff > 0.f) ? 1.0f : ((diff < 0.f) ? -1.0f : 0.f); }
+    else { f0 = diff; f1 = 1.0f; }
+    loss += f0 * w;
+    const float g = f1 * w * dm.sigma;
+    for (int t = q.term_begin; t < q.term_end; ++t) {
+      const pinn_term& tm = dm.terms[t];
+      for (int f = 0; f < tm.n_fac; ++f) {
+        const int id = tm.fac[f];
+        if (id >= PINN_SYM_COORD0) continue;
+        float prod = tm.coef * g;
+        for (int f2 = 0; f2 < tm.n_fac; ++f2)
+          if (f2 != f) prod *= sym[tm.fac[f2]];
+        sg[id] += prod;
+      }
+    }
+  }
+  loss_acc += loss;
+  for (int c = 0; c < C; ++c)
+    for (int o = 0; o < 4; ++o) yb[c][o] = sg[c * 4 + o];
+}
+
+// one warp per point (grid-stride); lanes stride over the hidden units.  KI = ceil(H / 32).
+template <int ACT, int KI>
+__global__ void __launch_bounds__(256) head_kernel(WNet net, const __grid_constant__ HeadArgs ha, float* __restrict__ ZL,
+                                                   const float* __restrict__ HL, int m, int Mc) {
+  extern __shared__ float sm[];  // Wout[O][H], then per-warp reduction scratch
+  const int H = net.H, O = net.n_out, C = net.C;
+  float* sW = sm;
+  for (int i = threadIdx.x; i < O * H; i += blockDim.x) sW[i] = net.W[net.L][i];
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+  const size_t plane = (size_t)Mc * H;
+  float gW[4][KI];
+  float gb[4] = {0.f, 0.f, 0.f, 0.f};
+  float loss = 0.f;
+#pragma unroll
+  for (int o = 0; o < 4; ++o)
+#pragma unroll
+    for (int i = 0; i < KI; ++i) gW[o][i] = 0.f;
+  for (int n = blockIdx.x * nwarps + warp; n < m; n += gridDim.x * nwarps) {
+    const int64_t ng = ha.n0 + n;
+    // y[c][o] = sum_k Wout[o][k] h[c][k] + bout[o]
+    float y[kMaxC][4];
+    for (int c = 0; c < C; ++c) {
+      float s[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+      for (int i = 0; i < KI; ++i) {
+        const int k = lane + 32 * i;
+        if (k < H) {
+          const float h = HL[c * plane + (size_t)n * H + k];
+#pragma unroll
+          for (int o = 0; o < 4; ++o)
+            if (o < O) s[o] += sW[o * H + k] * h;
+        }
+      }
+#pragma unroll
+      for (int o = 0; o < 4; ++o) {
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) s[o] += __shfl_xor_sync(0xffffffffu, s[o], d);
+        y[c][o] = s[o] + ((c == 0 && o < O) ? net.b[net.L][o] : 0.f);
+      }
+    }
+    if (ha.mode == W_MODE_FWD) {
+      if (lane == 0)
+        for (int c = 0; c < C; ++c)
+          for (int o = 0; o < O; ++o) ha.jets_out[(int64_t)(c * O + o) * ha.n_total + ng] = y[c][o];
+      continue;
+    }
+    float yb[kMaxC][4];
+    if (ha.mode == W_MODE_FUSED) {
+      float x[4] = {0.f, 0.f, 0.f, 0.f};
+      for (int d = 0; d < net.n_in; ++d) x[d] = ha.xs.p[d][ng];
+      float l = 0.f;
+      residual_loss_rt(ha.dom, C, ng, x, y, yb, l);
+      if (lane == 0) loss += l;
+    } else {
+      for (int c = 0; c < C; ++c)
+        for (int o = 0; o < 4; ++o) yb[c][o] = (o < O) ? ha.jets_bar[(int64_t)(c * O + o) * ha.n_total + ng] : 0.f;
+    }
+    if (lane == 0)
+      for (int o = 0; o < O; ++o) gb[o] += yb[0][o];
+    // zbar_L = act'(Z_L; Wout^T ybar); dWout += ybar^T h
+#pragma unroll
+    for (int i = 0; i < KI; ++i) {
+      const int k = lane + 32 * i;
+      if (k < H) {
+        float z[kMaxC], hb[kMaxC], zb[kMaxC];
+        for (int c = 0; c < C; ++c) {
+          z[c] = ZL[c * plane + (size_t)n * H + k];
+          const float h = HL[c * plane + (size_t)n * H + k];
+          float a = 0.f;
+#pragma unroll
+          for (int o = 0; o < 4; ++o)
+            if (o < O) {
+              a += sW[o * H + k] * yb[c][o];
+              gW[o][i] += yb[c][o] * h;
+            }
+          hb[c] = a;
+          zb[c] = 0.f;
+        }
+        jet_bwd<ACT>(net.NF, net.NS, z, hb, zb);
+        for (int c = 0; c < C; ++c) ZL[c * plane + (size_t)n * H + k] = zb[c];
+      }
+    }
+  }
+  if (ha.mode == W_MODE_FWD) return;
+  // block reduction over warps (fixed order), then += into this block's partial slot
+  float* red = sm + O * H;  // [nwarps][O*H + O + 1]
+  const int stride = O * H + O + 1;
+  __syncthreads();
+#pragma unroll
+  for (int o = 0; o < 4; ++o)
+#pragma unroll
+    for (int i = 0; i < KI; ++i) {
+      const int k = lane + 32 * i;
+      if (o < O && k < H) red[warp * stride + o * H + k] = gW[o][i];
+    }
+  if (lane == 0) {
+    for (int o = 0; o < O; ++o) red[warp * stride + O * H + o] = gb[o];
+    red[warp * stride + O * H + O] = loss;
+  }
+  __syncthreads();
+  float* out = ha.part + (size_t)blockIdx.x * stride;
+  for (int i = threadIdx.x; i < stride; i += blockDim.x) {
+    float s = 0.f;
+    for (int w = 0; w < nwarps; ++w) s += red[w * stride + i];
+    out[i] += s;
+  }
+}
+
+// ---- finalize: partial slots -> flat gradient (pinn_param_count order) and losses -----------
+struct WideLayout {  // workspace offsets in floats
+  int64_t Z, Hb;            // L planes-sets each: [l][C][Mc][H]
+  int64_t dw, db, first, head, loss_slots, acc_end, total;
+  int Mc, n_splits, tiles, n_dom;
+};
+
+__global__ void wide_finalize_kernel(WNet net, const float* __restrict__ ws, WideLayout wl, int64_t n_params,
+                                     float* __restrict__ flat, int add, float* __restrict__ losses, int n_dom) {
+  const int H = net.H, L = net.L, O = net.n_out, D = net.n_in;
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n_params) {
+    int64_t r = i;
+    float s = 0.f;
+    const float* fp = ws + wl.first;
+    const int hstride = O * H + O + 1;
+    if (r < (int64_t)H * D) {  // W1[j][d]
+      const int j = (int)(r / D), d = (int)(r % D);
+      for (int b = 0; b < kBlocks; ++b) s += fp[((size_t)b * 8 + d) * H + j];
+    } else if ((r -= (int64_t)H * D) < H) {  // b1 (slot PINN_MAX_IN)
+      for (int b = 0; b < kBlocks; ++b) s += fp[((size_t)b * 8 + PINN_MAX_IN) * H + r];
+    } else {
+      r -= H;
+      bool done = false;
+      for (int l = 2; l <= L && !done; ++l) {
+        if (r < (int64_t)H * H) {
+          const float* p = ws + wl.dw + (size_t)(l - 2) * wl.n_splits * H * H;
+          for (int sp = 0; sp < wl.n_splits; ++sp) s += p[(size_t)sp * H * H + r];
+          done = true;
+        } else if ((r -= (int64_t)H * H) < H) {
+          const float* p = ws + wl.db + (size_t)(l - 2) * kBlocks * 8 * H;
+          for (int b = 0; b < kBlocks; ++b) s += p[(size_t)b * 8 * H + r];
+          done = true;
+        } else {
+          r -= H;
+        }
+      }
+      if (!done) {  // Wout[o][k], bout[o]
+        const float* p = ws + wl.head;
+        for (int b = 0; b < kBlocks; ++b) s += p[(size_t)b * hstride + r];
+      }
+    }
+    flat[i] = add ? flat[i] + s : s;
+  }
+  if (blockIdx.x == 0 && threadIdx.x < n_dom && losses) {
+    const int hstride = O * H + O + 1;
+    float s = 0.f;
+    for (int b = 0; b < kBlocks; ++b) s += ws[wl.loss_slots + (size_t)threadIdx.x * kBlocks + b];
+    (void)hstride;
+    losses[threadIdx.x] = s;
+  }
+}
+
+// move this step's head-loss (slot O*H+O of every block partial) into the per-domain loss slots
+__global__ void wide_collect_loss_kernel(float* ws, WideLayout wl, int hstride, int slot) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b < kBlocks) {
+    float* p = ws + wl.head + (size_t)b * hstride + (hstride - 1);
+    ws[wl.loss_slots + (size_t)slot * kBlocks + b] += *p;
+    *p = 0.f;
+  }
+}
+
+// ---- host side -------------------------------------------------------------------
+bool make_net(const pinn_mlp* m, const pinn_jets* j, WNet* n) {
+  if (m->width <= 32 || m->width > 512 || (m->width % 4) != 0) return false;
+  if (m->n_hidden < 1 || j->n_first > 3 || j->n_second > j->n_first) return false;
+  memset(n, 0, sizeof(*n));
+  n->n_in = m->n_in; n->n_out = m->n_out; n->L = m->n_hidden; n->H = m->width; n->act = m->act;
+  n->NF = j->n_first; n->NS = j->n_second; n->C = 1 + n->NF + n->NS;
+  for (int i = 0; i < 4; ++i) n->first_in[i] = j->first_in[i];
+  for (int l = 0; l <= m->n_hidden; ++l) { n->W[l] = m->W[l]; n->b[l] = m->b[l]; }
+  return true;
+}
+
+WideLayout make_layout(const WNet& n, int n_dom) {
+  WideLayout wl;
+  const int64_t per_point = 2ll * n.L * n.C * n.H * 4;
+  int64_t mc = kChunkBudget / per_point;
+  mc = mc / kBM * kBM;
+  if (mc < 256) mc = 256;
+  if (mc > 65536) mc = 65536;
+  wl.Mc = (int)mc;
+  wl.tiles = (n.H + kBN - 1) / kBN;
+  int ns = kBlocks / (wl.tiles * wl.tiles);
+  if (ns < 1) ns = 1;
+  wl.n_splits = ns;
+  wl.n_dom = n_dom;
+  // accumulators first: their offsets must not depend on the jet plan (domains with
+  // different channel counts accumulate into the same slots); chunk planes last.
+  int64_t off = 0;
+  const int64_t planes = (int64_t)n.L * n.C * mc * n.H;
+  wl.dw = off; off += (int64_t)(n.L - 1) * ns * n.H * n.H;
+  wl.db = off; off += (int64_t)(n.L - 1) * kBlocks * 8 * n.H;
+  wl.first = off; off += (int64_t)kBlocks * 8 * n.H;
+  wl.head = off; off += (int64_t)kBlocks * (n.n_out * n.H + n.n_out + 1);
+  wl.loss_slots = off; off += (int64_t)kMaxDomains * kBlocks;
+  off = (off + 3) / 4 * 4;
+  wl.acc_end = off;
+  wl.Z = off; off += planes;
+  wl.Hb = off; off += planes;
+  wl.total = (off + 3) / 4 * 4;
+  return wl;
+}
+
+#define CK(call)                                   \
+  do {                                             \
+    cudaError_t e_ = (call);                       \
+    if (e_ != cudaSuccess) return (int)e_;         \
+  } while (0)
+
+template <int ACT, bool BT, int EPI>
+int launch_gemm_rows(const WNet& n, const float* A, const float* Wl, const float* bias, float* Zio, float* Hout, int m, int Mc,
+                     cudaStream_t st) {
+  dim3 grid((m + kBM - 1) / kBM, (n.H + kBN - 1) / kBN);
+  switch (n.C) {
+#define CASE(Cc) case Cc: gemm_rows_kernel<Cc, ACT, BT, EPI><<<grid, 256, 0, st>>>(n, A, Wl, bias, Zio, Hout, m, Mc); break;
+    CASE(1) CASE(2) CASE(3) CASE(4) CASE(5) CASE(6) CASE(7)
+#undef CASE
+    default: return PINN_E_UNSUPPORTED;
+  }
+  count_launch(1);
+  return (int)cudaGetLastError();
+}
+
+template <int ACT>
+int run_chunks(const WNet& n, const WideLayout& wl, float* ws, int mode, const pinn_domain* dom, int64_t N,
+               const float* const* coords, float* jets_out, const float* jets_bar, cudaStream_t st) {
+  const int H = n.H, C = n.C, L = n.L;
+  const size_t planes = (size_t)C * wl.Mc * H;
+  Coords xs;
+  for (int d = 0; d < PINN_MAX_IN; ++d) xs.p[d] = d < n.n_in ? coords[d] : nullptr;
+  const int hstride = n.n_out * H + n.n_out + 1;
+  for (int64_t n0 = 0; n0 < N; n0 += wl.Mc) {
+    const int m = (int)((N - n0 < wl.Mc) ? N - n0 : wl.Mc);
+    float* Z = ws + wl.Z;
+    float* Hb = ws + wl.Hb;
+    {
+      const int64_t tot = (int64_t)m * H;
+      first_fwd_kernel<ACT><<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(n, xs, n0, m, wl.Mc, Z, Hb);
+      count_launch(1);
+    }
+    for (int l = 2; l <= L; ++l) {
+      int rc = launch_gemm_rows<ACT, true, 0>(n, Hb + (l - 2) * planes, n.W[l - 1], n.b[l - 1], Z + (l - 1) * planes,
+                                              Hb + (l - 1) * planes, m, wl.Mc, st);
+      if (rc) return rc;
+    }
+    {
+      HeadArgs ha;
+      memset(&ha, 0, sizeof(ha));
+      ha.mode = mode;
+      if (dom) ha.dom = *dom;
+      ha.xs = xs;
+      ha.n0 = n0;
+      ha.n_total = N;
+      ha.jets_out = jets_out;
+      ha.jets_bar = jets_bar;
+      ha.part = ws + wl.head;
+      const int nwarps = 8;
+      const size_t smem = ((size_t)n.n_out * H + (size_t)nwarps * hstride) * 4;
+      int blocks = (m + nwarps - 1) / nwarps;
+      if (blocks > kBlocks) blocks = kBlocks;
+      if (H <= 128) {
+        CK(cudaFuncSetAttribute((const void*)head_kernel<ACT, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        head_kernel<ACT, 4><<<blocks, nwarps * 32, smem, st>>>(n, ha, Z + (L - 1) * planes, Hb + (L - 1) * planes, m, wl.Mc);
+      } else {
+        CK(cudaFuncSetAttribute((const void*)head_kernel<ACT, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        head_kernel<ACT, 16><<<blocks, nwarps * 32, smem, st>>>(n, ha, Z + (L - 1) * planes, Hb + (L - 1) * planes, m, wl.Mc);
+      }
+      count_launch(1);
+      CK(cudaGetLastError());
+    }
+    if (mode == W_MODE_FWD) continue;
+    for (int l = L; l >= 2; --l) {
+      float* zb = Z + (l - 1) * planes;        // zbar_l (in place of Z_l)
+      const float* hprev = Hb + (l - 2) * planes;
+      {
+        dim3 grid(wl.tiles * wl.tiles, wl.n_splits);
+        gemm_dw_kernel<<<grid, 256, 0, st>>>(zb, hprev, H, C, m, wl.Mc, ws + wl.dw + (size_t)(l - 2) * wl.n_splits * H * H, wl.tiles);
+        count_launch(1);
+        RedSpec rs;
+        memset(&rs, 0, sizeof(rs));
+        rs.nq = 1;
+        reduce_cols_kernel<<<kBlocks, 128, 0, st>>>(zb, rs, H, n0, m, wl.Mc, ws + wl.db + (size_t)(l - 2) * kBlocks * 8 * H);
+        count_launch(1);
+      }
+      int rc = launch_gemm_rows<ACT, false, 1>(n, zb, n.W[l - 1], nullptr, Z + (l - 2) * planes, nullptr, m, wl.Mc, st);
+      if (rc) return rc;
+    }
+    {
+      RedSpec rs;
+      memset(&rs, 0, sizeof(rs));
+      int q = 0;
+      for (int d = 0; d < n.n_in; ++d) { rs.plane[q] = 0; rs.w[q] = coords[d]; rs.slot[q] = d; ++q; }
+      rs.plane[q] = 0; rs.w[q] = nullptr; rs.slot[q] = PINN_MAX_IN; ++q;  // db1
+      for (int i = 0; i < n.NF; ++i) { rs.plane[q] = 1 + i; rs.w[q] = nullptr; rs.slot[q] = n.first_in[i]; ++q; }
+      rs.nq = q;
+      reduce_cols_kernel<<<kBlocks, 128, 0, st>>>(Z, rs, H, n0, m, wl.Mc, ws + wl.first);
+      count_launch(1);
+      CK(cudaGetLastError());
+    }
+  }
+  return 0;
+}
+
+int run_mode(const pinn_mlp* m, const pinn_jets* j, int mode, const pinn_domain* dom, int64_t N, const float* const* coords,
+             float* jets_out, const float* jets_bar, void* ws, int64_t ws_bytes, int n_slots, int slot, int accumulate,
+             cudaStream_t st) {
+  WNet n;
+  if (!make_net(m, j, &n)) return PINN_E_UNSUPPORTED;
+  if (n.n_in + 1 + n.NF > 8 || n_slots > kMaxDomains) return PINN_E_UNSUPPORTED;
+  const WideLayout wl = make_layout(n, n_slots);
+  if (!ws || ws_bytes < wl.total * 4) return PINN_E_WORKSPACE;
+  float* w = (float*)ws;
+  if (!accumulate && mode != W_MODE_FWD)  // clear every partial slot (all domains' loss slots included)
+    CK(cudaMemsetAsync(w + wl.dw, 0, (size_t)(wl.acc_end - wl.dw) * 4, st));
+  int rc = 0;
+#define RUN(A) rc = run_chunks<A>(n, wl, w, mode, dom, N, coords, jets_out, jets_bar, st)
+  ACT_SWITCH(n.act, RUN);
+#undef RUN
+  if (rc) return rc;
+  if (mode == W_MODE_FUSED) {
+    wide_collect_loss_kernel<<<1, 256, 0, st>>>(w, wl, n.n_out * n.H + n.n_out + 1, slot);
+    count_launch(1);
+  }
+  return (int)cudaGetLastError();
+}
+
+}  // namespace
+
+bool wide_supported(const pinn_mlp* m, const pinn_jets* j) {
+  WNet n;
+  return make_net(m, j, &n) && (n.n_in + 1 + n.NF <= 8);
+}
+
+int64_t wide_workspace_bytes(const pinn_mlp* m, const pinn_jets* j, int n_domains) {
+  WNet n;
+  if (!make_net(m, j, &n)) return 0;
+  return make_layout(n, n_domains).total * 4;
+}
+
+int wide_step_fused(const pinn_mlp* m, const pinn_jets* j, const pinn_domain* dom, void* ws, int64_t ws_bytes, int n_slots,
+                    int domain_slot, int accumulate, cudaStream_t st) {
+  const float* coords[PINN_MAX_IN];
+  for (int d = 0; d < PINN_MAX_IN; ++d) coords[d] = dom->coords[d];
+  return run_mode(m, j, W_MODE_FUSED, dom, dom->n_points, coords, nullptr, nullptr, ws, ws_bytes, n_slots, domain_slot,
+                  accumulate, st);
+}
+
+int wide_step_finalize(const pinn_mlp* m, const pinn_jets* j, void* ws, int64_t ws_bytes, int n_domains, float* flat_grad,
+                       int add_to_grad, float* losses, cudaStream_t st) {
+  WNet n;
+  if (!make_net(m, j, &n)) return PINN_E_UNSUPPORTED;
+  const WideLayout wl = make_layout(n, n_domains);
+  if (!ws || ws_bytes < wl.total * 4) return PINN_E_WORKSPACE;
+  const int64_t np = pinn_param_count(m);
+  wide_finalize_kernel<<<(unsigned)((np + 255) / 256), 256, 0, st>>>(n, (const float*)ws, wl, np, flat_grad, add_to_grad, losses,
+                                                                     n_domains);
+  count_launch(1);
+  return (int)cudaGetLastError();
+}
+
+int wide_jet_forward(const pinn_mlp* m, const pinn_jets* j, int64_t n_points, const float* const* coords, float* out, void* ws,
+                     int64_t ws_bytes, cudaStream_t st) {
+  return run_mode(m, j, W_MODE_FWD, nullptr, n_points, coords, out, nullptr, ws, ws_bytes, 1, 0, 0, st);
+}
+
+int wide_jet_backward(const pinn_mlp* m, const pinn_jets* j, int64_t n_points, const float* const* coords, const float* out_bar,
+                      void* ws, int64_t ws_bytes, int accumulate, cudaStream_t st) {
+  return run_mode(m, j, W_MODE_BWD, nullptr, n_points, coords, nullptr, out_bar, ws, ws_bytes, 1, 0, accumulate, st);
+}
+
 }  // namespace pinn

@@ -189,8 +189,10 @@ class JetFunction(torch.autograd.Function):
                           [t.data_ptr() for t in wbc[0::2]], [t.data_ptr() for t in wbc[1::2]])
         jets = nv.make_jets(plan.first_in, plan.n_second)
         out = torch.empty(plan.n_channels * Ws[-1].shape[0], n, device=cols[0].device, dtype=torch.float32)
+        ws_bytes = lib.pinn_workspace_bytes(C.byref(mlp), C.byref(jets), 1)
+        ws = torch.empty(max(ws_bytes // 4, 1), device=cols[0].device, dtype=torch.float32)
         nv.check(lib.pinn_jet_forward(C.byref(mlp), C.byref(jets), n, nv.ptr_array([c.data_ptr() for c in cols]),
-                                      out.data_ptr(), _stream_ptr()))
+                                      out.data_ptr(), ws.data_ptr(), ws_bytes, _stream_ptr()))
         ctx.plan, ctx.act, ctx.cols, ctx.wbc = plan, act, cols, wbc
         return out
 

@@ -94,7 +94,7 @@ _SIGNATURES = {
     "pinn_step_finalize": (C.c_int, [C.POINTER(PinnMlp), C.POINTER(PinnJets), C.c_void_p, C.c_int64, C.c_int32,
                                      C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]),
     "pinn_jet_forward": (C.c_int, [C.POINTER(PinnMlp), C.POINTER(PinnJets), C.c_int64, C.POINTER(_fp), C.c_void_p,
-                                   C.c_void_p]),
+                                   C.c_void_p, C.c_int64, C.c_void_p]),
     "pinn_jet_backward": (C.c_int, [C.POINTER(PinnMlp), C.POINTER(PinnJets), C.c_int64, C.POINTER(_fp), C.c_void_p,
                                     C.c_void_p, C.c_int64, C.c_int32, C.c_void_p]),
     "pinn_weight_norm_forward": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p]),

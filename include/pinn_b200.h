@@ -160,9 +160,12 @@ PINN_API int pinn_step_finalize(const pinn_mlp* mlp, const pinn_jets* jets, void
 /* Jets only: out[(c*n_out + o)*N + n] = channel c of output o at point n.
  * Replaces WrapEvaluate + Variables.differentiate_ for names such as u__x__x
  * when the residual is not a polynomial (idrlnet/graph.py:172-175), and serves
- * Solver.infer_step (idrlnet/solver.py:410-420). */
+ * Solver.infer_step (idrlnet/solver.py:410-420).  `coords` is a HOST array of
+ * n_in device pointers.  `workspace` (pinn_workspace_bytes(mlp, jets, 1)) is
+ * needed by the wide path only and may be NULL for narrow nets. */
 PINN_API int pinn_jet_forward(const pinn_mlp* mlp, const pinn_jets* jets, int64_t n_points,
-                     const float* const* coords, float* out, void* stream);
+                     const float* const* coords, float* out, void* workspace,
+                     int64_t workspace_bytes, void* stream);
 
 /* Reverse pass for caller-supplied adjoints out_bar (same layout as `out`):
  * gradient partials into workspace as pinn_step_fused does. */

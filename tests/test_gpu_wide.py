@@ -1,0 +1,143 @@
+"""GPU parity of the wide (H > 32) layer-streamed FP32 path, through the C ABI,
+against the CPU oracle and the golden vectors produced by the reference."""
+import copy
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import pinn_oracle as po
+from tests import golden_util as gu
+from tests import problem_util as pu
+from tests.test_emu_narrow import TOL, _check_grads
+
+pytestmark = pytest.mark.gpu
+
+
+def _compare_cuda(problem, tol=TOL):
+    ref = po.training_step(problem, dtype=torch.float64)
+    grads, losses, skipped, modules = pu.run_cuda_fused(problem)
+    assert not skipped, skipped
+    for dname, l in losses.items():
+        r = ref["loss_components"][dname]
+        assert abs(l - r) <= 10 * tol * max(abs(r), 1e-30), (dname, l, r)
+    _check_grads(ref, grads, problem, tol)
+    return ref, grads, losses, modules
+
+
+def _without(problem, names):
+    p = dict(problem)
+    p["domains"] = [d for d in problem["domains"] if d["name"] not in names]
+    return p
+
+
+def test_golden_ldc():
+    """examples/ldc: tanh 2-100x4-3, Navier-Stokes residuals with lambda=sdf."""
+    problem, flat = gu.load("ldc")
+    ref, grads, losses, modules = _compare_cuda(problem)
+    for k, v in gu.ref_components(flat, "ref32").items():
+        assert abs(losses[k[:-5]] - v) <= 1e-4 * abs(v)
+    for pname, g in gu.ref_grads(flat, "ref64").items():
+        net, rest = pname.split("/", 1)
+        p = dict(modules[net].named_parameters())[rest]
+        scale = max(np.max(np.abs(g)), 1e-30)
+        err = np.max(np.abs(p.grad.detach().cpu().numpy().reshape(g.shape) - g)) / scale
+        assert err <= 20 * TOL, (pname, err)
+
+
+def test_golden_allen_cahn_fusable_domains():
+    """examples/allen_cahn: tanh 2-128x4-2 weight-norm; the periodic-BC domain uses two
+    net evaluations per point and is not fusable (it runs on the generic path)."""
+    problem, flat = gu.load("allen_cahn")
+    from idrlnet_b200 import compiler as cp
+    with pytest.raises(cp.NotFusable):
+        pu.compile_problem_domain(problem, next(d for d in problem["domains"] if d["name"] == "AllenBc"))
+    _compare_cuda(_without(problem, ["AllenBc"]))
+
+
+def test_golden_ns_unsteady_wide():
+    """Arch.mlp_xl recipe (SiLU + weight-norm) at width 64, L1 data loss + NS residuals."""
+    problem, _ = gu.load("ns_unsteady_wide")
+    _compare_cuda(problem)
+
+
+WIDE_SHAPES = [
+    # (inputs, outputs, equation, act, width, n_hidden, n_points)
+    (("x", "y"), ("u", "v", "p"), "p__x + u*u__x + v*u__y - 0.01*u__x__x - 0.01*u__y__y", "tanh", 100, 4, 300),
+    (("x", "t"), ("u",), "5*u**3 - 5*u + u__t - 0.0001*u__x__x", "tanh", 128, 4, 257),
+    (("x", "y", "t"), ("u", "v", "p"), "u__t + p__y + u*v__x + v*v__y - 0.01*v__x__x - 0.01*v__y__y", "silu", 512, 2, 130),
+    (("x", "y"), ("T",), "normal_x*T__x + normal_y*T__y", "sin", 36, 3, 64),
+    (("x",), ("u",), "u", "silu", 64, 1, 33),
+    (("x", "y", "t"), ("u",), "u__x__x + u__y__y + u__t__t - x*y*u", "tanh", 256, 2, 100),
+    (("x", "y", "t"), ("u", "v"), "u__x + v__y + u__t", "silu", 40, 5, 1000),
+]
+
+
+@pytest.mark.parametrize("case", range(len(WIDE_SHAPES)))
+def test_random_wide_problems(case):
+    inputs, outputs, eq, act, width, n_hidden, n = WIDE_SHAPES[case]
+    rng = np.random.default_rng(200 + case)
+    problem = pu.random_problem(rng, n_in=len(inputs), n_out=len(outputs), width=width, n_hidden=n_hidden, act=act,
+                                n_points=n, equation=eq, inputs=inputs, outputs=outputs,
+                                weight_norm=(case % 2 == 0), with_lambda=(case % 3 == 0), sigma=1.0 + 0.5 * case,
+                                target=0.25 if case % 2 else 0.0)
+    if "normal_x" in eq:
+        d = problem["domains"][0]
+        d["points"]["normal_x"] = rng.standard_normal((n, 1)).astype(np.float32)
+        d["points"]["normal_y"] = rng.standard_normal((n, 1)).astype(np.float32)
+    _compare_cuda(problem)
+
+
+def test_multi_chunk_accumulation():
+    """More points than one workspace chunk holds (512 wide, 7 channels): the per-chunk
+    partial slots must add up to the one-shot oracle gradient."""
+    rng = np.random.default_rng(9)
+    problem = pu.random_problem(rng, n_in=3, n_out=1, inputs=("x", "y", "t"), outputs=("u",), width=512, n_hidden=2,
+                                act="tanh", n_points=4100, equation="u__x__x + u__y__y + u__t__t + u*u__x")
+    _compare_cuda(problem)
+
+
+def test_two_domains_share_the_net():
+    rng = np.random.default_rng(10)
+    problem = pu.random_problem(rng, n_in=2, n_out=2, inputs=("x", "y"), outputs=("u", "v"), width=100, n_hidden=3,
+                                act="tanh", n_points=200, equation="u__x + v__y")
+    d2 = copy.deepcopy(problem["domains"][0])
+    d2["name"] = "wall"
+    d2["targets"] = {"u": 1.0, "v": 0.0}
+    d2["lambdas"] = {}
+    d2["sigma"] = 3.0
+    problem["domains"].append(d2)
+    _compare_cuda(problem)
+
+
+def test_wide_jet_function():
+    from idrlnet_b200 import compiler as cp
+    from idrlnet_b200 import fused
+    rng = np.random.default_rng(6)
+    problem = pu.random_problem(rng, n_in=2, n_out=3, inputs=("x", "y"), outputs=("u", "v", "p"), n_points=333,
+                                width=100, n_hidden=2, act="tanh", equation="exp(u)*v__x + p__y + u__y__y*v__x__x")
+    want = ["u", "v", "p", "u__x", "u__y", "v__x", "p__y", "u__y__y", "v__x__x", "u__x__x", "v__y__y"]
+    ref = po.training_step(problem, dtype=torch.float64, want={"dom": want})
+    mod = pu.torch_module_from_net(problem["nets"][0], "cuda:0")
+    pack = fused.NetPack(mod, act="tanh")
+    plan = cp.plan_jets(("x", "y"), [tuple(w.split("__")[1:]) for w in want])
+    cols = {k: torch.as_tensor(v, device="cuda:0").reshape(-1) for k, v in pu.domain_columns(problem["domains"][0]).items()}
+    wb = [t for i in range(len(pack.layers)) for t in pack.raw_params(i)]
+    jets = fused.jet_mlp(plan, "tanh", [cols["x"], cols["y"]], wb)
+    sym = {}
+    for c, dn in enumerate(plan.channel_names(("x", "y"))):
+        for o, on in enumerate(("u", "v", "p")):
+            sym["__".join((on,) + dn)] = jets[c * 3 + o]
+    for w in want:
+        r = ref["domains"]["dom"][w].reshape(-1)
+        err = np.max(np.abs(sym[w].detach().cpu().numpy() - r)) / max(np.max(np.abs(r)), 1e-30)
+        assert err <= TOL, (w, err)
+    res = torch.exp(sym["u"]) * sym["v__x"] + sym["p__y"] + sym["u__y__y"] * sym["v__x__x"]
+    loss = torch.sum(res ** 2 * cols["area"])
+    loss.backward()
+    assert abs(float(loss.detach()) - ref["loss"]) <= 1e-4 * abs(ref["loss"])
+    parts = pu.flat_grad_from_oracle(ref, "net")
+    scale = max(np.max(np.abs(p)) for p in parts if p is not None)
+    for g, p in zip([p.grad for p in wb], parts):
+        err = np.max(np.abs(g.detach().cpu().numpy().ravel() - p)) / max(np.max(np.abs(p)), 1e-3 * scale)
+        assert err <= 20 * TOL, err
