@@ -1,4 +1,4 @@
-"""Short run of the bench workload (Burgers, 2^20 interior points) for ncu captures."""
+"""Short run of a bench workload (default Burgers, 2^20 interior points) for ncu captures."""
 import os
 import sys
 
@@ -9,13 +9,14 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import bench  # noqa: E402
 
 steps = int(sys.argv[1]) if len(sys.argv) > 1 else 4
+config = sys.argv[2] if len(sys.argv) > 2 else "burgers"
 torch.cuda.set_device(0)
 dev = torch.device("cuda:0")
-tr = bench.BurgersTrainer(dev)
+tr = bench.Trainer(bench.workload_configs()[config], dev)
 rng = np.random.default_rng(0)
 for _ in range(2):
-    hb = bench.make_batch_host(rng, bench.N_INTERIOR, bench.N_IC, bench.N_BC)
-    tr.bind_set({k: torch.as_tensor(hb[k], device=dev) for k in bench.BATCH_KEYS})
+    hb = tr.sample_host(rng)
+    tr.bind_set({k: torch.as_tensor(v, device=dev) for k, v in hb.items()})
 for i in range(steps):
     loss = tr.step(i % 2)
 torch.cuda.synchronize()
