@@ -231,3 +231,66 @@ def run_cuda_fused(problem, device="cuda:0"):
         for d, l in zip(doms, eng.losses.detach().cpu().numpy()):
             losses[d.name] = float(l)
     return grads, losses, skipped, modules
+
+
+# --------------------------------------------------------------------------- #
+# Solver-level helpers
+# --------------------------------------------------------------------------- #
+def solver_from_problem(problem, network_dir, device=None, **solver_kw):
+    """Build an idrlnet_b200 Solver (public API) from an oracle-format problem with FIXED points."""
+    import sympy
+    import torch
+    import idrlnet_b200.shortcut as sc
+    nodes, modules = [], {}
+    for n in problem["nets"]:
+        if n.get("shares"):
+            src = next(m for m in nodes if m.name == n["shares"])
+            nodes.append(sc.get_shared_net_node(src, inputs=tuple(n["inputs"]), outputs=tuple(n["outputs"]), name=n["name"]))
+            continue
+        mod = torch_module_from_net(n, "cpu")
+        modules[n["name"]] = mod
+        nodes.append(sc.NetNode(inputs=tuple(n["inputs"]), outputs=tuple(n["outputs"]), net=mod, name=n["name"]))
+    pdes = [sc.ExpressionNode(expression=sympy.sympify(e), name=k) for k, e in problem.get("exprs", {}).items()]
+    doms = []
+    for d in problem["domains"]:
+        pts = {k: np.asarray(v, np.float32) for k, v in d["points"].items()}
+        cons = {k: (np.asarray(v, np.float32) if np.ndim(v) else float(v)) for k, v in d["targets"].items()}
+        for k, v in d.get("lambdas", {}).items():
+            cons["lambda_" + k] = np.asarray(v, np.float32) if np.ndim(v) else float(v)
+        doms.append(sc.get_data_node((lambda p=pts, c=cons: (dict(p), dict(c))), name=d["name"],
+                                     loss_fn=d.get("loss", "square"), sigma=float(d.get("sigma", 1.0))))
+    s = sc.Solver(sample_domains=tuple(doms), netnodes=nodes, pdes=pdes, network_dir=str(network_dir), loading=False,
+                  **solver_kw)
+    return s, modules
+
+
+def oracle_train(problem, steps, lr=1e-3, gamma=0.95 ** 0.001):
+    """The reference training loop on the oracle (CPU, FP32): Adam + ExponentialLR
+    (idrlnet/optim.py:70-80), fixed points; returns the per-step (pre-update) losses."""
+    import torch
+    from oracle import pinn_oracle as po
+    nets = po.build_nets(problem)
+    owners = [n for n in nets if not n.get("shares")]
+    leaves = [t for n in owners for lay in n["raw"] for t in lay.values()]
+    opt = torch.optim.Adam(leaves, lr=lr)
+    losses = []
+    for step in range(steps):
+        opt.zero_grad()
+        for n in owners:
+            n["layers_t"][:] = [((torch._weight_norm(l["v"], l["g"], 0) if "g" in l else l["W"]), l["b"]) for l in n["raw"]]
+        total = 0.0
+        for dom in problem["domains"]:
+            var = po.forward_domain(problem, dom, nets)
+            like = next(iter(var.values()))
+            diff = {k: var[k] - po._as_t(t, torch.float32, like) for k, t in dom["targets"].items()}
+            lam = {k: po._as_t(t, torch.float32, like) for k, t in dom.get("lambdas", {}).items()}
+            for k in dom["targets"]:
+                if k not in lam and ("lambda_" + k) in dom["points"]:
+                    lam[k] = po._as_t(dom["points"]["lambda_" + k], torch.float32, like)
+            total = total + float(dom.get("sigma", 1.0)) * po.weighted_loss(diff, lam, var["area"], dom.get("loss", "square"))
+        total.backward()
+        opt.step()
+        for g in opt.param_groups:
+            g["lr"] = lr * gamma ** (step + 1)
+        losses.append(float(total.detach()))
+    return losses

@@ -1,0 +1,73 @@
+"""The public API on the GPU: Solver built from the reference's configurations runs the
+fused kernels, matches the oracle on one step, and tracks the reference training loop
+(oracle + Adam + ExponentialLR) over 1k steps."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import pinn_oracle as po
+from tests import golden_util as gu
+from tests import problem_util as pu
+
+pytestmark = pytest.mark.gpu
+
+
+def _param_grads_vs_golden(modules, flat, tol):
+    for pname, g in gu.ref_grads(flat, "ref64").items():
+        net, rest = pname.split("/", 1)
+        p = dict(modules[net].named_parameters())[rest]
+        err = np.max(np.abs(p.grad.detach().cpu().numpy().reshape(g.shape) - g)) / max(np.max(np.abs(g)), 1e-30)
+        assert err <= tol, (pname, err)
+
+
+@pytest.mark.parametrize("name,n_fused", [("simple_poisson", 3), ("burgers", 3), ("ldc", 3), ("ns_unsteady", 2)])
+def test_solver_step_matches_reference(name, n_fused, tmp_path):
+    problem, flat = gu.load(name)
+    s, modules = pu.solver_from_problem(problem, tmp_path)
+    assert len(s._fused_domains) == n_fused  # every domain runs the fused kernels
+    s.optimizers[0].zero_grad()
+    loss = float(s._loss_and_grads())
+    ref = float(flat["ref64/loss"])
+    assert abs(loss - ref) <= 1e-5 * abs(ref)
+    for k, v in gu.ref_components(flat, "ref64").items():
+        assert abs(float(s.loss_component[k]) - v) <= 1e-5 * max(abs(v), 1e-12), k
+    _param_grads_vs_golden(modules, flat, 2e-4)
+
+
+def test_solver_mixed_fused_and_generic_allen_cahn(tmp_path):
+    """Allen-Cahn: interior / IC / resampling domains fused; the periodic-BC domain (two
+    evaluations of a shared net, ExpressionNodes, Difference) on the generic graph with the
+    jets served by the kernel (no autograd.grad w.r.t. coordinates)."""
+    problem, flat = gu.load("allen_cahn")
+    s, modules = pu.solver_from_problem(problem, tmp_path)
+    assert sorted(s._fused_domains) == ["AllenInit", "allen_domain", "re_sampling_domain"]
+    assert len(s.vertex_pipelines["AllenBc"]._jet_plans) == 2  # net1 and the shared net2 serve jets
+    s.optimizers[0].zero_grad()
+    loss = float(s._loss_and_grads())
+    ref = float(flat["ref64/loss"])
+    assert abs(loss - ref) <= 1e-5 * abs(ref)
+    _param_grads_vs_golden(modules, flat, 2e-4)
+
+
+@pytest.mark.parametrize("name,steps,tol", [("simple_poisson", 1000, 2e-4), ("ldc", 300, 2e-4)])
+def test_loss_curve_tracks_reference_training(name, steps, tol, tmp_path):
+    problem, _ = gu.load(name)
+    ref_losses = pu.oracle_train(problem, steps)
+    s, _ = pu.solver_from_problem(problem, tmp_path, max_iter=steps, save_freq=10 ** 9, print_freq=10 ** 9)
+    ours = []
+    for _ in range(steps):
+        ours.append(s.train_pipe())
+    ours = torch.stack([l.reshape(()) for l in ours]).cpu().numpy()
+    rel = np.abs(ours - np.asarray(ref_losses)) / np.abs(ref_losses)
+    assert ours[-1] < ours[0]
+    assert rel.max() <= tol, (int(rel.argmax()), float(rel.max()), ours[:3], ref_losses[:3])
+
+
+def test_infer_step_serves_derivatives(tmp_path):
+    problem, flat = gu.load("burgers")
+    s, _ = pu.solver_from_problem(problem, tmp_path)
+    out = s.infer_step({"burgers_equation": ["x", "t", "u", "u__x", "u__x__x", "burgers_u"]})
+    ref = gu.ref_domain(flat, "ref64", "burgers_equation")
+    for k in ("u", "u__x", "u__x__x", "burgers_u"):
+        got = out["burgers_equation"][k].detach().cpu().numpy()
+        assert gu.normwise(got, ref[k]) <= 1e-5, k
