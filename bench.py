@@ -174,7 +174,7 @@ class Trainer:
     """A workload wired through the package's public pieces: get_net_node / MLP,
     the PDE nodes, the residual compiler and the fused StepEngine + torch Adam."""
 
-    def __init__(self, cfg, device, world=1, sizes=None):
+    def __init__(self, cfg, device, world=1, sizes=None, precision="fp32"):
         from idrlnet_b200 import compiler as cp
         from idrlnet_b200 import fused
         self.cfg, self.device, self.world, self.fused = cfg, device, world, fused
@@ -192,7 +192,7 @@ class Trainer:
         for dom in cfg["domains"]:
             name, _, cols, targets = dom[0], dom[1], dom[2], dom[3]
             self.compiled.append(cp.compile_domain(list(targets), exprs, spec, list(cols) + ["area"]))
-        self.pack = fused.NetPack(self.net.net)
+        self.pack = fused.NetPack(self.net.net, precision=precision)
         self.opt = torch.optim.Adam(list(self.net.net.parameters()), lr=1e-3, fused=True)
         self.sched = torch.optim.lr_scheduler.ExponentialLR(self.opt, gamma=math.pow(0.95, 0.001))
         self.engine, self.sets = None, []
@@ -451,7 +451,8 @@ def run_ours(args):
 
     cfg = workload_configs()[args.config]
     sizes = scaled_sizes(cfg, args.sample) if args.sample else None
-    trainer = Trainer(cfg, device, world=world, sizes=sizes)
+    trainer = Trainer(cfg, device, world=world, sizes=sizes, precision=args.precision)
+    wide_tc = args.precision == "tf32" and trainer.pack.width > 32
     rng = np.random.default_rng(1000 + rank)
     pts_per_step = trainer.points_per_step
     n_timed = trainer.sizes[cfg["domains"][cfg["timed"]][1]]
@@ -560,7 +561,7 @@ def run_ours(args):
         line = {
             "metric": METRIC, "value": value, "unit": "points/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "vs_baseline": None, "dtype": "tf32" if wide_tc else "f32", "data": "synthetic",
             "config": {"workload": f"{cfg['title']}: {' + '.join(str(trainer.sizes[d[1]]) for d in cfg['domains'])} "
                                    f"points per step per GPU ({', '.join(d[0] for d in cfg['domains'])})",
                        "net": f"{cfg['net_desc']}, Adam 1e-3 + ExponentialLR",
@@ -568,7 +569,8 @@ def run_ours(args):
                        "l2": f"{n_rotate} rotating point batches ({n_rotate * batch_bytes / 1e6:.0f} MB > 126 MB L2)"},
             "roofline": {"bound": cfg["bound"], "achieved": achieved, "peak": fp32_peak, "unit": "TFLOP/s",
                          "frac": achieved / fp32_peak if fp32_peak else None, "traffic": ncu_traffic(args.config),
-                         "kernel": cfg["kernel"], "kernel_ms": kern_ms, "flop_per_point": cfg["flop_per_point"],
+                         "kernel": ("tcgen05 TF32 tc_rows/tc_dw kernels (interior domain)" if wide_tc else cfg["kernel"]),
+                         "kernel_ms": kern_ms, "flop_per_point": cfg["flop_per_point"],
                          "peak_source": "FP32 FMA pipe, pinn_fp32_fma_probe measured in this run",
                          "hbm": {"achieved": hbm_achieved, "peak": hbm_peak, "unit": "GB/s",
                                  "frac": hbm_achieved / hbm_peak, "peak_source": peak_src}},
@@ -593,6 +595,8 @@ def main():
     ap.add_argument("--baseline-device", default="cpu", choices=["cpu", "cuda"],
                     help="--impl reference: where the reference algorithm (torch autograd) runs")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--precision", default="fp32", choices=["fp32", "tf32"],
+                    help="layer GEMMs of wide nets: FP32 FMA (parity) or tcgen05 TF32; narrow nets are always FP32")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

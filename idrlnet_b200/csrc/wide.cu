@@ -27,61 +27,11 @@
 #include <string.h>
 
 #include "wide.cuh"
+#include "wide_internal.cuh"
 
 namespace pinn {
 
 namespace {
-
-constexpr int kMaxC = 7;
-constexpr int kBlocks = 148;         // partial slots of the per-block reductions
-constexpr int kBM = 32;              // points per GEMM tile
-constexpr int kBN = 128;             // output columns per GEMM tile
-constexpr int kBK = 16;
-constexpr int64_t kChunkBudget = 96ll << 20;  // bytes of Z/H planes per chunk
-constexpr int kMaxDomains = 64;       // loss slots
-
-struct WNet {
-  int n_in, n_out, L, H, act, C, NF, NS;
-  int first_in[4];
-  const float* W[PINN_MAX_LAYERS];
-  const float* b[PINN_MAX_LAYERS];
-};
-
-// ---- activation jets with runtime channel counts ---------------------------
-template <int ACT>
-__device__ __forceinline__ void jet_fwd(int NF, int NS, const float* z, float* h) {
-  float s0, s1, s2, s3;
-  act_derivs<ACT>(z[0], s0, s1, s2, s3);
-  h[0] = s0;
-#pragma unroll
-  for (int i = 0; i < 3; ++i)
-    if (i < NF) h[1 + i] = s1 * z[1 + i];
-#pragma unroll
-  for (int s = 0; s < 3; ++s)
-    if (s < NS) h[1 + NF + s] = s2 * z[1 + s] * z[1 + s] + s1 * z[1 + NF + s];
-}
-
-template <int ACT>
-__device__ __forceinline__ void jet_bwd(int NF, int NS, const float* z, const float* hb, float* zb) {
-  float s0, s1, s2, s3;
-  act_derivs<ACT>(z[0], s0, s1, s2, s3);
-  float zv = hb[0] * s1;
-#pragma unroll
-  for (int i = 0; i < 3; ++i)
-    if (i < NF) {
-      zv += hb[1 + i] * s2 * z[1 + i];
-      zb[1 + i] = hb[1 + i] * s1;
-    }
-#pragma unroll
-  for (int s = 0; s < 3; ++s)
-    if (s < NS) {
-      const float zi = z[1 + s], zii = z[1 + NF + s], hbs = hb[1 + NF + s];
-      zv += hbs * (s3 * zi * zi + s2 * zii);
-      zb[1 + s] += 2.0f * hbs * s2 * zi;
-      zb[1 + NF + s] = hbs * s1;
-    }
-  zb[0] = zv;
-}
 
 #define ACT_SWITCH(act, CALL)                      \
   do {                                             \
@@ -302,32 +252,57 @@ struct RedSpec {
   int slot[8];
   const float* w[8];
 };
-__global__ void reduce_cols_kernel(const float* __restrict__ src, RedSpec rs, int H, int64_t n0, int m, int Mc,
-                                   float* __restrict__ part) {
+// grid (ceil(H/32), kBlocks); block = 32 columns x 8 row groups; blockIdx.y is the partial slot.
+__global__ void __launch_bounds__(256) reduce_cols_kernel(const float* __restrict__ src, RedSpec rs, int H, int64_t n0, int m,
+                                                           int Mc, float* __restrict__ part) {
+  __shared__ float red[8][8][33];
   const size_t plane = (size_t)Mc * H;
-  const int per = (m + gridDim.x - 1) / gridDim.x;
-  const int nb = blockIdx.x * per, ne = (nb + per < m) ? nb + per : m;
-  for (int j = threadIdx.x; j < H; j += blockDim.x) {
-    float a[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-    for (int n = nb; n < ne; ++n) {
+  const int per = (m + gridDim.y - 1) / gridDim.y;
+  const int nb = blockIdx.y * per, ne = (nb + per < m) ? nb + per : m;
+  const int jl = threadIdx.x & 31, rg = threadIdx.x >> 5;
+  const int j = blockIdx.x * 32 + jl;
+  float a[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  if (j < H) {
+    for (int n = nb + rg; n < ne; n += 32) {  // 4 rows in flight per thread
+      float v[4][8], w[4][8];
 #pragma unroll
-      for (int q = 0; q < 8; ++q)
-        if (q < rs.nq) {
-          const float v = src[rs.plane[q] * plane + (size_t)n * H + j];
-          a[q] += rs.w[q] ? v * rs.w[q][n0 + n] : v;
+      for (int u = 0; u < 4; ++u) {
+        const int nn = n + 8 * u;
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          v[u][q] = 0.f;
+          w[u][q] = 1.f;
+          if (q < rs.nq && nn < ne) {
+            v[u][q] = src[rs.plane[q] * plane + (size_t)nn * H + j];
+            if (rs.w[q]) w[u][q] = rs.w[q][n0 + nn];
+          }
         }
-    }
-    float o[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-#pragma unroll
-    for (int q = 0; q < 8; ++q)
-      if (q < rs.nq) {
-#pragma unroll
-        for (int t = 0; t < 8; ++t)
-          if (rs.slot[q] == t) o[t] += a[q];
       }
 #pragma unroll
-    for (int t = 0; t < 8; ++t)
-      if (o[t] != 0.f) part[((size_t)blockIdx.x * 8 + t) * H + j] += o[t];
+      for (int u = 0; u < 4; ++u)
+#pragma unroll
+        for (int q = 0; q < 8; ++q) a[q] += v[u][q] * w[u][q];
+    }
+  }
+  float o[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+  for (int q = 0; q < 8; ++q)
+    if (q < rs.nq) {
+#pragma unroll
+      for (int t = 0; t < 8; ++t)
+        if (rs.slot[q] == t) o[t] += a[q];
+    }
+#pragma unroll
+  for (int t = 0; t < 8; ++t) red[rg][t][jl] = o[t];
+  __syncthreads();
+  if (rg == 0 && j < H) {
+#pragma unroll
+    for (int t = 0; t < 8; ++t) {
+      float sum = 0.f;
+#pragma unroll
+      for (int g = 0; g < 8; ++g) sum += red[g][t][jl];
+      if (sum != 0.f) part[((size_t)blockIdx.y * 8 + t) * H + j] += sum;
+    }
   }
 }
 
@@ -343,7 +318,8 @@ struct HeadArgs {
 };
 enum { W_MODE_FUSED = 0, W_MODE_FWD = 1, W_MODE_BWD = 2 };
 
-__device__ __forceinline__ void residual_loss_rt(const pinn_domain& dm, int C, int64_t n, const float* x, const float (*y)[4],
+template <int C>
+__device__ __forceinline__ void residual_loss_rt(const pinn_domain& dm, int64_t n, const float* x, const float (*y)[4],
                                                  float (*yb)[4], float& loss_acc) {
   float sym[PINN_SYM_COUNT];
   float sg[PINN_SYM_COORD0];
@@ -390,28 +366,25 @@ __device__ __forceinline__ void residual_loss_rt(const pinn_domain& dm, int C, i
     for (int o = 0; o < 4; ++o) yb[c][o] = sg[c * 4 + o];
 }
 
-// one warp per point (grid-stride); lanes stride over the hidden units.  KI = ceil(H / 32).
-template <int ACT, int KI>
-__global__ void __launch_bounds__(256) head_kernel(WNet net, const __grid_constant__ HeadArgs ha, float* __restrict__ ZL,
-                                                   const float* __restrict__ HL, int m, int Mc) {
-  extern __shared__ float sm[];  // Wout[O][H], then per-warp reduction scratch
-  const int H = net.H, O = net.n_out, C = net.C;
+// head_y: one warp per point (grid-stride); lanes stride over the hidden units, KI = ceil(H / 32).
+// y[c][o] = Wout h_L + bout ; residual / loss ; ybar -> Yb[n][C*4]; dbout and the loss go to the
+// block's partial slot.
+template <int ACT, int KI, int C>
+__global__ void __launch_bounds__(512) head_y_kernel(WNet net, const __grid_constant__ HeadArgs ha, const float* __restrict__ HL,
+                                                     float* __restrict__ Yb, int m, int Mc) {
+  extern __shared__ float sm[];  // Wout[O][H], then per-warp scratch [nwarps][O + 1]
+  const int H = net.H, O = net.n_out;
   float* sW = sm;
   for (int i = threadIdx.x; i < O * H; i += blockDim.x) sW[i] = net.W[net.L][i];
   __syncthreads();
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
   const size_t plane = (size_t)Mc * H;
-  float gW[4][KI];
   float gb[4] = {0.f, 0.f, 0.f, 0.f};
   float loss = 0.f;
-#pragma unroll
-  for (int o = 0; o < 4; ++o)
-#pragma unroll
-    for (int i = 0; i < KI; ++i) gW[o][i] = 0.f;
   for (int n = blockIdx.x * nwarps + warp; n < m; n += gridDim.x * nwarps) {
     const int64_t ng = ha.n0 + n;
-    // y[c][o] = sum_k Wout[o][k] h[c][k] + bout[o]
-    float y[kMaxC][4];
+    float y[C][4];
+#pragma unroll
     for (int c = 0; c < C; ++c) {
       float s[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
@@ -437,65 +410,86 @@ __global__ void __launch_bounds__(256) head_kernel(WNet net, const __grid_consta
           for (int o = 0; o < O; ++o) ha.jets_out[(int64_t)(c * O + o) * ha.n_total + ng] = y[c][o];
       continue;
     }
-    float yb[kMaxC][4];
+    float yb[C][4];
     if (ha.mode == W_MODE_FUSED) {
       float x[4] = {0.f, 0.f, 0.f, 0.f};
       for (int d = 0; d < net.n_in; ++d) x[d] = ha.xs.p[d][ng];
       float l = 0.f;
-      residual_loss_rt(ha.dom, C, ng, x, y, yb, l);
+      residual_loss_rt<C>(ha.dom, ng, x, y, yb, l);
       if (lane == 0) loss += l;
     } else {
+#pragma unroll
       for (int c = 0; c < C; ++c)
+#pragma unroll
         for (int o = 0; o < 4; ++o) yb[c][o] = (o < O) ? ha.jets_bar[(int64_t)(c * O + o) * ha.n_total + ng] : 0.f;
     }
-    if (lane == 0)
-      for (int o = 0; o < O; ++o) gb[o] += yb[0][o];
-    // zbar_L = act'(Z_L; Wout^T ybar); dWout += ybar^T h
+    if (lane == 0) {
 #pragma unroll
-    for (int i = 0; i < KI; ++i) {
-      const int k = lane + 32 * i;
-      if (k < H) {
-        float z[kMaxC], hb[kMaxC], zb[kMaxC];
-        for (int c = 0; c < C; ++c) {
-          z[c] = ZL[c * plane + (size_t)n * H + k];
-          const float h = HL[c * plane + (size_t)n * H + k];
-          float a = 0.f;
+      for (int o = 0; o < 4; ++o) gb[o] += yb[0][o];
 #pragma unroll
-          for (int o = 0; o < 4; ++o)
-            if (o < O) {
-              a += sW[o * H + k] * yb[c][o];
-              gW[o][i] += yb[c][o] * h;
-            }
-          hb[c] = a;
-          zb[c] = 0.f;
-        }
-        jet_bwd<ACT>(net.NF, net.NS, z, hb, zb);
-        for (int c = 0; c < C; ++c) ZL[c * plane + (size_t)n * H + k] = zb[c];
-      }
+      for (int c = 0; c < C; ++c)
+        *reinterpret_cast<float4*>(Yb + ((size_t)n * C + c) * 4) = make_float4(yb[c][0], yb[c][1], yb[c][2], yb[c][3]);
     }
   }
   if (ha.mode == W_MODE_FWD) return;
-  // block reduction over warps (fixed order), then += into this block's partial slot
-  float* red = sm + O * H;  // [nwarps][O*H + O + 1]
-  const int stride = O * H + O + 1;
+  float* red = sm + O * H;  // [nwarps][O + 1]
   __syncthreads();
-#pragma unroll
-  for (int o = 0; o < 4; ++o)
-#pragma unroll
-    for (int i = 0; i < KI; ++i) {
-      const int k = lane + 32 * i;
-      if (o < O && k < H) red[warp * stride + o * H + k] = gW[o][i];
-    }
   if (lane == 0) {
-    for (int o = 0; o < O; ++o) red[warp * stride + O * H + o] = gb[o];
-    red[warp * stride + O * H + O] = loss;
+    for (int o = 0; o < O; ++o) red[warp * (O + 1) + o] = gb[o];
+    red[warp * (O + 1) + O] = loss;
   }
   __syncthreads();
-  float* out = ha.part + (size_t)blockIdx.x * stride;
-  for (int i = threadIdx.x; i < stride; i += blockDim.x) {
-    float s = 0.f;
-    for (int w = 0; w < nwarps; ++w) s += red[w * stride + i];
-    out[i] += s;
+  const int hstride = O * H + O + 1;
+  if (threadIdx.x <= O) {
+    float sum = 0.f;
+    for (int w = 0; w < nwarps; ++w) sum += red[w * (O + 1) + threadIdx.x];
+    ha.part[(size_t)blockIdx.x * hstride + O * H + threadIdx.x] += sum;
+  }
+}
+
+// head_bwd: streaming over (point, unit): zbar_L = act'(Z_L; Wout^T ybar) in place, dWout += ybar^T h_L.
+// grid (ceil(H/128), kBlocks); block = 128 units x 4 point lanes; blockIdx.y is the partial slot.
+template <int ACT, int C>
+__global__ void __launch_bounds__(512) head_bwd_kernel(WNet net, const float* __restrict__ Yb, float* __restrict__ ZL,
+                                                       const float* __restrict__ HL, int m, int Mc, float* __restrict__ part) {
+  __shared__ float red[4][4][129];
+  const int H = net.H, O = net.n_out;
+  const int jl = threadIdx.x & 127, pl = threadIdx.x >> 7;
+  const int j = blockIdx.x * 128 + jl;
+  const size_t plane = (size_t)Mc * H;
+  const int per = (m + gridDim.y - 1) / gridDim.y;
+  const int nb = blockIdx.y * per, ne = (nb + per < m) ? nb + per : m;
+  float gW[4] = {0.f, 0.f, 0.f, 0.f};
+  if (j < H) {
+    float wo[4];
+#pragma unroll
+    for (int o = 0; o < 4; ++o) wo[o] = (o < O) ? net.W[net.L][o * H + j] : 0.f;
+    for (int n = nb + pl; n < ne; n += 4) {
+      float z[kMaxC], hb[kMaxC], zb[kMaxC], h[C];
+#pragma unroll
+      for (int c = 0; c < C; ++c) {
+        z[c] = ZL[c * plane + (size_t)n * H + j];
+        h[c] = HL[c * plane + (size_t)n * H + j];
+      }
+#pragma unroll
+      for (int c = 0; c < C; ++c) {
+        const float4 yb = *reinterpret_cast<const float4*>(Yb + ((size_t)n * C + c) * 4);
+        hb[c] = wo[0] * yb.x + wo[1] * yb.y + wo[2] * yb.z + wo[3] * yb.w;
+        gW[0] += yb.x * h[c]; gW[1] += yb.y * h[c]; gW[2] += yb.z * h[c]; gW[3] += yb.w * h[c];
+        zb[c] = 0.f;
+      }
+      jet_bwd<ACT>(net.NF, net.NS, z, hb, zb);
+#pragma unroll
+      for (int c = 0; c < C; ++c) ZL[c * plane + (size_t)n * H + j] = zb[c];
+    }
+  }
+#pragma unroll
+  for (int o = 0; o < 4; ++o) red[pl][o][jl] = gW[o];
+  __syncthreads();
+  if (pl == 0 && j < H) {
+    const int hstride = O * H + O + 1;
+    for (int o = 0; o < O; ++o)
+      part[(size_t)blockIdx.y * hstride + o * H + j] += red[0][o][jl] + red[1][o][jl] + red[2][o][jl] + red[3][o][jl];
   }
 }
 
@@ -503,7 +497,8 @@ __global__ void __launch_bounds__(256) head_kernel(WNet net, const __grid_consta
 struct WideLayout {  // workspace offsets in floats
   int64_t Z, Hb;            // L planes-sets each: [l][C][Mc][H]
   int64_t dw, db, first, head, loss_slots, acc_end, total;
-  int Mc, n_splits, tiles, n_dom;
+  int64_t wt, ybar;
+  int Mc, n_splits, fp32_splits, tiles, n_dom;
 };
 
 __global__ void wide_finalize_kernel(WNet net, const float* __restrict__ ws, WideLayout wl, int64_t n_params,
@@ -569,6 +564,7 @@ bool make_net(const pinn_mlp* m, const pinn_jets* j, WNet* n) {
   memset(n, 0, sizeof(*n));
   n->n_in = m->n_in; n->n_out = m->n_out; n->L = m->n_hidden; n->H = m->width; n->act = m->act;
   n->NF = j->n_first; n->NS = j->n_second; n->C = 1 + n->NF + n->NS;
+  n->precision = (m->precision == 1) ? 1 : 0;
   for (int i = 0; i < 4; ++i) n->first_in[i] = j->first_in[i];
   for (int l = 0; l <= m->n_hidden; ++l) { n->W[l] = m->W[l]; n->b[l] = m->b[l]; }
   return true;
@@ -583,9 +579,10 @@ WideLayout make_layout(const WNet& n, int n_dom) {
   if (mc > 65536) mc = 65536;
   wl.Mc = (int)mc;
   wl.tiles = (n.H + kBN - 1) / kBN;
-  int ns = kBlocks / (wl.tiles * wl.tiles);
-  if (ns < 1) ns = 1;
+  int ns = tc_dw_splits(n.H);  // slot count (>= the FP32 kernel's split count)
   wl.n_splits = ns;
+  wl.fp32_splits = kBlocks / (wl.tiles * wl.tiles) < 1 ? 1 : kBlocks / (wl.tiles * wl.tiles);
+  if (wl.fp32_splits > ns) wl.fp32_splits = ns;
   wl.n_dom = n_dom;
   // accumulators first: their offsets must not depend on the jet plan (domains with
   // different channel counts accumulate into the same slots); chunk planes last.
@@ -597,9 +594,11 @@ WideLayout make_layout(const WNet& n, int n_dom) {
   wl.head = off; off += (int64_t)kBlocks * (n.n_out * n.H + n.n_out + 1);
   wl.loss_slots = off; off += (int64_t)kMaxDomains * kBlocks;
   off = (off + 3) / 4 * 4;
+  wl.wt = off; off += (int64_t)(n.L - 1) * n.H * n.H;  // W_l^T for the tensor-core reverse GEMM
   wl.acc_end = off;
   wl.Z = off; off += planes;
   wl.Hb = off; off += planes;
+  wl.ybar = off; off += (int64_t)mc * kMaxC * 4;
   wl.total = (off + 3) / 4 * 4;
   return wl;
 }
@@ -642,8 +641,11 @@ int run_chunks(const WNet& n, const WideLayout& wl, float* ws, int mode, const p
       count_launch(1);
     }
     for (int l = 2; l <= L; ++l) {
-      int rc = launch_gemm_rows<ACT, true, 0>(n, Hb + (l - 2) * planes, n.W[l - 1], n.b[l - 1], Z + (l - 1) * planes,
-                                              Hb + (l - 1) * planes, m, wl.Mc, st);
+      int rc = n.precision
+                   ? tc_launch_rows<ACT, 0>(n, Hb + (l - 2) * planes, n.W[l - 1], n.b[l - 1], Z + (l - 1) * planes,
+                                            Hb + (l - 1) * planes, m, wl.Mc, st)
+                   : launch_gemm_rows<ACT, true, 0>(n, Hb + (l - 2) * planes, n.W[l - 1], n.b[l - 1], Z + (l - 1) * planes,
+                                                    Hb + (l - 1) * planes, m, wl.Mc, st);
       if (rc) return rc;
     }
     {
@@ -657,17 +659,28 @@ int run_chunks(const WNet& n, const WideLayout& wl, float* ws, int mode, const p
       ha.jets_out = jets_out;
       ha.jets_bar = jets_bar;
       ha.part = ws + wl.head;
-      const int nwarps = 8;
-      const size_t smem = ((size_t)n.n_out * H + (size_t)nwarps * hstride) * 4;
+      const int nwarps = 16;
+      const size_t smem = ((size_t)n.n_out * H + (size_t)nwarps * (n.n_out + 1)) * 4;
       int blocks = (m + nwarps - 1) / nwarps;
       if (blocks > kBlocks) blocks = kBlocks;
+      float* zl = Z + (L - 1) * planes;
+      const float* hl = Hb + (L - 1) * planes;
+      float* yb = ws + wl.ybar;
+      const dim3 bgrid((H + 127) / 128, kBlocks);
+#define HEAD(KI_, C_)                                                                                       \
+  case C_: {                                                                                                \
+    head_y_kernel<ACT, KI_, C_><<<blocks, nwarps * 32, smem, st>>>(n, ha, hl, yb, m, wl.Mc);                \
+    if (mode != W_MODE_FWD) {                                                                               \
+      head_bwd_kernel<ACT, C_><<<bgrid, 512, 0, st>>>(n, yb, zl, hl, m, wl.Mc, ws + wl.head);               \
+      count_launch(1);                                                                                      \
+    }                                                                                                       \
+  } break;
       if (H <= 128) {
-        CK(cudaFuncSetAttribute((const void*)head_kernel<ACT, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        head_kernel<ACT, 4><<<blocks, nwarps * 32, smem, st>>>(n, ha, Z + (L - 1) * planes, Hb + (L - 1) * planes, m, wl.Mc);
+        switch (C) { HEAD(4, 1) HEAD(4, 2) HEAD(4, 3) HEAD(4, 4) HEAD(4, 5) HEAD(4, 6) HEAD(4, 7) default: return PINN_E_UNSUPPORTED; }
       } else {
-        CK(cudaFuncSetAttribute((const void*)head_kernel<ACT, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        head_kernel<ACT, 16><<<blocks, nwarps * 32, smem, st>>>(n, ha, Z + (L - 1) * planes, Hb + (L - 1) * planes, m, wl.Mc);
+        switch (C) { HEAD(16, 1) HEAD(16, 2) HEAD(16, 3) HEAD(16, 4) HEAD(16, 5) HEAD(16, 6) HEAD(16, 7) default: return PINN_E_UNSUPPORTED; }
       }
+#undef HEAD
       count_launch(1);
       CK(cudaGetLastError());
     }
@@ -676,16 +689,25 @@ int run_chunks(const WNet& n, const WideLayout& wl, float* ws, int mode, const p
       float* zb = Z + (l - 1) * planes;        // zbar_l (in place of Z_l)
       const float* hprev = Hb + (l - 2) * planes;
       {
-        dim3 grid(wl.tiles * wl.tiles, wl.n_splits);
-        gemm_dw_kernel<<<grid, 256, 0, st>>>(zb, hprev, H, C, m, wl.Mc, ws + wl.dw + (size_t)(l - 2) * wl.n_splits * H * H, wl.tiles);
-        count_launch(1);
+        float* dwp = ws + wl.dw + (size_t)(l - 2) * wl.n_splits * H * H;
+        if (n.precision) {
+          int rc = tc_launch_dw(zb, hprev, H, C, m, wl.Mc, dwp, wl.n_splits, st);
+          if (rc) return rc;
+        } else {
+          dim3 grid(wl.tiles * wl.tiles, wl.fp32_splits);
+          gemm_dw_kernel<<<grid, 256, 0, st>>>(zb, hprev, H, C, m, wl.Mc, dwp, wl.tiles);
+          count_launch(1);
+        }
         RedSpec rs;
         memset(&rs, 0, sizeof(rs));
         rs.nq = 1;
-        reduce_cols_kernel<<<kBlocks, 128, 0, st>>>(zb, rs, H, n0, m, wl.Mc, ws + wl.db + (size_t)(l - 2) * kBlocks * 8 * H);
+        reduce_cols_kernel<<<dim3((H + 31) / 32, kBlocks), 256, 0, st>>>(zb, rs, H, n0, m, wl.Mc, ws + wl.db + (size_t)(l - 2) * kBlocks * 8 * H);
         count_launch(1);
       }
-      int rc = launch_gemm_rows<ACT, false, 1>(n, zb, n.W[l - 1], nullptr, Z + (l - 2) * planes, nullptr, m, wl.Mc, st);
+      int rc = n.precision
+                   ? tc_launch_rows<ACT, 1>(n, zb, ws + wl.wt + (size_t)(l - 2) * H * H, nullptr, Z + (l - 2) * planes, nullptr,
+                                            m, wl.Mc, st)
+                   : launch_gemm_rows<ACT, false, 1>(n, zb, n.W[l - 1], nullptr, Z + (l - 2) * planes, nullptr, m, wl.Mc, st);
       if (rc) return rc;
     }
     {
@@ -696,7 +718,7 @@ int run_chunks(const WNet& n, const WideLayout& wl, float* ws, int mode, const p
       rs.plane[q] = 0; rs.w[q] = nullptr; rs.slot[q] = PINN_MAX_IN; ++q;  // db1
       for (int i = 0; i < n.NF; ++i) { rs.plane[q] = 1 + i; rs.w[q] = nullptr; rs.slot[q] = n.first_in[i]; ++q; }
       rs.nq = q;
-      reduce_cols_kernel<<<kBlocks, 128, 0, st>>>(Z, rs, H, n0, m, wl.Mc, ws + wl.first);
+      reduce_cols_kernel<<<dim3((H + 31) / 32, kBlocks), 256, 0, st>>>(Z, rs, H, n0, m, wl.Mc, ws + wl.first);
       count_launch(1);
       CK(cudaGetLastError());
     }
@@ -716,6 +738,11 @@ int run_mode(const pinn_mlp* m, const pinn_jets* j, int mode, const pinn_domain*
   if (!accumulate && mode != W_MODE_FWD)  // clear every partial slot (all domains' loss slots included)
     CK(cudaMemsetAsync(w + wl.dw, 0, (size_t)(wl.acc_end - wl.dw) * 4, st));
   int rc = 0;
+  if (n.precision && mode != W_MODE_FWD)
+    for (int l = 2; l <= n.L; ++l) {
+      rc = tc_transpose(n.W[l - 1], w + wl.wt + (size_t)(l - 2) * n.H * n.H, n.H, st);
+      if (rc) return rc;
+    }
 #define RUN(A) rc = run_chunks<A>(n, wl, w, mode, dom, N, coords, jets_out, jets_bar, st)
   ACT_SWITCH(n.act, RUN);
 #undef RUN

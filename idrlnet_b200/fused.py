@@ -25,6 +25,13 @@ from . import compiler as cp
 from . import native as nv
 
 
+def default_precision() -> str:
+    """Arithmetic of the wide-net layer GEMMs: "fp32" (parity path, default) or "tf32"
+    (tcgen05 tensor cores).  Set IDRLNET_B200_PRECISION=tf32 or pass precision= explicitly."""
+    import os
+    return os.environ.get("IDRLNET_B200_PRECISION", "fp32").lower()
+
+
 def _stream_ptr() -> int:
     return torch.cuda.current_stream().cuda_stream
 
@@ -67,8 +74,11 @@ def _activation_name(module: torch.nn.Module) -> str:
 class NetPack:
     """Kernel view of an MLP: Linear stack, uniform hidden width, one activation."""
 
-    def __init__(self, module: torch.nn.Module, act: Optional[str] = None):
+    def __init__(self, module: torch.nn.Module, act: Optional[str] = None, precision: Optional[str] = None):
         self.module = module
+        self.precision = precision or default_precision()
+        if self.precision not in nv.PRECISION:
+            raise ValueError(f"precision must be one of {sorted(nv.PRECISION)}")
         self.layers = _linear_layers(module)
         self.act = act or _activation_name(module)
         if len(self.layers) < 2:
@@ -131,7 +141,8 @@ class NetPack:
                     _require_cuda(t, "net parameter")
                     if not t.is_contiguous():
                         raise RuntimeError("idrlnet_b200: net parameters must be contiguous")
-            self._mlp = nv.make_mlp(self.n_in, self.n_out, self.n_hidden, self.width, self.act, ptrs[0::2], ptrs[1::2])
+            self._mlp = nv.make_mlp(self.n_in, self.n_out, self.n_hidden, self.width, self.act, ptrs[0::2], ptrs[1::2],
+                                    self.precision)
             self._mlp_key = ptrs
         return self._mlp
 
@@ -176,7 +187,7 @@ class JetFunction(torch.autograd.Function):
     derivatives ARE the jet channels)."""
 
     @staticmethod
-    def forward(ctx, plan: cp.JetPlan, act: str, coords: Tuple[torch.Tensor, ...], *wb: torch.Tensor):
+    def forward(ctx, plan: cp.JetPlan, act: str, precision: str, coords: Tuple[torch.Tensor, ...], *wb: torch.Tensor):
         lib = nv.lib()
         n_layers = len(wb) // 2
         Ws, bs = wb[0::2], wb[1::2]
@@ -186,14 +197,14 @@ class JetFunction(torch.autograd.Function):
         cols = [c.detach().reshape(-1).contiguous() for c in coords]
         wbc = [t.detach().contiguous() for t in wb]
         mlp = nv.make_mlp(len(cols), Ws[-1].shape[0], n_layers - 1, Ws[0].shape[0], act,
-                          [t.data_ptr() for t in wbc[0::2]], [t.data_ptr() for t in wbc[1::2]])
+                          [t.data_ptr() for t in wbc[0::2]], [t.data_ptr() for t in wbc[1::2]], precision)
         jets = nv.make_jets(plan.first_in, plan.n_second)
         out = torch.empty(plan.n_channels * Ws[-1].shape[0], n, device=cols[0].device, dtype=torch.float32)
         ws_bytes = lib.pinn_workspace_bytes(C.byref(mlp), C.byref(jets), 1)
         ws = torch.empty(max(ws_bytes // 4, 1), device=cols[0].device, dtype=torch.float32)
         nv.check(lib.pinn_jet_forward(C.byref(mlp), C.byref(jets), n, nv.ptr_array([c.data_ptr() for c in cols]),
                                       out.data_ptr(), ws.data_ptr(), ws_bytes, _stream_ptr()))
-        ctx.plan, ctx.act, ctx.cols, ctx.wbc = plan, act, cols, wbc
+        ctx.plan, ctx.act, ctx.cols, ctx.wbc, ctx.precision = plan, act, cols, wbc, precision
         return out
 
     @staticmethod
@@ -203,7 +214,7 @@ class JetFunction(torch.autograd.Function):
         Ws = wbc[0::2]
         n = cols[0].numel()
         mlp = nv.make_mlp(len(cols), Ws[-1].shape[0], len(Ws) - 1, Ws[0].shape[0], ctx.act,
-                          [t.data_ptr() for t in wbc[0::2]], [t.data_ptr() for t in wbc[1::2]])
+                          [t.data_ptr() for t in wbc[0::2]], [t.data_ptr() for t in wbc[1::2]], ctx.precision)
         jets = nv.make_jets(plan.first_in, plan.n_second)
         ws_bytes = lib.pinn_workspace_bytes(C.byref(mlp), C.byref(jets), 1)
         ws = torch.empty(ws_bytes // 4, device=cols[0].device, dtype=torch.float32)
@@ -218,11 +229,12 @@ class JetFunction(torch.autograd.Function):
         for t in wbc:
             grads.append(flat[off:off + t.numel()].view_as(t))
             off += t.numel()
-        return (None, None, None, *grads)
+        return (None, None, None, None, *grads)
 
 
-def jet_mlp(plan: cp.JetPlan, act: str, coords: Sequence[torch.Tensor], weights_and_biases: Sequence[torch.Tensor]):
-    return JetFunction.apply(plan, act, tuple(coords), *weights_and_biases)
+def jet_mlp(plan: cp.JetPlan, act: str, coords: Sequence[torch.Tensor], weights_and_biases: Sequence[torch.Tensor],
+            precision: Optional[str] = None):
+    return JetFunction.apply(plan, act, precision or default_precision(), tuple(coords), *weights_and_biases)
 
 
 # --------------------------------------------------------------------------- #

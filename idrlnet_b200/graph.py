@@ -217,7 +217,7 @@ class _JetServe:
                 wb += [torch._weight_norm(l.weight_v, l.weight_g, 0), l.bias]
             else:
                 wb += [l.weight, l.bias]
-        jets = fused.jet_mlp(self.plan, pack.act, [args[k] for k in self.node.inputs], wb)
+        jets = fused.jet_mlp(self.plan, pack.act, [args[k] for k in self.node.inputs], wb, pack.precision)
         n_out = pack.n_out
         out = {}
         for name, (c, o, scale) in self.names.items():

@@ -32,7 +32,7 @@ _fp = C.c_void_p  # device (or, for the emulator, host) pointer to float
 
 class PinnMlp(C.Structure):
     _fields_ = [("n_in", C.c_int32), ("n_out", C.c_int32), ("n_hidden", C.c_int32), ("width", C.c_int32),
-                ("act", C.c_int32), ("_pad", C.c_int32), ("W", _fp * MAX_LAYERS), ("b", _fp * MAX_LAYERS)]
+                ("act", C.c_int32), ("precision", C.c_int32), ("W", _fp * MAX_LAYERS), ("b", _fp * MAX_LAYERS)]
 
 
 class PinnJets(C.Structure):
@@ -55,10 +55,14 @@ class PinnDomain(C.Structure):
                 ("terms", PinnTerm * MAX_TERMS)]
 
 
+PRECISION = {"fp32": 0, "tf32": 1}
+
+
 def make_mlp(n_in: int, n_out: int, n_hidden: int, width: int, act: str, w_ptrs: Sequence[int],
-             b_ptrs: Sequence[int]) -> PinnMlp:
+             b_ptrs: Sequence[int], precision: str = "fp32") -> PinnMlp:
     m = PinnMlp()
     m.n_in, m.n_out, m.n_hidden, m.width, m.act = n_in, n_out, n_hidden, width, ACT[act]
+    m.precision = PRECISION[precision]
     assert len(w_ptrs) == n_hidden + 1 == len(b_ptrs)
     for i, (w, b) in enumerate(zip(w_ptrs, b_ptrs)):
         m.W[i], m.b[i] = w, b
@@ -103,6 +107,7 @@ _SIGNATURES = {
     "pinn_sample_box": (C.c_int, [C.POINTER(_fp), C.c_int32, C.POINTER(C.c_float), C.POINTER(C.c_float), C.c_int64,
                                   C.c_uint64, C.c_uint64, C.c_uint64, C.c_void_p, C.c_int32, C.c_void_p]),
     "pinn_fp32_fma_probe": (C.c_int64, [C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]),
+    "pinn_tc_selftest": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
 }
 EXPORTS = tuple(_SIGNATURES)
 

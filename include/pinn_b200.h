@@ -50,6 +50,10 @@ extern "C" {
 
 enum { PINN_ACT_TANH = 0, PINN_ACT_SILU = 1, PINN_ACT_SIN = 2 };
 enum { PINN_LOSS_SQUARE = 0, PINN_LOSS_L1 = 1, PINN_LOSS_IDENTITY = 2 };
+/* PINN_PREC_FP32: FP32 FMA everywhere (1e-5 parity with the reference's FP32 autograd).
+ * PINN_PREC_TF32: layer GEMMs of wide nets on tcgen05 tensor cores, multiplicands rounded
+ * to TF32, FP32 accumulate; everything else FP32.  Narrow nets ignore the field. */
+enum { PINN_PREC_FP32 = 0, PINN_PREC_TF32 = 1 };
 enum {
   PINN_E_INVALID = -1,     /* malformed descriptor                        */
   PINN_E_UNSUPPORTED = -2, /* valid but no kernel for it (width, channels) */
@@ -68,7 +72,7 @@ typedef struct pinn_mlp {
   int32_t n_hidden; /* L >= 1 hidden layers, all `width` wide              */
   int32_t width;    /* H                                                   */
   int32_t act;      /* PINN_ACT_*                                          */
-  int32_t _pad;
+  int32_t precision; /* PINN_PREC_*: arithmetic of the wide (H > 32) layer GEMMs */
   const float* W[PINN_MAX_LAYERS]; /* L+1 pointers                         */
   const float* b[PINN_MAX_LAYERS];
 } pinn_mlp;
@@ -198,6 +202,13 @@ PINN_API int pinn_sample_box(float* const* columns, int32_t n_dims, const float*
  * `iters` steps; returns the number of flops issued (time it with CUDA events to
  * get the FP32-pipe roofline denominator), or a negative cudaError_t. */
 PINN_API int64_t pinn_fp32_fma_probe(int32_t iters, int32_t blocks, float* scratch, void* stream);
+
+/* Self-test of the tcgen05 plumbing used by the wide tensor-core path: one CTA computes
+ * D[128][N] = A * B^T in TF32 (FP32 accumulate in TMEM).  variant 0: A[128][K], B[N][K]
+ * (K-major operands); variant 1: A[K][128], B[K][N] (MN-major operands).  *status (device
+ * int) is set to 1 if the MMA completion barrier timed out. */
+PINN_API int pinn_tc_selftest(int variant, int N, int K, const float* A, const float* B, float* D,
+                              int* status, void* stream);
 
 #ifdef __cplusplus
 }

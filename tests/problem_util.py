@@ -190,7 +190,7 @@ def torch_module_from_net(net, device):
     return m.to(device)
 
 
-def run_cuda_fused(problem, device="cuda:0"):
+def run_cuda_fused(problem, device="cuda:0", precision="fp32"):
     """All fusable domains through fused.StepEngine (the C ABI).  Returns
     ({net: flat eff grad (numpy)}, {domain: loss}, skipped, {net: module})."""
     import torch
@@ -208,7 +208,7 @@ def run_cuda_fused(problem, device="cuda:0"):
         owner = owner_net(problem, cd.net.name)
         if owner["name"] not in modules:
             modules[owner["name"]] = torch_module_from_net(owner, device)
-            packs[owner["name"]] = fused.NetPack(modules[owner["name"]], act=owner["act"])
+            packs[owner["name"]] = fused.NetPack(modules[owner["name"]], act=owner["act"], precision=precision)
         cols = {k: torch.as_tensor(v, device=device) for k, v in domain_columns(dom).items()}
 
         def val(v):

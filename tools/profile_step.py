@@ -10,9 +10,10 @@ import bench  # noqa: E402
 
 steps = int(sys.argv[1]) if len(sys.argv) > 1 else 4
 config = sys.argv[2] if len(sys.argv) > 2 else "burgers"
+precision = sys.argv[3] if len(sys.argv) > 3 else "fp32"
 torch.cuda.set_device(0)
 dev = torch.device("cuda:0")
-tr = bench.Trainer(bench.workload_configs()[config], dev)
+tr = bench.Trainer(bench.workload_configs()[config], dev, precision=precision)
 rng = np.random.default_rng(0)
 for _ in range(2):
     hb = tr.sample_host(rng)
