@@ -366,83 +366,121 @@ __device__ __forceinline__ void residual_loss_rt(const pinn_domain& dm, int64_t 
     for (int o = 0; o < 4; ++o) yb[c][o] = sg[c * 4 + o];
 }
 
-// head_y: one warp per point (grid-stride); lanes stride over the hidden units, KI = ceil(H / 32).
-// y[c][o] = Wout h_L + bout ; residual / loss ; ybar -> Yb[n][C*4]; dbout and the loss go to the
-// block's partial slot.
-template <int ACT, int KI, int C>
-__global__ void __launch_bounds__(512) head_y_kernel(WNet net, const __grid_constant__ HeadArgs ha, const float* __restrict__ HL,
-                                                     float* __restrict__ Yb, int m, int Mc) {
-  extern __shared__ float sm[];  // Wout[O][H], then per-warp scratch [nwarps][O + 1]
-  const int H = net.H, O = net.n_out;
-  float* sW = sm;
+// out_layer: y[n][c][o] = sum_k Wout[o][k] h_L[c][n][k] + bout[o]*(c==0), FP32 (the output values feed
+// residuals with cancellations, so this small skinny product stays off the TF32 pipe).  One warp
+// handles 4 rows (c, n) per iteration (16 loads in flight per lane), lanes stride over k.
+template <int KI>
+__global__ void __launch_bounds__(256) out_layer_kernel(WNet net, const float* __restrict__ HL, float* __restrict__ Yv, int m, int Mc) {
+  extern __shared__ float sW[];  // Wout[O][H]
+  const int H = net.H, O = net.n_out, C = net.C;
   for (int i = threadIdx.x; i < O * H; i += blockDim.x) sW[i] = net.W[net.L][i];
   __syncthreads();
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
   const size_t plane = (size_t)Mc * H;
-  float gb[4] = {0.f, 0.f, 0.f, 0.f};
-  float loss = 0.f;
-  for (int n = blockIdx.x * nwarps + warp; n < m; n += gridDim.x * nwarps) {
-    const int64_t ng = ha.n0 + n;
-    float y[C][4];
+  const int rows = C * m;
+  float w[4][KI];
 #pragma unroll
-    for (int c = 0; c < C; ++c) {
-      float s[4] = {0.f, 0.f, 0.f, 0.f};
+  for (int o = 0; o < 4; ++o)
+#pragma unroll
+    for (int i = 0; i < KI; ++i) {
+      const int k = lane + 32 * i;
+      w[o][i] = (o < O && k < H) ? sW[o * H + k] : 0.f;
+    }
+  for (int r0 = (blockIdx.x * nwarps + warp) * 4; r0 < rows; r0 += gridDim.x * nwarps * 4) {
+    float h[4][KI];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int r = r0 + u;
+      const int c = r / m, n = r - c * m;
 #pragma unroll
       for (int i = 0; i < KI; ++i) {
         const int k = lane + 32 * i;
-        if (k < H) {
-          const float h = HL[c * plane + (size_t)n * H + k];
-#pragma unroll
-          for (int o = 0; o < 4; ++o)
-            if (o < O) s[o] += sW[o * H + k] * h;
-        }
+        h[u][i] = (r < rows && k < H) ? HL[c * plane + (size_t)n * H + k] : 0.f;
       }
+    }
 #pragma unroll
-      for (int o = 0; o < 4; ++o) {
+    for (int u = 0; u < 4; ++u) {
+      float s[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+      for (int i = 0; i < KI; ++i)
+#pragma unroll
+        for (int o = 0; o < 4; ++o) s[o] += w[o][i] * h[u][i];
+#pragma unroll
+      for (int o = 0; o < 4; ++o)
 #pragma unroll
         for (int d = 16; d > 0; d >>= 1) s[o] += __shfl_xor_sync(0xffffffffu, s[o], d);
-        y[c][o] = s[o] + ((c == 0 && o < O) ? net.b[net.L][o] : 0.f);
+      const int r = r0 + u;
+      if (lane == 0 && r < rows) {
+        const int c = r / m, n = r - c * m;
+        float4 out = make_float4(s[0], s[1], s[2], s[3]);
+        if (c == 0) {
+          out.x += net.b[net.L][0];
+          if (O > 1) out.y += net.b[net.L][1];
+          if (O > 2) out.z += net.b[net.L][2];
+          if (O > 3) out.w += net.b[net.L][3];
+        }
+        *reinterpret_cast<float4*>(Yv + ((size_t)n * C + c) * 4) = out;
       }
     }
+  }
+}
+
+// head_point: one THREAD per point: residual / loss / ybar (in place in Yv) from the output-layer
+// values y[n][c][o]; dbout and loss to the block's partial slot.
+template <int C>
+__global__ void __launch_bounds__(256) head_point_kernel(WNet net, const __grid_constant__ HeadArgs ha, float* __restrict__ Yv, int m) {
+  __shared__ float red[8][5];
+  const int O = net.n_out, H = net.H;
+  float gb[4] = {0.f, 0.f, 0.f, 0.f};
+  float loss = 0.f;
+  for (int n = blockIdx.x * blockDim.x + threadIdx.x; n < m; n += gridDim.x * blockDim.x) {
+    const int64_t ng = ha.n0 + n;
+    float y[C][4], yb[C][4];
+#pragma unroll
+    for (int c = 0; c < C; ++c) {
+      const float4 t = *reinterpret_cast<const float4*>(Yv + ((size_t)n * C + c) * 4);
+      y[c][0] = t.x; y[c][1] = t.y; y[c][2] = t.z; y[c][3] = t.w;
+#pragma unroll
+      for (int o = 0; o < 4; ++o)
+        if (o >= O) y[c][o] = 0.f;
+    }
     if (ha.mode == W_MODE_FWD) {
-      if (lane == 0)
-        for (int c = 0; c < C; ++c)
-          for (int o = 0; o < O; ++o) ha.jets_out[(int64_t)(c * O + o) * ha.n_total + ng] = y[c][o];
+      for (int c = 0; c < C; ++c)
+        for (int o = 0; o < O; ++o) ha.jets_out[(int64_t)(c * O + o) * ha.n_total + ng] = y[c][o];
       continue;
     }
-    float yb[C][4];
     if (ha.mode == W_MODE_FUSED) {
       float x[4] = {0.f, 0.f, 0.f, 0.f};
       for (int d = 0; d < net.n_in; ++d) x[d] = ha.xs.p[d][ng];
-      float l = 0.f;
-      residual_loss_rt<C>(ha.dom, ng, x, y, yb, l);
-      if (lane == 0) loss += l;
+      residual_loss_rt<C>(ha.dom, ng, x, y, yb, loss);
     } else {
 #pragma unroll
       for (int c = 0; c < C; ++c)
 #pragma unroll
         for (int o = 0; o < 4; ++o) yb[c][o] = (o < O) ? ha.jets_bar[(int64_t)(c * O + o) * ha.n_total + ng] : 0.f;
     }
-    if (lane == 0) {
 #pragma unroll
-      for (int o = 0; o < 4; ++o) gb[o] += yb[0][o];
+    for (int o = 0; o < 4; ++o) gb[o] += yb[0][o];
 #pragma unroll
-      for (int c = 0; c < C; ++c)
-        *reinterpret_cast<float4*>(Yb + ((size_t)n * C + c) * 4) = make_float4(yb[c][0], yb[c][1], yb[c][2], yb[c][3]);
-    }
+    for (int c = 0; c < C; ++c)
+      *reinterpret_cast<float4*>(Yv + ((size_t)n * C + c) * 4) = make_float4(yb[c][0], yb[c][1], yb[c][2], yb[c][3]);
   }
   if (ha.mode == W_MODE_FWD) return;
-  float* red = sm + O * H;  // [nwarps][O + 1]
-  __syncthreads();
-  if (lane == 0) {
-    for (int o = 0; o < O; ++o) red[warp * (O + 1) + o] = gb[o];
-    red[warp * (O + 1) + O] = loss;
+  float vals[5] = {gb[0], gb[1], gb[2], gb[3], loss};
+#pragma unroll
+  for (int q = 0; q < 5; ++q) {
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) vals[q] += __shfl_xor_sync(0xffffffffu, vals[q], d);
   }
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (lane == 0)
+    for (int q = 0; q < 5; ++q) red[warp][q] = vals[q];
   __syncthreads();
   const int hstride = O * H + O + 1;
   if (threadIdx.x <= O) {
+    const int q = threadIdx.x < O ? threadIdx.x : 4;
     float sum = 0.f;
-    for (int w = 0; w < nwarps; ++w) sum += red[w * (O + 1) + threadIdx.x];
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) sum += red[w][q];
     ha.part[(size_t)blockIdx.x * hstride + O * H + threadIdx.x] += sum;
   }
 }
@@ -659,17 +697,19 @@ int run_chunks(const WNet& n, const WideLayout& wl, float* ws, int mode, const p
       ha.jets_out = jets_out;
       ha.jets_bar = jets_bar;
       ha.part = ws + wl.head;
-      const int nwarps = 16;
-      const size_t smem = ((size_t)n.n_out * H + (size_t)nwarps * (n.n_out + 1)) * 4;
-      int blocks = (m + nwarps - 1) / nwarps;
-      if (blocks > kBlocks) blocks = kBlocks;
       float* zl = Z + (L - 1) * planes;
       const float* hl = Hb + (L - 1) * planes;
       float* yb = ws + wl.ybar;
       const dim3 bgrid((H + 127) / 128, kBlocks);
 #define HEAD(KI_, C_)                                                                                       \
   case C_: {                                                                                                \
-    head_y_kernel<ACT, KI_, C_><<<blocks, nwarps * 32, smem, st>>>(n, ha, hl, yb, m, wl.Mc);                \
+    int ob = (C * m + 31) / 32;                                                                             \
+    if (ob > kBlocks * 4) ob = kBlocks * 4;                                                                 \
+    out_layer_kernel<KI_><<<ob, 256, (size_t)n.n_out * H * 4, st>>>(n, hl, yb, m, wl.Mc);                   \
+    int pb = (m + 255) / 256;                                                                               \
+    if (pb > kBlocks) pb = kBlocks;                                                                         \
+    head_point_kernel<C_><<<pb, 256, 0, st>>>(n, ha, yb, m);                                                \
+    count_launch(1);                                                                                        \
     if (mode != W_MODE_FWD) {                                                                               \
       head_bwd_kernel<ACT, C_><<<bgrid, 512, 0, st>>>(n, yb, zl, hl, m, wl.Mc, ws + wl.head);               \
       count_launch(1);                                                                                      \

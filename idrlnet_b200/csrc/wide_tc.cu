@@ -48,7 +48,7 @@ __device__ __forceinline__ void issue_chunk(uint32_t tmem, uint32_t sA, uint32_t
 template <int C, int ACT, int EPI>
 __global__ void __launch_bounds__(256) tc_rows_kernel(WNet net, const float* __restrict__ Bsrc, const float* __restrict__ Aw,
                                                       const float* __restrict__ bias, float* __restrict__ Zio,
-                                                      float* __restrict__ Hout, int m, int Mc) {
+                                                      float* __restrict__ Hout, int m, int Mc, int a_rows) {
   using T = TileCfg<C>;
   constexpr int P = T::P, N = T::N;
   const int H = net.H;
@@ -82,7 +82,7 @@ __global__ void __launch_bounds__(256) tc_rows_kernel(WNet net, const float* __r
     for (int u = 0; u < kItA; ++u) {
       const int i = tid + u * 256, row = i >> 4, kq = i & 15;
       ra[u] = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (j0 + row < H && k0 + kq * 4 < H) ra[u] = *reinterpret_cast<const float4*>(Aw + (size_t)(j0 + row) * H + k0 + kq * 4);
+      if (j0 + row < a_rows && k0 + kq * 4 < H) ra[u] = *reinterpret_cast<const float4*>(Aw + (size_t)(j0 + row) * H + k0 + kq * 4);
     }
 #pragma unroll
     for (int u = 0; u < kItB; ++u) {
@@ -115,40 +115,66 @@ __global__ void __launch_bounds__(256) tc_rows_kernel(WNet net, const float* __r
   if (!ok) __trap();
   tc::tc_fence_after();
 
-  // epilogue: lane = hidden unit; 16-point groups alternate between the two warp quads
+  // epilogue: lane = hidden unit (or output, EPI 2); 16-point groups alternate between the two warp quads
   const int j = j0 + (warp & 3) * 32 + lane;
   const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
-  const float bj = (EPI == 0 && j < H) ? bias[j] : 0.f;
+  const float bj = (EPI != 1 && j < a_rows) ? bias[j] : 0.f;
   for (int g = warp >> 2; g < P / 16; g += 2) {
     float v[C][16];
 #pragma unroll
     for (int c = 0; c < C; ++c) tc::tmem_ld16(tmem + lane_base + c * P + g * 16, v[c]);
-    tc::tmem_ld_wait();
-    if (j < H) {
+    if (EPI == 1) {
+      // reverse layer: fetch Z_{l-1} for 8 points at a time while the TMEM loads are in flight
 #pragma unroll
-      for (int i = 0; i < 16; ++i) {
-        const int n = n0 + g * 16 + i;
-        if (n >= m) break;
-        float a[kMaxC], b[kMaxC], o[kMaxC];
+      for (int half = 0; half < 2; ++half) {
+        float zin[C][8];
 #pragma unroll
-        for (int c = 0; c < C; ++c) a[c] = v[c][i];
-        if (EPI == 0) {
-          a[0] += bj;
-          jet_fwd<ACT>(net.NF, net.NS, a, o);
+        for (int i = 0; i < 8; ++i) {
+          const int n = n0 + g * 16 + half * 8 + i;
 #pragma unroll
-          for (int c = 0; c < C; ++c) {
-            Zio[c * plane + (size_t)n * H + j] = a[c];
-            Hout[c * plane + (size_t)n * H + j] = o[c];
-          }
-        } else {
+          for (int c = 0; c < C; ++c) zin[c][i] = (j < H && n < m) ? Zio[c * plane + (size_t)n * H + j] : 0.f;
+        }
+        if (half == 0) tc::tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int n = n0 + g * 16 + half * 8 + i;
+          float a[kMaxC], b[kMaxC], o[kMaxC];
 #pragma unroll
           for (int c = 0; c < C; ++c) {
-            b[c] = Zio[c * plane + (size_t)n * H + j];
+            a[c] = v[c][half * 8 + i];
+            b[c] = zin[c][i];
             o[c] = 0.f;
           }
           jet_bwd<ACT>(net.NF, net.NS, b, a, o);
+          if (j < H && n < m) {
 #pragma unroll
-          for (int c = 0; c < C; ++c) Zio[c * plane + (size_t)n * H + j] = o[c];
+            for (int c = 0; c < C; ++c) Zio[c * plane + (size_t)n * H + j] = o[c];
+          }
+        }
+      }
+    } else {
+      tc::tmem_ld_wait();
+      if (j < a_rows) {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          const int n = n0 + g * 16 + i;
+          if (n < m) {
+            float a[kMaxC], o[kMaxC];
+#pragma unroll
+            for (int c = 0; c < C; ++c) a[c] = v[c][i];
+            a[0] += bj;
+            if (EPI == 0) {
+              jet_fwd<ACT>(net.NF, net.NS, a, o);
+#pragma unroll
+              for (int c = 0; c < C; ++c) {
+                Zio[c * plane + (size_t)n * H + j] = a[c];
+                Hout[c * plane + (size_t)n * H + j] = o[c];
+              }
+            } else {  // EPI 2: output-layer values y[n][c][o = j]
+#pragma unroll
+              for (int c = 0; c < C; ++c) Zio[((size_t)n * C + c) * 4 + j] = a[c];
+            }
+          }
         }
       }
     }
@@ -293,7 +319,7 @@ __global__ void transpose_kernel(const float* __restrict__ W, float* __restrict_
 
 template <int C, int ACT, int EPI>
 int launch_rows_c(const WNet& n, const float* Bsrc, const float* Aw, const float* bias, float* Zio, float* Hout, int m, int Mc,
-                  cudaStream_t st) {
+                  int a_rows, cudaStream_t st) {
   using T = TileCfg<C>;
   const size_t smem = (size_t)(kKT / 4) * (129 + T::N + 1) * 4 * sizeof(float);
   static bool attr_set = false;
@@ -302,8 +328,8 @@ int launch_rows_c(const WNet& n, const float* Bsrc, const float* Aw, const float
     if (e != cudaSuccess) return (int)e;
     attr_set = true;
   }
-  dim3 grid((m + T::P - 1) / T::P, (n.H + 127) / 128);
-  tc_rows_kernel<C, ACT, EPI><<<grid, 256, smem, st>>>(n, Bsrc, Aw, bias, Zio, Hout, m, Mc);
+  dim3 grid((m + T::P - 1) / T::P, (a_rows + 127) / 128);
+  tc_rows_kernel<C, ACT, EPI><<<grid, 256, smem, st>>>(n, Bsrc, Aw, bias, Zio, Hout, m, Mc, a_rows);
   count_launch(1);
   return (int)cudaGetLastError();
 }
@@ -313,8 +339,9 @@ int launch_rows_c(const WNet& n, const float* Bsrc, const float* Aw, const float
 template <int ACT, int EPI>
 int tc_launch_rows(const WNet& n, const float* Bsrc, const float* Aw, const float* bias, float* Zio, float* Hout, int m, int Mc,
                    cudaStream_t st) {
+  const int a_rows = (EPI == 2) ? n.n_out : n.H;
   switch (n.C) {
-#define CASE(Cc) case Cc: return launch_rows_c<Cc, ACT, EPI>(n, Bsrc, Aw, bias, Zio, Hout, m, Mc, st);
+#define CASE(Cc) case Cc: return launch_rows_c<Cc, ACT, EPI>(n, Bsrc, Aw, bias, Zio, Hout, m, Mc, a_rows, st);
     CASE(1) CASE(2) CASE(3) CASE(4) CASE(5) CASE(6) CASE(7)
 #undef CASE
   }
@@ -323,7 +350,8 @@ int tc_launch_rows(const WNet& n, const float* Bsrc, const float* Aw, const floa
 
 #define INST(A)                                                                                                              \
   template int tc_launch_rows<A, 0>(const WNet&, const float*, const float*, const float*, float*, float*, int, int, cudaStream_t); \
-  template int tc_launch_rows<A, 1>(const WNet&, const float*, const float*, const float*, float*, float*, int, int, cudaStream_t);
+  template int tc_launch_rows<A, 1>(const WNet&, const float*, const float*, const float*, float*, float*, int, int, cudaStream_t); \
+  template int tc_launch_rows<A, 2>(const WNet&, const float*, const float*, const float*, float*, float*, int, int, cudaStream_t);
 INST(PINN_ACT_TANH)
 INST(PINN_ACT_SILU)
 INST(PINN_ACT_SIN)
