@@ -126,21 +126,32 @@ static int narrow_plan(const pinn_mlp* m, const pinn_jets* j, NarrowPlan* pl, bo
   return 0;
 }
 
+// grid: ceil(n_params / 32) blocks of 256 threads = 32 outputs x 8 CTA groups; each thread sums
+// its CTA group in fixed order, then the 8 partial sums are added in fixed order (deterministic).
 __global__ void finalize_kernel(const float* gpart, const float* lpart, int max_cta, int PP, int n_in, int n_out,
                                 int Hreal, int Hp, int L, int64_t n_params, float* flat_grad, int add, float* losses,
                                 int n_dom) {
-  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  __shared__ float red[8][33];
+  const int il = threadIdx.x & 31, cg = threadIdx.x >> 5;
+  const int64_t i = (int64_t)blockIdx.x * 32 + il;
+  float s = 0.f;
   if (i < n_params) {
     const Layout lay(Hp, L);
     const int idx = flat_to_layout(n_in, n_out, Hreal, lay, i);
-    float s = 0.f;
-    for (int c = 0; c < max_cta; ++c) s += gpart[(size_t)c * PP + idx];
-    flat_grad[i] = add ? flat_grad[i] + s : s;
+    for (int c = cg; c < max_cta; c += 8) s += gpart[(size_t)c * PP + idx];
+  }
+  red[cg][il] = s;
+  __syncthreads();
+  if (cg == 0 && i < n_params) {
+    float t = 0.f;
+#pragma unroll
+    for (int g = 0; g < 8; ++g) t += red[g][il];
+    flat_grad[i] = add ? flat_grad[i] + t : t;
   }
   if (blockIdx.x == 0 && threadIdx.x < n_dom && losses) {
-    float s = 0.f;
-    for (int c = 0; c < max_cta; ++c) s += lpart[(size_t)threadIdx.x * max_cta + c];
-    losses[threadIdx.x] = s;
+    float t = 0.f;
+    for (int c = 0; c < max_cta; ++c) t += lpart[(size_t)threadIdx.x * max_cta + c];
+    losses[threadIdx.x] = t;
   }
 }
 
@@ -284,7 +295,7 @@ int pinn_step_finalize(const pinn_mlp* m, const pinn_jets* j, void* ws, int64_t 
     if (n_domains > 256) return fail(PINN_E_INVALID, "too many domains");
     const int64_t np = pinn_param_count(m);
     const int threads = 256;
-    const int blocks = (int)((np + threads - 1) / threads);
+    const int blocks = (int)((np + 31) / 32);
     finalize_kernel<<<blocks, threads, 0, st>>>((const float*)ws, (const float*)((char*)ws + gbytes), kMaxCta, pl.PP,
                                                 m->n_in, m->n_out, m->width, pl.Hp, pl.L, np, flat_grad, add_to_grad,
                                                 losses, n_domains);

@@ -282,17 +282,31 @@ struct NarrowWarp {
             acc[c].x += w.x * hv; acc[c].y += w.y * hv; acc[c].z += w.z * hv; acc[c].w += w.w * hv;
           }
         }
-        store_row_tile(a_row, j4, acc);  // scratch for the reload below
         if (p.mode != MODE_FWD) {
 #pragma unroll
           for (int c = 0; c < C; ++c) st4(gs + stash_off(l, c, j4, lane_id), acc[c]);
         }
+        // activation of this tile inside the loop: its MUFU/ALU work overlaps the next tile's FMAs
+        f4 ht[C];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          float z[C], h[C];
+#pragma unroll
+          for (int c = 0; c < C; ++c) z[c] = (&acc[c].x)[e];
+          unit_fwd(z, h);
+#pragma unroll
+          for (int c = 0; c < C; ++c) (&ht[c].x)[e] = h[c];
+        }
+        store_row_tile(a_row, j4, ht);  // scratch: hin is still being read by the remaining tiles
       }
 #pragma unroll
       for (int k4 = 0; k4 < H4; ++k4) {
-        f4 zt[C];
-        load_row_tile(a_row, k4, zt);
-        act_tile_fwd(zt, k4, hin);
+        f4 ht[C];
+        load_row_tile(a_row, k4, ht);
+#pragma unroll
+        for (int c = 0; c < C; ++c) {
+          hin[c][k4 * 4 + 0] = ht[c].x; hin[c][k4 * 4 + 1] = ht[c].y; hin[c][k4 * 4 + 2] = ht[c].z; hin[c][k4 * 4 + 3] = ht[c].w;
+        }
       }
     }
     // output layer: y[c][o] = sum_k Woutt[k][o] * h[c][k] (+ bout)

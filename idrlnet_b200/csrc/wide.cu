@@ -488,9 +488,9 @@ __global__ void __launch_bounds__(256) head_point_kernel(WNet net, const __grid_
 // head_bwd: streaming over (point, unit): zbar_L = act'(Z_L; Wout^T ybar) in place, dWout += ybar^T h_L.
 // grid (ceil(H/128), kBlocks); block = 128 units x 4 point lanes; blockIdx.y is the partial slot.
 template <int ACT, int C>
-__global__ void __launch_bounds__(512) head_bwd_kernel(WNet net, const float* __restrict__ Yb, float* __restrict__ ZL,
-                                                       const float* __restrict__ HL, int m, int Mc, float* __restrict__ part) {
-  __shared__ float red[4][4][129];
+__global__ void __launch_bounds__(1024) head_bwd_kernel(WNet net, const float* __restrict__ Yb, float* __restrict__ ZL,
+                                                        const float* __restrict__ HL, int m, int Mc, float* __restrict__ part) {
+  __shared__ float red[8][4][129];
   const int H = net.H, O = net.n_out;
   const int jl = threadIdx.x & 127, pl = threadIdx.x >> 7;
   const int j = blockIdx.x * 128 + jl;
@@ -502,23 +502,37 @@ __global__ void __launch_bounds__(512) head_bwd_kernel(WNet net, const float* __
     float wo[4];
 #pragma unroll
     for (int o = 0; o < 4; ++o) wo[o] = (o < O) ? net.W[net.L][o * H + j] : 0.f;
-    for (int n = nb + pl; n < ne; n += 4) {
-      float z[kMaxC], hb[kMaxC], zb[kMaxC], h[C];
+    for (int n = nb + pl; n < ne; n += 16) {  // two points (n, n + 8) in flight
+      float z[2][kMaxC], h[2][C];
+      float4 yb[2][C];
 #pragma unroll
-      for (int c = 0; c < C; ++c) {
-        z[c] = ZL[c * plane + (size_t)n * H + j];
-        h[c] = HL[c * plane + (size_t)n * H + j];
+      for (int u = 0; u < 2; ++u) {
+        const int nn = n + 8 * u;
+#pragma unroll
+        for (int c = 0; c < C; ++c) {
+          const bool ok = nn < ne;
+          z[u][c] = ok ? ZL[c * plane + (size_t)nn * H + j] : 0.f;
+          h[u][c] = ok ? HL[c * plane + (size_t)nn * H + j] : 0.f;
+          yb[u][c] = ok ? *reinterpret_cast<const float4*>(Yb + ((size_t)nn * C + c) * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
       }
 #pragma unroll
-      for (int c = 0; c < C; ++c) {
-        const float4 yb = *reinterpret_cast<const float4*>(Yb + ((size_t)n * C + c) * 4);
-        hb[c] = wo[0] * yb.x + wo[1] * yb.y + wo[2] * yb.z + wo[3] * yb.w;
-        gW[0] += yb.x * h[c]; gW[1] += yb.y * h[c]; gW[2] += yb.z * h[c]; gW[3] += yb.w * h[c];
-        zb[c] = 0.f;
-      }
-      jet_bwd<ACT>(net.NF, net.NS, z, hb, zb);
+      for (int u = 0; u < 2; ++u) {
+        const int nn = n + 8 * u;
+        float hb[kMaxC], zb[kMaxC];
 #pragma unroll
-      for (int c = 0; c < C; ++c) ZL[c * plane + (size_t)n * H + j] = zb[c];
+        for (int c = 0; c < C; ++c) {
+          const float4 y4 = yb[u][c];
+          hb[c] = wo[0] * y4.x + wo[1] * y4.y + wo[2] * y4.z + wo[3] * y4.w;
+          gW[0] += y4.x * h[u][c]; gW[1] += y4.y * h[u][c]; gW[2] += y4.z * h[u][c]; gW[3] += y4.w * h[u][c];
+          zb[c] = 0.f;
+        }
+        jet_bwd<ACT>(net.NF, net.NS, z[u], hb, zb);
+        if (nn < ne) {
+#pragma unroll
+          for (int c = 0; c < C; ++c) ZL[c * plane + (size_t)nn * H + j] = zb[c];
+        }
+      }
     }
   }
 #pragma unroll
@@ -526,8 +540,12 @@ __global__ void __launch_bounds__(512) head_bwd_kernel(WNet net, const float* __
   __syncthreads();
   if (pl == 0 && j < H) {
     const int hstride = O * H + O + 1;
-    for (int o = 0; o < O; ++o)
-      part[(size_t)blockIdx.y * hstride + o * H + j] += red[0][o][jl] + red[1][o][jl] + red[2][o][jl] + red[3][o][jl];
+    for (int o = 0; o < O; ++o) {
+      float sum = 0.f;
+#pragma unroll
+      for (int g = 0; g < 8; ++g) sum += red[g][o][jl];
+      part[(size_t)blockIdx.y * hstride + o * H + j] += sum;
+    }
   }
 }
 
@@ -711,7 +729,7 @@ int run_chunks(const WNet& n, const WideLayout& wl, float* ws, int mode, const p
     head_point_kernel<C_><<<pb, 256, 0, st>>>(n, ha, yb, m);                                                \
     count_launch(1);                                                                                        \
     if (mode != W_MODE_FWD) {                                                                               \
-      head_bwd_kernel<ACT, C_><<<bgrid, 512, 0, st>>>(n, yb, zl, hl, m, wl.Mc, ws + wl.head);               \
+      head_bwd_kernel<ACT, C_><<<bgrid, 1024, 0, st>>>(n, yb, zl, hl, m, wl.Mc, ws + wl.head);               \
       count_launch(1);                                                                                      \
     }                                                                                                       \
   } break;

@@ -124,25 +124,30 @@ __global__ void __launch_bounds__(256) tc_rows_kernel(WNet net, const float* __r
 #pragma unroll
     for (int c = 0; c < C; ++c) tc::tmem_ld16(tmem + lane_base + c * P + g * 16, v[c]);
     if (EPI == 1) {
-      // reverse layer: fetch Z_{l-1} for 8 points at a time while the TMEM loads are in flight
+      // reverse layer: Z_{l-1} is fetched 4 points ahead (double-buffered registers) so the global
+      // loads of the next quad are in flight while the current quad's adjoints are computed
+      float zin[2][C][4];
+      auto fetch = [&](int quad, float (&dst)[C][4]) {
 #pragma unroll
-      for (int half = 0; half < 2; ++half) {
-        float zin[C][8];
+        for (int i = 0; i < 4; ++i) {
+          const int n = n0 + g * 16 + quad * 4 + i;
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const int n = n0 + g * 16 + half * 8 + i;
-#pragma unroll
-          for (int c = 0; c < C; ++c) zin[c][i] = (j < H && n < m) ? Zio[c * plane + (size_t)n * H + j] : 0.f;
+          for (int c = 0; c < C; ++c) dst[c][i] = (j < H && n < m) ? Zio[c * plane + (size_t)n * H + j] : 0.f;
         }
-        if (half == 0) tc::tmem_ld_wait();
+      };
+      fetch(0, zin[0]);
+      tc::tmem_ld_wait();
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const int n = n0 + g * 16 + half * 8 + i;
+      for (int quad = 0; quad < 4; ++quad) {
+        if (quad + 1 < 4) fetch(quad + 1, zin[(quad + 1) & 1]);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int n = n0 + g * 16 + quad * 4 + i;
           float a[kMaxC], b[kMaxC], o[kMaxC];
 #pragma unroll
           for (int c = 0; c < C; ++c) {
-            a[c] = v[c][half * 8 + i];
-            b[c] = zin[c][i];
+            a[c] = v[c][quad * 4 + i];
+            b[c] = zin[quad & 1][c][i];
             o[c] = 0.f;
           }
           jet_bwd<ACT>(net.NF, net.NS, b, a, o);
