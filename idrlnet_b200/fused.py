@@ -111,6 +111,25 @@ class NetPack:
         self._grad_wn: Dict[int, Tuple[torch.Tensor, torch.Tensor]] = {}
         self._mlp = None
         self._mlp_key = None
+        self._probe()
+
+    def _probe(self) -> None:
+        """The kernels evaluate `act(W h + b)` layer by layer.  A module with the right layers
+        but another forward (e.g. Siren's omega scaling, skip connections) must not be fused:
+        compare the module with that formula on a few random points."""
+        fn = {"tanh": torch.tanh, "silu": torch.nn.functional.silu, "sin": torch.sin}[self.act]
+        with torch.no_grad():
+            g = torch.Generator(device="cpu").manual_seed(1234)
+            x = (torch.rand(16, self.n_in, generator=g) * 2 - 1).to(self.device)
+            want = self.module(x)
+            h = x
+            for i, l in enumerate(self.layers):
+                W = torch._weight_norm(l.weight_v, l.weight_g, 0) if self.weight_norm[i] else l.weight
+                h = torch.nn.functional.linear(h, W, l.bias)
+                if i < self.n_hidden:
+                    h = fn(h)
+        if want.shape != h.shape or not torch.allclose(want, h, rtol=1e-4, atol=1e-5 * float(h.abs().max() + 1e-30)):
+            raise cp.NotFusable("module.forward is not a plain Linear/activation stack")
 
     # -- parameters ---------------------------------------------------------
     def raw_params(self, i: int):
