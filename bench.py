@@ -452,7 +452,7 @@ def run_ours(args):
     cfg = workload_configs()[args.config]
     sizes = scaled_sizes(cfg, args.sample) if args.sample else None
     trainer = Trainer(cfg, device, world=world, sizes=sizes, precision=args.precision)
-    wide_tc = args.precision == "tf32" and trainer.pack.width > 32
+    wide_tc = args.precision.startswith("tf32") and trainer.pack.width > 32
     rng = np.random.default_rng(1000 + rank)
     pts_per_step = trainer.points_per_step
     n_timed = trainer.sizes[cfg["domains"][cfg["timed"]][1]]
@@ -595,7 +595,7 @@ def main():
     ap.add_argument("--baseline-device", default="cpu", choices=["cpu", "cuda"],
                     help="--impl reference: where the reference algorithm (torch autograd) runs")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--precision", default="fp32", choices=["fp32", "tf32"],
+    ap.add_argument("--precision", default="fp32", choices=["fp32", "tf32", "tf32_streamed"],
                     help="layer GEMMs of wide nets: FP32 FMA (parity) or tcgen05 TF32; narrow nets are always FP32")
     args = ap.parse_args()
     if args.impl == "reference":

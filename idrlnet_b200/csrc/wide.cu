@@ -318,54 +318,6 @@ struct HeadArgs {
 };
 enum { W_MODE_FUSED = 0, W_MODE_FWD = 1, W_MODE_BWD = 2 };
 
-template <int C>
-__device__ __forceinline__ void residual_loss_rt(const pinn_domain& dm, int64_t n, const float* x, const float (*y)[4],
-                                                 float (*yb)[4], float& loss_acc) {
-  float sym[PINN_SYM_COUNT];
-  float sg[PINN_SYM_COORD0];
-  for (int i = 0; i < PINN_SYM_COUNT; ++i) sym[i] = 0.f;
-  for (int i = 0; i < PINN_SYM_COORD0; ++i) sg[i] = 0.f;
-  for (int c = 0; c < C; ++c)
-    for (int o = 0; o < 4; ++o) sym[c * 4 + o] = y[c][o];
-  for (int d = 0; d < 4; ++d) sym[PINN_SYM_COORD0 + d] = x[d];
-  for (int a = 0; a < dm.n_aux; ++a) sym[PINN_SYM_AUX0 + a] = dm.aux[a][n];
-  const float area = dm.area ? dm.area[n] : dm.area_const;
-  float loss = 0.f;
-  for (int e = 0; e < dm.n_eq; ++e) {
-    const pinn_equation& q = dm.eq[e];
-    float r = 0.f;
-    for (int t = q.term_begin; t < q.term_end; ++t) {
-      const pinn_term& tm = dm.terms[t];
-      float prod = tm.coef;
-      for (int f = 0; f < tm.n_fac; ++f) prod *= sym[tm.fac[f]];
-      r += prod;
-    }
-    const float tgt = q.target ? q.target[n] : q.target_const;
-    const float lam = q.lambda ? q.lambda[n] : q.lambda_const;
-    const float diff = r - tgt, w = lam * area;
-    float f0, f1;
-    if (dm.loss_kind == PINN_LOSS_SQUARE) { f0 = diff * diff; f1 = 2.0f * diff; }
-    else if (dm.loss_kind == PINN_LOSS_L1) { f0 = fabsf(diff); f1 = (diff > 0.f) ? 1.0f : ((diff < 0.f) ? -1.0f : 0.f); }
-    else { f0 = diff; f1 = 1.0f; }
-    loss += f0 * w;
-    const float g = f1 * w * dm.sigma;
-    for (int t = q.term_begin; t < q.term_end; ++t) {
-      const pinn_term& tm = dm.terms[t];
-      for (int f = 0; f < tm.n_fac; ++f) {
-        const int id = tm.fac[f];
-        if (id >= PINN_SYM_COORD0) continue;
-        float prod = tm.coef * g;
-        for (int f2 = 0; f2 < tm.n_fac; ++f2)
-          if (f2 != f) prod *= sym[tm.fac[f2]];
-        sg[id] += prod;
-      }
-    }
-  }
-  loss_acc += loss;
-  for (int c = 0; c < C; ++c)
-    for (int o = 0; o < 4; ++o) yb[c][o] = sg[c * 4 + o];
-}
-
 // out_layer: y[n][c][o] = sum_k Wout[o][k] h_L[c][n][k] + bout[o]*(c==0), FP32 (the output values feed
 // residuals with cancellations, so this small skinny product stays off the TF32 pipe).  One warp
 // handles 4 rows (c, n) per iteration (16 loads in flight per lane), lanes stride over k.
@@ -620,7 +572,7 @@ bool make_net(const pinn_mlp* m, const pinn_jets* j, WNet* n) {
   memset(n, 0, sizeof(*n));
   n->n_in = m->n_in; n->n_out = m->n_out; n->L = m->n_hidden; n->H = m->width; n->act = m->act;
   n->NF = j->n_first; n->NS = j->n_second; n->C = 1 + n->NF + n->NS;
-  n->precision = (m->precision == 1) ? 1 : 0;
+  n->precision = (m->precision == PINN_PREC_TF32 || m->precision == PINN_PREC_TF32_STREAMED) ? 1 : 0;
   for (int i = 0; i < 4; ++i) n->first_in[i] = j->first_in[i];
   for (int l = 0; l <= m->n_hidden; ++l) { n->W[l] = m->W[l]; n->b[l] = m->b[l]; }
   return true;
@@ -650,7 +602,11 @@ WideLayout make_layout(const WNet& n, int n_dom) {
   wl.head = off; off += (int64_t)kBlocks * (n.n_out * n.H + n.n_out + 1);
   wl.loss_slots = off; off += (int64_t)kMaxDomains * kBlocks;
   off = (off + 3) / 4 * 4;
-  wl.wt = off; off += (int64_t)(n.L - 1) * n.H * n.H;  // W_l^T for the tensor-core reverse GEMM
+  {  // W_l^T for the streamed tensor-core reverse GEMM, or the prepared weight tiles of the on-chip kernel
+    int64_t wt = (int64_t)(n.L - 1) * n.H * n.H;
+    if (n.H <= 128 && fused_wide_wprep_floats(n) > wt) wt = fused_wide_wprep_floats(n);
+    wl.wt = off; off += (wt + 3) / 4 * 4;
+  }
   wl.acc_end = off;
   wl.Z = off; off += planes;
   wl.Hb = off; off += planes;
@@ -796,11 +752,26 @@ int run_mode(const pinn_mlp* m, const pinn_jets* j, int mode, const pinn_domain*
   if (!accumulate && mode != W_MODE_FWD)  // clear every partial slot (all domains' loss slots included)
     CK(cudaMemsetAsync(w + wl.dw, 0, (size_t)(wl.acc_end - wl.dw) * 4, st));
   int rc = 0;
-  if (n.precision && mode != W_MODE_FWD)
+  const bool on_chip = mode == W_MODE_FUSED && fused_wide_supported(n) && m->precision == PINN_PREC_TF32 &&
+                       fused_wide_stash_floats(n) <= (int64_t)2 * n.L * n.C * wl.Mc * n.H;
+  if (n.precision && mode != W_MODE_FWD && !on_chip)
     for (int l = 2; l <= n.L; ++l) {
       rc = tc_transpose(n.W[l - 1], w + wl.wt + (size_t)(l - 2) * n.H * n.H, n.H, st);
       if (rc) return rc;
     }
+  if (on_chip) {
+    // whole step on chip (wide_fused.cu); same partial slots, same finalize
+    rc = fused_wide_prep(n, w + wl.wt, st);
+    if (rc) return rc;
+#define RUNF(A)                                                                                                   \
+  rc = fused_wide_launch<A>(n, dom, w + wl.Z, w + wl.wt, w + wl.dw, w + wl.db, w + wl.first, w + wl.head, wl.n_splits, st)
+    ACT_SWITCH(n.act, RUNF);
+#undef RUNF
+    if (rc) return rc;
+    wide_collect_loss_kernel<<<1, 256, 0, st>>>(w, wl, n.n_out * n.H + n.n_out + 1, slot);
+    count_launch(1);
+    return (int)cudaGetLastError();
+  }
 #define RUN(A) rc = run_chunks<A>(n, wl, w, mode, dom, N, coords, jets_out, jets_bar, st)
   ACT_SWITCH(n.act, RUN);
 #undef RUN

@@ -1,0 +1,503 @@
+// Wide nets, H <= 128, 2..4 hidden layers: the whole training step of a tile of 16 points on chip.
+//
+// One persistent CTA per SM walks over tiles of P = 16 collocation points.  The jets of the tile
+// never leave the SM between layers: each layer's GEMM runs on the tensor cores (tcgen05.mma
+// kind::tf32, accumulators in TMEM), in the swapped orientation of wide_tc.cu (TMEM lane = hidden
+// unit, column = channel * 16 + point), and the epilogue thread that owns a unit writes the next
+// layer's operand straight back into shared memory in the K-major canonical layout.  The only
+// forward state kept for the reverse pass is the pre-activation jet of layers 2..L, stashed in a
+// per-CTA global scratch that every tile overwrites (L2-resident, as in the narrow kernel).  The
+// weight gradients dW_l = zbar_l^T h_{l-1} are tensor-core GEMMs contracting over the tile's
+// (channel, point) pairs whose accumulators stay in TMEM for the whole kernel (3 x 128 columns)
+// and are written once per CTA into the per-split partial slots of the layer-streamed path, so
+// wide_finalize and the deterministic reduction are shared.  The output layer, the residual and
+// the loss are FP32 SIMT code.  HBM traffic per point: the coordinates (+ targets/lambda columns).
+#include <cuda_runtime.h>
+#include <stdio.h>
+#include <string.h>
+
+#include "tc_common.cuh"
+#include "wide_internal.cuh"
+
+namespace pinn {
+namespace {
+
+constexpr int kP = 16;       // points per tile
+constexpr int kMaxHid = 4;   // hidden layers supported (TMEM: 128 + 3 * 128 columns)
+
+struct FusedArgs {
+  pinn_domain dom;
+  const float* xs[PINN_MAX_IN];
+  int64_t n_points;
+  float* stash;          // [cta][(L-1)][C][kP][128]
+  const float* wprep;    // [2*(l-2) + dir][Kq*129*4]: W_l (dir 0) / W_l^T (dir 1), TF32-rounded, canonical padded tiles
+  float* dw_part;        // [(l-2)][n_splits][H*H]
+  float* db_part;        // [(l-2)][kBlocks][8][H]
+  float* first_part;     // [kBlocks][8][H]
+  float* head_part;      // [kBlocks][O*H + O + 1]
+  int n_splits;
+  int first_launch;      // unused (slots are always accumulated)
+};
+
+template <int C, int ACT>
+__global__ void __launch_bounds__(256, 1) wide_fused_kernel(WNet net, const __grid_constant__ FusedArgs fa) {
+  constexpr int N = C * kP;
+  const int H = net.H, L = net.L, O = net.n_out;
+  const int H8 = (H + 7) & ~7, Kq = H8 / 4, N2 = (H + 15) & ~15;
+  extern __shared__ __align__(128) float sm[];
+  __shared__ uint64_t bar[2];  // [0]: MMA completion, [1]: weight tile landed
+  __shared__ uint32_t tmem_slot;
+  float* sW = sm;                           // [Kq][129][4]      A operand: W_l or W_l^T
+  float* sX = sW + Kq * 129 * 4;            // [Kq][N + 1][4]    B operand: h_{l-1} / zbar_l, K = unit
+  float* sZt = sX + Kq * (N + 1) * 4;       // [N/4][129][4]     A operand of dW: zbar_l, K = (channel, point)
+  float* sHt = sZt + (N / 4) * 129 * 4;     // [N/4][N2 + 1][4]  B operand of dW: h_{l-1}, K = (channel, point)
+  float* sY = sHt + (N / 4) * (N2 + 1) * 4; // [N][4]  y, then ybar
+  float* sXc = sY + 2 * N * 4;              // [kP][4] coordinates of the tile
+  float* sWo = sXc + kP * 4;                // [4][128] Wout[o][k]
+  float* sRed = sWo + 4 * 128;              // scratch for the final reductions
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int j = (warp & 3) * 32 + lane;     // hidden unit owned by this thread (TMEM lane)
+  const int half = warp >> 2;               // which 8 of the tile's 16 points this thread handles
+  const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
+  const bool unit_ok = j < H;
+
+  if (tid == 0) {
+    tc::mbar_init(&bar[0], 1);
+    tc::mbar_init(&bar[1], 1);
+    tc::fence_mbar_init();
+  }
+  if (warp == 0) tc::tmem_alloc(&tmem_slot, 512);
+  for (int i = tid; i < 4 * 128; i += 256) {
+    const int o = i >> 7, k = i & 127;
+    sWo[i] = (o < O && k < H) ? net.W[L][o * H + k] : 0.f;
+  }
+  tc::tc_fence_before();
+  __syncthreads();
+  tc::tc_fence_after();
+  const uint32_t tmem = tmem_slot;
+  uint32_t phase = 0, wphase = 0;
+  // weight tiles are consumed in a fixed cyclic order per point tile: W_2 .. W_L, W_L^T .. W_2^T
+  const uint32_t wbytes = (uint32_t)(Kq * 129 * 4 * sizeof(float));
+  const int n_seq = 2 * (L - 1);
+  int wseq = 0;  // next tile to fetch (thread 0 only)
+  auto fetch_weights = [&]() {  // thread 0: asynchronous bulk copy of the next weight tile into sW
+    const int sidx = wseq % n_seq;
+    const int l = sidx < L - 1 ? 2 + sidx : L - (sidx - (L - 1));
+    const int dir = sidx < L - 1 ? 0 : 1;
+    tc::mbar_expect_tx(&bar[1], wbytes);
+    tc::bulk_copy_g2s(sW, fa.wprep + (size_t)(2 * (l - 2) + dir) * (wbytes / 4), wbytes, &bar[1]);
+    ++wseq;
+  };
+  if (tid == 0 && blockIdx.x < (fa.n_points + kP - 1) / kP) fetch_weights();
+
+  // per-unit constants in registers
+  float w1[4] = {0.f, 0.f, 0.f, 0.f}, b1 = 0.f, bl[kMaxHid] = {0.f, 0.f, 0.f, 0.f}, wo[4];
+  if (unit_ok) {
+    for (int d = 0; d < net.n_in; ++d) w1[d] = net.W[0][j * net.n_in + d];
+    b1 = net.b[0][j];
+#pragma unroll
+    for (int l = 2; l <= kMaxHid; ++l)
+      if (l <= L) bl[l - 1] = net.b[l - 1][j];
+  }
+#pragma unroll
+  for (int o = 0; o < 4; ++o) wo[o] = sWo[o * 128 + j];
+  float w1f[3] = {0.f, 0.f, 0.f};
+#pragma unroll
+  for (int i = 0; i < 3; ++i)
+    if (i < net.NF) {
+      const int d = net.first_in[i];
+      w1f[i] = d == 0 ? w1[0] : d == 1 ? w1[1] : d == 2 ? w1[2] : w1[3];
+    }
+
+  // per-unit gradient accumulators (both point halves accumulate; summed at the end)
+  float g_w1[4] = {0.f, 0.f, 0.f, 0.f}, g_b[kMaxHid + 1] = {0.f, 0.f, 0.f, 0.f, 0.f}, g_wo[4] = {0.f, 0.f, 0.f, 0.f};
+  float g_bo[4] = {0.f, 0.f, 0.f, 0.f}, loss = 0.f;
+
+  float* stash = fa.stash + (size_t)blockIdx.x * (L - 1) * C * kP * 128;
+  const uint32_t idesc_x = tc::idesc_tf32(N, 0, 0), idesc_w = tc::idesc_tf32(N2, 0, 0);
+  const int64_t n_tiles = (fa.n_points + kP - 1) / kP;
+  bool first_tile = true;
+
+  auto layer1 = [&](const float* x, float (&z)[kMaxC]) {
+    float v = b1;
+#pragma unroll
+    for (int d = 0; d < 4; ++d) v += w1[d] * x[d];
+    z[0] = v;
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+      if (i < net.NF) z[1 + i] = w1f[i];
+#pragma unroll
+    for (int s = 0; s < 3; ++s)
+      if (s < net.NS) z[1 + net.NF + s] = 0.f;
+  };
+  // element (row q = c*kP + p, K index = unit j) of the K = unit operand
+  auto sx_at = [&](int q) -> float& { return sX[((j >> 2) * (N + 1) + q) * 4 + (j & 3)]; };
+  // element (row = unit j, K index q) of the K = (channel, point) operands
+  auto szt_at = [&](int q) -> float& { return sZt[((q >> 2) * 129 + j) * 4 + (q & 3)]; };
+  auto sht_at = [&](int q) -> float& { return sHt[((q >> 2) * (N2 + 1) + j) * 4 + (q & 3)]; };
+
+  auto run_mma = [&](bool with_dw, int l, bool more) {  // D = sW * sX^T  (+ optionally D2_l += sZt * sHt^T)
+    tc::fence_async_smem();
+    __syncthreads();
+    if (tid == 0) {
+      if (!tc::mbar_wait(&bar[1], wphase & 1)) __trap();  // weight tile landed
+      ++wphase;
+      tc::tc_fence_after();
+      for (int ks = 0; ks < H8 / 8; ++ks) {
+        const uint64_t da = tc::smem_desc(tc::smem_u32(sW) + ks * 2 * (129 * 16), 129 * 16, 128);
+        const uint64_t db = tc::smem_desc(tc::smem_u32(sX) + ks * 2 * ((N + 1) * 16), (N + 1) * 16, 128);
+        tc::mma_tf32(tmem, da, db, idesc_x, ks > 0 ? 1u : 0u);
+      }
+      if (with_dw) {
+        const uint32_t d2 = tmem + 128 + (uint32_t)(l - 2) * 128;
+        for (int ks = 0; ks < N / 8; ++ks) {
+          const uint64_t da = tc::smem_desc(tc::smem_u32(sZt) + ks * 2 * (129 * 16), 129 * 16, 128);
+          const uint64_t db = tc::smem_desc(tc::smem_u32(sHt) + ks * 2 * ((N2 + 1) * 16), (N2 + 1) * 16, 128);
+          tc::mma_tf32(d2, da, db, idesc_w, (first_tile && ks == 0) ? 0u : 1u);
+        }
+      }
+      tc::mma_commit(&bar[0]);
+    }
+    if (!tc::mbar_wait(&bar[0], phase & 1)) __trap();
+    ++phase;
+    tc::tc_fence_after();
+    if (tid == 0 && more) fetch_weights();  // sW is free again: overlap the next tile's copy with the epilogue
+  };
+
+  for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    const int64_t n0 = tile * kP;
+    __syncthreads();  // previous tile fully consumed
+    if (tid < kP * 4) {
+      const int p = tid >> 2, d = tid & 3;
+      sXc[tid] = (d < net.n_in && n0 + p < fa.n_points) ? fa.xs[d][n0 + p] : 0.f;
+    }
+    __syncthreads();
+
+    // ---- hidden layer 1 (SIMT): h_1 -> sX -------------------------------------------------
+#pragma unroll 2
+    for (int pp = 0; pp < kP / 2; ++pp) {
+      const int p = half * (kP / 2) + pp;
+      float x[4] = {sXc[p * 4], sXc[p * 4 + 1], sXc[p * 4 + 2], sXc[p * 4 + 3]};
+      float z[kMaxC], h[kMaxC];
+      layer1(x, z);
+      jet_fwd<ACT>(net.NF, net.NS, z, h);
+      if (j < H8) {
+#pragma unroll
+        for (int c = 0; c < C; ++c) sx_at(c * kP + p) = unit_ok ? tc::to_tf32(h[c]) : 0.f;
+      }
+    }
+    // ---- hidden layers 2..L: tensor-core GEMM + activation epilogue -------------------------
+    for (int l = 2; l <= L; ++l) {
+      run_mma(false, 0, true);
+      float v[C][8];
+#pragma unroll
+      for (int c = 0; c < C; ++c) tc::tmem_ld8(tmem + lane_base + c * kP + half * 8, v[c]);
+      tc::tmem_ld_wait();
+      const float bias = l == 2 ? bl[1] : l == 3 ? bl[2] : bl[3];
+#pragma unroll
+      for (int pp = 0; pp < kP / 2; ++pp) {
+        const int p = half * (kP / 2) + pp;
+        float z[kMaxC], h[kMaxC];
+#pragma unroll
+        for (int c = 0; c < C; ++c) z[c] = v[c][pp];
+        z[0] += bias;
+        jet_fwd<ACT>(net.NF, net.NS, z, h);
+#pragma unroll
+        for (int c = 0; c < C; ++c) {
+          stash[(((size_t)(l - 2) * C + c) * kP + p) * 128 + j] = z[c];
+          if (j < H8) sx_at(c * kP + p) = unit_ok ? (l == L ? h[c] : tc::to_tf32(h[c])) : 0.f;
+        }
+      }
+      tc::tc_fence_before();
+    }
+    __syncthreads();
+    // ---- output layer (FP32 SIMT): y[q][o] = sum_k Wout[o][k] h_L[q][k] (h_L kept in FP32) ------
+    if (tid < N) {
+      const int q = tid;
+      float y[4] = {0.f, 0.f, 0.f, 0.f};
+      for (int k = 0; k < H; ++k) {
+        const float hv = sX[((k >> 2) * (N + 1) + q) * 4 + (k & 3)];
+#pragma unroll
+        for (int o = 0; o < 4; ++o) y[o] += sWo[o * 128 + k] * hv;
+      }
+      if (q < kP) {
+#pragma unroll
+        for (int o = 0; o < 4; ++o)
+          if (o < O) y[o] += net.b[L][o];
+      }
+      *reinterpret_cast<float4*>(sY + q * 4) = make_float4(y[0], y[1], y[2], y[3]);
+    }
+    __syncthreads();
+    // ---- residual, loss, ybar (one thread per point) ----------------------------------------
+    if (tid < kP) {
+      const int p = tid;
+      const int64_t ng = n0 + p;
+      float yb[C][4];
+      if (ng < fa.n_points) {
+        float y[C][4];
+#pragma unroll
+        for (int c = 0; c < C; ++c) {
+          const float4 t = *reinterpret_cast<const float4*>(sY + (c * kP + p) * 4);
+          y[c][0] = t.x; y[c][1] = t.y; y[c][2] = t.z; y[c][3] = t.w;
+        }
+        float x[4] = {sXc[p * 4], sXc[p * 4 + 1], sXc[p * 4 + 2], sXc[p * 4 + 3]};
+        residual_loss_rt<C>(fa.dom, ng, x, y, yb, loss);
+#pragma unroll
+        for (int o = 0; o < 4; ++o) g_bo[o] += yb[0][o];
+      } else {
+#pragma unroll
+        for (int c = 0; c < C; ++c)
+#pragma unroll
+          for (int o = 0; o < 4; ++o) yb[c][o] = 0.f;
+      }
+#pragma unroll
+      for (int c = 0; c < C; ++c)
+        *reinterpret_cast<float4*>(sY + N * 4 + (c * kP + p) * 4) = make_float4(yb[c][0], yb[c][1], yb[c][2], yb[c][3]);
+    }
+    __syncthreads();
+    const float* sYb = sY + N * 4;
+
+    // ---- reverse sweep -------------------------------------------------------------------
+    // step "l": produce zbar_l (into sX and sZt) and h_{l-1} (into sHt); then the tensor cores
+    // compute hbar_{l-1} = W_l^T zbar_l and dW_l += zbar_l^T h_{l-1}.
+    bool last_weights = false;
+    for (int l = L; l >= 1; --l) {
+      // stash reads do not depend on the tensor cores: issue them first
+      float zl[C][8], zp[C][8];
+#pragma unroll
+      for (int pp = 0; pp < kP / 2; ++pp) {
+        const int p = half * (kP / 2) + pp;
+#pragma unroll
+        for (int c = 0; c < C; ++c) {
+          zl[c][pp] = (l >= 2) ? stash[(((size_t)(l - 2) * C + c) * kP + p) * 128 + j] : 0.f;
+          zp[c][pp] = (l >= 3) ? stash[(((size_t)(l - 3) * C + c) * kP + p) * 128 + j] : 0.f;
+        }
+      }
+      float v[C][8];
+      if (l < L) {
+#pragma unroll
+        for (int c = 0; c < C; ++c) tc::tmem_ld8(tmem + lane_base + c * kP + half * 8, v[c]);
+        tc::tmem_ld_wait();
+      }
+#pragma unroll
+      for (int pp = 0; pp < kP / 2; ++pp) {
+        const int p = half * (kP / 2) + pp;
+        float x[4] = {sXc[p * 4], sXc[p * 4 + 1], sXc[p * 4 + 2], sXc[p * 4 + 3]};
+        float z[kMaxC], hb[kMaxC], zb[kMaxC], h[kMaxC];
+        if (l >= 2) {
+#pragma unroll
+          for (int c = 0; c < C; ++c) z[c] = zl[c][pp];
+        } else {
+          layer1(x, z);
+        }
+        // hbar_l: from ybar (l == L) or from the GEMM accumulators
+        if (l == L) {
+#pragma unroll
+          for (int c = 0; c < C; ++c) {
+            const float4 t = *reinterpret_cast<const float4*>(sYb + (c * kP + p) * 4);
+            hb[c] = wo[0] * t.x + wo[1] * t.y + wo[2] * t.z + wo[3] * t.w;
+          }
+          jet_fwd<ACT>(net.NF, net.NS, z, h);  // h_L for dWout
+#pragma unroll
+          for (int c = 0; c < C; ++c) {
+            const float4 t = *reinterpret_cast<const float4*>(sYb + (c * kP + p) * 4);
+            g_wo[0] += t.x * h[c]; g_wo[1] += t.y * h[c]; g_wo[2] += t.z * h[c]; g_wo[3] += t.w * h[c];
+          }
+        } else {
+#pragma unroll
+          for (int c = 0; c < C; ++c) hb[c] = v[c][pp];
+        }
+#pragma unroll
+        for (int c = 0; c < C; ++c) zb[c] = 0.f;
+        jet_bwd<ACT>(net.NF, net.NS, z, hb, zb);
+        if (!unit_ok) {
+#pragma unroll
+          for (int c = 0; c < C; ++c) zb[c] = 0.f;
+        }
+        if (l == 1) g_b[0] += zb[0];
+        else if (l == 2) g_b[1] += zb[0];
+        else if (l == 3) g_b[2] += zb[0];
+        else g_b[3] += zb[0];
+        if (l == 1) {
+#pragma unroll
+          for (int d = 0; d < 4; ++d) g_w1[d] += zb[0] * x[d];
+#pragma unroll
+          for (int i = 0; i < 3; ++i)
+            if (i < net.NF) {
+              const int d = net.first_in[i];
+              if (d == 0) g_w1[0] += zb[1 + i];
+              else if (d == 1) g_w1[1] += zb[1 + i];
+              else if (d == 2) g_w1[2] += zb[1 + i];
+              else g_w1[3] += zb[1 + i];
+            }
+        } else {
+          // operands of the next two GEMMs
+          float zq[kMaxC], hp[kMaxC];
+          if (l - 1 >= 2) {
+#pragma unroll
+            for (int c = 0; c < C; ++c) zq[c] = zp[c][pp];
+          } else {
+            layer1(x, zq);
+          }
+          jet_fwd<ACT>(net.NF, net.NS, zq, hp);
+#pragma unroll
+          for (int c = 0; c < C; ++c) {
+            const int q = c * kP + p;
+            const float zt = tc::to_tf32(zb[c]);
+            if (j < H8) sx_at(q) = zt;
+            szt_at(q) = zt;
+            if (j < N2) sht_at(q) = unit_ok ? tc::to_tf32(hp[c]) : 0.f;
+          }
+        }
+      }
+      if (l >= 2) {
+        tc::tc_fence_before();
+        last_weights = (l == 2) && (tile + gridDim.x >= n_tiles);  // nothing left to fetch after this GEMM
+        run_mma(true, l, !last_weights);
+      }
+    }
+    first_tile = false;
+  }
+
+  // ---- flush: TMEM dW accumulators and per-unit register accumulators -> partial slots -----------
+  __syncthreads();
+  const bool any_tile = blockIdx.x < n_tiles;
+  if (any_tile) {
+    tc::tc_fence_after();
+    for (int l = 2; l <= L; ++l) {
+      float* out = fa.dw_part + ((size_t)(l - 2) * fa.n_splits + blockIdx.x) * H * H;
+      for (int g = half; g < N2 / 16; g += 2) {
+        float v[16];
+        tc::tmem_ld16(tmem + 128 + (uint32_t)(l - 2) * 128 + lane_base + g * 16, v);
+        tc::tmem_ld_wait();
+        if (unit_ok) {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            const int k = g * 16 + i;
+            if (k < H) out[(size_t)j * H + k] += v[i];
+          }
+        }
+      }
+    }
+  }
+  // the two point-halves of a unit: add through shared memory, half 0 writes
+  float* red = sRed;  // reuse: needs 128 * 13 floats -> take it from sX (free now)
+  red = sX;
+  float acc[13] = {g_w1[0], g_w1[1], g_w1[2], g_w1[3], g_b[0], g_b[1], g_b[2], g_b[3], g_wo[0], g_wo[1], g_wo[2], g_wo[3], 0.f};
+  __syncthreads();
+  if (half == 1) {
+#pragma unroll
+    for (int i = 0; i < 12; ++i) red[i * 128 + j] = acc[i];
+  }
+  __syncthreads();
+  if (half == 0 && unit_ok) {
+#pragma unroll
+    for (int i = 0; i < 12; ++i) acc[i] += red[i * 128 + j];
+    float* fp = fa.first_part + (size_t)blockIdx.x * 8 * H;
+#pragma unroll
+    for (int d = 0; d < 4; ++d) fp[d * H + j] += acc[d];
+    fp[PINN_MAX_IN * H + j] += acc[4];
+#pragma unroll
+    for (int l = 2; l <= kMaxHid; ++l)
+      if (l <= L) fa.db_part[((size_t)(l - 2) * kBlocks + blockIdx.x) * 8 * H + j] += acc[4 + l - 1];
+    float* hp = fa.head_part + (size_t)blockIdx.x * (O * H + O + 1);
+    for (int o = 0; o < O; ++o) hp[o * H + j] += acc[8 + o];
+  }
+  __syncthreads();
+  if (tid < kP) {
+#pragma unroll
+    for (int o = 0; o < 4; ++o) red[o * kP + tid] = g_bo[o];
+    red[4 * kP + tid] = loss;
+  }
+  __syncthreads();
+  if (tid <= O) {
+    const int src = tid < O ? tid : 4;
+    float s = 0.f;
+    for (int p = 0; p < kP; ++p) s += red[src * kP + p];
+    fa.head_part[(size_t)blockIdx.x * (O * H + O + 1) + O * H + tid] += s;
+  }
+  tc::tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tc::tmem_dealloc(tmem, 512);
+}
+
+}  // namespace
+
+// W (row-major [H][H]) -> canonical padded K-major tile [Kq][129][4], TF32-rounded, zero padded;
+// transpose != 0 stores W^T (rows = input units of the layer, K = its output units)
+__global__ void prep_weights_kernel(const float* __restrict__ W, int H, int Kq, float* __restrict__ out, int transpose) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= Kq * 129 * 4) return;
+  const int e = i & 3, row = (i >> 2) % 129, kq = (i >> 2) / 129;
+  const int k = kq * 4 + e;
+  float v = 0.f;
+  if (row < H && k < H) v = tc::to_tf32(transpose ? W[(size_t)k * H + row] : W[(size_t)row * H + k]);
+  out[i] = v;
+}
+
+int fused_wide_prep(const WNet& n, float* wprep, cudaStream_t st) {
+  const int Kq = ((n.H + 7) & ~7) / 4, tile = Kq * 129 * 4;
+  for (int l = 2; l <= n.L; ++l)
+    for (int dir = 0; dir < 2; ++dir) {
+      prep_weights_kernel<<<(tile + 255) / 256, 256, 0, st>>>(n.W[l - 1], n.H, Kq, wprep + (size_t)(2 * (l - 2) + dir) * tile, dir);
+      count_launch(1);
+    }
+  return (int)cudaGetLastError();
+}
+
+int64_t fused_wide_wprep_floats(const WNet& n) { return (int64_t)2 * (n.L - 1) * (((n.H + 7) & ~7) / 4) * 129 * 4; }
+
+bool fused_wide_supported(const WNet& n) {
+  if (n.precision != 1 || n.H > 128 || n.L < 2 || n.L > kMaxHid || n.n_in > 4) return false;
+  const int H8 = (n.H + 7) & ~7, Kq = H8 / 4, N = n.C * kP, N2 = (n.H + 15) & ~15;
+  const size_t floats = (size_t)Kq * 129 * 4 + (size_t)Kq * (N + 1) * 4 + (size_t)(N / 4) * 129 * 4 +
+                        (size_t)(N / 4) * (N2 + 1) * 4 + 2 * N * 4 + kP * 4 + 4 * 128 + 64;
+  return floats * 4 <= 225 * 1024 && 12 * 128 <= Kq * (N + 1) * 4;
+}
+
+int64_t fused_wide_stash_floats(const WNet& n) { return (int64_t)kBlocks * (n.L - 1) * n.C * kP * 128; }
+
+template <int ACT>
+int fused_wide_launch(const WNet& n, const pinn_domain* dom, float* stash, const float* wt_base, float* dw_part, float* db_part,
+                      float* first_part, float* head_part, int n_splits, cudaStream_t st) {
+  FusedArgs fa;
+  memset(&fa, 0, sizeof(fa));
+  fa.dom = *dom;
+  for (int d = 0; d < PINN_MAX_IN; ++d) fa.xs[d] = d < n.n_in ? dom->coords[d] : nullptr;
+  fa.n_points = dom->n_points;
+  fa.stash = stash;
+  fa.wprep = wt_base;
+  fa.dw_part = dw_part;
+  fa.db_part = db_part;
+  fa.first_part = first_part;
+  fa.head_part = head_part;
+  fa.n_splits = n_splits;
+  if (n_splits < kBlocks) return PINN_E_UNSUPPORTED;
+  const int H8 = (n.H + 7) & ~7, Kq = H8 / 4, N = n.C * kP, N2 = (n.H + 15) & ~15;
+  const size_t smem = ((size_t)Kq * 129 * 4 + (size_t)Kq * (N + 1) * 4 + (size_t)(N / 4) * 129 * 4 +
+                       (size_t)(N / 4) * (N2 + 1) * 4 + 2 * N * 4 + kP * 4 + 4 * 128 + 64) * sizeof(float);
+  const int64_t tiles = (dom->n_points + kP - 1) / kP;
+  int grid = tiles < kBlocks ? (int)tiles : kBlocks;
+  if (grid < 1) return 0;
+#define CASE(Cc)                                                                                                       \
+  case Cc: {                                                                                                           \
+    cudaError_t e = cudaFuncSetAttribute((const void*)wide_fused_kernel<Cc, ACT>,                                      \
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);                      \
+    if (e != cudaSuccess) return (int)e;                                                                               \
+    wide_fused_kernel<Cc, ACT><<<grid, 256, smem, st>>>(n, fa);                                                        \
+  } break;
+  switch (n.C) {
+    CASE(1) CASE(2) CASE(3) CASE(4) CASE(5) CASE(6) CASE(7)
+    default: return PINN_E_UNSUPPORTED;
+  }
+#undef CASE
+  count_launch(1);
+  return (int)cudaGetLastError();
+}
+
+template int fused_wide_launch<PINN_ACT_TANH>(const WNet&, const pinn_domain*, float*, const float*, float*, float*, float*, float*, int, cudaStream_t);
+template int fused_wide_launch<PINN_ACT_SILU>(const WNet&, const pinn_domain*, float*, const float*, float*, float*, float*, float*, int, cudaStream_t);
+template int fused_wide_launch<PINN_ACT_SIN>(const WNet&, const pinn_domain*, float*, const float*, float*, float*, float*, float*, int, cudaStream_t);
+
+}  // namespace pinn

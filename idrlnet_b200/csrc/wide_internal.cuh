@@ -60,6 +60,64 @@ __device__ __forceinline__ void jet_bwd(int NF, int NS, const float* z, const fl
 }
 
 
+// residual polynomials, loss and its seed adjoint for one point (runtime descriptor, C channels)
+template <int C>
+__device__ __forceinline__ void residual_loss_rt(const pinn_domain& dm, int64_t n, const float* x, const float (*y)[4],
+                                                 float (*yb)[4], float& loss_acc) {
+  float sym[PINN_SYM_COUNT];
+  float sg[PINN_SYM_COORD0];
+  for (int i = 0; i < PINN_SYM_COUNT; ++i) sym[i] = 0.f;
+  for (int i = 0; i < PINN_SYM_COORD0; ++i) sg[i] = 0.f;
+  for (int c = 0; c < C; ++c)
+    for (int o = 0; o < 4; ++o) sym[c * 4 + o] = y[c][o];
+  for (int d = 0; d < 4; ++d) sym[PINN_SYM_COORD0 + d] = x[d];
+  for (int a = 0; a < dm.n_aux; ++a) sym[PINN_SYM_AUX0 + a] = dm.aux[a][n];
+  const float area = dm.area ? dm.area[n] : dm.area_const;
+  float loss = 0.f;
+  for (int e = 0; e < dm.n_eq; ++e) {
+    const pinn_equation& q = dm.eq[e];
+    float r = 0.f;
+    for (int t = q.term_begin; t < q.term_end; ++t) {
+      const pinn_term& tm = dm.terms[t];
+      float prod = tm.coef;
+      for (int f = 0; f < tm.n_fac; ++f) prod *= sym[tm.fac[f]];
+      r += prod;
+    }
+    const float tgt = q.target ? q.target[n] : q.target_const;
+    const float lam = q.lambda ? q.lambda[n] : q.lambda_const;
+    const float diff = r - tgt, w = lam * area;
+    float f0, f1;
+    if (dm.loss_kind == PINN_LOSS_SQUARE) { f0 = diff * diff; f1 = 2.0f * diff; }
+    else if (dm.loss_kind == PINN_LOSS_L1) { f0 = fabsf(diff); f1 = (diff > 0.f) ? 1.0f : ((diff < 0.f) ? -1.0f : 0.f); }
+    else { f0 = diff; f1 = 1.0f; }
+    loss += f0 * w;
+    const float g = f1 * w * dm.sigma;
+    for (int t = q.term_begin; t < q.term_end; ++t) {
+      const pinn_term& tm = dm.terms[t];
+      for (int f = 0; f < tm.n_fac; ++f) {
+        const int id = tm.fac[f];
+        if (id >= PINN_SYM_COORD0) continue;
+        float prod = tm.coef * g;
+        for (int f2 = 0; f2 < tm.n_fac; ++f2)
+          if (f2 != f) prod *= sym[tm.fac[f2]];
+        sg[id] += prod;
+      }
+    }
+  }
+  loss_acc += loss;
+  for (int c = 0; c < C; ++c)
+    for (int o = 0; o < 4; ++o) yb[c][o] = sg[c * 4 + o];
+}
+
+// whole-step-on-chip kernel for H <= 128 (wide_fused.cu)
+bool fused_wide_supported(const WNet& n);
+int64_t fused_wide_stash_floats(const WNet& n);
+int64_t fused_wide_wprep_floats(const WNet& n);
+int fused_wide_prep(const WNet& n, float* wprep, cudaStream_t st);
+template <int ACT>
+int fused_wide_launch(const WNet& n, const pinn_domain* dom, float* stash, const float* wt_base, float* dw_part, float* db_part,
+                      float* first_part, float* head_part, int n_splits, cudaStream_t st);
+
 // tensor-core GEMMs (wide_tc.cu)
 template <int ACT, int EPI>
 int tc_launch_rows(const WNet& n, const float* Bsrc, const float* Aw, const float* bias, float* Zio, float* Hout, int m, int Mc,

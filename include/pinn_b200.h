@@ -53,7 +53,11 @@ enum { PINN_LOSS_SQUARE = 0, PINN_LOSS_L1 = 1, PINN_LOSS_IDENTITY = 2 };
 /* PINN_PREC_FP32: FP32 FMA everywhere (1e-5 parity with the reference's FP32 autograd).
  * PINN_PREC_TF32: layer GEMMs of wide nets on tcgen05 tensor cores, multiplicands rounded
  * to TF32, FP32 accumulate; everything else FP32.  Narrow nets ignore the field. */
-enum { PINN_PREC_FP32 = 0, PINN_PREC_TF32 = 1 };
+enum {
+  PINN_PREC_FP32 = 0,
+  PINN_PREC_TF32 = 1,          /* on-chip fused kernel where it applies (H <= 128, 2..4 hidden layers), else streamed */
+  PINN_PREC_TF32_STREAMED = 2  /* always the layer-streamed tensor-core kernels (for comparison) */
+};
 enum {
   PINN_E_INVALID = -1,     /* malformed descriptor                        */
   PINN_E_UNSUPPORTED = -2, /* valid but no kernel for it (width, channels) */

@@ -17,9 +17,12 @@ pytestmark = pytest.mark.gpu
 TOL_TF32 = 1e-2 / 20  # _check_grads allows 20 * tol on gradients
 
 
-def _compare(problem, tol=TOL_TF32):
+PRECISIONS = ["tf32", "tf32_streamed"]  # on-chip fused kernel (where it applies) / layer-streamed kernels
+
+
+def _compare(problem, tol=TOL_TF32, precision="tf32"):
     ref = po.training_step(problem, dtype=torch.float64)
-    grads, losses, skipped, _ = pu.run_cuda_fused(problem, precision="tf32")
+    grads, losses, skipped, _ = pu.run_cuda_fused(problem, precision=precision)
     assert not skipped
     worst = 0.0
     for dname, l in losses.items():
@@ -32,19 +35,22 @@ def _compare(problem, tol=TOL_TF32):
     assert any(not np.array_equal(g32[k], grads[k]) for k in grads)
 
 
+@pytest.mark.parametrize("precision", PRECISIONS)
 @pytest.mark.parametrize("name", ["ldc", "ns_unsteady_wide"])
-def test_golden_tf32(name):
+def test_golden_tf32(name, precision):
     problem, _ = gu.load(name)
-    _compare(problem)
+    _compare(problem, precision=precision)
 
 
-def test_golden_allen_cahn_tf32():
+@pytest.mark.parametrize("precision", PRECISIONS)
+def test_golden_allen_cahn_tf32(precision):
     problem, _ = gu.load("allen_cahn")
-    _compare(_without(problem, ["AllenBc"]))
+    _compare(_without(problem, ["AllenBc"]), precision=precision)
 
 
+@pytest.mark.parametrize("precision", PRECISIONS)
 @pytest.mark.parametrize("case", range(len(WIDE_SHAPES)))
-def test_random_wide_tf32(case):
+def test_random_wide_tf32(case, precision):
     inputs, outputs, eq, act, width, n_hidden, n = WIDE_SHAPES[case]
     rng = np.random.default_rng(200 + case)
     problem = pu.random_problem(rng, n_in=len(inputs), n_out=len(outputs), width=width, n_hidden=n_hidden, act=act,
@@ -56,7 +62,17 @@ def test_random_wide_tf32(case):
         d["points"]["normal_y"] = rng.standard_normal((n, 1)).astype(np.float32)
     if n_hidden == 1:
         pytest.skip("single hidden layer: no hidden-to-hidden GEMM, nothing runs on the tensor cores")
-    _compare(problem)
+    _compare(problem, precision=precision)
+
+
+def test_fused_many_tiles_and_ragged_tail():
+    """On-chip kernel: more tiles than CTAs (persistent loop, TMEM dW accumulation across tiles)
+    and a last tile that is only partly filled."""
+    rng = np.random.default_rng(31)
+    problem = pu.random_problem(rng, n_in=2, n_out=3, inputs=("x", "y"), outputs=("u", "v", "p"), width=100, n_hidden=4,
+                                act="tanh", n_points=148 * 16 * 3 + 5,
+                                equation="p__x + u*u__x + v*u__y - 0.01*u__x__x - 0.01*u__y__y", with_lambda=True)
+    _compare(problem, precision="tf32")
 
 
 def test_multi_chunk_tf32():
