@@ -86,6 +86,29 @@ PINN_HD void act_derivs(float z, float& s0, float& s1, float& s2, float& s3) {
   }
 }
 
+// Same quantities with hardware approximations (MUFU.TANH, ex2/rcp, sin/cos approx): ~2^-11
+// relative error, used only on the TF32 tensor-core path whose multiplicands carry 10 mantissa bits.
+template <int ACT>
+PINN_HD void act_derivs_fast(float z, float& s0, float& s1, float& s2, float& s3) {
+#if defined(__CUDA_ARCH__)
+  if (ACT == PINN_ACT_TANH) {
+    float a;
+    asm("tanh.approx.f32 %0, %1;" : "=f"(a) : "f"(z));
+    s0 = a;
+    s1 = 1.0f - a * a;
+    s2 = -2.0f * a * s1;
+    s3 = -2.0f * s1 * (s1 - 2.0f * a * a);
+  } else if (ACT == PINN_ACT_SIN) {
+    const float sn = __sinf(z), cs = __cosf(z);
+    s0 = sn; s1 = cs; s2 = -sn; s3 = -cs;
+  } else {
+    act_derivs<ACT>(z, s0, s1, s2, s3);
+  }
+#else
+  act_derivs<ACT>(z, s0, s1, s2, s3);
+#endif
+}
+
 // Smallest S >= n (floats) with S % 4 == 0 and (S / 4) odd: per-lane rows of S
 // floats accessed as float4 are bank-conflict free (8 lanes of a 128-bit phase
 // land on 8 distinct 4-bank groups).

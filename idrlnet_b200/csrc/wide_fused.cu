@@ -39,8 +39,9 @@ struct FusedArgs {
   int first_launch;      // unused (slots are always accumulated)
 };
 
-template <int C, int ACT>
+template <int NF, int NS, int ACT>
 __global__ void __launch_bounds__(256, 1) wide_fused_kernel(WNet net, const __grid_constant__ FusedArgs fa) {
+  constexpr int C = 1 + NF + NS;
   constexpr int N = C * kP;
   const int H = net.H, L = net.L, O = net.n_out;
   const int H8 = (H + 7) & ~7, Kq = H8 / 4, N2 = (H + 15) & ~15;
@@ -102,13 +103,12 @@ __global__ void __launch_bounds__(256, 1) wide_fused_kernel(WNet net, const __gr
   }
 #pragma unroll
   for (int o = 0; o < 4; ++o) wo[o] = sWo[o * 128 + j];
-  float w1f[3] = {0.f, 0.f, 0.f};
+  float w1f[NF > 0 ? NF : 1];
 #pragma unroll
-  for (int i = 0; i < 3; ++i)
-    if (i < net.NF) {
-      const int d = net.first_in[i];
-      w1f[i] = d == 0 ? w1[0] : d == 1 ? w1[1] : d == 2 ? w1[2] : w1[3];
-    }
+  for (int i = 0; i < NF; ++i) {
+    const int d = net.first_in[i];
+    w1f[i] = d == 0 ? w1[0] : d == 1 ? w1[1] : d == 2 ? w1[2] : w1[3];
+  }
 
   // per-unit gradient accumulators (both point halves accumulate; summed at the end)
   float g_w1[4] = {0.f, 0.f, 0.f, 0.f}, g_b[kMaxHid + 1] = {0.f, 0.f, 0.f, 0.f, 0.f}, g_wo[4] = {0.f, 0.f, 0.f, 0.f};
@@ -119,17 +119,15 @@ __global__ void __launch_bounds__(256, 1) wide_fused_kernel(WNet net, const __gr
   const int64_t n_tiles = (fa.n_points + kP - 1) / kP;
   bool first_tile = true;
 
-  auto layer1 = [&](const float* x, float (&z)[kMaxC]) {
+  auto layer1 = [&](const float* x, float (&z)[C]) {
     float v = b1;
 #pragma unroll
     for (int d = 0; d < 4; ++d) v += w1[d] * x[d];
     z[0] = v;
 #pragma unroll
-    for (int i = 0; i < 3; ++i)
-      if (i < net.NF) z[1 + i] = w1f[i];
+    for (int i = 0; i < NF; ++i) z[1 + i] = w1f[i];
 #pragma unroll
-    for (int s = 0; s < 3; ++s)
-      if (s < net.NS) z[1 + net.NF + s] = 0.f;
+    for (int s = 0; s < NS; ++s) z[1 + NF + s] = 0.f;
   };
   // element (row q = c*kP + p, K index = unit j) of the K = unit operand
   auto sx_at = [&](int q) -> float& { return sX[((j >> 2) * (N + 1) + q) * 4 + (j & 3)]; };
@@ -179,9 +177,9 @@ __global__ void __launch_bounds__(256, 1) wide_fused_kernel(WNet net, const __gr
     for (int pp = 0; pp < kP / 2; ++pp) {
       const int p = half * (kP / 2) + pp;
       float x[4] = {sXc[p * 4], sXc[p * 4 + 1], sXc[p * 4 + 2], sXc[p * 4 + 3]};
-      float z[kMaxC], h[kMaxC];
+      float z[C], h[C];
       layer1(x, z);
-      jet_fwd<ACT>(net.NF, net.NS, z, h);
+      jet_fwd_t<ACT, NF, NS, true>(z, h);
       if (j < H8) {
 #pragma unroll
         for (int c = 0; c < C; ++c) sx_at(c * kP + p) = unit_ok ? tc::to_tf32(h[c]) : 0.f;
@@ -198,11 +196,11 @@ __global__ void __launch_bounds__(256, 1) wide_fused_kernel(WNet net, const __gr
 #pragma unroll
       for (int pp = 0; pp < kP / 2; ++pp) {
         const int p = half * (kP / 2) + pp;
-        float z[kMaxC], h[kMaxC];
+        float z[C], h[C];
 #pragma unroll
         for (int c = 0; c < C; ++c) z[c] = v[c][pp];
         z[0] += bias;
-        jet_fwd<ACT>(net.NF, net.NS, z, h);
+        jet_fwd_t<ACT, NF, NS, true>(z, h);
 #pragma unroll
         for (int c = 0; c < C; ++c) {
           stash[(((size_t)(l - 2) * C + c) * kP + p) * 128 + j] = z[c];
@@ -284,7 +282,7 @@ __global__ void __launch_bounds__(256, 1) wide_fused_kernel(WNet net, const __gr
       for (int pp = 0; pp < kP / 2; ++pp) {
         const int p = half * (kP / 2) + pp;
         float x[4] = {sXc[p * 4], sXc[p * 4 + 1], sXc[p * 4 + 2], sXc[p * 4 + 3]};
-        float z[kMaxC], hb[kMaxC], zb[kMaxC], h[kMaxC];
+        float z[C], hb[C], zb[C], h[C];
         if (l >= 2) {
 #pragma unroll
           for (int c = 0; c < C; ++c) z[c] = zl[c][pp];
@@ -298,7 +296,7 @@ __global__ void __launch_bounds__(256, 1) wide_fused_kernel(WNet net, const __gr
             const float4 t = *reinterpret_cast<const float4*>(sYb + (c * kP + p) * 4);
             hb[c] = wo[0] * t.x + wo[1] * t.y + wo[2] * t.z + wo[3] * t.w;
           }
-          jet_fwd<ACT>(net.NF, net.NS, z, h);  // h_L for dWout
+          jet_fwd_t<ACT, NF, NS, true>(z, h);  // h_L for dWout
 #pragma unroll
           for (int c = 0; c < C; ++c) {
             const float4 t = *reinterpret_cast<const float4*>(sYb + (c * kP + p) * 4);
@@ -310,7 +308,7 @@ __global__ void __launch_bounds__(256, 1) wide_fused_kernel(WNet net, const __gr
         }
 #pragma unroll
         for (int c = 0; c < C; ++c) zb[c] = 0.f;
-        jet_bwd<ACT>(net.NF, net.NS, z, hb, zb);
+        jet_bwd_t<ACT, NF, NS, true>(z, hb, zb);
         if (!unit_ok) {
 #pragma unroll
           for (int c = 0; c < C; ++c) zb[c] = 0.f;
@@ -323,24 +321,23 @@ __global__ void __launch_bounds__(256, 1) wide_fused_kernel(WNet net, const __gr
 #pragma unroll
           for (int d = 0; d < 4; ++d) g_w1[d] += zb[0] * x[d];
 #pragma unroll
-          for (int i = 0; i < 3; ++i)
-            if (i < net.NF) {
-              const int d = net.first_in[i];
-              if (d == 0) g_w1[0] += zb[1 + i];
-              else if (d == 1) g_w1[1] += zb[1 + i];
-              else if (d == 2) g_w1[2] += zb[1 + i];
-              else g_w1[3] += zb[1 + i];
-            }
+          for (int i = 0; i < NF; ++i) {
+            const int d = net.first_in[i];
+            if (d == 0) g_w1[0] += zb[1 + i];
+            else if (d == 1) g_w1[1] += zb[1 + i];
+            else if (d == 2) g_w1[2] += zb[1 + i];
+            else g_w1[3] += zb[1 + i];
+          }
         } else {
           // operands of the next two GEMMs
-          float zq[kMaxC], hp[kMaxC];
+          float zq[C], hp[C];
           if (l - 1 >= 2) {
 #pragma unroll
             for (int c = 0; c < C; ++c) zq[c] = zp[c][pp];
           } else {
             layer1(x, zq);
           }
-          jet_fwd<ACT>(net.NF, net.NS, zq, hp);
+          jet_fwd_t<ACT, NF, NS, true>(zq, hp);
 #pragma unroll
           for (int c = 0; c < C; ++c) {
             const int q = c * kP + p;
@@ -480,17 +477,17 @@ int fused_wide_launch(const WNet& n, const pinn_domain* dom, float* stash, const
   const int64_t tiles = (dom->n_points + kP - 1) / kP;
   int grid = tiles < kBlocks ? (int)tiles : kBlocks;
   if (grid < 1) return 0;
-#define CASE(Cc)                                                                                                       \
-  case Cc: {                                                                                                           \
-    cudaError_t e = cudaFuncSetAttribute((const void*)wide_fused_kernel<Cc, ACT>,                                      \
+#define CASE(NF_, NS_)                                                                                                 \
+  if (n.NF == NF_ && n.NS == NS_) {                                                                                   \
+    cudaError_t e = cudaFuncSetAttribute((const void*)wide_fused_kernel<NF_, NS_, ACT>,                                \
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);                      \
     if (e != cudaSuccess) return (int)e;                                                                               \
-    wide_fused_kernel<Cc, ACT><<<grid, 256, smem, st>>>(n, fa);                                                        \
-  } break;
-  switch (n.C) {
-    CASE(1) CASE(2) CASE(3) CASE(4) CASE(5) CASE(6) CASE(7)
-    default: return PINN_E_UNSUPPORTED;
+    wide_fused_kernel<NF_, NS_, ACT><<<grid, 256, smem, st>>>(n, fa);                                                  \
+    launched = true;                                                                                                   \
   }
+  bool launched = false;
+  CASE(0, 0) CASE(1, 0) CASE(1, 1) CASE(2, 0) CASE(2, 1) CASE(2, 2) CASE(3, 0) CASE(3, 1) CASE(3, 2) CASE(3, 3)
+  if (!launched) return PINN_E_UNSUPPORTED;
 #undef CASE
   count_launch(1);
   return (int)cudaGetLastError();

@@ -60,6 +60,41 @@ __device__ __forceinline__ void jet_bwd(int NF, int NS, const float* z, const fl
 }
 
 
+// compile-time channel structure (no dynamically indexed jet arrays -> everything stays in registers)
+template <int ACT, int NF, int NS, bool FAST>
+__device__ __forceinline__ void jet_fwd_t(const float (&z)[1 + NF + NS], float (&h)[1 + NF + NS]) {
+  float s0, s1, s2, s3;
+  if (FAST) act_derivs_fast<ACT>(z[0], s0, s1, s2, s3);
+  else act_derivs<ACT>(z[0], s0, s1, s2, s3);
+  h[0] = s0;
+#pragma unroll
+  for (int i = 0; i < NF; ++i) h[1 + i] = s1 * z[1 + i];
+#pragma unroll
+  for (int s = 0; s < NS; ++s) h[1 + NF + s] = s2 * z[1 + s] * z[1 + s] + s1 * z[1 + NF + s];
+}
+
+template <int ACT, int NF, int NS, bool FAST>
+__device__ __forceinline__ void jet_bwd_t(const float (&z)[1 + NF + NS], const float (&hb)[1 + NF + NS],
+                                          float (&zb)[1 + NF + NS]) {
+  float s0, s1, s2, s3;
+  if (FAST) act_derivs_fast<ACT>(z[0], s0, s1, s2, s3);
+  else act_derivs<ACT>(z[0], s0, s1, s2, s3);
+  float zv = hb[0] * s1;
+#pragma unroll
+  for (int i = 0; i < NF; ++i) {
+    zv += hb[1 + i] * s2 * z[1 + i];
+    zb[1 + i] = hb[1 + i] * s1;
+  }
+#pragma unroll
+  for (int s = 0; s < NS; ++s) {
+    const float zi = z[1 + s], zii = z[1 + NF + s], hbs = hb[1 + NF + s];
+    zv += hbs * (s3 * zi * zi + s2 * zii);
+    zb[1 + s] += 2.0f * hbs * s2 * zi;
+    zb[1 + NF + s] = hbs * s1;
+  }
+  zb[0] = zv;
+}
+
 // residual polynomials, loss and its seed adjoint for one point (runtime descriptor, C channels)
 template <int C>
 __device__ __forceinline__ void residual_loss_rt(const pinn_domain& dm, int64_t n, const float* x, const float (*y)[4],
