@@ -51,7 +51,7 @@ __global__ void first_fwd_kernel(WNet net, Coords xs, int64_t n0, int m, int Mc,
   const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= (int64_t)m * H) return;
   const int n = (int)(idx / H), j = (int)(idx % H);
-  float z[kMaxC], h[kMaxC];
+  float z[kMaxC] = {}, h[kMaxC] = {};
   float v = net.b[0][j];
   for (int d = 0; d < net.n_in; ++d) v += net.W[0][j * net.n_in + d] * xs.p[d][n0 + n];
   z[0] = v;
@@ -151,7 +151,7 @@ __global__ void __launch_bounds__(256) gemm_rows_kernel(WNet net, const float* _
       if (EPI == 0) bj = *reinterpret_cast<const float4*>(bias + j);
 #pragma unroll
       for (int e = 0; e < 4; ++e) {
-        float v[kMaxC], w[kMaxC], o[kMaxC];
+        float v[kMaxC] = {}, w[kMaxC] = {}, o[kMaxC] = {};
 #pragma unroll
         for (int c = 0; c < C; ++c) v[c] = acc[c][r][tq * 4 + e];
         if (EPI == 0) {
@@ -455,7 +455,7 @@ __global__ void __launch_bounds__(1024) head_bwd_kernel(WNet net, const float* _
 #pragma unroll
     for (int o = 0; o < 4; ++o) wo[o] = (o < O) ? net.W[net.L][o * H + j] : 0.f;
     for (int n = nb + pl; n < ne; n += 16) {  // two points (n, n + 8) in flight
-      float z[2][kMaxC], h[2][C];
+      float z[2][kMaxC] = {}, h[2][C];
       float4 yb[2][C];
 #pragma unroll
       for (int u = 0; u < 2; ++u) {
@@ -471,7 +471,7 @@ __global__ void __launch_bounds__(1024) head_bwd_kernel(WNet net, const float* _
 #pragma unroll
       for (int u = 0; u < 2; ++u) {
         const int nn = n + 8 * u;
-        float hb[kMaxC], zb[kMaxC];
+        float hb[kMaxC] = {}, zb[kMaxC] = {};
 #pragma unroll
         for (int c = 0; c < C; ++c) {
           const float4 y4 = yb[u][c];
@@ -505,7 +505,7 @@ __global__ void __launch_bounds__(1024) head_bwd_kernel(WNet net, const float* _
 struct WideLayout {  // workspace offsets in floats
   int64_t Z, Hb;            // L planes-sets each: [l][C][Mc][H]
   int64_t dw, db, first, head, loss_slots, acc_end, total;
-  int64_t wt, ybar;
+  int64_t wt, wprep, ybar;
   int Mc, n_splits, fp32_splits, tiles, n_dom;
 };
 
@@ -602,11 +602,9 @@ WideLayout make_layout(const WNet& n, int n_dom) {
   wl.head = off; off += (int64_t)kBlocks * (n.n_out * n.H + n.n_out + 1);
   wl.loss_slots = off; off += (int64_t)kMaxDomains * kBlocks;
   off = (off + 3) / 4 * 4;
-  {  // W_l^T for the streamed tensor-core reverse GEMM, or the prepared weight tiles of the on-chip kernel
-    int64_t wt = (int64_t)(n.L - 1) * n.H * n.H;
-    if (n.H <= 128 && fused_wide_wprep_floats(n) > wt) wt = fused_wide_wprep_floats(n);
-    wl.wt = off; off += (wt + 3) / 4 * 4;
-  }
+  // W_l^T for the streamed tensor-core reverse GEMM, then the prepared weight tiles of the on-chip kernel
+  wl.wt = off; off += ((int64_t)(n.L - 1) * n.H * n.H + 3) / 4 * 4;
+  wl.wprep = off; off += (n.H <= 128) ? (fused_wide_wprep_floats(n) + 3) / 4 * 4 : 0;
   wl.acc_end = off;
   wl.Z = off; off += planes;
   wl.Hb = off; off += planes;
@@ -750,21 +748,26 @@ int run_mode(const pinn_mlp* m, const pinn_jets* j, int mode, const pinn_domain*
   if (!ws || ws_bytes < wl.total * 4) return PINN_E_WORKSPACE;
   float* w = (float*)ws;
   if (!accumulate && mode != W_MODE_FWD)  // clear every partial slot (all domains' loss slots included)
-    CK(cudaMemsetAsync(w + wl.dw, 0, (size_t)(wl.acc_end - wl.dw) * 4, st));
+    CK(cudaMemsetAsync(w + wl.dw, 0, (size_t)(wl.wt - wl.dw) * 4, st));  // partial slots only (not the weight tiles)
   int rc = 0;
   const bool on_chip = mode == W_MODE_FUSED && fused_wide_supported(n) && m->precision == PINN_PREC_TF32 &&
                        fused_wide_stash_floats(n) <= (int64_t)2 * n.L * n.C * wl.Mc * n.H;
-  if (n.precision && mode != W_MODE_FWD && !on_chip)
+  // weight preparation once per step: later domains of the same step (accumulate != 0) reuse it
+  const bool prep = !accumulate || mode != W_MODE_FUSED;
+  if (n.precision && mode != W_MODE_FWD && prep)
     for (int l = 2; l <= n.L; ++l) {
       rc = tc_transpose(n.W[l - 1], w + wl.wt + (size_t)(l - 2) * n.H * n.H, n.H, st);
       if (rc) return rc;
     }
+  if (n.precision && mode == W_MODE_FUSED && prep && n.H <= 128 && n.L >= 2) {
+    rc = fused_wide_prep(n, w + wl.wprep, st);
+    if (rc) return rc;
+  }
   if (on_chip) {
     // whole step on chip (wide_fused.cu); same partial slots, same finalize
-    rc = fused_wide_prep(n, w + wl.wt, st);
-    if (rc) return rc;
+    (void)0;
 #define RUNF(A)                                                                                                   \
-  rc = fused_wide_launch<A>(n, dom, w + wl.Z, w + wl.wt, w + wl.dw, w + wl.db, w + wl.first, w + wl.head, wl.n_splits, st)
+  rc = fused_wide_launch<A>(n, dom, w + wl.Z, w + wl.wprep, w + wl.dw, w + wl.db, w + wl.first, w + wl.head, wl.n_splits, st)
     ACT_SWITCH(n.act, RUNF);
 #undef RUNF
     if (rc) return rc;

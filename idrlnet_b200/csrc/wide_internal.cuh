@@ -24,17 +24,29 @@ struct WNet {
 };
 
 // ---- activation jets with runtime channel counts ---------------------------
+// All array indices are compile-time constants (selection by predicate chains), so the jet
+// arrays stay in registers even though NF / NS are only known at run time.
+__device__ __forceinline__ float pick7(const float* a, int idx) {
+  float r = a[0];
+#pragma unroll
+  for (int c = 1; c < 7; ++c) r = (idx == c) ? a[c] : r;
+  return r;
+}
+
 template <int ACT>
 __device__ __forceinline__ void jet_fwd(int NF, int NS, const float* z, float* h) {
   float s0, s1, s2, s3;
   act_derivs<ACT>(z[0], s0, s1, s2, s3);
   h[0] = s0;
 #pragma unroll
-  for (int i = 0; i < 3; ++i)
-    if (i < NF) h[1 + i] = s1 * z[1 + i];
-#pragma unroll
-  for (int s = 0; s < 3; ++s)
-    if (s < NS) h[1 + NF + s] = s2 * z[1 + s] * z[1 + s] + s1 * z[1 + NF + s];
+  for (int c = 1; c < 7; ++c) {
+    if (c <= NF) {
+      h[c] = s1 * z[c];
+    } else if (c <= NF + NS) {
+      const float zi = pick7(z, c - NF);  // first-order channel of the same input
+      h[c] = s2 * zi * zi + s1 * z[c];
+    }
+  }
 }
 
 template <int ACT>
@@ -43,22 +55,22 @@ __device__ __forceinline__ void jet_bwd(int NF, int NS, const float* z, const fl
   act_derivs<ACT>(z[0], s0, s1, s2, s3);
   float zv = hb[0] * s1;
 #pragma unroll
-  for (int i = 0; i < 3; ++i)
-    if (i < NF) {
-      zv += hb[1 + i] * s2 * z[1 + i];
-      zb[1 + i] = hb[1 + i] * s1;
+  for (int c = 1; c < 7; ++c) {
+    if (c <= NF) {
+      float t = hb[c] * s1;
+      zv += hb[c] * s2 * z[c];
+      if (c <= NS) {  // this input also has a second-order channel at index c + NF
+        const float hbs = pick7(hb, c + NF), zii = pick7(z, c + NF);
+        zv += hbs * (s3 * z[c] * z[c] + s2 * zii);
+        t += 2.0f * hbs * s2 * z[c];
+      }
+      zb[c] = t;
+    } else if (c <= NF + NS) {
+      zb[c] = hb[c] * s1;
     }
-#pragma unroll
-  for (int s = 0; s < 3; ++s)
-    if (s < NS) {
-      const float zi = z[1 + s], zii = z[1 + NF + s], hbs = hb[1 + NF + s];
-      zv += hbs * (s3 * zi * zi + s2 * zii);
-      zb[1 + s] += 2.0f * hbs * s2 * zi;
-      zb[1 + NF + s] = hbs * s1;
-    }
+  }
   zb[0] = zv;
 }
-
 
 // compile-time channel structure (no dynamically indexed jet arrays -> everything stays in registers)
 template <int ACT, int NF, int NS, bool FAST>

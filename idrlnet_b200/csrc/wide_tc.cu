@@ -143,7 +143,7 @@ __global__ void __launch_bounds__(256) tc_rows_kernel(WNet net, const float* __r
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
           const int n = n0 + g * 16 + quad * 4 + i;
-          float a[kMaxC], b[kMaxC], o[kMaxC];
+          float a[kMaxC] = {}, b[kMaxC] = {}, o[kMaxC] = {};
 #pragma unroll
           for (int c = 0; c < C; ++c) {
             a[c] = v[c][quad * 4 + i];
@@ -164,7 +164,7 @@ __global__ void __launch_bounds__(256) tc_rows_kernel(WNet net, const float* __r
         for (int i = 0; i < 16; ++i) {
           const int n = n0 + g * 16 + i;
           if (n < m) {
-            float a[kMaxC], o[kMaxC];
+            float a[kMaxC] = {}, o[kMaxC] = {};
 #pragma unroll
             for (int c = 0; c < C; ++c) a[c] = v[c][i];
             a[0] += bj;

@@ -12,7 +12,8 @@ to polynomials over one supported net (`compiler.compile_domain`) is bound to th
 fused kernels; a training step for those domains is `pinn_step_fused` +
 `pinn_step_finalize` (forward jets, residual, loss and reverse pass in one kernel
 per domain) instead of forward graph + `compute_loss` + `loss.backward()`
-(idrlnet/solver.py:329-338).  Everything else runs the generic graph.  Under
+(idrlnet/solver.py:329-338).  `Solver(precision="tf32")` runs the layer GEMMs of wide nets on
+the tensor cores (stated tolerance 1e-2); the default "fp32" holds 1e-5.  Everything else runs the generic graph.  Under
 `torch.distributed` the points of every domain are sharded over the ranks and
 the flat gradient (+ loss scalars) is all-reduced once per step.
 
@@ -55,13 +56,16 @@ class Solver(Notifier, Optimizable):
                  max_iter: int = 1000, save_freq: int = 100, print_freq: int = 10, loading: bool = True,
                  init_network_dirs: Optional[List[str]] = None, opt_config: Dict = None, schedule_config: Dict = None,
                  result_dir="train_domain/results", fused: Optional[bool] = None, post_step_loss: bool = False,
-                 **kwargs):
+                 precision: Optional[str] = None, **kwargs):
         from . import callbacks
         self.network_dir = network_dir
         self.domain_losses = {d.name: d.loss_fn for d in sample_domains}
         self.netnodes: List[NetNode] = netnodes
         self.fused_enabled = fused
         self.post_step_loss = post_step_loss
+        # arithmetic of the layer GEMMs of wide (H > 32) nets: "fp32" (parity, default) or "tf32"
+        # (tcgen05 tensor cores); None -> IDRLNET_B200_PRECISION or "fp32"
+        self.precision = precision
         self._move_nets_to_device()
         self.init_network_dirs = init_network_dirs if init_network_dirs else []
         self.init_load()
@@ -193,7 +197,7 @@ class Solver(Notifier, Optimizable):
                     raise cp.NotFusable("fixed / no-grad net")
                 key = id(nn.net)
                 if key not in self._packs:
-                    self._packs[key] = fused.NetPack(nn.net)
+                    self._packs[key] = fused.NetPack(nn.net, precision=self.precision)
                 pack = self._packs[key]
                 if pack.n_in != len(nn.inputs) or pack.n_out < len(nn.outputs):
                     raise cp.NotFusable("net shape does not match the node's inputs/outputs")

@@ -71,3 +71,17 @@ def test_infer_step_serves_derivatives(tmp_path):
     for k in ("u", "u__x", "u__x__x", "burgers_u"):
         got = out["burgers_equation"][k].detach().cpu().numpy()
         assert gu.normwise(got, ref[k]) <= 1e-5, k
+
+
+def test_solver_tf32_precision_tracks_fp32(tmp_path):
+    """Solver(precision="tf32"): tensor-core path through the public API; the loss curve stays
+    within the stated TF32 band of the FP32 run (ldc, 100 steps)."""
+    problem, _ = gu.load("ldc")
+    curves = {}
+    for prec in ("fp32", "tf32"):
+        s, _ = pu.solver_from_problem(problem, tmp_path / prec, max_iter=100, save_freq=10 ** 9, print_freq=10 ** 9,
+                                      precision=prec)
+        assert len(s._fused_domains) == 3
+        curves[prec] = torch.stack([s.train_pipe().reshape(()) for _ in range(100)]).cpu().numpy()
+    rel = np.abs(curves["tf32"] - curves["fp32"]) / np.abs(curves["fp32"])
+    assert 0 < rel.max() <= 2e-2, float(rel.max())
