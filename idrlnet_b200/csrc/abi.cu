@@ -8,6 +8,7 @@
 #include <mutex>
 
 #include "narrow_kernel.cuh"
+#include "select.cuh"
 #include "wide.cuh"
 
 namespace pinn {
@@ -348,6 +349,46 @@ int pinn_jet_backward(const pinn_mlp* m, const pinn_jets* j, int64_t n_points, c
   }
   if (wide_supported(m, j)) return wide_jet_backward(m, j, n_points, coords, out_bar, ws, ws_bytes, accumulate, st);
   return fail(PINN_E_UNSUPPORTED, "no kernel for width %d", m->width);
+}
+
+// ---- forward-only residuals and top-k (adaptive re-sampling) -------------------------------------
+int64_t pinn_residual_workspace_bytes(const pinn_mlp* m, const pinn_jets* j, int64_t n_points) {
+  if (!m || !j || n_points < 0) return PINN_E_INVALID;
+  const int C = 1 + j->n_first + j->n_second;
+  const int64_t jets = (((int64_t)C * m->n_out * n_points * (int64_t)sizeof(float)) + 255) & ~(int64_t)255;
+  const int64_t fwd = pinn_workspace_bytes(m, j, 1);
+  return fwd < 0 ? fwd : jets + fwd;
+}
+
+int pinn_residual_forward(const pinn_mlp* m, const pinn_jets* j, const pinn_domain* dom, float* out, void* ws,
+                          int64_t ws_bytes, void* stream) {
+  int rc = check_mlp(m, j);
+  if (rc) return rc;
+  if (!dom || !out || !ws) return fail(PINN_E_INVALID, "null argument");
+  if (dom->n_eq < 1 || dom->n_eq > PINN_MAX_EQ || dom->n_terms > PINN_MAX_TERMS)
+    return fail(PINN_E_INVALID, "bad equation table");
+  if (dom->n_points == 0) return 0;
+  const int C = 1 + j->n_first + j->n_second;
+  const int64_t jets_bytes = (((int64_t)C * m->n_out * dom->n_points * (int64_t)sizeof(float)) + 255) & ~(int64_t)255;
+  if (ws_bytes < pinn_residual_workspace_bytes(m, j, dom->n_points)) return fail(PINN_E_WORKSPACE, "workspace too small");
+  float* jets = (float*)ws;
+  rc = pinn_jet_forward(m, j, dom->n_points, dom->coords, jets, (char*)ws + jets_bytes, ws_bytes - jets_bytes, stream);
+  if (rc) return rc;
+  rc = residual_eval(dom, m->n_out, jets, out, (cudaStream_t)stream);
+  return rc > 0 ? cuda_fail((cudaError_t)rc, "residual kernel launch") : rc;
+}
+
+int64_t pinn_topk_workspace_bytes(int32_t k) { return k < 1 || k > kTopkMax ? PINN_E_UNSUPPORTED : topk_workspace_bytes(k); }
+
+int pinn_topk_abs(const float* values, int64_t n, int32_t k, int64_t* idx_out, float* val_out, void* ws, int64_t ws_bytes,
+                  void* stream) {
+  if (!values || !idx_out || !ws || n < 0) return fail(PINN_E_INVALID, "null argument");
+  if (k < 1 || k > kTopkMax) return fail(PINN_E_UNSUPPORTED, "k = %d outside 1..%d", k, kTopkMax);
+  if (k > n) return fail(PINN_E_INVALID, "k = %d exceeds the %lld values", k, (long long)n);
+  if (n >= ((int64_t)1 << 32)) return fail(PINN_E_UNSUPPORTED, "more than 2^32 - 1 values");
+  if (ws_bytes < topk_workspace_bytes(k)) return fail(PINN_E_WORKSPACE, "workspace too small");
+  const int rc = topk_abs(values, n, k, idx_out, val_out, ws, (cudaStream_t)stream);
+  return rc > 0 ? cuda_fail((cudaError_t)rc, "top-k launch") : rc;
 }
 
 }  // extern "C"

@@ -320,6 +320,42 @@ class FusedDomain:
         return self._struct
 
 
+def topk_abs(values: torch.Tensor, k: int) -> Tuple[torch.Tensor, torch.Tensor]:
+    """(indices int64 [k], values [k]) of the k largest |values|, descending, ties by ascending
+    index -- `np.argsort(-np.abs(v), kind="stable")[:k]` on the device (pinn_topk_abs)."""
+    _require_cuda(values, "topk_abs input")
+    v = values.detach().reshape(-1).to(torch.float32).contiguous()
+    lib = nv.lib()
+    ws_bytes = lib.pinn_topk_workspace_bytes(k)
+    if ws_bytes < 0:
+        raise nv.PinnError(int(ws_bytes), f"top-k supports 1 <= k <= 4096, got {k}")
+    ws = torch.empty(ws_bytes, device=v.device, dtype=torch.uint8)
+    idx = torch.empty(k, device=v.device, dtype=torch.int64)
+    val = torch.empty(k, device=v.device, dtype=torch.float32)
+    nv.check(lib.pinn_topk_abs(v.data_ptr(), v.numel(), k, idx.data_ptr(), val.data_ptr(), ws.data_ptr(), ws_bytes,
+                               _stream_ptr()))
+    return idx, val
+
+
+def domain_residuals(pack: NetPack, domain: FusedDomain) -> torch.Tensor:
+    """[n_eq, N] values of the domain's equations at its bound points, forward only
+    (pinn_residual_forward): what `Solver.infer_step` returns for the PdeNode outputs."""
+    lib = nv.lib()
+    pack.refresh_effective()
+    mlp = pack.mlp_struct()
+    n = domain.n_points
+    out = torch.empty((len(domain.compiled.equations), n), device=pack.device, dtype=torch.float32)
+    if n == 0:
+        return out
+    ws_bytes = lib.pinn_residual_workspace_bytes(C.byref(mlp), C.byref(domain.jets), n)
+    if ws_bytes < 0:
+        raise nv.PinnError(int(ws_bytes), "no kernel for this net / jet plan")
+    ws = torch.empty(ws_bytes // 4 + 1, device=pack.device, dtype=torch.float32)
+    nv.check(lib.pinn_residual_forward(C.byref(mlp), C.byref(domain.jets), C.byref(domain.struct), out.data_ptr(),
+                                       ws.data_ptr(), ws_bytes, _stream_ptr()))
+    return out
+
+
 class StepEngine:
     """One net, several fused domains: gradient of sum_d sigma_d * loss_d."""
 

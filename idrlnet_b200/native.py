@@ -106,6 +106,12 @@ _SIGNATURES = {
                                             C.c_int32, C.c_void_p]),
     "pinn_sample_box": (C.c_int, [C.POINTER(_fp), C.c_int32, C.POINTER(C.c_float), C.POINTER(C.c_float), C.c_int64,
                                   C.c_uint64, C.c_uint64, C.c_uint64, C.c_void_p, C.c_int32, C.c_void_p]),
+    "pinn_residual_workspace_bytes": (C.c_int64, [C.POINTER(PinnMlp), C.POINTER(PinnJets), C.c_int64]),
+    "pinn_residual_forward": (C.c_int, [C.POINTER(PinnMlp), C.POINTER(PinnJets), C.POINTER(PinnDomain), C.c_void_p,
+                                        C.c_void_p, C.c_int64, C.c_void_p]),
+    "pinn_topk_workspace_bytes": (C.c_int64, [C.c_int32]),
+    "pinn_topk_abs": (C.c_int, [C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64,
+                                C.c_void_p]),
     "pinn_fp32_fma_probe": (C.c_int64, [C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]),
     "pinn_tc_selftest": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
 }

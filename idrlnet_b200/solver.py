@@ -371,6 +371,52 @@ class Solver(Notifier, Optimizable):
         in_var, _, _ = self.generate_in_out_dict(samples)
         return self.forward_through_all_graph(in_var, domain_attr)
 
+    def residual_top_k(self, domain_name: str, residual: str, k: int) -> Variables:
+        """Adaptive re-sampling on the device: sample `domain_name`, evaluate the
+        PdeNode output `residual` at every point with the forward-only kernels and return the k
+        points with the largest |residual| -- every sampled column of those points, the residual
+        itself and their `index` in the sample, ordered by descending |residual|.
+
+        The reference's recipe (examples/allen_cahn/allen_cahn.py:128-149) is `infer_step` +
+        `np.argsort` on the host; the selection here is identical (ties by ascending index).
+        With torch.distributed initialised every rank scores its shard and the per-rank winners
+        are all-gathered and re-selected, so all ranks return the same k points."""
+        from . import DEVICE, fused
+        if DEVICE.type != "cuda":
+            raise RuntimeError("residual_top_k runs on the CUDA kernels; there is no CPU implementation")
+        dom = self.get_sample_domain(domain_name)
+        sample = self._shard({domain_name: dom.sample()})[domain_name]
+        points = Variables({key: v for key, v in sample.items() if key in self.invar_dict_index[domain_name]})
+        points.to_torch_tensor_()
+        exprs = {sub.name: sub.evaluate.tf_eq for pde in self.pdes if isinstance(pde, PdeNode) for sub in pde.sub_nodes}
+        specs = [cp.NetSpec(nn.name, tuple(nn.inputs), tuple(nn.outputs)) for nn in self.netnodes]
+        cd = cp.compile_domain([residual], exprs, specs, list(points.keys()))
+        nn = next(n for n in self.netnodes if n.name == cd.net.name)
+        key = id(nn.net)
+        if key not in self._packs:
+            self._packs[key] = fused.NetPack(nn.net, precision=self.precision)
+        fd = fused.FusedDomain(domain_name, cd)
+        fd.bind(points, {residual: 0.0}, {}, 1.0)
+        r = fused.domain_residuals(self._packs[key], fd)[0]
+        n = r.numel()
+        idx, val = fused.topk_abs(r, min(k, n))
+        picked = {name: v.detach().reshape(n, -1)[idx] for name, v in points.items()
+                  if isinstance(v, torch.Tensor) and v.numel() >= n and v.shape[0] == n}
+        picked[residual] = val.reshape(-1, 1)
+        picked["index"] = idx.reshape(-1, 1)
+        d = _dist()
+        if d is not None and d.get_world_size() > 1:
+            world = d.get_world_size()
+            picked["index"] = picked["index"] * world + d.get_rank()  # position in the unsharded sample
+            gathered = {}
+            for name, v in picked.items():
+                parts = [torch.empty_like(v) for _ in range(world)]
+                d.all_gather(parts, v.contiguous())
+                gathered[name] = torch.cat(parts, dim=0)
+            sel, _ = fused.topk_abs(gathered[residual], min(k, gathered[residual].numel()))
+            picked = {name: v[sel] for name, v in gathered.items()}
+        return Variables(picked)
+
     # ------------------------------------------------------------- checkpoint
     def save(self):
         """`model.ckpt`: {<net>_dict, optimizer_<i>_dict, global_step} (idrlnet/solver.py:425-436)."""

@@ -190,6 +190,23 @@ PINN_API int pinn_weight_norm_forward(const float* g, const float* v, float* W, 
 PINN_API int pinn_weight_norm_backward(const float* g, const float* v, const float* dW, float* dg,
                               float* dv, int32_t out_dim, int32_t in_dim, void* stream);
 
+/* ---- adaptive re-sampling: forward-only residuals and top-k ------------- */
+/* out[e*N + n] = value of equation e at point n (no target subtracted, no loss):
+ * what Solver.infer_step (idrlnet/solver.py:410-420) returns for a PdeNode output
+ * such as "AllenCahn_u" in examples/allen_cahn/allen_cahn.py:134-136.  Jets by
+ * pinn_jet_forward into the workspace, then one elementwise kernel.  Only the
+ * equation table, coords, aux and n_points of `domain` are read. */
+PINN_API int64_t pinn_residual_workspace_bytes(const pinn_mlp* mlp, const pinn_jets* jets, int64_t n_points);
+PINN_API int pinn_residual_forward(const pinn_mlp* mlp, const pinn_jets* jets, const pinn_domain* domain,
+                          float* out, void* workspace, int64_t workspace_bytes, void* stream);
+/* Indices of the k largest |values[i]| in descending order, ties by ascending index
+ * (= np.argsort(-abs(values), kind="stable")[:k], the selection of
+ * examples/allen_cahn/allen_cahn.py:137-141), 1 <= k <= 4096, k <= n < 2^32.
+ * NaNs order above +inf.  val_out (may be NULL) receives values[idx_out[i]]. */
+PINN_API int64_t pinn_topk_workspace_bytes(int32_t k);
+PINN_API int pinn_topk_abs(const float* values, int64_t n, int32_t k, int64_t* idx_out, float* val_out,
+                  void* workspace, int64_t workspace_bytes, void* stream);
+
 /* ---- on-device sampling ------------------------------------------------ */
 /* Uniform points in an axis-aligned box (idrlnet/geo_utils/geo.py:316-343
  * `_ranged_sample`; the docs' "future versions will sample on GPU"), Philox4x32-10

@@ -334,3 +334,14 @@ def problem_from_flat(flat) -> dict:
                 d[grp][k] = v if v is not None else np.asarray(flat[f"dom/{m['name']}/{grp}/{k}"])
         problem["domains"].append(d)
     return problem
+
+
+def topk_abs(values, k):
+    """Adaptive re-sampling selection, examples/allen_cahn/allen_cahn.py:137-141:
+    `np.argsort(-1.0 * np.abs(residual))[:k]`.  The reference uses NumPy's default (unstable)
+    sort, so ties may come in any order there; the restatement fixes them by ascending index
+    (`kind="stable"`), which is one of the orders the reference can produce.  NaNs sort last in
+    NumPy (i.e. after every finite |r|); the CUDA path ranks them first -- residuals are finite."""
+    import numpy as np
+    v = np.abs(np.asarray(values, dtype=np.float32).ravel())
+    return np.argsort(-v, kind="stable")[:k]

@@ -190,38 +190,62 @@ def torch_module_from_net(net, device):
     return m.to(device)
 
 
+class cuda_packs(dict):
+    """Lazily built {owner net name: fused.NetPack} (+ .modules) of a problem on the GPU."""
+
+    def __init__(self, problem, device="cuda:0", precision="fp32"):
+        super().__init__()
+        self.problem, self.device, self.precision, self.modules = problem, device, precision, {}
+
+    def get_pack(self, net_name):
+        from idrlnet_b200 import fused
+        owner = owner_net(self.problem, net_name)
+        if owner["name"] not in self:
+            self.modules[owner["name"]] = torch_module_from_net(owner, self.device)
+            self[owner["name"]] = fused.NetPack(self.modules[owner["name"]], act=owner["act"], precision=self.precision)
+        return owner["name"], self[owner["name"]]
+
+
+def bind_fused_domain(problem, dom, packs):
+    """(fused.FusedDomain bound to the domain's columns on the GPU, its NetPack); raises NotFusable."""
+    import torch
+    from idrlnet_b200 import fused
+    cd = compile_problem_domain(problem, dom)
+    _, pack = packs.get_pack(cd.net.name)
+    device = packs.device
+    cols = {k: torch.as_tensor(v, device=device) for k, v in domain_columns(dom).items()}
+
+    def val(v):
+        return float(v) if np.ndim(v) == 0 else torch.as_tensor(np.asarray(v, np.float32).reshape(-1), device=device)
+
+    targets = {k: val(v) for k, v in dom["targets"].items()}
+    lambdas = {k: val(v) for k, v in dom.get("lambdas", {}).items()}
+    for k in dom["targets"]:
+        if k not in lambdas and ("lambda_" + k) in cols:
+            lambdas[k] = cols["lambda_" + k]
+    fd = fused.FusedDomain(dom["name"], cd, dom.get("loss", "square"), float(dom.get("sigma", 1.0)))
+    fd.bind(cols, targets, lambdas, cols["area"])
+    return fd, pack
+
+
 def run_cuda_fused(problem, device="cuda:0", precision="fp32"):
     """All fusable domains through fused.StepEngine (the C ABI).  Returns
     ({net: flat eff grad (numpy)}, {domain: loss}, skipped, {net: module})."""
     import torch
     from idrlnet_b200 import fused
-    modules, packs, per_net = {}, {}, {}
+    packs = cuda_packs(problem, device, precision)
+    per_net = {}
     skipped = []
     for dom in problem["domains"]:
         if not dom.get("targets"):
             continue
         try:
-            cd = compile_problem_domain(problem, dom)
+            fd, pack = bind_fused_domain(problem, dom, packs)
         except cp.NotFusable:
             skipped.append(dom["name"])
             continue
-        owner = owner_net(problem, cd.net.name)
-        if owner["name"] not in modules:
-            modules[owner["name"]] = torch_module_from_net(owner, device)
-            packs[owner["name"]] = fused.NetPack(modules[owner["name"]], act=owner["act"], precision=precision)
-        cols = {k: torch.as_tensor(v, device=device) for k, v in domain_columns(dom).items()}
-
-        def val(v):
-            return float(v) if np.ndim(v) == 0 else torch.as_tensor(np.asarray(v, np.float32).reshape(-1), device=device)
-
-        targets = {k: val(v) for k, v in dom["targets"].items()}
-        lambdas = {k: val(v) for k, v in dom.get("lambdas", {}).items()}
-        for k in dom["targets"]:
-            if k not in lambdas and ("lambda_" + k) in cols:
-                lambdas[k] = cols["lambda_" + k]
-        fd = fused.FusedDomain(dom["name"], cd, dom.get("loss", "square"), float(dom.get("sigma", 1.0)))
-        fd.bind(cols, targets, lambdas, cols["area"])
-        per_net.setdefault(owner["name"], []).append(fd)
+        name = next(k for k, v in packs.items() if v is pack)
+        per_net.setdefault(name, []).append(fd)
     grads, losses = {}, {}
     for name, doms in per_net.items():
         eng = fused.StepEngine(packs[name], doms)
@@ -230,7 +254,7 @@ def run_cuda_fused(problem, device="cuda:0", precision="fp32"):
         grads[name] = eng.grad.detach().cpu().numpy().copy()
         for d, l in zip(doms, eng.losses.detach().cpu().numpy()):
             losses[d.name] = float(l)
-    return grads, losses, skipped, modules
+    return grads, losses, skipped, packs.modules
 
 
 # --------------------------------------------------------------------------- #
@@ -264,30 +288,47 @@ def solver_from_problem(problem, network_dir, device=None, **solver_kw):
     return s, modules
 
 
-def oracle_train(problem, steps, lr=1e-3, gamma=0.95 ** 0.001):
+def _oracle_total(po, problem, nets, owners):
+    import torch
+    for n in owners:
+        n["layers_t"][:] = [((torch._weight_norm(l["v"], l["g"], 0) if "g" in l else l["W"]), l["b"]) for l in n["raw"]]
+    total = 0.0
+    for dom in problem["domains"]:
+        var = po.forward_domain(problem, dom, nets)
+        like = next(iter(var.values()))
+        diff = {k: var[k] - po._as_t(t, torch.float32, like) for k, t in dom["targets"].items()}
+        lam = {k: po._as_t(t, torch.float32, like) for k, t in dom.get("lambdas", {}).items()}
+        for k in dom["targets"]:
+            if k not in lam and ("lambda_" + k) in dom["points"]:
+                lam[k] = po._as_t(dom["points"]["lambda_" + k], torch.float32, like)
+        total = total + float(dom.get("sigma", 1.0)) * po.weighted_loss(diff, lam, var["area"], dom.get("loss", "square"))
+    return total
+
+
+def oracle_train(problem, steps, lr=1e-3, gamma=0.95 ** 0.001, lbfgs=None):
     """The reference training loop on the oracle (CPU, FP32): Adam + ExponentialLR
-    (idrlnet/optim.py:70-80), fixed points; returns the per-step (pre-update) losses."""
+    (idrlnet/optim.py:70-80), fixed points; returns the per-step (pre-update) losses.
+    `lbfgs=dict(lr=, max_iter=)` runs the closure branch instead (idrlnet/solver.py:316-326);
+    the value returned per step is then the first closure evaluation's loss, as torch's LBFGS does."""
     import torch
     from oracle import pinn_oracle as po
     nets = po.build_nets(problem)
     owners = [n for n in nets if not n.get("shares")]
     leaves = [t for n in owners for lay in n["raw"] for t in lay.values()]
+    if lbfgs is not None:
+        opt = torch.optim.LBFGS(leaves, **lbfgs)
+
+        def closure():
+            opt.zero_grad()
+            total = _oracle_total(po, problem, nets, owners)
+            total.backward()
+            return total
+        return [float(opt.step(closure).detach()) for _ in range(steps)]
     opt = torch.optim.Adam(leaves, lr=lr)
     losses = []
     for step in range(steps):
         opt.zero_grad()
-        for n in owners:
-            n["layers_t"][:] = [((torch._weight_norm(l["v"], l["g"], 0) if "g" in l else l["W"]), l["b"]) for l in n["raw"]]
-        total = 0.0
-        for dom in problem["domains"]:
-            var = po.forward_domain(problem, dom, nets)
-            like = next(iter(var.values()))
-            diff = {k: var[k] - po._as_t(t, torch.float32, like) for k, t in dom["targets"].items()}
-            lam = {k: po._as_t(t, torch.float32, like) for k, t in dom.get("lambdas", {}).items()}
-            for k in dom["targets"]:
-                if k not in lam and ("lambda_" + k) in dom["points"]:
-                    lam[k] = po._as_t(dom["points"]["lambda_" + k], torch.float32, like)
-            total = total + float(dom.get("sigma", 1.0)) * po.weighted_loss(diff, lam, var["area"], dom.get("loss", "square"))
+        total = _oracle_total(po, problem, nets, owners)
         total.backward()
         opt.step()
         for g in opt.param_groups:
