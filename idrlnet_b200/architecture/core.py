@@ -14,11 +14,11 @@ from typing import List, Sequence, Tuple, Union
 
 import torch
 
-from .header import logger
-from .net import NetNode
+from ..header import logger
+from ..net import NetNode
 
 __all__ = ["Activation", "Initializer", "get_activation_layer", "get_linear_layer", "MLP", "Siren", "Arch",
-           "get_net_node", "get_shared_net_node"]
+           "get_net_node", "get_shared_net_node", "SingleVar", "BoundedSingleVar"]
 
 
 class Activation(enum.Enum):  # idrlnet/architecture/layer.py:11-20

@@ -1,0 +1,315 @@
+"""Geometry kernel: parametric boundary pieces (`Edge`), signed-distance based solids with CSG
+(`Geometry`), and the samplers `sample_interior` / `sample_boundary`.
+
+Semantics follow idrlnet/geo_utils/geo.py:38-343 -- including the ORDER in which NumPy's global
+RNG is consumed (a 100-point area probe per edge, then the points, ranges in insertion order), so
+a seeded run draws the same point stream as the reference (tests/golden/geometry.npz).  Design
+differences: every SymPy expression is compiled once and cached (the reference re-lambdifies on
+every call); `Edge.rotation` is a proper rotation (the reference rotates the second coordinate with
+the already rotated first one, idrlnet/geo_utils/geo.py:52-61, which moves rotated edges off the
+solid); solids additionally sample on the GPU (`sample_interior_device`)."""
+import copy
+import itertools
+import math
+from typing import Callable, Dict, List, Optional, Tuple, Union
+
+import numpy as np
+import sympy
+from sympy import Max, Min, Symbol, cos, sin
+
+from .sympy_np import lambdify_np
+
+__all__ = ["Edge", "Geometry", "Geometry1D", "Geometry2D", "Geometry3D"]
+
+
+def _key(k) -> str:
+    return k if isinstance(k, str) else k.name
+
+
+def _low_discrepancy(n: int, stack: List[Tuple[str, Tuple[float, float]]]) -> Dict[str, np.ndarray]:
+    """Stratified points by recursive 2^dim-section (idrlnet/geo_utils/geo.py:370-403): the index range
+    is cut into 2^dim nearly equal blocks (remainders placed by a random shuffle), block i is squeezed
+    into the i-th orthant cell, recursively with halved cells."""
+    dim = len(stack)
+    cells = 2 ** dim
+    pts = np.random.rand(n, dim)
+
+    def split(lo: int, hi: int, corner: List[float], width: float) -> None:
+        if hi - lo <= 1:
+            return
+        base, rem = divmod(hi - lo, cells)
+        extra = (np.arange(cells - 1, 0, -1) + rem) // cells
+        np.random.shuffle(extra)
+        cuts = np.concatenate([[lo], (base + extra).cumsum() + lo, [hi]])
+        for i in range(cells):
+            a, b = cuts[i], cuts[i + 1]
+            bits = [(i >> j) & 1 for j in range(dim)]
+            for j in range(dim):
+                pts[a:b, j] = (pts[a:b, j] - corner[j]) / 2 + corner[j] + bits[j] * width
+            split(a, b, [c + width * bit for c, bit in zip(corner, bits)], width / 2)
+
+    split(0, n, [0.0] * dim, 0.5)
+    return {name: pts[:, j: j + 1] * (hi - lo) + lo for j, (name, (lo, hi)) in enumerate(stack)}
+
+
+def _ranged_sample(n: int, ranges: Dict, low_discrepancy: bool = False) -> Dict[str, np.ndarray]:
+    """number -> constant column, (lo, hi) -> uniform, callable -> callable(n)
+    (idrlnet/geo_utils/geo.py:316-343)."""
+    out: Dict[str, np.ndarray] = {}
+    stack = []
+    for key, value in ranges.items():
+        name = _key(key)
+        if isinstance(value, (float, int)):
+            out[name] = np.ones((n, 1)) * value
+        elif isinstance(value, tuple):
+            assert len(value) == 2, "Tuple: length of range should be 2!"
+            if low_discrepancy:
+                stack.append((name, value))
+            else:
+                out[name] = np.random.uniform(value[0], value[1], size=(n, 1))
+        elif callable(value):
+            out[name] = value(n)
+        else:
+            raise TypeError(f"range type {type(value)} not supported!")
+    if low_discrepancy:
+        out.update(_low_discrepancy(n, stack))
+    return {k: np.asarray(v, dtype=np.float64) for k, v in out.items()}
+
+
+class Edge:
+    """A boundary piece: coordinates and normals as functions of its parameters, with the
+    parameter ranges and its measure (`area`, possibly symbolic in shape parameters)."""
+
+    def __init__(self, functions: Dict, ranges: Dict, area):
+        self.functions = dict(functions)
+        self.ranges = dict(ranges)
+        self.area = area
+
+    @property
+    def axes(self) -> List[str]:
+        return [k for k in self.functions if not k.startswith("normal")]
+
+    def rotation(self, angle: float, axis: str = "z"):
+        assert len(self.axes) > 1, "Cannot rotate a object with dim<2"
+        a, b = [k for k in self.axes if k != axis][:2]
+        c, s = cos(angle), sin(angle)
+        f = self.functions
+        for u, v in ((a, b), ("normal_" + a, "normal_" + b)):
+            f[u], f[v] = c * f[u] - s * f[v], s * f[u] + c * f[v]
+        return self
+
+    def scaling(self, scale: float):
+        for k in self.axes:
+            self.functions[k] = self.functions[k] * scale
+        self.area = scale ** (len(self.axes) - 1) * self.area
+        return self
+
+    def translation(self, direction):
+        assert len(direction) == len(self.axes), "Moving direction must have the save dimension with the object"
+        for k, d in zip(self.axes, direction):
+            self.functions[k] = self.functions[k] + d
+        return self
+
+    def inverted(self) -> "Edge":
+        return Edge({k: (-v if k.startswith("normal_") else v) for k, v in self.functions.items()}, self.ranges, self.area)
+
+    def sample(self, density: int, param_ranges=None, low_discrepancy=False) -> Dict[str, np.ndarray]:
+        param_ranges = {} if param_ranges is None else param_ranges
+        ranges = {**self.ranges, **param_ranges}
+        names = [_key(k) for k in ranges]
+        area_fn = lambdify_np(self.area, names)
+        probe = _ranged_sample(100, ranges)                      # expected measure over the parameter ranges
+        n = int(density * np.mean(area_fn(**probe)))
+        params = _ranged_sample(n, ranges, low_discrepancy)
+        out = {"area": area_fn(**params) / n} if n else {"area": np.zeros((0, 1))}
+        for k, fn in self.functions.items():
+            out[k] = lambdify_np(fn, names)(**params)
+        for k in param_ranges:
+            out[_key(k)] = params[_key(k)]
+        return out
+
+
+def _rotate_bounds(bx: Tuple, by: Tuple, angle: float):
+    try:
+        c, s = math.cos(angle), math.sin(angle)
+    except TypeError:  # symbolic angle: the bounding square of a 45 degree turn covers every case
+        c, s = math.cos(math.pi / 4), math.sin(math.pi / 4)
+    xs, ys = zip(*[(c * x - s * y, s * x + c * y) for x, y in itertools.product(bx, by)])
+    return (min(xs), max(xs)), (min(ys), max(ys))
+
+
+def _combine(kind: str, f, g):
+    """max / min / negation of signed-distance fields that are SymPy expressions or callables."""
+    symbolic = all(isinstance(h, sympy.Basic) or isinstance(h, (int, float)) for h in (f, g) if h is not None)
+    if kind == "neg":
+        return -f if symbolic else (lambda **x: -lambdify_np(f, x)(**x))
+    if symbolic:
+        return Max(f, g) if kind == "max" else Min(f, g)
+    op = np.maximum if kind == "max" else np.minimum
+    return lambda **x: op(lambdify_np(f, x)(**x), lambdify_np(g, x)(**x))
+
+
+class Geometry:
+    """A solid: `sdf` (positive inside), bounding box `bounds` and boundary `edges`."""
+    edges: List[Edge] = None
+    bounds: Dict = None
+    sdf = None
+
+    @property
+    def axes(self) -> List[str]:
+        return self.edges[0].axes
+
+    def _blank(self, other: Optional["Geometry"] = None) -> "Geometry":
+        for base in (Geometry1D, Geometry2D, Geometry3D):
+            if isinstance(self, base):
+                assert other is None or isinstance(other, base), "CSG needs solids of the same dimension"
+                return base()
+        raise TypeError("CSG needs a Geometry1D/2D/3D")
+
+    # -- rigid motions and scaling ------------------------------------------------------------
+    def _need_symbolic_sdf(self):
+        if not isinstance(self.sdf, sympy.Basic):
+            raise NotImplementedError("this solid's sdf is a Python callable and cannot be transformed")
+
+    def translation(self, direction: Union[List, Tuple]) -> "Geometry":
+        assert len(direction) == len(self.axes)
+        self._need_symbolic_sdf()
+        for e in self.edges:
+            e.translation(direction)
+        self.sdf = self.sdf.subs([(Symbol(a), Symbol(a) - d) for a, d in zip(self.axes, direction)])
+        self.bounds = {**self.bounds, **{a: (self.bounds[a][0] + d, self.bounds[a][1] + d) for a, d in zip(self.axes, direction)}}
+        return self
+
+    def rotation(self, angle: float, axis: str = "z", center=None) -> "Geometry":
+        self._need_symbolic_sdf()
+        if center is not None:
+            self.translation([-c for c in center])
+        for e in self.edges:
+            e.rotation(angle, axis)
+        a, b = [k for k in self.axes if k != axis][:2]
+        sa, sb, ta, tb = Symbol(a), Symbol(b), Symbol("_rot_a"), Symbol("_rot_b")
+        self.sdf = self.sdf.subs({sa: cos(angle) * ta + sin(angle) * tb, sb: -sin(angle) * ta + cos(angle) * tb},
+                                 simultaneous=True).subs({ta: sa, tb: sb}, simultaneous=True)
+        self.bounds = dict(self.bounds)
+        self.bounds[a], self.bounds[b] = _rotate_bounds(self.bounds[a], self.bounds[b], angle)
+        if center is not None:
+            self.translation(center)
+        return self
+
+    def scaling(self, scale: float, center: Tuple = None) -> "Geometry":
+        assert scale > 0, "scaling must be positive"
+        self._need_symbolic_sdf()
+        if center is not None:
+            self.translation(tuple(-c for c in center))
+        for e in self.edges:
+            e.scaling(scale)
+        self.sdf = scale * self.sdf.subs({Symbol(a): Symbol(a) / scale for a in self.axes}, simultaneous=True)
+        self.bounds = {**self.bounds, **{a: (self.bounds[a][0] * scale, self.bounds[a][1] * scale) for a in self.axes}}
+        if center is not None:
+            self.translation(center)
+        return self
+
+    def duplicate(self) -> "Geometry":
+        return copy.deepcopy(self)
+
+    # -- CSG ----------------------------------------------------------------------------------------
+    def __add__(self, other: "Geometry") -> "Geometry":
+        g = self._blank(other)
+        g.edges = self.edges + other.edges
+        g.sdf = _combine("max", self.sdf, other.sdf)
+        g.bounds = {k: (min(v[0], other.bounds[k][0]), max(v[1], other.bounds[k][1])) for k, v in self.bounds.items()}
+        return g
+
+    def __sub__(self, other: "Geometry") -> "Geometry":
+        g = self._blank(other)
+        g.edges = self.edges + [e.inverted() for e in other.edges]
+        g.sdf = _combine("min", self.sdf, _combine("neg", other.sdf, None))
+        g.bounds = dict(self.bounds)
+        return g
+
+    def __and__(self, other: "Geometry") -> "Geometry":
+        g = self._blank(other)
+        g.edges = self.edges + other.edges
+        g.sdf = _combine("min", self.sdf, other.sdf)
+        g.bounds = {k: (max(v[0], other.bounds[k][0]), min(v[1], other.bounds[k][1])) for k, v in self.bounds.items()}
+        return g
+
+    def __invert__(self) -> "Geometry":
+        g = self._blank()
+        g.edges = [e.inverted() for e in self.edges]
+        g.sdf = _combine("neg", self.sdf, None)
+        g.bounds = {k: (-float("inf"), float("inf")) for k in self.bounds}
+        return g
+
+    # -- sampling ---------------------------------------------------------------------------------
+    def _sieve_points(self, points: Dict[str, np.ndarray], sieve, tol=1e-4, sign=1.0) -> Dict[str, np.ndarray]:
+        names = list(points.keys())
+        points["sdf"] = lambdify_np(self.sdf, names)(**{k: points[k] for k in names})
+        keep = np.logical_and(points["sdf"] > -tol, lambdify_np(True if sieve is None else sieve, list(points))(**points))
+        if sign == -1:
+            keep = np.logical_and(points["sdf"] < tol, keep)
+        return {k: v[keep[:, 0], :] for k, v in points.items()}
+
+    def sample_boundary(self, density: int, sieve=None, param_ranges: Dict = None, low_discrepancy=False):
+        param_ranges = {} if param_ranges is None else param_ranges
+        parts = [e.sample(density, param_ranges, low_discrepancy) for e in self.edges]
+        points = {k: np.concatenate([p[k] for p in parts], axis=0) for k in parts[0]}
+        return self._sieve_points(points, sieve, sign=-1, tol=1e-4)
+
+    def sample_interior(self, density: int, bounds: Dict = None, sieve=None, param_ranges: Dict = None,
+                        low_discrepancy=False) -> Dict[str, np.ndarray]:
+        bounds = self.bounds if bounds is None else bounds
+        bounds = {_key(k): v for k, v in bounds.items()}
+        param_ranges = {} if param_ranges is None else param_ranges
+        measure = np.prod([hi - lo for lo, hi in bounds.values()])
+        n = int(measure * density)
+        points = _ranged_sample(n, {**bounds, **param_ranges}, low_discrepancy)
+        points = self._sieve_points(points, sieve, tol=0.0)
+        points["area"] = np.zeros_like(points["sdf"]) + (1.0 / density)
+        return points
+
+    def sample_interior_device(self, density: int, seed: int = 0, offset: int = 0, bounds: Dict = None, sieve=None,
+                               device=None):
+        """`sample_interior` on the GPU: Philox box sampling by pinn_sample_box, the signed distance
+        and the sieve evaluated by the same SymPy expressions lowered to torch, rejection by mask.
+        Returns a dict of [n, 1] float32 device tensors (coordinates, `sdf`, `area`)."""
+        import ctypes as C
+
+        import torch
+
+        from .. import native as nv
+        from ..torch_util import torch_lambdify
+        dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        bounds = {_key(k): v for k, v in (self.bounds if bounds is None else bounds).items()}
+        names = list(bounds)
+        n = int(np.prod([hi - lo for lo, hi in bounds.values()]) * density)
+        cols = [torch.empty(n, device=dev, dtype=torch.float32) for _ in names]
+        lo = (C.c_float * len(names))(*[float(bounds[k][0]) for k in names])
+        hi = (C.c_float * len(names))(*[float(bounds[k][1]) for k in names])
+        nv.check(nv.lib().pinn_sample_box(nv.ptr_array([c.data_ptr() for c in cols]), len(names), lo, hi, n, seed, 0,
+                                          offset, None, 0, torch.cuda.current_stream(dev).cuda_stream))
+        pts = {k: c.reshape(-1, 1) for k, c in zip(names, cols)}
+        if not isinstance(self.sdf, sympy.Basic):
+            raise NotImplementedError("device sampling needs a symbolic sdf")
+        sdf = torch_lambdify(names, self.sdf)(**pts)
+        sdf = sdf if isinstance(sdf, torch.Tensor) and sdf.shape == pts[names[0]].shape else torch.zeros_like(pts[names[0]]) + sdf
+        keep = sdf > 0
+        if sieve is not None:
+            keep = keep & torch_lambdify(names + ["sdf"], sieve)(**pts, sdf=sdf)
+        mask = keep[:, 0]
+        out = {k: v[mask] for k, v in pts.items()}
+        out["sdf"] = sdf[mask]
+        out["area"] = torch.full_like(out["sdf"], 1.0 / density)
+        return out
+
+
+class Geometry1D(Geometry):
+    pass
+
+
+class Geometry2D(Geometry):
+    pass
+
+
+class Geometry3D(Geometry):
+    pass

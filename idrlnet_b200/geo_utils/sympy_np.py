@@ -1,0 +1,67 @@
+"""SymPy / constants / callables -> vectorised NumPy callables taking keyword columns
+(the role of idrlnet/geo_utils/sympy_np.py:134-165).
+
+Unlike the reference, which re-lambdifies on every sampling call (78 % of its as-shipped step
+time), compiled callables are cached on (expression, argument names)."""
+from functools import reduce
+from typing import Callable, Dict, Iterable, Tuple
+
+import numpy as np
+import sympy
+
+__all__ = ["lambdify_np"]
+
+_NUMERIC = {
+    "amin": lambda x: reduce(np.minimum, x),
+    "amax": lambda x: reduce(np.maximum, x),
+    "Min": lambda *x: reduce(np.minimum, x),
+    "Max": lambda *x: reduce(np.maximum, x),
+    "Heaviside": lambda x, *a: np.heaviside(x, 0.0),
+    "equal": lambda a, b: np.isclose(a, b),
+    "Xor": np.logical_xor,
+    "cos": np.cos, "sin": np.sin, "tan": np.tan, "exp": np.exp, "sqrt": np.sqrt, "log": np.log,
+    "sinh": np.sinh, "cosh": np.cosh, "tanh": np.tanh, "asin": np.arcsin, "acos": np.arccos,
+    "atan": np.arctan, "Abs": np.abs, "sign": np.sign, "DiracDelta": np.zeros_like,
+}
+
+_CACHE: Dict[Tuple, Callable] = {}
+
+
+def _names(keys: Iterable) -> Tuple[str, ...]:
+    return tuple(k if isinstance(k, str) else k.name for k in keys)
+
+
+def _like(cols: Dict[str, np.ndarray]):
+    return next(iter(cols.values()))
+
+
+def lambdify_np(f, r: Iterable) -> Callable:
+    """Callable `fn(**columns)`; `r` names the keyword arguments (strings or Symbols).
+    bool -> constant mask, number -> constant column, callable -> itself, SymPy -> NumPy code."""
+    names = _names(r.keys() if isinstance(r, dict) else r)
+    if isinstance(f, (bool, np.bool_)) or f is sympy.true or f is sympy.false:
+        flag = bool(f)
+        return lambda **x: np.full(_like(x).shape, flag, dtype=bool)
+    if callable(f) and not isinstance(f, sympy.Basic):
+        return f
+    try:
+        value = float(f)
+        return lambda **x: np.ones_like(_like(x), dtype=np.float64) * value
+    except (TypeError, ValueError):
+        pass
+    expr = sympy.sympify(f)
+    key = (expr, names)
+    fn = _CACHE.get(key)
+    if fn is None:
+        raw = sympy.lambdify([sympy.Symbol(n) for n in names], expr, [_NUMERIC, "numpy"])
+
+        def fn(*args, **x):
+            x = {**dict(zip(names, args)), **x}
+            out = raw(**{n: x[n] for n in names})
+            like = next((v for v in x.values() if isinstance(v, np.ndarray)), None)
+            if like is None:
+                return out
+            return out if isinstance(out, np.ndarray) and out.shape == like.shape else np.broadcast_to(out, like.shape).copy()
+        fn.input_keys = list(names)
+        _CACHE[key] = fn
+    return fn

@@ -103,7 +103,8 @@ class VertexTaskPipeline:
         for n in self.evaluation_order_list:
             if isinstance(n, PdeNode):
                 for s in n.sub_nodes:
-                    exprs[s.name] = s.evaluate.tf_eq
+                    if hasattr(s.evaluate, "tf_eq"):  # integral nodes (IntEq) are not expressions of the jets
+                        exprs[s.name] = s.evaluate.tf_eq
         wanted = set()
         for n in self.evaluation_order_list:
             wanted.update(n.derivatives)

@@ -1,31 +1,12 @@
-"""Predefined equations and operators (mirror of idrlnet/pde_op/equations.py and
-the pointwise operators of idrlnet/pde_op/operator.py).  Each class only builds
-SymPy expressions and calls `make_nodes()`; all of them are polynomials in the
-jet symbols, i.e. fusable by `compiler.py`."""
-from typing import Union
+"""Predefined equations (mirror of idrlnet/pde_op/equations.py).  Each class only builds SymPy
+expressions and calls `make_nodes()`; all of them are polynomials in the jet symbols, i.e. fusable
+by `compiler.py`."""
+from sympy import Number
 
-from sympy import Function, Number, Symbol, symbols
+from ..pde import PdeNode
+from ._common import _T, _X, _Y, _Z, _coords, _field
 
-from .pde import PdeNode
-
-__all__ = ["DiffusionNode", "NavierStokesNode", "WaveNode", "BurgersNode", "SchrodingerNode", "AllenCahnNode",
-           "NormalGradient", "Difference", "Derivative"]
-
-_X, _Y, _Z, _T = symbols("x y z t")
-
-
-def _coords(dim, time):
-    v = [_X, _Y, _Z][: int(dim)]
-    return v + ([_T] if time else [])
-
-
-def _field(s, variables):
-    """str -> unknown function of the coordinates; number -> constant."""
-    if isinstance(s, str):
-        return Function(s)(*variables)
-    if isinstance(s, (int, float)):
-        return Number(s)
-    return s
+__all__ = ["DiffusionNode", "NavierStokesNode", "WaveNode", "BurgersNode", "SchrodingerNode", "AllenCahnNode"]
 
 
 def _grad_sum(coef, f, variables):
@@ -120,41 +101,4 @@ class AllenCahnNode(PdeNode):
         self.gama_1, self.gama_2 = gamma_1, gamma_2
         uf = _field(u, [_X, _T])
         self.equations = {"AllenCahn_" + str(uf): uf.diff(_T) - gamma_1 * uf.diff(_X, 2) - gamma_2 * (uf - uf ** 3)}
-        self.make_nodes()
-
-
-class NormalGradient(PdeNode):
-    """n . grad T  (idrlnet/pde_op/operator.py:26-54)."""
-
-    def __init__(self, T: Union[str, Symbol, float, int], dim=3, time=True):
-        super().__init__()
-        self.T, self.dim, self.time = T, dim, time
-        nx, ny, nz = symbols("normal_x normal_y normal_z")
-        Tf = Function(T)(*_coords(dim, time))
-        self.equations = {"normal_gradient_" + T: nx * Tf.diff(_X) + ny * Tf.diff(_Y) + nz * Tf.diff(_Z)}
-        self.make_nodes()
-
-
-class Difference(PdeNode):
-    """T - S  (idrlnet/pde_op/operator.py:57-88)."""
-
-    def __init__(self, T, S, dim=3, time=True):
-        super().__init__()
-        self.T, self.S, self.dim, self.time = T, S, dim, time
-        variables = _coords(dim, time)
-        self.equations = {"difference_" + T + "_" + S: Function(T)(*variables) - Function(S)(*variables)}
-        self.make_nodes()
-
-
-class Derivative(PdeNode):
-    """dT/dp - S  (idrlnet/pde_op/operator.py:91-130)."""
-
-    def __init__(self, T, p, S=0.0, dim=3, time=True):
-        super().__init__()
-        self.T, self.S, self.dim, self.time = T, S, dim, time
-        variables = _coords(dim, time)
-        Sf = Function(S)(*variables) if isinstance(S, str) else (Number(S) if isinstance(S, (float, int)) else S)
-        p = Symbol(p) if isinstance(p, str) else p
-        name = "derivative_" + T + ":" + str(p) + ("_" + str(S) if isinstance(S, str) else "")
-        self.equations = {name: Function(T)(*variables).diff(p) - Sf}
         self.make_nodes()

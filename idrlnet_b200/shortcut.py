@@ -1,6 +1,6 @@
 """API facade -- `import idrlnet_b200.shortcut as sc` replaces
 `import idrlnet.shortcut as sc` (idrlnet/shortcut.py:1-13)."""
-from .geo import *  # noqa: F401,F403
+from .geo_utils import *  # noqa: F401,F403
 from .architecture import *  # noqa: F401,F403
 from .pde_op import *  # noqa: F401,F403
 from .net import NetNode  # noqa: F401

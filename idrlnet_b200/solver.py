@@ -184,7 +184,8 @@ class Solver(Notifier, Optimizable):
         for pde in self.pdes:
             if isinstance(pde, PdeNode):
                 for sub in pde.sub_nodes:
-                    exprs[sub.name] = sub.evaluate.tf_eq
+                    if hasattr(sub.evaluate, "tf_eq"):
+                        exprs[sub.name] = sub.evaluate.tf_eq
         specs = [cp.NetSpec(nn.name, tuple(nn.inputs), tuple(nn.outputs)) for nn in self.netnodes]
         by_name = {nn.name: nn for nn in self.netnodes}
         for dom in self.sample_domains:
@@ -388,7 +389,8 @@ class Solver(Notifier, Optimizable):
         sample = self._shard({domain_name: dom.sample()})[domain_name]
         points = Variables({key: v for key, v in sample.items() if key in self.invar_dict_index[domain_name]})
         points.to_torch_tensor_()
-        exprs = {sub.name: sub.evaluate.tf_eq for pde in self.pdes if isinstance(pde, PdeNode) for sub in pde.sub_nodes}
+        exprs = {sub.name: sub.evaluate.tf_eq for pde in self.pdes if isinstance(pde, PdeNode) for sub in pde.sub_nodes
+                 if hasattr(sub.evaluate, "tf_eq")}
         specs = [cp.NetSpec(nn.name, tuple(nn.inputs), tuple(nn.outputs)) for nn in self.netnodes]
         cd = cp.compile_domain([residual], exprs, specs, list(points.keys()))
         nn = next(n for n in self.netnodes if n.name == cd.net.name)
