@@ -44,14 +44,21 @@ def lambdify_np(f, r: Iterable) -> Callable:
         return lambda **x: np.full(_like(x).shape, flag, dtype=bool)
     if callable(f) and not isinstance(f, sympy.Basic):
         return f
-    try:
-        value = float(f)
-        return lambda **x: np.ones_like(_like(x), dtype=np.float64) * value
-    except (TypeError, ValueError):
-        pass
-    expr = sympy.sympify(f)
-    key = (expr, names)
+    if not isinstance(f, sympy.Basic):
+        try:
+            value = float(f)
+            return lambda **x: np.ones_like(_like(x), dtype=np.float64) * value
+        except (TypeError, ValueError):
+            f = sympy.sympify(f)
+    key = (f, names)                     # SymPy caches the hash: a hit costs one dict lookup
     fn = _CACHE.get(key)
+    if fn is None and not f.free_symbols and f.is_number:
+        value = float(f)
+
+        def fn(**x):
+            return np.ones_like(_like(x), dtype=np.float64) * value
+        _CACHE[key] = fn
+    expr = f
     if fn is None:
         raw = sympy.lambdify([sympy.Symbol(n) for n in names], expr, [_NUMERIC, "numpy"])
 

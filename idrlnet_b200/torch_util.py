@@ -24,12 +24,32 @@ def _integral_fun(x):
 
 integral = implemented_function("integral", lambda x: _integral_fun(x))  # idrlnet/torch_util.py:16-22
 
-TORCH_SYMPY_PRINTER = {  # idrlnet/torch_util.py:43-65
+def _tmax(a, b):
+    if isinstance(a, torch.Tensor) and isinstance(b, torch.Tensor):
+        return torch.maximum(a, b)
+    if isinstance(a, torch.Tensor):
+        return torch.clamp(a, min=float(b))
+    if isinstance(b, torch.Tensor):
+        return torch.clamp(b, min=float(a))
+    return max(a, b)
+
+
+def _tmin(a, b):
+    if isinstance(a, torch.Tensor) and isinstance(b, torch.Tensor):
+        return torch.minimum(a, b)
+    if isinstance(a, torch.Tensor):
+        return torch.clamp(a, max=float(b))
+    if isinstance(b, torch.Tensor):
+        return torch.clamp(b, max=float(a))
+    return min(a, b)
+
+
+TORCH_SYMPY_PRINTER = {  # idrlnet/torch_util.py:43-65 (Min/Max also take python scalars here)
     "sin": torch.sin, "cos": torch.cos, "tan": torch.tan, "exp": torch.exp, "sqrt": torch.sqrt,
     "Abs": torch.abs, "tanh": torch.tanh, "DiracDelta": torch.zeros_like,
-    "Heaviside": lambda x: torch.heaviside(x, torch.tensor([0.0], device=x.device)),
-    "amin": lambda x: reduce(torch.minimum, x), "amax": lambda x: reduce(torch.maximum, x),
-    "Min": lambda *x: reduce(torch.minimum, x), "Max": lambda *x: reduce(torch.maximum, x),
+    "Heaviside": lambda x, *half: torch.heaviside(x, torch.tensor([0.0], device=x.device, dtype=x.dtype)),
+    "amin": lambda x: reduce(_tmin, x), "amax": lambda x: reduce(_tmax, x),
+    "Min": lambda *x: reduce(_tmin, x), "Max": lambda *x: reduce(_tmax, x), "sign": torch.sign,
     "equal": lambda x, y: torch.isclose(x, y), "Xor": torch.logical_xor, "log": torch.log,
     "sinh": torch.sinh, "cosh": torch.cosh, "asin": torch.arcsin, "acos": torch.arccos, "atan": torch.arctan,
 }
