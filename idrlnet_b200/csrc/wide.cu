@@ -505,7 +505,7 @@ __global__ void __launch_bounds__(1024) head_bwd_kernel(WNet net, const float* _
 struct WideLayout {  // workspace offsets in floats
   int64_t Z, Hb;            // L planes-sets each: [l][C][Mc][H]
   int64_t dw, db, first, head, loss_slots, acc_end, total;
-  int64_t wt, wprep, ybar;
+  int64_t wt, wprep, ybar, tdw;  // tdw: re-tiled operands of the pipelined TF32 dW GEMM
   int Mc, n_splits, fp32_splits, tiles, n_dom;
 };
 
@@ -580,7 +580,7 @@ bool make_net(const pinn_mlp* m, const pinn_jets* j, WNet* n) {
 
 WideLayout make_layout(const WNet& n, int n_dom) {
   WideLayout wl;
-  const int64_t per_point = 2ll * n.L * n.C * n.H * 4;
+  const int64_t per_point = (2ll * n.L + (n.precision ? 3 : 0)) * n.C * n.H * 4;  // planes (+ re-tiled dW operands)
   int64_t mc = kChunkBudget / per_point;
   mc = mc / kBM * kBM;
   if (mc < 256) mc = 256;
@@ -609,6 +609,7 @@ WideLayout make_layout(const WNet& n, int n_dom) {
   wl.Z = off; off += planes;
   wl.Hb = off; off += planes;
   wl.ybar = off; off += (int64_t)mc * kMaxC * 4;
+  wl.tdw = off; off += n.precision ? (tc_dw2_scratch_floats(n.H, n.C, (int)mc) + 3) / 4 * 4 : 0;
   wl.total = (off + 3) / 4 * 4;
   return wl;
 }
@@ -640,7 +641,6 @@ int run_chunks(const WNet& n, const WideLayout& wl, float* ws, int mode, const p
   const size_t planes = (size_t)C * wl.Mc * H;
   Coords xs;
   for (int d = 0; d < PINN_MAX_IN; ++d) xs.p[d] = d < n.n_in ? coords[d] : nullptr;
-  const int hstride = n.n_out * H + n.n_out + 1;
   for (int64_t n0 = 0; n0 < N; n0 += wl.Mc) {
     const int m = (int)((N - n0 < wl.Mc) ? N - n0 : wl.Mc);
     float* Z = ws + wl.Z;
@@ -702,19 +702,19 @@ int run_chunks(const WNet& n, const WideLayout& wl, float* ws, int mode, const p
       const float* hprev = Hb + (l - 2) * planes;
       {
         float* dwp = ws + wl.dw + (size_t)(l - 2) * wl.n_splits * H * H;
-        if (n.precision) {
-          int rc = tc_launch_dw(zb, hprev, H, C, m, wl.Mc, dwp, wl.n_splits, st);
+        float* dbp = ws + wl.db + (size_t)(l - 2) * kBlocks * 8 * H;
+        if (n.precision) {  // db_l rides along with the re-tiling of zbar_l
+          int rc = tc_launch_dw2(zb, hprev, H, C, m, wl.Mc, dwp, wl.n_splits, ws + wl.tdw, dbp, st);
           if (rc) return rc;
         } else {
           dim3 grid(wl.tiles * wl.tiles, wl.fp32_splits);
           gemm_dw_kernel<<<grid, 256, 0, st>>>(zb, hprev, H, C, m, wl.Mc, dwp, wl.tiles);
-          count_launch(1);
+          RedSpec rs;
+          memset(&rs, 0, sizeof(rs));
+          rs.nq = 1;
+          reduce_cols_kernel<<<dim3((H + 31) / 32, kBlocks), 256, 0, st>>>(zb, rs, H, n0, m, wl.Mc, dbp);
+          count_launch(2);
         }
-        RedSpec rs;
-        memset(&rs, 0, sizeof(rs));
-        rs.nq = 1;
-        reduce_cols_kernel<<<dim3((H + 31) / 32, kBlocks), 256, 0, st>>>(zb, rs, H, n0, m, wl.Mc, ws + wl.db + (size_t)(l - 2) * kBlocks * 8 * H);
-        count_launch(1);
       }
       int rc = n.precision
                    ? tc_launch_rows<ACT, 1>(n, zb, ws + wl.wt + (size_t)(l - 2) * H * H, nullptr, Z + (l - 2) * planes, nullptr,

@@ -1,0 +1,198 @@
+// Weight-gradient GEMM of the layer-streamed TF32 path, pipelined:
+//   dW_l[j][k] (+)= sum over (channel c, point n) of zbar_l[c][n][j] * h_{l-1}[c][n][k].
+//
+// The contraction runs over points, so both operands are needed with K = point contiguous, i.e.
+// transposed with respect to the [c][n][unit] planes the row GEMMs use.  `retile_kernel` writes
+// each operand once in the tensor core's own shared-memory layout (no-swizzle K-major core
+// matrices, TF32-rounded): tiles of 32 points x R units, tile(kb, ub) at ((kb * UB + ub) * 8 * R * 4)
+// floats with element (unit row, point k) at ((k / 4) * R + row) * 4 + k % 4.  A tile is therefore one
+// contiguous block that `cp.async.bulk` drops into shared memory unchanged, and the GEMM kernel has
+// no staging code at all: one thread streams tiles through a 4-stage ring (mbarrier expect_tx),
+// one thread issues tcgen05.mma (M = 128 units j, N = R_B units k, K = 8 points per instruction) and
+// releases stages with tcgen05.commit, the accumulator stays in TMEM until the split's K range is
+// exhausted, then 128 threads add it into the split's partial slot.
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "tc_common.cuh"
+#include "wide_internal.cuh"
+
+namespace pinn {
+namespace {
+
+constexpr int kStages = 4;
+constexpr int kKB = 32;  // points per K block (4 MMAs of K = 8)
+
+// src: planes [c][n][j] (plane stride Mc * H), valid n < m, j < H.  grid (nblk, UB, C), 256 threads.
+// colsum (optional, R = 128 only): colsum[nb][j] = sum over the block's points of the UNROUNDED value
+// channel (c == 0) -- the bias gradient db_l = sum_n zbar_l[0][n][:] rides along with the re-tiling.
+template <int R>
+__global__ void __launch_bounds__(256) retile_kernel(const float* __restrict__ src, float* __restrict__ dst, int H, int m, int Mc,
+                                                     int nblk, int UB, float* __restrict__ colsum) {
+  __shared__ float t[kKB][R + 1];
+  __shared__ float red[256];
+  const int nb = blockIdx.x, ub = blockIdx.y, c = blockIdx.z;
+  const float* plane = src + (size_t)c * Mc * H;
+  float acc = 0.f;
+  for (int i = threadIdx.x; i < kKB * R; i += 256) {
+    const int p = i / R, jj = i - p * R;
+    const int n = nb * kKB + p, j = ub * R + jj;
+    const float v = (n < m && j < H) ? plane[(size_t)n * H + j] : 0.f;
+    acc += v;  // R divides 256: a thread always sees the same unit jj
+    t[p][jj] = tc::to_tf32(v);
+  }
+  if (R == 128 && colsum != nullptr && c == 0) {
+    red[threadIdx.x] = acc;
+    __syncthreads();
+    if (threadIdx.x < 128 && ub * 128 + threadIdx.x < H)
+      colsum[(size_t)nb * H + ub * 128 + threadIdx.x] = red[threadIdx.x] + red[threadIdx.x + 128];
+  }
+  __syncthreads();
+  float* tile = dst + ((size_t)(c * nblk + nb) * UB + ub) * (kKB * R);
+  for (int i = threadIdx.x; i < (kKB / 4) * R; i += 256) {
+    const int kq = i / R, row = i - kq * R;
+    *reinterpret_cast<float4*>(tile + (size_t)i * 4) = make_float4(t[kq * 4][row], t[kq * 4 + 1][row], t[kq * 4 + 2][row], t[kq * 4 + 3][row]);
+  }
+}
+
+// grid (tiles_j * tiles_k, splits); 128 threads.  tz: A tiles (R = 128), th: B tiles (R = NB).
+template <int NB>
+__global__ void __launch_bounds__(128, 1) tc_dw2_kernel(const float* __restrict__ tz, const float* __restrict__ th, int H, int kblocks,
+                                                        int UBA, int UBB, int tiles_k, float* __restrict__ part) {
+  extern __shared__ __align__(128) float sm[];
+  __shared__ uint64_t full[kStages], empty[kStages], done;
+  __shared__ uint32_t tmem_slot;
+  constexpr int kAFloats = kKB * 128, kBFloats = kKB * NB, kStageFloats = kAFloats + kBFloats;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int tj = blockIdx.x / tiles_k, tk = blockIdx.x % tiles_k;
+  const int per = (kblocks + gridDim.y - 1) / gridDim.y;
+  const int kb0 = blockIdx.y * per, kb1 = (kb0 + per < kblocks) ? kb0 + per : kblocks;
+  const int nit = kb1 - kb0;
+  if (tid == 0) {
+    for (int s = 0; s < kStages; ++s) {
+      tc::mbar_init(&full[s], 1);
+      tc::mbar_init(&empty[s], 1);
+    }
+    tc::mbar_init(&done, 1);
+    tc::fence_mbar_init();
+  }
+  if (warp == 0) tc::tmem_alloc(&tmem_slot, NB);
+  tc::tc_fence_before();
+  __syncthreads();
+  tc::tc_fence_after();
+  const uint32_t tmem = tmem_slot;
+  if (nit > 0) {
+    if (warp == 0 && lane == 0) {  // producer: whole tiles by bulk copy
+      for (int it = 0; it < nit; ++it) {
+        const int s = it % kStages;
+        if (it >= kStages && !tc::mbar_wait(&empty[s], ((it / kStages) - 1) & 1)) __trap();
+        float* sA = sm + (size_t)s * kStageFloats;
+        const size_t kb = (size_t)(kb0 + it);
+        tc::mbar_expect_tx(&full[s], (uint32_t)(kStageFloats * sizeof(float)));
+        tc::bulk_copy_g2s(sA, tz + (kb * UBA + tj) * kAFloats, kAFloats * sizeof(float), &full[s]);
+        tc::bulk_copy_g2s(sA + kAFloats, th + (kb * UBB + tk) * kBFloats, kBFloats * sizeof(float), &full[s]);
+      }
+    } else if (warp == 1 && lane == 0) {  // tensor-core issuer
+      const uint32_t idesc = tc::idesc_tf32(NB, 0, 0);
+      for (int it = 0; it < nit; ++it) {
+        const int s = it % kStages;
+        if (!tc::mbar_wait(&full[s], (it / kStages) & 1)) __trap();
+        tc::tc_fence_after();
+        const uint32_t a0 = tc::smem_u32(sm + (size_t)s * kStageFloats), b0 = a0 + kAFloats * sizeof(float);
+#pragma unroll
+        for (int ks = 0; ks < kKB / 8; ++ks) {
+          const uint64_t da = tc::smem_desc(a0 + ks * 2 * (128 * 16), 128 * 16, 128);
+          const uint64_t db = tc::smem_desc(b0 + ks * 2 * (NB * 16), NB * 16, 128);
+          tc::mma_tf32(tmem, da, db, idesc, (it > 0 || ks > 0) ? 1u : 0u);
+        }
+        tc::mma_commit(&empty[s]);  // the stage is free once these MMAs have read it
+      }
+      tc::mma_commit(&done);
+    }
+    __syncwarp();
+    if (!tc::mbar_wait(&done, 0)) __trap();
+    tc::tc_fence_after();
+    const int j = tj * 128 + tid;
+    const uint32_t lane_base = (uint32_t)(warp * 32) << 16;
+    float* out = part + (size_t)blockIdx.y * H * H;
+    for (int g = 0; g < NB / 16; ++g) {
+      float v[16];
+      tc::tmem_ld16(tmem + lane_base + g * 16, v);
+      tc::tmem_ld_wait();
+      if (j < H) {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          const int k = tk * NB + g * 16 + i;
+          if (k < H) out[(size_t)j * H + k] += v[i];
+        }
+      }
+    }
+  }
+  tc::tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tc::tmem_dealloc(tmem, NB);
+}
+
+// db slot (block 0, row 0 of the [kBlocks][8][H] partials) += sum over point blocks, in index order
+__global__ void colsum_finish_kernel(const float* __restrict__ colsum, int nblk, int H, float* __restrict__ db_slot) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= H) return;
+  float s = 0.f;
+  for (int nb = 0; nb < nblk; ++nb) s += colsum[(size_t)nb * H + j];
+  db_slot[j] += s;
+}
+
+int rows_b(int H) { return H > 128 ? 256 : 128; }
+
+}  // namespace
+
+// floats of scratch for the two re-tiled operands of one layer
+int64_t tc_dw2_scratch_floats(int H, int C, int Mc) {
+  const int64_t nblk = (Mc + kKB - 1) / kKB;
+  const int R = rows_b(H);
+  return (int64_t)C * nblk * ((H + 127) / 128) * (kKB * 128) + (int64_t)C * nblk * ((H + R - 1) / R) * (kKB * R) + nblk * H;
+}
+
+int tc_launch_dw2(const float* Zb, const float* Hb, int H, int C, int m, int Mc, float* part, int n_splits, float* scratch,
+                  float* db_slot, cudaStream_t st) {
+  const int nblk = (m + kKB - 1) / kKB, R = rows_b(H);
+  const int UBA = (H + 127) / 128, UBB = (H + R - 1) / R;
+  float* tz = scratch;
+  const size_t nblk_alloc = (size_t)(Mc + kKB - 1) / kKB;
+  float* th = scratch + (size_t)C * nblk_alloc * UBA * (kKB * 128);
+  float* colsum = th + (size_t)C * nblk_alloc * UBB * (kKB * R);
+  retile_kernel<128><<<dim3(nblk, UBA, C), 256, 0, st>>>(Zb, tz, H, m, Mc, nblk, UBA, colsum);
+  colsum_finish_kernel<<<(H + 127) / 128, 128, 0, st>>>(colsum, nblk, H, db_slot);
+  if (R == 256)
+    retile_kernel<256><<<dim3(nblk, UBB, C), 256, 0, st>>>(Hb, th, H, m, Mc, nblk, UBB, nullptr);
+  else
+    retile_kernel<128><<<dim3(nblk, UBB, C), 256, 0, st>>>(Hb, th, H, m, Mc, nblk, UBB, nullptr);
+  const int tiles = UBA * UBB, kblocks = C * nblk;
+  int splits = kBlocks / tiles;
+  if (splits < 1) splits = 1;
+  if (splits > n_splits) splits = n_splits;
+  if (splits > kblocks) splits = kblocks;
+  const size_t smem = (size_t)kStages * (kKB * 128 + kKB * R) * sizeof(float);
+  cudaError_t e;
+  if (R == 256) {
+    static bool set = false;
+    if (!set) {
+      e = cudaFuncSetAttribute((const void*)tc_dw2_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      if (e != cudaSuccess) return (int)e;
+      set = true;
+    }
+    tc_dw2_kernel<256><<<dim3(tiles, splits), 128, smem, st>>>(tz, th, H, kblocks, UBA, UBB, UBB, part);
+  } else {
+    static bool set = false;
+    if (!set) {
+      e = cudaFuncSetAttribute((const void*)tc_dw2_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      if (e != cudaSuccess) return (int)e;
+      set = true;
+    }
+    tc_dw2_kernel<128><<<dim3(tiles, splits), 128, smem, st>>>(tz, th, H, kblocks, UBA, UBB, UBB, part);
+  }
+  count_launch(4);
+  return (int)cudaGetLastError();
+}
+
+}  // namespace pinn

@@ -8,7 +8,7 @@
 //
 //   tc_rows  EPI 0:  Z_l[c][n][j]  = sum_k W_l[j][k] H_{l-1}[c][n][k] + b ;  H_l = act(Z_l)
 //            EPI 1:  zbar_{l-1}[c][n][k] = act'(Z_{l-1}; sum_j W_l^T[k][j] zbar_l[c][n][j])     (in place)
-//   tc_dw         :  dW_l[j][k] (+)= sum_{(c,n)} zbar_l[(c,n)][j] * H_{l-1}[(c,n)][k]   (per-split partial slots)
+//   (the weight-gradient GEMM dW_l = zbar_l^T H_{l-1} lives in wide_dw.cu)
 //
 // Operands are staged by the CTA's threads into the no-swizzle K-major canonical layout
 // (core matrix = 8 rows x 16 bytes), rounded to TF32 with cvt.rna; K is consumed in
@@ -189,128 +189,6 @@ __global__ void __launch_bounds__(256) tc_rows_kernel(WNet net, const float* __r
   if (warp == 0) tc::tmem_dealloc(tmem, 256);
 }
 
-// dW partial: D[j][k] = sum over this split's rows r=(c,n) of zbar[r][j] * h[r][k].
-// grid (tiles_j * tiles_k, n_splits); NB = 16-rounded min(H, 256) columns k.
-__global__ void __launch_bounds__(256) tc_dw_kernel(const float* __restrict__ Zb, const float* __restrict__ Hb, int H, int C,
-                                                    int m, int Mc, float* __restrict__ part, int tiles_k, int NB) {
-  extern __shared__ __align__(128) float sm[];
-  __shared__ uint64_t bar[1];
-  __shared__ uint32_t tmem_slot;
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int j0 = (blockIdx.x / tiles_k) * 128, k0 = (blockIdx.x % tiles_k) * 256;
-  const int split = blockIdx.y, n_splits = gridDim.y;
-  const size_t plane = (size_t)Mc * H;
-  const int rows = C * m;
-  int per = (rows + n_splits - 1) / n_splits;
-  per = (per + kKT - 1) / kKT * kKT;
-  const int r_begin = split * per, r_end = (r_begin + per < rows) ? r_begin + per : rows;
-  if (tid == 0) {
-    tc::mbar_init(&bar[0], 1);
-    tc::fence_mbar_init();
-  }
-  if (warp == 0) tc::tmem_alloc(&tmem_slot, 256);
-  tc::tc_fence_before();
-  __syncthreads();
-  tc::tc_fence_after();
-  const uint32_t tmem = tmem_slot;
-  const uint32_t idesc = tc::idesc_tf32(NB, 0, 0);
-  const int nch = (r_end > r_begin) ? (r_end - r_begin + kKT - 1) / kKT : 0;
-  float* sA = sm;
-  float* sB = sA + (kKT / 4) * 129 * 4;
-  const int nqb = NB / 4;
-  bool ok = true;
-  for (int ch = 0; ch < nch; ++ch) {
-    const int r0 = r_begin + ch * kKT;
-    // transposing loads: a thread reads 4 consecutive rows r (= K) x 4 consecutive columns and
-    // writes 4 core-matrix rows (column fixed, 4 consecutive K) as STS.128.  A: 16 row-groups x 32
-    // column-quads = 512 items; B: 16 x NB/4 items.
-    constexpr int kItA = 2;
-    float4 ta[kItA][4], tb[4][4];
-    int nb_items = (kKT / 4) * nqb;
-#pragma unroll
-    for (int u = 0; u < kItA; ++u) {
-      const int i = tid + u * 256, rg = i >> 5, jq = i & 31;
-#pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        const int r = r0 + rg * 4 + e;
-        ta[u][e] = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (r < r_end && j0 + jq * 4 < H) {
-          const int c = r / m, n = r - c * m;
-          ta[u][e] = *reinterpret_cast<const float4*>(Zb + c * plane + (size_t)n * H + j0 + jq * 4);
-        }
-      }
-    }
-#pragma unroll
-    for (int u = 0; u < 4; ++u) {
-      const int i = tid + u * 256;
-      const int rg = i / nqb, kq = i - rg * nqb;
-#pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        const int r = r0 + rg * 4 + e;
-        tb[u][e] = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (i < nb_items && r < r_end && k0 + kq * 4 < H) {
-          const int c = r / m, n = r - c * m;
-          tb[u][e] = *reinterpret_cast<const float4*>(Hb + c * plane + (size_t)n * H + k0 + kq * 4);
-        }
-      }
-    }
-    if (ch >= 1) ok = tc::mbar_wait(&bar[0], (ch - 1) & 1) && ok;
-#pragma unroll
-    for (int u = 0; u < kItA; ++u) {
-      const int i = tid + u * 256, rg = i >> 5, jq = i & 31;
-      float* dst = sA + ((size_t)rg * 129 + jq * 4) * 4;
-      const float4* t = ta[u];
-      *reinterpret_cast<float4*>(dst + 0) = tc::to_tf32(make_float4(t[0].x, t[1].x, t[2].x, t[3].x));
-      *reinterpret_cast<float4*>(dst + 4) = tc::to_tf32(make_float4(t[0].y, t[1].y, t[2].y, t[3].y));
-      *reinterpret_cast<float4*>(dst + 8) = tc::to_tf32(make_float4(t[0].z, t[1].z, t[2].z, t[3].z));
-      *reinterpret_cast<float4*>(dst + 12) = tc::to_tf32(make_float4(t[0].w, t[1].w, t[2].w, t[3].w));
-    }
-#pragma unroll
-    for (int u = 0; u < 4; ++u) {
-      const int i = tid + u * 256;
-      if (i < nb_items) {
-        const int rg = i / nqb, kq = i - rg * nqb;
-        float* dst = sB + ((size_t)rg * (NB + 1) + kq * 4) * 4;
-        const float4* t = tb[u];
-        *reinterpret_cast<float4*>(dst + 0) = tc::to_tf32(make_float4(t[0].x, t[1].x, t[2].x, t[3].x));
-        *reinterpret_cast<float4*>(dst + 4) = tc::to_tf32(make_float4(t[0].y, t[1].y, t[2].y, t[3].y));
-        *reinterpret_cast<float4*>(dst + 8) = tc::to_tf32(make_float4(t[0].z, t[1].z, t[2].z, t[3].z));
-        *reinterpret_cast<float4*>(dst + 12) = tc::to_tf32(make_float4(t[0].w, t[1].w, t[2].w, t[3].w));
-      }
-    }
-    tc::fence_async_smem();
-    __syncthreads();
-    if (tid == 0) {
-      tc::tc_fence_after();
-      issue_chunk(tmem, tc::smem_u32(sA), tc::smem_u32(sB), NB, idesc, ch == 0);
-      tc::mma_commit(&bar[0]);
-    }
-  }
-  if (nch > 0) {
-    ok = tc::mbar_wait(&bar[0], (nch - 1) & 1) && ok;
-    if (!ok) __trap();
-    tc::tc_fence_after();
-    const int j = j0 + (warp & 3) * 32 + lane;
-    const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
-    float* out = part + (size_t)split * H * H;
-    for (int g = warp >> 2; g < NB / 16; g += 2) {
-      float v[16];
-      tc::tmem_ld16(tmem + lane_base + g * 16, v);
-      tc::tmem_ld_wait();
-      if (j < H) {
-#pragma unroll
-        for (int i = 0; i < 16; ++i) {
-          const int k = k0 + g * 16 + i;
-          if (k < H) out[(size_t)j * H + k] += v[i];
-        }
-      }
-    }
-  }
-  tc::tc_fence_before();
-  __syncthreads();
-  if (warp == 0) tc::tmem_dealloc(tmem, 256);
-}
-
 __global__ void transpose_kernel(const float* __restrict__ W, float* __restrict__ WT, int H) {
   __shared__ float t[32][33];
   const int x = blockIdx.x * 32 + threadIdx.x, y0 = blockIdx.y * 32;
@@ -361,23 +239,6 @@ INST(PINN_ACT_TANH)
 INST(PINN_ACT_SILU)
 INST(PINN_ACT_SIN)
 #undef INST
-
-int tc_launch_dw(const float* Zb, const float* Hb, int H, int C, int m, int Mc, float* part, int n_splits, cudaStream_t st) {
-  const int tiles_j = (H + 127) / 128, tiles_k = (H + 255) / 256;
-  int NB = H - 0 < 256 ? ((H + 15) / 16) * 16 : 256;
-  if (tiles_k > 1) NB = 256;
-  const size_t smem = (size_t)(kKT / 4) * (129 + NB + 1) * 4 * sizeof(float);
-  static size_t attr_smem = 0;
-  if (smem > attr_smem) {
-    cudaError_t e = cudaFuncSetAttribute((const void*)tc_dw_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return (int)e;
-    attr_smem = smem;
-  }
-  dim3 grid(tiles_j * tiles_k, n_splits);
-  tc_dw_kernel<<<grid, 256, smem, st>>>(Zb, Hb, H, C, m, Mc, part, tiles_k, NB);
-  count_launch(1);
-  return (int)cudaGetLastError();
-}
 
 int tc_dw_splits(int H) {
   const int tiles = ((H + 127) / 128) * ((H + 255) / 256);
