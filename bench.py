@@ -381,6 +381,17 @@ def scaled_sizes(cfg, factor):
 CPU_SAMPLE = {"burgers": 1 / 8, "poisson": 1 / 8, "ldc": 1 / 32, "allen_cahn": 1 / 32, "ns_xl": 1 / 32}
 
 
+def use_all_host_threads():
+    """torchrun exports OMP_NUM_THREADS=1 to its workers; the CPU arm is entitled to every host
+    thread this process may run on."""
+    try:
+        n = len(os.sched_getaffinity(0))
+    except AttributeError:
+        n = os.cpu_count() or 1
+    torch.set_num_threads(max(n, 1))
+    return torch.get_num_threads()
+
+
 # --------------------------------------------------------------------------- #
 def run_reference(args):
     rank = int(os.environ.get("RANK", 0))
@@ -392,7 +403,7 @@ def run_reference(args):
         device = f"cuda:{int(os.environ.get('LOCAL_RANK', 0))}"
     factor = args.sample if args.sample else (CPU_SAMPLE[args.config] if device == "cpu" else 1 / 4)
     sizes = scaled_sizes(cfg, factor)
-    cores = torch.get_num_threads()
+    cores = use_all_host_threads()
     pps, dt = time_oracle(cfg, sizes, args.steps, args.warmup, device)
     sample = (f"{'+'.join(str(sizes[d[1]]) for d in cfg['domains'])} points/step ({factor:g} of the GPU workload), "
               f"{args.steps} steps, torch autograd FP32 on {device}")
@@ -554,6 +565,7 @@ def run_ours(args):
         cpu = None
         if world == 1 and not args.no_cpu_baseline:
             csz = scaled_sizes(cfg, CPU_SAMPLE[args.config])
+            use_all_host_threads()
             pps, dt = time_oracle(cfg, csz, 8, 2, "cpu")
             cpu = {"value": pps, "unit": "points/s", "cores": torch.get_num_threads(), "kind": "port",
                    "sample": f"{'+'.join(str(csz[d[1]]) for d in cfg['domains'])} points/step x 8 steps of the same "
