@@ -463,7 +463,7 @@ def run_ours(args):
     cfg = workload_configs()[args.config]
     sizes = scaled_sizes(cfg, args.sample) if args.sample else None
     trainer = Trainer(cfg, device, world=world, sizes=sizes, precision=args.precision)
-    wide_tc = args.precision.startswith("tf32") and trainer.pack.width > 32
+    wide_tc = args.precision != "fp32" and trainer.pack.width > 32
     rng = np.random.default_rng(1000 + rank)
     pts_per_step = trainer.points_per_step
     n_timed = trainer.sizes[cfg["domains"][cfg["timed"]][1]]
@@ -573,7 +573,7 @@ def run_ours(args):
         line = {
             "metric": METRIC, "value": value, "unit": "points/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "tf32" if wide_tc else "f32", "data": "synthetic",
+            "vs_baseline": None, "dtype": ("f32 (3xTF32 split on tensor cores)" if args.precision == "fp32x3" else "tf32") if wide_tc else "f32", "data": "synthetic",
             "config": {"workload": f"{cfg['title']}: {' + '.join(str(trainer.sizes[d[1]]) for d in cfg['domains'])} "
                                    f"points per step per GPU ({', '.join(d[0] for d in cfg['domains'])})",
                        "net": f"{cfg['net_desc']}, Adam 1e-3 + ExponentialLR",
@@ -607,7 +607,7 @@ def main():
     ap.add_argument("--baseline-device", default="cpu", choices=["cpu", "cuda"],
                     help="--impl reference: where the reference algorithm (torch autograd) runs")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--precision", default="fp32", choices=["fp32", "tf32", "tf32_streamed"],
+    ap.add_argument("--precision", default="fp32", choices=["fp32", "tf32", "tf32_streamed", "fp32x3"],
                     help="layer GEMMs of wide nets: FP32 FMA (parity) or tcgen05 TF32; narrow nets are always FP32")
     args = ap.parse_args()
     if args.impl == "reference":

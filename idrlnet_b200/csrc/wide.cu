@@ -572,7 +572,8 @@ bool make_net(const pinn_mlp* m, const pinn_jets* j, WNet* n) {
   memset(n, 0, sizeof(*n));
   n->n_in = m->n_in; n->n_out = m->n_out; n->L = m->n_hidden; n->H = m->width; n->act = m->act;
   n->NF = j->n_first; n->NS = j->n_second; n->C = 1 + n->NF + n->NS;
-  n->precision = (m->precision == PINN_PREC_TF32 || m->precision == PINN_PREC_TF32_STREAMED) ? 1 : 0;
+  n->precision = (m->precision == PINN_PREC_TF32 || m->precision == PINN_PREC_TF32_STREAMED) ? 1
+                 : (m->precision == PINN_PREC_FP32X3) ? 2 : 0;  // 0: FP32 SIMT, 1: TF32, 2: 3xTF32 (tensor cores, FP32-grade)
   for (int i = 0; i < 4; ++i) n->first_in[i] = j->first_in[i];
   for (int l = 0; l <= m->n_hidden; ++l) { n->W[l] = m->W[l]; n->b[l] = m->b[l]; }
   return true;
@@ -580,7 +581,7 @@ bool make_net(const pinn_mlp* m, const pinn_jets* j, WNet* n) {
 
 WideLayout make_layout(const WNet& n, int n_dom) {
   WideLayout wl;
-  const int64_t per_point = (2ll * n.L + (n.precision ? 3 : 0)) * n.C * n.H * 4;  // planes (+ re-tiled dW operands)
+  const int64_t per_point = (2ll * n.L + (n.precision == 2 ? 5 : n.precision ? 3 : 0)) * n.C * n.H * 4;  // planes (+ re-tiled dW operands)
   int64_t mc = kChunkBudget / per_point;
   mc = mc / kBM * kBM;
   if (mc < 256) mc = 256;
@@ -609,7 +610,7 @@ WideLayout make_layout(const WNet& n, int n_dom) {
   wl.Z = off; off += planes;
   wl.Hb = off; off += planes;
   wl.ybar = off; off += (int64_t)mc * kMaxC * 4;
-  wl.tdw = off; off += n.precision ? (tc_dw2_scratch_floats(n.H, n.C, (int)mc) + 3) / 4 * 4 : 0;
+  wl.tdw = off; off += n.precision ? (tc_dw2_scratch_floats(n.H, n.C, (int)mc, n.precision == 2) + 3) / 4 * 4 : 0;
   wl.total = (off + 3) / 4 * 4;
   return wl;
 }
@@ -704,7 +705,7 @@ int run_chunks(const WNet& n, const WideLayout& wl, float* ws, int mode, const p
         float* dwp = ws + wl.dw + (size_t)(l - 2) * wl.n_splits * H * H;
         float* dbp = ws + wl.db + (size_t)(l - 2) * kBlocks * 8 * H;
         if (n.precision) {  // db_l rides along with the re-tiling of zbar_l
-          int rc = tc_launch_dw2(zb, hprev, H, C, m, wl.Mc, dwp, wl.n_splits, ws + wl.tdw, dbp, st);
+          int rc = tc_launch_dw2(zb, hprev, H, C, m, wl.Mc, dwp, wl.n_splits, ws + wl.tdw, dbp, n.precision == 2, st);
           if (rc) return rc;
         } else {
           dim3 grid(wl.tiles * wl.tiles, wl.fp32_splits);
@@ -759,7 +760,7 @@ int run_mode(const pinn_mlp* m, const pinn_jets* j, int mode, const pinn_domain*
       rc = tc_transpose(n.W[l - 1], w + wl.wt + (size_t)(l - 2) * n.H * n.H, n.H, st);
       if (rc) return rc;
     }
-  if (n.precision && mode == W_MODE_FUSED && prep && n.H <= 128 && n.L >= 2) {
+  if (n.precision == 1 && mode == W_MODE_FUSED && prep && n.H <= 128 && n.L >= 2) {
     rc = fused_wide_prep(n, w + wl.wprep, st);
     if (rc) return rc;
   }

@@ -26,7 +26,8 @@ constexpr int kKB = 32;  // points per K block (4 MMAs of K = 8)
 // src: planes [c][n][j] (plane stride Mc * H), valid n < m, j < H.  grid (nblk, UB, C), 256 threads.
 // colsum (optional, R = 128 only): colsum[nb][j] = sum over the block's points of the UNROUNDED value
 // channel (c == 0) -- the bias gradient db_l = sum_n zbar_l[0][n][:] rides along with the re-tiling.
-template <int R>
+// X3: the tile is followed by its residual tile lo = tf32(x - tf32(x)) (3xTF32, see wide_tc.cu).
+template <int R, bool X3>
 __global__ void __launch_bounds__(256) retile_kernel(const float* __restrict__ src, float* __restrict__ dst, int H, int m, int Mc,
                                                      int nblk, int UB, float* __restrict__ colsum) {
   __shared__ float t[kKB][R + 1];
@@ -39,7 +40,7 @@ __global__ void __launch_bounds__(256) retile_kernel(const float* __restrict__ s
     const int n = nb * kKB + p, j = ub * R + jj;
     const float v = (n < m && j < H) ? plane[(size_t)n * H + j] : 0.f;
     acc += v;  // R divides 256: a thread always sees the same unit jj
-    t[p][jj] = tc::to_tf32(v);
+    t[p][jj] = v;
   }
   if (R == 128 && colsum != nullptr && c == 0) {
     red[threadIdx.x] = acc;
@@ -48,28 +49,34 @@ __global__ void __launch_bounds__(256) retile_kernel(const float* __restrict__ s
       colsum[(size_t)nb * H + ub * 128 + threadIdx.x] = red[threadIdx.x] + red[threadIdx.x + 128];
   }
   __syncthreads();
-  float* tile = dst + ((size_t)(c * nblk + nb) * UB + ub) * (kKB * R);
+  float* tile = dst + ((size_t)(c * nblk + nb) * UB + ub) * ((X3 ? 2 : 1) * kKB * R);
   for (int i = threadIdx.x; i < (kKB / 4) * R; i += 256) {
     const int kq = i / R, row = i - kq * R;
-    *reinterpret_cast<float4*>(tile + (size_t)i * 4) = make_float4(t[kq * 4][row], t[kq * 4 + 1][row], t[kq * 4 + 2][row], t[kq * 4 + 3][row]);
+    const float4 x = make_float4(t[kq * 4][row], t[kq * 4 + 1][row], t[kq * 4 + 2][row], t[kq * 4 + 3][row]);
+    const float4 hi = tc::to_tf32(x);
+    *reinterpret_cast<float4*>(tile + (size_t)i * 4) = hi;
+    if (X3)
+      *reinterpret_cast<float4*>(tile + kKB * R + (size_t)i * 4) =
+          tc::to_tf32(make_float4(x.x - hi.x, x.y - hi.y, x.z - hi.z, x.w - hi.w));
   }
 }
 
 // grid (tiles_j * tiles_k, splits); 128 threads.  tz: A tiles (R = 128), th: B tiles (R = NB).
-template <int NB>
+template <int NB, bool X3>
 __global__ void __launch_bounds__(128, 1) tc_dw2_kernel(const float* __restrict__ tz, const float* __restrict__ th, int H, int kblocks,
                                                         int UBA, int UBB, int tiles_k, float* __restrict__ part) {
   extern __shared__ __align__(128) float sm[];
-  __shared__ uint64_t full[kStages], empty[kStages], done;
+  __shared__ uint64_t full[kStages], empty[kStages], done;  // the first kS of each are used
   __shared__ uint32_t tmem_slot;
-  constexpr int kAFloats = kKB * 128, kBFloats = kKB * NB, kStageFloats = kAFloats + kBFloats;
+  constexpr int kS = X3 ? kStages / 2 : kStages;  // hi + lo tiles double a stage
+  constexpr int kAFloats = (X3 ? 2 : 1) * kKB * 128, kBFloats = (X3 ? 2 : 1) * kKB * NB, kStageFloats = kAFloats + kBFloats;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int tj = blockIdx.x / tiles_k, tk = blockIdx.x % tiles_k;
   const int per = (kblocks + gridDim.y - 1) / gridDim.y;
   const int kb0 = blockIdx.y * per, kb1 = (kb0 + per < kblocks) ? kb0 + per : kblocks;
   const int nit = kb1 - kb0;
   if (tid == 0) {
-    for (int s = 0; s < kStages; ++s) {
+    for (int s = 0; s < kS; ++s) {
       tc::mbar_init(&full[s], 1);
       tc::mbar_init(&empty[s], 1);
     }
@@ -84,8 +91,8 @@ __global__ void __launch_bounds__(128, 1) tc_dw2_kernel(const float* __restrict_
   if (nit > 0) {
     if (warp == 0 && lane == 0) {  // producer: whole tiles by bulk copy
       for (int it = 0; it < nit; ++it) {
-        const int s = it % kStages;
-        if (it >= kStages && !tc::mbar_wait(&empty[s], ((it / kStages) - 1) & 1)) __trap();
+        const int s = it % kS;
+        if (it >= kS && !tc::mbar_wait(&empty[s], ((it / kS) - 1) & 1)) __trap();
         float* sA = sm + (size_t)s * kStageFloats;
         const size_t kb = (size_t)(kb0 + it);
         tc::mbar_expect_tx(&full[s], (uint32_t)(kStageFloats * sizeof(float)));
@@ -95,15 +102,23 @@ __global__ void __launch_bounds__(128, 1) tc_dw2_kernel(const float* __restrict_
     } else if (warp == 1 && lane == 0) {  // tensor-core issuer
       const uint32_t idesc = tc::idesc_tf32(NB, 0, 0);
       for (int it = 0; it < nit; ++it) {
-        const int s = it % kStages;
-        if (!tc::mbar_wait(&full[s], (it / kStages) & 1)) __trap();
+        const int s = it % kS;
+        if (!tc::mbar_wait(&full[s], (it / kS) & 1)) __trap();
         tc::tc_fence_after();
         const uint32_t a0 = tc::smem_u32(sm + (size_t)s * kStageFloats), b0 = a0 + kAFloats * sizeof(float);
 #pragma unroll
         for (int ks = 0; ks < kKB / 8; ++ks) {
           const uint64_t da = tc::smem_desc(a0 + ks * 2 * (128 * 16), 128 * 16, 128);
           const uint64_t db = tc::smem_desc(b0 + ks * 2 * (NB * 16), NB * 16, 128);
-          tc::mma_tf32(tmem, da, db, idesc, (it > 0 || ks > 0) ? 1u : 0u);
+          if (X3) {  // lo*hi + hi*lo + hi*hi
+            const uint64_t dal = tc::smem_desc(a0 + kKB * 128 * 4 + ks * 2 * (128 * 16), 128 * 16, 128);
+            const uint64_t dbl = tc::smem_desc(b0 + kKB * NB * 4 + ks * 2 * (NB * 16), NB * 16, 128);
+            tc::mma_tf32(tmem, dal, db, idesc, (it > 0 || ks > 0) ? 1u : 0u);
+            tc::mma_tf32(tmem, da, dbl, idesc, 1u);
+            tc::mma_tf32(tmem, da, db, idesc, 1u);
+          } else {
+            tc::mma_tf32(tmem, da, db, idesc, (it > 0 || ks > 0) ? 1u : 0u);
+          }
         }
         tc::mma_commit(&empty[s]);  // the stage is free once these MMAs have read it
       }
@@ -144,55 +159,52 @@ __global__ void colsum_finish_kernel(const float* __restrict__ colsum, int nblk,
 
 int rows_b(int H) { return H > 128 ? 256 : 128; }
 
-}  // namespace
-
-// floats of scratch for the two re-tiled operands of one layer
-int64_t tc_dw2_scratch_floats(int H, int C, int Mc) {
-  const int64_t nblk = (Mc + kKB - 1) / kKB;
-  const int R = rows_b(H);
-  return (int64_t)C * nblk * ((H + 127) / 128) * (kKB * 128) + (int64_t)C * nblk * ((H + R - 1) / R) * (kKB * R) + nblk * H;
-}
-
-int tc_launch_dw2(const float* Zb, const float* Hb, int H, int C, int m, int Mc, float* part, int n_splits, float* scratch,
-                  float* db_slot, cudaStream_t st) {
-  const int nblk = (m + kKB - 1) / kKB, R = rows_b(H);
+template <int R, bool X3>
+int launch_dw2(const float* Zb, const float* Hb, int H, int C, int m, int Mc, float* part, int n_splits, float* scratch,
+               float* db_slot, cudaStream_t st) {
+  constexpr int F = X3 ? 2 : 1;
+  const int nblk = (m + kKB - 1) / kKB;
   const int UBA = (H + 127) / 128, UBB = (H + R - 1) / R;
-  float* tz = scratch;
   const size_t nblk_alloc = (size_t)(Mc + kKB - 1) / kKB;
-  float* th = scratch + (size_t)C * nblk_alloc * UBA * (kKB * 128);
-  float* colsum = th + (size_t)C * nblk_alloc * UBB * (kKB * R);
-  retile_kernel<128><<<dim3(nblk, UBA, C), 256, 0, st>>>(Zb, tz, H, m, Mc, nblk, UBA, colsum);
+  float* tz = scratch;
+  float* th = tz + (size_t)F * C * nblk_alloc * UBA * (kKB * 128);
+  float* colsum = th + (size_t)F * C * nblk_alloc * UBB * (kKB * R);
+  retile_kernel<128, X3><<<dim3(nblk, UBA, C), 256, 0, st>>>(Zb, tz, H, m, Mc, nblk, UBA, colsum);
   colsum_finish_kernel<<<(H + 127) / 128, 128, 0, st>>>(colsum, nblk, H, db_slot);
-  if (R == 256)
-    retile_kernel<256><<<dim3(nblk, UBB, C), 256, 0, st>>>(Hb, th, H, m, Mc, nblk, UBB, nullptr);
-  else
-    retile_kernel<128><<<dim3(nblk, UBB, C), 256, 0, st>>>(Hb, th, H, m, Mc, nblk, UBB, nullptr);
+  retile_kernel<R, X3><<<dim3(nblk, UBB, C), 256, 0, st>>>(Hb, th, H, m, Mc, nblk, UBB, nullptr);
   const int tiles = UBA * UBB, kblocks = C * nblk;
   int splits = kBlocks / tiles;
   if (splits < 1) splits = 1;
   if (splits > n_splits) splits = n_splits;
   if (splits > kblocks) splits = kblocks;
-  const size_t smem = (size_t)kStages * (kKB * 128 + kKB * R) * sizeof(float);
-  cudaError_t e;
-  if (R == 256) {
-    static bool set = false;
-    if (!set) {
-      e = cudaFuncSetAttribute((const void*)tc_dw2_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-      if (e != cudaSuccess) return (int)e;
-      set = true;
-    }
-    tc_dw2_kernel<256><<<dim3(tiles, splits), 128, smem, st>>>(tz, th, H, kblocks, UBA, UBB, UBB, part);
-  } else {
-    static bool set = false;
-    if (!set) {
-      e = cudaFuncSetAttribute((const void*)tc_dw2_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-      if (e != cudaSuccess) return (int)e;
-      set = true;
-    }
-    tc_dw2_kernel<128><<<dim3(tiles, splits), 128, smem, st>>>(tz, th, H, kblocks, UBA, UBB, UBB, part);
+  const size_t smem = (size_t)kStages * (kKB * 128 + kKB * R) * sizeof(float);  // X3: half the stages, twice the size
+  static bool set = false;
+  if (!set) {
+    cudaError_t e = cudaFuncSetAttribute((const void*)tc_dw2_kernel<R, X3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return (int)e;
+    set = true;
   }
+  tc_dw2_kernel<R, X3><<<dim3(tiles, splits), 128, smem, st>>>(tz, th, H, kblocks, UBA, UBB, UBB, part);
   count_launch(4);
   return (int)cudaGetLastError();
+}
+
+}  // namespace
+
+// floats of scratch for the two re-tiled operands of one layer (+ the per-block column sums)
+int64_t tc_dw2_scratch_floats(int H, int C, int Mc, bool x3) {
+  const int64_t nblk = (Mc + kKB - 1) / kKB;
+  const int R = rows_b(H), f = x3 ? 2 : 1;
+  return f * ((int64_t)C * nblk * ((H + 127) / 128) * (kKB * 128) + (int64_t)C * nblk * ((H + R - 1) / R) * (kKB * R)) + nblk * H;
+}
+
+int tc_launch_dw2(const float* Zb, const float* Hb, int H, int C, int m, int Mc, float* part, int n_splits, float* scratch,
+                  float* db_slot, bool x3, cudaStream_t st) {
+  if (rows_b(H) == 256)
+    return x3 ? launch_dw2<256, true>(Zb, Hb, H, C, m, Mc, part, n_splits, scratch, db_slot, st)
+              : launch_dw2<256, false>(Zb, Hb, H, C, m, Mc, part, n_splits, scratch, db_slot, st);
+  return x3 ? launch_dw2<128, true>(Zb, Hb, H, C, m, Mc, part, n_splits, scratch, db_slot, st)
+            : launch_dw2<128, false>(Zb, Hb, H, C, m, Mc, part, n_splits, scratch, db_slot, st);
 }
 
 }  // namespace pinn

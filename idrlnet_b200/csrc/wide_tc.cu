@@ -24,7 +24,7 @@
 namespace pinn {
 namespace {
 
-constexpr int kKT = 64;  // K elements per smem stage (8 MMAs of K = 8)
+__device__ __forceinline__ float4 sub4(float4 a, float4 b) { return make_float4(a.x - b.x, a.y - b.y, a.z - b.z, a.w - b.w); }
 
 template <int C>
 struct TileCfg {
@@ -33,24 +33,38 @@ struct TileCfg {
   static_assert(N % 16 == 0 && N <= 256 && P % 16 == 0, "tile");
 };
 
-// stage layout (floats): A[kKT/4][128 + 1][4] then B[kKT/4][NB + 1][4]: one 16-byte pad row per
-// K-quad slab (LBO = (rows + 1) * 16 bytes) so that the staging stores of the 16 K-quads of a row
-// fall into different banks.
+// stage layout (floats): A[KT/4][128 + 1][4] then B[KT/4][NB + 1][4]: one 16-byte pad row per
+// K-quad slab (LBO = (rows + 1) * 16 bytes) so that the staging stores of the K-quads of a row
+// fall into different banks.  X3 (3xTF32, FP32-grade products): every operand is split into
+// hi = tf32(x) and lo = tf32(x - hi), stored as two such blocks (hi first), and a K step issues
+// lo*hi + hi*lo + hi*hi (the dropped lo*lo term and the split residuals are ~2^-22 relative).
+template <int KT, bool X3>
 __device__ __forceinline__ void issue_chunk(uint32_t tmem, uint32_t sA, uint32_t sB, int nb, uint32_t idesc, bool first) {
+  const uint32_t a_lo = sA + (KT / 4) * 129 * 16, b_lo = sB + (KT / 4) * (nb + 1) * 16;
 #pragma unroll
-  for (int ks = 0; ks < kKT / 8; ++ks) {
-    const uint64_t da = tc::smem_desc(sA + ks * 2 * (129 * 16), 129 * 16, 128);
-    const uint64_t db = tc::smem_desc(sB + ks * 2 * ((nb + 1) * 16), (nb + 1) * 16, 128);
-    tc::mma_tf32(tmem, da, db, idesc, (first && ks == 0) ? 0u : 1u);
+  for (int ks = 0; ks < KT / 8; ++ks) {
+    const uint32_t oa = ks * 2 * (129 * 16), ob = ks * 2 * ((nb + 1) * 16);
+    const uint64_t da = tc::smem_desc(sA + oa, 129 * 16, 128);
+    const uint64_t db = tc::smem_desc(sB + ob, (nb + 1) * 16, 128);
+    if (X3) {
+      const uint64_t dal = tc::smem_desc(a_lo + oa, 129 * 16, 128);
+      const uint64_t dbl = tc::smem_desc(b_lo + ob, (nb + 1) * 16, 128);
+      tc::mma_tf32(tmem, dal, db, idesc, (first && ks == 0) ? 0u : 1u);
+      tc::mma_tf32(tmem, da, dbl, idesc, 1u);
+      tc::mma_tf32(tmem, da, db, idesc, 1u);
+    } else {
+      tc::mma_tf32(tmem, da, db, idesc, (first && ks == 0) ? 0u : 1u);
+    }
   }
 }
 
-template <int C, int ACT, int EPI>
+template <int C, int ACT, int EPI, bool X3>
 __global__ void __launch_bounds__(256) tc_rows_kernel(WNet net, const float* __restrict__ Bsrc, const float* __restrict__ Aw,
                                                       const float* __restrict__ bias, float* __restrict__ Zio,
                                                       float* __restrict__ Hout, int m, int Mc, int a_rows) {
   using T = TileCfg<C>;
   constexpr int P = T::P, N = T::N;
+  constexpr int kKT = X3 ? 32 : 64;  // K elements per smem stage
   const int H = net.H;
   extern __shared__ __align__(128) float sm[];
   __shared__ uint64_t bar[1];
@@ -71,7 +85,9 @@ __global__ void __launch_bounds__(256) tc_rows_kernel(WNet net, const float* __r
   const int nch = (H + kKT - 1) / kKT;
   bool ok = true;
   float* sA = sm;
-  float* sB = sA + (kKT / 4) * 129 * 4;
+  float* sB = sA + (X3 ? 2 : 1) * (kKT / 4) * 129 * 4;
+  constexpr int kLoA = (kKT / 4) * 129 * 4, kLoB = (kKT / 4) * (N + 1) * 4;  // offsets of the lo blocks (X3)
+  constexpr int kQ = kKT / 4;                                                // K quads per stage
   for (int ch = 0; ch < nch; ++ch) {
     const int k0 = ch * kKT;
     // global -> registers first (many loads in flight), then wait for the previous chunk's MMAs
@@ -80,13 +96,13 @@ __global__ void __launch_bounds__(256) tc_rows_kernel(WNet net, const float* __r
     float4 ra[kItA], rb[kItB];
 #pragma unroll
     for (int u = 0; u < kItA; ++u) {
-      const int i = tid + u * 256, row = i >> 4, kq = i & 15;
+      const int i = tid + u * 256, row = i / kQ, kq = i % kQ;
       ra[u] = make_float4(0.f, 0.f, 0.f, 0.f);
       if (j0 + row < a_rows && k0 + kq * 4 < H) ra[u] = *reinterpret_cast<const float4*>(Aw + (size_t)(j0 + row) * H + k0 + kq * 4);
     }
 #pragma unroll
     for (int u = 0; u < kItB; ++u) {
-      const int i = tid + u * 256, q = i >> 4, kq = i & 15;
+      const int i = tid + u * 256, q = i / kQ, kq = i % kQ;
       const int c = q / P, p = q % P;
       rb[u] = make_float4(0.f, 0.f, 0.f, 0.f);
       if (q < N && n0 + p < m && k0 + kq * 4 < H)
@@ -95,19 +111,25 @@ __global__ void __launch_bounds__(256) tc_rows_kernel(WNet net, const float* __r
     if (ch >= 1) ok = tc::mbar_wait(&bar[0], (ch - 1) & 1) && ok;
 #pragma unroll
     for (int u = 0; u < kItA; ++u) {
-      const int i = tid + u * 256, row = i >> 4, kq = i & 15;
-      *reinterpret_cast<float4*>(sA + ((size_t)kq * 129 + row) * 4) = tc::to_tf32(ra[u]);
+      const int i = tid + u * 256, row = i / kQ, kq = i % kQ;
+      const float4 hi = tc::to_tf32(ra[u]);
+      *reinterpret_cast<float4*>(sA + ((size_t)kq * 129 + row) * 4) = hi;
+      if (X3) *reinterpret_cast<float4*>(sA + kLoA + ((size_t)kq * 129 + row) * 4) = tc::to_tf32(sub4(ra[u], hi));
     }
 #pragma unroll
     for (int u = 0; u < kItB; ++u) {
-      const int i = tid + u * 256, q = i >> 4, kq = i & 15;
-      if (q < N) *reinterpret_cast<float4*>(sB + ((size_t)kq * (N + 1) + q) * 4) = tc::to_tf32(rb[u]);
+      const int i = tid + u * 256, q = i / kQ, kq = i % kQ;
+      if (q < N) {
+        const float4 hi = tc::to_tf32(rb[u]);
+        *reinterpret_cast<float4*>(sB + ((size_t)kq * (N + 1) + q) * 4) = hi;
+        if (X3) *reinterpret_cast<float4*>(sB + kLoB + ((size_t)kq * (N + 1) + q) * 4) = tc::to_tf32(sub4(rb[u], hi));
+      }
     }
     tc::fence_async_smem();
     __syncthreads();
     if (tid == 0) {
       tc::tc_fence_after();
-      issue_chunk(tmem, tc::smem_u32(sA), tc::smem_u32(sB), N, idesc, ch == 0);
+      issue_chunk<kKT, X3>(tmem, tc::smem_u32(sA), tc::smem_u32(sB), N, idesc, ch == 0);
       tc::mma_commit(&bar[0]);
     }
   }
@@ -115,7 +137,7 @@ __global__ void __launch_bounds__(256) tc_rows_kernel(WNet net, const float* __r
   if (!ok) __trap();
   tc::tc_fence_after();
 
-  // epilogue: lane = hidden unit (or output, EPI 2); 16-point groups alternate between the two warp quads
+  // epilogue: lane = hidden unit; 16-point groups alternate between the two warp quads
   const int j = j0 + (warp & 3) * 32 + lane;
   const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
   const float bj = (EPI != 1 && j < a_rows) ? bias[j] : 0.f;
@@ -168,16 +190,11 @@ __global__ void __launch_bounds__(256) tc_rows_kernel(WNet net, const float* __r
 #pragma unroll
             for (int c = 0; c < C; ++c) a[c] = v[c][i];
             a[0] += bj;
-            if (EPI == 0) {
-              jet_fwd<ACT>(net.NF, net.NS, a, o);
+            jet_fwd<ACT>(net.NF, net.NS, a, o);
 #pragma unroll
-              for (int c = 0; c < C; ++c) {
-                Zio[c * plane + (size_t)n * H + j] = a[c];
-                Hout[c * plane + (size_t)n * H + j] = o[c];
-              }
-            } else {  // EPI 2: output-layer values y[n][c][o = j]
-#pragma unroll
-              for (int c = 0; c < C; ++c) Zio[((size_t)n * C + c) * 4 + j] = a[c];
+            for (int c = 0; c < C; ++c) {
+              Zio[c * plane + (size_t)n * H + j] = a[c];
+              Hout[c * plane + (size_t)n * H + j] = o[c];
             }
           }
         }
@@ -200,19 +217,20 @@ __global__ void transpose_kernel(const float* __restrict__ W, float* __restrict_
     if (xo < H && yo0 + r < H) WT[(size_t)(yo0 + r) * H + xo] = t[threadIdx.x][r];
 }
 
-template <int C, int ACT, int EPI>
+template <int C, int ACT, int EPI, bool X3>
 int launch_rows_c(const WNet& n, const float* Bsrc, const float* Aw, const float* bias, float* Zio, float* Hout, int m, int Mc,
                   int a_rows, cudaStream_t st) {
   using T = TileCfg<C>;
-  const size_t smem = (size_t)(kKT / 4) * (129 + T::N + 1) * 4 * sizeof(float);
+  constexpr int KT = X3 ? 32 : 64;
+  const size_t smem = (size_t)(X3 ? 2 : 1) * (KT / 4) * (129 + T::N + 1) * 4 * sizeof(float);
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute((const void*)tc_rows_kernel<C, ACT, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute((const void*)tc_rows_kernel<C, ACT, EPI, X3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return (int)e;
     attr_set = true;
   }
   dim3 grid((m + T::P - 1) / T::P, (a_rows + 127) / 128);
-  tc_rows_kernel<C, ACT, EPI><<<grid, 256, smem, st>>>(n, Bsrc, Aw, bias, Zio, Hout, m, Mc, a_rows);
+  tc_rows_kernel<C, ACT, EPI, X3><<<grid, 256, smem, st>>>(n, Bsrc, Aw, bias, Zio, Hout, m, Mc, a_rows);
   count_launch(1);
   return (int)cudaGetLastError();
 }
@@ -222,9 +240,12 @@ int launch_rows_c(const WNet& n, const float* Bsrc, const float* Aw, const float
 template <int ACT, int EPI>
 int tc_launch_rows(const WNet& n, const float* Bsrc, const float* Aw, const float* bias, float* Zio, float* Hout, int m, int Mc,
                    cudaStream_t st) {
-  const int a_rows = (EPI == 2) ? n.n_out : n.H;
+  const int a_rows = n.H;
   switch (n.C) {
-#define CASE(Cc) case Cc: return launch_rows_c<Cc, ACT, EPI>(n, Bsrc, Aw, bias, Zio, Hout, m, Mc, a_rows, st);
+#define CASE(Cc)                                                                                              \
+  case Cc:                                                                                                    \
+    return n.precision == 2 ? launch_rows_c<Cc, ACT, EPI, true>(n, Bsrc, Aw, bias, Zio, Hout, m, Mc, a_rows, st) \
+                            : launch_rows_c<Cc, ACT, EPI, false>(n, Bsrc, Aw, bias, Zio, Hout, m, Mc, a_rows, st);
     CASE(1) CASE(2) CASE(3) CASE(4) CASE(5) CASE(6) CASE(7)
 #undef CASE
   }
@@ -233,8 +254,7 @@ int tc_launch_rows(const WNet& n, const float* Bsrc, const float* Aw, const floa
 
 #define INST(A)                                                                                                              \
   template int tc_launch_rows<A, 0>(const WNet&, const float*, const float*, const float*, float*, float*, int, int, cudaStream_t); \
-  template int tc_launch_rows<A, 1>(const WNet&, const float*, const float*, const float*, float*, float*, int, int, cudaStream_t); \
-  template int tc_launch_rows<A, 2>(const WNet&, const float*, const float*, const float*, float*, float*, int, int, cudaStream_t);
+  template int tc_launch_rows<A, 1>(const WNet&, const float*, const float*, const float*, float*, float*, int, int, cudaStream_t);
 INST(PINN_ACT_TANH)
 INST(PINN_ACT_SILU)
 INST(PINN_ACT_SIN)

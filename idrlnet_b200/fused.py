@@ -26,8 +26,10 @@ from . import native as nv
 
 
 def default_precision() -> str:
-    """Arithmetic of the wide-net layer GEMMs: "fp32" (parity path, default) or "tf32"
-    (tcgen05 tensor cores).  Set IDRLNET_B200_PRECISION=tf32 or pass precision= explicitly."""
+    """Arithmetic of the wide-net layer GEMMs: "fp32" (FP32 FMA, the parity path and default),
+    "fp32x3" (tcgen05 tensor cores with 3xTF32 operand splitting: FP32-grade, 1.4-3.4x faster),
+    "tf32" (tensor cores, 10-bit multiplicands; on-chip fused kernel where it applies) or
+    "tf32_streamed".  Set IDRLNET_B200_PRECISION or pass precision= explicitly."""
     import os
     return os.environ.get("IDRLNET_B200_PRECISION", "fp32").lower()
 

@@ -55,7 +55,7 @@ class PinnDomain(C.Structure):
                 ("terms", PinnTerm * MAX_TERMS)]
 
 
-PRECISION = {"fp32": 0, "tf32": 1, "tf32_streamed": 2}
+PRECISION = {"fp32": 0, "tf32": 1, "tf32_streamed": 2, "fp32x3": 3}
 
 
 def make_mlp(n_in: int, n_out: int, n_hidden: int, width: int, act: str, w_ptrs: Sequence[int],

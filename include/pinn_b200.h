@@ -56,7 +56,12 @@ enum { PINN_LOSS_SQUARE = 0, PINN_LOSS_L1 = 1, PINN_LOSS_IDENTITY = 2 };
 enum {
   PINN_PREC_FP32 = 0,
   PINN_PREC_TF32 = 1,          /* on-chip fused kernel where it applies (H <= 128, 2..4 hidden layers), else streamed */
-  PINN_PREC_TF32_STREAMED = 2  /* always the layer-streamed tensor-core kernels (for comparison) */
+  PINN_PREC_TF32_STREAMED = 2, /* always the layer-streamed tensor-core kernels (for comparison) */
+  PINN_PREC_FP32X3 = 3         /* layer-streamed tensor-core kernels with 3xTF32 operand splitting: every
+                                * multiplicand x is fed as tf32(x) + tf32(x - tf32(x)) and each product as
+                                * lo*hi + hi*lo + hi*hi with FP32 accumulation -- FP32-grade products
+                                * (~2^-22 relative): whole-gradient norm-wise error <= 1e-5 (observed <= 5e-6,
+                                * PINN_PREC_FP32: <= 1e-6), single small layers up to 2e-5 */
 };
 enum {
   PINN_E_INVALID = -1,     /* malformed descriptor                        */
