@@ -401,12 +401,15 @@ def run_reference(args):
     device = "cpu"
     if args.baseline_device == "cuda":
         device = f"cuda:{int(os.environ.get('LOCAL_RANK', 0))}"
+    if args.baseline_tf32:
+        torch.backends.cuda.matmul.allow_tf32 = True
+        torch.backends.cudnn.allow_tf32 = True
     factor = args.sample if args.sample else (CPU_SAMPLE[args.config] if device == "cpu" else 1 / 4)
     sizes = scaled_sizes(cfg, factor)
     cores = use_all_host_threads()
     pps, dt = time_oracle(cfg, sizes, args.steps, args.warmup, device)
     sample = (f"{'+'.join(str(sizes[d[1]]) for d in cfg['domains'])} points/step ({factor:g} of the GPU workload), "
-              f"{args.steps} steps, torch autograd FP32 on {device}")
+              f"{args.steps} steps, torch autograd {'TF32-allowed' if args.baseline_tf32 else 'FP32'} on {device}")
     line = {
         "impl": "reference", "metric": METRIC, "value": pps, "unit": "points/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
@@ -606,6 +609,9 @@ def main():
     ap.add_argument("--sample", type=float, default=None, help="scale every domain size by this factor")
     ap.add_argument("--baseline-device", default="cpu", choices=["cpu", "cuda"],
                     help="--impl reference: where the reference algorithm (torch autograd) runs")
+    ap.add_argument("--baseline-tf32", action="store_true",
+                    help="--impl reference --baseline-device cuda: allow TF32 matmuls in torch (the reference's pinned "
+                         "torch 1.7.1 did so silently on Ampere; torch 2.x defaults to FP32)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--precision", default="fp32", choices=["fp32", "tf32", "tf32_streamed", "fp32x3"],
                     help="layer GEMMs of wide nets: FP32 FMA (parity) or tcgen05 TF32; narrow nets are always FP32")

@@ -10,6 +10,7 @@ void count_launch(int n);
 
 // variant 0: A[128][K], B[N][K] (both K-major):   D[i][n] = sum_k A[i][k] * B[n][k]
 // variant 1: A[K][128], B[K][N] (both MN-major):  D[i][n] = sum_k A[k][i] * B[k][n]
+// variant 4: as 0, but the A operand is written to TMEM (tcgen05.st) and read from there by the MMA
 __global__ void __launch_bounds__(128) tc_selftest_kernel(int variant, int N, int K, const float* __restrict__ A,
                                                           const float* __restrict__ B, float* __restrict__ D, int* status) {
   extern __shared__ __align__(128) float sm[];
@@ -22,7 +23,7 @@ __global__ void __launch_bounds__(128) tc_selftest_kernel(int variant, int N, in
     tc::mbar_init(&bar, 1);
     tc::fence_mbar_init();
   }
-  if (warp == 0) tc::tmem_alloc(&tmem_slot, 256);
+  if (warp == 0) tc::tmem_alloc(&tmem_slot, 512);
   tc::tc_fence_before();
   __syncthreads();
   tc::tc_fence_after();
@@ -30,7 +31,16 @@ __global__ void __launch_bounds__(128) tc_selftest_kernel(int variant, int N, in
   const int amn = (variant == 1 || variant == 2) ? 1 : 0;   // A MN-major
   const int bmn = (variant == 1 || variant == 2 || variant == 3) ? 1 : 0;  // B MN-major
   const int swap = (variant == 2) ? 1 : 0;  // experiment: LBO/SBO roles swapped for MN-major
-  if (!amn) {
+  if (variant == 4) {  // row = tid: K values into TMEM columns 256 .. 256 + K of this thread's lane
+    for (int k0 = 0; k0 < K; k0 += 8) {
+      float v[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) v[i] = tc::to_tf32(A[(size_t)tid * K + k0 + i]);
+      tc::tmem_st8(tmem + ((uint32_t)(warp * 32) << 16) + 256 + k0, v);
+    }
+    tc::tmem_st_wait();
+    tc::tc_fence_before();
+  } else if (!amn) {
     // sX[k/4][row][4]
     for (int i = tid; i < 128 * (K / 4); i += 128) {
       const int row = i / (K / 4), kq = i % (K / 4);
@@ -71,7 +81,8 @@ __global__ void __launch_bounds__(128) tc_selftest_kernel(int variant, int N, in
       if (!bmn) db = tc::smem_desc(tc::smem_u32(sB) + ks * 2 * (N * 16), N * 16, 128);
       else if (!swap) db = tc::smem_desc(tc::smem_u32(sB) + ks * ((N / 4) * 128), (N / 4) * 128, 128);
       else db = tc::smem_desc(tc::smem_u32(sB) + ks * ((N / 4) * 128), 128, (N / 4) * 128);
-      tc::mma_tf32(tmem, da, db, idesc, ks > 0 ? 1u : 0u);
+      if (variant == 4) tc::mma_tf32_ts(tmem, tmem + 256 + ks * 8, db, idesc, ks > 0 ? 1u : 0u);
+      else tc::mma_tf32(tmem, da, db, idesc, ks > 0 ? 1u : 0u);
     }
     tc::mma_commit(&bar);
   }
@@ -90,14 +101,14 @@ __global__ void __launch_bounds__(128) tc_selftest_kernel(int variant, int N, in
   }
   tc::tc_fence_before();
   __syncthreads();
-  if (warp == 0) tc::tmem_dealloc(tmem, 256);
+  if (warp == 0) tc::tmem_dealloc(tmem, 512);
 }
 
 }  // namespace pinn
 
 extern "C" int pinn_tc_selftest(int variant, int N, int K, const float* A, const float* B, float* D, int* status,
                                           void* stream) {
-  if (N % 16 || N < 16 || N > 256 || K % 8 || K < 8 || (128 + N) * K * 4 > 200 * 1024) return PINN_E_INVALID;
+  if (N % 16 || N < 16 || N > 256 || K % 8 || K < 8 || (variant == 4 && K > 256) || (128 + N) * K * 4 > 200 * 1024) return PINN_E_INVALID;
   const size_t smem = (size_t)(128 + N) * K * 4;
   cudaError_t e = cudaFuncSetAttribute((const void*)pinn::tc_selftest_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return (int)e;

@@ -55,7 +55,7 @@ __global__ void __launch_bounds__(256, 1) wide_fused_kernel(WNet net, const __gr
   float* sY = sHt + (N / 4) * (N2 + 1) * 4; // [N][4]  y, then ybar
   float* sXc = sY + 2 * N * 4;              // [kP][4] coordinates of the tile
   float* sWo = sXc + kP * 4;                // [4][128] Wout[o][k]
-  float* sRed = sWo + 4 * 128;              // scratch for the final reductions
+  float* sG = sWo + 4 * 128;                // [PINN_MAX_EQ][kP] loss seeds of the tile
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int j = (warp & 3) * 32 + lane;     // hidden unit owned by this thread (TMEM lane)
@@ -95,7 +95,9 @@ __global__ void __launch_bounds__(256, 1) wide_fused_kernel(WNet net, const __gr
   // per-unit constants in registers
   float w1[4] = {0.f, 0.f, 0.f, 0.f}, b1 = 0.f, bl[kMaxHid] = {0.f, 0.f, 0.f, 0.f}, wo[4];
   if (unit_ok) {
-    for (int d = 0; d < net.n_in; ++d) w1[d] = net.W[0][j * net.n_in + d];
+#pragma unroll
+    for (int d = 0; d < 4; ++d)  // static indices keep w1 in registers
+      if (d < net.n_in) w1[d] = net.W[0][j * net.n_in + d];
     b1 = net.b[0][j];
 #pragma unroll
     for (int l = 2; l <= kMaxHid; ++l)
@@ -112,14 +114,14 @@ __global__ void __launch_bounds__(256, 1) wide_fused_kernel(WNet net, const __gr
 
   // per-unit gradient accumulators (both point halves accumulate; summed at the end)
   float g_w1[4] = {0.f, 0.f, 0.f, 0.f}, g_b[kMaxHid + 1] = {0.f, 0.f, 0.f, 0.f, 0.f}, g_wo[4] = {0.f, 0.f, 0.f, 0.f};
-  float g_bo[4] = {0.f, 0.f, 0.f, 0.f}, loss = 0.f;
+  float g_bo_r = 0.f, loss = 0.f;  // threads (o, p) = tid < 64 / threads (e, p) = tid < 128, summed at the end
 
   float* stash = fa.stash + (size_t)blockIdx.x * (L - 1) * C * kP * 128;
   const uint32_t idesc_x = tc::idesc_tf32(N, 0, 0), idesc_w = tc::idesc_tf32(N2, 0, 0);
   const int64_t n_tiles = (fa.n_points + kP - 1) / kP;
   bool first_tile = true;
 
-  auto layer1 = [&](const float* x, float (&z)[C]) {
+  auto layer1 = [&](const float (&x)[4], float (&z)[C]) {
     float v = b1;
 #pragma unroll
     for (int d = 0; d < 4; ++d) v += w1[d] * x[d];
@@ -134,6 +136,14 @@ __global__ void __launch_bounds__(256, 1) wide_fused_kernel(WNet net, const __gr
   // element (row = unit j, K index q) of the K = (channel, point) operands
   auto szt_at = [&](int q) -> float& { return sZt[((q >> 2) * 129 + j) * 4 + (q & 3)]; };
   auto sht_at = [&](int q) -> float& { return sHt[((q >> 2) * (N2 + 1) + j) * 4 + (q & 3)]; };
+
+  int64_t n0 = 0;
+  // residual symbol of point p of the current tile: output jets (sY), coordinates (sXc), aux columns (global)
+  auto sym_at = [&](int id, int p) -> float {
+    if (id < PINN_SYM_COORD0) return sY[((id >> 2) * kP + p) * 4 + (id & 3)];
+    if (id < PINN_SYM_AUX0) return sXc[p * 4 + (id - PINN_SYM_COORD0)];
+    return (n0 + p < fa.n_points) ? fa.dom.aux[id - PINN_SYM_AUX0][n0 + p] : 0.f;
+  };
 
   auto run_mma = [&](bool with_dw, int l, bool more) {  // D = sW * sX^T  (+ optionally D2_l += sZt * sHt^T)
     tc::fence_async_smem();
@@ -164,7 +174,7 @@ __global__ void __launch_bounds__(256, 1) wide_fused_kernel(WNet net, const __gr
   };
 
   for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-    const int64_t n0 = tile * kP;
+    n0 = tile * kP;
     __syncthreads();  // previous tile fully consumed
     if (tid < kP * 4) {
       const int p = tid >> 2, d = tid & 3;
@@ -227,31 +237,56 @@ __global__ void __launch_bounds__(256, 1) wide_fused_kernel(WNet net, const __gr
       *reinterpret_cast<float4*>(sY + q * 4) = make_float4(y[0], y[1], y[2], y[3]);
     }
     __syncthreads();
-    // ---- residual, loss, ybar (one thread per point) ----------------------------------------
-    if (tid < kP) {
-      const int p = tid;
+    // ---- residual, loss, ybar: two short parallel phases instead of one thread per point ---------
+    // R1: thread (point p, equation e) evaluates r_e, the loss term and the seed g = f'(r - target) * w * sigma
+    if (tid < kP * PINN_MAX_EQ) {
+      const int p = tid & (kP - 1), e = tid >> 4;
       const int64_t ng = n0 + p;
-      float yb[C][4];
-      if (ng < fa.n_points) {
-        float y[C][4];
-#pragma unroll
-        for (int c = 0; c < C; ++c) {
-          const float4 t = *reinterpret_cast<const float4*>(sY + (c * kP + p) * 4);
-          y[c][0] = t.x; y[c][1] = t.y; y[c][2] = t.z; y[c][3] = t.w;
+      float g = 0.f;
+      if (e < fa.dom.n_eq && ng < fa.n_points) {
+        const pinn_equation& q = fa.dom.eq[e];
+        float r = 0.f;
+        for (int t = q.term_begin; t < q.term_end; ++t) {
+          const pinn_term& tm = fa.dom.terms[t];
+          float prod = tm.coef;
+          for (int f = 0; f < tm.n_fac; ++f) prod *= sym_at(tm.fac[f], p);
+          r += prod;
         }
-        float x[4] = {sXc[p * 4], sXc[p * 4 + 1], sXc[p * 4 + 2], sXc[p * 4 + 3]};
-        residual_loss_rt<C>(fa.dom, ng, x, y, yb, loss);
-#pragma unroll
-        for (int o = 0; o < 4; ++o) g_bo[o] += yb[0][o];
-      } else {
-#pragma unroll
-        for (int c = 0; c < C; ++c)
-#pragma unroll
-          for (int o = 0; o < 4; ++o) yb[c][o] = 0.f;
+        const float area = fa.dom.area ? fa.dom.area[ng] : fa.dom.area_const;
+        const float tgt = q.target ? q.target[ng] : q.target_const;
+        const float lam = q.lambda ? q.lambda[ng] : q.lambda_const;
+        const float diff = r - tgt, w = lam * area;
+        float f0, f1;
+        if (fa.dom.loss_kind == PINN_LOSS_SQUARE) { f0 = diff * diff; f1 = 2.0f * diff; }
+        else if (fa.dom.loss_kind == PINN_LOSS_L1) { f0 = fabsf(diff); f1 = (diff > 0.f) ? 1.0f : ((diff < 0.f) ? -1.0f : 0.f); }
+        else { f0 = diff; f1 = 1.0f; }
+        loss += f0 * w;
+        g = f1 * w * fa.dom.sigma;
       }
-#pragma unroll
-      for (int c = 0; c < C; ++c)
-        *reinterpret_cast<float4*>(sY + N * 4 + (c * kP + p) * 4) = make_float4(yb[c][0], yb[c][1], yb[c][2], yb[c][3]);
+      sG[tid] = g;  // [e][p]
+    }
+    __syncthreads();
+    // R2: thread (point p, output symbol id) gathers ybar[id] = sum_e g_e * d r_e / d sym[id] (same e, term, factor order
+    // as the serial evaluation of the layer-streamed path)
+    for (int item = tid; item < C * 4 * kP; item += 256) {
+      const int p = item & (kP - 1), id = item >> 4;
+      float acc = 0.f;
+      for (int e = 0; e < fa.dom.n_eq; ++e) {
+        const float g = sG[e * kP + p];
+        const pinn_equation& q = fa.dom.eq[e];
+        for (int t = q.term_begin; t < q.term_end; ++t) {
+          const pinn_term& tm = fa.dom.terms[t];
+          for (int f = 0; f < tm.n_fac; ++f) {
+            if (tm.fac[f] != id) continue;
+            float prod = tm.coef * g;
+            for (int f2 = 0; f2 < tm.n_fac; ++f2)
+              if (f2 != f) prod *= sym_at(tm.fac[f2], p);
+            acc += prod;
+          }
+        }
+      }
+      sY[N * 4 + ((id >> 2) * kP + p) * 4 + (id & 3)] = acc;
+      if (item < 4 * kP) g_bo_r += acc;  // value channel of output o = id: dL/d bout[o]  (item == tid here)
     }
     __syncthreads();
     const float* sYb = sY + N * 4;
@@ -379,8 +414,7 @@ __global__ void __launch_bounds__(256, 1) wide_fused_kernel(WNet net, const __gr
     }
   }
   // the two point-halves of a unit: add through shared memory, half 0 writes
-  float* red = sRed;  // reuse: needs 128 * 13 floats -> take it from sX (free now)
-  red = sX;
+  float* red = sX;  // free now: 128 * 13 floats of scratch for the final reductions
   float acc[13] = {g_w1[0], g_w1[1], g_w1[2], g_w1[3], g_b[0], g_b[1], g_b[2], g_b[3], g_wo[0], g_wo[1], g_wo[2], g_wo[3], 0.f};
   __syncthreads();
   if (half == 1) {
@@ -402,16 +436,16 @@ __global__ void __launch_bounds__(256, 1) wide_fused_kernel(WNet net, const __gr
     for (int o = 0; o < O; ++o) hp[o * H + j] += acc[8 + o];
   }
   __syncthreads();
-  if (tid < kP) {
-#pragma unroll
-    for (int o = 0; o < 4; ++o) red[o * kP + tid] = g_bo[o];
-    red[4 * kP + tid] = loss;
-  }
+  if (tid < 4 * kP) red[tid] = g_bo_r;                   // [o][p]
+  if (tid < kP * PINN_MAX_EQ) red[4 * kP + tid] = loss;  // [e][p]
   __syncthreads();
   if (tid <= O) {
-    const int src = tid < O ? tid : 4;
     float s = 0.f;
-    for (int p = 0; p < kP; ++p) s += red[src * kP + p];
+    if (tid < O) {
+      for (int p = 0; p < kP; ++p) s += red[tid * kP + p];
+    } else {
+      for (int i = 0; i < kP * PINN_MAX_EQ; ++i) s += red[4 * kP + i];
+    }
     fa.head_part[(size_t)blockIdx.x * (O * H + O + 1) + O * H + tid] += s;
   }
   tc::tc_fence_before();
@@ -449,7 +483,7 @@ bool fused_wide_supported(const WNet& n) {
   if (n.precision != 1 || n.H > 128 || n.L < 2 || n.L > kMaxHid || n.n_in > 4) return false;
   const int H8 = (n.H + 7) & ~7, Kq = H8 / 4, N = n.C * kP, N2 = (n.H + 15) & ~15;
   const size_t floats = (size_t)Kq * 129 * 4 + (size_t)Kq * (N + 1) * 4 + (size_t)(N / 4) * 129 * 4 +
-                        (size_t)(N / 4) * (N2 + 1) * 4 + 2 * N * 4 + kP * 4 + 4 * 128 + 64;
+                        (size_t)(N / 4) * (N2 + 1) * 4 + 2 * N * 4 + kP * 4 + 4 * 128 + kP * PINN_MAX_EQ;
   return floats * 4 <= 225 * 1024 && 12 * 128 <= Kq * (N + 1) * 4;
 }
 
@@ -473,7 +507,7 @@ int fused_wide_launch(const WNet& n, const pinn_domain* dom, float* stash, const
   if (n_splits < kBlocks) return PINN_E_UNSUPPORTED;
   const int H8 = (n.H + 7) & ~7, Kq = H8 / 4, N = n.C * kP, N2 = (n.H + 15) & ~15;
   const size_t smem = ((size_t)Kq * 129 * 4 + (size_t)Kq * (N + 1) * 4 + (size_t)(N / 4) * 129 * 4 +
-                       (size_t)(N / 4) * (N2 + 1) * 4 + 2 * N * 4 + kP * 4 + 4 * 128 + 64) * sizeof(float);
+                       (size_t)(N / 4) * (N2 + 1) * 4 + 2 * N * 4 + kP * 4 + 4 * 128 + kP * PINN_MAX_EQ) * sizeof(float);
   const int64_t tiles = (dom->n_points + kP - 1) / kP;
   int grid = tiles < kBlocks ? (int)tiles : kBlocks;
   if (grid < 1) return 0;

@@ -19,7 +19,8 @@ def _tf32(a):
     return u.astype(np.uint32).view(np.float32)
 
 
-@pytest.mark.parametrize("variant,N,K", [(0, 16, 8), (0, 64, 32), (0, 240, 104), (0, 256, 64), (0, 112, 128)])
+@pytest.mark.parametrize("variant,N,K", [(0, 16, 8), (0, 64, 32), (0, 240, 104), (0, 256, 64), (0, 112, 128),
+                                         (4, 16, 8), (4, 64, 32), (4, 112, 160), (4, 256, 64)])  # 4: A operand from TMEM
 def test_tc_gemm(variant, N, K):
     rng = np.random.default_rng(N + K + variant)
     amn, bmn = variant in (1, 2), variant in (1, 2, 3)
