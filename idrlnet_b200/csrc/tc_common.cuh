@@ -81,6 +81,17 @@ __device__ __forceinline__ void tmem_ld8(uint32_t taddr, float (&v)[8]) {
 #pragma unroll
   for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[i]);
 }
+__device__ __forceinline__ void tmem_ld4(uint32_t taddr, float (&v)[4]) {
+  uint32_t r[4];
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
+               : "r"(taddr)
+               : "memory");
+#pragma unroll
+  for (int i = 0; i < 4; ++i) v[i] = __uint_as_float(r[i]);
+}
+__device__ __forceinline__ void tmem_ldn(uint32_t taddr, float (&v)[4]) { tmem_ld4(taddr, v); }
+__device__ __forceinline__ void tmem_ldn(uint32_t taddr, float (&v)[8]) { tmem_ld8(taddr, v); }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 // registers -> TMEM: thread t of warp w writes 8 consecutive 32-bit columns of lane 32*(w%4)+t
 __device__ __forceinline__ void tmem_st8(uint32_t taddr, const float (&v)[8]) {

@@ -39,10 +39,14 @@ struct FusedArgs {
   int first_launch;      // unused (slots are always accumulated)
 };
 
-template <int NF, int NS, int ACT>
-__global__ void __launch_bounds__(256, 1) wide_fused_kernel(WNet net, const __grid_constant__ FusedArgs fa) {
+// G point groups: 128 * G threads, thread (unit j, group g) handles the kP / G points g * kP / G ... of the tile.
+// G = 4 (16 warps, <= 128 registers) hides the latency of the serial layer chain better than G = 2 once the jets
+// have many channels.
+template <int NF, int NS, int ACT, int G>
+__global__ void __launch_bounds__(128 * G, 1) wide_fused_kernel(WNet net, const __grid_constant__ FusedArgs fa) {
   constexpr int C = 1 + NF + NS;
   constexpr int N = C * kP;
+  constexpr int kT = 128 * G, kPP = kP / G;
   const int H = net.H, L = net.L, O = net.n_out;
   const int H8 = (H + 7) & ~7, Kq = H8 / 4, N2 = (H + 15) & ~15;
   extern __shared__ __align__(128) float sm[];
@@ -59,7 +63,7 @@ __global__ void __launch_bounds__(256, 1) wide_fused_kernel(WNet net, const __gr
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int j = (warp & 3) * 32 + lane;     // hidden unit owned by this thread (TMEM lane)
-  const int half = warp >> 2;               // which 8 of the tile's 16 points this thread handles
+  const int grp = warp >> 2;                // which kPP of the tile's 16 points this thread handles
   const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
   const bool unit_ok = j < H;
 
@@ -69,7 +73,7 @@ __global__ void __launch_bounds__(256, 1) wide_fused_kernel(WNet net, const __gr
     tc::fence_mbar_init();
   }
   if (warp == 0) tc::tmem_alloc(&tmem_slot, 512);
-  for (int i = tid; i < 4 * 128; i += 256) {
+  for (int i = tid; i < 4 * 128; i += kT) {
     const int o = i >> 7, k = i & 127;
     sWo[i] = (o < O && k < H) ? net.W[L][o * H + k] : 0.f;
   }
@@ -184,8 +188,8 @@ __global__ void __launch_bounds__(256, 1) wide_fused_kernel(WNet net, const __gr
 
     // ---- hidden layer 1 (SIMT): h_1 -> sX -------------------------------------------------
 #pragma unroll 2
-    for (int pp = 0; pp < kP / 2; ++pp) {
-      const int p = half * (kP / 2) + pp;
+    for (int pp = 0; pp < kPP; ++pp) {
+      const int p = grp * kPP + pp;
       float x[4] = {sXc[p * 4], sXc[p * 4 + 1], sXc[p * 4 + 2], sXc[p * 4 + 3]};
       float z[C], h[C];
       layer1(x, z);
@@ -198,14 +202,14 @@ __global__ void __launch_bounds__(256, 1) wide_fused_kernel(WNet net, const __gr
     // ---- hidden layers 2..L: tensor-core GEMM + activation epilogue -------------------------
     for (int l = 2; l <= L; ++l) {
       run_mma(false, 0, true);
-      float v[C][8];
+      float v[C][kPP];
 #pragma unroll
-      for (int c = 0; c < C; ++c) tc::tmem_ld8(tmem + lane_base + c * kP + half * 8, v[c]);
+      for (int c = 0; c < C; ++c) tc::tmem_ldn(tmem + lane_base + c * kP + grp * kPP, v[c]);
       tc::tmem_ld_wait();
       const float bias = l == 2 ? bl[1] : l == 3 ? bl[2] : bl[3];
 #pragma unroll
-      for (int pp = 0; pp < kP / 2; ++pp) {
-        const int p = half * (kP / 2) + pp;
+      for (int pp = 0; pp < kPP; ++pp) {
+        const int p = grp * kPP + pp;
         float z[C], h[C];
 #pragma unroll
         for (int c = 0; c < C; ++c) z[c] = v[c][pp];
@@ -268,7 +272,7 @@ __global__ void __launch_bounds__(256, 1) wide_fused_kernel(WNet net, const __gr
     __syncthreads();
     // R2: thread (point p, output symbol id) gathers ybar[id] = sum_e g_e * d r_e / d sym[id] (same e, term, factor order
     // as the serial evaluation of the layer-streamed path)
-    for (int item = tid; item < C * 4 * kP; item += 256) {
+    for (int item = tid; item < C * 4 * kP; item += kT) {
       const int p = item & (kP - 1), id = item >> 4;
       float acc = 0.f;
       for (int e = 0; e < fa.dom.n_eq; ++e) {
@@ -297,25 +301,25 @@ __global__ void __launch_bounds__(256, 1) wide_fused_kernel(WNet net, const __gr
     bool last_weights = false;
     for (int l = L; l >= 1; --l) {
       // stash reads do not depend on the tensor cores: issue them first
-      float zl[C][8], zp[C][8];
+      float zl[C][kPP], zp[C][kPP];
 #pragma unroll
-      for (int pp = 0; pp < kP / 2; ++pp) {
-        const int p = half * (kP / 2) + pp;
+      for (int pp = 0; pp < kPP; ++pp) {
+        const int p = grp * kPP + pp;
 #pragma unroll
         for (int c = 0; c < C; ++c) {
           zl[c][pp] = (l >= 2) ? stash[(((size_t)(l - 2) * C + c) * kP + p) * 128 + j] : 0.f;
           zp[c][pp] = (l >= 3) ? stash[(((size_t)(l - 3) * C + c) * kP + p) * 128 + j] : 0.f;
         }
       }
-      float v[C][8];
+      float v[C][kPP];
       if (l < L) {
 #pragma unroll
-        for (int c = 0; c < C; ++c) tc::tmem_ld8(tmem + lane_base + c * kP + half * 8, v[c]);
+        for (int c = 0; c < C; ++c) tc::tmem_ldn(tmem + lane_base + c * kP + grp * kPP, v[c]);
         tc::tmem_ld_wait();
       }
 #pragma unroll
-      for (int pp = 0; pp < kP / 2; ++pp) {
-        const int p = half * (kP / 2) + pp;
+      for (int pp = 0; pp < kPP; ++pp) {
+        const int p = grp * kPP + pp;
         float x[4] = {sXc[p * 4], sXc[p * 4 + 1], sXc[p * 4 + 2], sXc[p * 4 + 3]};
         float z[C], hb[C], zb[C], h[C];
         if (l >= 2) {
@@ -399,7 +403,7 @@ __global__ void __launch_bounds__(256, 1) wide_fused_kernel(WNet net, const __gr
     tc::tc_fence_after();
     for (int l = 2; l <= L; ++l) {
       float* out = fa.dw_part + ((size_t)(l - 2) * fa.n_splits + blockIdx.x) * H * H;
-      for (int g = half; g < N2 / 16; g += 2) {
+      for (int g = grp; g < N2 / 16; g += G) {
         float v[16];
         tc::tmem_ld16(tmem + 128 + (uint32_t)(l - 2) * 128 + lane_base + g * 16, v);
         tc::tmem_ld_wait();
@@ -413,18 +417,20 @@ __global__ void __launch_bounds__(256, 1) wide_fused_kernel(WNet net, const __gr
       }
     }
   }
-  // the two point-halves of a unit: add through shared memory, half 0 writes
-  float* red = sX;  // free now: 128 * 13 floats of scratch for the final reductions
+  // the G point groups of a unit: add through shared memory, group 0 writes
+  float* red = sX;  // free now: (G - 1) * 12 * 128 floats of scratch for the final reductions
   float acc[13] = {g_w1[0], g_w1[1], g_w1[2], g_w1[3], g_b[0], g_b[1], g_b[2], g_b[3], g_wo[0], g_wo[1], g_wo[2], g_wo[3], 0.f};
   __syncthreads();
-  if (half == 1) {
+  if (grp > 0) {
 #pragma unroll
-    for (int i = 0; i < 12; ++i) red[i * 128 + j] = acc[i];
+    for (int i = 0; i < 12; ++i) red[((grp - 1) * 12 + i) * 128 + j] = acc[i];
   }
   __syncthreads();
-  if (half == 0 && unit_ok) {
+  if (grp == 0 && unit_ok) {
 #pragma unroll
-    for (int i = 0; i < 12; ++i) acc[i] += red[i * 128 + j];
+    for (int g = 1; g < G; ++g)
+#pragma unroll
+      for (int i = 0; i < 12; ++i) acc[i] += red[((g - 1) * 12 + i) * 128 + j];
     float* fp = fa.first_part + (size_t)blockIdx.x * 8 * H;
 #pragma unroll
     for (int d = 0; d < 4; ++d) fp[d * H + j] += acc[d];
@@ -484,7 +490,7 @@ bool fused_wide_supported(const WNet& n) {
   const int H8 = (n.H + 7) & ~7, Kq = H8 / 4, N = n.C * kP, N2 = (n.H + 15) & ~15;
   const size_t floats = (size_t)Kq * 129 * 4 + (size_t)Kq * (N + 1) * 4 + (size_t)(N / 4) * 129 * 4 +
                         (size_t)(N / 4) * (N2 + 1) * 4 + 2 * N * 4 + kP * 4 + 4 * 128 + kP * PINN_MAX_EQ;
-  return floats * 4 <= 225 * 1024 && 12 * 128 <= Kq * (N + 1) * 4;
+  return floats * 4 <= 225 * 1024 && 3 * 12 * 128 <= Kq * (N + 1) * 4;
 }
 
 int64_t fused_wide_stash_floats(const WNet& n) { return (int64_t)kBlocks * (n.L - 1) * n.C * kP * 128; }
@@ -513,10 +519,11 @@ int fused_wide_launch(const WNet& n, const pinn_domain* dom, float* stash, const
   if (grid < 1) return 0;
 #define CASE(NF_, NS_)                                                                                                 \
   if (n.NF == NF_ && n.NS == NS_) {                                                                                   \
-    cudaError_t e = cudaFuncSetAttribute((const void*)wide_fused_kernel<NF_, NS_, ACT>,                                \
+    constexpr int G_ = (1 + NF_ + NS_ >= 3) ? 4 : 2;                                                                   \
+    cudaError_t e = cudaFuncSetAttribute((const void*)wide_fused_kernel<NF_, NS_, ACT, G_>,                            \
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);                      \
     if (e != cudaSuccess) return (int)e;                                                                               \
-    wide_fused_kernel<NF_, NS_, ACT><<<grid, 256, smem, st>>>(n, fa);                                                  \
+    wide_fused_kernel<NF_, NS_, ACT, G_><<<grid, 128 * G_, smem, st>>>(n, fa);                                         \
     launched = true;                                                                                                   \
   }
   bool launched = false;
