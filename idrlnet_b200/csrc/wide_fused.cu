@@ -40,8 +40,8 @@ struct FusedArgs {
 };
 
 // G point groups: 128 * G threads, thread (unit j, group g) handles the kP / G points g * kP / G ... of the tile.
-// G = 4 (16 warps, <= 128 registers) hides the latency of the serial layer chain better than G = 2 once the jets
-// have many channels.
+// G = 4 (16 warps, <= 128 registers) hides the latency of the serial layer chain better than G = 2 (8 warps, up to
+// 234 registers): +8 % on the 5-channel LDC interior, and the value-only boundary domains are L2-latency bound.
 template <int NF, int NS, int ACT, int G>
 __global__ void __launch_bounds__(128 * G, 1) wide_fused_kernel(WNet net, const __grid_constant__ FusedArgs fa) {
   constexpr int C = 1 + NF + NS;
@@ -519,7 +519,7 @@ int fused_wide_launch(const WNet& n, const pinn_domain* dom, float* stash, const
   if (grid < 1) return 0;
 #define CASE(NF_, NS_)                                                                                                 \
   if (n.NF == NF_ && n.NS == NS_) {                                                                                   \
-    constexpr int G_ = (1 + NF_ + NS_ >= 3) ? 4 : 2;                                                                   \
+    constexpr int G_ = 4;                                                                                              \
     cudaError_t e = cudaFuncSetAttribute((const void*)wide_fused_kernel<NF_, NS_, ACT, G_>,                            \
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);                      \
     if (e != cudaSuccess) return (int)e;                                                                               \

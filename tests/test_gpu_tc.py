@@ -2,7 +2,8 @@
 
 Only K-major operands are exercised: on this B200 / CUDA 12.9 the MN-major no-swizzle
 descriptor form produced all-zero accumulators (selftest variants 1-3), so the production
-kernels transpose while staging instead (idrlnet_b200/csrc/wide_tc.cu, tc_dw_kernel)."""
+kernels re-tile the transposed operands instead (idrlnet_b200/csrc/wide_dw.cu).  Variant 4
+reads the A operand from TMEM (tcgen05.st + the TS form of tcgen05.mma)."""
 import numpy as np
 import pytest
 import torch
