@@ -65,6 +65,30 @@ __global__ void fma_probe_kernel(int iters, float* out) {
   if (s == 12345.678f) out[0] = s;  // keep the chains alive
 }
 
+// the same chains as packed pairs: fma.rn.f32x2 (SASS FFMA2), two FP32 FMAs per lane per instruction
+__global__ void fma2_probe_kernel(int iters, float* out) {
+  unsigned long long a[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const float2 v = make_float2(1.0f + 1e-3f * (threadIdx.x + 2 * i), 1.0f + 1e-3f * (threadIdx.x + 2 * i + 1));
+    a[i] = *reinterpret_cast<const unsigned long long*>(&v);
+  }
+  const float mf = 1.0f - 1e-7f * (threadIdx.x & 3), cf = 1e-9f * blockIdx.x;
+  const float2 m2 = make_float2(mf, mf), c2 = make_float2(cf, cf);
+  const unsigned long long m = *reinterpret_cast<const unsigned long long*>(&m2), c = *reinterpret_cast<const unsigned long long*>(&c2);
+  for (int it = 0; it < iters; ++it) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) asm volatile("fma.rn.f32x2 %0, %0, %1, %2;" : "+l"(a[i]) : "l"(m), "l"(c));
+  }
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const float2 v = *reinterpret_cast<const float2*>(&a[i]);
+    s += v.x + v.y;
+  }
+  if (s == 12345.678f) out[0] = s;
+}
+
 struct SampleArgs {
   float* col[PINN_MAX_IN];
   float lo[PINN_MAX_IN], hi[PINN_MAX_IN];
@@ -120,6 +144,14 @@ int pinn_weight_norm_backward(const float* g, const float* v, const float* dW, f
 int64_t pinn_fp32_fma_probe(int32_t iters, int32_t blocks, float* scratch, void* stream) {
   if (iters < 1 || blocks < 1 || !scratch) return PINN_E_INVALID;
   fma_probe_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(iters, scratch);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return -(int64_t)e;
+  return (int64_t)2 * 16 * iters * 256 * blocks;  // flops issued
+}
+
+int64_t pinn_fp32_fma2_probe(int32_t iters, int32_t blocks, float* scratch, void* stream) {
+  if (iters < 1 || blocks < 1 || !scratch) return PINN_E_INVALID;
+  fma2_probe_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(iters, scratch);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return -(int64_t)e;
   return (int64_t)2 * 16 * iters * 256 * blocks;  // flops issued

@@ -113,6 +113,7 @@ _SIGNATURES = {
     "pinn_topk_abs": (C.c_int, [C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64,
                                 C.c_void_p]),
     "pinn_fp32_fma_probe": (C.c_int64, [C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]),
+    "pinn_fp32_fma2_probe": (C.c_int64, [C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]),
     "pinn_tc_selftest": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
 }
 EXPORTS = tuple(_SIGNATURES)

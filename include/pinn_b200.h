@@ -228,6 +228,8 @@ PINN_API int pinn_sample_box(float* const* columns, int32_t n_dims, const float*
  * `iters` steps; returns the number of flops issued (time it with CUDA events to
  * get the FP32-pipe roofline denominator), or a negative cudaError_t. */
 PINN_API int64_t pinn_fp32_fma_probe(int32_t iters, int32_t blocks, float* scratch, void* stream);
+/* The same chains as packed pairs (fma.rn.f32x2, SASS FFMA2). */
+PINN_API int64_t pinn_fp32_fma2_probe(int32_t iters, int32_t blocks, float* scratch, void* stream);
 
 /* Self-test of the tcgen05 plumbing used by the wide tensor-core path: one CTA computes
  * D[128][N] = A * B^T in TF32 (FP32 accumulate in TMEM).  variant 0: A[128][K], B[N][K]
