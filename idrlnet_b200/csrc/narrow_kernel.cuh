@@ -76,8 +76,8 @@ __global__ void __launch_bounds__(256, 1) narrow_kernel(const __grid_constant__ 
 
 // One table per (H, ACT) translation unit: entries for every (NF, NS).
 #define PINN_NARROW_ENTRY(H, NF, NS, ACT) \
-  { narrow_kernel<NarrowWarp<H, NF, NS, ACT>>, H, 1 + NF + NS, &NarrowWarp<H, NF, NS, ACT>::warp_floats, \
-    &NarrowWarp<H, NF, NS, ACT>::stash_floats }
+  { narrow_kernel<NarrowWarpFor<H, NF, NS, ACT>>, H, 1 + NF + NS, &NarrowWarpFor<H, NF, NS, ACT>::warp_floats, \
+    &NarrowWarpFor<H, NF, NS, ACT>::stash_floats }
 
 #define PINN_NARROW_TABLE(NAME, H, ACT)                                          \
   const NarrowKernelInfo* NAME(int nf, int ns) {                                 \

@@ -27,6 +27,8 @@
 //
 // The code below is written as per-lane "phase" functions separated by
 // __syncwarp(); tests/emu runs the same functions lane by lane on the CPU.
+// NarrowWarp is the scalar-FMA program (any channel count); NarrowWarpPair (further down) is the
+// same program on channel pairs and packed FMAs for even channel counts; NarrowWarpFor picks one.
 #pragma once
 #include "pinn_common.h"
 
@@ -553,6 +555,439 @@ struct NarrowWarp {
     }
   }
 };
+
+// ---------------------------------------------------------------------------------------------
+// The same warp program for jets with an EVEN number of channels, with every jet stored as channel
+// pairs (2cp, 2cp+1) -- in registers, in the shared-memory rows and in the L2 stash -- so that the
+// three hot loops run on packed FMAs (FFMA2, half the FMA issue slots):
+//   forward   acc[cp][j] += W[j][k] (scalar, broadcast) * h[cp][k]
+//   reverse   hbar[cp][k] += W[j][k] (scalar) * zbar[cp][j]
+//   dW GEMM   acc[j][k] (pair of per-channel partial sums, added at the end) += zbar[cp][j] * h[cp][k]
+// Row layout (floats): [cp][half h][unit quad m][4] with the 4 floats = (unit 4m+2h: ch 2cp, ch 2cp+1,
+// unit 4m+2h+1: ch 2cp, ch 2cp+1).  The 4-unit tile of a channel pair is the two 16-byte chunks (h = 0, 1);
+// chunks of consecutive unit quads are adjacent, so the five (H = 20) or eight (H = 32) distinct chunks
+// that the lanes of a GEMM load touch fall into different bank groups.
+template <int H_, int NF_, int NS_, int ACT_>
+struct NarrowWarpPair {
+  using Base = NarrowWarp<H_, NF_, NS_, ACT_>;
+  static constexpr int H = H_, NF = NF_, NS = NS_, ACT = ACT_;
+  static constexpr int C = 1 + NF + NS;
+  static constexpr int CP = C / 2;
+  static constexpr int H4 = H / 4;
+  static_assert(C % 2 == 0, "channel pairs need an even channel count");
+
+  PINN_HD static int S() { return row_stride(C * H); }
+  PINN_HD static int off_a() { return 0; }
+  PINN_HD static int off_b() { return 32 * S(); }
+  PINN_HD static int off_xs() { return 2 * 32 * S(); }
+  PINN_HD static int off_gacc() { return off_xs() + 32 * 4; }
+  PINN_HD static int warp_floats(int L) { return off_gacc() + Layout(H, L).size(); }
+  // per-warp global stash (floats): [(l-2)][cp][k4][half][lane][4]
+  PINN_HD static int stash_floats(int L) { return (L - 1) * C * H * 32; }
+  PINN_HD static int stash_off(int l, int cp, int k4, int half, int lane) {
+    return ((((l - 2) * CP + cp) * H4 + k4) * 2 + half) * 128 + lane * 4;
+  }
+  PINN_HD static int chunk_off(int cp, int h, int m) { return ((cp * 2 + h) * H4 + m) * 4; }
+  // float offset of (channel c, unit j) inside a row
+  PINN_HD static int elem_off(int c, int j) { return chunk_off(c >> 1, (j >> 1) & 1, j >> 2) + (j & 1) * 2 + (c & 1); }
+
+  struct Lane {
+    float loss;
+    f2 zk[CP][H];  // zbar of the layer just differentiated, as channel pairs
+  };
+
+  PINN_HD static float get(const f2& v, int half) { return half ? v.y : v.x; }
+
+  // 4 units x one channel pair <-> the two chunks of a row
+  PINN_HD static void load_pairs(const float* row, int cp, int m, f2 (&t)[4]) {
+    const f4 a = ld4(row + chunk_off(cp, 0, m)), b = ld4(row + chunk_off(cp, 1, m));
+    t[0] = f2{a.x, a.y}; t[1] = f2{a.z, a.w}; t[2] = f2{b.x, b.y}; t[3] = f2{b.z, b.w};
+  }
+  PINN_HD static void store_pairs(float* row, int cp, int m, const f2 (&t)[4]) {
+    st4(row + chunk_off(cp, 0, m), f4{t[0].x, t[0].y, t[1].x, t[1].y});
+    st4(row + chunk_off(cp, 1, m), f4{t[2].x, t[2].y, t[3].x, t[3].y});
+  }
+
+  PINN_HD static void residual_loss(const NarrowParams& p, int64_t n, bool valid, const float (&x)[4], const f4 (&y)[C],
+                                    f4 (&yb)[C], Lane& lane) {
+    typename Base::Lane bl;
+    bl.loss = lane.loss;
+    Base::residual_loss(p, n, valid, x, y, yb, bl);
+    lane.loss = bl.loss;
+  }
+
+  PINN_HD static void phase_forward(const NarrowParams& p, const float* sw, float* wm, float* gs, int lane_id,
+                                    int64_t tile, Lane& lane) {
+    const int L = p.n_hidden;
+    const Layout lay(H, L);
+    const int s = S();
+    const int64_t n = tile * 32 + lane_id;
+    const bool valid = n < p.n_points;
+    float x[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int d = 0; d < 4; ++d)
+      if (d < p.n_in && valid) x[d] = p.coords[d][n];
+    st4(wm + off_xs() + lane_id * 4, f4{x[0], x[1], x[2], x[3]});
+    float* a_row = wm + off_a() + lane_id * s;
+
+    f2 hin[CP][H];
+#pragma unroll
+    for (int k4 = 0; k4 < H4; ++k4) {  // hidden layer 1
+      f4 zt[C];
+      Base::layer1_tile(sw, lay, p, x, k4, zt);
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        float z[C], h[C];
+#pragma unroll
+        for (int c = 0; c < C; ++c) z[c] = (&zt[c].x)[e];
+        Base::unit_fwd(z, h);
+#pragma unroll
+        for (int cp = 0; cp < CP; ++cp) hin[cp][k4 * 4 + e] = f2{h[2 * cp], h[2 * cp + 1]};
+      }
+    }
+    for (int l = 2; l <= L; ++l) {  // hidden layers 2..L
+      const float* Wt = sw + lay.wh(l);
+      const float* bl = sw + lay.bh(l);
+#if defined(__CUDA_ARCH__)
+#pragma unroll 1
+#endif
+      for (int j4 = 0; j4 < H4; ++j4) {
+        f2 acc[CP][4];  // acc[cp][e]: pre-activation of unit j4*4+e, channels (2cp, 2cp+1)
+        {
+          const f4 b = ld4(bl + j4 * 4);
+          acc[0][0] = f2{b.x, 0.f}; acc[0][1] = f2{b.y, 0.f}; acc[0][2] = f2{b.z, 0.f}; acc[0][3] = f2{b.w, 0.f};
+        }
+#pragma unroll
+        for (int cp = 1; cp < CP; ++cp)
+#pragma unroll
+          for (int e = 0; e < 4; ++e) acc[cp][e] = f2{0.f, 0.f};
+#pragma unroll
+        for (int k = 0; k < H; ++k) {
+          const f4 w = ld4(Wt + k * H + j4 * 4);
+#pragma unroll
+          for (int cp = 0; cp < CP; ++cp) {
+            acc[cp][0] = fma2s(hin[cp][k], w.x, acc[cp][0]);
+            acc[cp][1] = fma2s(hin[cp][k], w.y, acc[cp][1]);
+            acc[cp][2] = fma2s(hin[cp][k], w.z, acc[cp][2]);
+            acc[cp][3] = fma2s(hin[cp][k], w.w, acc[cp][3]);
+          }
+        }
+        if (p.mode != MODE_FWD) {
+#pragma unroll
+          for (int cp = 0; cp < CP; ++cp) {
+            st4(gs + stash_off(l, cp, j4, 0, lane_id), f4{acc[cp][0].x, acc[cp][0].y, acc[cp][1].x, acc[cp][1].y});
+            st4(gs + stash_off(l, cp, j4, 1, lane_id), f4{acc[cp][2].x, acc[cp][2].y, acc[cp][3].x, acc[cp][3].y});
+          }
+        }
+        f2 ht[CP][4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          float z[C], h[C];
+#pragma unroll
+          for (int c = 0; c < C; ++c) z[c] = get(acc[c >> 1][e], c & 1);
+          Base::unit_fwd(z, h);
+#pragma unroll
+          for (int cp = 0; cp < CP; ++cp) ht[cp][e] = f2{h[2 * cp], h[2 * cp + 1]};
+        }
+#pragma unroll
+        for (int cp = 0; cp < CP; ++cp) store_pairs(a_row, cp, j4, ht[cp]);  // scratch: hin is still being read
+      }
+#pragma unroll
+      for (int k4 = 0; k4 < H4; ++k4)
+#pragma unroll
+        for (int cp = 0; cp < CP; ++cp) {
+          f2 t[4];
+          load_pairs(a_row, cp, k4, t);
+          hin[cp][k4 * 4 + 0] = t[0]; hin[cp][k4 * 4 + 1] = t[1]; hin[cp][k4 * 4 + 2] = t[2]; hin[cp][k4 * 4 + 3] = t[3];
+        }
+    }
+    // output layer, packed over the output pairs (o0,o1), (o2,o3)
+    f2 y2[C][2];
+    {
+      const f4 b = ld4(sw + lay.bo());
+      y2[0][0] = f2{b.x, b.y}; y2[0][1] = f2{b.z, b.w};
+    }
+#pragma unroll
+    for (int c = 1; c < C; ++c) { y2[c][0] = f2{0.f, 0.f}; y2[c][1] = f2{0.f, 0.f}; }
+#pragma unroll
+    for (int k = 0; k < H; ++k) {
+      const f4 w = ld4(sw + lay.wo() + k * 4);
+#pragma unroll
+      for (int c = 0; c < C; ++c) {
+        const float hv = get(hin[c >> 1][k], c & 1);
+        y2[c][0] = fma2s(f2{w.x, w.y}, hv, y2[c][0]);
+        y2[c][1] = fma2s(f2{w.z, w.w}, hv, y2[c][1]);
+      }
+    }
+    f4 y[C];
+#pragma unroll
+    for (int c = 0; c < C; ++c) y[c] = f4{y2[c][0].x, y2[c][0].y, y2[c][1].x, y2[c][1].y};
+
+    if (p.mode == MODE_FWD) {
+      if (valid) {
+#pragma unroll
+        for (int c = 0; c < C; ++c)
+#pragma unroll
+          for (int o = 0; o < 4; ++o)
+            if (o < p.n_out) p.jets_out[(int64_t)(c * p.n_out + o) * p.n_points + n] = (&y[c].x)[o];
+      }
+      return;
+    }
+
+    f4 yb[C];
+    if (p.mode == MODE_FUSED) {
+      residual_loss(p, n, valid, x, y, yb, lane);
+    } else {
+#pragma unroll
+      for (int c = 0; c < C; ++c) {
+        yb[c] = f4{0.f, 0.f, 0.f, 0.f};
+        if (valid) {
+#pragma unroll
+          for (int o = 0; o < 4; ++o)
+            if (o < p.n_out) (&yb[c].x)[o] = p.jets_bar[(int64_t)(c * p.n_out + o) * p.n_points + n];
+        }
+      }
+    }
+#pragma unroll
+    for (int c = 0; c < C; ++c) st4(a_row + c * 4, yb[c]);  // A row now holds ybar[c][o4]
+  }
+
+  PINN_HD static void phase_backward(const NarrowParams& p, const float* sw, float* wm, const float* gs, int lane_id,
+                                     int l, Lane& lane) {
+    const int L = p.n_hidden;
+    const Layout lay(H, L);
+    const int s = S();
+    const float* a_row = wm + off_a() + lane_id * s;
+    float* b_row = wm + off_b() + lane_id * s;
+    f2 (&hbar)[CP][H] = lane.zk;  // adjoint of h_{l-1} (channel pairs); overwritten in place by zbar_{l-1}
+    if (l == L + 1) {
+      f4 yb[C];
+#pragma unroll
+      for (int c = 0; c < C; ++c) yb[c] = ld4(a_row + c * 4);
+      f2 ybp[CP][4];  // (ybar[2cp][o], ybar[2cp+1][o])
+#pragma unroll
+      for (int cp = 0; cp < CP; ++cp)
+#pragma unroll
+        for (int o = 0; o < 4; ++o) ybp[cp][o] = f2{(&yb[2 * cp].x)[o], (&yb[2 * cp + 1].x)[o]};
+#pragma unroll
+      for (int k = 0; k < H; ++k) {
+        const f4 w = ld4(sw + lay.wo() + k * 4);
+#pragma unroll
+        for (int cp = 0; cp < CP; ++cp) {
+          f2 t = f2{0.f, 0.f};
+          t = fma2s(ybp[cp][0], w.x, t);
+          t = fma2s(ybp[cp][1], w.y, t);
+          t = fma2s(ybp[cp][2], w.z, t);
+          t = fma2s(ybp[cp][3], w.w, t);
+          hbar[cp][k] = t;
+        }
+      }
+    } else {
+      const float* Wt = sw + lay.wh(l);
+#pragma unroll
+      for (int cp = 0; cp < CP; ++cp)
+#pragma unroll
+        for (int k = 0; k < H; ++k) hbar[cp][k] = f2{0.f, 0.f};
+#if defined(__CUDA_ARCH__)
+#pragma unroll 1
+#endif
+      for (int j4 = 0; j4 < H4; ++j4) {
+        f2 zb[CP][4];
+#pragma unroll
+        for (int cp = 0; cp < CP; ++cp) load_pairs(a_row, cp, j4, zb[cp]);
+#pragma unroll
+        for (int k = 0; k < H; ++k) {
+          const f4 w = ld4(Wt + k * H + j4 * 4);
+#pragma unroll
+          for (int cp = 0; cp < CP; ++cp) {
+            f2 t = hbar[cp][k];
+            t = fma2s(zb[cp][0], w.x, t);
+            t = fma2s(zb[cp][1], w.y, t);
+            t = fma2s(zb[cp][2], w.z, t);
+            t = fma2s(zb[cp][3], w.w, t);
+            hbar[cp][k] = t;
+          }
+        }
+      }
+    }
+    // through activation l-1
+    const int lm = l - 1;
+    float x[4];
+    {
+      const f4 xv = ld4(wm + off_xs() + lane_id * 4);
+      x[0] = xv.x; x[1] = xv.y; x[2] = xv.z; x[3] = xv.w;
+    }
+#pragma unroll
+    for (int k4 = 0; k4 < H4; ++k4) {
+      f4 zt[C];      // lm == 1: per-channel tiles from the first layer
+      f2 zp[CP][4];  // lm >= 2: channel pairs from the stash
+      if (lm >= 2) {
+#pragma unroll
+        for (int cp = 0; cp < CP; ++cp) {
+          const f4 a = ld4(gs + stash_off(lm, cp, k4, 0, lane_id)), b = ld4(gs + stash_off(lm, cp, k4, 1, lane_id));
+          zp[cp][0] = f2{a.x, a.y}; zp[cp][1] = f2{a.z, a.w}; zp[cp][2] = f2{b.x, b.y}; zp[cp][3] = f2{b.z, b.w};
+        }
+      } else {
+        Base::layer1_tile(sw, lay, p, x, k4, zt);
+      }
+      f2 ht[CP][4];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        float z[C], hb[C], h[C], zb[C];
+#pragma unroll
+        for (int c = 0; c < C; ++c) {
+          z[c] = (lm >= 2) ? get(zp[c >> 1][e], c & 1) : (&zt[c].x)[e];
+          hb[c] = get(hbar[c >> 1][k4 * 4 + e], c & 1);
+          zb[c] = 0.f;
+        }
+        Base::unit_bwd(z, hb, h, zb);
+#pragma unroll
+        for (int cp = 0; cp < CP; ++cp) {
+          ht[cp][e] = f2{h[2 * cp], h[2 * cp + 1]};
+          hbar[cp][k4 * 4 + e] = f2{zb[2 * cp], zb[2 * cp + 1]};
+        }
+      }
+#pragma unroll
+      for (int cp = 0; cp < CP; ++cp) store_pairs(b_row, cp, k4, ht[cp]);
+    }
+  }
+
+  PINN_HD static void phase_store_zk(float* wm, int lane_id, const Lane& lane) {
+    float* a_row = wm + off_a() + lane_id * S();
+#pragma unroll
+    for (int k4 = 0; k4 < H4; ++k4)
+#pragma unroll
+      for (int cp = 0; cp < CP; ++cp) {
+        const f2 t[4] = {lane.zk[cp][k4 * 4], lane.zk[cp][k4 * 4 + 1], lane.zk[cp][k4 * 4 + 2], lane.zk[cp][k4 * 4 + 3]};
+        store_pairs(a_row, cp, k4, t);
+      }
+  }
+
+  PINN_HD static void phase_gemm_out(const NarrowParams& p, float* wm, int lane_id) {
+    const int L = p.n_hidden;
+    const Layout lay(H, L);
+    const int s = S();
+    const float* yb = wm + off_a();
+    const float* hb = wm + off_b();
+    float* g = wm + off_gacc();
+    const int T = p.n_out * H4;
+    for (int t = lane_id; t < T; t += 32) {
+      const int o = t / H4, kb = t % H4;
+      f2 acc[4];  // per unit k: partial sums of the two channels of a pair
+#pragma unroll
+      for (int e = 0; e < 4; ++e) acc[e] = f2{0.f, 0.f};
+      for (int n = 0; n < 32; ++n) {
+#pragma unroll
+        for (int cp = 0; cp < CP; ++cp) {
+          const f2 a = f2{yb[n * s + (2 * cp) * 4 + o], yb[n * s + (2 * cp + 1) * 4 + o]};
+          f2 b[4];
+          load_pairs(hb + n * s, cp, kb, b);
+#pragma unroll
+          for (int e = 0; e < 4; ++e) acc[e] = fma2(a, b[e], acc[e]);
+        }
+      }
+      float* gw = g + lay.wo() + (kb * 4) * 4 + o;
+      gw[0] += acc[0].x + acc[0].y; gw[4] += acc[1].x + acc[1].y; gw[8] += acc[2].x + acc[2].y; gw[12] += acc[3].x + acc[3].y;
+    }
+    if (lane_id < p.n_out) {
+      float a = 0.f;
+      for (int n = 0; n < 32; ++n) a += yb[n * s + lane_id];
+      g[lay.bo() + lane_id] += a;
+    }
+  }
+
+  PINN_HD static void phase_gemm_hidden(const NarrowParams& p, float* wm, int lane_id, int l) {
+    const int L = p.n_hidden;
+    const Layout lay(H, L);
+    const int s = S();
+    const float* A = wm + off_a();  // zbar_l
+    const float* B = wm + off_b();  // h_{l-1}
+    float* g = wm + off_gacc();
+    for (int t = lane_id; t < H4 * H4; t += 32) {
+      const int ja = t / H4, kb = t % H4;
+      f2 acc[4][4];  // acc[kk][jj]: per-channel partial sums of dW[ja*4+jj][kb*4+kk]
+#pragma unroll
+      for (int kk = 0; kk < 4; ++kk)
+#pragma unroll
+        for (int jj = 0; jj < 4; ++jj) acc[kk][jj] = f2{0.f, 0.f};
+#if defined(__CUDA_ARCH__)
+#pragma unroll 2
+#endif
+      for (int n = 0; n < 32; ++n) {
+#pragma unroll
+        for (int cp = 0; cp < CP; ++cp) {
+          f2 a[4], b[4];
+          load_pairs(A + n * s, cp, ja, a);
+          load_pairs(B + n * s, cp, kb, b);
+#pragma unroll
+          for (int kk = 0; kk < 4; ++kk)
+#pragma unroll
+            for (int jj = 0; jj < 4; ++jj) acc[kk][jj] = fma2(a[jj], b[kk], acc[kk][jj]);
+        }
+      }
+#pragma unroll
+      for (int kk = 0; kk < 4; ++kk) {
+        float* gp = g + lay.wh(l) + (kb * 4 + kk) * H + ja * 4;
+        f4 v = ld4(gp);
+        v.x += acc[kk][0].x + acc[kk][0].y; v.y += acc[kk][1].x + acc[kk][1].y;
+        v.z += acc[kk][2].x + acc[kk][2].y; v.w += acc[kk][3].x + acc[kk][3].y;
+        st4(gp, v);
+      }
+    }
+    for (int t = lane_id; t < H4; t += 32) {
+      f4 a = f4{0.f, 0.f, 0.f, 0.f};
+      for (int n = 0; n < 32; ++n) {  // value channel = first half of pair 0
+        const f4 u = ld4(A + n * s + chunk_off(0, 0, t)), v = ld4(A + n * s + chunk_off(0, 1, t));
+        a.x += u.x; a.y += u.z; a.z += v.x; a.w += v.z;
+      }
+      float* gp = g + lay.bh(l) + t * 4;
+      f4 v = ld4(gp);
+      v.x += a.x; v.y += a.y; v.z += a.z; v.w += a.w;
+      st4(gp, v);
+    }
+  }
+
+  PINN_HD static void phase_gemm_first(const NarrowParams& p, float* wm, int lane_id) {
+    const int L = p.n_hidden;
+    const Layout lay(H, L);
+    const int s = S();
+    const float* X = wm + off_a();  // zbar_1
+    const float* xs = wm + off_xs();
+    float* g = wm + off_gacc();
+    for (int j = lane_id; j < H; j += 32) {
+      float ad[4] = {0.f, 0.f, 0.f, 0.f};
+      float af[NF > 0 ? NF : 1];
+#pragma unroll
+      for (int i = 0; i < NF; ++i) af[i] = 0.f;
+      float ab = 0.f;
+      for (int n = 0; n < 32; ++n) {
+        const float zv = X[n * s + elem_off(0, j)];
+        const f4 xv = ld4(xs + n * 4);
+        ad[0] += zv * xv.x; ad[1] += zv * xv.y; ad[2] += zv * xv.z; ad[3] += zv * xv.w;
+        ab += zv;
+#pragma unroll
+        for (int i = 0; i < NF; ++i) af[i] += X[n * s + elem_off(1 + i, j)];
+      }
+#pragma unroll
+      for (int d = 0; d < 4; ++d) g[lay.w1() + d * H + j] += ad[d];
+#pragma unroll
+      for (int i = 0; i < NF; ++i) g[lay.w1() + p.jets.first_in[i] * H + j] += af[i];
+      g[lay.b1() + j] += ab;
+    }
+  }
+};
+
+// even channel counts run the packed program, odd ones the scalar one
+template <int H, int NF, int NS, int ACT, bool EVEN = ((1 + NF + NS) % 2 == 0)>
+struct NarrowSelect {
+  using type = NarrowWarp<H, NF, NS, ACT>;
+};
+template <int H, int NF, int NS, int ACT>
+struct NarrowSelect<H, NF, NS, ACT, true> {
+  using type = NarrowWarpPair<H, NF, NS, ACT>;
+};
+template <int H, int NF, int NS, int ACT>
+using NarrowWarpFor = typename NarrowSelect<H, NF, NS, ACT>::type;
 
 // Weight staging: global (row-major [out,in]) -> smem padded/transposed Layout.
 // idx is an index into the Layout; returns the value to store there.

@@ -39,6 +39,44 @@ PINN_HD void st4(float* p, const f4& v) {
 }
 PINN_HD float& f4_at(f4& v, int i) { return (&v.x)[i]; }
 
+// A pair of FP32 values that travels in one 64-bit register: jets with an even number of channels
+// are stored as channel pairs so that the hot loops issue packed FMAs (fma.rn.f32x2 -> SASS FFMA2:
+// two FMAs per lane per issue slot; a scalar operand is broadcast to both halves for free).
+struct alignas(8) f2 {
+  float x, y;
+};
+
+// c + a * s (s broadcast)
+PINN_HD f2 fma2s(const f2& a, float s, const f2& c) {
+#if defined(__CUDA_ARCH__)
+  unsigned long long aa, ss, cc, rr;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(aa) : "f"(a.x), "f"(a.y));
+  asm("mov.b64 %0, {%1, %1};" : "=l"(ss) : "f"(s));
+  asm("mov.b64 %0, {%1, %2};" : "=l"(cc) : "f"(c.x), "f"(c.y));
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(rr) : "l"(aa), "l"(ss), "l"(cc));
+  f2 r;
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(r.x), "=f"(r.y) : "l"(rr));
+  return r;
+#else
+  return f2{fmaf(a.x, s, c.x), fmaf(a.y, s, c.y)};
+#endif
+}
+// c + a * b (elementwise)
+PINN_HD f2 fma2(const f2& a, const f2& b, const f2& c) {
+#if defined(__CUDA_ARCH__)
+  unsigned long long aa, bb, cc, rr;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(aa) : "f"(a.x), "f"(a.y));
+  asm("mov.b64 %0, {%1, %2};" : "=l"(bb) : "f"(b.x), "f"(b.y));
+  asm("mov.b64 %0, {%1, %2};" : "=l"(cc) : "f"(c.x), "f"(c.y));
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(rr) : "l"(aa), "l"(bb), "l"(cc));
+  f2 r;
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(r.x), "=f"(r.y) : "l"(rr));
+  return r;
+#else
+  return f2{fmaf(a.x, b.x, c.x), fmaf(a.y, b.y, c.y)};
+#endif
+}
+
 PINN_HD float fast_exp(float x) {
 #if defined(__CUDA_ARCH__)
   return __expf(x);

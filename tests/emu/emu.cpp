@@ -72,10 +72,10 @@ struct RunnerT : Runner {
 };
 
 #define ROW(H, A)                                                                                         \
-  {{new RunnerT<NarrowWarp<H, 0, 0, A>>, nullptr, nullptr, nullptr},                                      \
-   {new RunnerT<NarrowWarp<H, 1, 0, A>>, new RunnerT<NarrowWarp<H, 1, 1, A>>, nullptr, nullptr},          \
-   {new RunnerT<NarrowWarp<H, 2, 0, A>>, new RunnerT<NarrowWarp<H, 2, 1, A>>, new RunnerT<NarrowWarp<H, 2, 2, A>>, nullptr}, \
-   {new RunnerT<NarrowWarp<H, 3, 0, A>>, new RunnerT<NarrowWarp<H, 3, 1, A>>, new RunnerT<NarrowWarp<H, 3, 2, A>>, new RunnerT<NarrowWarp<H, 3, 3, A>>}}
+  {{new RunnerT<NarrowWarpFor<H, 0, 0, A>>, nullptr, nullptr, nullptr},                                      \
+   {new RunnerT<NarrowWarpFor<H, 1, 0, A>>, new RunnerT<NarrowWarpFor<H, 1, 1, A>>, nullptr, nullptr},          \
+   {new RunnerT<NarrowWarpFor<H, 2, 0, A>>, new RunnerT<NarrowWarpFor<H, 2, 1, A>>, new RunnerT<NarrowWarpFor<H, 2, 2, A>>, nullptr}, \
+   {new RunnerT<NarrowWarpFor<H, 3, 0, A>>, new RunnerT<NarrowWarpFor<H, 3, 1, A>>, new RunnerT<NarrowWarpFor<H, 3, 2, A>>, new RunnerT<NarrowWarpFor<H, 3, 3, A>>}}
 
 const Runner* lookup(int width, int act, int nf, int ns) {
   static const Runner* t20[3][4][4] = {ROW(20, PINN_ACT_TANH), ROW(20, PINN_ACT_SILU), ROW(20, PINN_ACT_SIN)};
