@@ -9,6 +9,7 @@
 
 #include "narrow_kernel.cuh"
 #include "select.cuh"
+#include "geometry.cuh"
 #include "wide.cuh"
 
 namespace pinn {
@@ -389,6 +390,42 @@ int pinn_topk_abs(const float* values, int64_t n, int32_t k, int64_t* idx_out, f
   if (ws_bytes < topk_workspace_bytes(k)) return fail(PINN_E_WORKSPACE, "workspace too small");
   const int rc = topk_abs(values, n, k, idx_out, val_out, ws, (cudaStream_t)stream);
   return rc > 0 ? cuda_fail((cudaError_t)rc, "top-k launch") : rc;
+}
+
+// ---- CSG sampling --------------------------------------------------------------------------
+int64_t pinn_sample_csg_workspace_bytes(int64_t n) { return n < 0 ? PINN_E_INVALID : csg_workspace_bytes(n); }
+
+int pinn_sample_csg(float* const* columns, int32_t n_dims, const float* lo, const float* hi, int64_t n, int64_t capacity,
+                    uint64_t seed, uint64_t stream_id, uint64_t offset, const pinn_shape_op* prog, int32_t n_ops, float* sdf,
+                    int64_t* count, void* ws, int64_t ws_bytes, void* stream) {
+  if (!columns || !lo || !hi || !prog || !count || !ws || n_dims < 1 || n_dims > PINN_MAX_IN || n < 0 || capacity < 0)
+    return fail(PINN_E_INVALID, "null or out-of-range argument");
+  if (n_ops < 1 || n_ops > PINN_MAX_SHAPE_OPS) return fail(PINN_E_UNSUPPORTED, "program of %d ops (max %d)", n_ops, PINN_MAX_SHAPE_OPS);
+  if (n >= ((int64_t)1 << 31) * 256) return fail(PINN_E_UNSUPPORTED, "too many candidates");
+  if (ws_bytes < csg_workspace_bytes(n)) return fail(PINN_E_WORKSPACE, "workspace too small");
+  int depth = 0;  // validate the stack program on the host: never below 1 operand, ends with exactly one, depth <= 8
+  for (int i = 0; i < n_ops; ++i) {
+    const int op = prog[i].op;
+    if (op >= PINN_SHAPE_INTERVAL && op <= PINN_SHAPE_SPHERE) {
+      const int need = (op == PINN_SHAPE_INTERVAL) ? (int)prog[i].p[2] + 1 : (op == PINN_SHAPE_BOX || op == PINN_SHAPE_SPHERE) ? 3 : 2;
+      if (need > n_dims || need < 1) return fail(PINN_E_INVALID, "op %d: primitive needs %d coordinates, have %d", i, need, n_dims);
+      ++depth;
+    } else if (op == PINN_CSG_UNION || op == PINN_CSG_DIFFERENCE || op == PINN_CSG_INTERSECTION) {
+      if (depth < 2) return fail(PINN_E_INVALID, "op %d: binary operator on %d operands", i, depth);
+      --depth;
+    } else if (op == PINN_CSG_COMPLEMENT) {
+      if (depth < 1) return fail(PINN_E_INVALID, "op %d: complement of nothing", i);
+    } else {
+      return fail(PINN_E_INVALID, "op %d: unknown opcode %d", i, op);
+    }
+    if (depth > 8) return fail(PINN_E_UNSUPPORTED, "CSG stack deeper than 8");
+  }
+  if (depth != 1) return fail(PINN_E_INVALID, "program leaves %d values on the stack", depth);
+  for (int d = 0; d < n_dims; ++d)
+    if (!columns[d]) return fail(PINN_E_INVALID, "null column");
+  const int rc = csg_sample(columns, n_dims, lo, hi, n, capacity, seed, stream_id, offset, prog, n_ops, sdf, count, ws,
+                            (cudaStream_t)stream);
+  return rc > 0 ? cuda_fail((cudaError_t)rc, "csg sampling launch") : rc;
 }
 
 }  // extern "C"

@@ -149,11 +149,28 @@ def _combine(kind: str, f, g):
     return lambda **x: op(lambdify_np(f, x)(**x), lambdify_np(g, x)(**x))
 
 
+def _program(tree) -> List[Tuple[str, Tuple[float, ...]]]:
+    """Post-order (op, params) list of a CSG tree: ("prim", name, params) | (op, left[, right])."""
+    if tree[0] == "prim":
+        return [(tree[1], tuple(float(v) for v in tree[2]))]
+    out = []
+    for sub in tree[1:]:
+        out += _program(sub)
+    return out + [(tree[0], ())]
+
+
 class Geometry:
     """A solid: `sdf` (positive inside), bounding box `bounds` and boundary `edges`."""
     edges: List[Edge] = None
     bounds: Dict = None
     sdf = None
+    # CSG tree over numeric primitives, kept while the solid is built from untransformed, non-symbolic
+    # shapes: lets `sample_interior_device` run the hand-written CSG kernel (pinn_sample_csg)
+    _tree = None
+
+    def _join(self, op: str, g: "Geometry", *others: "Geometry") -> None:
+        parts = (self,) + others
+        g._tree = (op,) + tuple(p._tree for p in parts) if all(p._tree is not None for p in parts) else None
 
     @property
     def axes(self) -> List[str]:
@@ -174,6 +191,7 @@ class Geometry:
     def translation(self, direction: Union[List, Tuple]) -> "Geometry":
         assert len(direction) == len(self.axes)
         self._need_symbolic_sdf()
+        self._tree = None
         for e in self.edges:
             e.translation(direction)
         self.sdf = self.sdf.subs([(Symbol(a), Symbol(a) - d) for a, d in zip(self.axes, direction)])
@@ -182,6 +200,7 @@ class Geometry:
 
     def rotation(self, angle: float, axis: str = "z", center=None) -> "Geometry":
         self._need_symbolic_sdf()
+        self._tree = None
         if center is not None:
             self.translation([-c for c in center])
         for e in self.edges:
@@ -199,6 +218,7 @@ class Geometry:
     def scaling(self, scale: float, center: Tuple = None) -> "Geometry":
         assert scale > 0, "scaling must be positive"
         self._need_symbolic_sdf()
+        self._tree = None
         if center is not None:
             self.translation(tuple(-c for c in center))
         for e in self.edges:
@@ -218,6 +238,7 @@ class Geometry:
         g.edges = self.edges + other.edges
         g.sdf = _combine("max", self.sdf, other.sdf)
         g.bounds = {k: (min(v[0], other.bounds[k][0]), max(v[1], other.bounds[k][1])) for k, v in self.bounds.items()}
+        self._join("union", g, other)
         return g
 
     def __sub__(self, other: "Geometry") -> "Geometry":
@@ -225,6 +246,7 @@ class Geometry:
         g.edges = self.edges + [e.inverted() for e in other.edges]
         g.sdf = _combine("min", self.sdf, _combine("neg", other.sdf, None))
         g.bounds = dict(self.bounds)
+        self._join("difference", g, other)
         return g
 
     def __and__(self, other: "Geometry") -> "Geometry":
@@ -232,6 +254,7 @@ class Geometry:
         g.edges = self.edges + other.edges
         g.sdf = _combine("min", self.sdf, other.sdf)
         g.bounds = {k: (max(v[0], other.bounds[k][0]), min(v[1], other.bounds[k][1])) for k, v in self.bounds.items()}
+        self._join("intersection", g, other)
         return g
 
     def __invert__(self) -> "Geometry":
@@ -239,6 +262,7 @@ class Geometry:
         g.edges = [e.inverted() for e in self.edges]
         g.sdf = _combine("neg", self.sdf, None)
         g.bounds = {k: (-float("inf"), float("inf")) for k in self.bounds}
+        self._join("complement", g)
         return g
 
     # -- sampling ---------------------------------------------------------------------------------
@@ -270,9 +294,11 @@ class Geometry:
 
     def sample_interior_device(self, density: int, seed: int = 0, offset: int = 0, bounds: Dict = None, sieve=None,
                                device=None):
-        """`sample_interior` on the GPU: Philox box sampling by pinn_sample_box, the signed distance
-        and the sieve evaluated by the same SymPy expressions lowered to torch, rejection by mask.
-        Returns a dict of [n, 1] float32 device tensors (coordinates, `sdf`, `area`)."""
+        """`sample_interior` on the GPU.  Candidates are the Philox points of pinn_sample_box in the bounding
+        box; a solid built from numeric primitives and CSG operators is evaluated and compacted by the
+        hand-written kernel (pinn_sample_csg: sdf program, ordered compaction, deterministic); anything else
+        (symbolic parameters, transformed solids, a `sieve`) falls back to the same SymPy expressions lowered
+        to torch.  Returns a dict of [n, 1] float32 device tensors (coordinates, `sdf`, `area`)."""
         import ctypes as C
 
         import torch
@@ -286,8 +312,28 @@ class Geometry:
         cols = [torch.empty(n, device=dev, dtype=torch.float32) for _ in names]
         lo = (C.c_float * len(names))(*[float(bounds[k][0]) for k in names])
         hi = (C.c_float * len(names))(*[float(bounds[k][1]) for k in names])
-        nv.check(nv.lib().pinn_sample_box(nv.ptr_array([c.data_ptr() for c in cols]), len(names), lo, hi, n, seed, 0,
-                                          offset, None, 0, torch.cuda.current_stream(dev).cuda_stream))
+        stream = torch.cuda.current_stream(dev).cuda_stream
+        lib = nv.lib()
+        if self._tree is not None and sieve is None and names == list(self.axes):
+            prog = _program(self._tree)
+            ops = (nv.PinnShapeOp * len(prog))()
+            for o, (name, params) in zip(ops, prog):
+                o.op = nv.SHAPE_OPS[name]
+                for i, v in enumerate(params):
+                    o.p[i] = v
+            sdf = torch.empty(n, device=dev, dtype=torch.float32)
+            count = torch.zeros(1, device=dev, dtype=torch.int64)
+            ws_bytes = lib.pinn_sample_csg_workspace_bytes(n)
+            ws = torch.empty(max(ws_bytes, 1), device=dev, dtype=torch.uint8)
+            nv.check(lib.pinn_sample_csg(nv.ptr_array([c.data_ptr() for c in cols]), len(names), lo, hi, n, n, seed, 0, offset,
+                                         ops, len(prog), sdf.data_ptr(), count.data_ptr(), ws.data_ptr(), ws_bytes, stream))
+            m = int(count.item())
+            out = {k: c[:m].reshape(-1, 1) for k, c in zip(names, cols)}
+            out["sdf"] = sdf[:m].reshape(-1, 1)
+            out["area"] = torch.full_like(out["sdf"], 1.0 / density)
+            return out
+        nv.check(lib.pinn_sample_box(nv.ptr_array([c.data_ptr() for c in cols]), len(names), lo, hi, n, seed, 0,
+                                     offset, None, 0, stream))
         pts = {k: c.reshape(-1, 1) for k, c in zip(names, cols)}
         if not isinstance(self.sdf, sympy.Basic):
             raise NotImplementedError("device sampling needs a symbolic sdf")

@@ -27,6 +27,10 @@ def _slab_sdf(coords: Sequence, centers: Sequence, halves: Sequence):
     return -(outside + inside)
 
 
+def _numeric(*values) -> bool:
+    return all(isinstance(v, (int, float)) for v in values)
+
+
 def _normals(axes: str, **nonzero) -> Dict[str, float]:
     return {"normal_" + a: nonzero.get(a, 0) for a in axes}
 
@@ -39,6 +43,8 @@ class Line1D(Geometry1D):
         half = (point_2 - point_1) / 2
         self.sdf = half - Abs(x - (point_1 + half))
         self.bounds = {"x": (point_1, point_2)}
+        if _numeric(point_1, point_2):
+            self._tree = ("prim", "interval", (point_1, point_2, 0))
 
 
 class Line(Geometry2D):
@@ -67,6 +73,8 @@ class Tube2D(Geometry2D):
         cy = point_1[1] + dy / 2
         self.sdf = _slab_sdf([y], [cy], [point_2[1] - cy])
         self.bounds = _box_bounds(point_1, point_2, "xy")
+        if _numeric(*point_1, *point_2):
+            self._tree = ("prim", "channel2d", (point_1[1], point_2[1]))
 
 
 class Rectangle(Geometry2D):
@@ -85,6 +93,8 @@ class Rectangle(Geometry2D):
         cx, cy = x0 + dx / 2, y0 + dy / 2
         self.sdf = _slab_sdf([x, y], [cx, cy], [x1 - cx, y1 - cy])
         self.bounds = _box_bounds(point_1, point_2, "xy")
+        if _numeric(x0, y0, x1, y1):
+            self._tree = ("prim", "rect", (x0, y0, x1, y1))
 
 
 class Circle(Geometry2D):
@@ -96,6 +106,8 @@ class Circle(Geometry2D):
                            {theta: (0, 2 * math.pi)}, 2 * pi * radius)]
         self.sdf = radius - sqrt((x - center[0]) ** 2 + (y - center[1]) ** 2)
         self.bounds = {"x": (center[0] - radius, center[0] + radius), "y": (center[1] - radius, center[1] + radius)}
+        if _numeric(*center, radius):
+            self._tree = ("prim", "circle", (center[0], center[1], radius))
 
 
 class Heart(Geometry2D):
@@ -258,6 +270,8 @@ class Box(Geometry3D):
         self.edges = _faces(centre, side, [(2, 1), (2, -1), (1, 1), (1, -1), (0, 1), (0, -1)])
         self.sdf = _slab_sdf(_XYZ, centre, [0.5 * s for s in side])
         self.bounds = _box_bounds(point_1, point_2)
+        if _numeric(*point_1, *point_2):
+            self._tree = ("prim", "box", tuple(point_1) + tuple(point_2))
 
 
 class Sphere(Geometry3D):
@@ -272,6 +286,8 @@ class Sphere(Geometry3D):
         self.edges = [Edge(fn, {v1: (0, 1), v2: (0, 1)}, 4 * pi * radius ** 2)]
         self.sdf = radius - sqrt((x - center[0]) ** 2 + (y - center[1]) ** 2 + (z - center[2]) ** 2)
         self.bounds = {a: (center[i] - radius, center[i] + radius) for i, a in enumerate("xyz")}
+        if _numeric(*center, radius):
+            self._tree = ("prim", "sphere", tuple(center) + (radius,))
 
 
 class Cylinder(Geometry3D):

@@ -77,6 +77,14 @@ def make_jets(first_in: Sequence[int], n_second: int) -> PinnJets:
     return j
 
 
+class PinnShapeOp(C.Structure):
+    _fields_ = [("op", C.c_int32), ("p", C.c_float * 6)]
+
+
+SHAPE_OPS = {"interval": 0, "rect": 1, "circle": 2, "channel2d": 3, "box": 4, "sphere": 5,
+             "union": 16, "difference": 17, "intersection": 18, "complement": 19}
+
+
 class PinnError(RuntimeError):
     def __init__(self, code: int, msg: str):
         super().__init__(f"libpinn_b200 error {code}: {msg}")
@@ -112,6 +120,10 @@ _SIGNATURES = {
     "pinn_topk_workspace_bytes": (C.c_int64, [C.c_int32]),
     "pinn_topk_abs": (C.c_int, [C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64,
                                 C.c_void_p]),
+    "pinn_sample_csg_workspace_bytes": (C.c_int64, [C.c_int64]),
+    "pinn_sample_csg": (C.c_int, [C.POINTER(_fp), C.c_int32, C.POINTER(C.c_float), C.POINTER(C.c_float), C.c_int64, C.c_int64,
+                                  C.c_uint64, C.c_uint64, C.c_uint64, C.POINTER(PinnShapeOp), C.c_int32, C.c_void_p, C.c_void_p,
+                                  C.c_void_p, C.c_int64, C.c_void_p]),
     "pinn_fp32_fma_probe": (C.c_int64, [C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]),
     "pinn_fp32_fma2_probe": (C.c_int64, [C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]),
     "pinn_tc_selftest": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),

@@ -238,6 +238,40 @@ PINN_API int64_t pinn_fp32_fma2_probe(int32_t iters, int32_t blocks, float* scra
 PINN_API int pinn_tc_selftest(int variant, int N, int K, const float* A, const float* B, float* D,
                               int* status, void* stream);
 
+/* ---- on-device sampling of CSG solids ----------------------------------- */
+/* A solid is a postfix program over signed distances (positive inside): primitives push one value
+ * (closed forms of idrlnet/geo_utils/geo_obj.py), operators combine the top of the stack as
+ * idrlnet/geo_utils/geo.py:246-300 does (union = max, difference = min(a, -b), intersection = min). */
+#define PINN_MAX_SHAPE_OPS 32
+enum {
+  PINN_SHAPE_INTERVAL = 0,  /* p = (x0, x1, axis)             Line1D            */
+  PINN_SHAPE_RECT = 1,      /* p = (x0, y0, x1, y1)           Rectangle         */
+  PINN_SHAPE_CIRCLE = 2,    /* p = (cx, cy, r)                Circle            */
+  PINN_SHAPE_CHANNEL2D = 3, /* p = (y0, y1)                   Tube2D            */
+  PINN_SHAPE_BOX = 4,       /* p = (x0, y0, z0, x1, y1, z1)   Box               */
+  PINN_SHAPE_SPHERE = 5,    /* p = (cx, cy, cz, r)            Sphere            */
+  PINN_CSG_UNION = 16,
+  PINN_CSG_DIFFERENCE = 17,
+  PINN_CSG_INTERSECTION = 18,
+  PINN_CSG_COMPLEMENT = 19
+};
+typedef struct pinn_shape_op {
+  int32_t op;
+  float p[6];
+} pinn_shape_op;
+
+/* Geometry.sample_interior on the device (idrlnet/geo_utils/geo.py:204-244): candidate i (0 <= i <
+ * n_candidates) is the point pinn_sample_box would draw for (seed, stream_id, offset + i) in the box
+ * [lo, hi); it is kept when the program's signed distance is > 0.  Survivors are written in candidate
+ * order to columns[d][0 .. *count) and sdf[0 .. *count) (sdf may be NULL); at most `capacity` are written
+ * and *count (DEVICE int64) is clamped to it.  `prog` is a HOST array.  Three launches, no atomics:
+ * the output is a deterministic function of the arguments. */
+PINN_API int64_t pinn_sample_csg_workspace_bytes(int64_t n_candidates);
+PINN_API int pinn_sample_csg(float* const* columns, int32_t n_dims, const float* lo, const float* hi,
+                    int64_t n_candidates, int64_t capacity, uint64_t seed, uint64_t stream_id, uint64_t offset,
+                    const pinn_shape_op* prog, int32_t n_ops, float* sdf, int64_t* count, void* workspace,
+                    int64_t workspace_bytes, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -98,6 +98,88 @@ def test_solver_residual_top_k_matches_infer_step(tmp_path):
     assert np.all(np.diff(np.abs(top["burgers_u"].cpu().numpy().ravel())) <= 0)
 
 
+def _host_reference(geo, density, seed, offset=0):
+    """Candidates of pinn_sample_box for the same (seed, offset), signed distance by the NumPy lowering of the
+    geometry's SymPy sdf (the reference's own evaluation path, float64)."""
+    import ctypes as C
+    from idrlnet_b200 import native as nv
+    from idrlnet_b200.geo_utils import lambdify_np
+    names = list(geo.bounds)
+    n = int(np.prod([hi - lo for lo, hi in geo.bounds.values()]) * density)
+    cols = [torch.empty(n, device="cuda") for _ in names]
+    lo = (C.c_float * len(names))(*[float(geo.bounds[k][0]) for k in names])
+    hi = (C.c_float * len(names))(*[float(geo.bounds[k][1]) for k in names])
+    nv.check(nv.lib().pinn_sample_box(nv.ptr_array([c.data_ptr() for c in cols]), len(names), lo, hi, n, seed, 0, offset,
+                                      None, 0, torch.cuda.current_stream().cuda_stream))
+    pts = {k: c.cpu().numpy().astype(np.float64).reshape(-1, 1) for k, c in zip(names, cols)}
+    return pts, lambdify_np(geo.sdf, names)(**pts)
+
+
+def _solids():
+    import idrlnet_b200.shortcut as sc
+    r, c = sc.Rectangle((-1.0, -1.0), (1.0, 1.0)), sc.Circle((0.2, 0.0), 0.5)
+    c2 = sc.Circle((-0.8, 0.9), 0.6)
+    return {
+        "rect_minus_circle": r - c,
+        "union": c + c2,
+        "intersection": r & c2,
+        "nested": (r - c) - (c2 & r),
+        "channel_minus_holes": sc.Tube2D((-1, -0.5), (1, 0.5)) - sc.Circle((-0.6, 0.0), 0.2) - sc.Circle((0.3, 0.1), 0.25),
+        "interval": sc.Line1D(-1.0, 2.5),
+        "box_and_sphere": sc.Box((-1, -1, 0), (1, 1, 1)) & sc.Sphere((0.0, 0.0, 0.2), 0.9),
+    }
+
+
+@pytest.mark.parametrize("name", ["rect_minus_circle", "union", "intersection", "nested", "channel_minus_holes", "interval",
+                                  "box_and_sphere"])
+def test_csg_kernel_matches_host_sdf(name):
+    """pinn_sample_csg: same Philox candidates as pinn_sample_box, kept iff sdf > 0, written in
+    candidate order; the signed distance agrees with the SymPy expression evaluated on the host in float64."""
+    geo = _solids()[name]
+    assert geo._tree is not None
+    density = 3000
+    got = geo.sample_interior_device(density, seed=5, offset=17)
+    again = geo.sample_interior_device(density, seed=5, offset=17)
+    pts, sdf = _host_reference(geo, density, 5, 17)
+    keep = sdf[:, 0] > 0
+    axes = list(geo.bounds)
+    near = np.abs(sdf[:, 0]) < 1e-6                      # float32 vs float64 may disagree on the sign only here
+    n_got = got[axes[0]].shape[0]
+    assert abs(n_got - keep.sum()) <= near.sum()
+    if near.sum() == 0:
+        for k in axes:
+            np.testing.assert_array_equal(got[k].cpu().numpy().ravel(), pts[k][keep, 0].astype(np.float32))   # order too
+        np.testing.assert_allclose(got["sdf"].cpu().numpy().ravel(), sdf[keep, 0], atol=2e-6)
+    assert (got["sdf"] > 0).all()
+    for k in got:
+        assert torch.equal(got[k], again[k])                                                                   # deterministic
+    assert torch.allclose(got["area"], torch.full_like(got["area"], 1.0 / density))
+
+
+def test_csg_kernel_rejects_bad_programs():
+    import ctypes as C
+    from idrlnet_b200 import native as nv
+    lib = nv.lib()
+    cols = [torch.empty(100, device="cuda") for _ in range(2)]
+    lo, hi = (C.c_float * 2)(-1, -1), (C.c_float * 2)(1, 1)
+    count = torch.zeros(1, dtype=torch.int64, device="cuda")
+    ws = torch.empty(64, dtype=torch.uint8, device="cuda")
+
+    def run(ops):
+        prog = (nv.PinnShapeOp * len(ops))()
+        for o, (op, p) in zip(prog, ops):
+            o.op = op
+            for i, v in enumerate(p):
+                o.p[i] = v
+        return lib.pinn_sample_csg(nv.ptr_array([c.data_ptr() for c in cols]), 2, lo, hi, 100, 100, 1, 0, 0, prog, len(ops),
+                                   None, count.data_ptr(), ws.data_ptr(), 64, torch.cuda.current_stream().cuda_stream)
+    assert run([(1, (-1, -1, 1, 1))]) == 0
+    assert run([(17, ())]) < 0                                   # operator without operands
+    assert run([(1, (-1, -1, 1, 1)), (2, (0, 0, 0.5))]) < 0     # two values left on the stack
+    assert run([(4, (0, 0, 0, 1, 1, 1))]) < 0                    # 3-D primitive with 2 coordinates
+    assert run([(99, ())]) < 0
+
+
 def test_device_geometry_sampler_matches_host_sdf():
     """SURVEY.md 8(f3): CSG solids sample on the GPU (Philox box points + SymPy sdf lowered to torch);
     the kept points are exactly those with sdf > 0 and their sdf agrees with the NumPy lowering."""
@@ -105,7 +187,8 @@ def test_device_geometry_sampler_matches_host_sdf():
     import idrlnet_b200.shortcut as sc
     from idrlnet_b200.geo_utils import lambdify_np
     x = sp.Symbol("x")
-    geo = sc.Rectangle((-1.0, -1.0), (1.0, 1.0)) - sc.Circle((0.2, 0.0), 0.5)
+    geo = (sc.Rectangle((-1.0, -1.0), (1.0, 1.0)) - sc.Circle((0.2, 0.0), 0.5)).translation((0.0, 0.0))  # no CSG tree: torch path
+    assert geo._tree is None
     a = geo.sample_interior_device(20000, seed=11)
     b = geo.sample_interior_device(20000, seed=11)
     c = geo.sample_interior_device(20000, seed=12, sieve=(x > 0))
