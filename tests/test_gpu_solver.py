@@ -100,3 +100,33 @@ def test_solver_tf32_precision_tracks_fp32(tmp_path):
         curves[prec] = torch.stack([s.train_pipe().reshape(()) for _ in range(100)]).cpu().numpy()
     rel = np.abs(curves["tf32"] - curves["fp32"]) / np.abs(curves["fp32"])
     assert 0 < rel.max() <= 2e-2, float(rel.max())
+
+
+def test_solver_trains_on_device_sampled_points(tmp_path):
+    """a datanode may return device tensors drawn by the CSG kernel; fresh points every step,
+    nothing sampled on the host, every domain on the fused kernels."""
+    import idrlnet_b200.shortcut as sc
+    geo = sc.Rectangle((-1.0, -1.0), (1.0, 1.0)) - sc.Circle((0.0, 0.0), 0.3)
+    state = {"step": 0}
+
+    @sc.datanode(name="interior")
+    class Interior(sc.SampleDomain):
+        def sampling(self, *args, **kwargs):
+            state["step"] += 1
+            pts = geo.sample_interior_device(2000, seed=3, offset=state["step"] * 8000)
+            return pts, {"diffusion_T": 1.0}
+
+    @sc.datanode(name="wall")
+    class Wall(sc.SampleDomain):
+        def sampling(self, *args, **kwargs):
+            return geo.sample_boundary(100), {"T": 0.0}
+
+    torch.manual_seed(0)
+    np.random.seed(0)
+    net = sc.get_net_node(inputs=("x", "y"), outputs=("T",), name="net1", arch=sc.Arch.mlp)
+    s = sc.Solver(sample_domains=(Interior(), Wall()), netnodes=[net],
+                  pdes=[sc.DiffusionNode(T="T", D=1.0, Q=0.0, dim=2, time=False)], network_dir=str(tmp_path), loading=False,
+                  max_iter=100)
+    assert sorted(s._fused_domains) == ["interior", "wall"]
+    losses = [float(s.train_pipe()) for _ in range(60)]
+    assert np.isfinite(losses).all() and np.mean(losses[-10:]) < 0.5 * np.mean(losses[:5])
