@@ -11,10 +11,12 @@
 //   (the weight-gradient GEMM dW_l = zbar_l^T H_{l-1} lives in wide_dw.cu)
 //
 // Operands are staged by the CTA's threads into the no-swizzle K-major canonical layout
-// (core matrix = 8 rows x 16 bytes), rounded to TF32 with cvt.rna; K is consumed in
-// chunks of 32 through a 2-stage smem ring whose slots are released by tcgen05.commit ->
-// mbarrier.  Inputs are FP32 in memory; only the multiplicands are rounded (10-bit
-// mantissa), sums are FP32: stated tolerance 2e-3 norm-wise on jets, see tests/test_gpu_wide_tc.py.
+// (core matrix = 8 rows x 16 bytes), rounded to TF32 with cvt.rna; K is consumed in chunks of 64
+// (32 with 3xTF32 splitting) through one smem stage released by tcgen05.commit -> mbarrier: the next
+// chunk's global loads are in flight in registers while the tensor core works, and two CTAs per SM
+// overlap each other's phases.  Inputs are FP32 in memory; only the multiplicands are rounded (10-bit
+// mantissa, or hi + lo pairs in 3xTF32 mode), sums are FP32.  Stated tolerance of the TF32 mode 1e-2
+// norm-wise (tests/test_gpu_wide_tc.py); the 3xTF32 mode is held to the FP32 bar (tests/test_gpu_wide.py).
 #include <cuda_runtime.h>
 #include <stdio.h>
 
