@@ -43,6 +43,17 @@ def peaks():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+def tensor_peak_tf32():
+    """Dense TF32 tensor throughput: half the BF16 cuBLAS figure (sustained: the kernels are timed inside a step)."""
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            d = json.load(f)
+        if "bf16_tflops_sustained" in d:
+            return d["bf16_tflops_sustained"] / 2, "TF32 = 1/2 of the measured sustained BF16 cuBLAS rate (MEASURED_PEAKS.json)"
+    return 2250.0 / 2 / 2, "fallback: 1/2 of half the nominal dense BF16 peak (B200_PROFILING.md)"
+
+
 # --------------------------------------------------------------------------- #
 # synthetic workloads (SURVEY.md 8(d2)); "burgers" is the headline (BASELINE configs[1])
 # --------------------------------------------------------------------------- #
@@ -113,7 +124,7 @@ def workload_configs():
                 ("burgers_equation", "int", {"x": "int_x", "t": "int_t"}, {"burgers_u": 0.0}, {}, lambda n: 2.0 / n["int"]),
                 ("x_boundary", "bc", {"x": "bc_x", "t": "bc_t"}, {"u": 0.0}, {}, lambda n: 2.0 / n["bc"]),
             ], timed=1, flop_per_point=_flop(2, 20, 4, 4, 4), bytes_per_point=8,
-            kernel="narrow_kernel<20,2,1,silu> (interior domain)", bound="fp32"),
+            kernel="narrow_kernel<NarrowWarpPair<20,2,1,silu>> (interior domain; channel pairs, packed FMAs)", bound="fp32"),
         "poisson": dict(
             title="simple_poisson (BASELINE configs[0])", net_desc="Arch.mlp 2-20x4-1 swish weight-norm",
             inputs=("x", "y"), outputs=("T",), oracle_act="silu",
@@ -564,6 +575,16 @@ def run_ours(args):
         hbm_peak, peak_src = peaks()
         fp32_peak = measure_fp32_peak(device)
         achieved = cfg["flop_per_point"] * n_timed / (kern_ms * 1e-3) / 1e12
+        if wide_tc:  # tensor-core kernels: the denominator is the TF32 tensor rate (a third of it under 3xTF32 splitting)
+            roof_peak, roof_src = tensor_peak_tf32()
+            if args.precision == "fp32x3":
+                roof_peak, roof_src = roof_peak / 3, roof_src + ", / 3 MMAs per product (3xTF32)"
+            roof_bound = "tensor"
+            roof_kernel = ("on-chip tcgen05 kernel wide_fused (interior domain)" if args.precision == "tf32" and trainer.pack.width <= 128
+                           else "tcgen05 tc_rows / tc_dw2 kernels (interior domain)")
+        else:
+            roof_peak, roof_src = fp32_peak, "FP32 FMA pipe, pinn_fp32_fma_probe measured in this run"
+            roof_bound, roof_kernel = cfg["bound"], cfg["kernel"]
         hbm_achieved = cfg["bytes_per_point"] * n_timed / (kern_ms * 1e-3) / 1e9
         cpu = None
         if world == 1 and not args.no_cpu_baseline:
@@ -582,11 +603,11 @@ def run_ours(args):
                        "net": f"{cfg['net_desc']}, Adam 1e-3 + ExponentialLR",
                        "points_per_step_per_gpu": pts_per_step, "parallelism": f"dp{world} (points sharded, 1 all-reduce)",
                        "l2": f"{n_rotate} rotating point batches ({n_rotate * batch_bytes / 1e6:.0f} MB > 126 MB L2)"},
-            "roofline": {"bound": cfg["bound"], "achieved": achieved, "peak": fp32_peak, "unit": "TFLOP/s",
-                         "frac": achieved / fp32_peak if fp32_peak else None, "traffic": ncu_traffic(args.config),
-                         "kernel": ("tcgen05 TF32 tc_rows/tc_dw kernels (interior domain)" if wide_tc else cfg["kernel"]),
-                         "kernel_ms": kern_ms, "flop_per_point": cfg["flop_per_point"],
-                         "peak_source": "FP32 FMA pipe, pinn_fp32_fma_probe measured in this run",
+            "roofline": {"bound": roof_bound, "achieved": achieved, "peak": roof_peak, "unit": "TFLOP/s",
+                         "frac": achieved / roof_peak if roof_peak else None,
+                         "traffic": None if wide_tc else ncu_traffic(args.config),
+                         "kernel": roof_kernel, "kernel_ms": kern_ms, "flop_per_point": cfg["flop_per_point"],
+                         "peak_source": roof_src, "fp32_fma_peak": fp32_peak,
                          "hbm": {"achieved": hbm_achieved, "peak": hbm_peak, "unit": "GB/s",
                                  "frac": hbm_achieved / hbm_peak, "peak_source": peak_src}},
             "cpu_baseline": cpu,
