@@ -1,6 +1,7 @@
 // extern "C" entry points of libpinn_b200.so (see include/pinn_b200.h).
 #include <cuda_runtime.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <stdarg.h>
 #include <string.h>
 
@@ -92,14 +93,18 @@ static DeviceInfo& device_info() {
 //                            [stash: MAX_CTA * 8 warps * stash_floats]
 // ----------------------------------------------------------------------------
 static const int kMaxCta = 160;  // >= SM count of a B200 (148); one persistent CTA per SM
-static const int kMaxWarps = 8;
+static const int kMaxWarps = 10;
 
 struct NarrowPlan {
   const NarrowKernelInfo* k;
   int Hp, L, PP, n_warps, smem_bytes, n_cta_cap;
   int64_t stash_floats_warp;
   int64_t head_bytes(int n_slots) const { return ((int64_t)kMaxCta * PP + (int64_t)n_slots * kMaxCta) * 4; }
+  // L2-resident scratch at the END of the workspace (offsets independent of the slot count): per-warp jet stash,
+  // preceded by the per-warp gradient accumulators
   int64_t stash_bytes() const { return (int64_t)kMaxCta * kMaxWarps * stash_floats_warp * 4; }
+  int64_t gacc_bytes() const { return (int64_t)kMaxCta * kMaxWarps * PP * 4; }
+  int64_t scratch_bytes() const { return stash_bytes() + gacc_bytes(); }
 };
 
 static int narrow_plan(const pinn_mlp* m, const pinn_jets* j, NarrowPlan* pl, bool need_device) {
@@ -120,6 +125,11 @@ static int narrow_plan(const pinn_mlp* m, const pinn_jets* j, NarrowPlan* pl, bo
   }
   int nw = (max_smem - lay.size() * 4) / (wf * 4);
   if (nw > kMaxWarps) nw = kMaxWarps;
+  if (nw > pl->k->max_warps) nw = pl->k->max_warps;
+  {  // tuning knob for occupancy experiments (profiles/r01/narrow_warps_sweep.txt)
+    static const int cap = getenv("PINN_NARROW_MAX_WARPS") ? atoi(getenv("PINN_NARROW_MAX_WARPS")) : 0;
+    if (cap > 0 && nw > cap) nw = cap;
+  }
   if (nw < 1) return fail(PINN_E_UNSUPPORTED, "net too deep for the narrow kernel (smem)");
   pl->n_warps = nw;
   pl->smem_bytes = (lay.size() + nw * wf) * 4;
@@ -223,7 +233,7 @@ int64_t pinn_workspace_bytes(const pinn_mlp* m, const pinn_jets* j, int32_t n_do
   if (narrow_lookup(m, j)) {
     NarrowPlan pl;
     if (narrow_plan(m, j, &pl, false)) return 0;
-    return pl.head_bytes(n_domains) + pl.stash_bytes();
+    return pl.head_bytes(n_domains) + pl.scratch_bytes();
   }
   return wide_workspace_bytes(m, j, n_domains);
 }
@@ -235,13 +245,14 @@ static int narrow_step_common(const pinn_mlp* m, const pinn_jets* j, NarrowParam
   if (rc) return rc;
   const int64_t gbytes = (int64_t)kMaxCta * pl.PP * 4;
   // the stash sits at the END of the workspace so that its offset does not depend on the slot count
-  if (!ws || ws_bytes < pl.head_bytes(n_slots_needed) + pl.stash_bytes())
+  if (!ws || ws_bytes < pl.head_bytes(n_slots_needed) + pl.scratch_bytes())
     return fail(PINN_E_WORKSPACE, "workspace too small: %lld bytes", (long long)ws_bytes);
   p.gpart = (float*)ws;
   p.lpart = (float*)((char*)ws + gbytes);
   p.stash = (float*)((char*)ws + (ws_bytes - pl.stash_bytes()));
+  p.gacc = (float*)((char*)ws + (ws_bytes - pl.scratch_bytes()));
   if (!accumulate) {
-    cudaError_t e = cudaMemsetAsync(ws, 0, (size_t)(ws_bytes - pl.stash_bytes()), st);
+    cudaError_t e = cudaMemsetAsync(ws, 0, (size_t)(ws_bytes - pl.scratch_bytes()), st);
     if (e != cudaSuccess) return cuda_fail(e, "cudaMemsetAsync(workspace)");
   }
   return launch_narrow(m, j, p, pl, st);

@@ -11,13 +11,13 @@ typedef void (*narrow_kernel_t)(const NarrowParams, int);
 
 struct NarrowKernelInfo {
   narrow_kernel_t fn;
-  int H, C;
+  int H, C, max_warps;
   int (*warp_floats)(int L);
   int (*stash_floats)(int L);
 };
 
 template <class NW>
-__global__ void __launch_bounds__(256, 1) narrow_kernel(const __grid_constant__ NarrowParams p, int Hreal) {
+__global__ void __launch_bounds__(NW::kMaxWarps * 32, 1) narrow_kernel(const __grid_constant__ NarrowParams p, int Hreal) {
   extern __shared__ __align__(16) float smem[];
   const int L = p.n_hidden;
   const Layout lay(NW::H, L);
@@ -28,11 +28,11 @@ __global__ void __launch_bounds__(256, 1) narrow_kernel(const __grid_constant__ 
   float* wm = smem + lay.size() + warp * wf;
   float* gs = p.stash + ((size_t)blockIdx.x * nwarps + warp) * NW::stash_floats(L);
 
+  float* g = p.gacc + ((size_t)blockIdx.x * nwarps + warp) * lay.size();  // this warp's gradient accumulators
+
   for (int i = tid; i < lay.size(); i += blockDim.x) smem[i] = stage_weight(p, Hreal, lay, i);
-  {
-    float* g = wm + NW::off_gacc();
+  if (p.mode != MODE_FWD)  // (the jets-only mode has no workspace)
     for (int i = lane; i < lay.size(); i += 32) g[i] = 0.f;
-  }
   __syncthreads();
 
   typename NW::Lane ln;
@@ -43,24 +43,24 @@ __global__ void __launch_bounds__(256, 1) narrow_kernel(const __grid_constant__ 
     for (int l = L + 1; l >= 2; --l) {
       NW::phase_backward(p, smem, wm, gs, lane, l, ln);
       __syncwarp();
-      if (l == L + 1) NW::phase_gemm_out(p, wm, lane);
-      else NW::phase_gemm_hidden(p, wm, lane, l);
+      if (l == L + 1) NW::phase_gemm_out(p, wm, g, lane);
+      else NW::phase_gemm_hidden(p, wm, g, lane, l);
       __syncwarp();
       NW::phase_store_zk(wm, lane, ln);
     }
     __syncwarp();
-    NW::phase_gemm_first(p, wm, lane);
+    NW::phase_gemm_first(p, wm, g, lane);
     __syncwarp();
   }
   if (p.mode == MODE_FWD) return;
 
   wm[NW::off_xs() + lane] = ln.loss;
-  __syncthreads();
+  __syncthreads();  // also orders this block's accumulator writes (global) before the reads below
   // per-CTA partial = sum over the CTA's warps, in warp order (deterministic)
   float* gp = p.gpart + (size_t)blockIdx.x * lay.size();
   for (int i = tid; i < lay.size(); i += blockDim.x) {
     float s = 0.f;
-    for (int w = 0; w < nwarps; ++w) s += smem[lay.size() + w * wf + NW::off_gacc() + i];
+    for (int w = 0; w < nwarps; ++w) s += p.gacc[((size_t)blockIdx.x * nwarps + w) * lay.size() + i];
     gp[i] += s;
   }
   if (p.mode == MODE_FUSED && tid == 0) {
@@ -76,15 +76,16 @@ __global__ void __launch_bounds__(256, 1) narrow_kernel(const __grid_constant__ 
 
 // One table per (H, ACT) translation unit: entries for every (NF, NS).
 #define PINN_NARROW_ENTRY(H, NF, NS, ACT) \
-  { narrow_kernel<NarrowWarpFor<H, NF, NS, ACT>>, H, 1 + NF + NS, &NarrowWarpFor<H, NF, NS, ACT>::warp_floats, \
+  { narrow_kernel<NarrowWarpFor<H, NF, NS, ACT>>, H, 1 + NF + NS, NarrowWarpFor<H, NF, NS, ACT>::kMaxWarps,       \
+    &NarrowWarpFor<H, NF, NS, ACT>::warp_floats, \
     &NarrowWarpFor<H, NF, NS, ACT>::stash_floats }
 
 #define PINN_NARROW_TABLE(NAME, H, ACT)                                          \
   const NarrowKernelInfo* NAME(int nf, int ns) {                                 \
     static const NarrowKernelInfo t[4][4] = {                                    \
-        {PINN_NARROW_ENTRY(H, 0, 0, ACT), {0, 0, 0, 0, 0}, {0, 0, 0, 0, 0}, {0, 0, 0, 0, 0}}, \
-        {PINN_NARROW_ENTRY(H, 1, 0, ACT), PINN_NARROW_ENTRY(H, 1, 1, ACT), {0, 0, 0, 0, 0}, {0, 0, 0, 0, 0}}, \
-        {PINN_NARROW_ENTRY(H, 2, 0, ACT), PINN_NARROW_ENTRY(H, 2, 1, ACT), PINN_NARROW_ENTRY(H, 2, 2, ACT), {0, 0, 0, 0, 0}}, \
+        {PINN_NARROW_ENTRY(H, 0, 0, ACT), {0, 0, 0, 0, 0, 0}, {0, 0, 0, 0, 0, 0}, {0, 0, 0, 0, 0, 0}}, \
+        {PINN_NARROW_ENTRY(H, 1, 0, ACT), PINN_NARROW_ENTRY(H, 1, 1, ACT), {0, 0, 0, 0, 0, 0}, {0, 0, 0, 0, 0, 0}}, \
+        {PINN_NARROW_ENTRY(H, 2, 0, ACT), PINN_NARROW_ENTRY(H, 2, 1, ACT), PINN_NARROW_ENTRY(H, 2, 2, ACT), {0, 0, 0, 0, 0, 0}}, \
         {PINN_NARROW_ENTRY(H, 3, 0, ACT), PINN_NARROW_ENTRY(H, 3, 1, ACT), PINN_NARROW_ENTRY(H, 3, 2, ACT), PINN_NARROW_ENTRY(H, 3, 3, ACT)}}; \
     if (nf < 0 || nf > 3 || ns < 0 || ns > nf) return nullptr;                   \
     return t[nf][ns].fn ? &t[nf][ns] : nullptr;                                  \

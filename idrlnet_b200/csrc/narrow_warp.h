@@ -54,6 +54,7 @@ struct NarrowParams {
   float* gpart;  // [max_cta][PP] gradient partials (padded layout, see Layout)
   float* lpart;  // [n_slots][max_cta] loss partials
   float* stash;  // [cta][warp][(L-1)*C*H*32] pre-activation jets of layers 2..L (L2-resident scratch)
+  float* gacc;   // [cta][warp][Layout] per-warp gradient accumulators (L2-resident scratch)
   int32_t max_cta, domain_slot;
   int32_t n_warps, n_tiles;
 };
@@ -77,17 +78,18 @@ struct NarrowWarp {
   static constexpr int H = H_, NF = NF_, NS = NS_, ACT = ACT_;
   static constexpr int C = 1 + NF + NS;
   static constexpr int H4 = H / 4;
+  static constexpr int kMaxWarps = 8;  // (10 warps fit in shared memory now, but at <= 200 registers they lose: profiles/r01/narrow_warps_sweep.txt)
   static_assert(H % 4 == 0, "hidden width must be a multiple of 4");
   static_assert(NS <= NF, "second-order channels need their first-order channel");
 
   // ---- per-warp shared memory carve-up (in floats) -----------------------
-  // [A: 32 rows of S][B: 32 rows of S][xs: 32 x 4][gacc: Layout]
+  // [A: 32 rows of S][B: 32 rows of S][xs: 32 x 4]; the per-warp gradient accumulators (Layout) live in an
+  // L2-resident global scratch so that shared memory holds 10 warps of row buffers
   PINN_HD static int S() { return row_stride(C * H); }
   PINN_HD static int off_a() { return 0; }
   PINN_HD static int off_b() { return 32 * S(); }
   PINN_HD static int off_xs() { return 2 * 32 * S(); }
-  PINN_HD static int off_gacc() { return off_xs() + 32 * 4; }
-  PINN_HD static int warp_floats(int L) { return off_gacc() + Layout(H, L).size(); }
+  PINN_HD static int warp_floats(int) { return off_xs() + 32 * 4; }
   // per-warp global stash (floats): [(l-2)][c][k4][lane][4]
   PINN_HD static int stash_floats(int L) { return (L - 1) * C * H * 32; }
   PINN_HD static int stash_off(int l, int c, int k4, int lane) { return (((l - 2) * C + c) * H4 + k4) * 128 + lane * 4; }
@@ -447,13 +449,12 @@ struct NarrowWarp {
 
   // ---- GEMM phases (cross-lane; run after __syncwarp) ----------------------
   // dWout[o][k] += sum_{n,c} ybar[n][c][o] * h_L[n][c][k];  dbout[o] += sum_n ybar[n][0][o]
-  PINN_HD static void phase_gemm_out(const NarrowParams& p, float* wm, int lane_id) {
+  PINN_HD static void phase_gemm_out(const NarrowParams& p, float* wm, float* g, int lane_id) {
     const int L = p.n_hidden;
     const Layout lay(H, L);
     const int s = S();
     const float* yb = wm + off_a();
     const float* hb = wm + off_b();
-    float* g = wm + off_gacc();
     const int T = p.n_out * H4;
     for (int t = lane_id; t < T; t += 32) {
       const int o = t / H4, kb = t % H4;
@@ -477,18 +478,21 @@ struct NarrowWarp {
   }
 
   // dW_l[j][k] += sum_{n,c} zbar_l[n][c][j] * h_{l-1}[n][c][k];  db_l[j] += sum_n zbar_l[n][0][j]
-  PINN_HD static void phase_gemm_hidden(const NarrowParams& p, float* wm, int lane_id, int l) {
+  PINN_HD static void phase_gemm_hidden(const NarrowParams& p, float* wm, float* g, int lane_id, int l) {
     const int L = p.n_hidden;
     const Layout lay(H, L);
     const int s = S();
     const float* A = wm + off_a();  // zbar_l
     const float* B = wm + off_b();  // h_{l-1}
-    float* g = wm + off_gacc();
     for (int t = lane_id; t < H4 * H4; t += 32) {
       const int ja = t / H4, kb = t % H4;
       f4 acc[4];  // acc[kk] = (j0..j3) for k = kb*4+kk
+      f4 gv[4];   // the accumulator tile is requested up front: its L2 latency hides behind the loop
 #pragma unroll
-      for (int kk = 0; kk < 4; ++kk) acc[kk] = f4{0.f, 0.f, 0.f, 0.f};
+      for (int kk = 0; kk < 4; ++kk) {
+        acc[kk] = f4{0.f, 0.f, 0.f, 0.f};
+        gv[kk] = ld4(g + lay.wh(l) + (kb * 4 + kk) * H + ja * 4);
+      }
 #if defined(__CUDA_ARCH__)
 #pragma unroll 2
 #endif
@@ -507,7 +511,7 @@ struct NarrowWarp {
 #pragma unroll
       for (int kk = 0; kk < 4; ++kk) {
         float* gp = g + lay.wh(l) + (kb * 4 + kk) * H + ja * 4;
-        f4 v = ld4(gp);
+        f4 v = gv[kk];
         v.x += acc[kk].x; v.y += acc[kk].y; v.z += acc[kk].z; v.w += acc[kk].w;
         st4(gp, v);
       }
@@ -526,13 +530,12 @@ struct NarrowWarp {
   }
 
   // dW1[j][d] += sum_n zbar_val[n][j] x_d[n] + [d == first_in[i]] sum_n zbar_i[n][j];  db1[j] += sum_n zbar_val[n][j]
-  PINN_HD static void phase_gemm_first(const NarrowParams& p, float* wm, int lane_id) {
+  PINN_HD static void phase_gemm_first(const NarrowParams& p, float* wm, float* g, int lane_id) {
     const int L = p.n_hidden;
     const Layout lay(H, L);
     const int s = S();
     const float* X = wm + off_a();  // zbar_1
     const float* xs = wm + off_xs();
-    float* g = wm + off_gacc();
     for (int j = lane_id; j < H; j += 32) {
       float ad[4] = {0.f, 0.f, 0.f, 0.f};
       float af[NF > 0 ? NF : 1];
@@ -574,14 +577,14 @@ struct NarrowWarpPair {
   static constexpr int C = 1 + NF + NS;
   static constexpr int CP = C / 2;
   static constexpr int H4 = H / 4;
+  static constexpr int kMaxWarps = 8;
   static_assert(C % 2 == 0, "channel pairs need an even channel count");
 
   PINN_HD static int S() { return row_stride(C * H); }
   PINN_HD static int off_a() { return 0; }
   PINN_HD static int off_b() { return 32 * S(); }
   PINN_HD static int off_xs() { return 2 * 32 * S(); }
-  PINN_HD static int off_gacc() { return off_xs() + 32 * 4; }
-  PINN_HD static int warp_floats(int L) { return off_gacc() + Layout(H, L).size(); }
+  PINN_HD static int warp_floats(int) { return off_xs() + 32 * 4; }
   // per-warp global stash (floats): [(l-2)][cp][k4][half][lane][4]
   PINN_HD static int stash_floats(int L) { return (L - 1) * C * H * 32; }
   PINN_HD static int stash_off(int l, int cp, int k4, int half, int lane) {
@@ -863,13 +866,12 @@ struct NarrowWarpPair {
       }
   }
 
-  PINN_HD static void phase_gemm_out(const NarrowParams& p, float* wm, int lane_id) {
+  PINN_HD static void phase_gemm_out(const NarrowParams& p, float* wm, float* g, int lane_id) {
     const int L = p.n_hidden;
     const Layout lay(H, L);
     const int s = S();
     const float* yb = wm + off_a();
     const float* hb = wm + off_b();
-    float* g = wm + off_gacc();
     const int T = p.n_out * H4;
     for (int t = lane_id; t < T; t += 32) {
       const int o = t / H4, kb = t % H4;
@@ -896,20 +898,22 @@ struct NarrowWarpPair {
     }
   }
 
-  PINN_HD static void phase_gemm_hidden(const NarrowParams& p, float* wm, int lane_id, int l) {
+  PINN_HD static void phase_gemm_hidden(const NarrowParams& p, float* wm, float* g, int lane_id, int l) {
     const int L = p.n_hidden;
     const Layout lay(H, L);
     const int s = S();
     const float* A = wm + off_a();  // zbar_l
     const float* B = wm + off_b();  // h_{l-1}
-    float* g = wm + off_gacc();
     for (int t = lane_id; t < H4 * H4; t += 32) {
       const int ja = t / H4, kb = t % H4;
       f2 acc[4][4];  // acc[kk][jj]: per-channel partial sums of dW[ja*4+jj][kb*4+kk]
+      f4 gv[4];      // the accumulator tile is requested up front: its L2 latency hides behind the loop
 #pragma unroll
-      for (int kk = 0; kk < 4; ++kk)
+      for (int kk = 0; kk < 4; ++kk) {
+        gv[kk] = ld4(g + lay.wh(l) + (kb * 4 + kk) * H + ja * 4);
 #pragma unroll
         for (int jj = 0; jj < 4; ++jj) acc[kk][jj] = f2{0.f, 0.f};
+      }
 #if defined(__CUDA_ARCH__)
 #pragma unroll 2
 #endif
@@ -928,7 +932,7 @@ struct NarrowWarpPair {
 #pragma unroll
       for (int kk = 0; kk < 4; ++kk) {
         float* gp = g + lay.wh(l) + (kb * 4 + kk) * H + ja * 4;
-        f4 v = ld4(gp);
+        f4 v = gv[kk];
         v.x += acc[kk][0].x + acc[kk][0].y; v.y += acc[kk][1].x + acc[kk][1].y;
         v.z += acc[kk][2].x + acc[kk][2].y; v.w += acc[kk][3].x + acc[kk][3].y;
         st4(gp, v);
@@ -947,13 +951,12 @@ struct NarrowWarpPair {
     }
   }
 
-  PINN_HD static void phase_gemm_first(const NarrowParams& p, float* wm, int lane_id) {
+  PINN_HD static void phase_gemm_first(const NarrowParams& p, float* wm, float* g, int lane_id) {
     const int L = p.n_hidden;
     const Layout lay(H, L);
     const int s = S();
     const float* X = wm + off_a();  // zbar_1
     const float* xs = wm + off_xs();
-    float* g = wm + off_gacc();
     for (int j = lane_id; j < H; j += 32) {
       float ad[4] = {0.f, 0.f, 0.f, 0.f};
       float af[NF > 0 ? NF : 1];

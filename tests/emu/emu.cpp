@@ -35,9 +35,11 @@ struct RunnerT : Runner {
     std::vector<typename NW::Lane> lanes((size_t)n_warps * 32);
     for (auto& l : lanes) l.loss = 0.f;
     std::vector<float> stash((size_t)n_warps * NW::stash_floats(L) + 4, 0.f);
+    std::vector<float> gacc((size_t)n_warps * lay.size(), 0.f);
     for (int warp = 0; warp < n_warps; ++warp) {
       float* wm = smem.data() + lay.size() + (size_t)warp * wf;
       float* gs = stash.data() + (size_t)warp * NW::stash_floats(L);
+      float* g = gacc.data() + (size_t)warp * lay.size();
       typename NW::Lane* ln = &lanes[(size_t)warp * 32];
       for (int64_t tile = (int64_t)cta * n_warps + warp; tile < p.n_tiles; tile += (int64_t)n_cta * n_warps) {
         for (int lane = 0; lane < 32; ++lane) NW::phase_forward(p, smem.data(), wm, gs, lane, tile, ln[lane]);
@@ -45,18 +47,18 @@ struct RunnerT : Runner {
         for (int l = L + 1; l >= 2; --l) {
           for (int lane = 0; lane < 32; ++lane) NW::phase_backward(p, smem.data(), wm, gs, lane, l, ln[lane]);
           for (int lane = 0; lane < 32; ++lane) {
-            if (l == L + 1) NW::phase_gemm_out(p, wm, lane);
-            else NW::phase_gemm_hidden(p, wm, lane, l);
+            if (l == L + 1) NW::phase_gemm_out(p, wm, g, lane);
+            else NW::phase_gemm_hidden(p, wm, g, lane, l);
           }
           for (int lane = 0; lane < 32; ++lane) NW::phase_store_zk(wm, lane, ln[lane]);
         }
-        for (int lane = 0; lane < 32; ++lane) NW::phase_gemm_first(p, wm, lane);
+        for (int lane = 0; lane < 32; ++lane) NW::phase_gemm_first(p, wm, g, lane);
       }
     }
     if (p.mode == MODE_FWD) return;
     for (int i = 0; i < lay.size(); ++i) {
       float s = 0.f;
-      for (int w = 0; w < n_warps; ++w) s += smem[lay.size() + (size_t)w * wf + NW::off_gacc() + i];
+      for (int w = 0; w < n_warps; ++w) s += gacc[(size_t)w * lay.size() + i];
       gpart_cta[i] += s;
     }
     if (p.mode == MODE_FUSED) {
