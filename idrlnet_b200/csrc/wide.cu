@@ -586,6 +586,17 @@ WideLayout make_layout(const WNet& n, int n_dom) {
   mc = mc / kBM * kBM;
   if (mc < 256) mc = 256;
   if (mc > 65536) mc = 65536;
+  if (n.precision) {
+    // tensor-core row GEMMs: one CTA per (P points, 128 units) tile, two CTAs per SM -> a wave is 2 * kBlocks CTAs.
+    // Shrink the chunk to a whole number of waves (4800 points of mlp_xl were 2.03 waves: a third of the last one idle).
+    const int P = tc_rows_points(n.C), units = (n.H + 127) / 128, wave = 2 * kBlocks;
+    int64_t tiles = mc / P * units;
+    if (tiles > wave) {
+      int64_t t = tiles / wave * wave;          // whole waves
+      while (t % units) t -= wave;              // ... that are also whole point tiles
+      if (t >= wave) mc = t / units * P;
+    }
+  }
   wl.Mc = (int)mc;
   wl.tiles = (n.H + kBN - 1) / kBN;
   int ns = tc_dw_splits(n.H);  // slot count (>= the FP32 kernel's split count)

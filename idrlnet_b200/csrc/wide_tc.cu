@@ -262,6 +262,10 @@ INST(PINN_ACT_SILU)
 INST(PINN_ACT_SIN)
 #undef INST
 
+int tc_rows_points(int C) {
+  return (C == 1) ? 256 : (C == 2) ? 128 : (C == 3) ? 80 : (C == 4) ? 64 : (C == 5) ? 48 : 32;  // TileCfg<C>::P
+}
+
 int tc_dw_splits(int H) {
   const int tiles = ((H + 127) / 128) * ((H + 255) / 256);
   int ns = 296 / tiles;  // two resident CTAs per SM
