@@ -258,8 +258,8 @@ static int narrow_step_common(const pinn_mlp* m, const pinn_jets* j, NarrowParam
   return launch_narrow(m, j, p, pl, st);
 }
 
-int pinn_step_fused(const pinn_mlp* m, const pinn_jets* j, const pinn_domain* dom, void* ws, int64_t ws_bytes,
-                    int32_t domain_slot, int32_t accumulate, void* stream) {
+static int step_or_loss(const pinn_mlp* m, const pinn_jets* j, const pinn_domain* dom, void* ws, int64_t ws_bytes,
+                        int32_t domain_slot, int32_t accumulate, bool loss_only, void* stream) {
   int rc = check_mlp(m, j);
   if (rc) return rc;
   if (!dom) return fail(PINN_E_INVALID, "null domain");
@@ -282,15 +282,25 @@ int pinn_step_fused(const pinn_mlp* m, const pinn_jets* j, const pinn_domain* do
   if (narrow_lookup(m, j)) {
     NarrowParams p;
     fill_net(p, m, j);
-    p.mode = MODE_FUSED;
+    p.mode = loss_only ? MODE_LOSS : MODE_FUSED;
     p.n_points = dom->n_points;
     for (int d = 0; d < m->n_in; ++d) p.coords[d] = dom->coords[d];
     p.dom = *dom;
     p.domain_slot = domain_slot;
     return narrow_step_common(m, j, p, ws, ws_bytes, domain_slot + 1, accumulate, st);
   }
-  if (wide_supported(m, j)) return wide_step_fused(m, j, dom, ws, ws_bytes, domain_slot + 1, domain_slot, accumulate, st);
+  if (wide_supported(m, j)) return wide_step_fused(m, j, dom, ws, ws_bytes, domain_slot + 1, domain_slot, accumulate, loss_only, st);
   return fail(PINN_E_UNSUPPORTED, "no fused kernel for width %d / act %d", m->width, m->act);
+}
+
+int pinn_step_fused(const pinn_mlp* m, const pinn_jets* j, const pinn_domain* dom, void* ws, int64_t ws_bytes,
+                    int32_t domain_slot, int32_t accumulate, void* stream) {
+  return step_or_loss(m, j, dom, ws, ws_bytes, domain_slot, accumulate, false, stream);
+}
+
+int pinn_loss_fused(const pinn_mlp* m, const pinn_jets* j, const pinn_domain* dom, void* ws, int64_t ws_bytes,
+                    int32_t domain_slot, int32_t accumulate, void* stream) {
+  return step_or_loss(m, j, dom, ws, ws_bytes, domain_slot, accumulate, true, stream);
 }
 
 int pinn_step_finalize(const pinn_mlp* m, const pinn_jets* j, void* ws, int64_t ws_bytes, int32_t n_domains,

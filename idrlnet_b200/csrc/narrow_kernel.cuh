@@ -39,7 +39,7 @@ __global__ void __launch_bounds__(NW::kMaxWarps * 32, 1) narrow_kernel(const __g
   ln.loss = 0.f;
   for (int64_t tile = (int64_t)blockIdx.x * nwarps + warp; tile < p.n_tiles; tile += (int64_t)gridDim.x * nwarps) {
     NW::phase_forward(p, smem, wm, gs, lane, tile, ln);
-    if (p.mode == MODE_FWD) continue;
+    if (p.mode == MODE_FWD || p.mode == MODE_LOSS) continue;
     for (int l = L + 1; l >= 2; --l) {
       NW::phase_backward(p, smem, wm, gs, lane, l, ln);
       __syncwarp();
@@ -58,12 +58,12 @@ __global__ void __launch_bounds__(NW::kMaxWarps * 32, 1) narrow_kernel(const __g
   __syncthreads();  // also orders this block's accumulator writes (global) before the reads below
   // per-CTA partial = sum over the CTA's warps, in warp order (deterministic)
   float* gp = p.gpart + (size_t)blockIdx.x * lay.size();
-  for (int i = tid; i < lay.size(); i += blockDim.x) {
+  for (int i = tid; i < lay.size() && p.mode != MODE_LOSS; i += blockDim.x) {
     float s = 0.f;
     for (int w = 0; w < nwarps; ++w) s += p.gacc[((size_t)blockIdx.x * nwarps + w) * lay.size() + i];
     gp[i] += s;
   }
-  if (p.mode == MODE_FUSED && tid == 0) {
+  if ((p.mode == MODE_FUSED || p.mode == MODE_LOSS) && tid == 0) {
     float s = 0.f;
     for (int w = 0; w < nwarps; ++w) {
       float sw_ = 0.f;

@@ -34,7 +34,7 @@
 
 namespace pinn {
 
-enum { MODE_FUSED = 0, MODE_FWD = 1, MODE_BWD = 2 };
+enum { MODE_FUSED = 0, MODE_FWD = 1, MODE_BWD = 2, MODE_LOSS = 3 };  // LOSS: forward + residual + loss, no reverse pass
 
 struct NarrowParams {
   // network
@@ -286,7 +286,7 @@ struct NarrowWarp {
             acc[c].x += w.x * hv; acc[c].y += w.y * hv; acc[c].z += w.z * hv; acc[c].w += w.w * hv;
           }
         }
-        if (p.mode != MODE_FWD) {
+        if (p.mode == MODE_FUSED || p.mode == MODE_BWD) {  // the stash only feeds the reverse pass
 #pragma unroll
           for (int c = 0; c < C; ++c) st4(gs + stash_off(l, c, j4, lane_id), acc[c]);
         }
@@ -340,7 +340,7 @@ struct NarrowWarp {
     }
 
     f4 yb[C];
-    if (p.mode == MODE_FUSED) {
+    if (p.mode == MODE_FUSED || p.mode == MODE_LOSS) {
       residual_loss(p, n, valid, x, y, yb, lane);
     } else {
 #pragma unroll
@@ -675,7 +675,7 @@ struct NarrowWarpPair {
             acc[cp][3] = fma2s(hin[cp][k], w.w, acc[cp][3]);
           }
         }
-        if (p.mode != MODE_FWD) {
+        if (p.mode == MODE_FUSED || p.mode == MODE_BWD) {  // the stash only feeds the reverse pass
 #pragma unroll
           for (int cp = 0; cp < CP; ++cp) {
             st4(gs + stash_off(l, cp, j4, 0, lane_id), f4{acc[cp][0].x, acc[cp][0].y, acc[cp][1].x, acc[cp][1].y});
@@ -738,7 +738,7 @@ struct NarrowWarpPair {
     }
 
     f4 yb[C];
-    if (p.mode == MODE_FUSED) {
+    if (p.mode == MODE_FUSED || p.mode == MODE_LOSS) {
       residual_loss(p, n, valid, x, y, yb, lane);
     } else {
 #pragma unroll

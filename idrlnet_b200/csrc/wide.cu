@@ -316,7 +316,7 @@ struct HeadArgs {
   const float* jets_bar;
   float* part;  // [block][O*H + O + 1]  (dWout, dbout, loss)
 };
-enum { W_MODE_FUSED = 0, W_MODE_FWD = 1, W_MODE_BWD = 2 };
+enum { W_MODE_FUSED = 0, W_MODE_FWD = 1, W_MODE_BWD = 2, W_MODE_LOSS = 3 };  // LOSS: FUSED without the reverse pass
 
 // out_layer: y[n][c][o] = sum_k Wout[o][k] h_L[c][n][k] + bout[o]*(c==0), FP32 (the output values feed
 // residuals with cancellations, so this small skinny product stays off the TF32 pipe).  One warp
@@ -673,7 +673,7 @@ int run_chunks(const WNet& n, const WideLayout& wl, float* ws, int mode, const p
     {
       HeadArgs ha;
       memset(&ha, 0, sizeof(ha));
-      ha.mode = mode;
+      ha.mode = mode == W_MODE_LOSS ? W_MODE_FUSED : mode;  // the head evaluates residual and loss as in the full step
       if (dom) ha.dom = *dom;
       ha.xs = xs;
       ha.n0 = n0;
@@ -694,7 +694,7 @@ int run_chunks(const WNet& n, const WideLayout& wl, float* ws, int mode, const p
     if (pb > kBlocks) pb = kBlocks;                                                                         \
     head_point_kernel<C_><<<pb, 256, 0, st>>>(n, ha, yb, m);                                                \
     count_launch(1);                                                                                        \
-    if (mode != W_MODE_FWD) {                                                                               \
+    if (mode != W_MODE_FWD && mode != W_MODE_LOSS) {                                                                 \
       head_bwd_kernel<ACT, C_><<<bgrid, 1024, 0, st>>>(n, yb, zl, hl, m, wl.Mc, ws + wl.head);               \
       count_launch(1);                                                                                      \
     }                                                                                                       \
@@ -708,7 +708,7 @@ int run_chunks(const WNet& n, const WideLayout& wl, float* ws, int mode, const p
       count_launch(1);
       CK(cudaGetLastError());
     }
-    if (mode == W_MODE_FWD) continue;
+    if (mode == W_MODE_FWD || mode == W_MODE_LOSS) continue;
     for (int l = L; l >= 2; --l) {
       float* zb = Z + (l - 1) * planes;        // zbar_l (in place of Z_l)
       const float* hprev = Hb + (l - 2) * planes;
@@ -762,16 +762,17 @@ int run_mode(const pinn_mlp* m, const pinn_jets* j, int mode, const pinn_domain*
   if (!accumulate && mode != W_MODE_FWD)  // clear every partial slot (all domains' loss slots included)
     CK(cudaMemsetAsync(w + wl.dw, 0, (size_t)(wl.wt - wl.dw) * 4, st));  // partial slots only (not the weight tiles)
   int rc = 0;
-  const bool on_chip = mode == W_MODE_FUSED && fused_wide_supported(n) && m->precision == PINN_PREC_TF32 &&
+  const bool stepping = mode == W_MODE_FUSED || mode == W_MODE_LOSS;
+  const bool on_chip = stepping && fused_wide_supported(n) && m->precision == PINN_PREC_TF32 &&
                        fused_wide_stash_floats(n) <= (int64_t)2 * n.L * n.C * wl.Mc * n.H;
   // weight preparation once per step: later domains of the same step (accumulate != 0) reuse it
-  const bool prep = !accumulate || mode != W_MODE_FUSED;
-  if (n.precision && mode != W_MODE_FWD && prep)
+  const bool prep = !accumulate || !stepping;
+  if (n.precision && mode != W_MODE_FWD && mode != W_MODE_LOSS && prep)
     for (int l = 2; l <= n.L; ++l) {
       rc = tc_transpose(n.W[l - 1], w + wl.wt + (size_t)(l - 2) * n.H * n.H, n.H, st);
       if (rc) return rc;
     }
-  if (n.precision == 1 && mode == W_MODE_FUSED && prep && n.H <= 128 && n.L >= 2) {
+  if (n.precision == 1 && stepping && prep && n.H <= 128 && n.L >= 2) {
     rc = fused_wide_prep(n, w + wl.wprep, st);
     if (rc) return rc;
   }
@@ -779,7 +780,7 @@ int run_mode(const pinn_mlp* m, const pinn_jets* j, int mode, const pinn_domain*
     // whole step on chip (wide_fused.cu); same partial slots, same finalize
     (void)0;
 #define RUNF(A)                                                                                                   \
-  rc = fused_wide_launch<A>(n, dom, w + wl.Z, w + wl.wprep, w + wl.dw, w + wl.db, w + wl.first, w + wl.head, wl.n_splits, st)
+  rc = fused_wide_launch<A>(n, dom, w + wl.Z, w + wl.wprep, w + wl.dw, w + wl.db, w + wl.first, w + wl.head, wl.n_splits, mode == W_MODE_LOSS, st)
     ACT_SWITCH(n.act, RUNF);
 #undef RUNF
     if (rc) return rc;
@@ -791,7 +792,7 @@ int run_mode(const pinn_mlp* m, const pinn_jets* j, int mode, const pinn_domain*
   ACT_SWITCH(n.act, RUN);
 #undef RUN
   if (rc) return rc;
-  if (mode == W_MODE_FUSED) {
+  if (stepping) {
     wide_collect_loss_kernel<<<1, 256, 0, st>>>(w, wl, n.n_out * n.H + n.n_out + 1, slot);
     count_launch(1);
   }
@@ -812,10 +813,10 @@ int64_t wide_workspace_bytes(const pinn_mlp* m, const pinn_jets* j, int n_domain
 }
 
 int wide_step_fused(const pinn_mlp* m, const pinn_jets* j, const pinn_domain* dom, void* ws, int64_t ws_bytes, int n_slots,
-                    int domain_slot, int accumulate, cudaStream_t st) {
+                    int domain_slot, int accumulate, bool loss_only, cudaStream_t st) {
   const float* coords[PINN_MAX_IN];
   for (int d = 0; d < PINN_MAX_IN; ++d) coords[d] = dom->coords[d];
-  return run_mode(m, j, W_MODE_FUSED, dom, dom->n_points, coords, nullptr, nullptr, ws, ws_bytes, n_slots, domain_slot,
+  return run_mode(m, j, loss_only ? W_MODE_LOSS : W_MODE_FUSED, dom, dom->n_points, coords, nullptr, nullptr, ws, ws_bytes, n_slots, domain_slot,
                   accumulate, st);
 }
 

@@ -36,7 +36,7 @@ struct FusedArgs {
   float* first_part;     // [kBlocks][8][H]
   float* head_part;      // [kBlocks][O*H + O + 1]
   int n_splits;
-  int first_launch;      // unused (slots are always accumulated)
+  int loss_only;         // forward + residual + loss only: no stash, no reverse sweep, no gradient partials
 };
 
 // G point groups: 128 * G threads, thread (unit j, group g) handles the kP / G points g * kP / G ... of the tile.
@@ -84,7 +84,7 @@ __global__ void __launch_bounds__(128 * G, 1) wide_fused_kernel(WNet net, const 
   uint32_t phase = 0, wphase = 0;
   // weight tiles are consumed in a fixed cyclic order per point tile: W_2 .. W_L, W_L^T .. W_2^T
   const uint32_t wbytes = (uint32_t)(Kq * 129 * 4 * sizeof(float));
-  const int n_seq = 2 * (L - 1);
+  const int n_seq = fa.loss_only ? (L - 1) : 2 * (L - 1);
   int wseq = 0;  // next tile to fetch (thread 0 only)
   auto fetch_weights = [&]() {  // thread 0: asynchronous bulk copy of the next weight tile into sW
     const int sidx = wseq % n_seq;
@@ -201,7 +201,7 @@ __global__ void __launch_bounds__(128 * G, 1) wide_fused_kernel(WNet net, const 
     }
     // ---- hidden layers 2..L: tensor-core GEMM + activation epilogue -------------------------
     for (int l = 2; l <= L; ++l) {
-      run_mma(false, 0, true);
+      run_mma(false, 0, !(fa.loss_only && l == L && tile + gridDim.x >= n_tiles));
       float v[C][kPP];
 #pragma unroll
       for (int c = 0; c < C; ++c) tc::tmem_ldn(tmem + lane_base + c * kP + grp * kPP, v[c]);
@@ -217,7 +217,7 @@ __global__ void __launch_bounds__(128 * G, 1) wide_fused_kernel(WNet net, const 
         jet_fwd_t<ACT, NF, NS, true>(z, h);
 #pragma unroll
         for (int c = 0; c < C; ++c) {
-          stash[(((size_t)(l - 2) * C + c) * kP + p) * 128 + j] = z[c];
+          if (!fa.loss_only) stash[(((size_t)(l - 2) * C + c) * kP + p) * 128 + j] = z[c];
           if (j < H8) sx_at(c * kP + p) = unit_ok ? (l == L ? h[c] : tc::to_tf32(h[c])) : 0.f;
         }
       }
@@ -270,6 +270,7 @@ __global__ void __launch_bounds__(128 * G, 1) wide_fused_kernel(WNet net, const 
       sG[tid] = g;  // [e][p]
     }
     __syncthreads();
+    if (fa.loss_only) continue;  // (uniform: every thread leaves together)
     // R2: thread (point p, output symbol id) gathers ybar[id] = sum_e g_e * d r_e / d sym[id] (same e, term, factor order
     // as the serial evaluation of the layer-streamed path)
     for (int item = tid; item < C * 4 * kP; item += kT) {
@@ -399,7 +400,7 @@ __global__ void __launch_bounds__(128 * G, 1) wide_fused_kernel(WNet net, const 
   // ---- flush: TMEM dW accumulators and per-unit register accumulators -> partial slots -----------
   __syncthreads();
   const bool any_tile = blockIdx.x < n_tiles;
-  if (any_tile) {
+  if (any_tile && !fa.loss_only) {
     tc::tc_fence_after();
     for (int l = 2; l <= L; ++l) {
       float* out = fa.dw_part + ((size_t)(l - 2) * fa.n_splits + blockIdx.x) * H * H;
@@ -497,9 +498,10 @@ int64_t fused_wide_stash_floats(const WNet& n) { return (int64_t)kBlocks * (n.L 
 
 template <int ACT>
 int fused_wide_launch(const WNet& n, const pinn_domain* dom, float* stash, const float* wt_base, float* dw_part, float* db_part,
-                      float* first_part, float* head_part, int n_splits, cudaStream_t st) {
+                      float* first_part, float* head_part, int n_splits, bool loss_only, cudaStream_t st) {
   FusedArgs fa;
   memset(&fa, 0, sizeof(fa));
+  fa.loss_only = loss_only ? 1 : 0;
   fa.dom = *dom;
   for (int d = 0; d < PINN_MAX_IN; ++d) fa.xs[d] = d < n.n_in ? dom->coords[d] : nullptr;
   fa.n_points = dom->n_points;
@@ -534,8 +536,8 @@ int fused_wide_launch(const WNet& n, const pinn_domain* dom, float* stash, const
   return (int)cudaGetLastError();
 }
 
-template int fused_wide_launch<PINN_ACT_TANH>(const WNet&, const pinn_domain*, float*, const float*, float*, float*, float*, float*, int, cudaStream_t);
-template int fused_wide_launch<PINN_ACT_SILU>(const WNet&, const pinn_domain*, float*, const float*, float*, float*, float*, float*, int, cudaStream_t);
-template int fused_wide_launch<PINN_ACT_SIN>(const WNet&, const pinn_domain*, float*, const float*, float*, float*, float*, float*, int, cudaStream_t);
+template int fused_wide_launch<PINN_ACT_TANH>(const WNet&, const pinn_domain*, float*, const float*, float*, float*, float*, float*, int, bool, cudaStream_t);
+template int fused_wide_launch<PINN_ACT_SILU>(const WNet&, const pinn_domain*, float*, const float*, float*, float*, float*, float*, int, bool, cudaStream_t);
+template int fused_wide_launch<PINN_ACT_SIN>(const WNet&, const pinn_domain*, float*, const float*, float*, float*, float*, float*, int, bool, cudaStream_t);
 
 }  // namespace pinn

@@ -163,7 +163,7 @@ int64_t fused_wide_wprep_floats(const WNet& n);
 int fused_wide_prep(const WNet& n, float* wprep, cudaStream_t st);
 template <int ACT>
 int fused_wide_launch(const WNet& n, const pinn_domain* dom, float* stash, const float* wt_base, float* dw_part, float* db_part,
-                      float* first_part, float* head_part, int n_splits, cudaStream_t st);
+                      float* first_part, float* head_part, int n_splits, bool loss_only, cudaStream_t st);
 
 // tensor-core GEMMs (wide_tc.cu)
 template <int ACT, int EPI>

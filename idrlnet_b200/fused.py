@@ -385,9 +385,11 @@ class StepEngine:
     def losses(self) -> torch.Tensor:
         return self.flat[self.pack.n_params:]
 
-    def launch(self, timed: Optional[Tuple[int, "torch.cuda.Event", "torch.cuda.Event"]] = None) -> None:
+    def launch(self, timed: Optional[Tuple[int, "torch.cuda.Event", "torch.cuda.Event"]] = None,
+               loss_only: bool = False) -> None:
         """Enqueue the step kernels on the current stream (no host sync).
-        `timed=(i, start, stop)` brackets domain i's kernel with CUDA events."""
+        `timed=(i, start, stop)` brackets domain i's kernel with CUDA events.  `loss_only` evaluates the
+        losses without the reverse pass (pinn_loss_fused); `grad` is then unspecified."""
         lib = nv.lib()
         st = _stream_ptr()
         pack = self.pack
@@ -396,8 +398,8 @@ class StepEngine:
         for i, d in enumerate(self.domains):
             if timed is not None and timed[0] == i:
                 timed[1].record()
-            nv.check(lib.pinn_step_fused(C.byref(mlp), C.byref(d.jets), C.byref(d.struct), self.ws.data_ptr(),
-                                         self.ws_bytes, i, 1 if i else 0, st))
+            fn = lib.pinn_loss_fused if loss_only else lib.pinn_step_fused
+            nv.check(fn(C.byref(mlp), C.byref(d.jets), C.byref(d.struct), self.ws.data_ptr(), self.ws_bytes, i, 1 if i else 0, st))
             if timed is not None and timed[0] == i:
                 timed[2].record()
         nv.check(lib.pinn_step_finalize(C.byref(mlp), C.byref(self.domains[0].jets), self.ws.data_ptr(), self.ws_bytes,

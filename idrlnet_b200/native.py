@@ -103,6 +103,8 @@ _SIGNATURES = {
     "pinn_last_error": (C.c_char_p, []),
     "pinn_step_fused": (C.c_int, [C.POINTER(PinnMlp), C.POINTER(PinnJets), C.POINTER(PinnDomain), C.c_void_p,
                                   C.c_int64, C.c_int32, C.c_int32, C.c_void_p]),
+    "pinn_loss_fused": (C.c_int, [C.POINTER(PinnMlp), C.POINTER(PinnJets), C.POINTER(PinnDomain), C.c_void_p,
+                                  C.c_int64, C.c_int32, C.c_int32, C.c_void_p]),
     "pinn_step_finalize": (C.c_int, [C.POINTER(PinnMlp), C.POINTER(PinnJets), C.c_void_p, C.c_int64, C.c_int32,
                                      C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]),
     "pinn_jet_forward": (C.c_int, [C.POINTER(PinnMlp), C.POINTER(PinnJets), C.c_int64, C.POINTER(_fp), C.c_void_p,

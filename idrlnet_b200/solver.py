@@ -290,7 +290,7 @@ class Solver(Notifier, Optimizable):
         engines = self._bind_fused(fused_names, in_var, true_out, lambda_out)
         dist = _dist()
         for eng in engines:
-            eng.launch()
+            eng.launch(loss_only=not grads)  # the post-update re-evaluation needs no reverse pass
             if dist is not None:
                 dist.all_reduce(eng.flat)
             for fd, l in zip(eng.domains, eng.losses):

@@ -161,6 +161,16 @@ PINN_API int pinn_step_fused(const pinn_mlp* mlp, const pinn_jets* jets, const p
                     void* workspace, int64_t workspace_bytes, int32_t domain_slot,
                     int32_t accumulate, void* stream);
 
+/* The loss of one domain WITHOUT the reverse pass: forward jets, residual, weighted loss into the domain's
+ * loss slot (same arguments and slot protocol as pinn_step_fused; finish with pinn_step_finalize for the losses --
+ * its gradient output is unspecified after loss-only calls, so do not mix the two kinds of call in one
+ * accumulate / finalize sequence).  Replaces the second,
+ * gradient-free evaluation every reference step ends with (idrlnet/solver.py:341-344: re-sample, forward,
+ * compute_loss -- the value train_pipe returns and logs): about a third of the cost of the full step. */
+PINN_API int pinn_loss_fused(const pinn_mlp* mlp, const pinn_jets* jets, const pinn_domain* domain,
+                    void* workspace, int64_t workspace_bytes, int32_t domain_slot, int32_t accumulate,
+                    void* stream);
+
 /* Deterministic reduction of the per-CTA partials:
  *   flat_grad[pinn_param_count] (+)= d(sum_d sigma_d*loss_d)/d(W,b)   (add_to_grad != 0 adds)
  *   losses[n_domains]            = loss_d (un-weighted by sigma, as

@@ -166,3 +166,38 @@ def test_device_sampler_matches_host_philox():
     x = host[0]
     assert x.min() >= -1.0 and x.max() < 1.0 and abs(x.mean()) < 0.01 and abs(x.var() - 1 / 3) < 0.01
     assert hsdf.min() > 0  # every sampled point is inside the rectangle
+
+
+def test_loss_only_mode_matches_the_full_step():
+    """pinn_loss_fused: forward + residual + loss without the reverse pass (idrlnet/solver.py:341-344) returns
+    bit-identical losses to the full step (the gradient output is unspecified then; the narrow kernel leaves it zero)."""
+    from idrlnet_b200 import fused
+    problem, _ = gu.load("burgers")
+    packs = pu.cuda_packs(problem)
+    doms = []
+    for d in problem["domains"]:
+        fd, pack = pu.bind_fused_domain(problem, d, packs)
+        doms.append(fd)
+    eng = fused.StepEngine(pack, doms)
+    eng.launch()
+    full = eng.losses.clone()
+    assert float(eng.grad.abs().max()) > 0
+    eng.launch(loss_only=True)
+    torch.cuda.synchronize()
+    assert torch.equal(eng.losses, full)
+    assert float(eng.grad.abs().max()) == 0.0
+    # wide nets: FP32 FMA streamed, 3xTF32 streamed and the on-chip TF32 kernel keep the same contract
+    problem, _ = gu.load("ldc")
+    for precision in ("fp32", "fp32x3", "tf32"):
+        packs = pu.cuda_packs(problem, precision=precision)
+        doms = []
+        for d in problem["domains"]:
+            fd, pack = pu.bind_fused_domain(problem, d, packs)
+            doms.append(fd)
+        eng = fused.StepEngine(pack, doms)
+        eng.launch()
+        full = eng.losses.clone()
+        assert float(eng.grad.abs().max()) > 0
+        eng.launch(loss_only=True)
+        torch.cuda.synchronize()
+        assert torch.equal(eng.losses, full), precision
