@@ -30,6 +30,20 @@ def _lambdify_np(expr, names):
     return lambda **kw: numpy.zeros_like(next(iter(kw.values()))) + fn(*[kw[n] for n in used])
 
 
+def _target_on_device(expr, input_vars, like: torch.Tensor) -> torch.Tensor:
+    try:  # a 0-d CPU tensor: broadcasts against device tensors and converts to float without a device sync
+        return torch.tensor(float(expr), dtype=torch.float32)
+    except (TypeError, ValueError):
+        pass
+    from .torch_util import torch_lambdify
+    e = sympy.sympify(expr)
+    used = [s.name for s in e.free_symbols]
+    cols = {n: (input_vars[n].detach() if isinstance(input_vars[n], torch.Tensor)
+                else torch.as_tensor(numpy.asarray(input_vars[n]), dtype=torch.float32, device=like.device)) for n in used}
+    out = torch_lambdify(used, e)(**cols)
+    return out if isinstance(out, torch.Tensor) else torch.full((1, 1), float(out), dtype=torch.float32, device=like.device)
+
+
 class DataNode(Node):
     counter = 0
 
@@ -52,12 +66,19 @@ class DataNode(Node):
         points; convert to tensors (idrlnet/data.py:75-97)."""
         input_vars, output_vars = self.sample_fn()
         output_vars = dict(output_vars)
+        on_device = next((v for v in input_vars.values() if isinstance(v, torch.Tensor)), None)
+        np_in = None
         for key, value in output_vars.items():
             if isinstance(value, (torch.Tensor, numpy.ndarray)):
                 continue
             try:
-                np_in = {k: (v.detach().cpu().numpy() if isinstance(v, torch.Tensor) else v)
-                         for k, v in input_vars.items()}
+                if on_device is not None:
+                    # points already live in tensors (e.g. drawn on the GPU): evaluate the target there instead of
+                    # copying every column to the host; a constant stays a 0-d scalar
+                    output_vars[key] = _target_on_device(value, input_vars, on_device)
+                    continue
+                if np_in is None:
+                    np_in = dict(input_vars)
                 output_vars[key] = _lambdify_np(value, list(np_in))(**np_in)
             except Exception:
                 logger.error("unsupported constraints type.")

@@ -229,6 +229,14 @@ class Solver(Notifier, Optimizable):
             return {d: Variables({k: v for k, v in var.items() if k in index[d]}) for d, var in samples.items()}
         return pick(self.invar_dict_index), pick(self.outvar_dict_index), pick(self.lambda_dict_index)
 
+    def _sigma(self, domain_name: str, device):
+        """The domain weight sigma: a python float when it is a constant (no per-step host-to-device copy),
+        the tensor itself when it is trainable (`var_sigma`)."""
+        sig = self.get_sample_domain(domain_name).sigma
+        if isinstance(sig, torch.Tensor):
+            return sig.to(device) if sig.requires_grad else float(sig)
+        return float(sig)
+
     def sample_variables_from_domains(self) -> DomainVariables:
         return {d.name: d.sample() for d in self.sample_domains}
 
@@ -298,13 +306,13 @@ class Solver(Notifier, Optimizable):
         ordered = {f"{d.name}_loss": comps[f"{d.name}_loss"] for d in self.sample_domains if f"{d.name}_loss" in comps}
         self.loss_component = Variables(ordered)
         self.notify(self, message={Signal.BEFORE_COMPUTE_LOSS: {**self.loss_component}})
-        loss = sum(self.get_sample_domain(k[:-5]).sigma.to(v.device) * v for k, v in ordered.items())
+        loss = sum(self._sigma(k[:-5], v.device) * v for k, v in ordered.items())
         self.notify(self, message={Signal.AFTER_COMPUTE_LOSS: {**self.loss_component, **{"total_loss": loss}}})
         if not grads:
             return loss.detach() if isinstance(loss, torch.Tensor) else loss
         self.notify(self, message={Signal.BEFORE_BACKWARD: "defaults"})
         if generic:
-            gen_loss = sum(self.get_sample_domain(n).sigma.to(comps[f"{n}_loss"].device) * comps[f"{n}_loss"]
+            gen_loss = sum(self._sigma(n, comps[f"{n}_loss"].device) * comps[f"{n}_loss"]
                            for n in generic)
             if isinstance(gen_loss, torch.Tensor) and gen_loss.requires_grad:
                 gen_loss.backward()
@@ -363,7 +371,7 @@ class Solver(Notifier, Optimizable):
         comps = self._loss_components(in_var, pred_out_sample, true_out, lambda_out)
         self.loss_component = Variables(comps)
         self.notify(self, message={Signal.BEFORE_COMPUTE_LOSS: {**self.loss_component}})
-        loss = sum(self.get_sample_domain(k[:-5]).sigma.to(v.device) * v for k, v in comps.items())
+        loss = sum(self._sigma(k[:-5], v.device) * v for k, v in comps.items())
         self.notify(self, message={Signal.AFTER_COMPUTE_LOSS: {**self.loss_component, **{"total_loss": loss}}})
         return loss
 
