@@ -61,7 +61,7 @@ __device__ __forceinline__ void issue_chunk(uint32_t tmem, uint32_t sA, uint32_t
 }
 
 template <int C, int ACT, int EPI, bool X3>
-__global__ void __launch_bounds__(256) tc_rows_kernel(WNet net, const float* __restrict__ Bsrc, const float* __restrict__ Aw,
+__global__ void __launch_bounds__(256, 2) tc_rows_kernel(WNet net, const float* __restrict__ Bsrc, const float* __restrict__ Aw,
                                                       const float* __restrict__ bias, float* __restrict__ Zio,
                                                       float* __restrict__ Hout, int m, int Mc, int a_rows) {
   using T = TileCfg<C>;
