@@ -150,3 +150,40 @@ def test_generic_path_reproduces_reference_golden(tmp_path):
     for pname, g in gu.ref_grads(flat, "ref32").items():
         p = dict(net.named_parameters())[pname.split("/", 1)[1]]
         assert np.max(np.abs(p.grad.numpy().reshape(g.shape) - g)) <= 2e-4 * np.max(np.abs(g)), pname
+
+
+def test_datanode_targets_for_tensor_points_stay_off_the_host_path():
+    """Points that arrive as tensors get their targets evaluated with torch (no numpy round trip): constants stay 0-d
+    scalars, SymPy targets become [N, 1] tensors with the values the numpy path gives."""
+    xs = torch.linspace(-1.0, 1.0, 11).reshape(-1, 1)
+    x = sp.Symbol("x")
+
+    @sc.datanode(name="tensor_points")
+    class Dom(sc.SampleDomain):
+        def sampling(self, *args, **kwargs):
+            return {"x": xs, "area": torch.full_like(xs, 0.1)}, {"u": 0.25, "v": -sp.sin(sp.pi * x), "lambda_u": 100.0}
+
+    out = Dom().sample()
+    assert out["u"].dim() == 0 and float(out["u"]) == 0.25 and out["u"].device.type == "cpu"
+    assert float(out["lambda_u"]) == 100.0
+    np.testing.assert_allclose(out["v"].detach().numpy().ravel(), -np.sin(np.pi * xs.numpy().ravel()), atol=1e-6)
+
+    @sc.datanode(name="numpy_points")
+    class DomNp(sc.SampleDomain):
+        def sampling(self, *args, **kwargs):
+            return {"x": xs.numpy(), "area": np.full_like(xs.numpy(), 0.1)}, {"u": 0.25, "v": -sp.sin(sp.pi * x)}
+
+    ref = DomNp().sample()
+    assert tuple(ref["u"].shape) == (11, 1)                      # the reference's shape for host-sampled points
+    np.testing.assert_allclose(ref["v"].detach().numpy(), out["v"].detach().numpy(), atol=1e-6)
+
+
+def test_csg_tree_is_tracked_for_the_device_sampler():
+    from idrlnet_b200.geo_utils.geo import _program
+    r, c = sc.Rectangle((-1.0, -1.0), (1.0, 1.0)), sc.Circle((0.2, 0.0), 0.5)
+    assert _program((r - c)._tree) == [("rect", (-1.0, -1.0, 1.0, 1.0)), ("circle", (0.2, 0.0, 0.5)), ("difference", ())]
+    assert _program((~(r & c))._tree)[-2:] == [("intersection", ()), ("complement", ())]
+    assert sc.Circle((0.0, 0.0), sp.Symbol("r"))._tree is None          # symbolic parameter: torch-lowered fallback
+    assert (r - sc.Circle((0.0, 0.0), sp.Symbol("r")))._tree is None
+    assert sc.Rectangle((0.0, 0.0), (1.0, 1.0)).scaling(2.0)._tree is None
+    assert sc.Polygon([(0, 0), (1, 0), (0, 1)])._tree is None
