@@ -43,7 +43,7 @@ struct RunnerT : Runner {
       typename NW::Lane* ln = &lanes[(size_t)warp * 32];
       for (int64_t tile = (int64_t)cta * n_warps + warp; tile < p.n_tiles; tile += (int64_t)n_cta * n_warps) {
         for (int lane = 0; lane < 32; ++lane) NW::phase_forward(p, smem.data(), wm, gs, lane, tile, ln[lane]);
-        if (p.mode == MODE_FWD) continue;
+        if (p.mode == MODE_FWD || p.mode == MODE_LOSS) continue;
         for (int l = L + 1; l >= 2; --l) {
           for (int lane = 0; lane < 32; ++lane) NW::phase_backward(p, smem.data(), wm, gs, lane, l, ln[lane]);
           for (int lane = 0; lane < 32; ++lane) {
@@ -56,12 +56,12 @@ struct RunnerT : Runner {
       }
     }
     if (p.mode == MODE_FWD) return;
-    for (int i = 0; i < lay.size(); ++i) {
+    for (int i = 0; i < lay.size() && p.mode != MODE_LOSS; ++i) {
       float s = 0.f;
       for (int w = 0; w < n_warps; ++w) s += gacc[(size_t)w * lay.size() + i];
       gpart_cta[i] += s;
     }
-    if (p.mode == MODE_FUSED) {
+    if (p.mode == MODE_FUSED || p.mode == MODE_LOSS) {
       float s = 0.f;
       for (int w = 0; w < n_warps; ++w) {
         float sw = 0.f;
@@ -106,7 +106,8 @@ void fill(NarrowParams& p, const pinn_mlp* m, const pinn_jets* j) {
 
 extern "C" {
 
-// mode 0: fused (dom, flat_grad += , loss_out +=); mode 1: jets_out; mode 2: jets_bar -> flat_grad +=
+// mode 0: fused (dom, flat_grad += , loss_out +=); mode 1: jets_out; mode 2: jets_bar -> flat_grad +=;
+// mode 3: loss only (dom, loss_out +=)
 __attribute__((visibility("default"))) int pinn_emu_run(const pinn_mlp* m, const pinn_jets* j, int mode,
                                                         const pinn_domain* dom, int64_t n_points,
                                                         const float* const* coords, float* jets_out,
@@ -117,7 +118,7 @@ __attribute__((visibility("default"))) int pinn_emu_run(const pinn_mlp* m, const
   NarrowParams p;
   fill(p, m, j);
   p.mode = mode;
-  if (mode == MODE_FUSED) {
+  if (mode == MODE_FUSED || mode == MODE_LOSS) {
     p.dom = *dom;
     n_points = dom->n_points;
     for (int d = 0; d < m->n_in; ++d) p.coords[d] = dom->coords[d];
@@ -140,7 +141,7 @@ __attribute__((visibility("default"))) int pinn_emu_run(const pinn_mlp* m, const
     for (int c = 0; c < n_cta; ++c) s += gpart[(size_t)c * lay.size() + idx];
     flat_grad[i] += s;
   }
-  if (mode == MODE_FUSED && loss_out) {
+  if ((mode == MODE_FUSED || mode == MODE_LOSS) && loss_out) {
     float s = 0.f;
     for (int c = 0; c < n_cta; ++c) s += lpart[c];
     *loss_out += s;

@@ -94,7 +94,7 @@ def compile_problem_domain(problem, dom):
     return cp.compile_domain(list(dom["targets"].keys()), problem.get("exprs", {}), net_specs(problem), list(cols))
 
 
-def run_emu_fused(problem, n_cta=3, n_warps=2):
+def run_emu_fused(problem, n_cta=3, n_warps=2, mode=0):
     """Every fusable domain through the emulator.  Returns
     {net: flat grad}, {domain: loss}, [names of domains that were not fusable]."""
     lib = emu_lib()
@@ -135,7 +135,7 @@ def run_emu_fused(problem, n_cta=3, n_warps=2):
         if owner not in grads:
             grads[owner] = np.zeros(sum(flat_layout_sizes(layers)), np.float32)
         loss = np.zeros(1, np.float32)
-        rc = lib.pinn_emu_run(C.byref(mlp), C.byref(jets), 0, C.byref(d), n, None, None, None,
+        rc = lib.pinn_emu_run(C.byref(mlp), C.byref(jets), mode, C.byref(d), n, None, None, None,
                               grads[owner].ctypes.data, loss.ctypes.data, n_cta, n_warps)
         assert rc == 0, rc
         losses[dom["name"]] = float(loss[0])

@@ -100,3 +100,12 @@ def test_emu_empty_and_tiny_domains():
         else:
             ref = po.training_step(problem, dtype=torch.float64)
             _check_grads(ref, grads, problem)
+
+
+def test_emu_loss_only_mode():
+    """MODE_LOSS (pinn_loss_fused): the same losses as the full step, no gradient."""
+    problem, _ = gu.load("burgers")
+    g_full, l_full, _ = pu.run_emu_fused(problem)
+    g_loss, l_loss, _ = pu.run_emu_fused(problem, mode=3)
+    assert l_loss == l_full
+    assert all(np.abs(g).max() > 0 for g in g_full.values()) and all(np.abs(g).max() == 0 for g in g_loss.values())
