@@ -10,7 +10,7 @@ from __future__ import annotations
 import enum
 import math
 from collections import OrderedDict
-from typing import List, Sequence, Tuple, Union
+from typing import List, Sequence, Union
 
 import torch
 

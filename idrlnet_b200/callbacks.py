@@ -5,7 +5,6 @@ training step never synchronises the device just to log a scalar."""
 import os
 from typing import Dict
 
-import torch
 
 from .receivers import Receiver, Signal
 from .variable import Variables

@@ -15,7 +15,7 @@ takes the generic path (jets from the kernel, residual in torch) or plain torch.
 from __future__ import annotations
 
 from dataclasses import dataclass, field
-from typing import Callable, Dict, List, Mapping, Optional, Sequence, Tuple, Union
+from typing import Callable, List, Mapping, Sequence, Tuple, Union
 
 import sympy
 

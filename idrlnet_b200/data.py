@@ -3,7 +3,7 @@ supply the [N,1] FP32 columns (coordinates, normals, sdf, area) and targets."""
 import abc
 import functools
 import inspect
-from typing import Callable, List, Tuple, Union
+from typing import Callable, List, Tuple
 
 import numpy
 import sympy

@@ -11,7 +11,7 @@ solid); solids additionally sample on the GPU (`sample_interior_device`)."""
 import copy
 import itertools
 import math
-from typing import Callable, Dict, List, Optional, Tuple, Union
+from typing import Dict, List, Optional, Tuple, Union
 
 import numpy as np
 import sympy

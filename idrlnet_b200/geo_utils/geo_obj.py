@@ -2,7 +2,7 @@
 numbers or SymPy symbols that are later sampled through `param_ranges`.  Edge order, parameter
 names and range order are part of the contract: they fix how the global NumPy RNG is consumed."""
 import math
-from typing import Dict, List, Sequence, Tuple, Union
+from typing import Dict, Sequence, Tuple
 
 import numpy as np
 from sympy import Abs, Heaviside, Max, Min, Symbol, asin, cos, pi, sign, sin, sqrt, symbols

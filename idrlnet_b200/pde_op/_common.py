@@ -1,9 +1,5 @@
 """Helpers shared by equations.py and operator.py."""
-from typing import Union
-
-from sympy import Function, Number, Symbol, symbols
-
-from ..pde import PdeNode
+from sympy import Function, Number, symbols
 
 _X, _Y, _Z, _T = symbols("x y z t")
 

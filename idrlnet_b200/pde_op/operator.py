@@ -10,7 +10,7 @@ from ..node import Node
 from ..pde import PdeNode
 from ..torch_util import _replace_derivatives, integral, torch_lambdify
 from ..variable import Variables
-from ._common import _X, _Y, _Z, _coords, _field
+from ._common import _X, _Y, _Z, _coords
 
 __all__ = ["NormalGradient", "Difference", "Derivative", "Curl", "Divergence", "ICNode", "Int1DNode", "IntEq"]
 

@@ -1,7 +1,6 @@
 import sys, torch, numpy as np
 import os; sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import bench
-from idrlnet_b200 import fused
 for config, prec in (("burgers", "fp32"), ("ldc", "tf32"), ("ldc", "fp32x3")):
     dev = torch.device("cuda:0")
     tr = bench.Trainer(bench.workload_configs()[config], dev, precision=prec)
