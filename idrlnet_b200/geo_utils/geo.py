@@ -76,6 +76,20 @@ def _ranged_sample(n: int, ranges: Dict, low_discrepancy: bool = False) -> Dict[
     return {k: np.asarray(v, dtype=np.float64) for k, v in out.items()}
 
 
+def _ranged_sample_quiet(n: int, ranges: Dict) -> Dict[str, np.ndarray]:
+    """`_ranged_sample` on a private generator: does not disturb the global NumPy stream."""
+    rng = np.random.default_rng(0)
+    out = {}
+    for key, value in ranges.items():
+        if isinstance(value, (float, int)):
+            out[_key(key)] = np.ones((n, 1)) * value
+        elif isinstance(value, tuple):
+            out[_key(key)] = rng.uniform(value[0], value[1], size=(n, 1))
+        else:
+            out[_key(key)] = np.asarray(value(n), dtype=np.float64)
+    return out
+
+
 class Edge:
     """A boundary piece: coordinates and normals as functions of its parameters, with the
     parameter ranges and its measure (`area`, possibly symbolic in shape parameters)."""
@@ -347,6 +361,68 @@ class Geometry:
         out["sdf"] = sdf[mask]
         out["area"] = torch.full_like(out["sdf"], 1.0 / density)
         return out
+
+
+    def sample_boundary_device(self, density: int, seed: int = 0, offset: int = 0, sieve=None, param_ranges: Dict = None,
+                               device=None):
+        """`sample_boundary` on the GPU: per edge, `int(density * measure)` Philox parameter draws
+        (pinn_sample_box), the edge's coordinate / normal expressions and the solid's signed distance lowered
+        to torch, then the reference's sieve (|sdf| < 1e-4 and the user's criterion).  Returns [n, 1] float32
+        device tensors with the same keys as `sample_boundary`."""
+        import ctypes as C
+
+        import torch
+
+        from .. import native as nv
+        from ..torch_util import torch_lambdify
+        dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        param_ranges = {} if param_ranges is None else param_ranges
+        stream = torch.cuda.current_stream(dev).cuda_stream if dev.type == "cuda" else None
+        lib = nv.lib()
+        parts = []
+        for e_idx, edge in enumerate(self.edges):
+            ranges = {**edge.ranges, **param_ranges}
+            names = [_key(k) for k in ranges]
+            area_fn = lambdify_np(edge.area, names)
+            n = int(density * np.mean(area_fn(**_ranged_sample_quiet(100, ranges))))   # host probe of the measure only
+            params = {}
+            drawn = [(k, v) for k, v in ranges.items() if isinstance(v, tuple)]
+            for g0 in range(0, len(drawn), 4):  # the box sampler draws up to 4 columns per call
+                grp = drawn[g0:g0 + 4]
+                cols = [torch.empty(n, device=dev, dtype=torch.float32) for _ in grp]
+                lo = (C.c_float * len(grp))(*[float(v[0]) for _, v in grp])
+                hi = (C.c_float * len(grp))(*[float(v[1]) for _, v in grp])
+                nv.check(lib.pinn_sample_box(nv.ptr_array([c.data_ptr() for c in cols]), len(grp), lo, hi, n, seed,
+                                             1 + e_idx * 16 + g0 // 4, offset, None, 0, stream))
+                for (k, _), c in zip(grp, cols):
+                    params[_key(k)] = c.reshape(-1, 1)
+            for k, v in ranges.items():
+                if isinstance(v, (int, float)):
+                    params[_key(k)] = torch.full((n, 1), float(v), device=dev)
+                elif not isinstance(v, tuple):
+                    params[_key(k)] = torch.as_tensor(np.asarray(v(n)), dtype=torch.float32, device=dev).reshape(-1, 1)
+            like = torch.zeros((n, 1), device=dev)
+
+            def column(expr):
+                out = torch_lambdify(names, expr)(**{k: params[k] for k in names})
+                return out + like if isinstance(out, torch.Tensor) else like + float(out)
+            pts = {"area": column(edge.area) / max(n, 1)}
+            for k, fn in edge.functions.items():
+                pts[k] = column(fn)
+            for k in param_ranges:
+                pts[_key(k)] = params[_key(k)]
+            parts.append(pts)
+        points = {k: torch.cat([p[k] for p in parts], dim=0) for k in parts[0]}
+        if not isinstance(self.sdf, sympy.Basic):
+            raise NotImplementedError("device sampling needs a symbolic sdf")
+        keys = list(points)
+        sdf = torch_lambdify(keys, self.sdf)(**points)
+        points["sdf"] = sdf + torch.zeros_like(points[keys[0]]) if isinstance(sdf, torch.Tensor) else torch.zeros_like(points[keys[0]]) + float(sdf)
+        keep = (points["sdf"] > -1e-4) & (points["sdf"] < 1e-4)
+        if sieve is not None:
+            keep = keep & torch_lambdify(list(points), sieve)(**points)
+        mask = keep[:, 0]
+        return {k: v[mask] for k, v in points.items()}
 
 
 class Geometry1D(Geometry):

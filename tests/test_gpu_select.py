@@ -200,3 +200,32 @@ def test_device_geometry_sampler_matches_host_sdf():
     host = lambdify_np(geo.sdf, ["x", "y"])(x=a["x"].cpu().numpy().astype(np.float64), y=a["y"].cpu().numpy().astype(np.float64))
     np.testing.assert_allclose(a["sdf"].cpu().numpy(), host, atol=2e-6)
     assert torch.allclose(a["area"], torch.full_like(a["area"], 1 / 20000))
+
+
+def test_device_boundary_sampler():
+    """`sample_boundary` on the device -- every kept point lies on the solid's boundary, normals are
+    unit vectors pointing outwards, per-edge counts and areas follow density x measure, the sieve applies."""
+    import sympy as sp
+    import idrlnet_b200.shortcut as sc
+    from idrlnet_b200.geo_utils import lambdify_np
+    x, y = sp.symbols("x y")
+    rect, circ = sc.Rectangle((-1.0, -1.0), (1.0, 1.0)), sc.Circle((0.2, 0.0), 0.5)
+    geo = rect - circ
+    b = geo.sample_boundary_device(1000, seed=4)
+    n = b["x"].shape[0]
+    expect = 4 * 2000 + int(1000 * 2 * np.pi * 0.5)
+    assert abs(n - expect) <= 2, (n, expect)                      # nothing of this solid's boundary is sieved away
+    assert set(b) == {"x", "y", "normal_x", "normal_y", "area", "sdf"}
+    host_sdf = lambdify_np(geo.sdf, ["x", "y"])(x=b["x"].cpu().numpy().astype(np.float64), y=b["y"].cpu().numpy().astype(np.float64))
+    assert np.abs(host_sdf).max() < 1e-5
+    nrm = (b["normal_x"] ** 2 + b["normal_y"] ** 2).cpu().numpy()
+    np.testing.assert_allclose(nrm, 1.0, atol=1e-5)
+    out = {"x": (b["x"] + 1e-3 * b["normal_x"]).cpu().numpy().astype(np.float64), "y": (b["y"] + 1e-3 * b["normal_y"]).cpu().numpy().astype(np.float64)}
+    assert (lambdify_np(geo.sdf, ["x", "y"])(**out) < 0).all()    # normals leave the solid (the hole's point inwards to it)
+    np.testing.assert_allclose(float(b["area"].sum()), 8.0 + 2 * np.pi * 0.5, rtol=1e-3)
+    again = geo.sample_boundary_device(1000, seed=4)
+    assert all(torch.equal(b[k], again[k]) for k in b)
+    left = rect.sample_boundary_device(500, seed=1, sieve=sp.Eq(x, -1.0))
+    assert left["x"].shape[0] == 1000 and float(left["x"].max()) == -1.0 and float(left["normal_x"].max()) == -1.0
+    inner = (rect + circ).sample_boundary_device(200, seed=2)      # the circle lies inside: its edge is sieved away
+    assert inner["x"].shape[0] == 4 * 400

@@ -187,3 +187,44 @@ def test_csg_tree_is_tracked_for_the_device_sampler():
     assert (r - sc.Circle((0.0, 0.0), sp.Symbol("r")))._tree is None
     assert sc.Rectangle((0.0, 0.0), (1.0, 1.0)).scaling(2.0)._tree is None
     assert sc.Polygon([(0, 0), (1, 0), (0, 1)])._tree is None
+
+
+def test_boundary_device_sampler_logic_with_a_stub_generator(monkeypatch):
+    """`sample_boundary_device` end to end on CPU tensors, with pinn_sample_box replaced by a NumPy stub (the kernel
+    itself is checked bit for bit in tests/test_gpu_narrow.py): per-edge counts, expressions, sieve, areas."""
+    import ctypes as C
+    from idrlnet_b200 import native as nv
+
+    class Stub:
+        calls = 0
+
+        def pinn_sample_box(self, cols, n_dims, lo, hi, n, seed, stream_id, offset, sdf, sdf_dims, stream):
+            rng = np.random.default_rng(int(seed) * 1000 + int(stream_id))
+            for d in range(n_dims):
+                buf = (C.c_float * n).from_address(cols[d])
+                buf[:] = rng.uniform(lo[d], hi[d], n).astype(np.float32).tolist()
+            Stub.calls += 1
+            return 0
+
+    monkeypatch.setattr(nv, "lib", lambda: Stub())
+    x, y = sp.symbols("x y")
+    rect, circ = sc.Rectangle((-1.0, -1.0), (1.0, 1.0)), sc.Circle((0.2, 0.0), 0.5)
+    geo = rect - circ
+    b = geo.sample_boundary_device(200, seed=4, device="cpu")
+    assert Stub.calls == 5
+    n = b["x"].shape[0]
+    assert abs(n - (4 * 400 + int(200 * 2 * np.pi * 0.5))) <= 2
+    assert set(b) == {"x", "y", "normal_x", "normal_y", "area", "sdf"}
+    assert float(b["sdf"].abs().max()) < 1e-4
+    np.testing.assert_allclose((b["normal_x"] ** 2 + b["normal_y"] ** 2).numpy(), 1.0, atol=1e-5)
+    np.testing.assert_allclose(float(b["area"].sum()), 8.0 + 2 * np.pi * 0.5, rtol=1e-3)
+    left = rect.sample_boundary_device(100, seed=1, sieve=sp.Eq(x, -1.0), device="cpu")
+    assert left["x"].shape[0] == 200 and float(left["x"].max()) == -1.0 and float(left["normal_x"].max()) == -1.0
+    inner = (rect + circ).sample_boundary_device(50, seed=2, device="cpu")   # the circle's edge lies inside: sieved away
+    assert inner["x"].shape[0] == 4 * 100
+    # parameterised solid: the radius is sampled per point and returned as a column
+    r = sp.Symbol("r")
+    holes = sc.Tube2D((-1, -0.5), (1, 0.5)) - sc.Circle((0.0, 0.0), r)
+    pb = holes.sample_boundary_device(100, seed=3, param_ranges={r: (0.1, 0.3)}, device="cpu")
+    assert "r" in pb and float(pb["r"].min()) >= 0.1 and float(pb["r"].max()) <= 0.3
+    assert float(pb["sdf"].abs().max()) < 1e-4
