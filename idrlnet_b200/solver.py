@@ -63,8 +63,8 @@ class Solver(Notifier, Optimizable):
         self.netnodes: List[NetNode] = netnodes
         self.fused_enabled = fused
         self.post_step_loss = post_step_loss
-        # arithmetic of the layer GEMMs of wide (H > 32) nets: "fp32" (parity, default) or "tf32"
-        # (tcgen05 tensor cores); None -> IDRLNET_B200_PRECISION or "fp32"
+        # arithmetic of the layer GEMMs of wide (H > 32) nets: "fp32" (FP32 FMA, parity, default), "fp32x3" (tensor
+        # cores, 3xTF32 splitting), "tf32" / "tf32_streamed" (tensor cores); None -> IDRLNET_B200_PRECISION or "fp32"
         self.precision = precision
         self._move_nets_to_device()
         self.init_network_dirs = init_network_dirs if init_network_dirs else []
