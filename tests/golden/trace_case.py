@@ -95,7 +95,71 @@ def cavity(sc, network_dir, iters):
                      network_dir=network_dir, loading=False)
 
 
-CASES = {"poisson": poisson, "burgers": burgers, "cavity": cavity}
+def beam_lbfgs(sc, network_dir, iters):
+    """examples/euler_beam/euler_beam_lbfgs.py: fourth-order derivatives through chained ExpressionNodes, Eq sieves on a
+    Line1D boundary, LBFGS closure (idrlnet/solver.py:316-326)."""
+    x = sp.symbols("x")
+    line = sc.Line1D(0, 1)
+    y = sp.Function("y")(x)
+
+    def dom(name, sampler, cons):
+        @sc.datanode(name=name)
+        class D(sc.SampleDomain):
+            def sampling(self, *args, **kwargs):
+                return sampler(), dict(cons)
+        return D()
+
+    doms = (dom("interior", lambda: line.sample_interior(100), {"dddd_y": 0}),
+            dom("left_boundary1", lambda: line.sample_boundary(10, sieve=sp.Eq(x, 0)), {"y": 0}),
+            dom("left_boundary2", lambda: line.sample_boundary(10, sieve=sp.Eq(x, 0)), {"d_y": 0}),
+            dom("right_boundary1", lambda: line.sample_boundary(10, sieve=sp.Eq(x, 1)), {"dd_y": 0}),
+            dom("right_boundary2", lambda: line.sample_boundary(10, sieve=sp.Eq(x, 1)), {"ddd_y": 0}))
+    np.random.seed(3)
+    torch.manual_seed(3)
+    net = sc.get_net_node(inputs=("x",), outputs=("y",), name="net", arch=sc.Arch.mlp)
+    pdes = [sc.ExpressionNode(name="dddd_y", expression=y.diff(x).diff(x).diff(x).diff(x) + 1),
+            sc.ExpressionNode(name="d_y", expression=y.diff(x)),
+            sc.ExpressionNode(name="dd_y", expression=y.diff(x).diff(x)),
+            sc.ExpressionNode(name="ddd_y", expression=y.diff(x).diff(x).diff(x))]
+    return net, dict(sample_domains=doms, netnodes=[net], pdes=pdes, max_iter=iters, network_dir=network_dir, loading=False,
+                     opt_config=dict(optimizer="LBFGS", lr=1))
+
+
+def periodic(sc, network_dir, iters):
+    """examples/allen_cahn in miniature: a net shared under a second name on shifted inputs (`get_shared_net_node`),
+    periodic conditions through ExpressionNode + Difference, a weighted initial condition."""
+    x, t = sp.Symbol("x"), sp.Symbol("t")
+    u, up = sp.Function("u")(x, t), sp.Function("up")(x, t)
+    geo = sc.Line1D(-1.0, 1.0)
+
+    @sc.datanode(name="allen_domain")
+    def interior():
+        return geo.sample_interior(200, bounds={x: (-1.0, 1.0)}, param_ranges={t: (0, 1)}), {"AllenCahn_u": 0}
+
+    @sc.datanode(name="AllenInit")
+    def init():
+        pts = geo.sample_interior(40, param_ranges={t: 0.0})
+        return pts, {"u": x ** 2 * sp.cos(sp.pi * x), "lambda_u": 100}
+
+    @sc.datanode(name="AllenBc")
+    def bc():
+        pts = geo.sample_boundary(20, sieve=sp.Eq(x, -1.0), param_ranges={t: (0, 1)})
+        return pts, {"difference_u_up": 0, "difference_diff_u_diff_up": 0}
+
+    np.random.seed(13)
+    torch.manual_seed(13)
+    mlp = sc.MLP([2, 24, 24, 2], activation=sc.Activation.tanh)
+    net_u = sc.NetNode(inputs=("x", "t"), outputs=("u",), name="net1", net=mlp)
+    xp = sc.ExpressionNode(name="xp", expression=x + 2)
+    net_up = sc.get_shared_net_node(net_u, inputs=("xp", "t"), outputs=("up",), name="net2", arch="mlp")
+    pdes = [xp, sc.ExpressionNode(expression=u.diff(x), name="diff_u"), sc.ExpressionNode(expression=up.diff(x), name="diff_up"),
+            sc.AllenCahnNode(u="u", gamma_1=0.0001, gamma_2=5), sc.Difference(T="diff_u", S="diff_up"),
+            sc.Difference(T="u", S="up")]
+    return net_u, dict(sample_domains=(interior(), init(), bc()), netnodes=[net_u, net_up], pdes=pdes, max_iter=iters,
+                       network_dir=network_dir, loading=False)
+
+
+CASES = {"poisson": poisson, "burgers": burgers, "cavity": cavity, "beam_lbfgs": beam_lbfgs, "periodic": periodic}
 
 
 def build(sc, network_dir, iters):  # (kept for callers of the first version)

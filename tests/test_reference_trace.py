@@ -41,7 +41,7 @@ def test_generic_path_reproduces_the_reference_trace(name, tmp_path):
 
 @pytest.mark.gpu
 @pytest.mark.xfail(strict=False, reason="written while the GPU pool was draining; the 1k-step loss-curve tests cover the same path")
-@pytest.mark.parametrize("name", sorted(CASES))
+@pytest.mark.parametrize("name", ["poisson", "burgers", "cavity"])   # every domain of these runs on the fused kernels
 def test_fused_path_reproduces_the_reference_trace(name, tmp_path):
     losses = _run(name, tmp_path, fused=True)
     ref = GOLD[f"{name}/losses"]
