@@ -159,7 +159,64 @@ def periodic(sc, network_dir, iters):
                        network_dir=network_dir, loading=False)
 
 
-CASES = {"poisson": poisson, "burgers": burgers, "cavity": cavity, "beam_lbfgs": beam_lbfgs, "periodic": periodic}
+def inverse_wave(sc, network_dir, iters):
+    """examples/inverse_wave_equation: a second "net" that is a single trainable coefficient (`Arch.single_var`), an L1
+    data loss on low-discrepancy samples, a PDE whose coefficient is the other net's output."""
+    x, t = sp.Symbol("x"), sp.Symbol("t")
+    L = float(math.pi)
+    geo = sc.Line1D(0, L)
+    np.random.seed(17)
+    obs = geo.sample_interior(density=4, bounds={x: (0, L)}, param_ranges={t: (0, 2 * L)}, low_discrepancy=True)
+    obs_u = np.sin(obs["x"]) * (np.sin(1.54 * obs["t"]) + np.cos(1.54 * obs["t"]))
+
+    @sc.datanode(name="wave_domain", loss_fn="L1")
+    class WaveExternal(sc.SampleDomain):
+        def sampling(self, *args, **kwargs):
+            return dict(obs), {"u": obs_u}
+
+    @sc.datanode(name="wave_external")
+    class WaveEq(sc.SampleDomain):
+        def sampling(self, *args, **kwargs):
+            return geo.sample_interior(density=20, bounds={x: (0, L)}, param_ranges={t: (0, 2 * L)}), {"wave_equation": 0.0}
+
+    torch.manual_seed(17)
+    net = sc.get_net_node(inputs=("x", "t"), outputs=("u",), name="net1", arch=sc.Arch.mlp)
+    var_c = sc.get_net_node(inputs=("x",), outputs=("c",), arch=sc.Arch.single_var)
+    pde = sc.WaveNode(c="c", dim=1, time=True, u="u")
+    return net, dict(sample_domains=(WaveExternal(), WaveEq()), netnodes=[net, var_c], pdes=[pde], max_iter=iters,
+                     network_dir=network_dir, loading=False)
+
+
+def volterra(sc, network_dir, iters):
+    """examples/Volterra_IDE: an integral operator (Int1DNode, Gauss-Legendre quadrature with the net evaluated at the
+    nodes) inside the training loop."""
+    x, s_, fs = sp.Symbol("x"), sp.Symbol("s"), sp.Symbol("fs")
+    f = sp.Function("f")(x)
+    geo = sc.Line1D(0, 5)
+
+    @sc.datanode
+    def interior():
+        return geo.sample_interior(40), {"difference_lhs_rhs": 0}
+
+    @sc.datanode
+    def init():
+        pts = geo.sample_boundary(1, sieve=sp.Eq(x, 0))
+        pts["lambda_f"] = 1000 * np.ones_like(pts["x"])
+        return pts, {"f": 1}
+
+    np.random.seed(19)
+    torch.manual_seed(19)
+    netnode = sc.get_net_node(inputs=("x",), outputs=("f",), name="net")
+    lhs = sc.ExpressionNode(expression=f.diff(x) + f, name="lhs")
+    rhs = sc.Int1DNode(expression=sp.exp(s_ - x) * fs, var=s_, lb=0, ub=x, expression_name="rhs",
+                       funs={"fs": {"eval": netnode, "input_map": {"x": "s"}, "output_map": {"f": "fs"}}}, degree=10)
+    diff = sc.Difference(T="lhs", S="rhs", dim=1, time=False)
+    return netnode, dict(sample_domains=(interior(), init()), netnodes=[netnode], pdes=[lhs, rhs, diff], max_iter=iters,
+                         network_dir=network_dir, loading=False)
+
+
+CASES = {"poisson": poisson, "burgers": burgers, "cavity": cavity, "beam_lbfgs": beam_lbfgs, "periodic": periodic,
+         "inverse_wave": inverse_wave, "volterra": volterra}
 
 
 def build(sc, network_dir, iters):  # (kept for callers of the first version)
