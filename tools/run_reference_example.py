@@ -4,7 +4,7 @@ iterations -- build-container check of the "examples run unchanged" boundary (SU
     python tools/run_reference_example.py /root/reference/examples/ldc/ldc.py [max_iter]
 
 matplotlib / pyevtk are stubbed (not installed here); `max_iter` is clamped and `network_dir`
-redirected to /tmp so nothing is written next to the example."""
+redirected to gpurun_out/exrun so nothing is written next to the example."""
 import os, sys, types, runpy, importlib
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 ex = sys.argv[1]
@@ -44,7 +44,7 @@ sc = idrlnet_b200.shortcut
 _init = sc.Solver.__init__
 def init(self, *a, **kw):
     kw['max_iter'] = min(kw.get('max_iter', 1000), iters)
-    kw.setdefault('network_dir', '/tmp/exrun/net_' + os.path.basename(ex))
+    kw.setdefault('network_dir', os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), 'gpurun_out', 'exrun', 'net_') + os.path.basename(ex))
     return _init(self, *a, **kw)
 sc.Solver.__init__ = init
 os.chdir(os.path.dirname(ex))
