@@ -215,8 +215,126 @@ def volterra(sc, network_dir, iters):
                          network_dir=network_dir, loading=False)
 
 
+def deepritz(sc, network_dir, iters):
+    """examples/deepritz: energy functional through ICNode with the "Identity" loss, a sigma-weighted boundary domain,
+    fixed point sets drawn once in the constructors."""
+    x, y = sp.symbols("x y")
+    u = sp.Function("u")(x, y)
+    geo = sc.Rectangle((-1, -1), (1.0, 1.0))
+    np.random.seed(23)
+
+    @sc.datanode(sigma=1000.0)
+    class Boundary(sc.SampleDomain):
+        def __init__(self):
+            self.points = geo.sample_boundary(25)
+            self.constraints = {"u": 0.0}
+
+        def sampling(self, *args, **kwargs):
+            return self.points, self.constraints
+
+    @sc.datanode(loss_fn="Identity")
+    class Interior(sc.SampleDomain):
+        def __init__(self):
+            self.points = geo.sample_interior(60)
+            self.constraints = {"integral_dxdy": 0}
+
+        def sampling(self, *args, **kwargs):
+            return self.points, self.constraints
+
+    domains = (Boundary(), Interior())
+    torch.manual_seed(23)
+    f = 2 * sp.pi ** 2 * sp.sin(sp.pi * x) * sp.sin(sp.pi * y)
+    dx_exp = sc.ExpressionNode(expression=0.5 * (u.diff(x) ** 2 + u.diff(y) ** 2) - u * f, name="dxdy")
+    net = sc.get_net_node(inputs=("x", "y"), outputs=("u",), name="net", arch=sc.Arch.mlp)
+    integral = sc.ICNode("dxdy", dim=2, time=False)
+    return net, dict(sample_domains=domains, netnodes=[net], pdes=[dx_exp, integral], max_iter=iters,
+                     network_dir=network_dir, loading=False)
+
+
+def param_poisson(sc, network_dir, iters):
+    """examples/parameterized_poisson: a design parameter as a third net input, parameter ranges on boundary samples,
+    a boundary target that is the parameter symbol itself, Eq sieves."""
+    x, y, temp = sp.symbols("x y temp")
+    temp_range = {temp: (-0.2, 0.2)}
+    rec = sc.Rectangle((-1.0, -1.0), (1.0, 1.0))
+
+    @sc.datanode
+    class Right(sc.SampleDomain):
+        def sampling(self, *args, **kwargs):
+            return rec.sample_boundary(40, sieve=(sp.Eq(x, 1.0)), param_ranges=temp_range), sc.Variables({"T": 0.0})
+
+    @sc.datanode
+    class Left(sc.SampleDomain):
+        def sampling(self, *args, **kwargs):
+            return rec.sample_boundary(40, sieve=(sp.Eq(x, -1.0)), param_ranges=temp_range), sc.Variables({"T": temp})
+
+    @sc.datanode(name="up_down")
+    class UpDown(sc.SampleDomain):
+        def sampling(self, *args, **kwargs):
+            return (rec.sample_boundary(40, sieve=((x > -1.0) & (x < 1.0)), param_ranges=temp_range),
+                    sc.Variables({"normal_gradient_T": 0.0}))
+
+    @sc.datanode(name="heat_domain")
+    class Heat(sc.SampleDomain):
+        def __init__(self):
+            self.points = 60
+
+        def sampling(self, *args, **kwargs):
+            return rec.sample_interior(self.points, param_ranges=temp_range), sc.Variables({"diffusion_T": 1.0})
+
+    np.random.seed(29)
+    torch.manual_seed(29)
+    net = sc.get_net_node(inputs=("x", "y", "temp"), outputs=("T",), name="net1", arch=sc.Arch.mlp)
+    pde = sc.DiffusionNode(T="T", D=1.0, Q=0.0, dim=2, time=False)
+    grad = sc.NormalGradient("T", dim=2, time=False)
+    return net, dict(sample_domains=(Heat(), Left(), Right(), UpDown()), netnodes=[net], pdes=[pde, grad], max_iter=iters,
+                     network_dir=network_dir, loading=False)
+
+
+def min_surface(sc, network_dir, iters):
+    """examples/minimal_surface_of_revolution: Abs / sqrt in the integrand, L1 loss on the integral, NumPy-array targets
+    on a two-point boundary, a constraint-free inference domain that must not contribute to the loss."""
+    x = sp.Symbol("x")
+    u = sp.Function("u")(x)
+    geo = sc.Line1D(-1, 0.5)
+    np.random.seed(31)
+
+    @sc.datanode(sigma=1000.0)
+    class Boundary(sc.SampleDomain):
+        def __init__(self):
+            self.points = geo.sample_boundary(1)
+            self.constraints = {"u": np.cosh(self.points["x"])}
+
+        def sampling(self, *args, **kwargs):
+            return self.points, self.constraints
+
+    @sc.datanode(loss_fn="L1")
+    class Interior(sc.SampleDomain):
+        def sampling(self, *args, **kwargs):
+            return geo.sample_interior(200), {"integral_dx": 0}
+
+    @sc.datanode
+    class InteriorInfer(sc.SampleDomain):
+        def __init__(self):
+            self.points = sc.Variables()
+            self.points["x"] = np.linspace(-1, 0.5, 11, endpoint=True).reshape(-1, 1)
+            self.points["area"] = np.ones_like(self.points["x"])
+
+        def sampling(self, *args, **kwargs):
+            return self.points, {}
+
+    domains = (Boundary(), Interior(), InteriorInfer())
+    torch.manual_seed(31)
+    dx_exp = sc.ExpressionNode(expression=sp.Abs(u) * sp.sqrt((u.diff(x)) ** 2 + 1), name="dx")
+    net = sc.get_net_node(inputs=("x",), outputs=("u",), name="net", arch=sc.Arch.mlp)
+    integral = sc.ICNode("dx", dim=1, time=False)
+    return net, dict(sample_domains=domains, netnodes=[net], pdes=[dx_exp, integral], max_iter=iters,
+                     network_dir=network_dir, loading=False)
+
+
 CASES = {"poisson": poisson, "burgers": burgers, "cavity": cavity, "beam_lbfgs": beam_lbfgs, "periodic": periodic,
-         "inverse_wave": inverse_wave, "volterra": volterra}
+         "inverse_wave": inverse_wave, "volterra": volterra, "deepritz": deepritz, "param_poisson": param_poisson,
+         "min_surface": min_surface}
 
 
 def build(sc, network_dir, iters):  # (kept for callers of the first version)
