@@ -332,9 +332,106 @@ def min_surface(sc, network_dir, iters):
                      network_dir=network_dir, loading=False)
 
 
+def consolidation(sc, network_dir, iters):
+    """examples/consolidation: per-point lambda arrays computed with NumPy, array-valued zero targets, a first-order
+    time-like term next to a second derivative."""
+    x, y = sp.symbols("x y")
+    p = sp.Function("p")(x, y)
+    geo = sc.Rectangle((0, 0), (1, 1))
+    np.random.seed(37)
+
+    @sc.datanode
+    class Init(sc.SampleDomain):
+        def __init__(self):
+            self.points = geo.sample_boundary(30, sieve=(sp.Eq(y, 0.0)))
+            self.constraints = {"p": 1.0, "lambda_p": 1 - np.power(self.points["x"], 5)}
+
+        def sampling(self, *args, **kwargs):
+            return self.points, self.constraints
+
+    @sc.datanode
+    class Interior(sc.SampleDomain):
+        def __init__(self):
+            self.points = geo.sample_interior(150)
+            self.constraints = {"consolidation": np.zeros_like(self.points["x"])}
+
+        def sampling(self, *args, **kwargs):
+            return self.points, self.constraints
+
+    @sc.datanode
+    class UpperBounds(sc.SampleDomain):
+        def __init__(self):
+            self.points = geo.sample_boundary(30, sieve=(sp.Eq(x, 1.0)))
+            self.constraints = {"p": 0.0, "lambda_p": np.power(self.points["y"], 0.2)}
+
+        def sampling(self, *args, **kwargs):
+            return self.points, self.constraints
+
+    @sc.datanode
+    class LowerBounds(sc.SampleDomain):
+        def __init__(self):
+            self.points = geo.sample_boundary(30, sieve=(sp.Eq(x, 0.0)))
+            self.constraints = {"normal_gradient_p": 0.0}
+
+        def sampling(self, *args, **kwargs):
+            return self.points, self.constraints
+
+    domains = (Init(), Interior(), UpperBounds(), LowerBounds())
+    torch.manual_seed(37)
+    pde = sc.ExpressionNode(name="consolidation", expression=p.diff(y) - 0.6 * p.diff(x, 2))
+    grad = sc.NormalGradient(T="p", dim=2, time=False)
+    net = sc.get_net_node(inputs=("x", "y"), outputs=("p",), arch=sc.Arch.mlp, name="net")
+    return net, dict(sample_domains=domains, netnodes=[net], pdes=[pde, grad], max_iter=iters,
+                     network_dir=network_dir, loading=False)
+
+
+def ns_steady(sc, network_dir, iters):
+    """examples/ns_steady: rectangle minus circle (CSG interior and boundary sampling with sieves), a six-output net in
+    the stress formulation, a symbolic inlet profile, two targets in one domain."""
+    x, y = sp.Symbol("x"), sp.Symbol("y")
+    rec = sc.Rectangle((0.0, 0.0), (1.1, 0.41))
+    geo = rec - sc.Circle((0.2, 0.2), 0.05)
+    u, v, p = (sp.Function(n)(x, y) for n in ("u", "v", "p"))
+    s11, s22, s12 = (sp.Function(n)(x, y) for n in ("s11", "s22", "s12"))
+    nu = 0.02
+
+    @sc.datanode
+    class Inlet(sc.SampleDomain):
+        def sampling(self, *args, **kwargs):
+            return (rec.sample_boundary(60, sieve=(sp.Eq(x, 0.0))),
+                    sc.Variables({"u": 4 * (0.41 - y) * y / (0.41 * 0.41)}))
+
+    @sc.datanode
+    class Outlet(sc.SampleDomain):
+        def sampling(self, *args, **kwargs):
+            return geo.sample_boundary(60, sieve=(sp.Eq(x, 1.1))), sc.Variables({"p": 0.0})
+
+    @sc.datanode
+    class Wall(sc.SampleDomain):
+        def sampling(self, *args, **kwargs):
+            return geo.sample_boundary(60, sieve=((x > 0.0) & (x < 1.1))), sc.Variables({"u": 0.0, "v": 0.0})
+
+    @sc.datanode(name="NS_external")
+    class Interior(sc.SampleDomain):
+        def sampling(self, *args, **kwargs):
+            return geo.sample_interior(300), {"f_s11": 0.0, "f_s22": 0.0, "f_s12": 0.0, "f_u": 0.0, "f_v": 0.0, "f_p": 0.0}
+
+    np.random.seed(41)
+    torch.manual_seed(41)
+    net = sc.get_net_node(inputs=("x", "y"), outputs=("u", "v", "p", "s11", "s22", "s12"), name="net", arch=sc.Arch.mlp)
+    pdes = [sc.ExpressionNode(name="f_s11", expression=-p + 2 * nu * u.diff(x) - s11),
+            sc.ExpressionNode(name="f_s22", expression=-p + 2 * nu * v.diff(y) - s22),
+            sc.ExpressionNode(name="f_s12", expression=nu * (u.diff(y) + v.diff(x)) - s12),
+            sc.ExpressionNode(name="f_u", expression=u * u.diff(x) + v * u.diff(y) - nu * (s11.diff(x) + s12.diff(y))),
+            sc.ExpressionNode(name="f_v", expression=u * v.diff(x) + v * v.diff(y) - nu * (s12.diff(x) + s22.diff(y))),
+            sc.ExpressionNode(name="f_p", expression=p + (s11 + s22) / 2)]
+    return net, dict(sample_domains=(Inlet(), Outlet(), Wall(), Interior()), netnodes=[net], pdes=pdes, max_iter=iters,
+                     network_dir=network_dir, loading=False)
+
+
 CASES = {"poisson": poisson, "burgers": burgers, "cavity": cavity, "beam_lbfgs": beam_lbfgs, "periodic": periodic,
          "inverse_wave": inverse_wave, "volterra": volterra, "deepritz": deepritz, "param_poisson": param_poisson,
-         "min_surface": min_surface}
+         "min_surface": min_surface, "consolidation": consolidation, "ns_steady": ns_steady}
 
 
 def build(sc, network_dir, iters):  # (kept for callers of the first version)
