@@ -47,3 +47,28 @@ def test_fused_path_reproduces_the_reference_trace(name, tmp_path):
     ref = GOLD[f"{name}/losses"]
     rel = np.abs(losses - ref) / np.abs(ref)
     assert rel.max() <= 5e-4, (rel, losses, ref)
+
+
+def test_reference_checkpoint_resumes_with_the_reference_losses(tmp_path):
+    """`model.ckpt` written by the REAL reference after 6 Burgers iterations (tests/golden/make_ckpt_golden.py) is loaded by
+    `Solver(loading=True)` -- parameters, Adam moments, global_step (idrlnet/solver.py:425-460) -- and the next 6
+    `train_pipe()` losses equal those of the reference's own resumed run.  (The generator also asserts the reverse
+    direction: the reference resumes from a checkpoint this package wrote with identical losses.)"""
+    import shutil
+    RESUME_SEED = 101  # tests/golden/make_ckpt_golden.py
+    gold = np.load(os.path.join(os.path.dirname(__file__), "golden", "ckpt_trace.npz"))
+    shutil.copy(os.path.join(os.path.dirname(__file__), "golden", "ref_burgers_step6.ckpt"), str(tmp_path / "model.ckpt"))
+    was_gpu, dev = pkg.GPU_ENABLED, pkg.DEVICE
+    pkg.use_cpu()
+    try:
+        _, kw = CASES["burgers"](sc, str(tmp_path), 12)
+        kw["loading"] = True
+        s = sc.Solver(post_step_loss=True, **kw)
+        assert s.global_step == int(gold["global_step"]) == 6
+        np.random.seed(RESUME_SEED)
+        losses = np.array([float(s.train_pipe()) for _ in range(6)])
+    finally:
+        if was_gpu:
+            pkg.use_gpu(dev)
+    rel = np.abs(losses - gold["losses"]) / np.abs(gold["losses"])
+    assert rel.max() <= 5e-6, (rel, losses, gold["losses"])
