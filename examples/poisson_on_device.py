@@ -5,8 +5,10 @@
 The only line an IDRLnet script changes is the import; the rest below uses two opt-in additions:
 points drawn on the device (`sample_interior_device` / `sample_boundary_device`) and the top-k
 residual query used for adaptive re-sampling."""
+import os
 import sys
 
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))  # run from a source checkout
 import idrlnet_b200.shortcut as sc        # instead of: import idrlnet.shortcut as sc
 
 plate = sc.Rectangle((-1.0, -1.0), (1.0, 1.0)) - sc.Circle((0.0, 0.0), 0.3)

@@ -10,7 +10,7 @@ import numpy as np
 HERE = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, HERE)
 from make_golden import _install_shims  # noqa: E402
-from trace_case import CASES  # noqa: E402
+from trace_case import CASES, INFER, INFER_SEED  # noqa: E402
 
 
 def main():
@@ -24,6 +24,12 @@ def main():
         s = sc.Solver(**kw)
         out[f"{name}/losses"] = np.array([float(s.train_pipe()) for _ in range(12)])
         print(name, out[f"{name}/losses"])
+        if name in INFER:  # Solver.infer_step (idrlnet/solver.py:410-420) on freshly drawn points of one domain
+            np.random.seed(INFER_SEED)
+            dom, cols = INFER[name]
+            res = s.infer_step({dom: cols})[dom]
+            for c in cols:
+                out[f"{name}/infer/{c}"] = res[c].detach().cpu().numpy()
     np.savez(os.path.join(HERE, "train_trace.npz"), **out)
 
 

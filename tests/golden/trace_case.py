@@ -433,6 +433,12 @@ CASES = {"poisson": poisson, "burgers": burgers, "cavity": cavity, "beam_lbfgs":
          "inverse_wave": inverse_wave, "volterra": volterra, "deepritz": deepritz, "param_poisson": param_poisson,
          "min_surface": min_surface, "consolidation": consolidation, "ns_steady": ns_steady}
 
+# after the 12 iterations: `infer_step` of these columns on freshly drawn points (seeded) of one domain
+INFER_SEED = 55
+INFER = {"poisson": ("heat_domain", ["x", "y", "T", "T__x", "T__y__y", "diffusion_T"]),
+         "burgers": ("burgers_equation", ["x", "t", "u", "u__t", "u__x__x", "burgers_u"]),
+         "ns_steady": ("NS_external", ["x", "y", "u", "s12__y", "f_u", "f_p"])}
+
 
 def build(sc, network_dir, iters):  # (kept for callers of the first version)
     return poisson(sc, network_dir, iters)

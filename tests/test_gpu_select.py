@@ -202,8 +202,7 @@ def test_device_geometry_sampler_matches_host_sdf():
     assert torch.allclose(a["area"], torch.full_like(a["area"], 1 / 20000))
 
 
-@pytest.mark.xfail(strict=False, reason="written while the GPU pool was draining: its logic is covered on the CPU by "
-                   "tests/test_host_api.py::test_boundary_device_sampler_logic_with_a_stub_generator; remove once run on a B200")
+@pytest.mark.gpu
 def test_device_boundary_sampler():
     """`sample_boundary` on the device -- every kept point lies on the solid's boundary, normals are
     unit vectors pointing outwards, per-edge counts and areas follow density x measure, the sieve applies."""

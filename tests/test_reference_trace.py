@@ -10,19 +10,35 @@ import torch
 
 import idrlnet_b200 as pkg
 import idrlnet_b200.shortcut as sc
-from tests.golden.trace_case import CASES
+from tests.golden.trace_case import CASES, INFER, INFER_SEED
 
+# LBFGS (no line search, 20 inner iterations per train_pipe) on the fourth-order beam amplifies the FP32 rounding
+# differences between the CPU and GPU math libraries by 10-50x per outer iteration (observed on a B200: 3e-5, 2.6e-4,
+# 1.5e-2, 0.7 ...; the CPU tier matches all 12): on the GPU only the first two outer iterations are compared.
+GPU_TOL = {"beam_lbfgs": 1e-3}
+GPU_STEPS = {"beam_lbfgs": 2}
 GOLD = np.load(os.path.join(os.path.dirname(__file__), "golden", "train_trace.npz"))
 
 
-def _run(name, tmp_path, fused):
+def _run(name, tmp_path, fused, infer_tol=2e-5):
     net, kw = CASES[name](sc, str(tmp_path), 12)
     prefix = f"{name}/state/"
     for k in GOLD.files:
         if k.startswith(prefix):  # the same torch seed gives the reference's initial parameters
             np.testing.assert_allclose(net.net.state_dict()[k[len(prefix):]].cpu().numpy(), GOLD[k], rtol=0, atol=0)
     s = sc.Solver(post_step_loss=True, fused=fused, **kw)
-    return np.array([float(s.train_pipe()) for _ in range(12)])
+    losses = np.array([float(s.train_pipe()) for _ in range(12)])
+    if name in INFER:  # derivative / residual columns of `infer_step` on the trained net, same fresh points
+        np.random.seed(INFER_SEED)
+        dom, cols = INFER[name]
+        res = s.infer_step({dom: cols})[dom]
+        for c in cols:
+            ref = GOLD[f"{name}/infer/{c}"]
+            got = res[c].detach().cpu().numpy()
+            assert got.shape == ref.shape, (c, got.shape, ref.shape)
+            err = np.linalg.norm(got - ref) / max(np.linalg.norm(ref), 1e-30)
+            assert err <= infer_tol, (name, c, err)
+    return losses
 
 
 @pytest.mark.parametrize("name", sorted(CASES))
@@ -40,13 +56,24 @@ def test_generic_path_reproduces_the_reference_trace(name, tmp_path):
 
 
 @pytest.mark.gpu
-@pytest.mark.xfail(strict=False, reason="written while the GPU pool was draining; the 1k-step loss-curve tests cover the same path")
 @pytest.mark.parametrize("name", ["poisson", "burgers", "cavity"])   # every domain of these runs on the fused kernels
 def test_fused_path_reproduces_the_reference_trace(name, tmp_path):
-    losses = _run(name, tmp_path, fused=True)
+    losses = _run(name, tmp_path, fused=True, infer_tol=2e-3)
     ref = GOLD[f"{name}/losses"]
     rel = np.abs(losses - ref) / np.abs(ref)
     assert rel.max() <= 5e-4, (rel, losses, ref)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", sorted(CASES))
+def test_gpu_auto_path_reproduces_the_reference_trace(name, tmp_path):
+    """Every case on the GPU the way a switching user runs it (`fused=None`): domains that compile run the fused kernels,
+    the others the generic graph with value / derivative columns served by the jet kernel where the net is supported."""
+    losses = _run(name, tmp_path, fused=None, infer_tol=2e-3)
+    ref = GOLD[f"{name}/losses"]
+    rel = (np.abs(losses - ref) / np.abs(ref))[:GPU_STEPS.get(name, 12)]
+    print(name, "max rel", rel.max())
+    assert rel.max() <= GPU_TOL.get(name, 5e-4), (rel, losses, ref)
 
 
 def test_reference_checkpoint_resumes_with_the_reference_losses(tmp_path):
