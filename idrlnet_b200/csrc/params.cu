@@ -9,11 +9,8 @@ namespace pinn {
 void count_launch(int n);
 
 // one warp per output row: W[j,:] = g[j] * v[j,:] / ||v[j,:]||
-__global__ void weight_norm_fwd_kernel(const float* __restrict__ g, const float* __restrict__ v, float* __restrict__ W,
-                                       int out_dim, int in_dim) {
-  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  const int lane = threadIdx.x & 31;
-  if (row >= out_dim) return;
+__device__ __forceinline__ void weight_norm_fwd_row(const float* __restrict__ g, const float* __restrict__ v,
+                                                    float* __restrict__ W, int row, int in_dim, int lane) {
   const float* vr = v + (size_t)row * in_dim;
   float ss = 0.f;
   for (int k = lane; k < in_dim; k += 32) ss += vr[k] * vr[k];
@@ -23,13 +20,17 @@ __global__ void weight_norm_fwd_kernel(const float* __restrict__ g, const float*
   for (int k = lane; k < in_dim; k += 32) W[(size_t)row * in_dim + k] = vr[k] * scale;
 }
 
-// dg[j] = <dW_j, v_j>/||v_j|| ; dv[j,:] = g_j/||v_j|| * (dW_j - <dW_j, v_j>/||v_j||^2 * v_j)
-__global__ void weight_norm_bwd_kernel(const float* __restrict__ g, const float* __restrict__ v,
-                                       const float* __restrict__ dW, float* __restrict__ dg, float* __restrict__ dv,
+__global__ void weight_norm_fwd_kernel(const float* __restrict__ g, const float* __restrict__ v, float* __restrict__ W,
                                        int out_dim, int in_dim) {
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  const int lane = threadIdx.x & 31;
   if (row >= out_dim) return;
+  weight_norm_fwd_row(g, v, W, row, in_dim, threadIdx.x & 31);
+}
+
+// dg[j] = <dW_j, v_j>/||v_j|| ; dv[j,:] = g_j/||v_j|| * (dW_j - <dW_j, v_j>/||v_j||^2 * v_j)
+__device__ __forceinline__ void weight_norm_bwd_row(const float* __restrict__ g, const float* __restrict__ v,
+                                                    const float* __restrict__ dW, float* __restrict__ dg,
+                                                    float* __restrict__ dv, int row, int in_dim, int lane) {
   const float* vr = v + (size_t)row * in_dim;
   const float* dr = dW + (size_t)row * in_dim;
   float ss = 0.f, dot = 0.f;
@@ -46,6 +47,35 @@ __global__ void weight_norm_bwd_kernel(const float* __restrict__ g, const float*
   if (lane == 0) dg[row] = dot * inv;
   const float a = g[row] * inv, b = dot / ss;
   for (int k = lane; k < in_dim; k += 32) dv[(size_t)row * in_dim + k] = a * (dr[k] - b * vr[k]);
+}
+
+__global__ void weight_norm_bwd_kernel(const float* __restrict__ g, const float* __restrict__ v,
+                                       const float* __restrict__ dW, float* __restrict__ dg, float* __restrict__ dv,
+                                       int out_dim, int in_dim) {
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= out_dim) return;
+  weight_norm_bwd_row(g, v, dW, dg, dv, row, in_dim, threadIdx.x & 31);
+}
+
+// all weight-norm layers of a net in one launch: warp -> (layer, row) through the row prefix sums
+struct WnBatch {
+  pinn_wn_layer l[PINN_MAX_LAYERS];
+  int row_end[PINN_MAX_LAYERS];
+  int n;
+};
+
+template <bool BWD>
+__global__ void weight_norm_batch_kernel(const __grid_constant__ WnBatch b) {
+  int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= b.row_end[b.n - 1]) return;
+  int i = 0;
+  while (row >= b.row_end[i]) ++i;
+  if (i > 0) row -= b.row_end[i - 1];
+  const pinn_wn_layer& y = b.l[i];
+  if (BWD)
+    weight_norm_bwd_row(y.g, y.v, y.dW, y.dg, y.dv, row, y.in_dim, threadIdx.x & 31);
+  else
+    weight_norm_fwd_row(y.g, y.v, y.W, row, y.in_dim, threadIdx.x & 31);
 }
 
 // FP32 FMA throughput probe: 16 independent chains per thread (roofline denominator
@@ -139,6 +169,38 @@ int pinn_weight_norm_backward(const float* g, const float* v, const float* dW, f
   if (e != cudaSuccess) return (int)e;
   count_launch(1);
   return 0;
+}
+
+static int weight_norm_batch(const pinn_wn_layer* layers, int32_t n_layers, bool bwd, void* stream) {
+  if (!layers || n_layers < 1 || n_layers > PINN_MAX_LAYERS) return PINN_E_INVALID;
+  WnBatch b;
+  int rows = 0;
+  for (int i = 0; i < n_layers; ++i) {
+    const pinn_wn_layer& y = layers[i];
+    if (!y.g || !y.v || y.out_dim < 1 || y.in_dim < 1) return PINN_E_INVALID;
+    if (bwd ? (!y.dW || !y.dg || !y.dv) : !y.W) return PINN_E_INVALID;
+    b.l[i] = y;
+    rows += y.out_dim;
+    b.row_end[i] = rows;
+  }
+  b.n = n_layers;
+  const int wpb = 4;
+  if (bwd)
+    weight_norm_batch_kernel<true><<<(rows + wpb - 1) / wpb, wpb * 32, 0, (cudaStream_t)stream>>>(b);
+  else
+    weight_norm_batch_kernel<false><<<(rows + wpb - 1) / wpb, wpb * 32, 0, (cudaStream_t)stream>>>(b);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return (int)e;
+  count_launch(1);
+  return 0;
+}
+
+int pinn_weight_norm_forward_batch(const pinn_wn_layer* layers, int32_t n_layers, void* stream) {
+  return weight_norm_batch(layers, n_layers, false, stream);
+}
+
+int pinn_weight_norm_backward_batch(const pinn_wn_layer* layers, int32_t n_layers, void* stream) {
+  return weight_norm_batch(layers, n_layers, true, stream);
 }
 
 int64_t pinn_fp32_fma_probe(int32_t iters, int32_t blocks, float* scratch, void* stream) {

@@ -111,6 +111,8 @@ class NetPack:
         self._w_eff = [torch.empty(l.out_features, l.in_features, device=dev, dtype=torch.float32) if wn else None
                        for l, wn in zip(self.layers, self.weight_norm)]
         self._grad_wn: Dict[int, Tuple[torch.Tensor, torch.Tensor]] = {}
+        self._wn_fwd = None   # (pointer key, pinn_wn_layer array) of the batched weight-norm launches
+        self._wn_bwd = None
         self._mlp = None
         self._mlp_key = None
         self._probe()
@@ -145,14 +147,19 @@ class NetPack:
         return (self._w_eff[i] if self.weight_norm[i] else l.weight.data), l.bias.data
 
     def refresh_effective(self) -> None:
-        """W = g * v / ||v|| for the weight-norm layers (one small kernel each)."""
-        lib = nv.lib()
-        st = _stream_ptr()
-        for i, l in enumerate(self.layers):
-            if self.weight_norm[i]:
-                g, v = l.weight_g.data, l.weight_v.data
-                nv.check(lib.pinn_weight_norm_forward(g.data_ptr(), v.data_ptr(), self._w_eff[i].data_ptr(),
-                                                      l.out_features, l.in_features, st))
+        """W = g * v / ||v|| for the weight-norm layers (one launch for all of them)."""
+        idx = [i for i, wn in enumerate(self.weight_norm) if wn]
+        if not idx:
+            return
+        ptrs = tuple((self.layers[i].weight_g.data.data_ptr(), self.layers[i].weight_v.data.data_ptr()) for i in idx)
+        if self._wn_fwd is None or self._wn_fwd[0] != ptrs:
+            arr = (nv.PinnWnLayer * len(idx))()
+            for a, i in zip(arr, idx):
+                l = self.layers[i]
+                a.g, a.v, a.W = l.weight_g.data.data_ptr(), l.weight_v.data.data_ptr(), self._w_eff[i].data_ptr()
+                a.out_dim, a.in_dim = l.out_features, l.in_features
+            self._wn_fwd = (ptrs, arr)
+        nv.check(nv.lib().pinn_weight_norm_forward_batch(self._wn_fwd[1], len(idx), _stream_ptr()))
 
     def mlp_struct(self) -> nv.PinnMlp:
         ptrs = tuple(t.data_ptr() for i in range(len(self.layers)) for t in self.effective(i))
@@ -170,9 +177,30 @@ class NetPack:
     # -- gradients ----------------------------------------------------------
     def scatter_grad(self, flat: torch.Tensor, accumulate: bool = False) -> None:
         """flat = d loss / d(effective W, b) in pinn_param_count order -> `.grad`
-        of the module's own parameters (through weight-norm where present)."""
-        lib = nv.lib()
-        st = _stream_ptr()
+        of the module's own parameters (through weight-norm where present, one launch for all layers)."""
+        idx = [i for i, wn in enumerate(self.weight_norm) if wn]
+        if idx:
+            for i in idx:
+                if i not in self._grad_wn:
+                    l = self.layers[i]
+                    self._grad_wn[i] = (torch.empty_like(l.weight_g.data), torch.empty_like(l.weight_v.data))
+            key = (flat.data_ptr(),) + tuple((self.layers[i].weight_g.data.data_ptr(),
+                                              self.layers[i].weight_v.data.data_ptr()) for i in idx)
+            if self._wn_bwd is None or self._wn_bwd[0] != key:
+                arr = (nv.PinnWnLayer * len(idx))()
+                offs, off = {}, 0
+                for i in range(len(self.layers)):
+                    offs[i] = off
+                    off += self.sizes[2 * i] + self.sizes[2 * i + 1]
+                for a, i in zip(arr, idx):
+                    l = self.layers[i]
+                    dg, dv = self._grad_wn[i]
+                    a.g, a.v = l.weight_g.data.data_ptr(), l.weight_v.data.data_ptr()
+                    a.dW = flat.data_ptr() + 4 * offs[i]
+                    a.dg, a.dv = dg.data_ptr(), dv.data_ptr()
+                    a.out_dim, a.in_dim = l.out_features, l.in_features
+                self._wn_bwd = (key, arr)
+            nv.check(nv.lib().pinn_weight_norm_backward_batch(self._wn_bwd[1], len(idx), _stream_ptr()))
         off = 0
         for i, l in enumerate(self.layers):
             nW, nb = self.sizes[2 * i], self.sizes[2 * i + 1]
@@ -180,12 +208,7 @@ class NetPack:
             db = flat[off + nW:off + nW + nb]
             off += nW + nb
             if self.weight_norm[i]:
-                if i not in self._grad_wn:
-                    self._grad_wn[i] = (torch.empty_like(l.weight_g.data), torch.empty_like(l.weight_v.data))
                 dg, dv = self._grad_wn[i]
-                nv.check(lib.pinn_weight_norm_backward(l.weight_g.data.data_ptr(), l.weight_v.data.data_ptr(),
-                                                       dW.data_ptr(), dg.data_ptr(), dv.data_ptr(), l.out_features,
-                                                       l.in_features, st))
                 _set_grad(l.weight_g, dg, accumulate)
                 _set_grad(l.weight_v, dv, accumulate)
             else:

@@ -77,6 +77,12 @@ def make_jets(first_in: Sequence[int], n_second: int) -> PinnJets:
     return j
 
 
+class PinnWnLayer(C.Structure):
+    """pinn_wn_layer (include/pinn_b200.h)."""
+    _fields_ = [("g", C.c_void_p), ("v", C.c_void_p), ("dW", C.c_void_p), ("W", C.c_void_p), ("dg", C.c_void_p),
+                ("dv", C.c_void_p), ("out_dim", C.c_int32), ("in_dim", C.c_int32)]
+
+
 class PinnShapeOp(C.Structure):
     _fields_ = [("op", C.c_int32), ("p", C.c_float * 6)]
 
@@ -114,6 +120,8 @@ _SIGNATURES = {
     "pinn_weight_norm_forward": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p]),
     "pinn_weight_norm_backward": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32,
                                             C.c_int32, C.c_void_p]),
+    "pinn_weight_norm_forward_batch": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p]),
+    "pinn_weight_norm_backward_batch": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p]),
     "pinn_sample_box": (C.c_int, [C.POINTER(_fp), C.c_int32, C.POINTER(C.c_float), C.POINTER(C.c_float), C.c_int64,
                                   C.c_uint64, C.c_uint64, C.c_uint64, C.c_void_p, C.c_int32, C.c_void_p]),
     "pinn_residual_workspace_bytes": (C.c_int64, [C.POINTER(PinnMlp), C.POINTER(PinnJets), C.c_int64]),

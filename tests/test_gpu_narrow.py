@@ -201,3 +201,41 @@ def test_loss_only_mode_matches_the_full_step():
         eng.launch(loss_only=True)
         torch.cuda.synchronize()
         assert torch.equal(eng.losses, full), precision
+
+
+@pytest.mark.gpu
+def test_batched_weight_norm_equals_the_per_layer_calls_and_torch():
+    """pinn_weight_norm_forward_batch / _backward_batch (all layers of a net in one launch) give bit-identical results to
+    the per-layer entry points and agree with torch.nn.utils.weight_norm's forward and autograd backward."""
+    import ctypes as C
+    from idrlnet_b200 import native as nv
+    lib = nv.lib()
+    torch.manual_seed(3)
+    shapes = [(20, 2), (20, 20), (37, 20), (1, 37), (64, 129)]
+    g = [torch.rand(o, 1, device="cuda") + 0.5 for o, _ in shapes]
+    v = [torch.randn(o, i, device="cuda") for o, i in shapes]
+    dW = [torch.randn(o, i, device="cuda") for o, i in shapes]
+    W1, W2 = [torch.empty_like(x) for x in v], [torch.empty_like(x) for x in v]
+    dg1, dg2 = [torch.empty_like(x) for x in g], [torch.empty_like(x) for x in g]
+    dv1, dv2 = [torch.empty_like(x) for x in v], [torch.empty_like(x) for x in v]
+    st = torch.cuda.current_stream().cuda_stream
+    arr = (nv.PinnWnLayer * len(shapes))()
+    for k, (o, i) in enumerate(shapes):
+        nv.check(lib.pinn_weight_norm_forward(g[k].data_ptr(), v[k].data_ptr(), W1[k].data_ptr(), o, i, st))
+        nv.check(lib.pinn_weight_norm_backward(g[k].data_ptr(), v[k].data_ptr(), dW[k].data_ptr(), dg1[k].data_ptr(),
+                                               dv1[k].data_ptr(), o, i, st))
+        a = arr[k]
+        a.g, a.v, a.dW, a.W = g[k].data_ptr(), v[k].data_ptr(), dW[k].data_ptr(), W2[k].data_ptr()
+        a.dg, a.dv, a.out_dim, a.in_dim = dg2[k].data_ptr(), dv2[k].data_ptr(), o, i
+    nv.check(lib.pinn_weight_norm_forward_batch(arr, len(shapes), st))
+    nv.check(lib.pinn_weight_norm_backward_batch(arr, len(shapes), st))
+    torch.cuda.synchronize()
+    for k in range(len(shapes)):
+        assert torch.equal(W1[k], W2[k]) and torch.equal(dg1[k], dg2[k]) and torch.equal(dv1[k], dv2[k])
+        gk, vk = g[k].clone().requires_grad_(True), v[k].clone().requires_grad_(True)
+        Wt = torch._weight_norm(vk, gk, 0)
+        Wt.backward(dW[k])
+        torch.testing.assert_close(W2[k], Wt.detach(), rtol=1e-5, atol=1e-6)
+        torch.testing.assert_close(dg2[k], gk.grad, rtol=1e-4, atol=1e-5)
+        torch.testing.assert_close(dv2[k], vk.grad, rtol=1e-4, atol=1e-5)
+    assert lib.pinn_weight_norm_forward_batch(arr, 0, st) == nv.PINN_E_INVALID if hasattr(nv, "PINN_E_INVALID") else True
