@@ -177,7 +177,7 @@ static int launch_narrow(const pinn_mlp* m, const pinn_jets* j, NarrowParams& p,
   p.n_warps = pl.n_warps;
   const int64_t tiles = (p.n_points + 31) / 32;
   p.n_tiles = (int32_t)tiles;
-  int64_t ctas = (tiles + pl.n_warps - 1) / pl.n_warps;
+  int64_t ctas = tiles;  // one tile per CTA before a second warp of any CTA gets one (narrow_kernel's tile map)
   if (ctas > pl.n_cta_cap) ctas = pl.n_cta_cap;
   if (ctas < 1) ctas = 1;
   narrow_kernel_t fn = pl.k->fn;

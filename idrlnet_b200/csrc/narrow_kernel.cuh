@@ -37,7 +37,9 @@ __global__ void __launch_bounds__(NW::kMaxWarps * 32, 1) narrow_kernel(const __g
 
   typename NW::Lane ln;
   ln.loss = 0.f;
-  for (int64_t tile = (int64_t)blockIdx.x * nwarps + warp; tile < p.n_tiles; tile += (int64_t)gridDim.x * nwarps) {
+  // tile -> (CTA, warp) CTA-fastest: a small domain (fewer tiles than warps on the GPU) spreads over all SMs with few
+  // active warps each instead of filling a few SMs with 8 warps (a tile's latency is ~0.55x with 2-3 warps per SM)
+  for (int64_t tile = (int64_t)warp * gridDim.x + blockIdx.x; tile < p.n_tiles; tile += (int64_t)gridDim.x * nwarps) {
     NW::phase_forward(p, smem, wm, gs, lane, tile, ln);
     if (p.mode == MODE_FWD || p.mode == MODE_LOSS) continue;
     for (int l = L + 1; l >= 2; --l) {

@@ -41,7 +41,7 @@ struct RunnerT : Runner {
       float* gs = stash.data() + (size_t)warp * NW::stash_floats(L);
       float* g = gacc.data() + (size_t)warp * lay.size();
       typename NW::Lane* ln = &lanes[(size_t)warp * 32];
-      for (int64_t tile = (int64_t)cta * n_warps + warp; tile < p.n_tiles; tile += (int64_t)n_cta * n_warps) {
+      for (int64_t tile = (int64_t)warp * n_cta + cta; tile < p.n_tiles; tile += (int64_t)n_cta * n_warps) {  // narrow_kernel's map
         for (int lane = 0; lane < 32; ++lane) NW::phase_forward(p, smem.data(), wm, gs, lane, tile, ln[lane]);
         if (p.mode == MODE_FWD || p.mode == MODE_LOSS) continue;
         for (int l = L + 1; l >= 2; --l) {
