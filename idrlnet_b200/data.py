@@ -17,17 +17,19 @@ __all__ = ["DataNode", "get_data_node", "get_data_nodes", "datanode", "SampleDom
 
 
 def _lambdify_np(expr, names):
-    """Evaluate a constant / SymPy target on the sampled numpy columns
-    (idrlnet/data.py:82-92 via geo_utils/sympy_np.lambdify_np)."""
-    try:
-        const = float(expr)
-        return lambda **kw: numpy.zeros_like(next(iter(kw.values()))) + const
-    except (TypeError, ValueError):
-        pass
-    e = sympy.sympify(expr)
-    used = [s.name for s in e.free_symbols]
-    fn = sympy.lambdify([sympy.Symbol(n) for n in used], e, "numpy")
-    return lambda **kw: numpy.zeros_like(next(iter(kw.values()))) + fn(*[kw[n] for n in used])
+    """Evaluate a target on the sampled numpy columns exactly as idrlnet/data.py:82-92 does: through
+    `geo_utils.sympy_np.lambdify_np`, which takes numbers, bools, python callables `f(**columns)` and SymPy
+    expressions (compiled once and cached); the result is broadcast to the column shape."""
+    from .geo_utils.sympy_np import lambdify_np
+    fn = lambdify_np(expr, names)
+
+    def call(**kw):
+        like = next(iter(kw.values()))
+        out = numpy.asarray(fn(**kw))
+        if out.dtype == bool:
+            out = out.astype(numpy.float64)
+        return out if out.shape == numpy.shape(like) else numpy.broadcast_to(out, numpy.shape(like)).copy()
+    return call
 
 
 def _target_on_device(expr, input_vars, like: torch.Tensor) -> torch.Tensor:

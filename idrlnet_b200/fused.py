@@ -398,7 +398,20 @@ class StepEngine:
         self.ws = torch.empty(max(self.ws_bytes // 4, 1), device=pack.device, dtype=torch.float32)
         # flat gradient with the per-domain losses appended: ONE buffer to all-reduce
         self.flat = torch.zeros(pack.n_params + len(self.domains), device=pack.device, dtype=torch.float32)
-        self.sigmas = torch.tensor([d.sigma for d in self.domains], device=pack.device, dtype=torch.float32)
+        # loss-only evaluations (the reference's post-update re-evaluation) write into their own buffer: `.grad`
+        # of the module parameters may be views of `flat` and must survive until the next gradient step
+        self._flat_eval: Optional[torch.Tensor] = None
+        self._last = self.flat
+        self._sigma_vals = [d.sigma for d in self.domains]
+        self.sigmas = torch.tensor(self._sigma_vals, device=pack.device, dtype=torch.float32)
+
+    def set_domains(self, domains: Sequence[FusedDomain]) -> None:
+        """Swap in another binding of the same domains (fresh points); domain weights are re-read."""
+        self.domains = list(domains)
+        vals = [d.sigma for d in self.domains]
+        if vals != self._sigma_vals:
+            self._sigma_vals = vals
+            self.sigmas = torch.tensor(vals, device=self.pack.device, dtype=torch.float32)
 
     @property
     def grad(self) -> torch.Tensor:
@@ -406,7 +419,8 @@ class StepEngine:
 
     @property
     def losses(self) -> torch.Tensor:
-        return self.flat[self.pack.n_params:]
+        """Per-domain un-weighted losses of the most recent launch."""
+        return self._last[self.pack.n_params:]
 
     def launch(self, timed: Optional[Tuple[int, "torch.cuda.Event", "torch.cuda.Event"]] = None,
                loss_only: bool = False) -> None:
@@ -425,8 +439,15 @@ class StepEngine:
             nv.check(fn(C.byref(mlp), C.byref(d.jets), C.byref(d.struct), self.ws.data_ptr(), self.ws_bytes, i, 1 if i else 0, st))
             if timed is not None and timed[0] == i:
                 timed[2].record()
+        if loss_only:
+            if self._flat_eval is None:
+                self._flat_eval = torch.zeros_like(self.flat)
+            out = self._flat_eval
+        else:
+            out = self.flat
+        self._last = out
         nv.check(lib.pinn_step_finalize(C.byref(mlp), C.byref(self.domains[0].jets), self.ws.data_ptr(), self.ws_bytes,
-                                        len(self.domains), self.flat.data_ptr(), 0, self.losses.data_ptr(), st))
+                                        len(self.domains), out.data_ptr(), 0, out.data_ptr() + 4 * pack.n_params, st))
 
     def total_loss(self) -> torch.Tensor:
         return torch.dot(self.losses, self.sigmas)

@@ -111,12 +111,43 @@ class VertexTaskPipeline:
         for n in self.evaluation_order_list:
             if isinstance(n, NetNode):
                 try:
+                    self._check_no_chain_through(n, wanted)
                     js = _JetServe.build(n, wanted, sampled, exprs)
                 except cp.NotFusable as e:
                     logger.debug(f"net {n.name}: torch path ({e})")
                     js = None
                 if js is not None:
                     self._jet_plans[id(n)] = js
+
+    def _check_no_chain_through(self, net: NetNode, wanted) -> None:
+        """A jet-served net returns columns with NO autograd edge to the coordinates (the input derivatives are the
+        jet channels).  That is only sound when every derivative symbol that depends on the net is a derivative OF
+        one of the net's own outputs.  A wanted `flux__x` where `flux` is an ExpressionNode / PdeNode output built
+        from `u`, or `v__x` of a second net fed with `u`, needs the chain rule through this net
+        (idrlnet/variable.py:161-208 differentiates whatever the graph produced): such a pipeline keeps the torch
+        path for this net instead of silently getting zeros from `allow_unused`."""
+        producer = {}
+        for n in self.evaluation_order_list:
+            for out in n.outputs:
+                producer.setdefault(out, n)
+        mine = set(net.outputs)
+
+        def reaches(name: str, seen: set) -> bool:
+            base = cp.split_name(name)[0]
+            if base in mine:
+                return True
+            node = producer.get(name) or producer.get(base)
+            if node is None or id(node) in seen:
+                return False
+            seen.add(id(node))
+            return any(reaches(q, seen) for q in list(node.inputs) + list(node.derivatives))
+
+        for w in wanted:
+            base, derivs = cp.split_name(w)
+            if not derivs or base in mine:
+                continue
+            if reaches(base, set()):
+                raise cp.NotFusable(f"{w}: derivative of a downstream quantity needs the chain rule through net {net.name}")
 
     def operation_order(self, invar: Variables):
         for node in self.evaluation_order_list:

@@ -17,10 +17,15 @@ the tensor cores (stated tolerance 1e-2); the default "fp32" holds 1e-5.  Everyt
 `torch.distributed` the points of every domain are sharded over the ranks and
 the flat gradient (+ loss scalars) is all-reduced once per step.
 
-Deviation, on purpose: the reference re-samples and re-evaluates the loss after
-the optimiser step only to return/log it (idrlnet/solver.py:341-344), doubling the
-cost; here `train_pipe` returns the loss of the step it just took unless
-`post_step_loss=True` is passed.
+Reference semantics are the default: like idrlnet/solver.py:341-344, `train_pipe`
+re-samples every domain after the optimiser step and returns / logs the loss of that
+second, gradient-free evaluation (run here by the loss-only mode of the kernels,
+`pinn_loss_fused`, about a third of a full step), so an unchanged example sees the
+same returned losses, the same Signals (BEFORE/AFTER_COMPUTE_LOSS fire twice per
+step) and the same consumption of the NumPy sampling stream as with the reference.
+`Solver(post_step_loss=False)` (or IDRLNET_B200_POST_STEP_LOSS=0) is the opt-in fast
+mode: one sampling round per step, the returned loss is the one the gradient was
+taken of.
 """
 from __future__ import annotations
 
@@ -55,14 +60,16 @@ class Solver(Notifier, Optimizable):
                  pdes: Optional[List] = None, network_dir: str = "./network_dir", summary_dir: Optional[str] = None,
                  max_iter: int = 1000, save_freq: int = 100, print_freq: int = 10, loading: bool = True,
                  init_network_dirs: Optional[List[str]] = None, opt_config: Dict = None, schedule_config: Dict = None,
-                 result_dir="train_domain/results", fused: Optional[bool] = None, post_step_loss: bool = False,
+                 result_dir="train_domain/results", fused: Optional[bool] = None, post_step_loss: Optional[bool] = None,
                  precision: Optional[str] = None, **kwargs):
         from . import callbacks
         self.network_dir = network_dir
         self.domain_losses = {d.name: d.loss_fn for d in sample_domains}
         self.netnodes: List[NetNode] = netnodes
         self.fused_enabled = fused
-        self.post_step_loss = post_step_loss
+        if post_step_loss is None:  # reference behaviour unless the fast mode is asked for
+            post_step_loss = os.environ.get("IDRLNET_B200_POST_STEP_LOSS", "1") not in ("0", "false", "False")
+        self.post_step_loss = bool(post_step_loss)
         # arithmetic of the layer GEMMs of wide (H > 32) nets: "fp32" (FP32 FMA, parity, default), "fp32x3" (tensor
         # cores, 3xTF32 splitting), "tf32" / "tf32_streamed" (tensor cores); None -> IDRLNET_B200_PRECISION or "fp32"
         self.precision = precision
@@ -196,6 +203,8 @@ class Solver(Notifier, Optimizable):
                 nn = by_name[cd.net.name]
                 if nn.fixed or nn.require_no_grad:
                     raise cp.NotFusable("fixed / no-grad net")
+                if isinstance(dom.sigma, torch.Tensor) and dom.sigma.requires_grad:
+                    raise cp.NotFusable("trainable domain weight (var_sigma): the sigma leaf gets its grad from autograd")
                 key = id(nn.net)
                 if key not in self._packs:
                     self._packs[key] = fused.NetPack(nn.net, precision=self.precision)
@@ -300,7 +309,7 @@ class Solver(Notifier, Optimizable):
         for eng in engines:
             eng.launch(loss_only=not grads)  # the post-update re-evaluation needs no reverse pass
             if dist is not None:
-                dist.all_reduce(eng.flat)
+                dist.all_reduce(eng.flat if grads else eng.losses)
             for fd, l in zip(eng.domains, eng.losses):
                 comps[f"{fd.name}_loss"] = l
         ordered = {f"{d.name}_loss": comps[f"{d.name}_loss"] for d in self.sample_domains if f"{d.name}_loss" in comps}
@@ -317,13 +326,31 @@ class Solver(Notifier, Optimizable):
             if isinstance(gen_loss, torch.Tensor) and gen_loss.requires_grad:
                 gen_loss.backward()
                 if dist is not None:
-                    for nn in self.netnodes:
-                        for p in nn.net.parameters():
-                            if p.grad is not None:
-                                dist.all_reduce(p.grad)
+                    self._all_reduce_param_grads(dist)
         for eng in engines:
             eng.pack.scatter_grad(eng.grad, accumulate=bool(generic) or len(engines) > 1)
         return loss.detach() if isinstance(loss, torch.Tensor) else loss
+
+    def _all_reduce_param_grads(self, dist) -> None:
+        """SUM of the generic-path `.grad`s over the ranks: every Parameter once (a net shared through
+        `get_shared_net_node` shows up in two NetNodes with the same Parameter objects), flattened into one
+        buffer -> one collective, as on the fused path."""
+        seen, grads = set(), []
+        for nn in self.netnodes:
+            if nn.is_reference:
+                continue
+            for p in nn.net.parameters():
+                if p.grad is not None and id(p) not in seen:
+                    seen.add(id(p))
+                    grads.append(p.grad)
+        if not grads:
+            return
+        flat = torch.cat([g.reshape(-1) for g in grads])
+        dist.all_reduce(flat)
+        off = 0
+        for g in grads:
+            g.copy_(flat[off:off + g.numel()].view_as(g))
+            off += g.numel()
 
     def _bind_fused(self, names, in_var, true_out, lambda_out):
         from . import fused
@@ -335,6 +362,7 @@ class Solver(Notifier, Optimizable):
             for k in list(true_out[n].keys()):
                 if k not in lambdas and ("lambda_" + k) in pts:  # idrlnet/solver.py:371-378
                     lambdas[k] = pts["lambda_" + k]
+            fd.sigma = float(self.get_sample_domain(n).sigma)  # read every step, as idrlnet/solver.py:394 does
             fd.bind(pts, {k: v for k, v in true_out[n].to_torch_tensor_().items()}, lambdas, pts.get("area"))
             groups.setdefault(id(self._fused_owner[n].net), []).append(fd)
         engines = []
@@ -346,7 +374,7 @@ class Solver(Notifier, Optimizable):
                 eng._sig = sig
                 self._engines[key] = eng
             else:
-                eng.domains = fds
+                eng.set_domains(fds)
             engines.append(eng)
         return engines
 

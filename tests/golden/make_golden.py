@@ -284,7 +284,18 @@ def cfg_ns_unsteady_wide():
         seq=[3, 64, 64, 64, 3]))
 
 
+def cfg_ns_unsteady_xl():
+    """The BASELINE configs[4] net at its TRUE shape: `Arch.mlp_xl` = 3-512x6-3 SiLU + weight-norm
+    (idrlnet/architecture/mlp.py:235-246), 1 319 942 parameters -- the shape `bench.py --config ns_xl` times."""
+    return _cfg_ns_unsteady(lambda: sc.get_net_node(
+        inputs=("x", "y", "t"), outputs=("u", "v", "p"), name="net", arch=sc.Arch.mlp_xl))
+
+
+# fixtures whose parameter gradients are stored in float32 only (the FP64 run's, rounded; 5 MB instead of 16 MB)
+COMPACT = {"ns_unsteady_xl"}
+
 CONFIGS = {
+    "ns_unsteady_xl": cfg_ns_unsteady_xl,
     "simple_poisson": cfg_simple_poisson,
     "burgers": cfg_burgers,
     "allen_cahn": cfg_allen_cahn,
@@ -401,6 +412,10 @@ def build(name):
                 flat[f"{tag}/dom/{dname}/{k}"] = a
         for k, a in grads.items():
             if a is not None:
+                if name in COMPACT:
+                    if tag == "ref32":
+                        continue
+                    a = a.astype(np.float32)
                 flat[f"{tag}/grad/{k}"] = a
         flat[f"{tag}/grad_none"] = np.array(json.dumps(sorted(k for k, a in grads.items() if a is None)))
     torch.set_default_dtype(torch.float32)
@@ -412,5 +427,5 @@ def build(name):
 
 
 if __name__ == "__main__":
-    for cfg in (sys.argv[1:] or list(CONFIGS)):
+    for cfg in (sys.argv[1:] or [c for c in CONFIGS if c not in COMPACT]):
         build(cfg)

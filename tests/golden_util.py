@@ -6,6 +6,9 @@ import numpy as np
 
 GOLDEN_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 CONFIGS = ["simple_poisson", "burgers", "allen_cahn", "ldc", "ns_unsteady", "ns_unsteady_wide"]
+# the mlp_xl net at its true shape 3-512x6-3 (BASELINE configs[4]); gradients of the reference's FP64 run only,
+# stored rounded to float32 (see make_golden.COMPACT)
+XL = "ns_unsteady_xl"
 
 
 def load(name):

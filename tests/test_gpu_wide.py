@@ -179,3 +179,37 @@ def test_whole_gradient_normwise(name, precision, bound):
         full = np.concatenate([np.zeros(sz) if p is None else np.asarray(p).ravel() for p, sz in zip(parts, sizes)])
         err = np.abs(flat - full).max() / np.abs(full).max()
         assert err <= bound, (net, err)
+
+
+def _raw_param_grads_vs_golden(modules, flat, tol):
+    worst = 0.0
+    for pname, g in gu.ref_grads(flat, "ref64").items():
+        net, rest = pname.split("/", 1)
+        p = dict(modules[net].named_parameters())[rest]
+        err = np.max(np.abs(p.grad.detach().cpu().numpy().reshape(g.shape) - g)) / max(np.max(np.abs(g)), 1e-30)
+        worst = max(worst, err)
+        assert err <= tol, (pname, err)
+    return worst
+
+
+# precision -> (norm-wise bound on losses, on every effective-gradient segment (x20 in _check_grads), on the raw
+# weight_g / weight_v / bias gradients of the reference's FP64 run)
+XL_BOUNDS = {"fp32": (1e-5, TOL, 20 * TOL), "fp32x3": (1e-5, TOL, 20 * TOL), "tf32_streamed": (1e-2, 1e-2 / 20, 1e-2),
+             "tf32": (1e-2, 1e-2 / 20, 1e-2)}
+
+
+@pytest.mark.parametrize("precision", list(XL_BOUNDS))
+def test_golden_mlp_xl_true_shape(precision):
+    """BASELINE configs[4] at the TRUE net shape: Arch.mlp_xl 3-512x6-3 SiLU + weight-norm (1 319 942 parameters),
+    NS residuals with u_t / v_t + the L1 data domain -- the shape `bench.py --config ns_xl` times -- against the
+    golden vectors the real reference produced (tests/golden/make_golden.py::cfg_ns_unsteady_xl): losses vs its
+    FP32 run, raw parameter gradients vs its FP64 run, in every arithmetic mode of the wide path."""
+    problem, flat = gu.load(gu.XL)
+    ltol, gtol, rawtol = XL_BOUNDS[precision]
+    ref = po.training_step(problem, dtype=torch.float64)
+    grads, losses, skipped, modules = pu.run_cuda_fused(problem, precision=precision)
+    assert not skipped, skipped
+    for k, v in gu.ref_components(flat, "ref64").items():
+        assert abs(losses[k[:-5]] - v) <= 10 * ltol * abs(v), (k, losses[k[:-5]], v)
+    _check_grads(ref, grads, problem, gtol)
+    _raw_param_grads_vs_golden(modules, flat, rawtol)

@@ -53,3 +53,28 @@ def test_oracle_matches_reference_fp32(name):
 @pytest.mark.parametrize("name", gu.CONFIGS)
 def test_oracle_matches_reference_fp64(name):
     _check(name, torch.float64, "ref64", 1e-12)
+
+
+def test_oracle_matches_reference_at_the_true_mlp_xl_shape():
+    """Arch.mlp_xl 3-512x6-3 SiLU + weight-norm (idrlnet/architecture/mlp.py:235-246): every graph variable of the
+    reference's FP32 and FP64 runs, the losses, and the FP64 run's parameter gradients (stored as float32, hence the
+    2e-7 floor on top of the FP64 agreement)."""
+    name = gu.XL
+    problem, flat = gu.load(name)
+    for dtype, tag, tol in ((torch.float32, "ref32", 2e-5), (torch.float64, "ref64", 1e-11)):
+        want = {d["name"]: [k for k in gu.ref_domain(flat, tag, d["name"])] for d in problem["domains"]}
+        res = po.training_step(problem, dtype=dtype, want=want)
+        for d in problem["domains"]:
+            for k, v in gu.ref_domain(flat, tag, d["name"]).items():
+                err = gu.normwise(res["domains"][d["name"]][k], v)
+                assert err <= tol, f"{d['name']}/{k}: {err:.3e}"
+        ref_loss = float(flat[f"{tag}/loss"])
+        assert abs(res["loss"] - ref_loss) <= 10 * tol * abs(ref_loss)
+    n_checked = 0
+    for pname, g in gu.ref_grads(flat, "ref64").items():
+        net, rest = pname.split("/", 1)
+        parts = rest.split(".")
+        og = res["grads"][net][int(parts[1].split("_")[1])][_KEY[parts[2]]]
+        assert gu.normwise(og.reshape(g.shape), g) <= 2e-7, pname
+        n_checked += g.size
+    assert n_checked == 1319942  # SURVEY 8: P of Arch.mlp_xl on (x, y, t) -> (u, v, p)
