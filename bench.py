@@ -1,24 +1,28 @@
 #!/usr/bin/env python
-"""Headline benchmark: collocation points / second per PINN training step
-(forward jets + residual + loss + backward + gradient reduction + Adam) on the
-Burgers configuration of BASELINE.json (configs[1]: examples/burgers_equation,
-default MLP 2-20x4-1 swish + weight-norm, 2^20 interior + 10240 IC + 10240 BC
-synthetic points per step per GPU).
+"""Headline benchmark: collocation points / second per PINN training step (forward jets + residual + loss +
+backward + gradient reduction + Adam) on the Burgers configuration of BASELINE.json (configs[1]:
+examples/burgers_equation, default MLP 2-20x4-1 swish + weight-norm, 2^20 interior + 10240 IC + 10240 BC synthetic
+points per step per GPU), driven through the package's PUBLIC API: `Solver.train_pipe()` on sampling domains that
+hand out device-resident (value) or freshly uploaded (e2e) points.
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
 
-Prints ONE JSON line (see the driver contract in the task statement).
-`--impl reference` times the reference's own algorithm (the CPU oracle port,
-oracle/pinn_oracle.py: torch autograd on the host cores) on a bounded sample of
-the same workload.
+Prints ONE JSON line (driver contract).  Beside the headline it carries a `configs` object: the other BASELINE
+configurations at their stated sizes (simple_poisson 2^20, ldc 2^21 per GPU = 16 M over 8, allen_cahn 2^22 with its
+periodic-BC and re-sampling domains, ns_unsteady `mlp_xl` 2^20 at N=1 / 2^26 over N >= 2 GPUs), each with its
+roofline and -- at N=1 -- the UNMODIFIED reference (baseline/_ref, `idrlnet.use_gpu(0)`) timed on the same B200 on
+the same workload (baseline/ref_harness.py: strict pass of idrlnet/solver.py:329-339, and train_pipe as shipped).
+
+`--impl reference` times the reference's own CPU implementation (the same unmodified package) on the host cores
+on a bounded sample of the headline workload.
 """
 import argparse
-import ctypes as C
 import json
 import math
 import os
 import subprocess
 import sys
+import tempfile
 import threading
 import time
 
@@ -29,220 +33,25 @@ if ROOT not in sys.path:
 import numpy as np
 import torch
 
+from baseline import workloads as wl
+
 METRIC = "collocation points/sec per train step (fwd+derivs+residual+bwd+optimizer)"
-NU = 0.01 / math.pi
-N_ROTATE = 32  # distinct point batches; 32 * 8.4 MB = 270 MB > 126 MB L2
+L2_BYTES = 126e6
+HARNESS = os.path.join(ROOT, "baseline", "ref_harness.py")
+# bounded CPU samples (fraction of the one-GPU workload) for the reference's CPU path
+CPU_SAMPLE = {"burgers": 1 / 8, "poisson": 1 / 8, "ldc": 1 / 256, "allen_cahn": 1 / 128, "ns_xl": 1 / 512}
+# wide-net arithmetic modes reported per config: (key suffix, precision)
+WIDE_MODES = (("", "fp32x3"), ("_tf32", "tf32"))
+# steps of the secondary configs (their steps are 50-500 ms long)
+SECONDARY_STEPS = {"poisson": (5, 50), "ldc": (3, 10), "allen_cahn": (3, 8), "ns_xl": (3, 6)}
 
 
-def peaks():
+def measured_peaks():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(path):
         with open(path) as f:
-            d = json.load(f)
-        return d.get("hbm_gbs", 6650.0), "measured (MEASURED_PEAKS.json)"
-    return 6650.0, "fallback (B200_PROFILING.md)"
-
-
-def tensor_peak_tf32():
-    """Dense TF32 tensor throughput: half the BF16 cuBLAS figure (sustained: the kernels are timed inside a step)."""
-    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
-    if os.path.exists(path):
-        with open(path) as f:
-            d = json.load(f)
-        if "bf16_tflops_sustained" in d:
-            return d["bf16_tflops_sustained"] / 2, "TF32 = 1/2 of the measured sustained BF16 cuBLAS rate (MEASURED_PEAKS.json)"
-    return 2250.0 / 2 / 2, "fallback: 1/2 of half the nominal dense BF16 peak (B200_PROFILING.md)"
-
-
-# --------------------------------------------------------------------------- #
-# synthetic workloads (SURVEY.md 8(d2)); "burgers" is the headline (BASELINE configs[1])
-# --------------------------------------------------------------------------- #
-F32 = np.float32
-
-
-def _u(rng, lo, hi, n):
-    return rng.uniform(lo, hi, n).astype(F32)
-
-
-def _sample_burgers(rng, n):
-    ic_x = _u(rng, -1, 1, n["ic"])
-    return {"int_x": _u(rng, -1, 1, n["int"]), "int_t": _u(rng, 0, 1, n["int"]),
-            "ic_x": ic_x, "ic_t": np.zeros(n["ic"], F32), "ic_u": (-np.sin(np.pi * ic_x)).astype(F32),
-            "bc_x": np.where(rng.uniform(size=n["bc"]) < 0.5, -1.0, 1.0).astype(F32), "bc_t": _u(rng, 0, 1, n["bc"])}
-
-
-def _sample_poisson(rng, n):
-    nb = n["bc"]
-    side = np.where(rng.uniform(size=nb) < 0.5, -1.0, 1.0).astype(F32)
-    side2 = np.where(rng.uniform(size=nb) < 0.5, -1.0, 1.0).astype(F32)
-    return {"int_x": _u(rng, -1, 1, n["int"]), "int_y": _u(rng, -1, 1, n["int"]),
-            "lr_x": side, "lr_y": _u(rng, -1, 1, nb),
-            "ud_x": _u(rng, -1, 1, nb), "ud_y": side2, "ud_nx": np.zeros(nb, F32), "ud_ny": side2.copy()}
-
-
-def _sample_ldc(rng, n):
-    ix, iy = _u(rng, -0.05, 0.05, n["int"]), _u(rng, -0.05, 0.05, n["int"])
-    sdf = np.minimum(0.05 - np.abs(ix), 0.05 - np.abs(iy)).astype(F32)
-    nw = n["wall"]
-    w = rng.integers(0, 3, nw)
-    s = _u(rng, -0.05, 0.05, nw)
-    wx = np.where(w == 0, -0.05, np.where(w == 1, 0.05, s)).astype(F32)
-    wy = np.where(w == 2, -0.05, s).astype(F32)
-    lx = _u(rng, -0.05, 0.05, n["lid"])
-    return {"int_x": ix, "int_y": iy, "int_sdf": sdf, "wall_x": wx, "wall_y": wy,
-            "lid_x": lx, "lid_y": np.full(n["lid"], 0.05, F32), "lid_lam": (1 - 20 * np.abs(lx)).astype(F32)}
-
-
-def _sample_allen(rng, n):
-    ic_x = _u(rng, -1, 1, n["ic"])
-    return {"int_x": _u(rng, -1, 1, n["int"]), "int_t": _u(rng, 0, 1, n["int"]),
-            "ic_x": ic_x, "ic_t": np.zeros(n["ic"], F32), "ic_u": (ic_x ** 2 * np.cos(np.pi * ic_x)).astype(F32)}
-
-
-def _sample_ns(rng, n):
-    nd = n["data"]
-    return {"int_x": _u(rng, 1, 8, n["int"]), "int_y": _u(rng, -2, 2, n["int"]), "int_t": _u(rng, 0, 20, n["int"]),
-            "d_x": _u(rng, 1, 8, nd), "d_y": _u(rng, -2, 2, nd), "d_t": _u(rng, 0, 20, nd),
-            "d_u": _u(rng, -1, 1, nd), "d_v": _u(rng, -1, 1, nd), "d_p": _u(rng, -1, 1, nd)}
-
-
-def _flop(d, H, L, C, pairs):  # SURVEY.md 8(d4): F_step = 3 * 2 * [d*H + C*(L-1)*H^2 + n_pairs*H]
-    return 3 * 2 * (d * H + C * (L - 1) * H * H + pairs * H)
-
-
-def workload_configs():
-    import idrlnet_b200.shortcut as sc
-    return {
-        "burgers": dict(
-            title="burgers_equation (BASELINE configs[1])", net_desc="Arch.mlp 2-20x4-1 swish weight-norm",
-            inputs=("x", "t"), outputs=("u",), oracle_act="silu",
-            net=lambda: sc.get_net_node(inputs=("x", "t"), outputs=("u",), name="net1", arch=sc.Arch.mlp),
-            pdes=lambda: [sc.BurgersNode(u="u", v=NU)],
-            sizes={"int": 1 << 20, "ic": 10240, "bc": 10240}, sample=_sample_burgers,
-            domains=[  # (name, size key, columns {symbol: column}, targets, lambdas, area)
-                ("t_boundary", "ic", {"x": "ic_x", "t": "ic_t"}, {"u": "ic_u"}, {}, lambda n: 2.0 / n["ic"]),
-                ("burgers_equation", "int", {"x": "int_x", "t": "int_t"}, {"burgers_u": 0.0}, {}, lambda n: 2.0 / n["int"]),
-                ("x_boundary", "bc", {"x": "bc_x", "t": "bc_t"}, {"u": 0.0}, {}, lambda n: 2.0 / n["bc"]),
-            ], timed=1, flop_per_point=_flop(2, 20, 4, 4, 4), bytes_per_point=8,
-            kernel="narrow_kernel<NarrowWarpPair<20,2,1,silu>> (interior domain; channel pairs, packed FMAs)", bound="fp32"),
-        "poisson": dict(
-            title="simple_poisson (BASELINE configs[0])", net_desc="Arch.mlp 2-20x4-1 swish weight-norm",
-            inputs=("x", "y"), outputs=("T",), oracle_act="silu",
-            net=lambda: sc.get_net_node(inputs=("x", "y"), outputs=("T",), name="net1", arch=sc.Arch.mlp),
-            pdes=lambda: [sc.DiffusionNode(T="T", D=1.0, Q=0.0, dim=2, time=False), sc.NormalGradient("T", dim=2, time=False)],
-            sizes={"int": 1 << 20, "bc": 1 << 16}, sample=_sample_poisson,
-            domains=[
-                ("LeftRight", "bc", {"x": "lr_x", "y": "lr_y"}, {"T": 0.0}, {}, lambda n: 4.0 / n["bc"]),
-                ("heat_domain", "int", {"x": "int_x", "y": "int_y"}, {"diffusion_T": 1.0}, {}, lambda n: 4.0 / n["int"]),
-                ("up_down", "bc", {"x": "ud_x", "y": "ud_y", "normal_x": "ud_nx", "normal_y": "ud_ny"},
-                 {"normal_gradient_T": 0.0}, {}, lambda n: 4.0 / n["bc"]),
-            ], timed=1, flop_per_point=_flop(2, 20, 4, 5, 5), bytes_per_point=8,
-            kernel="narrow_kernel<20,2,2,silu> (interior domain)", bound="fp32"),
-        "ldc": dict(
-            title="ldc (BASELINE configs[3])", net_desc="MLP 2-100x4-3 tanh Xavier",
-            inputs=("x", "y"), outputs=("u", "v", "p"), oracle_act="tanh",
-            net=lambda: sc.NetNode(inputs=("x", "y"), outputs=("u", "v", "p"), name="net_u",
-                                   net=sc.MLP([2, 100, 100, 100, 100, 3], activation=sc.Activation.tanh,
-                                              initialization=sc.Initializer.Xavier_uniform, weight_norm=False)),
-            pdes=lambda: [sc.NavierStokesNode(nu=0.01, rho=1.0, dim=2, time=False)],
-            sizes={"int": 1 << 18, "wall": 1 << 14, "lid": 1 << 12}, sample=_sample_ldc,
-            domains=[
-                ("left_right_down", "wall", {"x": "wall_x", "y": "wall_y"}, {"u": 0.0, "v": 0.0}, {}, lambda n: 1e-4),
-                ("flow_domain", "int", {"x": "int_x", "y": "int_y"}, {"continuity": 0.0, "momentum_x": 0.0, "momentum_y": 0.0},
-                 {"continuity": "int_sdf", "momentum_x": "int_sdf", "momentum_y": "int_sdf"}, lambda n: 0.01 / n["int"]),
-                ("up", "lid", {"x": "lid_x", "y": "lid_y"}, {"u": 1.0, "v": 0.0}, {"u": "lid_lam"}, lambda n: 1e-4),
-            ], timed=1, flop_per_point=_flop(2, 100, 4, 5, 12), bytes_per_point=12,
-            kernel="wide gemm_rows/gemm_dw kernels (interior domain)", bound="fp32"),
-        "allen_cahn": dict(
-            title="allen_cahn (BASELINE configs[2])", net_desc="MLP 2-128x4-2 tanh weight-norm",
-            inputs=("x", "t"), outputs=("u",), oracle_act="tanh",
-            net=lambda: sc.NetNode(inputs=("x", "t"), outputs=("u",), name="net1",
-                                   net=sc.MLP([2, 128, 128, 128, 128, 2], activation=sc.Activation.tanh)),
-            pdes=lambda: [sc.AllenCahnNode(u="u", gamma_1=0.0001, gamma_2=5)],
-            sizes={"int": 1 << 18, "ic": 1 << 14}, sample=_sample_allen,
-            domains=[
-                ("AllenInit", "ic", {"x": "ic_x", "t": "ic_t"}, {"u": "ic_u"}, {"u": 100.0}, lambda n: 2.0 / n["ic"]),
-                ("allen_domain", "int", {"x": "int_x", "t": "int_t"}, {"AllenCahn_u": 0.0}, {}, lambda n: 2.0 / n["int"]),
-            ], timed=1, flop_per_point=_flop(2, 128, 4, 4, 4), bytes_per_point=8,
-            kernel="wide gemm_rows/gemm_dw kernels (interior domain)", bound="fp32"),
-        "ns_xl": dict(
-            title="ns_unsteady with Arch.mlp_xl (BASELINE configs[4])", net_desc="Arch.mlp_xl 3-512x6-3 SiLU weight-norm",
-            inputs=("x", "y", "t"), outputs=("u", "v", "p"), oracle_act="silu",
-            net=lambda: sc.get_net_node(inputs=("x", "y", "t"), outputs=("u", "v", "p"), name="net", arch=sc.Arch.mlp_xl),
-            pdes=lambda: [sc.NavierStokesNode(nu=0.01, rho=1.0, dim=2, time=True)],
-            sizes={"int": 1 << 15, "data": 5000}, sample=_sample_ns,
-            domains=[
-                ("NS_domain", "data", {"x": "d_x", "y": "d_y", "t": "d_t"}, {"u": "d_u", "v": "d_v", "p": "d_p"}, {},
-                 lambda n: 1.0 / n["data"], "L1"),
-                ("NS_external", "int", {"x": "int_x", "y": "int_y", "t": "int_t"},
-                 {"continuity": 0.0, "momentum_x": 0.0, "momentum_y": 0.0}, {}, lambda n: 28.0 / n["int"]),
-            ], timed=1, flop_per_point=_flop(3, 512, 6, 6, 14), bytes_per_point=12,
-            kernel="wide gemm_rows/gemm_dw kernels (interior domain)", bound="fp32"),
-    }
-
-
-class Trainer:
-    """A workload wired through the package's public pieces: get_net_node / MLP,
-    the PDE nodes, the residual compiler and the fused StepEngine + torch Adam."""
-
-    def __init__(self, cfg, device, world=1, sizes=None, precision="fp32"):
-        from idrlnet_b200 import compiler as cp
-        from idrlnet_b200 import fused
-        self.cfg, self.device, self.world, self.fused = cfg, device, world, fused
-        self.sizes = dict(cfg["sizes"] if sizes is None else sizes)
-        torch.manual_seed(0)
-        self.net = cfg["net"]()
-        self.net.net.to(device)
-        exprs = {}
-        for pde in cfg["pdes"]():
-            for sn in pde.sub_nodes:
-                exprs[sn.name] = sn.evaluate.tf_eq
-        self.exprs = exprs
-        spec = [cp.NetSpec(self.net.name, tuple(cfg["inputs"]), tuple(cfg["outputs"]))]
-        self.compiled = []
-        for dom in cfg["domains"]:
-            name, _, cols, targets = dom[0], dom[1], dom[2], dom[3]
-            self.compiled.append(cp.compile_domain(list(targets), exprs, spec, list(cols) + ["area"]))
-        self.pack = fused.NetPack(self.net.net, precision=precision)
-        self.opt = torch.optim.Adam(list(self.net.net.parameters()), lr=1e-3, fused=True)
-        self.sched = torch.optim.lr_scheduler.ExponentialLR(self.opt, gamma=math.pow(0.95, 0.001))
-        self.engine, self.sets = None, []
-        self.points_per_step = sum(self.sizes[d[1]] for d in cfg["domains"])
-        self.batch_keys = None
-
-    def sample_host(self, rng):
-        b = self.cfg["sample"](rng, self.sizes)
-        if self.batch_keys is None:
-            self.batch_keys = tuple(b)
-        return b
-
-    def bind_set(self, cols):
-        doms = []
-        for dom, cd in zip(self.cfg["domains"], self.compiled):
-            name, _, colmap, targets, lambdas, area = dom[:6]
-            loss = dom[6] if len(dom) > 6 else "square"
-            fd = self.fused.FusedDomain(name, cd, loss)
-            val = lambda v: cols[v] if isinstance(v, str) else v
-            fd.bind({k: cols[c] for k, c in colmap.items()}, {k: val(v) for k, v in targets.items()},
-                    {k: val(v) for k, v in lambdas.items()}, area(self.sizes))
-            doms.append(fd)
-        if self.engine is None:
-            self.engine = self.fused.StepEngine(self.pack, doms)
-        self.sets.append(doms)
-        return len(self.sets) - 1
-
-    def step(self, set_idx, ev=None):
-        """One full training step on the current stream; returns the loss (0-d device tensor)."""
-        eng = self.engine
-        eng.domains = self.sets[set_idx]
-        eng.launch(timed=None if ev is None else (self.cfg["timed"], ev[0], ev[1]))
-        if self.world > 1:
-            torch.distributed.all_reduce(eng.flat)
-        self.pack.scatter_grad(eng.grad)
-        loss = eng.total_loss()
-        self.opt.step()
-        self.sched.step()
-        return loss
+            return json.load(f), "measured (MEASURED_PEAKS.json)"
+    return {"hbm_gbs": 6650.0, "bf16_tflops_sustained": 2250.0 / 2}, "fallback (B200_PROFILING.md)"
 
 
 class ClockSampler:
@@ -263,6 +72,7 @@ class ClockSampler:
             self.thread.start()
         except Exception:
             self.proc = None
+        return self
 
     def _read(self):
         for line in self.proc.stdout:
@@ -294,107 +104,8 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
-# --------------------------------------------------------------------------- #
-# Reference-algorithm baselines: the oracle (torch autograd restatement of the
-# reference, oracle/pinn_oracle.py) on the host cores, or -- for the "reference's
-# own PyTorch CUDA path" comparison of BASELINE.md section 3 -- on the GPU.
-# --------------------------------------------------------------------------- #
-def net_layers_numpy(net_module):
-    out = []
-    for k, l in net_module.layers.items():
-        if k.endswith("_activation"):
-            continue
-        if hasattr(l, "weight_g"):
-            out.append({"g": l.weight_g.detach().cpu().numpy().copy(), "v": l.weight_v.detach().cpu().numpy().copy(),
-                        "b": l.bias.detach().cpu().numpy().copy()})
-        else:
-            out.append({"W": l.weight.detach().cpu().numpy().copy(), "b": l.bias.detach().cpu().numpy().copy()})
-    return out
-
-
-def oracle_problem(cfg, sizes, rng):
-    """The workload as an oracle-format problem (see oracle/pinn_oracle.py)."""
-    torch.manual_seed(0)
-    node = cfg["net"]()
-    exprs = {}
-    for pde in cfg["pdes"]():
-        for sn in pde.sub_nodes:
-            exprs[sn.name] = str(sn.evaluate.tf_eq)
-    b = cfg["sample"](rng, sizes)
-    domains = []
-    for dom in cfg["domains"]:
-        name, skey, colmap, targets, lambdas, area = dom[:6]
-        n = sizes[skey]
-        pts = {k: b[c].reshape(-1, 1) for k, c in colmap.items()}
-        pts["area"] = np.full((n, 1), area(sizes), np.float32)
-        val = lambda v: b[v].reshape(-1, 1) if isinstance(v, str) else float(v)
-        domains.append({"name": name, "points": pts, "targets": {k: val(v) for k, v in targets.items()},
-                        "lambdas": {k: val(v) for k, v in lambdas.items()},
-                        "loss": dom[6] if len(dom) > 6 else "square", "sigma": 1.0})
-    return {"nets": [{"name": node.name, "inputs": list(cfg["inputs"]), "outputs": list(cfg["outputs"]),
-                      "act": cfg["oracle_act"], "layers": net_layers_numpy(node.net), "shares": None}],
-            "exprs": exprs, "domains": domains}
-
-
-def time_oracle(cfg, sizes, steps, warmup, device="cpu"):
-    """Reference algorithm: forward graph (one autograd.grad per derivative symbol) +
-    loss + backward + Adam, all domains, on `device`."""
-    from oracle import pinn_oracle as po
-    rng = np.random.default_rng(0)
-    problem = oracle_problem(cfg, sizes, rng)
-    dev = torch.device(device)
-    nets = po.build_nets(problem)
-    for lay in nets[0]["raw"]:
-        for k in list(lay):
-            lay[k] = lay[k].detach().to(dev).requires_grad_()
-    leaves = [t for lay in nets[0]["raw"] for t in lay.values()]
-    opt = torch.optim.Adam(leaves, lr=1e-3)
-    # points resident on the device before timing
-    for dom in problem["domains"]:
-        dom["points"] = {k: torch.as_tensor(v, device=dev) for k, v in dom["points"].items()}
-        dom["targets"] = {k: (torch.as_tensor(v, device=dev) if not np.isscalar(v) else v) for k, v in dom["targets"].items()}
-        dom["lambdas"] = {k: (torch.as_tensor(v, device=dev) if not np.isscalar(v) else v) for k, v in dom["lambdas"].items()}
-
-    def one_step():
-        opt.zero_grad()
-        eff = []
-        for leaf in nets[0]["raw"]:
-            eff.append(((torch._weight_norm(leaf["v"], leaf["g"], 0) if "g" in leaf else leaf["W"]), leaf["b"]))
-        nets[0]["layers_t"] = eff
-        total = 0.0
-        for dom in problem["domains"]:
-            var = po.forward_domain(problem, dom, nets)
-            like = next(iter(var.values()))
-            diff = {k: var[k] - po._as_t(t, torch.float32, like) for k, t in dom["targets"].items()}
-            lam = {k: po._as_t(t, torch.float32, like) for k, t in dom["lambdas"].items()}
-            total = total + po.weighted_loss(diff, lam, var["area"], dom["loss"])
-        total.backward()
-        opt.step()
-        return total
-
-    sync = (lambda: torch.cuda.synchronize()) if dev.type == "cuda" else (lambda: None)
-    for _ in range(warmup):
-        one_step()
-    sync()
-    t0 = time.perf_counter()
-    for _ in range(steps):
-        one_step()
-    sync()
-    dt = (time.perf_counter() - t0) / steps
-    pts = sum(sizes[d[1]] for d in cfg["domains"])
-    return pts / dt, dt
-
-
-def scaled_sizes(cfg, factor):
-    return {k: max(32, int(v * factor)) for k, v in cfg["sizes"].items()}
-
-
-CPU_SAMPLE = {"burgers": 1 / 8, "poisson": 1 / 8, "ldc": 1 / 32, "allen_cahn": 1 / 32, "ns_xl": 1 / 32}
-
-
 def use_all_host_threads():
-    """torchrun exports OMP_NUM_THREADS=1 to its workers; the CPU arm is entitled to every host
-    thread this process may run on."""
+    """torchrun exports OMP_NUM_THREADS=1 to its workers; the CPU arm is entitled to every host thread."""
     try:
         n = len(os.sched_getaffinity(0))
     except AttributeError:
@@ -404,38 +115,133 @@ def use_all_host_threads():
 
 
 # --------------------------------------------------------------------------- #
+# the reference (unmodified idrlnet from baseline/_ref), in a subprocess
+# --------------------------------------------------------------------------- #
+def run_harness(config, device, steps, warmup, factor=1.0, pipe_steps=0, threads=0, sizes=None, tf32=False, gpu_index=0,
+                timeout=1500):
+    cmd = [sys.executable, HARNESS, "--config", config, "--device", device, "--steps", str(steps), "--warmup", str(warmup),
+           "--factor", repr(factor), "--pipe-steps", str(pipe_steps), "--threads", str(threads), "--gpu-index", str(gpu_index)]
+    if sizes:
+        cmd += ["--sizes", ",".join(f"{k}={v}" for k, v in sizes.items())]
+    if tf32:
+        cmd.append("--tf32")
+    env = dict(os.environ)
+    for k in ("RANK", "LOCAL_RANK", "WORLD_SIZE", "OMP_NUM_THREADS", "MKL_NUM_THREADS"):
+        env.pop(k, None)
+    try:
+        out = subprocess.run(cmd, capture_output=True, text=True, timeout=timeout, env=env, cwd=tempfile.mkdtemp(prefix="ref_run_"))
+    except subprocess.TimeoutExpired:
+        return {"impl": "reference", "unavailable": f"timed out after {timeout} s"}
+    for line in reversed(out.stdout.strip().splitlines()):
+        if line.startswith("{"):
+            try:
+                return json.loads(line)
+            except json.JSONDecodeError:
+                continue
+    tail = (out.stderr or out.stdout).strip().splitlines()[-1:] or ["no output"]
+    return {"impl": "reference", "unavailable": f"harness failed (rc {out.returncode}): {tail[0][:200]}"}
+
+
 def run_reference(args):
-    rank = int(os.environ.get("RANK", 0))
-    if rank != 0:
+    """CPU arm: the reference's own implementation on the host cores, bounded sample of the headline workload."""
+    if int(os.environ.get("RANK", 0)) != 0:
         return
-    cfg = workload_configs()[args.config]
-    device = "cpu"
-    if args.baseline_device == "cuda":
-        device = f"cuda:{int(os.environ.get('LOCAL_RANK', 0))}"
-    if args.baseline_tf32:
-        torch.backends.cuda.matmul.allow_tf32 = True
-        torch.backends.cudnn.allow_tf32 = True
-    factor = args.sample if args.sample else (CPU_SAMPLE[args.config] if device == "cpu" else 1 / 4)
-    sizes = scaled_sizes(cfg, factor)
     cores = use_all_host_threads()
-    pps, dt = time_oracle(cfg, sizes, args.steps, args.warmup, device)
-    sample = (f"{'+'.join(str(sizes[d[1]]) for d in cfg['domains'])} points/step ({factor:g} of the GPU workload), "
-              f"{args.steps} steps, torch autograd {'TF32-allowed' if args.baseline_tf32 else 'FP32'} on {device}")
+    factor = args.sample if args.sample else CPU_SAMPLE[args.config]
+    res = run_harness(args.config, "cpu", args.steps, args.warmup, factor=factor, threads=cores)
+    cfg = wl.CONFIGS[args.config]
+    if "strict" not in res:  # baseline/_ref missing: fall back to the oracle port of the same algorithm
+        res = time_oracle_port(args.config, factor, args.steps, args.warmup)
+        kind = "port"
+    else:
+        kind = "reference"
+    pps, ms = res["strict"]["value"], res["strict"]["ms_per_step"]
+    sample = (f"{'+'.join(str(v) for v in res['sizes'].values())} points/step ({factor:g} of the one-GPU workload), "
+              f"{args.steps} steps, " + ("unmodified idrlnet 2.0.0 (baseline/_ref), strict pass of idrlnet/solver.py:329-339, "
+                                         if kind == "reference" else "oracle port (torch autograd), ") + "FP32 on the host cores")
     line = {
         "impl": "reference", "metric": METRIC, "value": pps, "unit": "points/s", "n_gpus": args.gpus,
-        "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"{cfg['title']}: reference algorithm (torch autograd) on {device}, bounded sample",
-                   "net": cfg["net_desc"], "points_per_step": sum(sizes[d[1]] for d in cfg["domains"])},
-        "cpu_baseline": {"value": pps, "unit": "points/s", "cores": cores, "kind": "port", "sample": sample},
+        "config": {"workload": f"{cfg['title']}: reference implementation on the host CPU, bounded sample",
+                   "net": cfg["net_desc"], "points_per_step": res["points_per_step"]},
+        "cpu_baseline": {"value": pps, "unit": "points/s", "cores": res.get("threads", cores), "kind": kind, "sample": sample},
         "e2e": {"value": pps, "unit": "points/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line))
 
 
+def time_oracle_port(config, factor, steps, warmup):
+    """Fallback CPU baseline when baseline/_ref is absent: the oracle's restatement of the reference algorithm."""
+    from oracle import pinn_oracle as po
+    import idrlnet_b200 as pkg
+    pkg.use_cpu()
+    import idrlnet_b200.shortcut as sc
+    cfg = wl.CONFIGS[config]
+    sizes = wl.scaled_sizes(cfg["sizes"](1), factor)
+    rng = np.random.default_rng(0)
+    b = cfg["sample"](rng, sizes)
+    torch.manual_seed(0)
+    nets = cfg["nets"](sc)
+    exprs = {sn.name: str(sn.evaluate.tf_eq) for pde in cfg["pdes"](sc) for sn in getattr(pde, "sub_nodes", [])
+             if hasattr(sn.evaluate, "tf_eq")}
+    node = nets[0]
+    layers = []
+    for k, l in node.net.layers.items():
+        if k.endswith("_activation"):
+            continue
+        if hasattr(l, "weight_g"):
+            layers.append({"g": l.weight_g.detach().numpy().copy(), "v": l.weight_v.detach().numpy().copy(), "b": l.bias.detach().numpy().copy()})
+        else:
+            layers.append({"W": l.weight.detach().numpy().copy(), "b": l.bias.detach().numpy().copy()})
+    act = {"burgers": "silu", "poisson": "silu", "ldc": "tanh", "allen_cahn": "tanh", "ns_xl": "silu"}[config]
+    domains = []
+    for row in cfg["domains"]:
+        name, skey, colmap, targets, lambdas, area, loss = row
+        if any(t.startswith("difference") for t in targets):
+            continue
+        n = sizes[skey]
+        pts = {k: b[c].reshape(-1, 1) for k, c in colmap.items()}
+        pts["area"] = np.full((n, 1), area(sizes), np.float32)
+        val = lambda v: b[v].reshape(-1, 1) if isinstance(v, str) else float(v)
+        domains.append({"name": name, "points": pts, "targets": {k: val(v) for k, v in targets.items()},
+                        "lambdas": {k: val(v) for k, v in lambdas.items()}, "loss": loss, "sigma": 1.0})
+    problem = {"nets": [{"name": node.name, "inputs": list(node.inputs), "outputs": list(node.outputs), "act": act,
+                         "layers": layers, "shares": None}], "exprs": exprs, "domains": domains}
+    onets = po.build_nets(problem)
+    leaves = [t for lay in onets[0]["raw"] for t in lay.values()]
+    opt = torch.optim.Adam(leaves, lr=1e-3)
+
+    def one_step():
+        opt.zero_grad()
+        onets[0]["layers_t"] = [((torch._weight_norm(l["v"], l["g"], 0) if "g" in l else l["W"]), l["b"]) for l in onets[0]["raw"]]
+        total = 0.0
+        for dom in problem["domains"]:
+            var = po.forward_domain(problem, dom, onets)
+            like = next(iter(var.values()))
+            diff = {k: var[k] - po._as_t(t, torch.float32, like) for k, t in dom["targets"].items()}
+            lam = {k: po._as_t(t, torch.float32, like) for k, t in dom["lambdas"].items()}
+            total = total + po.weighted_loss(diff, lam, var["area"], dom["loss"])
+        total.backward()
+        opt.step()
+
+    for _ in range(warmup):
+        one_step()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        one_step()
+    dt = (time.perf_counter() - t0) / steps
+    pts = sum(len(next(iter(d["points"].values()))) for d in domains)
+    return {"strict": {"value": pts / dt, "ms_per_step": dt * 1e3}, "sizes": sizes, "points_per_step": pts,
+            "threads": torch.get_num_threads()}
+
+
+# --------------------------------------------------------------------------- #
+# this package
+# --------------------------------------------------------------------------- #
 def ncu_traffic(config):
-    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, from the
-    committed `ncu --set full` capture (profiles/ncu_traffic.json); None if not captured."""
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, from the committed
+    `ncu --set full` capture (profiles/ncu_traffic.json); None if not captured."""
     path = os.path.join(ROOT, "profiles", "ncu_traffic.json")
     if os.path.exists(path):
         with open(path) as f:
@@ -462,6 +268,184 @@ def measure_fp32_peak(device):
     return best
 
 
+def measure_tf32_peak(device):
+    """Dense TF32 tcgen05 throughput (TFLOP/s) measured by the library's own probe (one persistent CTA per SM issuing
+    M=128 N=256 K=8 kind::tf32 MMAs on resident shared-memory operands); falls back to half the measured sustained
+    BF16 cuBLAS rate when the probe is not in this build."""
+    from idrlnet_b200 import native as nv
+    lib = nv.lib()
+    if hasattr(lib, "pinn_tf32_mma_probe"):
+        scratch = torch.zeros(1024, device=device)
+        st = torch.cuda.current_stream().cuda_stream
+        if lib.pinn_tf32_mma_probe(200, scratch.data_ptr(), st) > 0:
+            torch.cuda.synchronize()
+            best = 0.0
+            for _ in range(3):
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                flops = lib.pinn_tf32_mma_probe(4000, scratch.data_ptr(), st)
+                e1.record()
+                torch.cuda.synchronize()
+                best = max(best, flops / (e0.elapsed_time(e1) * 1e-3) / 1e12)
+            if best > 0:
+                return best, "dense TF32 tcgen05 rate measured in this run (pinn_tf32_mma_probe)"
+    pk, src = measured_peaks()
+    return pk.get("bf16_tflops_sustained", 1125.0) / 2, f"1/2 of the sustained BF16 cuBLAS rate, {src}"
+
+
+class OursRun:
+    """One workload on this package's public API: Solver + device point sets."""
+
+    def __init__(self, name, device, world, rank, precision=None, sizes=None):
+        import idrlnet_b200.shortcut as sc
+        self.name, self.device, self.world, self.rank = name, device, world, rank
+        self.cfg = wl.CONFIGS[name]
+        self.sizes = dict(sizes) if sizes else self.cfg["sizes"](world)
+        self.precision = precision
+        self.sets = wl.PointSets(self.cfg, self.sizes, device, torch)
+        self.rng = np.random.default_rng(1000 + rank)
+        hb = self.cfg["sample"](self.rng, self.sizes)
+        self.batch_bytes = sum(hb[c].nbytes for c in self.sets.columns)
+        self.n_rotate = max(2, min(32, int(math.ceil(2.15 * L2_BYTES / self.batch_bytes))))
+        if self.batch_bytes > 1.2 * L2_BYTES:
+            self.n_rotate = 2
+        self.sets.add_host_batch(hb)
+        for _ in range(self.n_rotate - 1):
+            self.sets.add_host_batch(self.cfg["sample"](self.rng, self.sizes))
+        torch.manual_seed(0)
+        domains, nets, pdes = wl.build_problem(sc, self.cfg, self.sets, requires_grad=False)
+        self.solver = sc.Solver(sample_domains=domains, netnodes=nets, pdes=pdes, max_iter=10 ** 9, loading=False,
+                                network_dir=tempfile.mkdtemp(prefix="bench_net_"), post_step_loss=False,
+                                precision=precision, shard_points=False,
+                                opt_config=dict(optimizer="Adam", lr=1e-3, fused=True))
+        self.points_per_step = wl.points_per_step(self.cfg, self.sizes)
+        self.fused_domains = sorted(self.solver._fused_domains)
+
+    def step(self, set_idx):
+        self.sets.current = set_idx
+        return self.solver.train_pipe()
+
+    def sync_all(self):
+        torch.cuda.synchronize()
+        if self.world > 1:
+            torch.distributed.barrier()
+            torch.cuda.synchronize()
+
+    def timed(self, steps, warmup):
+        """(ms per step [max over ranks], mean kernel ms of the timed domain, final loss, host ms per step, launches)."""
+        from idrlnet_b200 import native as nv
+        for i in range(warmup):
+            self.step(i % self.n_rotate)
+        self.sync_all()
+        events = self.solver.kernel_events.setdefault(self.cfg["timed"], [])
+        events.clear()
+        launches0 = nv.lib().pinn_launch_count()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        t0 = time.perf_counter()
+        loss = None
+        for i in range(steps):
+            loss = self.step((warmup + i) % self.n_rotate)
+        host_ms = (time.perf_counter() - t0) * 1e3 / steps
+        e1.record()
+        self.sync_all()
+        launches = nv.lib().pinn_launch_count() - launches0
+        ms = torch.tensor([e0.elapsed_time(e1)], device=self.device)
+        if self.world > 1:
+            torch.distributed.all_reduce(ms, op=torch.distributed.ReduceOp.MAX)
+        kern_ms = float(np.mean([a.elapsed_time(b) for a, b in events])) if events else None
+        self.solver.kernel_events.pop(self.cfg["timed"], None)
+        return float(ms) / steps, kern_ms, float(loss), host_ms, int(launches)
+
+    def e2e(self, steps, warmup):
+        """Same metric end to end: every step's coordinates come from pinned host memory (H2D on a copy stream,
+        double-buffered against compute) and the step's loss is read back to the host."""
+        n_host = 4
+        cols = self.sets.columns
+        host_sets = []
+        for _ in range(n_host):
+            hb = self.cfg["sample"](self.rng, self.sizes)
+            host_sets.append({k: torch.as_tensor(hb[k].reshape(-1, 1)).pin_memory() for k in cols})
+        slots = [self.sets.add_empty(), self.sets.add_empty()]
+        copy_stream = torch.cuda.Stream(device=self.device)
+        ready = [torch.cuda.Event() for _ in range(2)]
+        consumed = [torch.cuda.Event() for _ in range(2)]
+        loss_host = torch.zeros(steps + warmup + 2, dtype=torch.float32).pin_memory()
+        h2d_bytes = sum(host_sets[0][k].numel() * 4 for k in cols)
+
+        def upload(i):
+            slot = i % 2
+            with torch.cuda.stream(copy_stream), torch.no_grad():
+                copy_stream.wait_event(consumed[slot])
+                dst = self.sets.sets[slots[slot]]
+                for k in cols:
+                    dst[k].copy_(host_sets[i % n_host][k], non_blocking=True)
+                ready[slot].record(copy_stream)
+
+        def loop(n):
+            main = torch.cuda.current_stream()
+            upload(0)
+            for i in range(n):
+                slot = i % 2
+                if i + 1 < n:
+                    upload(i + 1)  # overlaps with this step's compute
+                main.wait_event(ready[slot])
+                l = self.step(slots[slot])
+                consumed[slot].record(main)
+                loss_host[i].copy_(l, non_blocking=True)
+
+        for sl in range(2):
+            consumed[sl].record(torch.cuda.current_stream())
+        loop(warmup)
+        self.sync_all()
+        t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0.record()
+        loop(steps)
+        t1.record()
+        self.sync_all()
+        ms = torch.tensor([t0.elapsed_time(t1)], device=self.device)
+        if self.world > 1:
+            torch.distributed.all_reduce(ms, op=torch.distributed.ReduceOp.MAX)
+        return self.points_per_step * self.world / (float(ms) / steps * 1e-3), h2d_bytes
+
+    def close(self):
+        self.solver = None
+        self.sets = None
+        import gc
+        gc.collect()
+        torch.cuda.empty_cache()
+
+
+def roofline_of(run: OursRun, kern_ms, fp32_peak, tf32_peak, hbm_peak, hbm_src):
+    cfg = run.cfg
+    n_timed = run.sizes[next(d[1] for d in cfg["domains"] if d[0] == cfg["timed"])]
+    if kern_ms is None:
+        return None
+    achieved = cfg["flop_per_point"] * n_timed / (kern_ms * 1e-3) / 1e12
+    tensor = cfg["wide"] and run.precision in ("tf32", "tf32_streamed", "fp32x3")
+    if tensor:
+        peak, src = tf32_peak
+        if run.precision == "fp32x3":
+            peak, src = peak / 3, src + ", / 3 MMAs per product (3xTF32 operand splitting)"
+        bound = "tensor"
+    else:
+        peak, src, bound = fp32_peak, "FP32 FMA pipe, pinn_fp32_fma_probe measured in this run", "fp32"
+    hbm = cfg["bytes_per_point"] * n_timed / (kern_ms * 1e-3) / 1e9
+    return {"bound": bound, "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak if peak else None,
+            "traffic": ncu_traffic(run.name if not run.precision or not cfg["wide"] else f"{run.name}_{run.precision}"),
+            "kernel": cfg["kernel"] + (f" [{run.precision}]" if cfg["wide"] else ""), "kernel_ms": kern_ms,
+            "flop_per_point": cfg["flop_per_point"], "peak_source": src, "fp32_fma_peak": fp32_peak,
+            "hbm": {"achieved": hbm, "peak": hbm_peak, "unit": "GB/s", "frac": hbm / hbm_peak, "peak_source": hbm_src}}
+
+
+def torch_cuda_arm(name, local, steps=20, warmup=3, pipe_steps=4):
+    """The unmodified reference on this GPU (`idrlnet.use_gpu`), same workload; sizes halved on OOM by the harness."""
+    clk = ClockSampler(local).start()
+    res = run_harness(name, "cuda", steps, warmup, pipe_steps=pipe_steps, gpu_index=local)
+    res["clocks"] = clk.stop()
+    return res
+
+
 def run_ours(args):
     rank = int(os.environ.get("RANK", 0))
     local = int(os.environ.get("LOCAL_RANK", 0))
@@ -472,150 +456,104 @@ def run_ours(args):
     device = torch.device(f"cuda:{local}")
     if world > 1:
         torch.distributed.init_process_group("nccl", device_id=device)
+    import idrlnet_b200 as pkg
+    pkg.use_gpu(local)
     from idrlnet_b200 import native as nv
+    nv.lib()  # fail loudly if the CUDA library is missing
 
-    cfg = workload_configs()[args.config]
-    sizes = scaled_sizes(cfg, args.sample) if args.sample else None
-    trainer = Trainer(cfg, device, world=world, sizes=sizes, precision=args.precision)
-    wide_tc = args.precision != "fp32" and trainer.pack.width > 32
-    rng = np.random.default_rng(1000 + rank)
-    pts_per_step = trainer.points_per_step
-    n_timed = trainer.sizes[cfg["domains"][cfg["timed"]][1]]
-    # ---- device-resident rotating batches (value): together larger than L2 -------
-    hb = trainer.sample_host(rng)
-    batch_bytes = sum(v.nbytes for v in hb.values())
-    n_rotate = max(2, min(N_ROTATE, int(math.ceil(270e6 / batch_bytes))))
-    for i in range(n_rotate):
-        if i:
-            hb = trainer.sample_host(rng)
-        trainer.bind_set({k: torch.as_tensor(v, device=device) for k, v in hb.items()})
-    keys = trainer.batch_keys
-
-    def sync_all():
-        torch.cuda.synchronize()
-        if world > 1:
-            torch.distributed.barrier()
-            torch.cuda.synchronize()
-
-    clocks = ClockSampler(local)
-    clocks.start()  # samples cover warm-up + timed region + e2e region (all under load)
-    for i in range(args.warmup):
-        trainer.step(i % n_rotate)
-    sync_all()
-    kernel_events = []
-    launches0 = nv.lib().pinn_launch_count()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    loss = None
-    for i in range(args.steps):
-        ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
-        kernel_events.append(ev)
-        loss = trainer.step((args.warmup + i) % n_rotate, ev)
-    e1.record()
-    sync_all()
-    launches = nv.lib().pinn_launch_count() - launches0
-    ms = torch.tensor([e0.elapsed_time(e1)], device=device)
-    if world > 1:
-        torch.distributed.all_reduce(ms, op=torch.distributed.ReduceOp.MAX)
-    ms_per_step = float(ms) / args.steps
-    value = pts_per_step * world / (ms_per_step * 1e-3)
-    kern_ms = float(np.mean([a.elapsed_time(b) for a, b in kernel_events]))
-    final_loss = float(loss)
-
-    # ---- end to end: host (pinned) points in, loss out, every step -----------
-    n_host = 4
-    host_sets = []
-    for _ in range(n_host):
-        hb = trainer.sample_host(rng)
-        host_sets.append({k: torch.as_tensor(hb[k]).pin_memory() for k in keys})
-    dev_bufs = [{k: torch.empty_like(host_sets[0][k], device=device) for k in keys} for _ in range(2)]
-    set_ids = [trainer.bind_set(b) for b in dev_bufs]
-    copy_stream = torch.cuda.Stream(device=device)
-    ready = [torch.cuda.Event() for _ in range(2)]
-    consumed = [torch.cuda.Event() for _ in range(2)]
-    loss_host = torch.zeros(args.steps + args.warmup + 2, dtype=torch.float32).pin_memory()
-    h2d_bytes = sum(host_sets[0][k].numel() * 4 for k in keys)
-
-    def upload(i):
-        slot = i % 2
-        with torch.cuda.stream(copy_stream):
-            copy_stream.wait_event(consumed[slot])
-            for k in keys:
-                dev_bufs[slot][k].copy_(host_sets[i % n_host][k], non_blocking=True)
-            ready[slot].record(copy_stream)
-
-    def e2e_loop(n):
-        main = torch.cuda.current_stream()
-        upload(0)
-        for i in range(n):
-            slot = i % 2
-            if i + 1 < n:
-                upload(i + 1)  # overlaps with this step's compute
-            main.wait_event(ready[slot])
-            l = trainer.step(set_ids[slot])
-            consumed[slot].record(main)
-            loss_host[i].copy_(l, non_blocking=True)
-
-    for sl in range(2):
-        consumed[sl].record(torch.cuda.current_stream())
-    e2e_loop(args.warmup)
-    sync_all()
-    t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    t0.record()
-    e2e_loop(args.steps)
-    t1.record()
-    sync_all()
-    ms2 = torch.tensor([t0.elapsed_time(t1)], device=device)
-    if world > 1:
-        torch.distributed.all_reduce(ms2, op=torch.distributed.ReduceOp.MAX)
-    e2e_value = pts_per_step * world / (float(ms2) / args.steps * 1e-3)
+    cfg = wl.CONFIGS[args.config]
+    sizes = wl.scaled_sizes(cfg["sizes"](world), args.sample) if args.sample else None
+    head_prec = args.precision if cfg["wide"] else None
+    clocks = ClockSampler(local).start()  # samples cover warm-up + timed region + e2e region (all under load)
+    run = OursRun(args.config, device, world, rank, precision=head_prec, sizes=sizes)
+    ms_per_step, kern_ms, final_loss, host_ms, launches = run.timed(args.steps, args.warmup)
+    value = run.points_per_step * world / (ms_per_step * 1e-3)
+    e2e_value, h2d_bytes = run.e2e(args.steps, args.warmup)
     clk = clocks.stop()
+    pk, pk_src = measured_peaks()
+    fp32_peak = measure_fp32_peak(device)
+    tf32_peak = measure_tf32_peak(device)
+    roof = roofline_of(run, kern_ms, fp32_peak, tf32_peak, pk["hbm_gbs"], pk_src)
+    head_sizes, head_rot, head_bytes, head_fused = run.sizes, run.n_rotate, run.batch_bytes, run.fused_domains
+    head_pts = run.points_per_step
+    run.close()
+
+    # ---- the other BASELINE configurations at their stated sizes -------------------------------------------
+    configs = {}
+    names = [] if args.no_configs else [n for n in ("poisson", "ldc", "allen_cahn", "ns_xl") if n != args.config]
+    if world > 1:
+        names = [n for n in names if n in ("ldc", "ns_xl")]  # the configs the north star names for multi-GPU runs
+    for name in names:
+        c = wl.CONFIGS[name]
+        modes = WIDE_MODES if c["wide"] else (("", None),)
+        for suffix, prec in modes:
+            w, k = SECONDARY_STEPS[name]
+            try:
+                r = OursRun(name, device, world, rank, precision=prec)
+                ck = ClockSampler(local).start()
+                ms, kms, loss, hms, _ = r.timed(k, w)
+                entry = {"value": r.points_per_step * world / (ms * 1e-3), "unit": "points/s", "ms_per_step": ms,
+                         "steps": k, "warmup": w, "scaling": c["scaling"], "precision": prec or "fp32",
+                         "workload": f"{c['title']}: {' + '.join(str(r.sizes[d[1]]) for d in c['domains'])} points per step per GPU "
+                                     f"({', '.join(d[0] for d in c['domains'])})",
+                         "net": c["net_desc"], "points_per_step_per_gpu": r.points_per_step, "fused_domains": r.fused_domains,
+                         "l2": f"{r.n_rotate} rotating point batches of {r.batch_bytes / 1e6:.0f} MB",
+                         "host_ms_per_step": hms, "final_loss": loss,
+                         "roofline": roofline_of(r, kms, fp32_peak, tf32_peak, pk["hbm_gbs"], pk_src), "clocks": ck.stop()}
+                r.close()
+            except Exception as e:  # a secondary config must never take the headline line down
+                entry = {"error": f"{type(e).__name__}: {e}"[:300]}
+            configs[name + suffix] = entry
 
     if rank == 0:
-        hbm_peak, peak_src = peaks()
-        fp32_peak = measure_fp32_peak(device)
-        achieved = cfg["flop_per_point"] * n_timed / (kern_ms * 1e-3) / 1e12
-        if wide_tc:  # tensor-core kernels: the denominator is the TF32 tensor rate (a third of it under 3xTF32 splitting)
-            roof_peak, roof_src = tensor_peak_tf32()
-            if args.precision == "fp32x3":
-                roof_peak, roof_src = roof_peak / 3, roof_src + ", / 3 MMAs per product (3xTF32)"
-            roof_bound = "tensor"
-            roof_kernel = ("on-chip tcgen05 kernel wide_fused (interior domain)" if args.precision == "tf32" and trainer.pack.width <= 128
-                           else "tcgen05 tc_rows / tc_dw2 kernels (interior domain)")
-        else:
-            roof_peak, roof_src = fp32_peak, "FP32 FMA pipe, pinn_fp32_fma_probe measured in this run"
-            roof_bound, roof_kernel = cfg["bound"], cfg["kernel"]
-        hbm_achieved = cfg["bytes_per_point"] * n_timed / (kern_ms * 1e-3) / 1e9
         cpu = None
         if world == 1 and not args.no_cpu_baseline:
-            csz = scaled_sizes(cfg, CPU_SAMPLE[args.config])
-            use_all_host_threads()
-            pps, dt = time_oracle(cfg, csz, 8, 2, "cpu")
-            cpu = {"value": pps, "unit": "points/s", "cores": torch.get_num_threads(), "kind": "port",
-                   "sample": f"{'+'.join(str(csz[d[1]]) for d in cfg['domains'])} points/step x 8 steps of the same "
-                             f"workload (oracle: reference algorithm, torch autograd FP32)"}
+            cores = use_all_host_threads()
+            res = run_harness(args.config, "cpu", 100 if args.config in ("burgers", "poisson") else 6, 2,
+                              factor=CPU_SAMPLE[args.config], threads=cores)
+            if "strict" in res:
+                cpu = {"value": res["strict"]["value"], "unit": "points/s", "cores": res.get("threads", cores), "kind": "reference",
+                       "sample": f"{'+'.join(str(v) for v in res['sizes'].values())} points/step x {res['strict']['steps']} steps of the same "
+                                 f"workload (unmodified idrlnet 2.0.0 from baseline/_ref, strict pass idrlnet/solver.py:329-339, FP32)"}
+            else:
+                cpu = {"value": None, "unit": "points/s", "cores": cores, "kind": "reference", "sample": res.get("unavailable", "failed")}
+        if world == 1 and not args.no_torch_cuda:
+            # the reference's own PyTorch CUDA path on this B200: the >= 20x denominator
+            torch.cuda.empty_cache()
+            for name in [args.config] + names:
+                ref = torch_cuda_arm(name, local)
+                keys = [args.config] if name == args.config else [k for k in configs if k == name or k.startswith(name + "_")]
+                for key in keys:
+                    tgt = configs.setdefault(key, {}) if key != args.config else None
+                    ours_v = value if key == args.config else configs[key].get("value")
+                    ratio = (ours_v / ref["strict"]["value"]) if ("strict" in ref and ours_v) else None
+                    if tgt is None:
+                        head_ref, head_ratio = ref, ratio
+                    else:
+                        tgt["torch_cuda"], tgt["vs_torch_cuda"] = ref, ratio
         line = {
             "metric": METRIC, "value": value, "unit": "points/s", "n_gpus": world, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": ("f32 (3xTF32 split on tensor cores)" if args.precision == "fp32x3" else "tf32") if wide_tc else "f32", "data": "synthetic",
-            "config": {"workload": f"{cfg['title']}: {' + '.join(str(trainer.sizes[d[1]]) for d in cfg['domains'])} "
+            "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": cfg["scaling"],
+            "vs_baseline": None,
+            "dtype": "f32" if not cfg["wide"] or head_prec in (None, "fp32") else ("f32 (3xTF32 split on tensor cores)" if head_prec == "fp32x3" else "tf32"),
+            "data": "synthetic",
+            "config": {"workload": f"{cfg['title']}: {' + '.join(str(head_sizes[d[1]]) for d in cfg['domains'])} "
                                    f"points per step per GPU ({', '.join(d[0] for d in cfg['domains'])})",
                        "net": f"{cfg['net_desc']}, Adam 1e-3 + ExponentialLR",
-                       "points_per_step_per_gpu": pts_per_step, "parallelism": f"dp{world} (points sharded, 1 all-reduce)",
-                       "l2": f"{n_rotate} rotating point batches ({n_rotate * batch_bytes / 1e6:.0f} MB > 126 MB L2)"},
-            "roofline": {"bound": roof_bound, "achieved": achieved, "peak": roof_peak, "unit": "TFLOP/s",
-                         "frac": achieved / roof_peak if roof_peak else None,
-                         "traffic": None if wide_tc else ncu_traffic(args.config),
-                         "kernel": roof_kernel, "kernel_ms": kern_ms, "flop_per_point": cfg["flop_per_point"],
-                         "peak_source": roof_src, "fp32_fma_peak": fp32_peak,
-                         "hbm": {"achieved": hbm_achieved, "peak": hbm_peak, "unit": "GB/s",
-                                 "frac": hbm_achieved / hbm_peak, "peak_source": peak_src}},
-            "cpu_baseline": cpu,
+                       "api": "idrlnet_b200.Solver.train_pipe() (post_step_loss=False: one evaluation per step, the strict step "
+                              "of idrlnet/solver.py:329-339)", "fused_domains": head_fused,
+                       "points_per_step_per_gpu": head_pts, "parallelism": f"dp{world} (points sharded, 1 all-reduce)",
+                       "l2": f"{head_rot} rotating point batches ({head_rot * head_bytes / 1e6:.0f} MB > 126 MB L2)"},
+            "roofline": roof, "cpu_baseline": cpu,
             "e2e": {"value": e2e_value, "unit": "points/s", "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 4},
-            "gpu_launches": int(launches), "clocks": clk, "final_loss": final_loss,
+            "gpu_launches": launches, "clocks": clk, "final_loss": final_loss, "host_ms_per_step": host_ms,
+            "configs": configs,
         }
+        if world == 1 and not args.no_torch_cuda:
+            line["torch_cuda"], line["vs_torch_cuda"] = head_ref, head_ratio
         print(json.dumps(line))
     if world > 1:
+        torch.distributed.barrier()
         torch.distributed.destroy_process_group()
 
 
@@ -625,17 +563,14 @@ def main():
     ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--config", default="burgers", choices=["burgers", "poisson", "ldc", "allen_cahn", "ns_xl"],
-                    help="workload; the driver's default (burgers) is the headline")
-    ap.add_argument("--sample", type=float, default=None, help="scale every domain size by this factor")
-    ap.add_argument("--baseline-device", default="cpu", choices=["cpu", "cuda"],
-                    help="--impl reference: where the reference algorithm (torch autograd) runs")
-    ap.add_argument("--baseline-tf32", action="store_true",
-                    help="--impl reference --baseline-device cuda: allow TF32 matmuls in torch (the reference's pinned "
-                         "torch 1.7.1 did so silently on Ampere; torch 2.x defaults to FP32)")
+    ap.add_argument("--config", default="burgers", choices=list(wl.CONFIGS),
+                    help="headline workload; the driver's default (burgers) is BASELINE configs[1]")
+    ap.add_argument("--sample", type=float, default=None, help="scale every domain size of the headline by this factor")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--precision", default="fp32", choices=["fp32", "tf32", "tf32_streamed", "fp32x3"],
-                    help="layer GEMMs of wide nets: FP32 FMA (parity) or tcgen05 TF32; narrow nets are always FP32")
+    ap.add_argument("--no-configs", action="store_true", help="headline only: skip the `configs` object")
+    ap.add_argument("--no-torch-cuda", action="store_true", help="skip the reference-on-CUDA arms (N=1 only anyway)")
+    ap.add_argument("--precision", default="fp32x3", choices=["fp32", "tf32", "tf32_streamed", "fp32x3"],
+                    help="layer GEMMs of a WIDE headline config; narrow nets are always FP32 FMA")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

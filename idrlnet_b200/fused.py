@@ -99,6 +99,9 @@ class NetPack:
         if self.n_in > nv.MAX_IN or self.n_out > nv.MAX_OUT or len(self.layers) > nv.MAX_LAYERS:
             raise cp.NotFusable("net too large for the descriptors")
         self.weight_norm = [hasattr(l, "weight_g") and hasattr(l, "weight_v") for l in self.layers]
+        if any(p.dtype != torch.float32 for l in self.layers for p in l.parameters()):
+            raise cp.NotFusable("the kernels compute in FP32; a net of another dtype (e.g. an FP64 tie-breaker run) "
+                                "takes the torch path")
         dev = self.layers[0].bias.device
         if dev.type != "cuda":
             raise RuntimeError("idrlnet_b200: the net must live on a CUDA device (there is no CPU path)")

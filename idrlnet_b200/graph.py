@@ -238,7 +238,8 @@ class _JetServe:
         return _JetServe(node, pack, plan, names)
 
     def usable(self, args) -> bool:
-        return all(isinstance(args.get(k), torch.Tensor) and args[k].is_cuda for k in self.node.inputs)
+        return all(isinstance(args.get(k), torch.Tensor) and args[k].is_cuda and args[k].dtype == torch.float32
+                   for k in self.node.inputs)
 
     def evaluate(self, args) -> Dict[str, torch.Tensor]:
         from . import fused

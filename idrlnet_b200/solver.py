@@ -61,7 +61,7 @@ class Solver(Notifier, Optimizable):
                  max_iter: int = 1000, save_freq: int = 100, print_freq: int = 10, loading: bool = True,
                  init_network_dirs: Optional[List[str]] = None, opt_config: Dict = None, schedule_config: Dict = None,
                  result_dir="train_domain/results", fused: Optional[bool] = None, post_step_loss: Optional[bool] = None,
-                 precision: Optional[str] = None, **kwargs):
+                 precision: Optional[str] = None, shard_points: bool = True, **kwargs):
         from . import callbacks
         self.network_dir = network_dir
         self.domain_losses = {d.name: d.loss_fn for d in sample_domains}
@@ -73,6 +73,12 @@ class Solver(Notifier, Optimizable):
         # arithmetic of the layer GEMMs of wide (H > 32) nets: "fp32" (FP32 FMA, parity, default), "fp32x3" (tensor
         # cores, 3xTF32 splitting), "tf32" / "tf32_streamed" (tensor cores); None -> IDRLNET_B200_PRECISION or "fp32"
         self.precision = precision
+        # under torch.distributed every sampled domain is split [rank::world] (all ranks draw the same seeded points, as
+        # an unchanged example does); shard_points=False is for callers whose samplers already return this rank's points
+        self.shard_points = shard_points
+        # measurement hook: {domain name: list} -> a (start, stop) CUDA-event pair around that domain's fused kernel is
+        # appended at every gradient step (bench.py's roofline.kernel_ms)
+        self.kernel_events: Dict[str, list] = {}
         self._move_nets_to_device()
         self.init_network_dirs = init_network_dirs if init_network_dirs else []
         self.init_load()
@@ -285,7 +291,7 @@ class Solver(Notifier, Optimizable):
 
     def _shard(self, samples: DomainVariables) -> DomainVariables:
         d = _dist()
-        if d is None:
+        if d is None or not self.shard_points:
             return samples
         r, w = d.get_rank(), d.get_world_size()
         return {name: Variables({k: (v[r::w] if isinstance(v, torch.Tensor) and v.dim() > 0 and v.shape[0] > 1 else v)
@@ -307,7 +313,15 @@ class Solver(Notifier, Optimizable):
         engines = self._bind_fused(fused_names, in_var, true_out, lambda_out)
         dist = _dist()
         for eng in engines:
-            eng.launch(loss_only=not grads)  # the post-update re-evaluation needs no reverse pass
+            timed = None
+            if grads and self.kernel_events:
+                for i, fd in enumerate(eng.domains):
+                    if fd.name in self.kernel_events:
+                        ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+                        self.kernel_events[fd.name].append(ev)
+                        timed = (i, ev[0], ev[1])
+                        break
+            eng.launch(loss_only=not grads, timed=timed)  # the post-update re-evaluation needs no reverse pass
             if dist is not None:
                 dist.all_reduce(eng.flat if grads else eng.losses)
             for fd, l in zip(eng.domains, eng.losses):

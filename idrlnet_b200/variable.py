@@ -54,12 +54,13 @@ class Variables(dict):
         return Variables({k: self[k] for k in subset_keys if k in self})
 
     def to_torch_tensor_(self) -> "Variables":
-        """numpy -> FP32 tensors on the active device; everything except `area`
-        and `lambda_*` becomes a requires_grad leaf (idrlnet/variable.py:105-113)."""
+        """numpy -> tensors of torch's default dtype (FP32 unless the user switched it, exactly what the reference's
+        `torch.Tensor(val)` gives) on the active device; everything except `area` and `lambda_*` becomes a
+        requires_grad leaf (idrlnet/variable.py:105-113)."""
         dev = default_device()
         for key, val in self.items():
             if not isinstance(val, torch.Tensor):
-                t = torch.as_tensor(np.asarray(val), dtype=torch.float32).to(dev)
+                t = torch.as_tensor(np.asarray(val), dtype=torch.get_default_dtype()).to(dev)
                 if not key.startswith("lambda_") and key != "area":
                     t.requires_grad_()
                 self[key] = t

@@ -33,5 +33,33 @@ def main():
     np.savez(os.path.join(HERE, "train_trace.npz"), **out)
 
 
+def fp64_traces(names=("beam_lbfgs",)):
+    """FP64 tie-breaker traces: the same seeded case with the net cast to double and torch's default dtype
+    float64 (so `torch.Tensor(val)` in idrlnet/variable.py:109 keeps the NumPy points in double).  Appended to
+    train_trace.npz as `<case>/losses64`.  For the LBFGS beam the reference's OWN FP32 and FP64 traces separate by
+    5e-6, 2e-4, 1.6e-2, 2.3 ... per outer iteration: the case is chaotic in FP32, which is why the GPU FP32 run is
+    only compared for its first outer iterations while the FP64 run is compared for all twelve."""
+    _install_shims()
+    import torch
+    import idrlnet.shortcut as sc
+    path = os.path.join(HERE, "train_trace.npz")
+    out = dict(np.load(path))
+    for name in names:
+        net, kw = CASES[name](sc, tempfile.mkdtemp(), 12)
+        net.net.double()
+        torch.set_default_dtype(torch.float64)
+        try:
+            s = sc.Solver(**kw)
+            out[f"{name}/losses64"] = np.array([float(s.train_pipe()) for _ in range(12)])
+        finally:
+            torch.set_default_dtype(torch.float32)
+        print(name, "fp64", out[f"{name}/losses64"])
+    np.savez(path, **out)
+
+
 if __name__ == "__main__":
-    main()
+    if len(sys.argv) > 1 and sys.argv[1] == "--fp64":
+        fp64_traces(tuple(sys.argv[2:]) or ("beam_lbfgs",))
+    else:
+        main()
+        fp64_traces()
