@@ -439,10 +439,20 @@ def roofline_of(run: OursRun, kern_ms, fp32_peak, tf32_peak, hbm_peak, hbm_src):
 
 
 def torch_cuda_arm(name, local, steps=20, warmup=3, pipe_steps=4):
-    """The unmodified reference on this GPU (`idrlnet.use_gpu`), same workload; sizes halved on OOM by the harness."""
+    """The unmodified reference on this GPU (`idrlnet.use_gpu`), same workload, at the size where it ran fastest in the
+    sweep from the BASELINE size down to 1/64 of it (tools/ref_sweep.py -> baseline/ref_best_sizes.json; the reference
+    keeps the whole double-backward graph of a step in HBM -- 41 KB / point for ldc, 1.1 MB / point for mlp_xl -- so its
+    feasible N ends well below the 16 M / 64 M points of the named configs); without that file: the BASELINE size,
+    halved by the harness until it fits."""
+    sizes = None
+    path = os.path.join(ROOT, "baseline", "ref_best_sizes.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            sizes = json.load(f).get(name, {}).get("sizes")
     clk = ClockSampler(local).start()
-    res = run_harness(name, "cuda", steps, warmup, pipe_steps=pipe_steps, gpu_index=local)
+    res = run_harness(name, "cuda", steps, warmup, pipe_steps=pipe_steps, gpu_index=local, sizes=sizes)
     res["clocks"] = clk.stop()
+    res["size_choice"] = "best of the size sweep (baseline/ref_best_sizes.json)" if sizes else "BASELINE size, halved on OOM"
     return res
 
 

@@ -116,3 +116,73 @@ extern "C" int pinn_tc_selftest(int variant, int N, int K, const float* A, const
   pinn::count_launch(1);
   return (int)cudaGetLastError();
 }
+
+// ---- dense TF32 tcgen05 rate (roofline denominator of the wide tensor-core kernels) -------------------------
+namespace pinn {
+// One CTA per SM; thread 0 issues `iters` rounds of 8 MMAs (M = 128, N = 256, K = 8, kind::tf32, both operands
+// resident in shared memory, K-major canonical layout) into two alternating TMEM accumulators: nothing but the
+// tensor pipe and its shared-memory operand reads is exercised, which is the ceiling the wide kernels are held to.
+__global__ void __launch_bounds__(128) tf32_mma_probe_kernel(int iters, float* __restrict__ scratch) {
+  extern __shared__ __align__(128) float sm[];
+  __shared__ uint64_t bar;
+  __shared__ uint32_t tmem_slot;
+  constexpr int K = 64, N = 256;
+  float* sA = sm;            // [K/4][128][4]
+  float* sB = sm + 128 * K;  // [K/4][N][4]
+  const int tid = threadIdx.x, warp = tid >> 5;
+  for (int i = tid; i < (128 + N) * K; i += 128) {
+    const uint32_t h = (uint32_t)i * 2654435761u + blockIdx.x * 40503u;
+    sm[i] = tc::to_tf32((float)((h >> 9) & 0xFFFF) * (1.0f / 65536.0f) - 0.5f);
+  }
+  if (tid == 0) {
+    tc::mbar_init(&bar, 1);
+    tc::fence_mbar_init();
+  }
+  if (warp == 0) tc::tmem_alloc(&tmem_slot, 512);
+  tc::fence_async_smem();
+  tc::tc_fence_before();
+  __syncthreads();
+  tc::tc_fence_after();
+  const uint32_t tmem = tmem_slot;
+  if (tid == 0) {
+    const uint32_t idesc = tc::idesc_tf32(N, 0, 0);
+    for (int it = 0; it < iters; ++it) {
+      const uint32_t d = tmem + (uint32_t)(it & 1) * 256;
+      for (int ks = 0; ks < K / 8; ++ks) {
+        const uint64_t da = tc::smem_desc(tc::smem_u32(sA) + ks * 2 * (128 * 16), 128 * 16, 128);
+        const uint64_t db = tc::smem_desc(tc::smem_u32(sB) + ks * 2 * (N * 16), N * 16, 128);
+        tc::mma_tf32(d, da, db, idesc, (it > 1 || ks > 0) ? 1u : 0u);
+      }
+    }
+    tc::mma_commit(&bar);
+  }
+  const bool ok = tc::mbar_wait(&bar, 0);
+  tc::tc_fence_after();
+  if (ok) {
+    float v[4];
+    tc::tmem_ld4(tmem + ((uint32_t)(warp * 32) << 16), v);
+    tc::tmem_ld_wait();
+    if (v[0] == 123.456f) scratch[blockIdx.x] = v[1];  // keep the result observable
+  } else if (tid == 0) {
+    scratch[blockIdx.x] = -1.f;
+  }
+  tc::tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tc::tmem_dealloc(tmem, 512);
+}
+}  // namespace pinn
+
+extern "C" int64_t pinn_tf32_mma_probe(int32_t iters, float* scratch, void* stream) {
+  if (iters < 1 || !scratch) return PINN_E_INVALID;
+  int dev = 0, sms = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess)
+    return PINN_E_NO_DEVICE;
+  const size_t smem = (size_t)(128 + 256) * 64 * 4;
+  cudaError_t e = cudaFuncSetAttribute((const void*)pinn::tf32_mma_probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return -(int64_t)e;
+  pinn::tf32_mma_probe_kernel<<<sms, 128, smem, (cudaStream_t)stream>>>(iters, scratch);
+  pinn::count_launch(1);
+  e = cudaGetLastError();
+  if (e != cudaSuccess) return -(int64_t)e;
+  return (int64_t)sms * iters * 8 * 2 * 128 * 256 * 8;
+}

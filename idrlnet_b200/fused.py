@@ -127,7 +127,8 @@ class NetPack:
         fn = {"tanh": torch.tanh, "silu": torch.nn.functional.silu, "sin": torch.sin}[self.act]
         with torch.no_grad():
             g = torch.Generator(device="cpu").manual_seed(1234)
-            x = (torch.rand(16, self.n_in, generator=g) * 2 - 1).to(self.device)
+            x = (torch.rand(16, self.n_in, generator=g, device="cpu") * 2 - 1).to(self.device)  # explicit device: the
+            # reference's use_gpu() makes CUDA the default tensor type (idrlnet/__init__.py:29)
             want = self.module(x)
             h = x
             for i, l in enumerate(self.layers):

@@ -136,6 +136,7 @@ _SIGNATURES = {
                                   C.c_void_p, C.c_int64, C.c_void_p]),
     "pinn_fp32_fma_probe": (C.c_int64, [C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]),
     "pinn_fp32_fma2_probe": (C.c_int64, [C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]),
+    "pinn_tf32_mma_probe": (C.c_int64, [C.c_int32, C.c_void_p, C.c_void_p]),
     "pinn_tc_selftest": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
 }
 EXPORTS = tuple(_SIGNATURES)

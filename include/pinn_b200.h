@@ -255,6 +255,11 @@ PINN_API int64_t pinn_fp32_fma_probe(int32_t iters, int32_t blocks, float* scrat
 /* The same chains as packed pairs (fma.rn.f32x2, SASS FFMA2). */
 PINN_API int64_t pinn_fp32_fma2_probe(int32_t iters, int32_t blocks, float* scratch, void* stream);
 
+/* Dense TF32 tensor-core rate: one CTA per SM, each issuing `iters` x 8 tcgen05.mma (M=128, N=256, K=8, kind::tf32)
+ * on shared-memory-resident operands; returns the number of flops issued (time it with CUDA events: the roofline
+ * denominator of the wide tensor-core kernels), or a negative error.  `scratch` needs one float per SM. */
+PINN_API int64_t pinn_tf32_mma_probe(int32_t iters, float* scratch, void* stream);
+
 /* Self-test of the tcgen05 plumbing used by the wide tensor-core path: one CTA computes
  * D[128][N] = A * B^T in TF32 (FP32 accumulate in TMEM).  variant 0: A[128][K], B[N][K]
  * (K-major operands); variant 1: A[K][128], B[K][N] (MN-major operands).  *status (device
