@@ -474,6 +474,16 @@ def run_ours(args):
     cfg = wl.CONFIGS[args.config]
     sizes = wl.scaled_sizes(cfg["sizes"](world), args.sample) if args.sample else None
     head_prec = args.precision if cfg["wide"] else None
+    names = [] if args.no_configs else [n for n in ("poisson", "ldc", "allen_cahn", "ns_xl") if n != args.config]
+    if world > 1:
+        names = [n for n in names if n in ("ldc", "ns_xl")]  # the configs the north star names for multi-GPU runs
+    # ---- the reference's own PyTorch CUDA path on this B200 (the >= 20x denominator), FIRST: each arm
+    # is a fresh process that needs the whole 180 GB (116 GB for ldc at 2^21 points, 177 GB for mlp_xl at 2^17), so it runs
+    # before this process allocates anything on the device
+    ref_arms = {}
+    if world == 1 and not args.no_torch_cuda:
+        for name in [args.config] + names:
+            ref_arms[name] = torch_cuda_arm(name, local)
     clocks = ClockSampler(local).start()  # samples cover warm-up + timed region + e2e region (all under load)
     run = OursRun(args.config, device, world, rank, precision=head_prec, sizes=sizes)
     ms_per_step, kern_ms, final_loss, host_ms, launches = run.timed(args.steps, args.warmup)
@@ -490,9 +500,6 @@ def run_ours(args):
 
     # ---- the other BASELINE configurations at their stated sizes -------------------------------------------
     configs = {}
-    names = [] if args.no_configs else [n for n in ("poisson", "ldc", "allen_cahn", "ns_xl") if n != args.config]
-    if world > 1:
-        names = [n for n in names if n in ("ldc", "ns_xl")]  # the configs the north star names for multi-GPU runs
     for name in names:
         c = wl.CONFIGS[name]
         modes = WIDE_MODES if c["wide"] else (("", None),)
@@ -527,20 +534,16 @@ def run_ours(args):
                                  f"workload (unmodified idrlnet 2.0.0 from baseline/_ref, strict pass idrlnet/solver.py:329-339, FP32)"}
             else:
                 cpu = {"value": None, "unit": "points/s", "cores": cores, "kind": "reference", "sample": res.get("unavailable", "failed")}
-        if world == 1 and not args.no_torch_cuda:
-            # the reference's own PyTorch CUDA path on this B200: the >= 20x denominator
-            torch.cuda.empty_cache()
-            for name in [args.config] + names:
-                ref = torch_cuda_arm(name, local)
-                keys = [args.config] if name == args.config else [k for k in configs if k == name or k.startswith(name + "_")]
-                for key in keys:
-                    tgt = configs.setdefault(key, {}) if key != args.config else None
-                    ours_v = value if key == args.config else configs[key].get("value")
-                    ratio = (ours_v / ref["strict"]["value"]) if ("strict" in ref and ours_v) else None
-                    if tgt is None:
-                        head_ref, head_ratio = ref, ratio
-                    else:
-                        tgt["torch_cuda"], tgt["vs_torch_cuda"] = ref, ratio
+        head_ref = head_ratio = None
+        for name, ref in ref_arms.items():
+            ref_v = ref.get("strict", {}).get("value")
+            if name == args.config:
+                head_ref, head_ratio = ref, (value / ref_v if ref_v else None)
+                continue
+            for key in [k for k in configs if k == name or k.startswith(name + "_")]:
+                ours_v = configs[key].get("value")
+                configs[key]["torch_cuda"] = ref
+                configs[key]["vs_torch_cuda"] = (ours_v / ref_v) if (ours_v and ref_v) else None
         line = {
             "metric": METRIC, "value": value, "unit": "points/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": cfg["scaling"],

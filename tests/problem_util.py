@@ -288,31 +288,32 @@ def solver_from_problem(problem, network_dir, device=None, **solver_kw):
     return s, modules
 
 
-def _oracle_total(po, problem, nets, owners):
+def _oracle_total(po, problem, nets, owners, dtype=None):
     import torch
+    dtype = dtype or torch.float32
     for n in owners:
         n["layers_t"][:] = [((torch._weight_norm(l["v"], l["g"], 0) if "g" in l else l["W"]), l["b"]) for l in n["raw"]]
     total = 0.0
     for dom in problem["domains"]:
-        var = po.forward_domain(problem, dom, nets)
+        var = po.forward_domain(problem, dom, nets, dtype=dtype)
         like = next(iter(var.values()))
-        diff = {k: var[k] - po._as_t(t, torch.float32, like) for k, t in dom["targets"].items()}
-        lam = {k: po._as_t(t, torch.float32, like) for k, t in dom.get("lambdas", {}).items()}
+        diff = {k: var[k] - po._as_t(t, dtype, like) for k, t in dom["targets"].items()}
+        lam = {k: po._as_t(t, dtype, like) for k, t in dom.get("lambdas", {}).items()}
         for k in dom["targets"]:
             if k not in lam and ("lambda_" + k) in dom["points"]:
-                lam[k] = po._as_t(dom["points"]["lambda_" + k], torch.float32, like)
+                lam[k] = po._as_t(dom["points"]["lambda_" + k], dtype, like)
         total = total + float(dom.get("sigma", 1.0)) * po.weighted_loss(diff, lam, var["area"], dom.get("loss", "square"))
     return total
 
 
-def oracle_train(problem, steps, lr=1e-3, gamma=0.95 ** 0.001, lbfgs=None):
+def oracle_train(problem, steps, lr=1e-3, gamma=0.95 ** 0.001, lbfgs=None, dtype=None):
     """The reference training loop on the oracle (CPU, FP32): Adam + ExponentialLR
     (idrlnet/optim.py:70-80), fixed points; returns the per-step (pre-update) losses.
     `lbfgs=dict(lr=, max_iter=)` runs the closure branch instead (idrlnet/solver.py:316-326);
     the value returned per step is then the first closure evaluation's loss, as torch's LBFGS does."""
     import torch
     from oracle import pinn_oracle as po
-    nets = po.build_nets(problem)
+    nets = po.build_nets(problem, dtype=dtype or torch.float32)
     owners = [n for n in nets if not n.get("shares")]
     leaves = [t for n in owners for lay in n["raw"] for t in lay.values()]
     if lbfgs is not None:
@@ -320,7 +321,7 @@ def oracle_train(problem, steps, lr=1e-3, gamma=0.95 ** 0.001, lbfgs=None):
 
         def closure():
             opt.zero_grad()
-            total = _oracle_total(po, problem, nets, owners)
+            total = _oracle_total(po, problem, nets, owners, dtype)
             total.backward()
             return total
         return [float(opt.step(closure).detach()) for _ in range(steps)]
@@ -328,7 +329,7 @@ def oracle_train(problem, steps, lr=1e-3, gamma=0.95 ** 0.001, lbfgs=None):
     losses = []
     for step in range(steps):
         opt.zero_grad()
-        total = _oracle_total(po, problem, nets, owners)
+        total = _oracle_total(po, problem, nets, owners, dtype)
         total.backward()
         opt.step()
         for g in opt.param_groups:

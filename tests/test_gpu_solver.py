@@ -54,19 +54,35 @@ def test_loss_curve_tracks_reference_training(name, tmp_path):
     """SURVEY 8(c6) / BASELINE.md 3.4: 1k-step loss curves on simple_poisson AND ldc.  The Solver runs with its
     defaults, i.e. the reference's `train_pipe` semantics (idrlnet/solver.py:341-344): the loss returned by step i
     is the gradient-free re-evaluation AFTER update i -- with the fixed points of these problems that is the
-    pre-update loss of step i+1 of the reference training loop (oracle + Adam + ExponentialLR on the CPU)."""
+    pre-update loss of step i+1 of the reference training loop (oracle + Adam + ExponentialLR on the CPU).
+
+    Tie-breaker: the same loop is also run in FP64.  Wherever the reference algorithm's own FP32 and
+    FP64 curves agree (1e-5), the kernels must match the FP32 curve to 2e-4.  On ldc the two reference curves sit on a
+    plateau (8.78e-4) until about step 600 and then leave it at rounding-dependent times -- they differ from EACH OTHER
+    by up to 47 % between steps 650 and 1000 -- so there the kernels are held to that envelope, not to 2e-4."""
     steps, tol = 1000, 2e-4
     problem, _ = gu.load(name)
-    ref_losses = np.asarray(pu.oracle_train(problem, steps + 1))
+    ref32 = np.asarray(pu.oracle_train(problem, steps + 1))
+    ref64 = np.asarray(pu.oracle_train(problem, steps + 1, dtype=torch.float64))
+    env = np.abs(ref32 - ref64)[1:] / np.abs(ref64[1:])
+    stable = int(np.argmax(env > 1e-5)) if (env > 1e-5).any() else steps  # steps before the reference turns chaotic
+    assert stable >= 500, (name, stable)
     s, _ = pu.solver_from_problem(problem, tmp_path, max_iter=steps, save_freq=10 ** 9, print_freq=10 ** 9)
     assert s.post_step_loss  # the drop-in default is the reference's
     ours = []
     for _ in range(steps):
         ours.append(s.train_pipe())
     ours = torch.stack([l.reshape(()) for l in ours]).cpu().numpy()
-    rel = np.abs(ours - ref_losses[1:]) / np.abs(ref_losses[1:])
-    assert ours[-1] < ref_losses[0]
-    assert rel.max() <= tol, (int(rel.argmax()), float(rel.max()), ours[:3], ref_losses[:4])
+    rel = np.abs(ours - ref32[1:]) / np.abs(ref32[1:])
+    print(f"{name}: reference FP32 vs FP64 agree to 1e-5 for {stable} steps (max separation {env.max():.2e}); "
+          f"ours vs reference FP32: {rel[:stable].max():.2e} there, {rel.max():.2e} over all {steps} steps")
+    assert ours[-1] < ref32[0]
+    assert rel[:stable].max() <= tol, (int(rel[:stable].argmax()), float(rel[:stable].max()), ours[:3], ref32[:4])
+    if stable < steps:
+        rel64 = np.abs(ours - ref64[1:]) / np.abs(ref64[1:])
+        assert min(rel.max(), rel64.max()) <= 2.0 * env.max(), (float(rel.max()), float(rel64.max()), float(env.max()))
+    else:
+        assert rel.max() <= tol
 
 
 def test_fast_mode_returns_the_pre_update_loss(tmp_path):
