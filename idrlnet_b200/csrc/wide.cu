@@ -773,21 +773,14 @@ int run_mode(const pinn_mlp* m, const pinn_jets* j, int mode, const pinn_domain*
       rc = tc_transpose(n.W[l - 1], w + wl.wt + (size_t)(l - 2) * n.H * n.H, n.H, st);
       if (rc) return rc;
     }
-  // second-generation on-chip kernel (wide_fused2.cu) wherever its TMEM / shared-memory budget allows;
-  // PINN_WIDE_FUSED_GEN=1 in the environment selects the first generation (for comparison runs)
-  static const bool gen1 = [] { const char* e = getenv("PINN_WIDE_FUSED_GEN"); return e && e[0] == '1'; }();
-  const bool gen2 = on_chip && !gen1 && fused2_wide_supported(n);
   if (n.precision == 1 && stepping && prep && n.H <= 128 && n.L >= 2) {
-    rc = gen2 ? fused2_wide_prep(n, w + wl.wprep, st) : fused_wide_prep(n, w + wl.wprep, st);
+    rc = fused_wide_prep(n, w + wl.wprep, st);
     if (rc) return rc;
   }
   if (on_chip) {
     // whole step on chip; same partial slots, same finalize
-#define RUNF(A)                                                                                                                  \
-  rc = gen2 ? fused2_wide_launch<A>(n, dom, w + wl.Z, w + wl.wprep, w + wl.dw, w + wl.db, w + wl.first, w + wl.head, wl.n_splits, \
-                                    mode == W_MODE_LOSS, st)                                                                     \
-            : fused_wide_launch<A>(n, dom, w + wl.Z, w + wl.wprep, w + wl.dw, w + wl.db, w + wl.first, w + wl.head, wl.n_splits,  \
-                                   mode == W_MODE_LOSS, st)
+#define RUNF(A)                                                                                                   \
+  rc = fused_wide_launch<A>(n, dom, w + wl.Z, w + wl.wprep, w + wl.dw, w + wl.db, w + wl.first, w + wl.head, wl.n_splits, mode == W_MODE_LOSS, st)
     ACT_SWITCH(n.act, RUNF);
 #undef RUNF
     if (rc) return rc;

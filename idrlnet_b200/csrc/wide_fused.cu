@@ -24,48 +24,76 @@ namespace {
 
 constexpr int kP = 16;       // points per tile
 constexpr int kMaxHid = 4;   // hidden layers supported (TMEM: 128 + 3 * 128 columns)
+constexpr int kSl = 6;       // unit slices of the SIMT output layer (kSl * C * kP <= 512 threads for C <= 5)
 
 struct FusedArgs {
   pinn_domain dom;
   const float* xs[PINN_MAX_IN];
   int64_t n_points;
   float* stash;          // [cta][(L-1)][C][kP][128]
-  const float* wprep;    // [2*(l-2) + dir][Kq*129*4]: W_l (dir 0) / W_l^T (dir 1), TF32-rounded, canonical padded tiles
+  const float* wprep;    // [2*(l-2) + dir][Kq*128*4]: W_l (dir 0) / W_l^T (dir 1), TF32-rounded, K-major canonical tiles
   float* dw_part;        // [(l-2)][n_splits][H*H]
   float* db_part;        // [(l-2)][kBlocks][8][H]
   float* first_part;     // [kBlocks][8][H]
   float* head_part;      // [kBlocks][O*H + O + 1]
   int n_splits;
   int loss_only;         // forward + residual + loss only: no stash, no reverse sweep, no gradient partials
+  int dbl;               // two sHt buffers: h_{l-2} is prepared while the GEMMs of reverse step l run
 };
 
-// G point groups: 128 * G threads, thread (unit j, group g) handles the kP / G points g * kP / G ... of the tile.
-// G = 4 (16 warps, <= 128 registers) hides the latency of the serial layer chain better than G = 2 (8 warps, up to
-// 234 registers): +8 % on the 5-channel LDC interior, and the value-only boundary domains are L2-latency bound.
-template <int NF, int NS, int ACT, int G>
-__global__ void __launch_bounds__(128 * G, 1) wide_fused_kernel(WNet net, const __grid_constant__ FusedArgs fa) {
+struct FusedSmem {  // offsets in floats
+  int sW, sX, sZt, sHt, sHt2, sY, sP, sXc, sWo, sG, total;
+};
+__host__ __device__ inline FusedSmem fused_smem(int H, int C, bool dbl) {
+  const int H8 = (H + 7) & ~7, Kq = H8 / 4, N = C * kP, N2 = (H + 15) & ~15;
+  FusedSmem s;
+  int off = 0;
+  s.sW = off; off += Kq * 128 * 4;               // [Kq][128][4]      A operand: W_l or W_l^T (arrives by bulk copy)
+  s.sX = off; off += Kq * (N + 1) * 4;           // [Kq][N + 1][4]    B operand: h_{l-1} / zbar_l, K = unit
+  s.sZt = off; off += (N / 4) * 129 * 4;         // [N/4][129][4]     A operand of dW: zbar_l, K = (channel, point)
+  s.sHt = off; off += (N / 4) * (N2 + 1) * 4;    // [N/4][N2 + 1][4]  B operand of dW: h_{l-1}, K = (channel, point)
+  s.sHt2 = dbl ? off : s.sHt; off += dbl ? (N / 4) * (N2 + 1) * 4 : 0;
+  s.sY = off; off += 2 * N * 4;                  // y[N][4], then ybar[N][4]
+  s.sP = off; off += kSl * N * 4;                // partial sums of the output layer
+  s.sXc = off; off += kP * 4;                    // coordinates of the tile
+  s.sWo = off; off += 4 * 128;                   // Wout[o][k]
+  s.sG = off; off += PINN_MAX_EQ * kP;           // loss seeds of the tile
+  s.total = off;
+  return s;
+}
+
+// round-to-nearest (ties away) to TF32: what cvt.rna.tf32.f32 expands to on sm_100a minus its inf/nan test
+// (the operands here are finite activations and adjoints): 2 instructions instead of 3
+__device__ __forceinline__ float tf32r(float x) { return __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xffffe000u); }
+
+// 512 threads: thread (unit j = TMEM lane, point group g) handles the four points 4g .. 4g+3 of the tile.
+template <int NF, int NS, int ACT>
+__global__ void __launch_bounds__(512, 1) wide_fused_kernel(WNet net, const __grid_constant__ FusedArgs fa) {
   constexpr int C = 1 + NF + NS;
   constexpr int N = C * kP;
-  constexpr int kT = 128 * G, kPP = kP / G;
+  constexpr int kT = 512, G = 4;
   const int H = net.H, L = net.L, O = net.n_out;
   const int H8 = (H + 7) & ~7, Kq = H8 / 4, N2 = (H + 15) & ~15;
   extern __shared__ __align__(128) float sm[];
   __shared__ uint64_t bar[2];  // [0]: MMA completion, [1]: weight tile landed
   __shared__ uint32_t tmem_slot;
-  float* sW = sm;                           // [Kq][129][4]      A operand: W_l or W_l^T
-  float* sX = sW + Kq * 129 * 4;            // [Kq][N + 1][4]    B operand: h_{l-1} / zbar_l, K = unit
-  float* sZt = sX + Kq * (N + 1) * 4;       // [N/4][129][4]     A operand of dW: zbar_l, K = (channel, point)
-  float* sHt = sZt + (N / 4) * 129 * 4;     // [N/4][N2 + 1][4]  B operand of dW: h_{l-1}, K = (channel, point)
-  float* sY = sHt + (N / 4) * (N2 + 1) * 4; // [N][4]  y, then ybar
-  float* sXc = sY + 2 * N * 4;              // [kP][4] coordinates of the tile
-  float* sWo = sXc + kP * 4;                // [4][128] Wout[o][k]
-  float* sG = sWo + 4 * 128;                // [PINN_MAX_EQ][kP] loss seeds of the tile
+  const FusedSmem lay = fused_smem(H, C, fa.dbl != 0);
+  float* const sW = sm + lay.sW;
+  float* const sX = sm + lay.sX;
+  float* const sZt = sm + lay.sZt;
+  float* const sY = sm + lay.sY;
+  float* const sYb = sY + N * 4;
+  float* const sP = sm + lay.sP;
+  float* const sXc = sm + lay.sXc;
+  float* const sWo = sm + lay.sWo;
+  float* const sG = sm + lay.sG;
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int j = (warp & 3) * 32 + lane;     // hidden unit owned by this thread (TMEM lane)
-  const int grp = warp >> 2;                // which kPP of the tile's 16 points this thread handles
+  const int grp = warp >> 2;                // which four of the tile's 16 points this thread handles
   const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
-  const bool unit_ok = j < H;
+  const bool unit_ok = j < H;               // only the final flush needs it: padded units carry exact zeros throughout
+  const bool k_ok = j < H8, n2_ok = j < N2; // rows of the K = unit / K = (channel, point) operands this thread writes
 
   if (tid == 0) {
     tc::mbar_init(&bar[0], 1);
@@ -83,21 +111,27 @@ __global__ void __launch_bounds__(128 * G, 1) wide_fused_kernel(WNet net, const 
   const uint32_t tmem = tmem_slot;
   uint32_t phase = 0, wphase = 0;
   // weight tiles are consumed in a fixed cyclic order per point tile: W_2 .. W_L, W_L^T .. W_2^T
-  const uint32_t wbytes = (uint32_t)(Kq * 129 * 4 * sizeof(float));
+  const uint32_t wbytes = (uint32_t)(Kq * 128 * 4 * sizeof(float));
   const int n_seq = fa.loss_only ? (L - 1) : 2 * (L - 1);
-  int wseq = 0;  // next tile to fetch (thread 0 only)
+  const int64_t n_tiles = (fa.n_points + kP - 1) / kP;
+  const int64_t my_tiles = blockIdx.x < n_tiles ? (n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+  int64_t wleft = my_tiles * n_seq;  // weight tiles still to fetch (thread 0 only)
+  int wseq = 0;
   auto fetch_weights = [&]() {  // thread 0: asynchronous bulk copy of the next weight tile into sW
-    const int sidx = wseq % n_seq;
+    if (wleft <= 0) return;
+    --wleft;
+    const int sidx = wseq;
+    wseq = (wseq + 1 == n_seq) ? 0 : wseq + 1;
     const int l = sidx < L - 1 ? 2 + sidx : L - (sidx - (L - 1));
     const int dir = sidx < L - 1 ? 0 : 1;
     tc::mbar_expect_tx(&bar[1], wbytes);
     tc::bulk_copy_g2s(sW, fa.wprep + (size_t)(2 * (l - 2) + dir) * (wbytes / 4), wbytes, &bar[1]);
-    ++wseq;
   };
-  if (tid == 0 && blockIdx.x < (fa.n_points + kP - 1) / kP) fetch_weights();
+  if (tid == 0) fetch_weights();
 
-  // per-unit constants in registers
-  float w1[4] = {0.f, 0.f, 0.f, 0.f}, b1 = 0.f, bl[kMaxHid] = {0.f, 0.f, 0.f, 0.f}, wo[4];
+  // per-unit constants in registers (zero for padded units: their pre-activations, activations and adjoints are then
+  // exactly zero everywhere -- tanh(0) = sin(0) = silu(0) = 0 and every derivative channel is a multiple of a zero)
+  float w1[4] = {0.f, 0.f, 0.f, 0.f}, b1 = 0.f, bl[kMaxHid] = {0.f, 0.f, 0.f, 0.f};
   if (unit_ok) {
 #pragma unroll
     for (int d = 0; d < 4; ++d)  // static indices keep w1 in registers
@@ -107,8 +141,6 @@ __global__ void __launch_bounds__(128 * G, 1) wide_fused_kernel(WNet net, const 
     for (int l = 2; l <= kMaxHid; ++l)
       if (l <= L) bl[l - 1] = net.b[l - 1][j];
   }
-#pragma unroll
-  for (int o = 0; o < 4; ++o) wo[o] = sWo[o * 128 + j];
   float w1f[NF > 0 ? NF : 1];
 #pragma unroll
   for (int i = 0; i < NF; ++i) {
@@ -116,30 +148,46 @@ __global__ void __launch_bounds__(128 * G, 1) wide_fused_kernel(WNet net, const 
     w1f[i] = d == 0 ? w1[0] : d == 1 ? w1[1] : d == 2 ? w1[2] : w1[3];
   }
 
-  // per-unit gradient accumulators (both point halves accumulate; summed at the end)
+  // per-unit gradient accumulators (all four point groups accumulate; summed at the end)
   float g_w1[4] = {0.f, 0.f, 0.f, 0.f}, g_b[kMaxHid + 1] = {0.f, 0.f, 0.f, 0.f, 0.f}, g_wo[4] = {0.f, 0.f, 0.f, 0.f};
   float g_bo_r = 0.f, loss = 0.f;  // threads (o, p) = tid < 64 / threads (e, p) = tid < 128, summed at the end
 
-  float* stash = fa.stash + (size_t)blockIdx.x * (L - 1) * C * kP * 128;
+  // per-thread bases: every element this thread touches is base + a compile-time offset (c, pp)
+  const int p0 = grp * 4;
+  float* const stash_t = fa.stash + (size_t)blockIdx.x * (L - 1) * C * kP * 128 + p0 * 128 + j;  // + ((l-2)*C + c)*kP*128 + pp*128
+  float* const sx_t = sX + ((j >> 2) * (N + 1) + p0) * 4 + (j & 3);                              // + (c*kP + pp)*4
+  float* const szt_t = sZt + (grp * 129 + j) * 4;                                                // + c*4*129*4   (float4 = 4 points)
+  const int sht_off = (grp * (N2 + 1) + j) * 4;                                                  // + c*4*(N2+1)*4 (float4 = 4 points)
+  const uint32_t t_acc = tmem + lane_base + p0;                                                  // + c*kP
   const uint32_t idesc_x = tc::idesc_tf32(N, 0, 0), idesc_w = tc::idesc_tf32(N2, 0, 0);
-  const int64_t n_tiles = (fa.n_points + kP - 1) / kP;
   bool first_tile = true;
 
-  auto layer1 = [&](const float (&x)[4], float (&z)[C]) {
-    float v = b1;
-#pragma unroll
-    for (int d = 0; d < 4; ++d) v += w1[d] * x[d];
-    z[0] = v;
+  auto layer1 = [&](int p, float (&z)[C]) {
+    const float4 xv = *reinterpret_cast<const float4*>(sXc + p * 4);
+    z[0] = b1 + w1[0] * xv.x + w1[1] * xv.y + w1[2] * xv.z + w1[3] * xv.w;
 #pragma unroll
     for (int i = 0; i < NF; ++i) z[1 + i] = w1f[i];
 #pragma unroll
     for (int s = 0; s < NS; ++s) z[1 + NF + s] = 0.f;
   };
-  // element (row q = c*kP + p, K index = unit j) of the K = unit operand
-  auto sx_at = [&](int q) -> float& { return sX[((j >> 2) * (N + 1) + q) * 4 + (j & 3)]; };
-  // element (row = unit j, K index q) of the K = (channel, point) operands
-  auto szt_at = [&](int q) -> float& { return sZt[((q >> 2) * 129 + j) * 4 + (q & 3)]; };
-  auto sht_at = [&](int q) -> float& { return sHt[((q >> 2) * (N2 + 1) + j) * 4 + (q & 3)]; };
+  // z_m of this thread's point pp: from the stash (m >= 2) or recomputed (m == 1)
+  auto load_z = [&](int m, int pp, float (&z)[C]) {
+    if (m >= 2) {
+      const float* sp = stash_t + (size_t)(m - 2) * C * kP * 128 + pp * 128;
+#pragma unroll
+      for (int c = 0; c < C; ++c) z[c] = sp[c * kP * 128];
+    } else {
+      layer1(p0 + pp, z);
+    }
+  };
+  // h_m (TF32) of this thread's four points -> the K = (channel, point) operand buffer `dst` (one 128-bit store per channel)
+  auto store_ht = [&](float* dst, const float (&hq)[C][4]) {
+    if (n2_ok) {
+#pragma unroll
+      for (int c = 0; c < C; ++c)
+        *reinterpret_cast<float4*>(dst + sht_off + c * 4 * (N2 + 1) * 4) = make_float4(hq[c][0], hq[c][1], hq[c][2], hq[c][3]);
+    }
+  };
 
   int64_t n0 = 0;
   // residual symbol of point p of the current tile: output jets (sY), coordinates (sXc), aux columns (global)
@@ -149,7 +197,8 @@ __global__ void __launch_bounds__(128 * G, 1) wide_fused_kernel(WNet net, const 
     return (n0 + p < fa.n_points) ? fa.dom.aux[id - PINN_SYM_AUX0][n0 + p] : 0.f;
   };
 
-  auto run_mma = [&](bool with_dw, int l, bool more) {  // D = sW * sX^T  (+ optionally D2_l += sZt * sHt^T)
+  // D = sW * sX^T  (+ optionally D2_l += sZt * sHt^T): barrier, then ONE thread issues; nobody waits here
+  auto issue_mma = [&](bool with_dw, int l, const float* sHt_cur) {
     tc::fence_async_smem();
     __syncthreads();
     if (tid == 0) {
@@ -157,7 +206,7 @@ __global__ void __launch_bounds__(128 * G, 1) wide_fused_kernel(WNet net, const 
       ++wphase;
       tc::tc_fence_after();
       for (int ks = 0; ks < H8 / 8; ++ks) {
-        const uint64_t da = tc::smem_desc(tc::smem_u32(sW) + ks * 2 * (129 * 16), 129 * 16, 128);
+        const uint64_t da = tc::smem_desc(tc::smem_u32(sW) + ks * 2 * (128 * 16), 128 * 16, 128);
         const uint64_t db = tc::smem_desc(tc::smem_u32(sX) + ks * 2 * ((N + 1) * 16), (N + 1) * 16, 128);
         tc::mma_tf32(tmem, da, db, idesc_x, ks > 0 ? 1u : 0u);
       }
@@ -165,16 +214,18 @@ __global__ void __launch_bounds__(128 * G, 1) wide_fused_kernel(WNet net, const 
         const uint32_t d2 = tmem + 128 + (uint32_t)(l - 2) * 128;
         for (int ks = 0; ks < N / 8; ++ks) {
           const uint64_t da = tc::smem_desc(tc::smem_u32(sZt) + ks * 2 * (129 * 16), 129 * 16, 128);
-          const uint64_t db = tc::smem_desc(tc::smem_u32(sHt) + ks * 2 * ((N2 + 1) * 16), (N2 + 1) * 16, 128);
+          const uint64_t db = tc::smem_desc(tc::smem_u32(sHt_cur) + ks * 2 * ((N2 + 1) * 16), (N2 + 1) * 16, 128);
           tc::mma_tf32(d2, da, db, idesc_w, (first_tile && ks == 0) ? 0u : 1u);
         }
       }
       tc::mma_commit(&bar[0]);
     }
+  };
+  auto wait_mma = [&]() {
     if (!tc::mbar_wait(&bar[0], phase & 1)) __trap();
     ++phase;
     tc::tc_fence_after();
-    if (tid == 0 && more) fetch_weights();  // sW is free again: overlap the next tile's copy with the epilogue
+    if (tid == 0) fetch_weights();  // sW is free again: the next tile's copy overlaps the epilogue
   };
 
   for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
@@ -186,61 +237,89 @@ __global__ void __launch_bounds__(128 * G, 1) wide_fused_kernel(WNet net, const 
     }
     __syncthreads();
 
-    // ---- hidden layer 1 (SIMT): h_1 -> sX -------------------------------------------------
-#pragma unroll 2
-    for (int pp = 0; pp < kPP; ++pp) {
-      const int p = grp * kPP + pp;
-      float x[4] = {sXc[p * 4], sXc[p * 4 + 1], sXc[p * 4 + 2], sXc[p * 4 + 3]};
-      float z[C], h[C];
-      layer1(x, z);
-      jet_fwd_t<ACT, NF, NS, true>(z, h);
-      if (j < H8) {
+    // ---- hidden layer 1 (SIMT): h_1 -> sX (and -> sHt when it is the dW operand of the first reverse step) ------
+    {
+      float hq[C][4];
 #pragma unroll
-        for (int c = 0; c < C; ++c) sx_at(c * kP + p) = unit_ok ? tc::to_tf32(h[c]) : 0.f;
-      }
-    }
-    // ---- hidden layers 2..L: tensor-core GEMM + activation epilogue -------------------------
-    for (int l = 2; l <= L; ++l) {
-      run_mma(false, 0, !(fa.loss_only && l == L && tile + gridDim.x >= n_tiles));
-      float v[C][kPP];
-#pragma unroll
-      for (int c = 0; c < C; ++c) tc::tmem_ldn(tmem + lane_base + c * kP + grp * kPP, v[c]);
-      tc::tmem_ld_wait();
-      const float bias = l == 2 ? bl[1] : l == 3 ? bl[2] : bl[3];
-#pragma unroll
-      for (int pp = 0; pp < kPP; ++pp) {
-        const int p = grp * kPP + pp;
+      for (int pp = 0; pp < 4; ++pp) {
         float z[C], h[C];
-#pragma unroll
-        for (int c = 0; c < C; ++c) z[c] = v[c][pp];
-        z[0] += bias;
+        layer1(p0 + pp, z);
         jet_fwd_t<ACT, NF, NS, true>(z, h);
 #pragma unroll
         for (int c = 0; c < C; ++c) {
-          if (!fa.loss_only) stash[(((size_t)(l - 2) * C + c) * kP + p) * 128 + j] = z[c];
-          if (j < H8) sx_at(c * kP + p) = unit_ok ? (l == L ? h[c] : tc::to_tf32(h[c])) : 0.f;
+          hq[c][pp] = tf32r(h[c]);
+          if (k_ok) sx_t[(c * kP + pp) * 4] = hq[c][pp];
         }
       }
+      if (L == 2 && !fa.loss_only) store_ht(sm + lay.sHt, hq);
+    }
+    // ---- hidden layers 2..L: tensor-core GEMM + activation epilogue; the stash stores of layer l ride in the
+    //      shadow of the GEMM of layer l + 1 ----------------------------------------------------------------------
+    float zk[C][4];  // pre-activations of the layer just finished (kept for the deferred stash stores)
+    for (int l = 2; l <= L; ++l) {
+      issue_mma(false, 0, nullptr);
+      if (l > 2 && !fa.loss_only && k_ok) {  // z_{l-1} -> stash while the GEMM of layer l runs
+        float* sp = stash_t + (size_t)(l - 3) * C * kP * 128;
+#pragma unroll
+        for (int c = 0; c < C; ++c)
+#pragma unroll
+          for (int pp = 0; pp < 4; ++pp) sp[c * kP * 128 + pp * 128] = zk[c][pp];
+      }
+      wait_mma();
+#pragma unroll
+      for (int c = 0; c < C; ++c) tc::tmem_ld4(t_acc + c * kP, zk[c]);
+      tc::tmem_ld_wait();
+      const float bias = l == 2 ? bl[1] : l == 3 ? bl[2] : bl[3];
+      float hq[C][4];
+#pragma unroll
+      for (int pp = 0; pp < 4; ++pp) {
+        float z[C], h[C];
+        zk[0][pp] += bias;
+#pragma unroll
+        for (int c = 0; c < C; ++c) z[c] = zk[c][pp];
+        jet_fwd_t<ACT, NF, NS, true>(z, h);
+#pragma unroll
+        for (int c = 0; c < C; ++c) {
+          hq[c][pp] = tf32r(h[c]);
+          if (k_ok) sx_t[(c * kP + pp) * 4] = (l == L) ? h[c] : hq[c][pp];  // h_L stays FP32 for the SIMT output layer
+        }
+      }
+      if (l == L - 1 && !fa.loss_only) store_ht(sm + lay.sHt, hq);  // h_{L-1}: B operand of dW_L, first reverse step
       tc::tc_fence_before();
     }
-    __syncthreads();
-    // ---- output layer (FP32 SIMT): y[q][o] = sum_k Wout[o][k] h_L[q][k] (h_L kept in FP32) ------
-    if (tid < N) {
-      const int q = tid;
-      float y[4] = {0.f, 0.f, 0.f, 0.f};
-      for (int k = 0; k < H; ++k) {
-        const float hv = sX[((k >> 2) * (N + 1) + q) * 4 + (k & 3)];
+    if (!fa.loss_only && k_ok) {  // z_L -> stash
+      float* sp = stash_t + (size_t)(L - 2) * C * kP * 128;
 #pragma unroll
-        for (int o = 0; o < 4; ++o) y[o] += sWo[o * 128 + k] * hv;
-      }
-      if (q < kP) {
+      for (int c = 0; c < C; ++c)
 #pragma unroll
-        for (int o = 0; o < 4; ++o)
-          if (o < O) y[o] += net.b[L][o];
-      }
-      *reinterpret_cast<float4*>(sY + q * 4) = make_float4(y[0], y[1], y[2], y[3]);
+        for (int pp = 0; pp < 4; ++pp) sp[c * kP * 128 + pp * 128] = zk[c][pp];
     }
     __syncthreads();
+    // ---- output layer (FP32 SIMT, h_L in FP32): partial sums over kSl slices of the units, then a short reduction ----
+    {
+      const int per = (H + kSl - 1) / kSl;
+      for (int t = tid; t < kSl * N; t += kT) {
+        const int q = t % N, sl = t / N;
+        const int k0 = sl * per, k1 = min(H, k0 + per);
+        float y[4] = {0.f, 0.f, 0.f, 0.f};
+        for (int k = k0; k < k1; ++k) {
+          const float hv = sX[((k >> 2) * (N + 1) + q) * 4 + (k & 3)];
+#pragma unroll
+          for (int o = 0; o < 4; ++o) y[o] += sWo[o * 128 + k] * hv;
+        }
+        *reinterpret_cast<float4*>(sP + (sl * N + q) * 4) = make_float4(y[0], y[1], y[2], y[3]);
+      }
+      __syncthreads();
+      if (tid < N * 4) {
+        const int q = tid >> 2, o = tid & 3;
+        float y = 0.f;
+#pragma unroll
+        for (int sl = 0; sl < kSl; ++sl) y += sP[(sl * N + q) * 4 + o];
+        if (q < kP && o < O) y += net.b[L][o];
+        sY[q * 4 + o] = y;
+      }
+      __syncthreads();
+    }
     // ---- residual, loss, ybar: two short parallel phases instead of one thread per point ---------
     // R1: thread (point p, equation e) evaluates r_e, the loss term and the seed g = f'(r - target) * w * sigma
     if (tid < kP * PINN_MAX_EQ) {
@@ -290,76 +369,64 @@ __global__ void __launch_bounds__(128 * G, 1) wide_fused_kernel(WNet net, const 
           }
         }
       }
-      sY[N * 4 + ((id >> 2) * kP + p) * 4 + (id & 3)] = acc;
+      sYb[((id >> 2) * kP + p) * 4 + (id & 3)] = acc;
       if (item < 4 * kP) g_bo_r += acc;  // value channel of output o = id: dL/d bout[o]  (item == tid here)
     }
     __syncthreads();
-    const float* sYb = sY + N * 4;
 
     // ---- reverse sweep -------------------------------------------------------------------
-    // step "l": produce zbar_l (into sX and sZt) and h_{l-1} (into sHt); then the tensor cores
-    // compute hbar_{l-1} = W_l^T zbar_l and dW_l += zbar_l^T h_{l-1}.
-    bool last_weights = false;
+    // step l: zbar_l -> sX and sZt; the tensor cores then compute hbar_{l-1} = W_l^T zbar_l and dW_l += zbar_l^T h_{l-1}
+    // with h_{l-1} taken from an sHt buffer that was filled EARLIER: by the forward epilogue (l = L), or -- with two
+    // buffers -- while the GEMMs of step l + 1 were running.
+    int buf = 0;
     for (int l = L; l >= 1; --l) {
-      // stash reads do not depend on the tensor cores: issue them first
-      float zl[C][kPP], zp[C][kPP];
+      float zl[C][4];  // z_l of the four points (stash reads do not depend on the tensor cores: issued before the wait)
 #pragma unroll
-      for (int pp = 0; pp < kPP; ++pp) {
-        const int p = grp * kPP + pp;
+      for (int pp = 0; pp < 4; ++pp) {
+        float z[C];
+        load_z(l, pp, z);
 #pragma unroll
-        for (int c = 0; c < C; ++c) {
-          zl[c][pp] = (l >= 2) ? stash[(((size_t)(l - 2) * C + c) * kP + p) * 128 + j] : 0.f;
-          zp[c][pp] = (l >= 3) ? stash[(((size_t)(l - 3) * C + c) * kP + p) * 128 + j] : 0.f;
-        }
+        for (int c = 0; c < C; ++c) zl[c][pp] = z[c];
       }
-      float v[C][kPP];
-      if (l < L) {
+      float wo[4];
+      if (l == L) {
 #pragma unroll
-        for (int c = 0; c < C; ++c) tc::tmem_ldn(tmem + lane_base + c * kP + grp * kPP, v[c]);
-        tc::tmem_ld_wait();
+        for (int o = 0; o < 4; ++o) wo[o] = sWo[o * 128 + j];
+      } else {
+        wait_mma();
       }
+      float zq[C][4];  // zbar_l (TF32) of the four points
 #pragma unroll
-      for (int pp = 0; pp < kPP; ++pp) {
-        const int p = grp * kPP + pp;
-        float x[4] = {sXc[p * 4], sXc[p * 4 + 1], sXc[p * 4 + 2], sXc[p * 4 + 3]};
-        float z[C], hb[C], zb[C], h[C];
-        if (l >= 2) {
+      for (int pp = 0; pp < 4; ++pp) {
+        const int p = p0 + pp;
+        float z[C], hb[C], zb[C];
 #pragma unroll
-          for (int c = 0; c < C; ++c) z[c] = zl[c][pp];
-        } else {
-          layer1(x, z);
-        }
-        // hbar_l: from ybar (l == L) or from the GEMM accumulators
+        for (int c = 0; c < C; ++c) z[c] = zl[c][pp];
         if (l == L) {
-#pragma unroll
-          for (int c = 0; c < C; ++c) {
-            const float4 t = *reinterpret_cast<const float4*>(sYb + (c * kP + p) * 4);
-            hb[c] = wo[0] * t.x + wo[1] * t.y + wo[2] * t.z + wo[3] * t.w;
-          }
+          float h[C];
           jet_fwd_t<ACT, NF, NS, true>(z, h);  // h_L for dWout
 #pragma unroll
           for (int c = 0; c < C; ++c) {
             const float4 t = *reinterpret_cast<const float4*>(sYb + (c * kP + p) * 4);
+            hb[c] = wo[0] * t.x + wo[1] * t.y + wo[2] * t.z + wo[3] * t.w;
             g_wo[0] += t.x * h[c]; g_wo[1] += t.y * h[c]; g_wo[2] += t.z * h[c]; g_wo[3] += t.w * h[c];
           }
         } else {
 #pragma unroll
-          for (int c = 0; c < C; ++c) hb[c] = v[c][pp];
+          for (int c = 0; c < C; ++c)  // one TMEM column per load keeps the live set small; the C loads pipeline
+            asm volatile("tcgen05.ld.sync.aligned.32x32b.x1.b32 {%0}, [%1];" : "=f"(hb[c]) : "r"(t_acc + c * kP + pp) : "memory");
+          tc::tmem_ld_wait();
         }
 #pragma unroll
         for (int c = 0; c < C; ++c) zb[c] = 0.f;
         jet_bwd_t<ACT, NF, NS, true>(z, hb, zb);
-        if (!unit_ok) {
-#pragma unroll
-          for (int c = 0; c < C; ++c) zb[c] = 0.f;
-        }
         if (l == 1) g_b[0] += zb[0];
         else if (l == 2) g_b[1] += zb[0];
         else if (l == 3) g_b[2] += zb[0];
         else g_b[3] += zb[0];
         if (l == 1) {
-#pragma unroll
-          for (int d = 0; d < 4; ++d) g_w1[d] += zb[0] * x[d];
+          const float4 xv = *reinterpret_cast<const float4*>(sXc + p * 4);
+          g_w1[0] += zb[0] * xv.x; g_w1[1] += zb[0] * xv.y; g_w1[2] += zb[0] * xv.z; g_w1[3] += zb[0] * xv.w;
 #pragma unroll
           for (int i = 0; i < NF; ++i) {
             const int d = net.first_in[i];
@@ -369,29 +436,44 @@ __global__ void __launch_bounds__(128 * G, 1) wide_fused_kernel(WNet net, const 
             else g_w1[3] += zb[1 + i];
           }
         } else {
-          // operands of the next two GEMMs
-          float zq[C], hp[C];
-          if (l - 1 >= 2) {
-#pragma unroll
-            for (int c = 0; c < C; ++c) zq[c] = zp[c][pp];
-          } else {
-            layer1(x, zq);
-          }
-          jet_fwd_t<ACT, NF, NS, true>(zq, hp);
 #pragma unroll
           for (int c = 0; c < C; ++c) {
-            const int q = c * kP + p;
-            const float zt = tc::to_tf32(zb[c]);
-            if (j < H8) sx_at(q) = zt;
-            szt_at(q) = zt;
-            if (j < N2) sht_at(q) = unit_ok ? tc::to_tf32(hp[c]) : 0.f;
+            zq[c][pp] = tf32r(zb[c]);
+            if (k_ok) sx_t[(c * kP + pp) * 4] = zq[c][pp];
           }
         }
       }
       if (l >= 2) {
+#pragma unroll
+        for (int c = 0; c < C; ++c)
+          *reinterpret_cast<float4*>(szt_t + c * 4 * 129 * 4) = make_float4(zq[c][0], zq[c][1], zq[c][2], zq[c][3]);
+        if (!fa.dbl && l < L) {  // single sHt buffer: h_{l-1} now (the GEMMs of step l + 1 have completed)
+          float hq[C][4];
+#pragma unroll
+          for (int pp = 0; pp < 4; ++pp) {
+            float z[C], h[C];
+            load_z(l - 1, pp, z);
+            jet_fwd_t<ACT, NF, NS, true>(z, h);
+#pragma unroll
+            for (int c = 0; c < C; ++c) hq[c][pp] = tf32r(h[c]);
+          }
+          store_ht(sm + lay.sHt, hq);
+        }
         tc::tc_fence_before();
-        last_weights = (l == 2) && (tile + gridDim.x >= n_tiles);  // nothing left to fetch after this GEMM
-        run_mma(true, l, !last_weights);
+        issue_mma(true, l, sm + (buf ? lay.sHt2 : lay.sHt));
+        if (fa.dbl && l >= 3) {  // h_{l-2}, the dW operand of the NEXT step, in the shadow of this step's GEMMs
+          float hq[C][4];
+#pragma unroll
+          for (int pp = 0; pp < 4; ++pp) {
+            float z[C], h[C];
+            load_z(l - 2, pp, z);
+            jet_fwd_t<ACT, NF, NS, true>(z, h);
+#pragma unroll
+            for (int c = 0; c < C; ++c) hq[c][pp] = tf32r(h[c]);
+          }
+          buf ^= 1;
+          store_ht(sm + (buf ? lay.sHt2 : lay.sHt), hq);
+        }
       }
     }
     first_tile = false;
@@ -419,7 +501,7 @@ __global__ void __launch_bounds__(128 * G, 1) wide_fused_kernel(WNet net, const 
     }
   }
   // the G point groups of a unit: add through shared memory, group 0 writes
-  float* red = sX;  // free now: (G - 1) * 12 * 128 floats of scratch for the final reductions
+  float* red = sW;  // free now (no copy in flight): (G - 1) * 12 * 128 floats of scratch for the final reductions
   float acc[13] = {g_w1[0], g_w1[1], g_w1[2], g_w1[3], g_b[0], g_b[1], g_b[2], g_b[3], g_wo[0], g_wo[1], g_wo[2], g_wo[3], 0.f};
   __syncthreads();
   if (grp > 0) {
@@ -462,12 +544,12 @@ __global__ void __launch_bounds__(128 * G, 1) wide_fused_kernel(WNet net, const 
 
 }  // namespace
 
-// W (row-major [H][H]) -> canonical padded K-major tile [Kq][129][4], TF32-rounded, zero padded;
+// W (row-major [H][H]) -> K-major canonical tile [Kq][128][4], TF32-rounded, zero padded;
 // transpose != 0 stores W^T (rows = input units of the layer, K = its output units)
 __global__ void prep_weights_kernel(const float* __restrict__ W, int H, int Kq, float* __restrict__ out, int transpose) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= Kq * 129 * 4) return;
-  const int e = i & 3, row = (i >> 2) % 129, kq = (i >> 2) / 129;
+  if (i >= Kq * 128 * 4) return;
+  const int e = i & 3, row = (i >> 2) & 127, kq = i >> 9;
   const int k = kq * 4 + e;
   float v = 0.f;
   if (row < H && k < H) v = tc::to_tf32(transpose ? W[(size_t)k * H + row] : W[(size_t)row * H + k]);
@@ -475,7 +557,7 @@ __global__ void prep_weights_kernel(const float* __restrict__ W, int H, int Kq, 
 }
 
 int fused_wide_prep(const WNet& n, float* wprep, cudaStream_t st) {
-  const int Kq = ((n.H + 7) & ~7) / 4, tile = Kq * 129 * 4;
+  const int Kq = ((n.H + 7) & ~7) / 4, tile = Kq * 128 * 4;
   for (int l = 2; l <= n.L; ++l)
     for (int dir = 0; dir < 2; ++dir) {
       prep_weights_kernel<<<(tile + 255) / 256, 256, 0, st>>>(n.W[l - 1], n.H, Kq, wprep + (size_t)(2 * (l - 2) + dir) * tile, dir);
@@ -484,14 +566,18 @@ int fused_wide_prep(const WNet& n, float* wprep, cudaStream_t st) {
   return (int)cudaGetLastError();
 }
 
-int64_t fused_wide_wprep_floats(const WNet& n) { return (int64_t)2 * (n.L - 1) * (((n.H + 7) & ~7) / 4) * 129 * 4; }
+int64_t fused_wide_wprep_floats(const WNet& n) { return (int64_t)2 * (n.L - 1) * (((n.H + 7) & ~7) / 4) * 128 * 4; }
+
+static bool fused_fits(const WNet& n, bool dbl) {
+  const int N = n.C * kP;
+  const FusedSmem lay = fused_smem(n.H, n.C, dbl);
+  (void)N;
+  return (size_t)lay.total * 4 <= 226 * 1024 && 3 * 12 * 128 <= (((n.H + 7) & ~7) / 4) * 128 * 4;
+}
 
 bool fused_wide_supported(const WNet& n) {
   if (n.precision != 1 || n.H > 128 || n.L < 2 || n.L > kMaxHid || n.n_in > 4) return false;
-  const int H8 = (n.H + 7) & ~7, Kq = H8 / 4, N = n.C * kP, N2 = (n.H + 15) & ~15;
-  const size_t floats = (size_t)Kq * 129 * 4 + (size_t)Kq * (N + 1) * 4 + (size_t)(N / 4) * 129 * 4 +
-                        (size_t)(N / 4) * (N2 + 1) * 4 + 2 * N * 4 + kP * 4 + 4 * 128 + kP * PINN_MAX_EQ;
-  return floats * 4 <= 225 * 1024 && 3 * 12 * 128 <= Kq * (N + 1) * 4;
+  return fused_fits(n, false);
 }
 
 int64_t fused_wide_stash_floats(const WNet& n) { return (int64_t)kBlocks * (n.L - 1) * n.C * kP * 128; }
@@ -513,19 +599,17 @@ int fused_wide_launch(const WNet& n, const pinn_domain* dom, float* stash, const
   fa.head_part = head_part;
   fa.n_splits = n_splits;
   if (n_splits < kBlocks) return PINN_E_UNSUPPORTED;
-  const int H8 = (n.H + 7) & ~7, Kq = H8 / 4, N = n.C * kP, N2 = (n.H + 15) & ~15;
-  const size_t smem = ((size_t)Kq * 129 * 4 + (size_t)Kq * (N + 1) * 4 + (size_t)(N / 4) * 129 * 4 +
-                       (size_t)(N / 4) * (N2 + 1) * 4 + 2 * N * 4 + kP * 4 + 4 * 128 + kP * PINN_MAX_EQ) * sizeof(float);
+  fa.dbl = fused_fits(n, true) ? 1 : 0;
+  const size_t smem = (size_t)fused_smem(n.H, n.C, fa.dbl != 0).total * sizeof(float);
   const int64_t tiles = (dom->n_points + kP - 1) / kP;
   int grid = tiles < kBlocks ? (int)tiles : kBlocks;
   if (grid < 1) return 0;
 #define CASE(NF_, NS_)                                                                                                 \
   if (n.NF == NF_ && n.NS == NS_) {                                                                                   \
-    constexpr int G_ = 4;                                                                                              \
-    cudaError_t e = cudaFuncSetAttribute((const void*)wide_fused_kernel<NF_, NS_, ACT, G_>,                            \
+    cudaError_t e = cudaFuncSetAttribute((const void*)wide_fused_kernel<NF_, NS_, ACT>,                                \
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);                      \
     if (e != cudaSuccess) return (int)e;                                                                               \
-    wide_fused_kernel<NF_, NS_, ACT, G_><<<grid, 128 * G_, smem, st>>>(n, fa);                                         \
+    wide_fused_kernel<NF_, NS_, ACT><<<grid, 512, smem, st>>>(n, fa);                                                  \
     launched = true;                                                                                                   \
   }
   bool launched = false;

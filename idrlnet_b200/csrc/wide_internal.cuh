@@ -165,13 +165,6 @@ template <int ACT>
 int fused_wide_launch(const WNet& n, const pinn_domain* dom, float* stash, const float* wt_base, float* dw_part, float* db_part,
                       float* first_part, float* head_part, int n_splits, bool loss_only, cudaStream_t st);
 
-// second generation of the on-chip kernel (wide_fused2.cu): two half-tiles in flight, warp-specialised MMA issuer
-bool fused2_wide_supported(const WNet& n);
-int fused2_wide_prep(const WNet& n, float* wprep, cudaStream_t st);
-template <int ACT>
-int fused2_wide_launch(const WNet& n, const pinn_domain* dom, float* stash, const float* wt_base, float* dw_part, float* db_part,
-                       float* first_part, float* head_part, int n_splits, bool loss_only, cudaStream_t st);
-
 // tensor-core GEMMs (wide_tc.cu)
 template <int ACT, int EPI>
 int tc_launch_rows(const WNet& n, const float* Bsrc, const float* Aw, const float* bias, float* Zio, float* Hout, int m, int Mc,

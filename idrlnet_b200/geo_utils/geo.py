@@ -19,7 +19,50 @@ from sympy import Max, Min, Symbol, cos, sin
 
 from .sympy_np import lambdify_np
 
-__all__ = ["Edge", "Geometry", "Geometry1D", "Geometry2D", "Geometry3D"]
+__all__ = ["Edge", "Geometry", "Geometry1D", "Geometry2D", "Geometry3D", "device_sampling", "set_device_sampling"]
+
+
+class _DeviceSampling:
+    """Product-path switch for SURVEY.md 8 a7 ("geometry sampling moved on-device"): while enabled and a CUDA device is
+    active, `Geometry.sample_interior` / `sample_boundary` -- the calls an unchanged example makes from its
+    `SampleDomain.sampling` -- draw their points on the GPU (Philox4x32-10 keyed by (seed, stream), counter = running
+    offset, so every call sees fresh points and every rank of a torch.distributed job its own stream) and return
+    device tensors; nothing is sampled on the host and nothing is copied.  The point STREAM differs from NumPy's
+    (statistically equivalent, tests/test_gpu_sampling.py); keep it off to reproduce a seeded reference run."""
+    enabled = False
+    seed = 0
+    offset = 0
+
+    @classmethod
+    def next_offset(cls, n: int) -> int:
+        off = cls.offset
+        cls.offset += max(int(n), 1)
+        return off
+
+    @staticmethod
+    def rank_world():
+        try:
+            import torch.distributed as dist
+            if dist.is_available() and dist.is_initialized():
+                return dist.get_rank(), dist.get_world_size()
+        except Exception:
+            pass
+        return 0, 1
+
+
+def set_device_sampling(enabled: bool = True, seed: int = 0) -> None:
+    """Switch every `sample_interior` / `sample_boundary` call to the GPU samplers (see `_DeviceSampling`);
+    `Solver(device_sampling=True)` and IDRLNET_B200_DEVICE_SAMPLING=1 call this."""
+    _DeviceSampling.enabled = bool(enabled)
+    _DeviceSampling.seed = int(seed)
+    _DeviceSampling.offset = 0
+
+
+def device_sampling() -> bool:
+    if not _DeviceSampling.enabled:
+        return False
+    from .. import DEVICE
+    return DEVICE.type == "cuda"
 
 
 def _key(k) -> str:
@@ -173,6 +216,18 @@ def _program(tree) -> List[Tuple[str, Tuple[float, ...]]]:
     return out + [(tree[0], ())]
 
 
+def _box_fills_bounds(tree, bounds: Dict) -> bool:
+    """True when the primitive ("interval" | "rect" | "box") coincides with the box it is sampled over."""
+    kind, p = tree[1], [float(v) for v in tree[2]]
+    b = [(float(lo), float(hi)) for lo, hi in bounds.values()]
+    if kind == "interval":
+        return len(b) == 1 and abs(p[0] - b[0][0]) < 1e-12 and abs(p[1] - b[0][1]) < 1e-12
+    d = len(b)
+    if (kind == "rect" and d != 2) or (kind == "box" and d != 3):
+        return False
+    return all(abs(p[i] - b[i][0]) < 1e-12 and abs(p[d + i] - b[i][1]) < 1e-12 for i in range(d))
+
+
 class Geometry:
     """A solid: `sdf` (positive inside), bounding box `bounds` and boundary `edges`."""
     edges: List[Edge] = None
@@ -289,6 +344,8 @@ class Geometry:
         return {k: v[keep[:, 0], :] for k, v in points.items()}
 
     def sample_boundary(self, density: int, sieve=None, param_ranges: Dict = None, low_discrepancy=False):
+        if device_sampling() and not low_discrepancy:
+            return self.sample_boundary_device(density, seed=_DeviceSampling.seed, offset=None, sieve=sieve, param_ranges=param_ranges)
         param_ranges = {} if param_ranges is None else param_ranges
         parts = [e.sample(density, param_ranges, low_discrepancy) for e in self.edges]
         points = {k: np.concatenate([p[k] for p in parts], axis=0) for k in parts[0]}
@@ -296,6 +353,9 @@ class Geometry:
 
     def sample_interior(self, density: int, bounds: Dict = None, sieve=None, param_ranges: Dict = None,
                         low_discrepancy=False) -> Dict[str, np.ndarray]:
+        if device_sampling() and not low_discrepancy:
+            return self.sample_interior_device(density, seed=_DeviceSampling.seed, offset=None, bounds=bounds, sieve=sieve,
+                                               param_ranges=param_ranges)
         bounds = self.bounds if bounds is None else bounds
         bounds = {_key(k): v for k, v in bounds.items()}
         param_ranges = {} if param_ranges is None else param_ranges
@@ -306,13 +366,17 @@ class Geometry:
         points["area"] = np.zeros_like(points["sdf"]) + (1.0 / density)
         return points
 
-    def sample_interior_device(self, density: int, seed: int = 0, offset: int = 0, bounds: Dict = None, sieve=None,
-                               device=None):
+    def sample_interior_device(self, density: int, seed: int = 0, offset: Optional[int] = 0, bounds: Dict = None, sieve=None,
+                               device=None, param_ranges: Dict = None):
         """`sample_interior` on the GPU.  Candidates are the Philox points of pinn_sample_box in the bounding
         box; a solid built from numeric primitives and CSG operators is evaluated and compacted by the
-        hand-written kernel (pinn_sample_csg: sdf program, ordered compaction, deterministic); anything else
-        (symbolic parameters, transformed solids, a `sieve`) falls back to the same SymPy expressions lowered
-        to torch.  Returns a dict of [n, 1] float32 device tensors (coordinates, `sdf`, `area`)."""
+        hand-written kernel (pinn_sample_csg: sdf program, ordered compaction, deterministic); a box-shaped
+        primitive sampled over its own bounding box needs no rejection at all (one launch, no host sync); anything
+        else (symbolic parameters, transformed solids, a `sieve`) falls back to the same SymPy expressions lowered
+        to torch.  `param_ranges` columns (time, design parameters: idrlnet/geo_utils/geo.py:233-240) are drawn for the
+        surviving points on their own Philox stream.  `offset=None` takes the next offset of the process-wide counter
+        (fresh points on every call); under torch.distributed the stream id carries the rank.  Returns a dict of
+        [n, 1] float32 device tensors (coordinates, parameters, `sdf`, `area`)."""
         import ctypes as C
 
         import torch
@@ -321,14 +385,51 @@ class Geometry:
         from ..torch_util import torch_lambdify
         dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
         bounds = {_key(k): v for k, v in (self.bounds if bounds is None else bounds).items()}
+        param_ranges = {} if param_ranges is None else {_key(k): v for k, v in param_ranges.items()}
         names = list(bounds)
         n = int(np.prod([hi - lo for lo, hi in bounds.values()]) * density)
+        rank, world = _DeviceSampling.rank_world()
+        if offset is None:
+            offset = _DeviceSampling.next_offset(n)
+        sid = 64 * rank  # Philox stream ids 64*rank .. 64*rank + 63 belong to this rank
         cols = [torch.empty(n, device=dev, dtype=torch.float32) for _ in names]
         lo = (C.c_float * len(names))(*[float(bounds[k][0]) for k in names])
         hi = (C.c_float * len(names))(*[float(bounds[k][1]) for k in names])
         stream = torch.cuda.current_stream(dev).cuda_stream
         lib = nv.lib()
-        if self._tree is not None and sieve is None and names == list(self.axes):
+
+        def with_params(out, m):
+            drawn = [(k, v) for k, v in param_ranges.items() if isinstance(v, tuple)]
+            for g0 in range(0, len(drawn), 4):
+                grp = drawn[g0:g0 + 4]
+                pc = [torch.empty(m, device=dev, dtype=torch.float32) for _ in grp]
+                plo = (C.c_float * len(grp))(*[float(v[0]) for _, v in grp])
+                phi = (C.c_float * len(grp))(*[float(v[1]) for _, v in grp])
+                if m:
+                    nv.check(lib.pinn_sample_box(nv.ptr_array([c.data_ptr() for c in pc]), len(grp), plo, phi, m, seed,
+                                                 sid + 32 + g0 // 4, offset, None, 0, stream))
+                for (k, _), c in zip(grp, pc):
+                    out[k] = c.reshape(-1, 1)
+            for k, v in param_ranges.items():
+                if isinstance(v, (int, float)):
+                    out[k] = torch.full((m, 1), float(v), device=dev, dtype=torch.float32)
+                elif not isinstance(v, tuple):
+                    out[k] = torch.as_tensor(np.asarray(v(m)), dtype=torch.float32, device=dev).reshape(-1, 1)
+            out["area"] = torch.full((m, 1), 1.0 / density, device=dev, dtype=torch.float32)
+            return out
+
+        tree_ok = self._tree is not None and sieve is None and names == list(self.axes)
+        if tree_ok and self._tree[0] == "prim" and self._tree[1] in ("interval", "rect", "box") and _box_fills_bounds(self._tree, bounds):
+            # the solid IS the sampling box: every candidate is interior (a coordinate exactly on a face, probability 2^-24
+            # per draw, is kept: a null set) -> one launch, the count is known on the host, no synchronisation
+            sdf = torch.empty(n, device=dev, dtype=torch.float32)
+            if n:
+                nv.check(lib.pinn_sample_box(nv.ptr_array([c.data_ptr() for c in cols]), len(names), lo, hi, n, seed, sid,
+                                             offset, sdf.data_ptr(), len(names), stream))
+            out = {k: c.reshape(-1, 1) for k, c in zip(names, cols)}
+            out["sdf"] = sdf.reshape(-1, 1)
+            return with_params(out, n)
+        if tree_ok:
             prog = _program(self._tree)
             ops = (nv.PinnShapeOp * len(prog))()
             for o, (name, params) in zip(ops, prog):
@@ -339,31 +440,32 @@ class Geometry:
             count = torch.zeros(1, device=dev, dtype=torch.int64)
             ws_bytes = lib.pinn_sample_csg_workspace_bytes(n)
             ws = torch.empty(max(ws_bytes, 1), device=dev, dtype=torch.uint8)
-            nv.check(lib.pinn_sample_csg(nv.ptr_array([c.data_ptr() for c in cols]), len(names), lo, hi, n, n, seed, 0, offset,
+            nv.check(lib.pinn_sample_csg(nv.ptr_array([c.data_ptr() for c in cols]), len(names), lo, hi, n, n, seed, sid, offset,
                                          ops, len(prog), sdf.data_ptr(), count.data_ptr(), ws.data_ptr(), ws_bytes, stream))
             m = int(count.item())
             out = {k: c[:m].reshape(-1, 1) for k, c in zip(names, cols)}
             out["sdf"] = sdf[:m].reshape(-1, 1)
-            out["area"] = torch.full_like(out["sdf"], 1.0 / density)
-            return out
-        nv.check(lib.pinn_sample_box(nv.ptr_array([c.data_ptr() for c in cols]), len(names), lo, hi, n, seed, 0,
-                                     offset, None, 0, stream))
-        pts = {k: c.reshape(-1, 1) for k, c in zip(names, cols)}
+            return with_params(out, m)
+        if n:
+            nv.check(lib.pinn_sample_box(nv.ptr_array([c.data_ptr() for c in cols]), len(names), lo, hi, n, seed, sid,
+                                         offset, None, 0, stream))
+        pts = with_params({k: c.reshape(-1, 1) for k, c in zip(names, cols)}, n)
+        area = pts.pop("area")
         if not isinstance(self.sdf, sympy.Basic):
             raise NotImplementedError("device sampling needs a symbolic sdf")
-        sdf = torch_lambdify(names, self.sdf)(**pts)
+        keys = list(pts)
+        sdf = torch_lambdify(keys, self.sdf)(**pts)
         sdf = sdf if isinstance(sdf, torch.Tensor) and sdf.shape == pts[names[0]].shape else torch.zeros_like(pts[names[0]]) + sdf
         keep = sdf > 0
         if sieve is not None:
-            keep = keep & torch_lambdify(names + ["sdf"], sieve)(**pts, sdf=sdf)
+            keep = keep & torch_lambdify(keys + ["sdf"], sieve)(**pts, sdf=sdf)
         mask = keep[:, 0]
         out = {k: v[mask] for k, v in pts.items()}
         out["sdf"] = sdf[mask]
-        out["area"] = torch.full_like(out["sdf"], 1.0 / density)
+        out["area"] = area[mask]
         return out
 
-
-    def sample_boundary_device(self, density: int, seed: int = 0, offset: int = 0, sieve=None, param_ranges: Dict = None,
+    def sample_boundary_device(self, density: int, seed: int = 0, offset: Optional[int] = 0, sieve=None, param_ranges: Dict = None,
                                device=None):
         """`sample_boundary` on the GPU: per edge, `int(density * measure)` Philox parameter draws
         (pinn_sample_box), the edge's coordinate / normal expressions and the solid's signed distance lowered
@@ -380,11 +482,15 @@ class Geometry:
         stream = torch.cuda.current_stream(dev).cuda_stream if dev.type == "cuda" else None
         lib = nv.lib()
         parts = []
+        rank, _ = _DeviceSampling.rank_world()
+        auto = offset is None
         for e_idx, edge in enumerate(self.edges):
             ranges = {**edge.ranges, **param_ranges}
             names = [_key(k) for k in ranges]
             area_fn = lambdify_np(edge.area, names)
             n = int(density * np.mean(area_fn(**_ranged_sample_quiet(100, ranges))))   # host probe of the measure only
+            if auto:
+                offset = _DeviceSampling.next_offset(n)
             params = {}
             drawn = [(k, v) for k, v in ranges.items() if isinstance(v, tuple)]
             for g0 in range(0, len(drawn), 4):  # the box sampler draws up to 4 columns per call
@@ -392,8 +498,9 @@ class Geometry:
                 cols = [torch.empty(n, device=dev, dtype=torch.float32) for _ in grp]
                 lo = (C.c_float * len(grp))(*[float(v[0]) for _, v in grp])
                 hi = (C.c_float * len(grp))(*[float(v[1]) for _, v in grp])
-                nv.check(lib.pinn_sample_box(nv.ptr_array([c.data_ptr() for c in cols]), len(grp), lo, hi, n, seed,
-                                             1 + e_idx * 16 + g0 // 4, offset, None, 0, stream))
+                if n:
+                    nv.check(lib.pinn_sample_box(nv.ptr_array([c.data_ptr() for c in cols]), len(grp), lo, hi, n, seed,
+                                                 (rank << 20) + 1024 + e_idx * 16 + g0 // 4, offset, None, 0, stream))
                 for (k, _), c in zip(grp, cols):
                     params[_key(k)] = c.reshape(-1, 1)
             for k, v in ranges.items():

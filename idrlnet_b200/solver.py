@@ -61,7 +61,8 @@ class Solver(Notifier, Optimizable):
                  max_iter: int = 1000, save_freq: int = 100, print_freq: int = 10, loading: bool = True,
                  init_network_dirs: Optional[List[str]] = None, opt_config: Dict = None, schedule_config: Dict = None,
                  result_dir="train_domain/results", fused: Optional[bool] = None, post_step_loss: Optional[bool] = None,
-                 precision: Optional[str] = None, shard_points: bool = True, **kwargs):
+                 precision: Optional[str] = None, shard_points: bool = True, device_sampling: Optional[bool] = None,
+                 sampling_seed: int = 0, **kwargs):
         from . import callbacks
         self.network_dir = network_dir
         self.domain_losses = {d.name: d.loss_fn for d in sample_domains}
@@ -76,6 +77,19 @@ class Solver(Notifier, Optimizable):
         # under torch.distributed every sampled domain is split [rank::world] (all ranks draw the same seeded points, as
         # an unchanged example does); shard_points=False is for callers whose samplers already return this rank's points
         self.shard_points = shard_points
+        # draw the points of every `geo.sample_interior` / `geo.sample_boundary` call on the GPU (Philox
+        # streams, rank-offset under torch.distributed: each rank draws ITS OWN points, so nothing is sharded afterwards);
+        # None -> IDRLNET_B200_DEVICE_SAMPLING; off by default because the point stream then differs from NumPy's
+        if device_sampling is None:
+            device_sampling = os.environ.get("IDRLNET_B200_DEVICE_SAMPLING", "0") not in ("0", "false", "False", "")
+        self.device_sampling = bool(device_sampling)
+        if self.device_sampling:
+            from . import DEVICE
+            if DEVICE.type != "cuda":
+                raise RuntimeError("Solver(device_sampling=True) needs a CUDA device: the samplers are CUDA kernels")
+            from .geo_utils import geo as _geo
+            _geo.set_device_sampling(True, seed=sampling_seed)
+            self.shard_points = False
         # measurement hook: {domain name: list} -> a (start, stop) CUDA-event pair around that domain's fused kernel is
         # appended at every gradient step (bench.py's roofline.kernel_ms)
         self.kernel_events: Dict[str, list] = {}

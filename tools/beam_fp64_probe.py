@@ -35,3 +35,15 @@ print({k: (v if isinstance(v, str) else float(np.float64(v))) for k, v in out.it
 for k, v in out.items():
     if k != "device":
         print(k, repr(v))
+
+# PyTorch's fused CUDA weight-norm kernel vs the composite formula, in double (suspected: the kernel takes the row norm
+# with sqrtf, i.e. in single precision, whatever the tensor dtype)
+if pkg.DEVICE.type == "cuda":
+    torch.manual_seed(0)
+    v = torch.randn(20, 20, dtype=torch.float64)
+    g = torch.rand(20, 1, dtype=torch.float64) + 0.5
+    ref = v * (g / torch.norm_except_dim(v, 2, 0))
+    fused_cuda = torch._weight_norm(v.cuda(), g.cuda(), 0).cpu()
+    comp_cuda = (v.cuda() * (g.cuda() / torch.norm_except_dim(v.cuda(), 2, 0))).cpu()
+    print("torch._weight_norm cuda float64 vs CPU composite: max rel", float(((fused_cuda - ref).abs() / ref.abs()).max()))
+    print("composite formula on cuda float64 vs CPU composite: max rel", float(((comp_cuda - ref).abs() / ref.abs()).max()))
