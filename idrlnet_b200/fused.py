@@ -99,6 +99,14 @@ class NetPack:
         if self.n_in > nv.MAX_IN or self.n_out > nv.MAX_OUT or len(self.layers) > nv.MAX_LAYERS:
             raise cp.NotFusable("net too large for the descriptors")
         self.weight_norm = [hasattr(l, "weight_g") and hasattr(l, "weight_v") for l in self.layers]
+        # Siren (idrlnet/architecture/mlp.py:79-137): hidden layer i computes sin(omega_i * (W x + b)); folded into the
+        # effective parameters the kernels read, W_eff = omega_i * W, b_eff = omega_i * b (the `sin` jets exist already)
+        self.scale = [1.0] * len(self.layers)
+        if hasattr(module, "first_omega") and hasattr(module, "omega"):
+            for i in range(self.n_hidden):
+                self.scale[i] = float(module.first_omega if i == 0 else module.omega)
+            if any(self.weight_norm):
+                raise cp.NotFusable("omega-scaled layers with weight-norm are not supported")
         if any(p.dtype != torch.float32 for l in self.layers for p in l.parameters()):
             raise cp.NotFusable("the kernels compute in FP32; a net of another dtype (e.g. an FP64 tie-breaker run) "
                                 "takes the torch path")
@@ -111,8 +119,10 @@ class NetPack:
             self.sizes += [l.out_features * l.in_features, l.out_features]
         self.n_params = sum(self.sizes)
         # effective-weight buffers for weight-norm layers (plain layers are read in place)
-        self._w_eff = [torch.empty(l.out_features, l.in_features, device=dev, dtype=torch.float32) if wn else None
-                       for l, wn in zip(self.layers, self.weight_norm)]
+        self._w_eff = [torch.empty(l.out_features, l.in_features, device=dev, dtype=torch.float32) if (wn or sc != 1.0) else None
+                       for l, wn, sc in zip(self.layers, self.weight_norm, self.scale)]
+        self._b_eff = [torch.empty(l.out_features, device=dev, dtype=torch.float32) if sc != 1.0 else None
+                       for l, sc in zip(self.layers, self.scale)]
         self._grad_wn: Dict[int, Tuple[torch.Tensor, torch.Tensor]] = {}
         self._wn_fwd = None   # (pointer key, pinn_wn_layer array) of the batched weight-norm launches
         self._wn_bwd = None
@@ -133,7 +143,7 @@ class NetPack:
             h = x
             for i, l in enumerate(self.layers):
                 W = torch._weight_norm(l.weight_v, l.weight_g, 0) if self.weight_norm[i] else l.weight
-                h = torch.nn.functional.linear(h, W, l.bias)
+                h = torch.nn.functional.linear(h, W, l.bias) * self.scale[i]
                 if i < self.n_hidden:
                     h = fn(h)
         if want.shape != h.shape or not torch.allclose(want, h, rtol=1e-4, atol=1e-5 * float(h.abs().max() + 1e-30)):
@@ -148,10 +158,31 @@ class NetPack:
 
     def effective(self, i: int) -> Tuple[torch.Tensor, torch.Tensor]:
         l = self.layers[i]
+        if self.scale[i] != 1.0:
+            return self._w_eff[i], self._b_eff[i]
         return (self._w_eff[i] if self.weight_norm[i] else l.weight.data), l.bias.data
 
+    def differentiable_effective(self) -> List[torch.Tensor]:
+        """[W_0, b_0, W_1, b_1, ...] as autograd functions of the module's own parameters (generic path)."""
+        wb = []
+        for i, l in enumerate(self.layers):
+            W = torch._weight_norm(l.weight_v, l.weight_g, 0) if self.weight_norm[i] else l.weight
+            b = l.bias
+            if self.scale[i] != 1.0:
+                W, b = W * self.scale[i], b * self.scale[i]
+            wb += [W, b]
+        return wb
+
     def refresh_effective(self) -> None:
-        """W = g * v / ||v|| for the weight-norm layers (one launch for all of them)."""
+        """W = g * v / ||v|| for the weight-norm layers (one launch for all of them); omega * (W, b) for Siren layers."""
+        scaled = [i for i, sc in enumerate(self.scale) if sc != 1.0]
+        if scaled:
+            with torch.no_grad():
+                torch._foreach_mul_  # (availability check: torch >= 1.9)
+                outs = [self._w_eff[i] for i in scaled] + [self._b_eff[i] for i in scaled]
+                srcs = [self.layers[i].weight.data for i in scaled] + [self.layers[i].bias.data for i in scaled]
+                torch._foreach_copy_(outs, srcs)
+                torch._foreach_mul_(outs, [self.scale[i] for i in scaled] * 2)
         idx = [i for i, wn in enumerate(self.weight_norm) if wn]
         if not idx:
             return
@@ -211,6 +242,9 @@ class NetPack:
             dW = flat[off:off + nW].view(l.out_features, l.in_features)
             db = flat[off + nW:off + nW + nb]
             off += nW + nb
+            if self.scale[i] != 1.0:  # d/dW = omega * d/dW_eff (in place: the flat buffer is rewritten by the next step)
+                dW.mul_(self.scale[i])
+                db.mul_(self.scale[i])
             if self.weight_norm[i]:
                 dg, dv = self._grad_wn[i]
                 _set_grad(l.weight_g, dg, accumulate)

@@ -244,12 +244,7 @@ class _JetServe:
     def evaluate(self, args) -> Dict[str, torch.Tensor]:
         from . import fused
         pack = self.pack
-        wb = []
-        for i, l in enumerate(pack.layers):
-            if pack.weight_norm[i]:
-                wb += [torch._weight_norm(l.weight_v, l.weight_g, 0), l.bias]
-            else:
-                wb += [l.weight, l.bias]
+        wb = pack.differentiable_effective()
         jets = fused.jet_mlp(self.plan, pack.act, [args[k] for k in self.node.inputs], wb, pack.precision)
         n_out = pack.n_out
         out = {}

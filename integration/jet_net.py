@@ -51,9 +51,7 @@ class JetModule(torch.nn.Module):
         if self._pack is None:
             self._pack = fused.NetPack(self.mlp, precision=self.precision)  # raises if the net is not a supported MLP on CUDA
         pack = self._pack
-        wb = []
-        for i, layer in enumerate(pack.layers):  # effective weights stay differentiable w.r.t. weight_g / weight_v
-            wb += [torch._weight_norm(layer.weight_v, layer.weight_g, 0) if pack.weight_norm[i] else layer.weight, layer.bias]
+        wb = pack.differentiable_effective()  # effective weights stay differentiable w.r.t. weight_g / weight_v (/ omega)
         cols = [x[:, i] for i in range(x.shape[1])]
         jets = fused.jet_mlp(self.plan, pack.act, cols, wb, pack.precision)  # [C * n_out, N]
         return torch.stack([jets[c * pack.n_out + o] for c, o in self.columns], dim=1)

@@ -48,18 +48,70 @@ def test_mixed_derivative_falls_back_to_autograd(tmp_path):
     assert abs(float(loss) - ref["loss"]) <= 1e-4 * abs(ref["loss"])
 
 
-def test_non_mlp_net_runs_on_torch_path(tmp_path):
+@pytest.mark.parametrize("omegas", [(30.0, 30.0), (3.0, 2.0)])
+def test_siren_runs_on_the_fused_kernels(tmp_path, omegas):
+    """SURVEY 8 f4: Siren (idrlnet/architecture/mlp.py:79-137) = sin MLP whose hidden pre-activations are scaled by omega;
+    the scale is folded into the effective parameters the kernels read, so the fused step applies.  Loss and raw
+    parameter gradients against torch autograd in FP64 on the same module."""
     rng = np.random.default_rng(1)
     pts = _points(rng, 128)
     torch.manual_seed(0)
-    net = sc.get_net_node(inputs=("x", "y"), outputs=("T",), name="siren", arch=sc.Arch.siren, seq=[2, 32, 32, 1])
+    from idrlnet_b200.architecture.core import Siren
+    mod = Siren([2, 32, 32, 1], first_omega=omegas[0], omega=omegas[1])
+    net = sc.NetNode(inputs=("x", "y"), outputs=("T",), net=mod, name="siren")
     pde = sc.DiffusionNode(T="T", D=1.0, Q=0.0, dim=2, time=False)
     s = sc.Solver(sample_domains=(_fixed_domain("dom", pts, {"diffusion_T": 1.0}),), netnodes=[net], pdes=[pde],
                   network_dir=str(tmp_path), loading=False, max_iter=3)
-    assert not s._fused_domains  # Siren scales its pre-activations: not a plain Linear stack
+    assert sorted(s._fused_domains) == ["dom"]
+    s.optimizers[0].zero_grad()
+    loss = float(s._loss_and_grads())
+    got = {k: p.grad.detach().cpu().double().numpy().copy() for k, p in mod.named_parameters()}
+    # FP64 autograd reference on a CPU copy of the module
+    import copy
+    ref = copy.deepcopy(mod).cpu().double()
+    x = torch.tensor(pts["x"], dtype=torch.float64, requires_grad=True)
+    y = torch.tensor(pts["y"], dtype=torch.float64, requires_grad=True)
+    T = ref(torch.cat([x, y], dim=1))
+    g = lambda a, b: torch.autograd.grad(a, b, torch.ones_like(a), create_graph=True)[0]
+    r = -g(g(T, x), x) - g(g(T, y), y)
+    area = torch.tensor(pts["area"], dtype=torch.float64)
+    want = torch.sum((r - 1.0) ** 2 * area)
+    want.backward()
+    assert abs(loss - float(want)) <= 2e-5 * abs(float(want)), (loss, float(want))
+    for k, p in ref.named_parameters():
+        w = p.grad.numpy()
+        err = np.max(np.abs(got[k] - w)) / max(np.max(np.abs(w)), 1e-30)
+        assert err <= 2e-4, (k, err)
     l0 = float(s.train_pipe())
     l1 = float(s.train_pipe())
     assert np.isfinite(l0) and np.isfinite(l1)
+
+
+def test_derivative_of_a_downstream_expression_keeps_the_chain_rule(tmp_path):
+    """a constraint on `flux__x`, where `flux` is an ExpressionNode built from the net output, needs the
+    chain rule THROUGH the net (idrlnet/variable.py:161-208 differentiates whatever the graph produced).  A jet-served
+    net has no autograd edge to the coordinates, so such a pipeline must keep the torch path for that net instead of
+    silently differentiating to zero."""
+    import sympy as sp
+    rng = np.random.default_rng(3)
+    pts = _points(rng, 64)
+    torch.manual_seed(0)
+    net = sc.get_net_node(inputs=("x", "y"), outputs=("u",), name="net1", arch=sc.Arch.mlp)
+    xs, u = sp.Symbol("x"), sp.Function("u")(sp.Symbol("x"), sp.Symbol("y"))
+    flux = sc.ExpressionNode(name="flux", expression=u * u + 2 * xs)
+    s = sc.Solver(sample_domains=(_fixed_domain("dom", pts, {"flux__x": 0.0}),), netnodes=[net], pdes=[flux],
+                  network_dir=str(tmp_path), loading=False, max_iter=3, post_step_loss=False)
+    assert not s._fused_domains and not s.vertex_pipelines["dom"]._jet_plans  # torch path: autograd keeps the chain
+    loss = float(s.train_pipe())
+    # train_pipe (fast mode) returned the loss at the PRE-update parameters: recompute it in FP64 with autograd
+    torch.manual_seed(0)
+    net0 = sc.get_net_node(inputs=("x", "y"), outputs=("u",), name="net1b", arch=sc.Arch.mlp).net.cpu().double()
+    x = torch.tensor(pts["x"], dtype=torch.float64, requires_grad=True)
+    y = torch.tensor(pts["y"], dtype=torch.float64)
+    uu = net0(torch.cat([x, y], dim=1))
+    fx = torch.autograd.grad(uu * uu + 2 * x, x, torch.ones_like(uu))[0]
+    want = float(torch.sum(fx ** 2 * torch.tensor(pts["area"], dtype=torch.float64)))
+    assert want > 0 and abs(loss - want) <= 1e-4 * want, (loss, want)
 
 
 def test_lbfgs_closure_on_fused_step(tmp_path):

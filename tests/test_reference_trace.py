@@ -89,7 +89,8 @@ def _run_fp64(name, tmp_path, exact_weight_norm=False):
     v * (g / ||v||) that the CPU implementation uses, which the same GPU reproduces to 3e-16) -- a float32-sized
     perturbation that this chaotic case amplifies to 2e-5 after one LBFGS outer iteration.  A tie-breaker run in FP64
     must not contain it, so on the GPU the weight-norm hook is pointed at the composite formula."""
-    import torch.nn.utils.weight_norm as wn_mod
+    import sys
+    wn_mod = sys.modules["torch.nn.utils.weight_norm"]  # (the attribute of that name on torch.nn.utils is the function)
     real = wn_mod._weight_norm
     if exact_weight_norm:
         wn_mod._weight_norm = lambda v, g, dim=0: v * (g / torch.norm_except_dim(v, 2, dim))
