@@ -416,6 +416,68 @@ class OursRun:
         torch.cuda.empty_cache()
 
 
+def sampled_leg(device, world, steps, warmup):
+    """SURVEY.md 8 a7 end to end: the Burgers example AS WRITTEN (examples/burgers_equation/burgers_equation.py:7-45, its
+    densities raised to the benchmark's 2^20 + 10240 + 10240 points) under `Solver(device_sampling=True)`: every step draws
+    fresh points with the Philox kernels on the GPU (rank-offset streams under torchrun) -- no host sampling, no H2D copy --
+    then runs the fused step.  Returns whole-job points/s."""
+    import sympy as sp
+    import idrlnet_b200.shortcut as sc
+    from idrlnet_b200.geo_utils import geo as geo_mod
+    x, t = sp.Symbol("x"), sp.Symbol("t")
+    time_range = {t: (0, 1)}
+    line = sc.Line1D(-1.0, 1.0)
+    geo_mod.set_device_sampling(True, seed=1234)
+
+    @sc.datanode(name="burgers_equation")
+    def interior_domain():
+        return line.sample_interior(1 << 19, bounds={x: (-1.0, 1.0)}, param_ranges=time_range), {"burgers_u": 0}
+
+    @sc.datanode(name="t_boundary")
+    def init_domain():
+        return line.sample_interior(5120, param_ranges={t: 0.0}), sc.Variables({"u": -sp.sin(math.pi * x)})
+
+    @sc.datanode(name="x_boundary")
+    def boundary_domain():
+        return line.sample_boundary(5120, param_ranges=time_range), sc.Variables({"u": 0})
+
+    torch.manual_seed(0)
+    net = sc.get_net_node(inputs=("x", "t"), outputs=("u",), name="net1", arch=sc.Arch.mlp)
+    solver = sc.Solver(sample_domains=(interior_domain(), init_domain(), boundary_domain()), netnodes=[net],
+                       pdes=[sc.BurgersNode(u="u", v=wl.NU)], max_iter=10 ** 9, loading=False,
+                       network_dir=tempfile.mkdtemp(prefix="bench_sampled_"), post_step_loss=False, device_sampling=True,
+                       sampling_seed=1234, opt_config=dict(optimizer="Adam", lr=1e-3, fused=True))
+    try:
+        assert len(solver._fused_domains) == 3
+        pts = sum(int(v["x"].shape[0]) for v in solver.sample_variables_from_domains().values())
+
+        def sync_all():
+            torch.cuda.synchronize()
+            if world > 1:
+                torch.distributed.barrier()
+                torch.cuda.synchronize()
+        for _ in range(warmup):
+            solver.train_pipe()
+        sync_all()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            loss = solver.train_pipe()
+        host_ms = (time.perf_counter() - t0) * 1e3 / steps
+        e1.record()
+        sync_all()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=device)
+        if world > 1:
+            torch.distributed.all_reduce(ms, op=torch.distributed.ReduceOp.MAX)
+        return {"value": pts * world / (float(ms) / steps * 1e-3), "unit": "points/s", "ms_per_step": float(ms) / steps,
+                "host_ms_per_step": host_ms, "points_per_step_per_gpu": pts, "final_loss": float(loss),
+                "what": "examples/burgers_equation as written under Solver(device_sampling=True): points drawn on the GPU every "
+                        "step (Philox, rank-offset streams), h2d_bytes_per_step = 0"}
+    finally:
+        geo_mod.set_device_sampling(False)
+
+
 def roofline_of(run: OursRun, kern_ms, fp32_peak, tf32_peak, hbm_peak, hbm_src):
     cfg = run.cfg
     n_timed = run.sizes[next(d[1] for d in cfg["domains"] if d[0] == cfg["timed"])]
@@ -489,6 +551,12 @@ def run_ours(args):
     ms_per_step, kern_ms, final_loss, host_ms, launches = run.timed(args.steps, args.warmup)
     value = run.points_per_step * world / (ms_per_step * 1e-3)
     e2e_value, h2d_bytes = run.e2e(args.steps, args.warmup)
+    sampled = None
+    if args.config == "burgers" and not args.sample:
+        try:
+            sampled = sampled_leg(device, world, args.steps, args.warmup)
+        except Exception as e:  # never take the headline down
+            sampled = {"error": f"{type(e).__name__}: {e}"[:300]}
     clk = clocks.stop()
     pk, pk_src = measured_peaks()
     fp32_peak = measure_fp32_peak(device)
@@ -559,6 +627,7 @@ def run_ours(args):
                        "l2": f"{head_rot} rotating point batches ({head_rot * head_bytes / 1e6:.0f} MB > 126 MB L2)"},
             "roofline": roof, "cpu_baseline": cpu,
             "e2e": {"value": e2e_value, "unit": "points/s", "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 4},
+            "e2e_device_sampling": sampled,
             "gpu_launches": launches, "clocks": clk, "final_loss": final_loss, "host_ms_per_step": host_ms,
             "configs": configs,
         }

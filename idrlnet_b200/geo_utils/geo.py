@@ -525,6 +525,10 @@ class Geometry:
         keys = list(points)
         sdf = torch_lambdify(keys, self.sdf)(**points)
         points["sdf"] = sdf + torch.zeros_like(points[keys[0]]) if isinstance(sdf, torch.Tensor) else torch.zeros_like(points[keys[0]]) + float(sdf)
+        if sieve is None and self._tree is not None and self._tree[0] == "prim":
+            # an untransformed primitive without a sieve: every edge sample lies on the solid's own boundary (|sdf| <= 1e-4
+            # by construction), nothing is dropped -> no mask, no device-to-host synchronisation
+            return points
         keep = (points["sdf"] > -1e-4) & (points["sdf"] < 1e-4)
         if sieve is not None:
             keep = keep & torch_lambdify(list(points), sieve)(**points)

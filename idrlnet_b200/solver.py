@@ -48,6 +48,27 @@ from .variable import DomainVariables, Variables
 __all__ = ["Solver"]
 
 
+_NVTX = os.environ.get("IDRLNET_B200_NVTX", "0") not in ("0", "", "false", "False")
+
+
+class _Range:
+    """NVTX range around a phase of the step (IDRLNET_B200_NVTX=1; shows up in nsys / ncu --nvtx timelines):
+    `sample`, `fused_step`, `generic_graph`, `all_reduce`, `optimizer`, `post_step_loss`."""
+    __slots__ = ("name",)
+
+    def __init__(self, name: str):
+        self.name = name
+
+    def __enter__(self):
+        if _NVTX and torch.cuda.is_available():
+            torch.cuda.nvtx.range_push(self.name)
+
+    def __exit__(self, *exc):
+        if _NVTX and torch.cuda.is_available():
+            torch.cuda.nvtx.range_pop()
+        return False
+
+
 def _dist():
     d = torch.distributed
     if d.is_available() and d.is_initialized() and d.get_world_size() > 1:
@@ -294,9 +315,11 @@ class Solver(Notifier, Optimizable):
             else:
                 opt.zero_grad()
                 loss = self._loss_and_grads()
-                opt.step()
+                with _Range("optimizer"):
+                    opt.step()
         if self.post_step_loss:
-            loss = self._loss_and_grads(grads=False)  # idrlnet/solver.py:341-344
+            with _Range("post_step_loss"):
+                loss = self._loss_and_grads(grads=False)  # idrlnet/solver.py:341-344
         self.global_step += 1
         for scheduler in self.schedulers:
             scheduler.step(self.global_step)
@@ -312,17 +335,19 @@ class Solver(Notifier, Optimizable):
                                  for k, v in var.items()}) for name, var in samples.items()}
 
     def _loss_and_grads(self, grads: bool = True) -> torch.Tensor:
-        samples = self._shard(self.sample_variables_from_domains())
-        in_var, true_out, lambda_out = self.generate_in_out_dict(samples)
+        with _Range("sample"):
+            samples = self._shard(self.sample_variables_from_domains())
+            in_var, true_out, lambda_out = self.generate_in_out_dict(samples)
         fused_names = [n for n in self._fused_domains if len(true_out[n]) > 0]
         generic = {n: idx for n, idx in self.outvar_dict_index.items() if n not in fused_names and len(true_out[n]) > 0}
         comps: Dict[str, torch.Tensor] = {}
         gen_loss = None
         # -- generic domains: graph forward + torch loss ------------------------
         if generic:
-            pred = self.forward_through_all_graph(in_var, generic)
-            comps.update(self._loss_components(in_var, pred, {n: true_out[n] for n in generic},
-                                               {n: lambda_out[n] for n in generic}))
+            with _Range("generic_graph"):
+                pred = self.forward_through_all_graph(in_var, generic)
+                comps.update(self._loss_components(in_var, pred, {n: true_out[n] for n in generic},
+                                                   {n: lambda_out[n] for n in generic}))
         # -- fused domains: one kernel per domain --------------------------------
         engines = self._bind_fused(fused_names, in_var, true_out, lambda_out)
         dist = _dist()
@@ -335,9 +360,11 @@ class Solver(Notifier, Optimizable):
                         self.kernel_events[fd.name].append(ev)
                         timed = (i, ev[0], ev[1])
                         break
-            eng.launch(loss_only=not grads, timed=timed)  # the post-update re-evaluation needs no reverse pass
+            with _Range("fused_step"):
+                eng.launch(loss_only=not grads, timed=timed)  # the post-update re-evaluation needs no reverse pass
             if dist is not None:
-                dist.all_reduce(eng.flat if grads else eng.losses)
+                with _Range("all_reduce"):
+                    dist.all_reduce(eng.flat if grads else eng.losses)
             for fd, l in zip(eng.domains, eng.losses):
                 comps[f"{fd.name}_loss"] = l
         ordered = {f"{d.name}_loss": comps[f"{d.name}_loss"] for d in self.sample_domains if f"{d.name}_loss" in comps}

@@ -78,9 +78,13 @@ def test_siren_runs_on_the_fused_kernels(tmp_path, omegas):
     want = torch.sum((r - 1.0) ** 2 * area)
     want.backward()
     assert abs(loss - float(want)) <= 2e-5 * abs(float(want)), (loss, float(want))
+    scale = max(float(p.grad.abs().max()) for p in ref.parameters() if p.grad is not None)
     for k, p in ref.named_parameters():
+        if p.grad is None:  # output bias: only derivatives of T enter the residual -> exact zeros here
+            assert np.max(np.abs(got[k])) == 0.0, k
+            continue
         w = p.grad.numpy()
-        err = np.max(np.abs(got[k] - w)) / max(np.max(np.abs(w)), 1e-30)
+        err = np.max(np.abs(got[k] - w)) / max(np.max(np.abs(w)), 1e-3 * scale)
         assert err <= 2e-4, (k, err)
     l0 = float(s.train_pipe())
     l1 = float(s.train_pipe())
