@@ -181,3 +181,128 @@ int csg_sample(float* const* columns, int n_dims, const float* lo, const float* 
 }
 
 }  // namespace pinn
+
+// ---------------------------------------------------------------------------------------------------------
+// Expression programs: the parametric boundary pieces of a solid (idrlnet/geo_utils/geo.py:38-108 `Edge`: coordinates,
+// normals and the measure as SymPy functions of the edge parameters) and symbolic signed distances, evaluated on the
+// device.  The host compiles every SymPy expression once into a postfix program over
+//   variables = the Philox-drawn parameters of the point (edge parameter(s), time / design-parameter ranges)
+// and one launch draws the parameters of `n` points and writes every output column (replaces the NumPy lambdify +
+// per-key H2D copy of `Edge.sample`, idrlnet/geo_utils/geo.py:80-108).
+namespace pinn {
+namespace {
+
+struct ExprArgs {
+  float* out[PINN_EXPR_MAX_OUT];
+  int32_t begin[PINN_EXPR_MAX_OUT + 1];
+  float lo[PINN_EXPR_MAX_VARS], hi[PINN_EXPR_MAX_VARS];
+  int32_t n_out, n_vars;
+  int64_t n;
+  uint64_t seed, stream_id, offset;
+  pinn_expr_op ops[PINN_EXPR_MAX_OPS];
+};
+
+__global__ void __launch_bounds__(kBlock) expr_program_kernel(const __grid_constant__ ExprArgs a) {
+  const int64_t i = (int64_t)blockIdx.x * kBlock + threadIdx.x;
+  if (i >= a.n) return;
+  float var[PINN_EXPR_MAX_VARS];
+#pragma unroll
+  for (int g = 0; g < PINN_EXPR_MAX_VARS / 4; ++g) {
+    if (g * 4 < a.n_vars) {
+      uint32_t r[4];
+      philox4x32_10(a.seed, a.stream_id + (uint64_t)g, a.offset + (uint64_t)i, r);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) var[g * 4 + k] = box_point(r[k], a.lo[g * 4 + k], a.hi[g * 4 + k]);
+    }
+  }
+  for (int o = 0; o < a.n_out; ++o) {
+    float st[PINN_EXPR_STACK];
+    int sp = 0;
+    for (int pc = a.begin[o]; pc < a.begin[o + 1]; ++pc) {
+      const pinn_expr_op op = a.ops[pc];
+      switch (op.op) {
+        case PINN_EX_CONST: st[sp++] = op.imm; break;
+        case PINN_EX_VAR: st[sp++] = var[(int)op.imm]; break;
+        case PINN_EX_ADD: --sp; st[sp - 1] += st[sp]; break;
+        case PINN_EX_SUB: --sp; st[sp - 1] -= st[sp]; break;
+        case PINN_EX_MUL: --sp; st[sp - 1] *= st[sp]; break;
+        case PINN_EX_DIV: --sp; st[sp - 1] /= st[sp]; break;
+        case PINN_EX_MIN: --sp; st[sp - 1] = fminf(st[sp - 1], st[sp]); break;
+        case PINN_EX_MAX: --sp; st[sp - 1] = fmaxf(st[sp - 1], st[sp]); break;
+        case PINN_EX_POW: --sp; st[sp - 1] = powf(st[sp - 1], st[sp]); break;
+        case PINN_EX_NEG: st[sp - 1] = -st[sp - 1]; break;
+        case PINN_EX_ABS: st[sp - 1] = fabsf(st[sp - 1]); break;
+        case PINN_EX_SQRT: st[sp - 1] = sqrtf(st[sp - 1]); break;
+        case PINN_EX_SIN: st[sp - 1] = sinf(st[sp - 1]); break;
+        case PINN_EX_COS: st[sp - 1] = cosf(st[sp - 1]); break;
+        case PINN_EX_TAN: st[sp - 1] = tanf(st[sp - 1]); break;
+        case PINN_EX_EXP: st[sp - 1] = expf(st[sp - 1]); break;
+        case PINN_EX_LOG: st[sp - 1] = logf(st[sp - 1]); break;
+        case PINN_EX_TANH: st[sp - 1] = tanhf(st[sp - 1]); break;
+        case PINN_EX_SIGN: st[sp - 1] = (st[sp - 1] > 0.f) ? 1.f : ((st[sp - 1] < 0.f) ? -1.f : 0.f); break;
+        case PINN_EX_HEAVISIDE: st[sp - 1] = (st[sp - 1] > 0.f) ? 1.f : ((st[sp - 1] < 0.f) ? 0.f : 0.5f); break;
+        case PINN_EX_SQUARE: st[sp - 1] *= st[sp - 1]; break;
+        case PINN_EX_RCP: st[sp - 1] = 1.0f / st[sp - 1]; break;
+        case PINN_EX_ATAN2: --sp; st[sp - 1] = atan2f(st[sp - 1], st[sp]); break;
+        case PINN_EX_SCALE: st[sp - 1] *= op.imm; break;    // * immediate
+        case PINN_EX_OFFSET: st[sp - 1] += op.imm; break;   // + immediate
+        case PINN_EX_ASIN: st[sp - 1] = asinf(fminf(fmaxf(st[sp - 1], -1.f), 1.f)); break;
+        case PINN_EX_ACOS: st[sp - 1] = acosf(fminf(fmaxf(st[sp - 1], -1.f), 1.f)); break;
+        case PINN_EX_ATAN: st[sp - 1] = atanf(st[sp - 1]); break;
+        case PINN_EX_SINH: st[sp - 1] = sinhf(st[sp - 1]); break;
+        case PINN_EX_COSH: st[sp - 1] = coshf(st[sp - 1]); break;
+        default: break;
+      }
+    }
+    a.out[o][i] = sp > 0 ? st[0] : 0.f;
+  }
+}
+
+}  // namespace
+}  // namespace pinn
+
+extern "C" int pinn_sample_program(float* const* out, int32_t n_out, const pinn_expr_op* ops, const int32_t* begin,
+                                   const float* lo, const float* hi, int32_t n_vars, int64_t n_points, uint64_t seed,
+                                   uint64_t stream_id, uint64_t offset, void* stream) {
+  using namespace pinn;
+  if (!out || !ops || !begin || n_out < 1 || n_out > PINN_EXPR_MAX_OUT || n_vars < 0 || n_vars > PINN_EXPR_MAX_VARS || n_points < 0 ||
+      (n_vars > 0 && (!lo || !hi)))
+    return PINN_E_INVALID;
+  if (begin[0] != 0 || begin[n_out] > PINN_EXPR_MAX_OPS) return PINN_E_INVALID;
+  ExprArgs a;
+  memset(&a, 0, sizeof(a));
+  for (int o = 0; o < n_out; ++o) {
+    if (!out[o] || begin[o + 1] < begin[o]) return PINN_E_INVALID;
+    a.out[o] = out[o];
+  }
+  for (int o = 0; o <= n_out; ++o) a.begin[o] = begin[o];
+  // validate the programs on the host: stack depth, variable indices, op codes
+  for (int o = 0; o < n_out; ++o) {
+    int sp = 0;
+    for (int pc = begin[o]; pc < begin[o + 1]; ++pc) {
+      const int op = ops[pc].op;
+      int pop = 0, push = 0;
+      if (op == PINN_EX_CONST) push = 1;
+      else if (op == PINN_EX_VAR) {
+        push = 1;
+        if ((int)ops[pc].imm < 0 || (int)ops[pc].imm >= n_vars) return PINN_E_INVALID;
+      } else if (op == PINN_EX_ADD || op == PINN_EX_SUB || op == PINN_EX_MUL || op == PINN_EX_DIV || op == PINN_EX_MIN ||
+                 op == PINN_EX_MAX || op == PINN_EX_POW || op == PINN_EX_ATAN2) { pop = 2; push = 1; }
+      else if (op >= PINN_EX_NEG && op <= PINN_EX_COSH) { pop = 1; push = 1; }
+      else return PINN_E_INVALID;
+      if (sp < pop) return PINN_E_INVALID;
+      sp += push - pop;
+      if (sp > PINN_EXPR_STACK) return PINN_E_UNSUPPORTED;
+    }
+    if (sp != 1) return PINN_E_INVALID;
+    for (int pc = begin[o]; pc < begin[o + 1]; ++pc) a.ops[pc] = ops[pc];
+  }
+  for (int v = 0; v < n_vars; ++v) { a.lo[v] = lo[v]; a.hi[v] = hi[v]; }
+  a.n_out = n_out; a.n_vars = n_vars; a.n = n_points;
+  a.seed = seed; a.stream_id = stream_id; a.offset = offset;
+  if (n_points == 0) return 0;
+  const int64_t blocks = (n_points + kBlock - 1) / kBlock;
+  expr_program_kernel<<<(unsigned)blocks, kBlock, 0, (cudaStream_t)stream>>>(a);
+  count_launch(1);
+  return (int)cudaGetLastError();
+}

@@ -62,9 +62,11 @@ __host__ __device__ inline FusedSmem fused_smem(int H, int C, bool dbl) {
   return s;
 }
 
-// round-to-nearest (ties away) to TF32: what cvt.rna.tf32.f32 expands to on sm_100a minus its inf/nan test
-// (the operands here are finite activations and adjoints): 2 instructions instead of 3
-__device__ __forceinline__ float tf32r(float x) { return __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xffffe000u); }
+// round-to-nearest (ties away) to TF32: cvt.rna.tf32.f32 expands on sm_100a to {inf/nan test, add 0x1000 to the bit
+// pattern, mask the 13 low mantissa bits}; the operands here are finite and kind::tf32 reads only the upper 19 bits of a
+// 32-bit operand, so the add alone gives the tensor core the same multiplicand: 1 instruction instead of 3 (the parity
+// tests of tests/test_gpu_wide_tc.py bound the result either way)
+__device__ __forceinline__ float tf32r(float x) { return __uint_as_float(__float_as_uint(x) + 0x1000u); }
 
 // 512 threads: thread (unit j = TMEM lane, point group g) handles the four points 4g .. 4g+3 of the tile.
 template <int NF, int NS, int ACT>
@@ -484,13 +486,29 @@ __global__ void __launch_bounds__(512, 1) wide_fused_kernel(WNet net, const __gr
   const bool any_tile = blockIdx.x < n_tiles;
   if (any_tile && !fa.loss_only) {
     tc::tc_fence_after();
+    // TMEM row = unit j (one per lane), 16 columns k per load; a 32 x 17 shared-memory tile per warp turns the
+    // read-modify-write of dw_part[j][k] into row segments of 16 consecutive floats (two rows per warp access)
+    // instead of 32 scattered words (the flush was 7 % of the kernel's stall samples, half of a boundary launch)
+    float* tile = sW + warp * (32 * 17);  // sW and sX (adjacent) are free now; tiny nets that cannot hold 16 tiles write directly
+    const bool use_tile = 16 * 32 * 17 <= Kq * 128 * 4 + Kq * (N + 1) * 4;
     for (int l = 2; l <= L; ++l) {
       float* out = fa.dw_part + ((size_t)(l - 2) * fa.n_splits + blockIdx.x) * H * H;
       for (int g = grp; g < N2 / 16; g += G) {
         float v[16];
         tc::tmem_ld16(tmem + 128 + (uint32_t)(l - 2) * 128 + lane_base + g * 16, v);
         tc::tmem_ld_wait();
-        if (unit_ok) {
+        if (use_tile) {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) tile[lane * 17 + i] = v[i];
+          __syncwarp();
+          const int k = g * 16 + (lane & 15), jb = (warp & 3) * 32;
+#pragma unroll
+          for (int r = 0; r < 32; r += 2) {
+            const int rr = r + (lane >> 4), jj = jb + rr;
+            if (jj < H && k < H) out[(size_t)jj * H + k] += tile[rr * 17 + (lane & 15)];
+          }
+          __syncwarp();
+        } else if (unit_ok) {
 #pragma unroll
           for (int i = 0; i < 16; ++i) {
             const int k = g * 16 + i;

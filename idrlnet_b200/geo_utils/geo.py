@@ -216,6 +216,22 @@ def _program(tree) -> List[Tuple[str, Tuple[float, ...]]]:
     return out + [(tree[0], ())]
 
 
+_CONST_COLUMNS: Dict = {}
+
+
+def _const_column(m: int, value: float, dev):
+    """[m, 1] float32 device column filled with `value`, created once per (m, value, device): constant parameter and
+    `area` columns are read-only downstream, so every sampling call can hand out the same tensor (no fill launch)."""
+    import torch
+    key = (int(m), float(value), str(dev))
+    col = _CONST_COLUMNS.get(key)
+    if col is None:
+        if len(_CONST_COLUMNS) > 64:
+            _CONST_COLUMNS.clear()
+        col = _CONST_COLUMNS[key] = torch.full((m, 1), float(value), device=dev, dtype=torch.float32)
+    return col
+
+
 def _box_fills_bounds(tree, bounds: Dict) -> bool:
     """True when the primitive ("interval" | "rect" | "box") coincides with the box it is sampled over."""
     kind, p = tree[1], [float(v) for v in tree[2]]
@@ -412,10 +428,10 @@ class Geometry:
                     out[k] = c.reshape(-1, 1)
             for k, v in param_ranges.items():
                 if isinstance(v, (int, float)):
-                    out[k] = torch.full((m, 1), float(v), device=dev, dtype=torch.float32)
+                    out[k] = _const_column(m, float(v), dev)
                 elif not isinstance(v, tuple):
                     out[k] = torch.as_tensor(np.asarray(v(m)), dtype=torch.float32, device=dev).reshape(-1, 1)
-            out["area"] = torch.full((m, 1), 1.0 / density, device=dev, dtype=torch.float32)
+            out["area"] = _const_column(m, 1.0 / density, dev)
             return out
 
         tree_ok = self._tree is not None and sieve is None and names == list(self.axes)
@@ -481,9 +497,13 @@ class Geometry:
         param_ranges = {} if param_ranges is None else param_ranges
         stream = torch.cuda.current_stream(dev).cuda_stream if dev.type == "cuda" else None
         lib = nv.lib()
-        parts = []
         rank, _ = _DeviceSampling.rank_world()
         auto = offset is None
+        if dev.type == "cuda":
+            fast = self._sample_boundary_programs(density, seed, offset, sieve, param_ranges, dev, stream, rank)
+            if fast is not None:
+                return fast
+        parts = []
         for e_idx, edge in enumerate(self.edges):
             ranges = {**edge.ranges, **param_ranges}
             names = [_key(k) for k in ranges]
@@ -534,6 +554,92 @@ class Geometry:
             keep = keep & torch_lambdify(list(points), sieve)(**points)
         mask = keep[:, 0]
         return {k: v[mask] for k, v in points.items()}
+
+
+    # -- boundary sampling by compiled edge programs (csrc/geometry.cu: pinn_sample_program) ----------------
+    def _edge_programs(self, density: int, param_ranges: Dict):
+        """Per edge: (n, packed programs, parameter bounds) -- compiled once per (solid state, density, ranges) and cached.
+        Output order = the keys `sample_boundary` returns: area, edge functions, parameter columns, sdf."""
+        from . import expr_prog as xp
+        # identity of the (immutable) expression objects: a moved / rotated / scaled solid holds new ones.  The entry pins
+        # the objects so that an id cannot be recycled while it is a key.
+        key = (density, tuple((_key(k), v if not callable(v) else id(v)) for k, v in param_ranges.items()), id(self.sdf),
+               tuple(id(f) for e in self.edges for f in e.functions.values()))
+        cache = self.__dict__.setdefault("_prog_cache", {})
+        if key in cache:
+            return cache[key][0]
+        pins = (self.sdf, [f for e in self.edges for f in e.functions.values()])
+        entry = None
+        try:
+            if not isinstance(self.sdf, sympy.Basic):
+                raise xp.Unsupported("callable sdf")
+            plan, keys = [], None
+            for edge in self.edges:
+                ranges = {**edge.ranges, **param_ranges}
+                names = [_key(k) for k in ranges]
+                drawn = [(_key(k), v) for k, v in ranges.items() if isinstance(v, tuple)]
+                consts = {_key(k): float(v) for k, v in ranges.items() if isinstance(v, (int, float))}
+                if any(callable(v) for v in ranges.values()) or len(drawn) > nv_expr_max_vars():
+                    raise xp.Unsupported("callable range / too many parameters")
+                var_index = {k: i for i, (k, _) in enumerate(drawn)}
+                area_fn = lambdify_np(edge.area, names)
+                n = int(density * np.mean(area_fn(**_ranged_sample_quiet(100, ranges))))   # host probe of the measure only
+                out_keys = ["area"] + list(edge.functions) + [_key(k) for k in param_ranges] + ["sdf"]
+                if keys is None:
+                    keys = out_keys
+                elif keys != out_keys:
+                    raise xp.Unsupported("edges with different columns")
+                progs = [xp.compile_expr(sympy.sympify(edge.area) / max(n, 1), var_index, consts)]
+                progs += [xp.compile_expr(fn, var_index, consts) for fn in edge.functions.values()]
+                progs += [xp.compile_expr(Symbol(_key(k)), var_index, consts) for k in param_ranges]
+                on_edge = {Symbol(a): sympy.sympify(edge.functions[a]) for a in edge.axes}
+                progs.append(xp.compile_expr(self.sdf.subs(on_edge, simultaneous=True), var_index, consts))
+                ops, begin = xp.pack_programs(progs)
+                import ctypes as C
+                lo = (C.c_float * max(len(drawn), 1))(*[float(v[0]) for _, v in drawn])
+                hi = (C.c_float * max(len(drawn), 1))(*[float(v[1]) for _, v in drawn])
+                plan.append((n, ops, begin, lo, hi, len(drawn)))
+            entry = (keys, plan)
+        except xp.Unsupported:
+            entry = None
+        cache[key] = (entry, pins)
+        return entry
+
+    def _sample_boundary_programs(self, density, seed, offset, sieve, param_ranges, dev, stream, rank):
+        """One launch per edge writes every column of its samples straight into the concatenated output; None when an
+        expression has no device op (the caller then lowers the same SymPy expressions to torch)."""
+        import torch
+
+        from .. import native as nv
+        from ..torch_util import torch_lambdify
+        entry = self._edge_programs(density, param_ranges)
+        if entry is None:
+            return None
+        keys, plan = entry
+        total = sum(p[0] for p in plan)
+        buf = torch.empty((len(keys), max(total, 1)), device=dev, dtype=torch.float32)
+        base, row, start = buf.data_ptr(), buf.stride(0) * 4, 0
+        lib = nv.lib()
+        for e_idx, (n, ops, begin, lo, hi, n_vars) in enumerate(plan):
+            off = _DeviceSampling.next_offset(n) if offset is None else offset
+            if n:
+                ptrs = nv.ptr_array([base + r * row + start * 4 for r in range(len(keys))])
+                nv.check(lib.pinn_sample_program(ptrs, len(keys), ops, begin, lo, hi, n_vars, n, seed,
+                                                 (rank << 20) + 1024 + e_idx * 16, off, stream))
+            start += n
+        points = {k: buf[i, :total].unsqueeze(1) for i, k in enumerate(keys)}
+        if sieve is None and self._tree is not None and self._tree[0] == "prim":
+            return points  # every edge sample of an untransformed primitive lies on its own boundary: nothing to drop, no sync
+        keep = (points["sdf"] > -1e-4) & (points["sdf"] < 1e-4)
+        if sieve is not None:
+            keep = keep & torch_lambdify(list(points), sieve)(**points)
+        mask = keep[:, 0]
+        return {k: v[mask] for k, v in points.items()}
+
+
+def nv_expr_max_vars() -> int:
+    from .. import native as nv
+    return nv.EXPR_MAX_VARS
 
 
 class Geometry1D(Geometry):

@@ -87,6 +87,16 @@ class PinnShapeOp(C.Structure):
     _fields_ = [("op", C.c_int32), ("p", C.c_float * 6)]
 
 
+class PinnExprOp(C.Structure):
+    """pinn_expr_op (include/pinn_b200.h)."""
+    _fields_ = [("op", C.c_int32), ("imm", C.c_float)]
+
+
+EXPR_MAX_OUT, EXPR_MAX_VARS, EXPR_MAX_OPS, EXPR_STACK = 12, 8, 448, 16
+EX = {"const": 0, "var": 1, "add": 2, "sub": 3, "mul": 4, "div": 5, "min": 6, "max": 7, "pow": 8, "atan2": 9, "neg": 16, "abs": 17,
+      "sqrt": 18, "sin": 19, "cos": 20, "tan": 21, "exp": 22, "log": 23, "tanh": 24, "sign": 25, "heaviside": 26, "square": 27,
+      "rcp": 28, "scale": 29, "offset": 30, "asin": 31, "acos": 32, "atan": 33, "sinh": 34, "cosh": 35}
+
 SHAPE_OPS = {"interval": 0, "rect": 1, "circle": 2, "channel2d": 3, "box": 4, "sphere": 5,
              "union": 16, "difference": 17, "intersection": 18, "complement": 19}
 
@@ -134,6 +144,8 @@ _SIGNATURES = {
     "pinn_sample_csg": (C.c_int, [C.POINTER(_fp), C.c_int32, C.POINTER(C.c_float), C.POINTER(C.c_float), C.c_int64, C.c_int64,
                                   C.c_uint64, C.c_uint64, C.c_uint64, C.POINTER(PinnShapeOp), C.c_int32, C.c_void_p, C.c_void_p,
                                   C.c_void_p, C.c_int64, C.c_void_p]),
+    "pinn_sample_program": (C.c_int, [C.POINTER(_fp), C.c_int32, C.POINTER(PinnExprOp), C.POINTER(C.c_int32), C.POINTER(C.c_float),
+                                      C.POINTER(C.c_float), C.c_int32, C.c_int64, C.c_uint64, C.c_uint64, C.c_uint64, C.c_void_p]),
     "pinn_fp32_fma_probe": (C.c_int64, [C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]),
     "pinn_fp32_fma2_probe": (C.c_int64, [C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]),
     "pinn_tf32_mma_probe": (C.c_int64, [C.c_int32, C.c_void_p, C.c_void_p]),

@@ -301,6 +301,35 @@ PINN_API int pinn_sample_csg(float* const* columns, int32_t n_dims, const float*
                     const pinn_shape_op* prog, int32_t n_ops, float* sdf, int64_t* count, void* workspace,
                     int64_t workspace_bytes, void* stream);
 
+/* ---- on-device evaluation of parametric boundary pieces and symbolic expressions ------------------------------ */
+/* Edge.sample on the device (idrlnet/geo_utils/geo.py:80-108): every point i draws `n_vars` parameters -- Philox4x32-10,
+ * stream_id + v/4, counter offset + i, the generator of pinn_sample_box -- uniformly in [lo[v], hi[v]) and evaluates
+ * `n_out` postfix programs over them (the edge's coordinate / normal / measure expressions, parameter columns, the
+ * solid's signed distance composed with the coordinates), writing out[o][i].  `ops` / `begin` are HOST arrays:
+ * program o is ops[begin[o] .. begin[o+1]).  Replaces the per-call NumPy lambdify + H2D copies of the reference. */
+#define PINN_EXPR_MAX_OUT 12
+#define PINN_EXPR_MAX_VARS 8
+#define PINN_EXPR_MAX_OPS 448
+#define PINN_EXPR_STACK 16
+enum {
+  PINN_EX_CONST = 0, /* push imm                     */
+  PINN_EX_VAR = 1,   /* push parameter (int)imm      */
+  PINN_EX_ADD = 2, PINN_EX_SUB = 3, PINN_EX_MUL = 4, PINN_EX_DIV = 5, PINN_EX_MIN = 6, PINN_EX_MAX = 7, PINN_EX_POW = 8,
+  PINN_EX_ATAN2 = 9, /* binary: a op b with b on top of the stack */
+  PINN_EX_NEG = 16, PINN_EX_ABS = 17, PINN_EX_SQRT = 18, PINN_EX_SIN = 19, PINN_EX_COS = 20, PINN_EX_TAN = 21, PINN_EX_EXP = 22,
+  PINN_EX_LOG = 23, PINN_EX_TANH = 24, PINN_EX_SIGN = 25, PINN_EX_HEAVISIDE = 26, PINN_EX_SQUARE = 27, PINN_EX_RCP = 28,
+  PINN_EX_SCALE = 29, /* top *= imm */
+  PINN_EX_OFFSET = 30, /* top += imm */
+  PINN_EX_ASIN = 31, PINN_EX_ACOS = 32, PINN_EX_ATAN = 33, PINN_EX_SINH = 34, PINN_EX_COSH = 35
+};
+typedef struct pinn_expr_op {
+  int32_t op;
+  float imm;
+} pinn_expr_op;
+PINN_API int pinn_sample_program(float* const* out, int32_t n_out, const pinn_expr_op* ops, const int32_t* begin,
+                                 const float* lo, const float* hi, int32_t n_vars, int64_t n_points, uint64_t seed,
+                                 uint64_t stream_id, uint64_t offset, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
