@@ -97,10 +97,20 @@ __global__ void __launch_bounds__(512, 1) wide_fused_kernel(WNet net, const __gr
   const bool unit_ok = j < H;               // only the final flush needs it: padded units carry exact zeros throughout
   const bool k_ok = j < H8, n2_ok = j < N2; // rows of the K = unit / K = (channel, point) operands this thread writes
 
+  // residual evaluation tables (built once): entry i of the (term, factor) list, and its count
+  __shared__ uint8_t tf_t[128], tf_f[128];
+  __shared__ int n_tf_s;
   if (tid == 0) {
     tc::mbar_init(&bar[0], 1);
     tc::mbar_init(&bar[1], 1);
     tc::fence_mbar_init();
+    int n = 0;
+    for (int t = 0; t < fa.dom.n_terms; ++t)
+      for (int f = 0; f < fa.dom.terms[t].n_fac; ++f) {
+        if (n < 128) { tf_t[n] = (uint8_t)t; tf_f[n] = (uint8_t)f; }
+        ++n;
+      }
+    n_tf_s = n;
   }
   if (warp == 0) tc::tmem_alloc(&tmem_slot, 512);
   for (int i = tid; i < 4 * 128; i += kT) {
@@ -111,6 +121,9 @@ __global__ void __launch_bounds__(512, 1) wide_fused_kernel(WNet net, const __gr
   __syncthreads();
   tc::tc_fence_after();
   const uint32_t tmem = tmem_slot;
+  const int n_tf = n_tf_s;
+  // wide residual phases (one thread per (point, term) and per (point, term, factor)) when their scratch fits into sP
+  const bool wide_res = n_tf <= 128 && (fa.dom.n_terms + n_tf) * kP <= kSl * N * 4;
   uint32_t phase = 0, wphase = 0;
   // weight tiles are consumed in a fixed cyclic order per point tile: W_2 .. W_L, W_L^T .. W_2^T
   const uint32_t wbytes = (uint32_t)(Kq * 128 * 4 * sizeof(float));
@@ -322,8 +335,24 @@ __global__ void __launch_bounds__(512, 1) wide_fused_kernel(WNet net, const __gr
       }
       __syncthreads();
     }
-    // ---- residual, loss, ybar: two short parallel phases instead of one thread per point ---------
-    // R1: thread (point p, equation e) evaluates r_e, the loss term and the seed g = f'(r - target) * w * sigma
+    // ---- residual, loss, ybar ------------------------------------------------------------------------------
+    // Four short, wide phases (the serial per-equation / per-symbol loops were 10 % of the kernel's stall samples, spent
+    // by 464 threads waiting at the barriers for 48): R1a thread (point, term) -> the monomial; R1b thread (point,
+    // equation) -> r_e, loss term, seed g_e = f'(r - target) * w * sigma; R2a thread (point, term, factor) -> g_e * d term /
+    // d factor; R2b thread (point, output symbol) -> ybar.  Summation orders (terms within an equation; equations, terms
+    // and factors within a symbol) are those of the serial evaluation of the layer-streamed path: bitwise the same sums.
+    float* const sT = sP;                                // [n_terms][kP]
+    float* const sPt = sP + fa.dom.n_terms * kP;         // [n_tf][kP]
+    if (wide_res) {
+      for (int item = tid; item < fa.dom.n_terms * kP; item += kT) {
+        const int p = item & (kP - 1), t = item >> 4;
+        const pinn_term& tm = fa.dom.terms[t];
+        float prod = tm.coef;
+        for (int f = 0; f < tm.n_fac; ++f) prod *= sym_at(tm.fac[f], p);
+        sT[item] = prod;
+      }
+      __syncthreads();
+    }
     if (tid < kP * PINN_MAX_EQ) {
       const int p = tid & (kP - 1), e = tid >> 4;
       const int64_t ng = n0 + p;
@@ -331,11 +360,15 @@ __global__ void __launch_bounds__(512, 1) wide_fused_kernel(WNet net, const __gr
       if (e < fa.dom.n_eq && ng < fa.n_points) {
         const pinn_equation& q = fa.dom.eq[e];
         float r = 0.f;
-        for (int t = q.term_begin; t < q.term_end; ++t) {
-          const pinn_term& tm = fa.dom.terms[t];
-          float prod = tm.coef;
-          for (int f = 0; f < tm.n_fac; ++f) prod *= sym_at(tm.fac[f], p);
-          r += prod;
+        if (wide_res) {
+          for (int t = q.term_begin; t < q.term_end; ++t) r += sT[t * kP + p];
+        } else {
+          for (int t = q.term_begin; t < q.term_end; ++t) {
+            const pinn_term& tm = fa.dom.terms[t];
+            float prod = tm.coef;
+            for (int f = 0; f < tm.n_fac; ++f) prod *= sym_at(tm.fac[f], p);
+            r += prod;
+          }
         }
         const float area = fa.dom.area ? fa.dom.area[ng] : fa.dom.area_const;
         const float tgt = q.target ? q.target[ng] : q.target_const;
@@ -352,27 +385,48 @@ __global__ void __launch_bounds__(512, 1) wide_fused_kernel(WNet net, const __gr
     }
     __syncthreads();
     if (fa.loss_only) continue;  // (uniform: every thread leaves together)
-    // R2: thread (point p, output symbol id) gathers ybar[id] = sum_e g_e * d r_e / d sym[id] (same e, term, factor order
-    // as the serial evaluation of the layer-streamed path)
-    for (int item = tid; item < C * 4 * kP; item += kT) {
-      const int p = item & (kP - 1), id = item >> 4;
-      float acc = 0.f;
-      for (int e = 0; e < fa.dom.n_eq; ++e) {
-        const float g = sG[e * kP + p];
-        const pinn_equation& q = fa.dom.eq[e];
-        for (int t = q.term_begin; t < q.term_end; ++t) {
-          const pinn_term& tm = fa.dom.terms[t];
-          for (int f = 0; f < tm.n_fac; ++f) {
-            if (tm.fac[f] != id) continue;
-            float prod = tm.coef * g;
-            for (int f2 = 0; f2 < tm.n_fac; ++f2)
-              if (f2 != f) prod *= sym_at(tm.fac[f2], p);
-            acc += prod;
+    if (wide_res) {
+      for (int item = tid; item < n_tf * kP; item += kT) {
+        const int p = item & (kP - 1), i = item >> 4;
+        const int t = tf_t[i], f = tf_f[i];
+        const pinn_term& tm = fa.dom.terms[t];
+        int e = 0;
+        while (e + 1 < fa.dom.n_eq && t >= fa.dom.eq[e].term_end) ++e;
+        float prod = tm.coef * sG[e * kP + p];
+        for (int f2 = 0; f2 < tm.n_fac; ++f2)
+          if (f2 != f) prod *= sym_at(tm.fac[f2], p);
+        sPt[item] = prod;
+      }
+      __syncthreads();
+      for (int item = tid; item < C * 4 * kP; item += kT) {
+        const int p = item & (kP - 1), id = item >> 4;
+        float acc = 0.f;
+        for (int i = 0; i < n_tf; ++i)
+          if (fa.dom.terms[tf_t[i]].fac[tf_f[i]] == id) acc += sPt[i * kP + p];
+        sYb[((id >> 2) * kP + p) * 4 + (id & 3)] = acc;
+        if (item < 4 * kP) g_bo_r += acc;  // value channel of output o = id: dL/d bout[o]  (item == tid here)
+      }
+    } else {
+      for (int item = tid; item < C * 4 * kP; item += kT) {
+        const int p = item & (kP - 1), id = item >> 4;
+        float acc = 0.f;
+        for (int e = 0; e < fa.dom.n_eq; ++e) {
+          const float g = sG[e * kP + p];
+          const pinn_equation& q = fa.dom.eq[e];
+          for (int t = q.term_begin; t < q.term_end; ++t) {
+            const pinn_term& tm = fa.dom.terms[t];
+            for (int f = 0; f < tm.n_fac; ++f) {
+              if (tm.fac[f] != id) continue;
+              float prod = tm.coef * g;
+              for (int f2 = 0; f2 < tm.n_fac; ++f2)
+                if (f2 != f) prod *= sym_at(tm.fac[f2], p);
+              acc += prod;
+            }
           }
         }
+        sYb[((id >> 2) * kP + p) * 4 + (id & 3)] = acc;
+        if (item < 4 * kP) g_bo_r += acc;  // value channel of output o = id: dL/d bout[o]  (item == tid here)
       }
-      sYb[((id >> 2) * kP + p) * 4 + (id & 3)] = acc;
-      if (item < 4 * kP) g_bo_r += acc;  // value channel of output o = id: dL/d bout[o]  (item == tid here)
     }
     __syncthreads();
 
