@@ -573,6 +573,8 @@ def run_ours(args):
         modes = WIDE_MODES if c["wide"] else (("", None),)
         for suffix, prec in modes:
             w, k = SECONDARY_STEPS[name]
+            if name == "ns_xl" and world > 1:
+                k = 3  # 2^26 / N points per GPU: a step takes seconds
             try:
                 r = OursRun(name, device, world, rank, precision=prec)
                 ck = ClockSampler(local).start()

@@ -13,7 +13,8 @@ fused kernels; a training step for those domains is `pinn_step_fused` +
 `pinn_step_finalize` (forward jets, residual, loss and reverse pass in one kernel
 per domain) instead of forward graph + `compute_loss` + `loss.backward()`
 (idrlnet/solver.py:329-338).  `Solver(precision="tf32")` runs the layer GEMMs of wide nets on
-the tensor cores (stated tolerance 1e-2); the default "fp32" holds 1e-5.  Everything else runs the generic graph.  Under
+the tensor cores in TF32 (stated tolerance 1e-2); the default "fp32x3" (tensor cores, 3xTF32 operand splitting) and "fp32"
+(FP32 FMA) hold 1e-5.  Everything else runs the generic graph.  Under
 `torch.distributed` the points of every domain are sharded over the ranks and
 the flat gradient (+ loss scalars) is all-reduced once per step.
 
@@ -92,8 +93,8 @@ class Solver(Notifier, Optimizable):
         if post_step_loss is None:  # reference behaviour unless the fast mode is asked for
             post_step_loss = os.environ.get("IDRLNET_B200_POST_STEP_LOSS", "1") not in ("0", "false", "False")
         self.post_step_loss = bool(post_step_loss)
-        # arithmetic of the layer GEMMs of wide (H > 32) nets: "fp32" (FP32 FMA, parity, default), "fp32x3" (tensor
-        # cores, 3xTF32 splitting), "tf32" / "tf32_streamed" (tensor cores); None -> IDRLNET_B200_PRECISION or "fp32"
+        # arithmetic of the layer GEMMs of wide (H > 32) nets: "fp32x3" (tensor cores, 3xTF32 splitting: FP32-grade, the
+        # default), "fp32" (FP32 FMA), "tf32" / "tf32_streamed" (tensor cores, 1e-2); None -> IDRLNET_B200_PRECISION or "fp32x3"
         self.precision = precision
         # under torch.distributed every sampled domain is split [rank::world] (all ranks draw the same seeded points, as
         # an unchanged example does); shard_points=False is for callers whose samplers already return this rank's points
