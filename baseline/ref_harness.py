@@ -164,12 +164,23 @@ def time_sizes(sc, wl, cfg, sizes, device, args, np, torch):
            "sizes": sizes, "torch": torch.__version__, "tf32_allowed": bool(args.tf32),
            "what": "unmodified idrlnet 2.0.0 from baseline/_ref" + (", idrlnet.use_gpu(%d)" % args.gpu_index if device.type == "cuda" else ", CPU"),
            "threads": torch.get_num_threads()}
+    if device.type == "cuda":
+        torch.cuda.reset_peak_memory_stats(device)
     for mode, fn, steps, warmup in (("strict", lambda: strict_step(solver), args.steps, args.warmup),
                                     ("train_pipe", solver.train_pipe, args.pipe_steps, min(args.warmup, 2))):
         if steps <= 0:
             continue
-        for _ in range(warmup):
-            fn()
+        try:
+            for _ in range(warmup):
+                fn()
+        except torch.cuda.OutOfMemoryError:
+            if mode == "strict":
+                raise  # the caller halves the problem
+            # train_pipe as shipped keeps the graph of its returned (post-step) loss alive into the next iteration: it needs
+            # more memory than the strict pass and may not fit at the size where the strict pass runs fastest
+            out[mode] = {"unavailable": "CUDA out of memory at this size (the strict pass fits)"}
+            torch.cuda.empty_cache()
+            continue
         sync()
         if device.type == "cuda":
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -181,6 +192,10 @@ def time_sizes(sc, wl, cfg, sizes, device, args, np, torch):
         if device.type == "cuda":
             e1.record()
         sync()
+        if mode == "strict":
+            loss_val = float(loss)
+            del loss  # drop the graph before the next mode runs
+            loss = loss_val
         wall = (time.perf_counter() - t0) / steps
         dt = e0.elapsed_time(e1) * 1e-3 / steps if device.type == "cuda" else wall
         out[mode] = {"value": pts / dt, "unit": "points/s", "ms_per_step": dt * 1e3, "steps": steps, "warmup": warmup,
