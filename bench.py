@@ -239,13 +239,18 @@ def time_oracle_port(config, factor, steps, warmup):
 # --------------------------------------------------------------------------- #
 # this package
 # --------------------------------------------------------------------------- #
-def ncu_traffic(config):
+def ncu_traffic(config, n_points=None):
     """dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, from the committed
-    `ncu --set full` capture (profiles/ncu_traffic.json); None if not captured."""
+    `ncu --set full` capture (profiles/ncu_traffic.json; scaled linearly when the capture was taken at another point
+    count than the timed launch); None if not captured."""
     path = os.path.join(ROOT, "profiles", "ncu_traffic.json")
     if os.path.exists(path):
         with open(path) as f:
-            return json.load(f).get(config, {}).get("dram_bytes_per_launch")
+            e = json.load(f).get(config, {})
+        b = e.get("dram_bytes_per_launch")
+        if b is not None and n_points and e.get("points"):
+            b = int(b * n_points / e["points"])
+        return b
     return None
 
 
@@ -494,7 +499,7 @@ def roofline_of(run: OursRun, kern_ms, fp32_peak, tf32_peak, hbm_peak, hbm_src):
         peak, src, bound = fp32_peak, "FP32 FMA pipe, pinn_fp32_fma_probe measured in this run", "fp32"
     hbm = cfg["bytes_per_point"] * n_timed / (kern_ms * 1e-3) / 1e9
     return {"bound": bound, "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak if peak else None,
-            "traffic": ncu_traffic(run.name if not run.precision or not cfg["wide"] else f"{run.name}_{run.precision}"),
+            "traffic": ncu_traffic(run.name if not run.precision or not cfg["wide"] else f"{run.name}_{run.precision}", n_timed),
             "kernel": cfg["kernel"] + (f" [{run.precision}]" if cfg["wide"] else ""), "kernel_ms": kern_ms,
             "flop_per_point": cfg["flop_per_point"], "peak_source": src, "fp32_fma_peak": fp32_peak,
             "hbm": {"achieved": hbm, "peak": hbm_peak, "unit": "GB/s", "frac": hbm / hbm_peak, "peak_source": hbm_src}}
