@@ -181,49 +181,9 @@ static int launch_narrow(const pinn_mlp* m, const pinn_jets* j, NarrowParams& p,
   if (ctas > pl.n_cta_cap) ctas = pl.n_cta_cap;
   if (ctas < 1) ctas = 1;
   narrow_kernel_t fn = pl.k->fn;
-  // The per-warp scratch (jet stash + gradient accumulators, 43 MB for the default MLP) is rewritten by every tile and
-  // only ever needs to live in L2, yet the plain launch wrote 214 MB of it back to DRAM per 2^20-point launch
-  // (profiles/r02/ncu_narrow_r02.txt).  Mark it persisting for THIS launch (a launch attribute, not stream state): hits
-  // stay in the L2 set-aside, everything else streams.  PINN_L2_PERSIST=0 disables it.
-  static const bool persist = [] { const char* e = getenv("PINN_L2_PERSIST"); return !(e && e[0] == '0'); }();
-  static int persist_bytes = -1;  // set-aside granted by the device (0: unsupported / refused)
-  if (persist && persist_bytes < 0) {
-    std::lock_guard<std::mutex> lk(mu);
-    int dev = 0, max_persist = 0, max_window = 0;
-    persist_bytes = 0;
-    if (cudaGetDevice(&dev) == cudaSuccess &&
-        cudaDeviceGetAttribute(&max_persist, cudaDevAttrMaxPersistingL2CacheSize, dev) == cudaSuccess &&
-        cudaDeviceGetAttribute(&max_window, cudaDevAttrMaxAccessPolicyWindowSize, dev) == cudaSuccess && max_persist > 0) {
-      size_t want = (size_t)64 << 20;
-      if (want > (size_t)max_persist) want = (size_t)max_persist;
-      if (cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, want) == cudaSuccess)
-        persist_bytes = (int)(want < (size_t)max_window ? want : (size_t)max_window);
-    }
-    cudaGetLastError();
-  }
-  const int64_t scratch = pl.scratch_bytes();
-  if (persist && persist_bytes > 0 && p.gacc != nullptr && (p.mode == MODE_FUSED || p.mode == MODE_BWD)) {
-    cudaLaunchConfig_t cfg;
-    memset(&cfg, 0, sizeof(cfg));
-    cfg.gridDim = dim3((unsigned)ctas);
-    cfg.blockDim = dim3((unsigned)(pl.n_warps * 32));
-    cfg.dynamicSmemBytes = (size_t)pl.smem_bytes;
-    cfg.stream = st;
-    cudaLaunchAttribute attr[1];
-    memset(attr, 0, sizeof(attr));
-    attr[0].id = cudaLaunchAttributeAccessPolicyWindow;
-    attr[0].val.accessPolicyWindow.base_ptr = (void*)p.gacc;
-    attr[0].val.accessPolicyWindow.num_bytes = (size_t)(scratch < persist_bytes ? scratch : persist_bytes);
-    attr[0].val.accessPolicyWindow.hitRatio = 1.0f;
-    attr[0].val.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
-    attr[0].val.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
-    cfg.attrs = attr;
-    cfg.numAttrs = 1;
-    cudaError_t le = cudaLaunchKernelEx(&cfg, fn, p, (int)m->width);
-    if (le != cudaSuccess) return cuda_fail(le, "narrow kernel launch (access policy window)");
-  } else {
-    fn<<<(unsigned)ctas, pl.n_warps * 32, pl.smem_bytes, st>>>(p, m->width);
-  }
+  // (A per-launch persisting-L2 access-policy window over the per-warp scratch was measured and NOT kept: DRAM writes of
+  // the 2^20-point Burgers launch went from 210 MB to 1 364 MB -- profiles/r02/narrow_l2_persist_experiment.txt.)
+  fn<<<(unsigned)ctas, pl.n_warps * 32, pl.smem_bytes, st>>>(p, m->width);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return cuda_fail(e, "narrow kernel launch");
   count_launch(1);

@@ -5,6 +5,10 @@
 
 #include "narrow_warp.h"
 
+#ifndef PINN_NARROW_BOUNDS
+#define PINN_NARROW_BOUNDS __launch_bounds__(NW::kMaxWarps * 32, 1)
+#endif
+
 namespace pinn {
 
 typedef void (*narrow_kernel_t)(const NarrowParams, int);
@@ -17,7 +21,7 @@ struct NarrowKernelInfo {
 };
 
 template <class NW>
-__global__ void __launch_bounds__(NW::kMaxWarps * 32, 1) narrow_kernel(const __grid_constant__ NarrowParams p, int Hreal) {
+__global__ void PINN_NARROW_BOUNDS narrow_kernel(const __grid_constant__ NarrowParams p, int Hreal) {
   extern __shared__ __align__(16) float smem[];
   const int L = p.n_hidden;
   const Layout lay(NW::H, L);

@@ -32,6 +32,10 @@
 #pragma once
 #include "pinn_common.h"
 
+#ifndef PINN_PAIR_WARPS
+#define PINN_PAIR_WARPS 8  // warps per CTA of the packed program (register budget: 65536 / (32 * warps))
+#endif
+
 namespace pinn {
 
 enum { MODE_FUSED = 0, MODE_FWD = 1, MODE_BWD = 2, MODE_LOSS = 3 };  // LOSS: forward + residual + loss, no reverse pass
@@ -478,7 +482,7 @@ struct NarrowWarp {
   }
 
   // dW_l[j][k] += sum_{n,c} zbar_l[n][c][j] * h_{l-1}[n][c][k];  db_l[j] += sum_n zbar_l[n][0][j]
-  PINN_HD static void phase_gemm_hidden(const NarrowParams& p, float* wm, float* g, int lane_id, int l) {
+  PINN_HD static void phase_gemm_hidden_fma(const NarrowParams& p, float* wm, float* g, int lane_id, int l) {
     const int L = p.n_hidden;
     const Layout lay(H, L);
     const int s = S();
@@ -529,6 +533,172 @@ struct NarrowWarp {
     }
   }
 
+  // ---- the same contraction on the warp-level tensor path (mma.sync m16n8k8, 3xTF32 operand split) -----------------
+  // D (M = units j, N = units k) += A (M x K) * B (K x N), K = (point, channel); one k-step is EIGHT points of one channel:
+  // column t <-> point n0 + 2t, column t + 4 <-> point n0 + 2t + 1.  Tile row g <-> unit 2u, row g + 8 <-> unit 2u + 1
+  // (u = 8 mt + g): a 64-bit load per point is (a0, a1) / (a2, a3); on the B side a 64-bit load is b0 (or b1) of two n8
+  // tiles (even / odd units of u = 8 nb + g).  Rows are [c][H] with an odd quad stride, so the half-warp of a 64-bit load
+  // (four g, four t) covers sixteen distinct 8-byte banks.  H = 20: the four left-over units are one n8 tile from scalar
+  // loads whose column 4 carries ones for the value channel (bias gradient).  See NarrowWarpPair for the packed layout.
+  static constexpr int NPAIR = H / 2;
+  static constexpr int MT = (NPAIR + 7) / 8;
+  static constexpr int NB2 = NPAIR / 8;
+  static constexpr int NPL = NPAIR % 8;
+  static constexpr int NTL = NPL == 0 ? 0 : (NPL <= 2 ? 1 : 2);
+  static constexpr int NT = 2 * NB2 + NTL;
+  static constexpr bool kBiasInMma = (NTL == 1);
+
+  // fragments of lane (g = lane / 4, t = lane % 4) for k-step (channel c, points n0 .. n0 + 7)
+  PINN_HD static void load_a_frags(const float* A, int s, int c, int n0, int lane_id, float (&a)[MT][4]) {
+    const int gq = lane_id >> 2, t = lane_id & 3;
+    const float* r0 = A + (n0 + 2 * t) * s + c * H;
+    const float* r1 = r0 + s;
+#pragma unroll
+    for (int mt = 0; mt < MT; ++mt) {
+      const int u = 8 * mt + gq;
+      f2 v0 = f2{0.f, 0.f}, v1 = f2{0.f, 0.f};
+      if (8 * mt + 7 < NPAIR || u < NPAIR) { v0 = ld2(r0 + 2 * u); v1 = ld2(r1 + 2 * u); }
+      a[mt][0] = v0.x; a[mt][1] = v0.y; a[mt][2] = v1.x; a[mt][3] = v1.y;
+    }
+  }
+  PINN_HD static void load_b_frags(const float* B, int s, int c, int n0, int lane_id, float (&b)[NT][2]) {
+    const int gq = lane_id >> 2, t = lane_id & 3;
+    const float* r0 = B + (n0 + 2 * t) * s + c * H;
+    const float* r1 = r0 + s;
+#pragma unroll
+    for (int nb = 0; nb < NB2 + (NTL == 2 ? 1 : 0); ++nb) {
+      const int u = 8 * nb + gq;
+      f2 v0 = f2{0.f, 0.f}, v1 = f2{0.f, 0.f};
+      if (nb < NB2 || u < NPAIR) { v0 = ld2(r0 + 2 * u); v1 = ld2(r1 + 2 * u); }
+      b[2 * nb][0] = v0.x; b[2 * nb + 1][0] = v0.y; b[2 * nb][1] = v1.x; b[2 * nb + 1][1] = v1.y;
+    }
+    if (NTL == 1) {
+      float v0 = 0.f, v1 = 0.f;
+      if (gq < 2 * NPL) { v0 = r0[16 * NB2 + gq]; v1 = r1[16 * NB2 + gq]; }
+      else if (gq == 4 && c == 0) { v0 = 1.0f; v1 = 1.0f; }  // bias column: ones against the value channel
+      b[NT - 1][0] = v0; b[NT - 1][1] = v1;
+    }
+  }
+  // float offset in the gradient accumulators of the element pair (rows g, g + 8; column cn) of tile (mt, nt); -1: padding
+  PINN_HD static int dw_target(const Layout& lay, int l, int mt, int nt, int gq, int cn) {
+    const int ua = 8 * mt + gq;
+    if (ua >= NPAIR) return -1;
+    if (NTL == 1 && nt == NT - 1) {
+      if (cn < 2 * NPL) return lay.wh(l) + (16 * NB2 + cn) * H + 2 * ua;
+      return cn == 4 ? lay.bh(l) + 2 * ua : -1;
+    }
+    const int ub = 8 * (nt >> 1) + cn;
+    if (ub >= NPAIR) return -1;
+    return lay.wh(l) + (2 * ub + (nt & 1)) * H + 2 * ua;
+  }
+
+  PINN_HD static void phase_gemm_hidden(const NarrowParams& p, float* wm, float* g, int lane_id, int l) {
+#if defined(PINN_NARROW_DW_FMA)
+    phase_gemm_hidden_fma(p, wm, g, lane_id, l);
+#else
+    const int L = p.n_hidden;
+    const Layout lay(H, L);
+    const int s = S();
+    const float* A = wm + off_a();  // zbar_l
+    const float* B = wm + off_b();  // h_{l-1}
+    const int gq = lane_id >> 2, t = lane_id & 3;
+    float acc[MT][NT][4];
+    // this lane's accumulator targets are requested up front: their L2 latency hides behind the MMA loop (and the loads
+    // cannot be ordered behind the stores of other targets, which the compiler must assume may alias)
+    int goff[MT][NT][2];
+    f2 gv[MT][NT][2];
+#pragma unroll
+    for (int mt = 0; mt < MT; ++mt)
+#pragma unroll
+      for (int nt = 0; nt < NT; ++nt) {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) acc[mt][nt][e] = 0.f;
+#pragma unroll
+        for (int w = 0; w < 2; ++w) {
+          goff[mt][nt][w] = dw_target(lay, l, mt, nt, gq, 2 * t + w);
+          gv[mt][nt][w] = goff[mt][nt][w] >= 0 ? ld2(g + goff[mt][nt][w]) : f2{0.f, 0.f};
+        }
+      }
+#if defined(__CUDA_ARCH__)
+#pragma unroll 1
+    for (int c = 0; c < C; ++c) {
+#pragma unroll 2
+      for (int n0 = 0; n0 < 32; n0 += 8) {
+        float a[MT][4], b[NT][2];
+        load_a_frags(A, s, c, n0, lane_id, a);
+        load_b_frags(B, s, c, n0, lane_id, b);
+        uint32_t ah[MT][4], al[MT][4], bh[NT][2], bl[NT][2];
+#pragma unroll
+        for (int mt = 0; mt < MT; ++mt)
+#pragma unroll
+          for (int e = 0; e < 4; ++e) split_tf32(a[mt][e], ah[mt][e], al[mt][e]);
+#pragma unroll
+        for (int nt = 0; nt < NT; ++nt)
+#pragma unroll
+          for (int e = 0; e < 2; ++e) split_tf32(b[nt][e], bh[nt][e], bl[nt][e]);
+#pragma unroll
+        for (int mt = 0; mt < MT; ++mt)
+#pragma unroll
+          for (int nt = 0; nt < NT; ++nt) mma_m16n8k8_tf32(acc[mt][nt], al[mt], bh[nt]);
+#pragma unroll
+        for (int mt = 0; mt < MT; ++mt)
+#pragma unroll
+          for (int nt = 0; nt < NT; ++nt) mma_m16n8k8_tf32(acc[mt][nt], ah[mt], bl[nt]);
+#pragma unroll
+        for (int mt = 0; mt < MT; ++mt)
+#pragma unroll
+          for (int nt = 0; nt < NT; ++nt) mma_m16n8k8_tf32(acc[mt][nt], ah[mt], bh[nt]);
+      }
+    }
+#else
+    // host emulation (tests/emu): this lane's D elements from the fragments the OTHER lanes would hold
+    for (int c = 0; c < C; ++c)
+      for (int n0 = 0; n0 < 32; n0 += 8) {
+        float af[4][MT][4], bf[2][4][NT][2];
+        for (int tt = 0; tt < 4; ++tt) {
+          load_a_frags(A, s, c, n0, gq * 4 + tt, af[tt]);
+          for (int w = 0; w < 2; ++w) load_b_frags(B, s, c, n0, (2 * t + w) * 4 + tt, bf[w][tt]);
+        }
+        for (int mt = 0; mt < MT; ++mt)
+          for (int nt = 0; nt < NT; ++nt)
+            for (int e = 0; e < 4; ++e) {
+              const int row_hi = e >> 1, w = e & 1;
+              float d = 0.f;
+              for (int kk = 0; kk < 8; ++kk)
+                d += mul_tf32x3(af[kk & 3][mt][row_hi + 2 * (kk >> 2)], bf[w][kk & 3][nt][kk >> 2]);
+              acc[mt][nt][e] += d;
+            }
+      }
+#endif
+#pragma unroll
+    for (int mt = 0; mt < MT; ++mt)
+#pragma unroll
+      for (int nt = 0; nt < NT; ++nt)
+#pragma unroll
+        for (int w = 0; w < 2; ++w) {
+          if (goff[mt][nt][w] >= 0) {
+            f2 v = gv[mt][nt][w];
+            v.x += acc[mt][nt][w];
+            v.y += acc[mt][nt][2 + w];
+            st2(g + goff[mt][nt][w], v);
+          }
+        }
+    if (!kBiasInMma) {
+      for (int tq = lane_id; tq < H4; tq += 32) {
+        f4 a = f4{0.f, 0.f, 0.f, 0.f};
+        for (int n = 0; n < 32; ++n) {
+          const f4 v = ld4(A + n * s + tq * 4);
+          a.x += v.x; a.y += v.y; a.z += v.z; a.w += v.w;
+        }
+        float* gp = g + lay.bh(l) + tq * 4;
+        f4 v = ld4(gp);
+        v.x += a.x; v.y += a.y; v.z += a.z; v.w += a.w;
+        st4(gp, v);
+      }
+    }
+#endif
+  }
+
   // dW1[j][d] += sum_n zbar_val[n][j] x_d[n] + [d == first_in[i]] sum_n zbar_i[n][j];  db1[j] += sum_n zbar_val[n][j]
   PINN_HD static void phase_gemm_first(const NarrowParams& p, float* wm, float* g, int lane_id) {
     const int L = p.n_hidden;
@@ -577,7 +747,7 @@ struct NarrowWarpPair {
   static constexpr int C = 1 + NF + NS;
   static constexpr int CP = C / 2;
   static constexpr int H4 = H / 4;
-  static constexpr int kMaxWarps = 8;
+  static constexpr int kMaxWarps = PINN_PAIR_WARPS;
   static_assert(C % 2 == 0, "channel pairs need an even channel count");
 
   PINN_HD static int S() { return row_stride(C * H); }
@@ -898,7 +1068,7 @@ struct NarrowWarpPair {
     }
   }
 
-  PINN_HD static void phase_gemm_hidden(const NarrowParams& p, float* wm, float* g, int lane_id, int l) {
+  PINN_HD static void phase_gemm_hidden_fma(const NarrowParams& p, float* wm, float* g, int lane_id, int l) {
     const int L = p.n_hidden;
     const Layout lay(H, L);
     const int s = S();
@@ -949,6 +1119,181 @@ struct NarrowWarpPair {
       v.x += a.x; v.y += a.y; v.z += a.z; v.w += a.w;
       st4(gp, v);
     }
+  }
+
+  // ---- dW_l on the warp-level tensor path (mma.sync m16n8k8, 3xTF32 operand split) -------------------------------
+  // dW_l[j][k] = sum over the 32 points n and C channels c of zbar_l[n][c][j] * h_{l-1}[n][c][k] as D (M = units j, N =
+  // units k) += A (M x K) * B (K x N) with the contraction index K = (point, channel).  One k-step (K = 8) is four points
+  // x the two channels of a pair: column t <-> (point P(t), channel 2cp), column t + 4 <-> (P(t), 2cp + 1).  A row buffer
+  // keeps the units of a channel pair in 16-byte chunks (unit 2u: both channels, unit 2u + 1: both channels), so with tile
+  // row g <-> even unit of chunk q = 8 mt + g and row g + 8 <-> its odd unit, ONE 128-bit load is the lane's whole A
+  // fragment (a0, a2, a1, a3), and on the B side one 128-bit load is the fragments (b0, b1) of two n8 tiles (even units /
+  // odd units of chunks 8 nb + g).  Every operand element is read once per layer (20 KB per tile and layer instead of
+  // 100 KB for 4x4 register tiles: the FFMA2 GEMM was bound by the shared-memory return path).
+  // Points of a k-step are P(t) = n0 + 2t: with an odd quad stride the quarter-warp (two g, four t) then lands on eight
+  // distinct 16-byte bank groups because chunks of consecutive g are adjacent.
+  // H = 20: 10 chunks -> two m16 tiles (the second with two valid row pairs), one chunk group (two n8 tiles) + the two
+  // left-over chunks as one n8 tile loaded with 64-bit loads (columns 0..3), whose free column 4 carries ones for the
+  // value channel: D[:, 4] of that tile is the bias gradient.  H = 32: two m16 tiles, two groups (four n8 tiles).
+  static constexpr int NPAIR = H / 2;          // 16-byte chunks (unit pairs) per channel pair
+  static constexpr int MT = (NPAIR + 7) / 8;   // m16 tiles
+  static constexpr int NB2 = NPAIR / 8;        // full chunk groups on the N side
+  static constexpr int NPL = NPAIR % 8;        // left-over chunks on the N side
+  static constexpr int NTL = NPL == 0 ? 0 : (NPL <= 2 ? 1 : 2);
+  static constexpr int NT = 2 * NB2 + NTL;     // n8 tiles
+  static constexpr bool kBiasInMma = (NTL == 1);
+  PINN_HD static int kstep_point(int ks, int t) { return (ks >> 1) * 8 + (ks & 1) + 2 * t; }
+  PINN_HD static int chunk_unit(int q) { return 4 * (q % H4) + 2 * (q / H4); }  // even unit of chunk q
+
+  PINN_HD static void load_a_frags(const float* A, int s, int cp, int ks, int lane_id, float (&a)[MT][4]) {
+    const int gq = lane_id >> 2, t = lane_id & 3;
+    const float* row = A + kstep_point(ks, t) * s + cp * 2 * H;
+#pragma unroll
+    for (int mt = 0; mt < MT; ++mt) {
+      const int q = 8 * mt + gq;
+      f4 v = f4{0.f, 0.f, 0.f, 0.f};
+      if (8 * mt + 7 < NPAIR || q < NPAIR) v = ld4(row + q * 4);
+      a[mt][0] = v.x; a[mt][2] = v.y; a[mt][1] = v.z; a[mt][3] = v.w;
+    }
+  }
+  PINN_HD static void load_b_frags(const float* B, int s, int cp, int ks, int lane_id, float (&b)[NT][2]) {
+    const int gq = lane_id >> 2, t = lane_id & 3;
+    const float* row = B + kstep_point(ks, t) * s + cp * 2 * H;
+#pragma unroll
+    for (int nb = 0; nb < NB2 + (NTL == 2 ? 1 : 0); ++nb) {
+      const int q = 8 * nb + gq;
+      f4 v = f4{0.f, 0.f, 0.f, 0.f};
+      if (nb < NB2 || q < NPAIR) v = ld4(row + q * 4);
+      b[2 * nb][0] = v.x; b[2 * nb][1] = v.y; b[2 * nb + 1][0] = v.z; b[2 * nb + 1][1] = v.w;
+    }
+    if (NTL == 1) {
+      f2 v = f2{0.f, 0.f};
+      if (gq < 2 * NPL) v = ld2(row + (8 * NB2 + (gq >> 1)) * 4 + (gq & 1) * 2);
+      else if (gq == 4 && cp == 0) v.x = 1.0f;  // bias column: ones against the value channel
+      b[NT - 1][0] = v.x; b[NT - 1][1] = v.y;
+    }
+  }
+  // float offset in the gradient accumulators of the element pair (rows g, g + 8; column cn) of tile (mt, nt); -1: padding
+  PINN_HD static int dw_target(const Layout& lay, int l, int mt, int nt, int gq, int cn) {
+    const int qa = 8 * mt + gq;
+    if (qa >= NPAIR) return -1;
+    const int j = chunk_unit(qa);
+    if (NTL == 1 && nt == NT - 1) {
+      if (cn < 2 * NPL) return lay.wh(l) + (chunk_unit(8 * NB2 + (cn >> 1)) + (cn & 1)) * H + j;
+      return cn == 4 ? lay.bh(l) + j : -1;
+    }
+    const int qb = 8 * (nt >> 1) + cn;
+    if (qb >= NPAIR) return -1;
+    return lay.wh(l) + (chunk_unit(qb) + (nt & 1)) * H + j;
+  }
+
+  PINN_HD static void phase_gemm_hidden(const NarrowParams& p, float* wm, float* g, int lane_id, int l) {
+#if defined(PINN_NARROW_DW_FMA)
+    phase_gemm_hidden_fma(p, wm, g, lane_id, l);
+#else
+    const int L = p.n_hidden;
+    const Layout lay(H, L);
+    const int s = S();
+    const float* A = wm + off_a();  // zbar_l
+    const float* B = wm + off_b();  // h_{l-1}
+    const int gq = lane_id >> 2, t = lane_id & 3;
+    float acc[MT][NT][4];
+    // this lane's accumulator targets are requested up front: their L2 latency hides behind the MMA loop (and the loads
+    // cannot be ordered behind the stores of other targets, which the compiler must assume may alias)
+    int goff[MT][NT][2];
+    f2 gv[MT][NT][2];
+#pragma unroll
+    for (int mt = 0; mt < MT; ++mt)
+#pragma unroll
+      for (int nt = 0; nt < NT; ++nt) {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) acc[mt][nt][e] = 0.f;
+#pragma unroll
+        for (int w = 0; w < 2; ++w) {
+          goff[mt][nt][w] = dw_target(lay, l, mt, nt, gq, 2 * t + w);
+          gv[mt][nt][w] = goff[mt][nt][w] >= 0 ? ld2(g + goff[mt][nt][w]) : f2{0.f, 0.f};
+        }
+      }
+#if defined(__CUDA_ARCH__)
+#pragma unroll 1
+    for (int cp = 0; cp < CP; ++cp) {
+#pragma unroll 2
+      for (int ks = 0; ks < 8; ++ks) {
+        float a[MT][4], b[NT][2];
+        load_a_frags(A, s, cp, ks, lane_id, a);
+        load_b_frags(B, s, cp, ks, lane_id, b);
+        uint32_t ah[MT][4], al[MT][4], bh[NT][2], bl[NT][2];
+#pragma unroll
+        for (int mt = 0; mt < MT; ++mt)
+#pragma unroll
+          for (int e = 0; e < 4; ++e) split_tf32(a[mt][e], ah[mt][e], al[mt][e]);
+#pragma unroll
+        for (int nt = 0; nt < NT; ++nt)
+#pragma unroll
+          for (int e = 0; e < 2; ++e) split_tf32(b[nt][e], bh[nt][e], bl[nt][e]);
+        // term-major: consecutive MMAs go to different accumulators (small terms first)
+#pragma unroll
+        for (int mt = 0; mt < MT; ++mt)
+#pragma unroll
+          for (int nt = 0; nt < NT; ++nt) mma_m16n8k8_tf32(acc[mt][nt], al[mt], bh[nt]);
+#pragma unroll
+        for (int mt = 0; mt < MT; ++mt)
+#pragma unroll
+          for (int nt = 0; nt < NT; ++nt) mma_m16n8k8_tf32(acc[mt][nt], ah[mt], bl[nt]);
+#pragma unroll
+        for (int mt = 0; mt < MT; ++mt)
+#pragma unroll
+          for (int nt = 0; nt < NT; ++nt) mma_m16n8k8_tf32(acc[mt][nt], ah[mt], bh[nt]);
+      }
+    }
+#else
+    // host emulation (tests/emu): this lane's D elements from the fragments the OTHER lanes would hold
+    for (int cp = 0; cp < CP; ++cp)
+      for (int ks = 0; ks < 8; ++ks) {
+        float af[4][MT][4], bf[2][4][NT][2];
+        for (int tt = 0; tt < 4; ++tt) {
+          load_a_frags(A, s, cp, ks, gq * 4 + tt, af[tt]);
+          for (int w = 0; w < 2; ++w) load_b_frags(B, s, cp, ks, (2 * t + w) * 4 + tt, bf[w][tt]);
+        }
+        for (int mt = 0; mt < MT; ++mt)
+          for (int nt = 0; nt < NT; ++nt)
+            for (int e = 0; e < 4; ++e) {
+              const int row_hi = e >> 1, w = e & 1;
+              float d = 0.f;
+              for (int kk = 0; kk < 8; ++kk)
+                d += mul_tf32x3(af[kk & 3][mt][row_hi + 2 * (kk >> 2)], bf[w][kk & 3][nt][kk >> 2]);
+              acc[mt][nt][e] += d;
+            }
+      }
+#endif
+    // accumulate into this warp's gradient scratch: (rows g, g+8) = (even, odd unit of a chunk) are adjacent in Wt[k][j]
+#pragma unroll
+    for (int mt = 0; mt < MT; ++mt)
+#pragma unroll
+      for (int nt = 0; nt < NT; ++nt)
+#pragma unroll
+        for (int w = 0; w < 2; ++w) {
+          if (goff[mt][nt][w] >= 0) {
+            f2 v = gv[mt][nt][w];
+            v.x += acc[mt][nt][w];
+            v.y += acc[mt][nt][2 + w];
+            st2(g + goff[mt][nt][w], v);
+          }
+        }
+    if (!kBiasInMma) {
+      for (int tq = lane_id; tq < H4; tq += 32) {
+        f4 a = f4{0.f, 0.f, 0.f, 0.f};
+        for (int n = 0; n < 32; ++n) {  // value channel = first half of pair 0
+          const f4 u = ld4(A + n * s + chunk_off(0, 0, tq)), v = ld4(A + n * s + chunk_off(0, 1, tq));
+          a.x += u.x; a.y += u.z; a.z += v.x; a.w += v.z;
+        }
+        float* gp = g + lay.bh(l) + tq * 4;
+        f4 v = ld4(gp);
+        v.x += a.x; v.y += a.y; v.z += a.z; v.w += a.w;
+        st4(gp, v);
+      }
+    }
+#endif
   }
 
   PINN_HD static void phase_gemm_first(const NarrowParams& p, float* wm, float* g, int lane_id) {
