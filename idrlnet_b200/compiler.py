@@ -43,51 +43,90 @@ class NetSpec:
 @dataclass
 class JetPlan:
     """first_in[i] = net-input index of first-order channel i; the first
-    n_second of them also carry a pure second-order channel."""
+    n_second of them also carry a pure second-order channel.  Extra channels
+    (narrow nets): n_mixed = 1 adds d2/d(first_in[0]) d(first_in[1]); n_high = 1 / 2
+    adds the pure third (and fourth) derivative along first_in[0]."""
     first_in: Tuple[int, ...] = ()
     n_second: int = 0
+    n_mixed: int = 0
+    n_high: int = 0
 
     @property
     def n_channels(self) -> int:
-        return 1 + len(self.first_in) + self.n_second
+        return 1 + len(self.first_in) + self.n_second + self.n_mixed + self.n_high
 
     def channel(self, inputs: Sequence[str], derivs: Tuple[str, ...]) -> int:
+        nf = len(self.first_in)
         if len(derivs) == 0:
             return 0
         if len(derivs) == 1:
             return 1 + self.first_in.index(inputs.index(derivs[0]))
-        if len(derivs) == 2 and derivs[0] == derivs[1]:
+        if len(set(derivs)) == 1:
             s = self.first_in.index(inputs.index(derivs[0]))
-            if s >= self.n_second:
-                raise KeyError(derivs)
-            return 1 + len(self.first_in) + s
-        raise NotFusable(f"derivative {DIFF.join(derivs)} (mixed or order > 2) has no fused channel")
+            if len(derivs) == 2:
+                if s >= self.n_second:
+                    raise KeyError(derivs)
+                return 1 + nf + s
+            if s == 0 and len(derivs) - 2 <= self.n_high:
+                return 1 + nf + self.n_second + self.n_mixed + (len(derivs) - 3)
+        elif len(derivs) == 2 and self.n_mixed and nf >= 2:
+            if {inputs.index(v) for v in derivs} == {self.first_in[0], self.first_in[1]}:
+                return 1 + nf + self.n_second
+        raise NotFusable(f"derivative {DIFF.join(derivs)} has no fused channel")
 
     def channel_names(self, inputs: Sequence[str]) -> List[Tuple[str, ...]]:
         out: List[Tuple[str, ...]] = [()]
         out += [(inputs[d],) for d in self.first_in]
         out += [(inputs[d], inputs[d]) for d in self.first_in[: self.n_second]]
+        if self.n_mixed:
+            out.append((inputs[self.first_in[0]], inputs[self.first_in[1]]))
+        out += [(inputs[self.first_in[0]],) * (3 + k) for k in range(self.n_high)]
         return out
 
 
 def plan_jets(inputs: Sequence[str], derivative_tuples: Sequence[Tuple[str, ...]]) -> JetPlan:
+    """Channels for a set of derivative symbols.  Beyond first / pure second order the kernels carry ONE mixed second
+    derivative (of exactly two differentiated inputs) or the pure third / fourth derivative along ONE input
+    (idrlnet_b200/csrc/narrow_warp.h, NarrowWarp's X); anything else is NotFusable."""
     first, second = [], []
+    mixed, high_var, n_high = None, None, 0
     for dt in derivative_tuples:
         if len(dt) == 0:
             continue
-        if len(dt) > 2 or (len(dt) == 2 and dt[0] != dt[1]):
-            raise NotFusable(f"derivative {DIFF.join(dt)} (mixed or order > 2) has no fused channel")
         for v in dt:
             if v not in inputs:
                 raise NotFusable(f"derivative w.r.t. {v}, which is not an input of the net")
-        if dt[0] not in first:
-            first.append(dt[0])
-        if len(dt) == 2 and dt[0] not in second:
-            second.append(dt[0])
+        if len(set(dt)) == 1:
+            if len(dt) > 4:
+                raise NotFusable(f"derivative {DIFF.join(dt)} (order > 4) has no fused channel")
+            if dt[0] not in first:
+                first.append(dt[0])
+            if len(dt) >= 2 and dt[0] not in second:
+                second.append(dt[0])
+            if len(dt) >= 3:
+                if high_var not in (None, dt[0]):
+                    raise NotFusable("third/fourth-order derivatives along more than one input")
+                high_var, n_high = dt[0], max(n_high, len(dt) - 2)
+        elif len(dt) == 2:
+            pair = frozenset(dt)
+            if mixed not in (None, pair):
+                raise NotFusable("more than one mixed second derivative")
+            mixed = pair
+            for v in dt:
+                if v not in first:
+                    first.append(v)
+        else:
+            raise NotFusable(f"derivative {DIFF.join(dt)} (mixed, order > 2) has no fused channel")
+    if mixed is not None and n_high:
+        raise NotFusable("mixed and third/fourth-order derivatives in one net")
     order = sorted(second, key=inputs.index) + sorted([v for v in first if v not in second], key=inputs.index)
+    if high_var is not None:  # the high-order input leads
+        order = [high_var] + [v for v in order if v != high_var]
     if len(order) > 3:
         raise NotFusable("more than 3 differentiated inputs")
-    return JetPlan(tuple(inputs.index(v) for v in order), len(second))
+    if mixed is not None and set(order[:2]) != set(mixed):
+        raise NotFusable("the mixed derivative must be of the first two differentiated inputs")
+    return JetPlan(tuple(inputs.index(v) for v in order), len(second), 1 if mixed is not None else 0, n_high)
 
 
 # --------------------------------------------------------------------------- #

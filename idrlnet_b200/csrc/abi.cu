@@ -33,17 +33,25 @@ void count_launch(int n) { g_launches += n; }
 
 static int padded_width(int H) { return H <= 20 ? 20 : (H <= 32 ? 32 : 0); }
 
+// extra-channel mode of the narrow kernels (NarrowWarp's X): 0 none, 1 mixed, 2 third order, 3 third + fourth; -1: no kernel
+static int jets_extra(const pinn_jets* j) {
+  if (j->n_mixed == 0 && j->n_high == 0) return 0;
+  if (j->n_mixed == 1 && j->n_high == 0) return 1;
+  if (j->n_mixed == 0 && (j->n_high == 1 || j->n_high == 2)) return 1 + j->n_high;
+  return -1;
+}
+
 static const NarrowKernelInfo* narrow_lookup(const pinn_mlp* m, const pinn_jets* j) {
   const int Hp = padded_width(m->width);
   if (!Hp) return nullptr;
   if (Hp == 20) {
-    if (m->act == PINN_ACT_TANH) return narrow_table_h20_tanh(j->n_first, j->n_second);
-    if (m->act == PINN_ACT_SILU) return narrow_table_h20_silu(j->n_first, j->n_second);
-    if (m->act == PINN_ACT_SIN) return narrow_table_h20_sin(j->n_first, j->n_second);
+    if (m->act == PINN_ACT_TANH) return narrow_table_h20_tanh(j->n_first, j->n_second, jets_extra(j));
+    if (m->act == PINN_ACT_SILU) return narrow_table_h20_silu(j->n_first, j->n_second, jets_extra(j));
+    if (m->act == PINN_ACT_SIN) return narrow_table_h20_sin(j->n_first, j->n_second, jets_extra(j));
   } else {
-    if (m->act == PINN_ACT_TANH) return narrow_table_h32_tanh(j->n_first, j->n_second);
-    if (m->act == PINN_ACT_SILU) return narrow_table_h32_silu(j->n_first, j->n_second);
-    if (m->act == PINN_ACT_SIN) return narrow_table_h32_sin(j->n_first, j->n_second);
+    if (m->act == PINN_ACT_TANH) return narrow_table_h32_tanh(j->n_first, j->n_second, jets_extra(j));
+    if (m->act == PINN_ACT_SILU) return narrow_table_h32_silu(j->n_first, j->n_second, jets_extra(j));
+    if (m->act == PINN_ACT_SIN) return narrow_table_h32_sin(j->n_first, j->n_second, jets_extra(j));
   }
   return nullptr;
 }
@@ -57,6 +65,9 @@ static int check_mlp(const pinn_mlp* m, const pinn_jets* j) {
   if (m->act < 0 || m->act > PINN_ACT_SIN) return fail(PINN_E_INVALID, "act=%d", m->act);
   if (j->n_first < 0 || j->n_first > 3 || j->n_second < 0 || j->n_second > j->n_first)
     return fail(PINN_E_UNSUPPORTED, "jet plan (%d first, %d second) not supported", j->n_first, j->n_second);
+  if (j->n_mixed < 0 || j->n_mixed > 1 || j->n_high < 0 || j->n_high > 2 || (j->n_mixed && j->n_first < 2) ||
+      (j->n_high && j->n_second < 1) || (j->n_mixed && j->n_high))
+    return fail(PINN_E_UNSUPPORTED, "jet plan (%d mixed, %d third/fourth-order channels) not supported", j->n_mixed, j->n_high);
   for (int i = 0; i < j->n_first; ++i)
     if (j->first_in[i] < 0 || j->first_in[i] >= m->n_in) return fail(PINN_E_INVALID, "first_in[%d]=%d", i, j->first_in[i]);
   for (int l = 0; l <= m->n_hidden; ++l)
@@ -378,7 +389,7 @@ int pinn_jet_backward(const pinn_mlp* m, const pinn_jets* j, int64_t n_points, c
 // ---- forward-only residuals and top-k (adaptive re-sampling) -------------------------------------
 int64_t pinn_residual_workspace_bytes(const pinn_mlp* m, const pinn_jets* j, int64_t n_points) {
   if (!m || !j || n_points < 0) return PINN_E_INVALID;
-  const int C = 1 + j->n_first + j->n_second;
+  const int C = PINN_JET_CHANNELS(j);
   const int64_t jets = (((int64_t)C * m->n_out * n_points * (int64_t)sizeof(float)) + 255) & ~(int64_t)255;
   const int64_t fwd = pinn_workspace_bytes(m, j, 1);
   return fwd < 0 ? fwd : jets + fwd;
@@ -392,7 +403,7 @@ int pinn_residual_forward(const pinn_mlp* m, const pinn_jets* j, const pinn_doma
   if (dom->n_eq < 1 || dom->n_eq > PINN_MAX_EQ || dom->n_terms > PINN_MAX_TERMS)
     return fail(PINN_E_INVALID, "bad equation table");
   if (dom->n_points == 0) return 0;
-  const int C = 1 + j->n_first + j->n_second;
+  const int C = PINN_JET_CHANNELS(j);
   const int64_t jets_bytes = (((int64_t)C * m->n_out * dom->n_points * (int64_t)sizeof(float)) + 255) & ~(int64_t)255;
   if (ws_bytes < pinn_residual_workspace_bytes(m, j, dom->n_points)) return fail(PINN_E_WORKSPACE, "workspace too small");
   float* jets = (float*)ws;

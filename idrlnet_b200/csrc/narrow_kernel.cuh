@@ -80,28 +80,36 @@ __global__ void PINN_NARROW_BOUNDS narrow_kernel(const __grid_constant__ NarrowP
   }
 }
 
-// One table per (H, ACT) translation unit: entries for every (NF, NS).
-#define PINN_NARROW_ENTRY(H, NF, NS, ACT) \
-  { narrow_kernel<NarrowWarpFor<H, NF, NS, ACT>>, H, 1 + NF + NS, NarrowWarpFor<H, NF, NS, ACT>::kMaxWarps,       \
-    &NarrowWarpFor<H, NF, NS, ACT>::warp_floats, \
-    &NarrowWarpFor<H, NF, NS, ACT>::stash_floats }
+// One table per (H, ACT) translation unit: entries for every (NF, NS), plus the extra-channel programs
+// (x: NarrowWarp's X) for the plans that occur: mixed with (2, 0) / (2, 1) / (2, 2), third and third + fourth order
+// with (1, 1).
+#define PINN_NARROW_ENTRY(H, NF, NS, ACT, X) \
+  { narrow_kernel<NarrowWarpFor<H, NF, NS, ACT, X>>, H, NarrowWarpFor<H, NF, NS, ACT, X>::C, NarrowWarpFor<H, NF, NS, ACT, X>::kMaxWarps, \
+    &NarrowWarpFor<H, NF, NS, ACT, X>::warp_floats, \
+    &NarrowWarpFor<H, NF, NS, ACT, X>::stash_floats }
 
 #define PINN_NARROW_TABLE(NAME, H, ACT)                                          \
-  const NarrowKernelInfo* NAME(int nf, int ns) {                                 \
+  const NarrowKernelInfo* NAME(int nf, int ns, int x) {                          \
     static const NarrowKernelInfo t[4][4] = {                                    \
-        {PINN_NARROW_ENTRY(H, 0, 0, ACT), {0, 0, 0, 0, 0, 0}, {0, 0, 0, 0, 0, 0}, {0, 0, 0, 0, 0, 0}}, \
-        {PINN_NARROW_ENTRY(H, 1, 0, ACT), PINN_NARROW_ENTRY(H, 1, 1, ACT), {0, 0, 0, 0, 0, 0}, {0, 0, 0, 0, 0, 0}}, \
-        {PINN_NARROW_ENTRY(H, 2, 0, ACT), PINN_NARROW_ENTRY(H, 2, 1, ACT), PINN_NARROW_ENTRY(H, 2, 2, ACT), {0, 0, 0, 0, 0, 0}}, \
-        {PINN_NARROW_ENTRY(H, 3, 0, ACT), PINN_NARROW_ENTRY(H, 3, 1, ACT), PINN_NARROW_ENTRY(H, 3, 2, ACT), PINN_NARROW_ENTRY(H, 3, 3, ACT)}}; \
+        {PINN_NARROW_ENTRY(H, 0, 0, ACT, 0), {0, 0, 0, 0, 0, 0}, {0, 0, 0, 0, 0, 0}, {0, 0, 0, 0, 0, 0}}, \
+        {PINN_NARROW_ENTRY(H, 1, 0, ACT, 0), PINN_NARROW_ENTRY(H, 1, 1, ACT, 0), {0, 0, 0, 0, 0, 0}, {0, 0, 0, 0, 0, 0}}, \
+        {PINN_NARROW_ENTRY(H, 2, 0, ACT, 0), PINN_NARROW_ENTRY(H, 2, 1, ACT, 0), PINN_NARROW_ENTRY(H, 2, 2, ACT, 0), {0, 0, 0, 0, 0, 0}}, \
+        {PINN_NARROW_ENTRY(H, 3, 0, ACT, 0), PINN_NARROW_ENTRY(H, 3, 1, ACT, 0), PINN_NARROW_ENTRY(H, 3, 2, ACT, 0), PINN_NARROW_ENTRY(H, 3, 3, ACT, 0)}}; \
+    static const NarrowKernelInfo mixed20 = PINN_NARROW_ENTRY(H, 2, 0, ACT, 1), mixed21 = PINN_NARROW_ENTRY(H, 2, 1, ACT, 1), \
+                                  mixed22 = PINN_NARROW_ENTRY(H, 2, 2, ACT, 1);  \
+    static const NarrowKernelInfo third = PINN_NARROW_ENTRY(H, 1, 1, ACT, 2), fourth = PINN_NARROW_ENTRY(H, 1, 1, ACT, 3); \
     if (nf < 0 || nf > 3 || ns < 0 || ns > nf) return nullptr;                   \
+    if (x == 1) return nf != 2 ? nullptr : ns == 0 ? &mixed20 : ns == 1 ? &mixed21 : &mixed22; \
+    if (x == 2 || x == 3) return (nf == 1 && ns == 1) ? (x == 2 ? &third : &fourth) : nullptr; \
+    if (x != 0) return nullptr;                                                  \
     return t[nf][ns].fn ? &t[nf][ns] : nullptr;                                  \
   }
 
-const NarrowKernelInfo* narrow_table_h20_tanh(int nf, int ns);
-const NarrowKernelInfo* narrow_table_h20_silu(int nf, int ns);
-const NarrowKernelInfo* narrow_table_h20_sin(int nf, int ns);
-const NarrowKernelInfo* narrow_table_h32_tanh(int nf, int ns);
-const NarrowKernelInfo* narrow_table_h32_silu(int nf, int ns);
-const NarrowKernelInfo* narrow_table_h32_sin(int nf, int ns);
+const NarrowKernelInfo* narrow_table_h20_tanh(int nf, int ns, int x);
+const NarrowKernelInfo* narrow_table_h20_silu(int nf, int ns, int x);
+const NarrowKernelInfo* narrow_table_h20_sin(int nf, int ns, int x);
+const NarrowKernelInfo* narrow_table_h32_tanh(int nf, int ns, int x);
+const NarrowKernelInfo* narrow_table_h32_silu(int nf, int ns, int x);
+const NarrowKernelInfo* narrow_table_h32_sin(int nf, int ns, int x);
 
 }  // namespace pinn

@@ -77,10 +77,20 @@ struct Layout {
   PINN_HD int size() const { return bo() + 4; }
 };
 
-template <int H_, int NF_, int NS_, int ACT_>
+// X_ selects extra jet channels after the pure second-order ones: 1 = the mixed second derivative
+// d2/d(first_in[0]) d(first_in[1]); 2 = the pure third derivative along first_in[0]; 3 = third and fourth (the chain of
+// examples/euler_beam/euler_beam.py:47-54).
+template <int H_, int NF_, int NS_, int ACT_, int X_ = 0>
 struct NarrowWarp {
-  static constexpr int H = H_, NF = NF_, NS = NS_, ACT = ACT_;
-  static constexpr int C = 1 + NF + NS;
+  static constexpr int H = H_, NF = NF_, NS = NS_, ACT = ACT_, X = X_;
+  static constexpr int NM = (X == 1) ? 1 : 0;                 // mixed channels
+  static constexpr int NH = (X == 2) ? 1 : (X == 3) ? 2 : 0;  // third / fourth order channels
+  static constexpr int CM = 1 + NF + NS;                      // index of the mixed channel
+  static constexpr int C3 = 1 + NF + NS + NM;                 // index of the third-order channel (fourth: C3 + 1)
+  static constexpr int C = 1 + NF + NS + NM + NH;
+  static_assert(X >= 0 && X <= 3, "extra-channel mode");
+  static_assert(NM == 0 || NF >= 2, "the mixed channel needs two first-order channels");
+  static_assert(NH == 0 || NS >= 1, "third/fourth order along first_in[0] need its second-order channel");
   static constexpr int H4 = H / 4;
   static constexpr int kMaxWarps = 8;  // (10 warps fit in shared memory now, but at <= 200 registers they lose: profiles/r01/narrow_warps_sweep.txt)
   static_assert(H % 4 == 0, "hidden width must be a multiple of 4");
@@ -104,20 +114,44 @@ struct NarrowWarp {
   };
 
   // ---- small pieces -------------------------------------------------------
+  // sigma .. sigma^(5) at z (the orders above 3 only for the third/fourth-order channels)
+  PINN_HD static void act_all(float z, float (&sd)[6]) {
+    if (NH > 0) {
+      act_derivs6<ACT>(z, sd);
+    } else {
+      act_derivs<ACT>(z, sd[0], sd[1], sd[2], sd[3]);
+      sd[4] = 0.f; sd[5] = 0.f;
+    }
+  }
+
+  // h = sigma(z) as a jet.  Third / fourth order along one input (Faa di Bruno; z1, z2, z3, z4 the derivatives of z):
+  //   h3 = s3 z1^3 + 3 s2 z1 z2 + s1 z3;   h4 = s4 z1^4 + 6 s3 z1^2 z2 + 3 s2 z2^2 + 4 s2 z1 z3 + s1 z4;
+  // mixed: h_ab = s2 z_a z_b + s1 z_ab.
   PINN_HD static void unit_fwd(const float (&z)[C], float (&h)[C]) {
-    float s0, s1, s2, s3;
-    act_derivs<ACT>(z[0], s0, s1, s2, s3);
-    h[0] = s0;
+    float sd[6];
+    act_all(z[0], sd);
+    const float s1 = sd[1], s2 = sd[2];
+    h[0] = sd[0];
 #pragma unroll
     for (int i = 0; i < NF; ++i) h[1 + i] = s1 * z[1 + i];
 #pragma unroll
     for (int s = 0; s < NS; ++s) h[1 + NF + s] = s2 * z[1 + s] * z[1 + s] + s1 * z[1 + NF + s];
+    if (NM > 0) h[CM] = s2 * z[1] * z[NF >= 2 ? 2 : 1] + s1 * z[CM];
+    if (NH > 0) {
+      const float z1 = z[1], z2 = z[1 + NF], z3 = z[C3];
+      h[C3] = sd[3] * z1 * z1 * z1 + 3.0f * s2 * z1 * z2 + s1 * z3;
+      if (NH > 1)
+        h[C - 1] = sd[4] * (z1 * z1) * (z1 * z1) + 6.0f * sd[3] * z1 * z1 * z2 + s2 * (3.0f * z2 * z2 + 4.0f * z1 * z3) +
+                   s1 * z[C - 1];
+    }
   }
 
+  // adjoint of unit_fwd: zb = (dh/dz)^T hb (every sigma^(n) becomes sigma^(n+1) in the value slot); also returns h
   PINN_HD static void unit_bwd(const float (&z)[C], const float (&hb)[C], float (&h)[C], float (&zb)[C]) {
-    float s0, s1, s2, s3;
-    act_derivs<ACT>(z[0], s0, s1, s2, s3);
-    h[0] = s0;
+    float sd[6];
+    act_all(z[0], sd);
+    const float s1 = sd[1], s2 = sd[2], s3 = sd[3];
+    h[0] = sd[0];
     float zv = hb[0] * s1;
 #pragma unroll
     for (int i = 0; i < NF; ++i) {
@@ -132,6 +166,32 @@ struct NarrowWarp {
       zv += hbs * (s3 * zi * zi + s2 * zii);
       zb[1 + s] += 2.0f * hbs * s2 * zi;
       zb[1 + NF + s] = hbs * s1;
+    }
+    if (NM > 0) {
+      constexpr int B = NF >= 2 ? 2 : 1;
+      const float za = z[1], zc = z[B], zm = z[CM], hbm = hb[CM];
+      h[CM] = s2 * za * zc + s1 * zm;
+      zv += hbm * (s3 * za * zc + s2 * zm);
+      zb[1] += hbm * s2 * zc;
+      zb[B] += hbm * s2 * za;
+      zb[CM] = hbm * s1;
+    }
+    if (NH > 0) {
+      const float z1 = z[1], z2 = z[1 + NF], z3 = z[C3], hb3 = hb[C3], s4 = sd[4];
+      h[C3] = s3 * z1 * z1 * z1 + 3.0f * s2 * z1 * z2 + s1 * z3;
+      zv += hb3 * (s4 * z1 * z1 * z1 + 3.0f * s3 * z1 * z2 + s2 * z3);
+      zb[1] += hb3 * (3.0f * s3 * z1 * z1 + 3.0f * s2 * z2);
+      zb[1 + NF] += hb3 * 3.0f * s2 * z1;
+      zb[C3] = hb3 * s1;
+      if (NH > 1) {
+        const float z4 = z[C - 1], hb4 = hb[C - 1], q1 = z1 * z1;
+        h[C - 1] = s4 * q1 * q1 + 6.0f * s3 * q1 * z2 + s2 * (3.0f * z2 * z2 + 4.0f * z1 * z3) + s1 * z4;
+        zv += hb4 * (sd[5] * q1 * q1 + 6.0f * s4 * q1 * z2 + s3 * (3.0f * z2 * z2 + 4.0f * z1 * z3) + s2 * z4);
+        zb[1] += hb4 * (4.0f * s4 * q1 * z1 + 12.0f * s3 * z1 * z2 + 4.0f * s2 * z3);
+        zb[1 + NF] += hb4 * (6.0f * s3 * q1 + 6.0f * s2 * z2);
+        zb[C3] += hb4 * 4.0f * s2 * z1;
+        zb[C - 1] = hb4 * s1;
+      }
     }
     zb[0] = zv;
   }
@@ -161,7 +221,7 @@ struct NarrowWarp {
       zt[1 + i] = r;
     }
 #pragma unroll
-    for (int s = 0; s < NS; ++s) zt[1 + NF + s] = f4{0.f, 0.f, 0.f, 0.f};
+    for (int c = 1 + NF; c < C; ++c) zt[c] = f4{0.f, 0.f, 0.f, 0.f};  // z_1 is linear in x: every higher derivative is zero
   }
 
   PINN_HD static void load_row_tile(const float* row, int k4, f4 (&t)[C]) {
@@ -740,11 +800,11 @@ struct NarrowWarp {
 // unit 4m+2h+1: ch 2cp, ch 2cp+1).  The 4-unit tile of a channel pair is the two 16-byte chunks (h = 0, 1);
 // chunks of consecutive unit quads are adjacent, so the five (H = 20) or eight (H = 32) distinct chunks
 // that the lanes of a GEMM load touch fall into different bank groups.
-template <int H_, int NF_, int NS_, int ACT_>
+template <int H_, int NF_, int NS_, int ACT_, int X_ = 0>
 struct NarrowWarpPair {
-  using Base = NarrowWarp<H_, NF_, NS_, ACT_>;
-  static constexpr int H = H_, NF = NF_, NS = NS_, ACT = ACT_;
-  static constexpr int C = 1 + NF + NS;
+  using Base = NarrowWarp<H_, NF_, NS_, ACT_, X_>;
+  static constexpr int H = H_, NF = NF_, NS = NS_, ACT = ACT_, X = X_;
+  static constexpr int C = Base::C;
   static constexpr int CP = C / 2;
   static constexpr int H4 = H / 4;
   static constexpr int kMaxWarps = PINN_PAIR_WARPS;
@@ -1326,16 +1386,16 @@ struct NarrowWarpPair {
 };
 
 // even channel counts run the packed program, odd ones the scalar one
-template <int H, int NF, int NS, int ACT, bool EVEN = ((1 + NF + NS) % 2 == 0)>
+template <int H, int NF, int NS, int ACT, int X = 0, bool EVEN = (NarrowWarp<H, NF, NS, ACT, X>::C % 2 == 0)>
 struct NarrowSelect {
-  using type = NarrowWarp<H, NF, NS, ACT>;
+  using type = NarrowWarp<H, NF, NS, ACT, X>;
 };
-template <int H, int NF, int NS, int ACT>
-struct NarrowSelect<H, NF, NS, ACT, true> {
-  using type = NarrowWarpPair<H, NF, NS, ACT>;
+template <int H, int NF, int NS, int ACT, int X>
+struct NarrowSelect<H, NF, NS, ACT, X, true> {
+  using type = NarrowWarpPair<H, NF, NS, ACT, X>;
 };
-template <int H, int NF, int NS, int ACT>
-using NarrowWarpFor = typename NarrowSelect<H, NF, NS, ACT>::type;
+template <int H, int NF, int NS, int ACT, int X = 0>
+using NarrowWarpFor = typename NarrowSelect<H, NF, NS, ACT, X>::type;
 
 // Weight staging: global (row-major [out,in]) -> smem padded/transposed Layout.
 // idx is an index into the Layout; returns the value to store there.

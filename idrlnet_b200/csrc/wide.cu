@@ -570,6 +570,7 @@ __global__ void wide_collect_loss_kernel(float* ws, WideLayout wl, int hstride, 
 bool make_net(const pinn_mlp* m, const pinn_jets* j, WNet* n) {
   if (m->width <= 32 || m->width > 512 || (m->width % 4) != 0) return false;
   if (m->n_hidden < 1 || j->n_first > 3 || j->n_second > j->n_first) return false;
+  if (j->n_mixed || j->n_high) return false;  // mixed / third / fourth-order channels: narrow kernels only
   memset(n, 0, sizeof(*n));
   n->n_in = m->n_in; n->n_out = m->n_out; n->L = m->n_hidden; n->H = m->width; n->act = m->act;
   n->NF = j->n_first; n->NS = j->n_second; n->C = 1 + n->NF + n->NS;

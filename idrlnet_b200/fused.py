@@ -282,7 +282,7 @@ class JetFunction(torch.autograd.Function):
         wbc = [t.detach().contiguous() for t in wb]
         mlp = nv.make_mlp(len(cols), Ws[-1].shape[0], n_layers - 1, Ws[0].shape[0], act,
                           [t.data_ptr() for t in wbc[0::2]], [t.data_ptr() for t in wbc[1::2]], precision)
-        jets = nv.make_jets(plan.first_in, plan.n_second)
+        jets = nv.make_jets(plan.first_in, plan.n_second, plan.n_mixed, plan.n_high)
         out = torch.empty(plan.n_channels * Ws[-1].shape[0], n, device=cols[0].device, dtype=torch.float32)
         ws_bytes = lib.pinn_workspace_bytes(C.byref(mlp), C.byref(jets), 1)
         ws = torch.empty(max(ws_bytes // 4, 1), device=cols[0].device, dtype=torch.float32)
@@ -299,7 +299,7 @@ class JetFunction(torch.autograd.Function):
         n = cols[0].numel()
         mlp = nv.make_mlp(len(cols), Ws[-1].shape[0], len(Ws) - 1, Ws[0].shape[0], ctx.act,
                           [t.data_ptr() for t in wbc[0::2]], [t.data_ptr() for t in wbc[1::2]], ctx.precision)
-        jets = nv.make_jets(plan.first_in, plan.n_second)
+        jets = nv.make_jets(plan.first_in, plan.n_second, plan.n_mixed, plan.n_high)
         ws_bytes = lib.pinn_workspace_bytes(C.byref(mlp), C.byref(jets), 1)
         ws = torch.empty(ws_bytes // 4, device=cols[0].device, dtype=torch.float32)
         ob = out_bar.contiguous()
@@ -333,7 +333,7 @@ class FusedDomain:
         self.compiled = compiled
         self.loss = loss
         self.sigma = float(sigma)
-        self.jets = nv.make_jets(compiled.plan.first_in, compiled.plan.n_second)
+        self.jets = nv.make_jets(compiled.plan.first_in, compiled.plan.n_second, compiled.plan.n_mixed, compiled.plan.n_high)
         self._struct: Optional[nv.PinnDomain] = None
         self._keep: List[torch.Tensor] = []
         self.n_points = 0

@@ -222,7 +222,7 @@ class _JetServe:
             raise cp.NotFusable("more outputs named than the net has")
         from . import native as nv
         import ctypes as C
-        jets = nv.make_jets(plan.first_in, plan.n_second)
+        jets = nv.make_jets(plan.first_in, plan.n_second, plan.n_mixed, plan.n_high)
         pack.refresh_effective()
         if not nv.lib().pinn_supported(C.byref(pack.mlp_struct()), C.byref(jets)):
             raise cp.NotFusable("no kernel for this width / jet plan")

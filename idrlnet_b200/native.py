@@ -36,7 +36,8 @@ class PinnMlp(C.Structure):
 
 
 class PinnJets(C.Structure):
-    _fields_ = [("n_first", C.c_int32), ("n_second", C.c_int32), ("first_in", C.c_int32 * MAX_FIRST)]
+    _fields_ = [("n_first", C.c_int32), ("n_second", C.c_int32), ("first_in", C.c_int32 * MAX_FIRST),
+                ("n_mixed", C.c_int32), ("n_high", C.c_int32)]
 
 
 class PinnTerm(C.Structure):
@@ -69,9 +70,9 @@ def make_mlp(n_in: int, n_out: int, n_hidden: int, width: int, act: str, w_ptrs:
     return m
 
 
-def make_jets(first_in: Sequence[int], n_second: int) -> PinnJets:
+def make_jets(first_in: Sequence[int], n_second: int, n_mixed: int = 0, n_high: int = 0) -> PinnJets:
     j = PinnJets()
-    j.n_first, j.n_second = len(first_in), n_second
+    j.n_first, j.n_second, j.n_mixed, j.n_high = len(first_in), n_second, n_mixed, n_high
     for i, d in enumerate(first_in):
         j.first_in[i] = d
     return j

@@ -89,12 +89,21 @@ typedef struct pinn_mlp {
 /* Which input-derivative "jet" channels to propagate.  Replaces the nested
  * torch.autograd.grad calls of idrlnet/variable.py:161-208: channel 0 is the
  * value, channel 1+i is d/d(input first_in[i]), channel 1+n_first+s is
- * d2/d(input first_in[s])^2  (s < n_second <= n_first). */
+ * d2/d(input first_in[s])^2  (s < n_second <= n_first).  Extra channels follow in
+ * this order (narrow nets only; at most one kind at a time):
+ *   n_mixed (0/1): d2 / d(input first_in[0]) d(input first_in[1])   (needs n_first >= 2)
+ *   n_high (0..2): d3 / d(input first_in[0])^3, then d4 / d(input first_in[0])^4
+ *                  (needs n_second >= 1; the derivative chain of
+ *                  examples/euler_beam/euler_beam.py:47-54). */
 typedef struct pinn_jets {
   int32_t n_first;
   int32_t n_second;
   int32_t first_in[PINN_MAX_FIRST];
+  int32_t n_mixed;
+  int32_t n_high;
 } pinn_jets;
+/* number of channels of a jet plan */
+#define PINN_JET_CHANNELS(j) (1 + (j)->n_first + (j)->n_second + (j)->n_mixed + (j)->n_high)
 
 /* A residual is a polynomial in the symbols (what idrlnet/pde.py:65-79 +
  * idrlnet/torch_util.py:25-39 lambdify; every PDE of idrlnet/pde_op/equations.py

@@ -78,14 +78,28 @@ struct RunnerT : Runner {
    {new RunnerT<NarrowWarpFor<H, 1, 0, A>>, new RunnerT<NarrowWarpFor<H, 1, 1, A>>, nullptr, nullptr},          \
    {new RunnerT<NarrowWarpFor<H, 2, 0, A>>, new RunnerT<NarrowWarpFor<H, 2, 1, A>>, new RunnerT<NarrowWarpFor<H, 2, 2, A>>, nullptr}, \
    {new RunnerT<NarrowWarpFor<H, 3, 0, A>>, new RunnerT<NarrowWarpFor<H, 3, 1, A>>, new RunnerT<NarrowWarpFor<H, 3, 2, A>>, new RunnerT<NarrowWarpFor<H, 3, 3, A>>}}
+// extra-channel programs: [0..2] mixed (2, 0) / (2, 1) / (2, 2), [3] third order (1, 1), [4] third + fourth order (1, 1)
+#define XROW(H, A)                                                                                        \
+  {new RunnerT<NarrowWarpFor<H, 2, 0, A, 1>>, new RunnerT<NarrowWarpFor<H, 2, 1, A, 1>>,                    \
+   new RunnerT<NarrowWarpFor<H, 2, 2, A, 1>>, new RunnerT<NarrowWarpFor<H, 1, 1, A, 2>>,                    \
+   new RunnerT<NarrowWarpFor<H, 1, 1, A, 3>>}
 
-const Runner* lookup(int width, int act, int nf, int ns) {
+const Runner* lookup(int width, int act, const pinn_jets* j) {
   static const Runner* t20[3][4][4] = {ROW(20, PINN_ACT_TANH), ROW(20, PINN_ACT_SILU), ROW(20, PINN_ACT_SIN)};
   static const Runner* t32[3][4][4] = {ROW(32, PINN_ACT_TANH), ROW(32, PINN_ACT_SILU), ROW(32, PINN_ACT_SIN)};
-  if (act < 0 || act > 2 || nf < 0 || nf > 3 || ns < 0 || ns > nf) return nullptr;
+  static const Runner* x20[3][5] = {XROW(20, PINN_ACT_TANH), XROW(20, PINN_ACT_SILU), XROW(20, PINN_ACT_SIN)};
+  static const Runner* x32[3][5] = {XROW(32, PINN_ACT_TANH), XROW(32, PINN_ACT_SILU), XROW(32, PINN_ACT_SIN)};
+  const int nf = j->n_first, ns = j->n_second;
+  if (act < 0 || act > 2 || nf < 0 || nf > 3 || ns < 0 || ns > nf || width > 32) return nullptr;
+  if (j->n_mixed || j->n_high) {
+    int k = -1;
+    if (j->n_mixed == 1 && !j->n_high && nf == 2) k = ns;
+    if (!j->n_mixed && (j->n_high == 1 || j->n_high == 2) && nf == 1 && ns == 1) k = 2 + j->n_high;
+    if (k < 0) return nullptr;
+    return width <= 20 ? x20[act][k] : x32[act][k];
+  }
   if (width <= 20) return t20[act][nf][ns];
-  if (width <= 32) return t32[act][nf][ns];
-  return nullptr;
+  return t32[act][nf][ns];
 }
 
 int64_t param_count(const pinn_mlp* m) {
@@ -113,7 +127,7 @@ __attribute__((visibility("default"))) int pinn_emu_run(const pinn_mlp* m, const
                                                         const float* const* coords, float* jets_out,
                                                         const float* jets_bar, float* flat_grad, float* loss_out,
                                                         int n_cta, int n_warps) {
-  const Runner* r = lookup(m->width, m->act, j->n_first, j->n_second);
+  const Runner* r = lookup(m->width, m->act, j);
   if (!r) return PINN_E_UNSUPPORTED;
   NarrowParams p;
   fill(p, m, j);

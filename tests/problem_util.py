@@ -114,7 +114,7 @@ def run_emu_fused(problem, n_cta=3, n_warps=2, mode=0):
         layers = effective_layers(net)
         keep.append(layers)
         mlp = mlp_struct(layers, len(cd.net.inputs), len(cd.net.outputs), net["act"], lambda a: a.ctypes.data)
-        jets = nv.make_jets(cd.plan.first_in, cd.plan.n_second)
+        jets = nv.make_jets(cd.plan.first_in, cd.plan.n_second, cd.plan.n_mixed, cd.plan.n_high)
 
         def val(v):
             if np.ndim(v) == 0:

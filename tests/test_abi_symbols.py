@@ -40,6 +40,6 @@ def test_struct_sizes_match_header():
     # sizes implied by include/pinn_b200.h on LP64
     assert C.sizeof(nv.PinnTerm) == 12
     assert C.sizeof(nv.PinnEquation) == 32
-    assert C.sizeof(nv.PinnJets) == 24
+    assert C.sizeof(nv.PinnJets) == 32
     assert C.sizeof(nv.PinnMlp) == 24 + 2 * 16 * 8
     assert C.sizeof(nv.PinnDomain) == 8 + 4 * 8 + 8 * 8 + 8 + 6 * 4 + 8 * 32 + 64 * 12

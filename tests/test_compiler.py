@@ -69,8 +69,11 @@ def test_expression_nodes_are_substituted():
 
 @pytest.mark.parametrize("targets,exprs,nets,sampled,why", [
     (["e"], {"e": "sin(u)"}, [("n", ("x",), ("u",))], ["x"], "polynomial"),
-    (["e"], {"e": "u__x__y"}, [("n", ("x", "y"), ("u",))], ["x", "y"], "mixed"),
-    (["e"], {"e": "u__x__x__x"}, [("n", ("x",), ("u",))], ["x"], "order"),
+    (["e"], {"e": "u__x__y + u__y__t"}, [("n", ("x", "y", "t"), ("u",))], ["x", "y", "t"], "more than one mixed"),
+    (["e"], {"e": "u__x__x__y"}, [("n", ("x", "y"), ("u",))], ["x", "y"], "mixed, order > 2"),
+    (["e"], {"e": "u__x__x__x__x__x"}, [("n", ("x",), ("u",))], ["x"], "order > 4"),
+    (["e"], {"e": "u__x__x__x + u__y__y__y"}, [("n", ("x", "y"), ("u",))], ["x", "y"], "more than one input"),
+    (["e"], {"e": "u__x__x__x + u__x__y"}, [("n", ("x", "y"), ("u",))], ["x", "y"], "mixed and third"),
     (["e"], {"e": "u - up"}, [("a", ("x",), ("u",)), ("b", ("xp",), ("up",))], ["x", "xp"], "nets"),
     (["e"], {"e": "u", "xp": "x + 2"}, [("n", ("xp",), ("u",))], ["x"], "upstream"),
     (["e"], {"e": "u*q"}, [("n", ("x",), ("u",))], ["x"], "cannot"),
@@ -79,6 +82,25 @@ def test_not_fusable(targets, exprs, nets, sampled, why):
     with pytest.raises(cp.NotFusable) as e:
         cp.compile_domain(targets, exprs, [cp.NetSpec(*n) for n in nets], sampled)
     assert why in str(e.value)
+
+
+def test_mixed_and_high_order_channels_are_planned():
+    """one mixed second derivative, or the pure third / fourth derivative along one input
+    (examples/euler_beam/euler_beam.py:47-54), get their own jet channels."""
+    cd = cp.compile_domain(["e"], {"e": "u__x__x + u__y__y + u__y__x"}, [cp.NetSpec("n", ("x", "y"), ("u",))], ["x", "y"])
+    assert cd.plan.first_in == (0, 1) and cd.plan.n_second == 2 and cd.plan.n_mixed == 1 and cd.plan.n_channels == 6
+    assert cd.plan.channel(("x", "y"), ("y", "x")) == cd.plan.channel(("x", "y"), ("x", "y")) == 5
+    assert cd.plan.channel_names(("x", "y"))[5] == ("x", "y")
+    x = sympy.Symbol("x")
+    y = sympy.Function("y")(x)
+    beam = sc.ExpressionNode(name="dddd_y", expression=y.diff(x).diff(x).diff(x).diff(x) + 1)
+    cd = cp.compile_domain(["dddd_y"], _exprs(beam), [cp.NetSpec("n", ("x",), ("y",))], ["x"])
+    assert cd.plan.first_in == (0,) and cd.plan.n_second == 1 and cd.plan.n_high == 2 and cd.plan.n_channels == 5
+    assert sorted(i for _, ids in cd.equations[0].terms for i in ids) == [4 * nv.MAX_OUT]
+    # the high-order input leads even when another input sorts before it
+    cd = cp.compile_domain(["e"], {"e": "u__t__t__t + u__x__x"}, [cp.NetSpec("n", ("x", "t"), ("u",))], ["x", "t"])
+    assert cd.plan.first_in == (1, 0) and cd.plan.n_second == 2 and cd.plan.n_high == 1
+    assert cd.plan.channel(("x", "t"), ("t", "t", "t")) == 5
 
 
 def test_domain_struct_round_trip():

@@ -63,6 +63,15 @@ SHAPES = [
     (("x", "t"), ("u", "v"), "u__t + 0.5*v__x__x + (u**2 + v**2)*v", "tanh", 32, 3, 70),
     (("x", "y", "t"), ("u",), "u__x + u__y + u__t", "silu", 32, 2, 40),
     (("x", "t"), ("u",), "u__t - u__x", "tanh", 8, 5, 100),
+    # the mixed second derivative, and the pure third / fourth derivative along one input
+    (("x", "y"), ("u",), "u__x__y + u*u__x - 0.3*u__y", "tanh", 20, 3, 45),
+    (("x", "y"), ("u", "v"), "u__x__x + u__y__y + 0.5*v__x__y - v*u__y__x", "silu", 20, 3, 40),
+    (("x", "y"), ("u",), "u__y__x*u__x__y + u", "sin", 32, 2, 38),
+    (("x", "y"), ("u",), "u__x__y + u__x__x - u", "silu", 20, 4, 50),
+    (("x",), ("y",), "y__x__x__x + y*y__x__x - y__x", "tanh", 20, 3, 41),
+    (("x",), ("y",), "y__x__x__x__x + 1", "silu", 20, 4, 40),
+    (("x",), ("y", "w"), "y__x__x__x__x + w__x__x__x*y - 0.1*w__x", "sin", 20, 2, 35),
+    (("x",), ("y",), "y__x__x__x__x*y - y__x__x", "tanh", 32, 3, 33),
 ]
 
 

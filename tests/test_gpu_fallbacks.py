@@ -22,30 +22,7 @@ def _points(rng, n, keys=("x", "y")):
     return p
 
 
-def test_mixed_derivative_falls_back_to_autograd(tmp_path):
-    rng = np.random.default_rng(0)
-    pts = _points(rng, 200)
-    x, y = sp.symbols("x y")
-    u = sp.Function("u")(x, y)
-    torch.manual_seed(0)
-    net = sc.get_net_node(inputs=("x", "y"), outputs=("u",), name="net1", arch=sc.Arch.mlp)
-    eq = sc.ExpressionNode(expression=u.diff(x).diff(y) + u.diff(x, 2) - u, name="mixed")
-    s = sc.Solver(sample_domains=(_fixed_domain("dom", pts, {"mixed": 0.0}),), netnodes=[net], pdes=[eq],
-                  network_dir=str(tmp_path), loading=False)
-    assert "dom" not in s._fused_domains  # u__x__y has no fused channel
-    s.optimizers[0].zero_grad()
-    loss = s._loss_and_grads()
-    assert loss.is_cuda and float(loss) > 0
-    assert all(p.grad is not None and p.grad.is_cuda for p in net.net.parameters() if p.requires_grad)
-    # same numbers as the oracle (reference algorithm)
-    problem = {"nets": [{"name": "net1", "inputs": ["x", "y"], "outputs": ["u"], "act": "silu", "shares": None,
-                         "layers": [{"g": l.weight_g.detach().cpu().numpy(), "v": l.weight_v.detach().cpu().numpy(),
-                                     "b": l.bias.detach().cpu().numpy()}
-                                    for k, l in net.net.layers.items() if not k.endswith("_activation")]}],
-               "exprs": {"mixed": "u__x__y + u__x__x - u"},
-               "domains": [{"name": "dom", "points": pts, "targets": {"mixed": 0.0}, "lambdas": {}, "loss": "square", "sigma": 1.0}]}
-    ref = po.training_step(problem, dtype=torch.float64)
-    assert abs(float(loss) - ref["loss"]) <= 1e-4 * abs(ref["loss"])
+# (mixed second derivatives now have a fused channel: tests/test_gpu_f4.py holds the remaining fallback case)
 
 
 @pytest.mark.parametrize("omegas", [(30.0, 30.0), (3.0, 2.0)])
