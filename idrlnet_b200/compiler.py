@@ -126,6 +126,8 @@ def plan_jets(inputs: Sequence[str], derivative_tuples: Sequence[Tuple[str, ...]
         raise NotFusable("more than 3 differentiated inputs")
     if mixed is not None and set(order[:2]) != set(mixed):
         raise NotFusable("the mixed derivative must be of the first two differentiated inputs")
+    # (padding an odd channel count to the packed-FMA program with an unused mixed channel was measured on the Poisson
+    # step: 2.21 vs 1.95 ms per launch -- not done)
     return JetPlan(tuple(inputs.index(v) for v in order), len(second), 1 if mixed is not None else 0, n_high)
 
 

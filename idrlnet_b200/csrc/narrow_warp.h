@@ -652,8 +652,11 @@ struct NarrowWarp {
     return lay.wh(l) + (2 * ub + (nt & 1)) * H + 2 * ua;
   }
 
+  // The scalar program keeps the FFMA GEMM by default: with an odd channel count a k-step is eight points of ONE channel
+  // (4 C k-steps of 18 MMAs per layer: 360 for C = 5 against 288 for the packed program's C = 4) and the Poisson step
+  // measured 9 % SLOWER on the tensor path (1.947 vs 1.788 ms per 2^20-point launch); PINN_NARROW_SCALAR_DW_MMA selects it.
   PINN_HD static void phase_gemm_hidden(const NarrowParams& p, float* wm, float* g, int lane_id, int l) {
-#if defined(PINN_NARROW_DW_FMA)
+#if defined(PINN_NARROW_DW_FMA) || !defined(PINN_NARROW_SCALAR_DW_MMA)
     phase_gemm_hidden_fma(p, wm, g, lane_id, l);
 #else
     const int L = p.n_hidden;
