@@ -520,8 +520,12 @@ struct NarrowWarp {
     const float* yb = wm + off_a();
     const float* hb = wm + off_b();
     const int T = p.n_out * H4;
+    // (accumulator targets are requested before the reduction loops: their L2 round trip hides behind them)
+    const float gb = lane_id < p.n_out ? g[lay.bo() + lane_id] : 0.f;
     for (int t = lane_id; t < T; t += 32) {
       const int o = t / H4, kb = t % H4;
+      float* gw = g + lay.wo() + (kb * 4) * 4 + o;
+      const float g0 = gw[0], g1 = gw[4], g2 = gw[8], g3 = gw[12];
       f4 acc = f4{0.f, 0.f, 0.f, 0.f};
       for (int n = 0; n < 32; ++n) {
 #pragma unroll
@@ -531,13 +535,12 @@ struct NarrowWarp {
           acc.x += a * b.x; acc.y += a * b.y; acc.z += a * b.z; acc.w += a * b.w;
         }
       }
-      float* gw = g + lay.wo() + (kb * 4) * 4 + o;
-      gw[0] += acc.x; gw[4] += acc.y; gw[8] += acc.z; gw[12] += acc.w;
+      gw[0] = g0 + acc.x; gw[4] = g1 + acc.y; gw[8] = g2 + acc.z; gw[12] = g3 + acc.w;
     }
     if (lane_id < p.n_out) {
       float a = 0.f;
       for (int n = 0; n < 32; ++n) a += yb[n * s + lane_id];
-      g[lay.bo() + lane_id] += a;
+      g[lay.bo() + lane_id] = gb + a;
     }
   }
 
@@ -770,6 +773,12 @@ struct NarrowWarp {
     const float* X = wm + off_a();  // zbar_1
     const float* xs = wm + off_xs();
     for (int j = lane_id; j < H; j += 32) {
+      // targets first (five independent loads whose L2 latency hides behind the loop); the first-order sums are folded
+      // into the column of their input in registers, so no read-modify-write is ordered behind another
+      float gd[4];
+#pragma unroll
+      for (int d = 0; d < 4; ++d) gd[d] = g[lay.w1() + d * H + j];
+      const float gb = g[lay.b1() + j];
       float ad[4] = {0.f, 0.f, 0.f, 0.f};
       float af[NF > 0 ? NF : 1];
 #pragma unroll
@@ -784,10 +793,14 @@ struct NarrowWarp {
         for (int i = 0; i < NF; ++i) af[i] += X[n * s + (1 + i) * H + j];
       }
 #pragma unroll
-      for (int d = 0; d < 4; ++d) g[lay.w1() + d * H + j] += ad[d];
+      for (int d = 0; d < 4; ++d) {
+        float v = gd[d] + ad[d];
 #pragma unroll
-      for (int i = 0; i < NF; ++i) g[lay.w1() + p.jets.first_in[i] * H + j] += af[i];
-      g[lay.b1() + j] += ab;
+        for (int i = 0; i < NF; ++i)
+          if (p.jets.first_in[i] == d) v += af[i];
+        g[lay.w1() + d * H + j] = v;
+      }
+      g[lay.b1() + j] = gb + ab;
     }
   }
 };
@@ -1106,8 +1119,11 @@ struct NarrowWarpPair {
     const float* yb = wm + off_a();
     const float* hb = wm + off_b();
     const int T = p.n_out * H4;
+    const float gb = lane_id < p.n_out ? g[lay.bo() + lane_id] : 0.f;  // targets first: see NarrowWarp::phase_gemm_out
     for (int t = lane_id; t < T; t += 32) {
       const int o = t / H4, kb = t % H4;
+      float* gw = g + lay.wo() + (kb * 4) * 4 + o;
+      const float g0 = gw[0], g1 = gw[4], g2 = gw[8], g3 = gw[12];
       f2 acc[4];  // per unit k: partial sums of the two channels of a pair
 #pragma unroll
       for (int e = 0; e < 4; ++e) acc[e] = f2{0.f, 0.f};
@@ -1121,13 +1137,13 @@ struct NarrowWarpPair {
           for (int e = 0; e < 4; ++e) acc[e] = fma2(a, b[e], acc[e]);
         }
       }
-      float* gw = g + lay.wo() + (kb * 4) * 4 + o;
-      gw[0] += acc[0].x + acc[0].y; gw[4] += acc[1].x + acc[1].y; gw[8] += acc[2].x + acc[2].y; gw[12] += acc[3].x + acc[3].y;
+      gw[0] = g0 + (acc[0].x + acc[0].y); gw[4] = g1 + (acc[1].x + acc[1].y);
+      gw[8] = g2 + (acc[2].x + acc[2].y); gw[12] = g3 + (acc[3].x + acc[3].y);
     }
     if (lane_id < p.n_out) {
       float a = 0.f;
       for (int n = 0; n < 32; ++n) a += yb[n * s + lane_id];
-      g[lay.bo() + lane_id] += a;
+      g[lay.bo() + lane_id] = gb + a;
     }
   }
 
@@ -1366,6 +1382,11 @@ struct NarrowWarpPair {
     const float* X = wm + off_a();  // zbar_1
     const float* xs = wm + off_xs();
     for (int j = lane_id; j < H; j += 32) {
+      // targets first, first-order sums folded in registers: see NarrowWarp::phase_gemm_first
+      float gd[4];
+#pragma unroll
+      for (int d = 0; d < 4; ++d) gd[d] = g[lay.w1() + d * H + j];
+      const float gb = g[lay.b1() + j];
       float ad[4] = {0.f, 0.f, 0.f, 0.f};
       float af[NF > 0 ? NF : 1];
 #pragma unroll
@@ -1380,10 +1401,14 @@ struct NarrowWarpPair {
         for (int i = 0; i < NF; ++i) af[i] += X[n * s + elem_off(1 + i, j)];
       }
 #pragma unroll
-      for (int d = 0; d < 4; ++d) g[lay.w1() + d * H + j] += ad[d];
+      for (int d = 0; d < 4; ++d) {
+        float v = gd[d] + ad[d];
 #pragma unroll
-      for (int i = 0; i < NF; ++i) g[lay.w1() + p.jets.first_in[i] * H + j] += af[i];
-      g[lay.b1() + j] += ab;
+        for (int i = 0; i < NF; ++i)
+          if (p.jets.first_in[i] == d) v += af[i];
+        g[lay.w1() + d * H + j] = v;
+      }
+      g[lay.b1() + j] = gb + ab;
     }
   }
 };

@@ -167,7 +167,7 @@ def lib() -> C.CDLL:
         for name, (res, args) in _SIGNATURES.items():
             fn = getattr(handle, name)
             fn.restype, fn.argtypes = res, args
-        if handle.pinn_abi_version() != 1:
+        if handle.pinn_abi_version() != 2:
             raise ImportError("libpinn_b200.so ABI version mismatch; rebuild")
         _LIB = handle
     return _LIB

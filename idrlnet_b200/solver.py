@@ -371,7 +371,10 @@ class Solver(Notifier, Optimizable):
         ordered = {f"{d.name}_loss": comps[f"{d.name}_loss"] for d in self.sample_domains if f"{d.name}_loss" in comps}
         self.loss_component = Variables(ordered)
         self.notify(self, message={Signal.BEFORE_COMPUTE_LOSS: {**self.loss_component}})
-        loss = sum(self._sigma(k[:-5], v.device) * v for k, v in ordered.items())
+        if len(engines) == 1 and not generic and list(ordered) == [f"{fd.name}_loss" for fd in engines[0].domains]:
+            loss = engines[0].total_loss()  # sum_d sigma_d * loss_d as ONE dot product (was 2 tiny kernels per domain)
+        else:
+            loss = sum(self._sigma(k[:-5], v.device) * v for k, v in ordered.items())
         self.notify(self, message={Signal.AFTER_COMPUTE_LOSS: {**self.loss_component, **{"total_loss": loss}}})
         if not grads:
             return loss.detach() if isinstance(loss, torch.Tensor) else loss

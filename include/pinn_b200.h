@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define PINN_ABI_VERSION 1
+#define PINN_ABI_VERSION 2
 
 #if defined(__GNUC__)
 #define PINN_API __attribute__((visibility("default")))

@@ -24,7 +24,7 @@ def test_header_symbols_are_exported():
 
 def test_host_only_queries():
     lib = nv.lib()
-    assert lib.pinn_abi_version() == 1
+    assert lib.pinn_abi_version() == 2
     mlp = nv.make_mlp(2, 1, 4, 20, "silu", [1] * 5, [1] * 5)  # pointers are not dereferenced by the queries
     assert lib.pinn_param_count(C.byref(mlp)) == 2 * 20 + 20 + 3 * (400 + 20) + 20 + 1 == 1341 + 0 * 1
     jets = nv.make_jets((0, 1), 1)
