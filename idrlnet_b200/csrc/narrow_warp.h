@@ -32,6 +32,9 @@
 #pragma once
 #include "pinn_common.h"
 
+#ifndef PINN_DW_UNROLL
+#define PINN_DW_UNROLL 8  // k-steps of the tensor-path dW loop unrolled together (1 / 2 / 4 / 8 measured: profiles/r02/narrow_dw_variants.txt)
+#endif
 #ifndef PINN_PAIR_WARPS
 #define PINN_PAIR_WARPS 8  // warps per CTA of the packed program (register budget: 65536 / (32 * warps))
 #endif
@@ -1294,9 +1297,10 @@ struct NarrowWarpPair {
         }
       }
 #if defined(__CUDA_ARCH__)
+    constexpr int kUnroll = PINN_DW_UNROLL;
 #pragma unroll 1
     for (int cp = 0; cp < CP; ++cp) {
-#pragma unroll 2
+#pragma unroll kUnroll
       for (int ks = 0; ks < 8; ++ks) {
         float a[MT][4], b[NT][2];
         load_a_frags(A, s, cp, ks, lane_id, a);

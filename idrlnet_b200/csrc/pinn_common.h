@@ -117,8 +117,13 @@ PINN_HD float bits_f(uint32_t u) {
 // a*b ~= a_lo*b_hi + a_hi*b_lo + a_hi*b_hi, the pipe reading the upper 19 bits of every operand.  What is dropped:
 // the truncation of lo (<= 2^-21 |x| per operand) and lo*lo (<= 2^-22 |ab|).
 PINN_HD void split_tf32(float x, uint32_t& hi, uint32_t& lo) {
+#if defined(PINN_SPLIT_TRUNC)  // experiment: hi by truncation (the pipe ignores the low bits of x itself): 2 instructions
+  hi = f_bits(x);
+  lo = f_bits(x - bits_f(f_bits(x) & 0xffffe000u));
+#else
   hi = (f_bits(x) + 0x1000u) & 0xffffe000u;
   lo = f_bits(x - bits_f(hi));
+#endif
 }
 // the same product in plain arithmetic (host emulation of the tensor pipe: tests/emu)
 PINN_HD float mul_tf32x3(float a, float b) {
