@@ -765,7 +765,10 @@ int run_mode(const pinn_mlp* m, const pinn_jets* j, int mode, const pinn_domain*
     CK(cudaMemsetAsync(w + wl.dw, 0, (size_t)(wl.wt - wl.dw) * 4, st));  // partial slots only (not the weight tiles)
   int rc = 0;
   const bool stepping = mode == W_MODE_FUSED || mode == W_MODE_LOSS;
-  const bool on_chip = stepping && fused_wide_supported(n) && m->precision == PINN_PREC_TF32 &&
+  // whole step on chip: TF32 (16-point tiles) and, where the doubled operand buffers fit, FP32-grade 3xTF32 (8-point
+  // tiles); PINN_PREC_TF32_STREAMED and everything else take the layer-streamed kernels
+  const bool on_chip = stepping && fused_wide_supported(n) &&
+                       (m->precision == PINN_PREC_TF32 || m->precision == PINN_PREC_FP32X3) &&
                        fused_wide_stash_floats(n) <= (int64_t)2 * n.L * n.C * wl.Mc * n.H;
   // weight preparation once per step: later domains of the same step (accumulate != 0) reuse it
   const bool prep = !accumulate || !stepping;
@@ -774,7 +777,9 @@ int run_mode(const pinn_mlp* m, const pinn_jets* j, int mode, const pinn_domain*
       rc = tc_transpose(n.W[l - 1], w + wl.wt + (size_t)(l - 2) * n.H * n.H, n.H, st);
       if (rc) return rc;
     }
-  if (n.precision == 1 && stepping && prep && n.H <= 128 && n.L >= 2) {
+  // (prepared whenever ANY domain of this net could take the on-chip kernel: whether one does depends on its channel
+  // count, and later domains of the step reuse the first one's preparation)
+  if (stepping && prep && (m->precision == PINN_PREC_TF32 || m->precision == PINN_PREC_FP32X3) && n.H <= 128 && n.L >= 2) {
     rc = fused_wide_prep(n, w + wl.wprep, st);
     if (rc) return rc;
   }

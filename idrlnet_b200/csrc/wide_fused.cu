@@ -22,16 +22,20 @@
 namespace pinn {
 namespace {
 
-constexpr int kP = 16;       // points per tile
+// Two instances per jet plan: KP = 16 points per tile with single-pass TF32 multiplicands (PINN_PREC_TF32), and KP = 8 with
+// 3xTF32 operand splitting (PINN_PREC_FP32X3, FP32-grade: every operand buffer holds a hi block followed by a lo block,
+// hi = tf32(x), lo = x - hi, and a K step issues lo*hi + hi*lo + hi*hi).  The doubled buffers are why the FP32-grade
+// instance works on half tiles: 220 KB of shared memory at H = 100, C = 5; it does not fit H = 128.
+constexpr int kPMax = 16;    // points per tile of the TF32 instance (the stash is sized for it)
 constexpr int kMaxHid = 4;   // hidden layers supported (TMEM: 128 + 3 * 128 columns)
-constexpr int kSl = 6;       // unit slices of the SIMT output layer (kSl * C * kP <= 512 threads for C <= 5)
+constexpr int kSl = 6;       // unit slices of the SIMT output layer
 
 struct FusedArgs {
   pinn_domain dom;
   const float* xs[PINN_MAX_IN];
   int64_t n_points;
-  float* stash;          // [cta][(L-1)][C][kP][128]
-  const float* wprep;    // [2*(l-2) + dir][Kq*128*4]: W_l (dir 0) / W_l^T (dir 1), TF32-rounded, K-major canonical tiles
+  float* stash;          // [cta][(L-1)][C][KP][128]
+  const float* wprep;    // [2*(l-2) + dir][Kq*128*4 (x2: hi, lo)]: W_l (dir 0) / W_l^T (dir 1), TF32-rounded, K-major canonical tiles
   float* dw_part;        // [(l-2)][n_splits][H*H]
   float* db_part;        // [(l-2)][kBlocks][8][H]
   float* first_part;     // [kBlocks][8][H]
@@ -41,23 +45,28 @@ struct FusedArgs {
   int dbl;               // two sHt buffers: h_{l-2} is prepared while the GEMMs of reverse step l run
 };
 
-struct FusedSmem {  // offsets in floats
+struct FusedSmem {  // offsets in floats; with x3 every operand buffer is [hi block][lo block], lo at + its *_lo stride
   int sW, sX, sZt, sHt, sHt2, sY, sP, sXc, sWo, sG, total;
+  int w_lo, x_lo, zt_lo, ht_lo;  // size of one block of each operand buffer (= offset of its lo block)
 };
-__host__ __device__ inline FusedSmem fused_smem(int H, int C, bool dbl) {
-  const int H8 = (H + 7) & ~7, Kq = H8 / 4, N = C * kP, N2 = (H + 15) & ~15;
+__host__ __device__ inline FusedSmem fused_smem(int H, int C, int kp, bool x3, bool dbl) {
+  const int H8 = (H + 7) & ~7, Kq = H8 / 4, N = C * kp, N2 = (H + 15) & ~15, m = x3 ? 2 : 1;
   FusedSmem s;
+  s.w_lo = Kq * 128 * 4;
+  s.x_lo = Kq * (N + 1) * 4;
+  s.zt_lo = (N / 4) * 129 * 4;
+  s.ht_lo = (N / 4) * (N2 + 1) * 4;
   int off = 0;
-  s.sW = off; off += Kq * 128 * 4;               // [Kq][128][4]      A operand: W_l or W_l^T (arrives by bulk copy)
-  s.sX = off; off += Kq * (N + 1) * 4;           // [Kq][N + 1][4]    B operand: h_{l-1} / zbar_l, K = unit
-  s.sZt = off; off += (N / 4) * 129 * 4;         // [N/4][129][4]     A operand of dW: zbar_l, K = (channel, point)
-  s.sHt = off; off += (N / 4) * (N2 + 1) * 4;    // [N/4][N2 + 1][4]  B operand of dW: h_{l-1}, K = (channel, point)
-  s.sHt2 = dbl ? off : s.sHt; off += dbl ? (N / 4) * (N2 + 1) * 4 : 0;
+  s.sW = off; off += m * s.w_lo;                 // [Kq][128][4]      A operand: W_l or W_l^T (arrives by bulk copy)
+  s.sX = off; off += m * s.x_lo;                 // [Kq][N + 1][4]    B operand: h_{l-1} / zbar_l, K = unit
+  s.sZt = off; off += m * s.zt_lo;               // [N/4][129][4]     A operand of dW: zbar_l, K = (channel, point)
+  s.sHt = off; off += m * s.ht_lo;               // [N/4][N2 + 1][4]  B operand of dW: h_{l-1}, K = (channel, point)
+  s.sHt2 = dbl ? off : s.sHt; off += dbl ? m * s.ht_lo : 0;
   s.sY = off; off += 2 * N * 4;                  // y[N][4], then ybar[N][4]
   s.sP = off; off += kSl * N * 4;                // partial sums of the output layer
-  s.sXc = off; off += kP * 4;                    // coordinates of the tile
+  s.sXc = off; off += kp * 4;                    // coordinates of the tile
   s.sWo = off; off += 4 * 128;                   // Wout[o][k]
-  s.sG = off; off += PINN_MAX_EQ * kP;           // loss seeds of the tile
+  s.sG = off; off += PINN_MAX_EQ * kp;           // loss seeds of the tile
   s.total = off;
   return s;
 }
@@ -67,19 +76,30 @@ __host__ __device__ inline FusedSmem fused_smem(int H, int C, bool dbl) {
 // 32-bit operand, so the add alone gives the tensor core the same multiplicand: 1 instruction instead of 3 (the parity
 // tests of tests/test_gpu_wide_tc.py bound the result either way)
 __device__ __forceinline__ float tf32r(float x) { return __uint_as_float(__float_as_uint(x) + 0x1000u); }
+// 3xTF32 operand split: hi = x rounded to TF32 (masked, so that lo = x - hi is exact), lo as it is (the tensor core reads
+// its upper 19 bits): dropped terms <= 2^-21 |x| per operand and lo*lo <= 2^-22 |ab|
+__device__ __forceinline__ void split3(float x, float& hi, float& lo) {
+  hi = __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xffffe000u);
+  lo = x - hi;
+}
 
-// 512 threads: thread (unit j = TMEM lane, point group g) handles the four points 4g .. 4g+3 of the tile.
-template <int NF, int NS, int ACT>
-__global__ void __launch_bounds__(512, 1) wide_fused_kernel(WNet net, const __grid_constant__ FusedArgs fa) {
+// KP * 32 threads: thread (unit j = TMEM lane, point group g) handles the four points 4g .. 4g+3 of the tile.
+template <int NF, int NS, int ACT, int KP, bool X3>
+__global__ void __launch_bounds__(KP * 32, 1) wide_fused_kernel(WNet net, const __grid_constant__ FusedArgs fa) {
   constexpr int C = 1 + NF + NS;
+  constexpr int kP = KP;
   constexpr int N = C * kP;
-  constexpr int kT = 512, G = 4;
+  // MMA N of the layer GEMMs: M = 128 wants a multiple of 16.  For N = 40 (8-point tiles, C = 5) the MMA reads eight rows
+  // past each K-quad slab of sX (the next slab's first rows / the following buffer): finite garbage into accumulator
+  // columns N .. NB-1 that nobody reads (shared memory is cleared once so that it IS finite).
+  constexpr int NB = (N + 15) & ~15;
+  constexpr int kT = KP * 32, G = KP / 4;
   const int H = net.H, L = net.L, O = net.n_out;
   const int H8 = (H + 7) & ~7, Kq = H8 / 4, N2 = (H + 15) & ~15;
   extern __shared__ __align__(128) float sm[];
   __shared__ uint64_t bar[2];  // [0]: MMA completion, [1]: weight tile landed
   __shared__ uint32_t tmem_slot;
-  const FusedSmem lay = fused_smem(H, C, fa.dbl != 0);
+  const FusedSmem lay = fused_smem(H, C, kP, X3, fa.dbl != 0);
   float* const sW = sm + lay.sW;
   float* const sX = sm + lay.sX;
   float* const sZt = sm + lay.sZt;
@@ -113,6 +133,8 @@ __global__ void __launch_bounds__(512, 1) wide_fused_kernel(WNet net, const __gr
     n_tf_s = n;
   }
   if (warp == 0) tc::tmem_alloc(&tmem_slot, 512);
+  if (NB > N || X3)  // operand rows the epilogues never write (pad rows, the lo block of h_L, what the N..NB-1 columns read)
+    for (int i = tid; i < lay.sY; i += kT) sm[i] = 0.f;  // the operand buffers only (sWo is being filled by other threads)
   for (int i = tid; i < 4 * 128; i += kT) {
     const int o = i >> 7, k = i & 127;
     sWo[i] = (o < O && k < H) ? net.W[L][o * H + k] : 0.f;
@@ -126,7 +148,7 @@ __global__ void __launch_bounds__(512, 1) wide_fused_kernel(WNet net, const __gr
   const bool wide_res = n_tf <= 128 && (fa.dom.n_terms + n_tf) * kP <= kSl * N * 4;
   uint32_t phase = 0, wphase = 0;
   // weight tiles are consumed in a fixed cyclic order per point tile: W_2 .. W_L, W_L^T .. W_2^T
-  const uint32_t wbytes = (uint32_t)(Kq * 128 * 4 * sizeof(float));
+  const uint32_t wbytes = (uint32_t)((X3 ? 2 : 1) * Kq * 128 * 4 * sizeof(float));
   const int n_seq = fa.loss_only ? (L - 1) : 2 * (L - 1);
   const int64_t n_tiles = (fa.n_points + kP - 1) / kP;
   const int64_t my_tiles = blockIdx.x < n_tiles ? (n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
@@ -171,10 +193,10 @@ __global__ void __launch_bounds__(512, 1) wide_fused_kernel(WNet net, const __gr
   const int p0 = grp * 4;
   float* const stash_t = fa.stash + (size_t)blockIdx.x * (L - 1) * C * kP * 128 + p0 * 128 + j;  // + ((l-2)*C + c)*kP*128 + pp*128
   float* const sx_t = sX + ((j >> 2) * (N + 1) + p0) * 4 + (j & 3);                              // + (c*kP + pp)*4
-  float* const szt_t = sZt + (grp * 129 + j) * 4;                                                // + c*4*129*4   (float4 = 4 points)
-  const int sht_off = (grp * (N2 + 1) + j) * 4;                                                  // + c*4*(N2+1)*4 (float4 = 4 points)
+  float* const szt_t = sZt + (grp * 129 + j) * 4;                                                // + c*G*129*4   (float4 = 4 points)
+  const int sht_off = (grp * (N2 + 1) + j) * 4;                                                  // + c*G*(N2+1)*4 (float4 = 4 points)
   const uint32_t t_acc = tmem + lane_base + p0;                                                  // + c*kP
-  const uint32_t idesc_x = tc::idesc_tf32(N, 0, 0), idesc_w = tc::idesc_tf32(N2, 0, 0);
+  const uint32_t idesc_x = tc::idesc_tf32(NB, 0, 0), idesc_w = tc::idesc_tf32(N2, 0, 0);
   bool first_tile = true;
 
   auto layer1 = [&](int p, float (&z)[C]) {
@@ -196,11 +218,32 @@ __global__ void __launch_bounds__(512, 1) wide_fused_kernel(WNet net, const __gr
     }
   };
   // h_m (TF32) of this thread's four points -> the K = (channel, point) operand buffer `dst` (one 128-bit store per channel)
+  // (X3: h arrives unrounded and is split here into the hi and lo blocks)
   auto store_ht = [&](float* dst, const float (&hq)[C][4]) {
     if (n2_ok) {
 #pragma unroll
-      for (int c = 0; c < C; ++c)
-        *reinterpret_cast<float4*>(dst + sht_off + c * 4 * (N2 + 1) * 4) = make_float4(hq[c][0], hq[c][1], hq[c][2], hq[c][3]);
+      for (int c = 0; c < C; ++c) {
+        if (X3) {
+          float hi[4], lo[4];
+#pragma unroll
+          for (int pp = 0; pp < 4; ++pp) split3(hq[c][pp], hi[pp], lo[pp]);
+          *reinterpret_cast<float4*>(dst + sht_off + c * G * (N2 + 1) * 4) = make_float4(hi[0], hi[1], hi[2], hi[3]);
+          *reinterpret_cast<float4*>(dst + lay.ht_lo + sht_off + c * G * (N2 + 1) * 4) = make_float4(lo[0], lo[1], lo[2], lo[3]);
+        } else {
+          *reinterpret_cast<float4*>(dst + sht_off + c * G * (N2 + 1) * 4) = make_float4(hq[c][0], hq[c][1], hq[c][2], hq[c][3]);
+        }
+      }
+    }
+  };
+  // one multiplicand of the layer GEMMs -> this thread's slot of sX (hi block, and lo block with X3)
+  auto store_x = [&](int c, int pp, float v) {
+    if (X3) {
+      float hi, lo;
+      split3(v, hi, lo);
+      sx_t[(c * kP + pp) * 4] = hi;
+      sx_t[lay.x_lo + (c * kP + pp) * 4] = lo;
+    } else {
+      sx_t[(c * kP + pp) * 4] = tf32r(v);
     }
   };
 
@@ -221,16 +264,35 @@ __global__ void __launch_bounds__(512, 1) wide_fused_kernel(WNet net, const __gr
       ++wphase;
       tc::tc_fence_after();
       for (int ks = 0; ks < H8 / 8; ++ks) {
-        const uint64_t da = tc::smem_desc(tc::smem_u32(sW) + ks * 2 * (128 * 16), 128 * 16, 128);
-        const uint64_t db = tc::smem_desc(tc::smem_u32(sX) + ks * 2 * ((N + 1) * 16), (N + 1) * 16, 128);
-        tc::mma_tf32(tmem, da, db, idesc_x, ks > 0 ? 1u : 0u);
+        const uint32_t oa = ks * 2 * (128 * 16), ob = ks * 2 * ((N + 1) * 16);
+        const uint64_t da = tc::smem_desc(tc::smem_u32(sW) + oa, 128 * 16, 128);
+        const uint64_t db = tc::smem_desc(tc::smem_u32(sX) + ob, (N + 1) * 16, 128);
+        if (X3) {
+          const uint64_t dal = tc::smem_desc(tc::smem_u32(sW + lay.w_lo) + oa, 128 * 16, 128);
+          const uint64_t dbl = tc::smem_desc(tc::smem_u32(sX + lay.x_lo) + ob, (N + 1) * 16, 128);
+          tc::mma_tf32(tmem, dal, db, idesc_x, ks > 0 ? 1u : 0u);
+          tc::mma_tf32(tmem, da, dbl, idesc_x, 1u);
+          tc::mma_tf32(tmem, da, db, idesc_x, 1u);
+        } else {
+          tc::mma_tf32(tmem, da, db, idesc_x, ks > 0 ? 1u : 0u);
+        }
       }
       if (with_dw) {
         const uint32_t d2 = tmem + 128 + (uint32_t)(l - 2) * 128;
         for (int ks = 0; ks < N / 8; ++ks) {
-          const uint64_t da = tc::smem_desc(tc::smem_u32(sZt) + ks * 2 * (129 * 16), 129 * 16, 128);
-          const uint64_t db = tc::smem_desc(tc::smem_u32(sHt_cur) + ks * 2 * ((N2 + 1) * 16), (N2 + 1) * 16, 128);
-          tc::mma_tf32(d2, da, db, idesc_w, (first_tile && ks == 0) ? 0u : 1u);
+          const uint32_t oa = ks * 2 * (129 * 16), ob = ks * 2 * ((N2 + 1) * 16);
+          const uint64_t da = tc::smem_desc(tc::smem_u32(sZt) + oa, 129 * 16, 128);
+          const uint64_t db = tc::smem_desc(tc::smem_u32(sHt_cur) + ob, (N2 + 1) * 16, 128);
+          const uint32_t acc0 = (first_tile && ks == 0) ? 0u : 1u;
+          if (X3) {
+            const uint64_t dal = tc::smem_desc(tc::smem_u32(sZt + lay.zt_lo) + oa, 129 * 16, 128);
+            const uint64_t dbl = tc::smem_desc(tc::smem_u32(sHt_cur + lay.ht_lo) + ob, (N2 + 1) * 16, 128);
+            tc::mma_tf32(d2, dal, db, idesc_w, acc0);
+            tc::mma_tf32(d2, da, dbl, idesc_w, 1u);
+            tc::mma_tf32(d2, da, db, idesc_w, 1u);
+          } else {
+            tc::mma_tf32(d2, da, db, idesc_w, acc0);
+          }
         }
       }
       tc::mma_commit(&bar[0]);
@@ -259,11 +321,11 @@ __global__ void __launch_bounds__(512, 1) wide_fused_kernel(WNet net, const __gr
       for (int pp = 0; pp < 4; ++pp) {
         float z[C], h[C];
         layer1(p0 + pp, z);
-        jet_fwd_t<ACT, NF, NS, true>(z, h);
+        jet_fwd_t<ACT, NF, NS, !X3>(z, h);
 #pragma unroll
         for (int c = 0; c < C; ++c) {
-          hq[c][pp] = tf32r(h[c]);
-          if (k_ok) sx_t[(c * kP + pp) * 4] = hq[c][pp];
+          hq[c][pp] = X3 ? h[c] : tf32r(h[c]);
+          if (k_ok) store_x(c, pp, h[c]);
         }
       }
       if (L == 2 && !fa.loss_only) store_ht(sm + lay.sHt, hq);
@@ -292,11 +354,14 @@ __global__ void __launch_bounds__(512, 1) wide_fused_kernel(WNet net, const __gr
         zk[0][pp] += bias;
 #pragma unroll
         for (int c = 0; c < C; ++c) z[c] = zk[c][pp];
-        jet_fwd_t<ACT, NF, NS, true>(z, h);
+        jet_fwd_t<ACT, NF, NS, !X3>(z, h);
 #pragma unroll
         for (int c = 0; c < C; ++c) {
-          hq[c][pp] = tf32r(h[c]);
-          if (k_ok) sx_t[(c * kP + pp) * 4] = (l == L) ? h[c] : hq[c][pp];  // h_L stays FP32 for the SIMT output layer
+          hq[c][pp] = X3 ? h[c] : tf32r(h[c]);
+          if (k_ok) {
+            if (l == L) sx_t[(c * kP + pp) * 4] = h[c];  // h_L stays FP32 for the SIMT output layer
+            else store_x(c, pp, h[c]);
+          }
         }
       }
       if (l == L - 1 && !fa.loss_only) store_ht(sm + lay.sHt, hq);  // h_{L-1}: B operand of dW_L, first reverse step
@@ -345,7 +410,7 @@ __global__ void __launch_bounds__(512, 1) wide_fused_kernel(WNet net, const __gr
     float* const sPt = sP + fa.dom.n_terms * kP;         // [n_tf][kP]
     if (wide_res) {
       for (int item = tid; item < fa.dom.n_terms * kP; item += kT) {
-        const int p = item & (kP - 1), t = item >> 4;
+        const int p = item % kP, t = item / kP;
         const pinn_term& tm = fa.dom.terms[t];
         float prod = tm.coef;
         for (int f = 0; f < tm.n_fac; ++f) prod *= sym_at(tm.fac[f], p);
@@ -354,7 +419,7 @@ __global__ void __launch_bounds__(512, 1) wide_fused_kernel(WNet net, const __gr
       __syncthreads();
     }
     if (tid < kP * PINN_MAX_EQ) {
-      const int p = tid & (kP - 1), e = tid >> 4;
+      const int p = tid % kP, e = tid / kP;
       const int64_t ng = n0 + p;
       float g = 0.f;
       if (e < fa.dom.n_eq && ng < fa.n_points) {
@@ -387,7 +452,7 @@ __global__ void __launch_bounds__(512, 1) wide_fused_kernel(WNet net, const __gr
     if (fa.loss_only) continue;  // (uniform: every thread leaves together)
     if (wide_res) {
       for (int item = tid; item < n_tf * kP; item += kT) {
-        const int p = item & (kP - 1), i = item >> 4;
+        const int p = item % kP, i = item / kP;
         const int t = tf_t[i], f = tf_f[i];
         const pinn_term& tm = fa.dom.terms[t];
         int e = 0;
@@ -399,7 +464,7 @@ __global__ void __launch_bounds__(512, 1) wide_fused_kernel(WNet net, const __gr
       }
       __syncthreads();
       for (int item = tid; item < C * 4 * kP; item += kT) {
-        const int p = item & (kP - 1), id = item >> 4;
+        const int p = item % kP, id = item / kP;
         float acc = 0.f;
         for (int i = 0; i < n_tf; ++i)
           if (fa.dom.terms[tf_t[i]].fac[tf_f[i]] == id) acc += sPt[i * kP + p];
@@ -408,7 +473,7 @@ __global__ void __launch_bounds__(512, 1) wide_fused_kernel(WNet net, const __gr
       }
     } else {
       for (int item = tid; item < C * 4 * kP; item += kT) {
-        const int p = item & (kP - 1), id = item >> 4;
+        const int p = item % kP, id = item / kP;
         float acc = 0.f;
         for (int e = 0; e < fa.dom.n_eq; ++e) {
           const float g = sG[e * kP + p];
@@ -460,7 +525,7 @@ __global__ void __launch_bounds__(512, 1) wide_fused_kernel(WNet net, const __gr
         for (int c = 0; c < C; ++c) z[c] = zl[c][pp];
         if (l == L) {
           float h[C];
-          jet_fwd_t<ACT, NF, NS, true>(z, h);  // h_L for dWout
+          jet_fwd_t<ACT, NF, NS, !X3>(z, h);  // h_L for dWout
 #pragma unroll
           for (int c = 0; c < C; ++c) {
             const float4 t = *reinterpret_cast<const float4*>(sYb + (c * kP + p) * 4);
@@ -475,7 +540,7 @@ __global__ void __launch_bounds__(512, 1) wide_fused_kernel(WNet net, const __gr
         }
 #pragma unroll
         for (int c = 0; c < C; ++c) zb[c] = 0.f;
-        jet_bwd_t<ACT, NF, NS, true>(z, hb, zb);
+        jet_bwd_t<ACT, NF, NS, !X3>(z, hb, zb);
         if (l == 1) g_b[0] += zb[0];
         else if (l == 2) g_b[1] += zb[0];
         else if (l == 3) g_b[2] += zb[0];
@@ -494,24 +559,33 @@ __global__ void __launch_bounds__(512, 1) wide_fused_kernel(WNet net, const __gr
         } else {
 #pragma unroll
           for (int c = 0; c < C; ++c) {
-            zq[c][pp] = tf32r(zb[c]);
-            if (k_ok) sx_t[(c * kP + pp) * 4] = zq[c][pp];
+            zq[c][pp] = X3 ? zb[c] : tf32r(zb[c]);
+            if (k_ok) store_x(c, pp, zb[c]);
           }
         }
       }
       if (l >= 2) {
 #pragma unroll
-        for (int c = 0; c < C; ++c)
-          *reinterpret_cast<float4*>(szt_t + c * 4 * 129 * 4) = make_float4(zq[c][0], zq[c][1], zq[c][2], zq[c][3]);
+        for (int c = 0; c < C; ++c) {
+          if (X3) {
+            float hi[4], lo[4];
+#pragma unroll
+            for (int pp = 0; pp < 4; ++pp) split3(zq[c][pp], hi[pp], lo[pp]);
+            *reinterpret_cast<float4*>(szt_t + c * G * 129 * 4) = make_float4(hi[0], hi[1], hi[2], hi[3]);
+            *reinterpret_cast<float4*>(szt_t + lay.zt_lo + c * G * 129 * 4) = make_float4(lo[0], lo[1], lo[2], lo[3]);
+          } else {
+            *reinterpret_cast<float4*>(szt_t + c * G * 129 * 4) = make_float4(zq[c][0], zq[c][1], zq[c][2], zq[c][3]);
+          }
+        }
         if (!fa.dbl && l < L) {  // single sHt buffer: h_{l-1} now (the GEMMs of step l + 1 have completed)
           float hq[C][4];
 #pragma unroll
           for (int pp = 0; pp < 4; ++pp) {
             float z[C], h[C];
             load_z(l - 1, pp, z);
-            jet_fwd_t<ACT, NF, NS, true>(z, h);
+            jet_fwd_t<ACT, NF, NS, !X3>(z, h);
 #pragma unroll
-            for (int c = 0; c < C; ++c) hq[c][pp] = tf32r(h[c]);
+            for (int c = 0; c < C; ++c) hq[c][pp] = X3 ? h[c] : tf32r(h[c]);
           }
           store_ht(sm + lay.sHt, hq);
         }
@@ -523,9 +597,9 @@ __global__ void __launch_bounds__(512, 1) wide_fused_kernel(WNet net, const __gr
           for (int pp = 0; pp < 4; ++pp) {
             float z[C], h[C];
             load_z(l - 2, pp, z);
-            jet_fwd_t<ACT, NF, NS, true>(z, h);
+            jet_fwd_t<ACT, NF, NS, !X3>(z, h);
 #pragma unroll
-            for (int c = 0; c < C; ++c) hq[c][pp] = tf32r(h[c]);
+            for (int c = 0; c < C; ++c) hq[c][pp] = X3 ? h[c] : tf32r(h[c]);
           }
           buf ^= 1;
           store_ht(sm + (buf ? lay.sHt2 : lay.sHt), hq);
@@ -543,8 +617,8 @@ __global__ void __launch_bounds__(512, 1) wide_fused_kernel(WNet net, const __gr
     // TMEM row = unit j (one per lane), 16 columns k per load; a 32 x 17 shared-memory tile per warp turns the
     // read-modify-write of dw_part[j][k] into row segments of 16 consecutive floats (two rows per warp access)
     // instead of 32 scattered words (the flush was 7 % of the kernel's stall samples, half of a boundary launch)
-    float* tile = sW + warp * (32 * 17);  // sW and sX (adjacent) are free now; tiny nets that cannot hold 16 tiles write directly
-    const bool use_tile = 16 * 32 * 17 <= Kq * 128 * 4 + Kq * (N + 1) * 4;
+    float* tile = sW + warp * (32 * 17);  // sW and sX (adjacent) are free now; tiny nets that cannot hold a tile per warp write directly
+    const bool use_tile = (kT / 32) * 32 * 17 <= lay.sZt - lay.sW;
     for (int l = 2; l <= L; ++l) {
       float* out = fa.dw_part + ((size_t)(l - 2) * fa.n_splits + blockIdx.x) * H * H;
       for (int g = grp; g < N2 / 16; g += G) {
@@ -617,42 +691,55 @@ __global__ void __launch_bounds__(512, 1) wide_fused_kernel(WNet net, const __gr
 }  // namespace
 
 // W (row-major [H][H]) -> K-major canonical tile [Kq][128][4], TF32-rounded, zero padded;
-// transpose != 0 stores W^T (rows = input units of the layer, K = its output units)
-__global__ void prep_weights_kernel(const float* __restrict__ W, int H, int Kq, float* __restrict__ out, int transpose) {
+// transpose != 0 stores W^T (rows = input units of the layer, K = its output units); x3: the hi tile is followed by the
+// residual tile lo = W - hi
+__global__ void prep_weights_kernel(const float* __restrict__ W, int H, int Kq, float* __restrict__ out, int transpose, int x3) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= Kq * 128 * 4) return;
   const int e = i & 3, row = (i >> 2) & 127, kq = i >> 9;
   const int k = kq * 4 + e;
   float v = 0.f;
-  if (row < H && k < H) v = tc::to_tf32(transpose ? W[(size_t)k * H + row] : W[(size_t)row * H + k]);
-  out[i] = v;
+  if (row < H && k < H) v = transpose ? W[(size_t)k * H + row] : W[(size_t)row * H + k];
+  const float hi = tc::to_tf32(v);
+  out[i] = hi;
+  if (x3) out[Kq * 128 * 4 + i] = v - hi;
 }
 
 int fused_wide_prep(const WNet& n, float* wprep, cudaStream_t st) {
+  const int x3 = n.precision == 2 ? 1 : 0;
   const int Kq = ((n.H + 7) & ~7) / 4, tile = Kq * 128 * 4;
   for (int l = 2; l <= n.L; ++l)
     for (int dir = 0; dir < 2; ++dir) {
-      prep_weights_kernel<<<(tile + 255) / 256, 256, 0, st>>>(n.W[l - 1], n.H, Kq, wprep + (size_t)(2 * (l - 2) + dir) * tile, dir);
+      prep_weights_kernel<<<(tile + 255) / 256, 256, 0, st>>>(n.W[l - 1], n.H, Kq, wprep + (size_t)(2 * (l - 2) + dir) * tile * (1 + x3), dir, x3);
       count_launch(1);
     }
   return (int)cudaGetLastError();
 }
 
-int64_t fused_wide_wprep_floats(const WNet& n) { return (int64_t)2 * (n.L - 1) * (((n.H + 7) & ~7) / 4) * 128 * 4; }
+// (sized for the 3xTF32 instance: hi + lo tiles)
+int64_t fused_wide_wprep_floats(const WNet& n) { return (int64_t)2 * 2 * (n.L - 1) * (((n.H + 7) & ~7) / 4) * 128 * 4; }
 
-static bool fused_fits(const WNet& n, bool dbl) {
-  const int N = n.C * kP;
-  const FusedSmem lay = fused_smem(n.H, n.C, dbl);
-  (void)N;
-  return (size_t)lay.total * 4 <= 226 * 1024 && 3 * 12 * 128 <= (((n.H + 7) & ~7) / 4) * 128 * 4;
+static bool fused_fits_kp(const WNet& n, int kp, bool dbl) {
+  const FusedSmem lay = fused_smem(n.H, n.C, kp, n.precision == 2, dbl);
+  // (the reductions of the flush reuse sW: (G - 1) * 12 * 128 floats; the dW GEMM contracts over N = C * kp in steps of 8)
+  return (size_t)lay.total * 4 <= 226 * 1024 && (kp / 4 - 1) * 12 * 128 <= lay.sZt - lay.sW && (n.C * kp) % 8 == 0;
 }
 
+// tile size of the instance that serves this net: TF32 -> 16-point tiles; FP32-grade (3xTF32, doubled operand buffers) ->
+// 8-point tiles, or 4-point tiles where only those fit (H = 128)
+static int fused_kp(const WNet& n) {
+  if (n.precision != 2) return kPMax;
+  return fused_fits_kp(n, 8, false) ? 8 : 4;
+}
+
+static bool fused_fits(const WNet& n, bool dbl) { return fused_fits_kp(n, fused_kp(n), dbl); }
+
 bool fused_wide_supported(const WNet& n) {
-  if (n.precision != 1 || n.H > 128 || n.L < 2 || n.L > kMaxHid || n.n_in > 4) return false;
+  if ((n.precision != 1 && n.precision != 2) || n.H > 128 || n.L < 2 || n.L > kMaxHid || n.n_in > 4) return false;
   return fused_fits(n, false);
 }
 
-int64_t fused_wide_stash_floats(const WNet& n) { return (int64_t)kBlocks * (n.L - 1) * n.C * kP * 128; }
+int64_t fused_wide_stash_floats(const WNet& n) { return (int64_t)kBlocks * (n.L - 1) * n.C * kPMax * 128; }
 
 template <int ACT>
 int fused_wide_launch(const WNet& n, const pinn_domain* dom, float* stash, const float* wt_base, float* dw_part, float* db_part,
@@ -672,22 +759,31 @@ int fused_wide_launch(const WNet& n, const pinn_domain* dom, float* stash, const
   fa.n_splits = n_splits;
   if (n_splits < kBlocks) return PINN_E_UNSUPPORTED;
   fa.dbl = fused_fits(n, true) ? 1 : 0;
-  const size_t smem = (size_t)fused_smem(n.H, n.C, fa.dbl != 0).total * sizeof(float);
-  const int64_t tiles = (dom->n_points + kP - 1) / kP;
+  const int kp = fused_kp(n);
+  const bool x3 = n.precision == 2;
+  const size_t smem = (size_t)fused_smem(n.H, n.C, kp, x3, fa.dbl != 0).total * sizeof(float);
+  const int64_t tiles = (dom->n_points + kp - 1) / kp;
   int grid = tiles < kBlocks ? (int)tiles : kBlocks;
   if (grid < 1) return 0;
-#define CASE(NF_, NS_)                                                                                                 \
-  if (n.NF == NF_ && n.NS == NS_) {                                                                                   \
-    cudaError_t e = cudaFuncSetAttribute((const void*)wide_fused_kernel<NF_, NS_, ACT>,                                \
+#define LAUNCH(NF_, NS_, KP_, X3_)                                                                                    \
+  {                                                                                                                   \
+    cudaError_t e = cudaFuncSetAttribute((const void*)wide_fused_kernel<NF_, NS_, ACT, KP_, X3_>,                      \
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);                      \
     if (e != cudaSuccess) return (int)e;                                                                               \
-    wide_fused_kernel<NF_, NS_, ACT><<<grid, 512, smem, st>>>(n, fa);                                                  \
+    wide_fused_kernel<NF_, NS_, ACT, KP_, X3_><<<grid, KP_ * 32, smem, st>>>(n, fa);                                   \
     launched = true;                                                                                                   \
+  }
+#define CASE(NF_, NS_)                                                                                                 \
+  if (n.NF == NF_ && n.NS == NS_) {                                                                                   \
+    if (x3 && kp == 8) LAUNCH(NF_, NS_, 8, true)                                                                      \
+    else if (x3) LAUNCH(NF_, NS_, 4, true)                                                                            \
+    else LAUNCH(NF_, NS_, kPMax, false)                                                                               \
   }
   bool launched = false;
   CASE(0, 0) CASE(1, 0) CASE(1, 1) CASE(2, 0) CASE(2, 1) CASE(2, 2) CASE(3, 0) CASE(3, 1) CASE(3, 2) CASE(3, 3)
   if (!launched) return PINN_E_UNSUPPORTED;
 #undef CASE
+#undef LAUNCH
   count_launch(1);
   return (int)cudaGetLastError();
 }

@@ -10,7 +10,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 KEYS = ["UTCHMMA", "UTCQMMA", "LDTM", "STTM", "UTCBAR", "UBLKCP", "UTMALDG", "UTMASTG", "UTCATOMSWS", "SYNCS", "FFMA2", "FFMA", "HMMA",
         "MUFU.TANH", "MUFU.EX2", "MUFU.RCP", "LDS.128", "STS.128", "LDG", "STG", "RED", "ATOM"]
 print("SASS mnemonic counts per object (cuobjdump -sass, sm_100a).  UTCHMMA = tcgen05.mma kind::tf32/f16, LDTM/STTM = tcgen05.ld/st,")
-print("UTCBAR = tcgen05.commit, UBLKCP = cp.async.bulk (TMA engine, 1-D), FFMA2 = fma.rn.f32x2; no HMMA (legacy mma.sync) anywhere.\n")
+print("UTCBAR = tcgen05.commit, UBLKCP = cp.async.bulk (TMA engine, 1-D), FFMA2 = fma.rn.f32x2, HMMA = mma.sync.m16n8k8 TF32 (the per-warp dW contraction of the packed narrow program, 3xTF32).\n")
 print(f"{'object':28s}" + "".join(f"{k:>10s}" for k in KEYS))
 for obj in sorted(glob.glob(os.path.join(ROOT, "idrlnet_b200", "csrc", "build", "*.o"))):
     sass = subprocess.run(["cuobjdump", "-sass", obj], capture_output=True, text=True).stdout
