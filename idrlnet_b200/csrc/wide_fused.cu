@@ -726,11 +726,9 @@ static bool fused_fits_kp(const WNet& n, int kp, bool dbl) {
 }
 
 // tile size of the instance that serves this net: TF32 -> 16-point tiles; FP32-grade (3xTF32, doubled operand buffers) ->
-// 8-point tiles, or 4-point tiles where only those fit (H = 128)
-static int fused_kp(const WNet& n) {
-  if (n.precision != 2) return kPMax;
-  return fused_fits_kp(n, 8, false) ? 8 : 4;
-}
+// 8-point tiles.  (A 4-point instance fits H = 128 -- 186 KB -- but measured SLOWER than the layer-streamed 3xTF32 kernels
+// on allen_cahn, 2.28e7 vs 2.60e7 points/s, so such nets stay on the streamed path.)
+static int fused_kp(const WNet& n) { return n.precision == 2 ? 8 : kPMax; }
 
 static bool fused_fits(const WNet& n, bool dbl) { return fused_fits_kp(n, fused_kp(n), dbl); }
 
@@ -775,8 +773,7 @@ int fused_wide_launch(const WNet& n, const pinn_domain* dom, float* stash, const
   }
 #define CASE(NF_, NS_)                                                                                                 \
   if (n.NF == NF_ && n.NS == NS_) {                                                                                   \
-    if (x3 && kp == 8) LAUNCH(NF_, NS_, 8, true)                                                                      \
-    else if (x3) LAUNCH(NF_, NS_, 4, true)                                                                            \
+    if (x3) LAUNCH(NF_, NS_, 8, true)                                                                                 \
     else LAUNCH(NF_, NS_, kPMax, false)                                                                               \
   }
   bool launched = false;
