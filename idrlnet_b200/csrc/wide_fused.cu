@@ -65,7 +65,7 @@ __host__ __device__ inline FusedSmem fused_smem(int H, int C, int kp, bool x3, b
   s.sY = off; off += 2 * N * 4;                  // y[N][4], then ybar[N][4]
   s.sP = off; off += kSl * N * 4;                // partial sums of the output layer
   s.sXc = off; off += kp * 4;                    // coordinates of the tile
-  s.sWo = off; off += 4 * 128;                   // Wout[o][k]
+  s.sWo = off; off += 4 * 128;                   // Wout as [k][4 outputs]: one 128-bit load per unit
   s.sG = off; off += PINN_MAX_EQ * kp;           // loss seeds of the tile
   s.total = off;
   return s;
@@ -136,7 +136,7 @@ __global__ void __launch_bounds__(KP * 32, 1) wide_fused_kernel(WNet net, const 
   if (NB > N || X3)  // operand rows the epilogues never write (pad rows, the lo block of h_L, what the N..NB-1 columns read)
     for (int i = tid; i < lay.sY; i += kT) sm[i] = 0.f;  // the operand buffers only (sWo is being filled by other threads)
   for (int i = tid; i < 4 * 128; i += kT) {
-    const int o = i >> 7, k = i & 127;
+    const int o = i & 3, k = i >> 2;
     sWo[i] = (o < O && k < H) ? net.W[L][o * H + k] : 0.f;
   }
   tc::tc_fence_before();
@@ -384,8 +384,8 @@ __global__ void __launch_bounds__(KP * 32, 1) wide_fused_kernel(WNet net, const 
         float y[4] = {0.f, 0.f, 0.f, 0.f};
         for (int k = k0; k < k1; ++k) {
           const float hv = sX[((k >> 2) * (N + 1) + q) * 4 + (k & 3)];
-#pragma unroll
-          for (int o = 0; o < 4; ++o) y[o] += sWo[o * 128 + k] * hv;
+          const float4 w = *reinterpret_cast<const float4*>(sWo + k * 4);  // warp-uniform: one broadcast load
+          y[0] += w.x * hv; y[1] += w.y * hv; y[2] += w.z * hv; y[3] += w.w * hv;
         }
         *reinterpret_cast<float4*>(sP + (sl * N + q) * 4) = make_float4(y[0], y[1], y[2], y[3]);
       }
@@ -511,8 +511,8 @@ __global__ void __launch_bounds__(KP * 32, 1) wide_fused_kernel(WNet net, const 
       }
       float wo[4];
       if (l == L) {
-#pragma unroll
-        for (int o = 0; o < 4; ++o) wo[o] = sWo[o * 128 + j];
+        const float4 w = *reinterpret_cast<const float4*>(sWo + j * 4);
+        wo[0] = w.x; wo[1] = w.y; wo[2] = w.z; wo[3] = w.w;
       } else {
         wait_mma();
       }
