@@ -191,7 +191,8 @@ __global__ void __launch_bounds__(KP * 32, 1) wide_fused_kernel(WNet net, const 
 
   // per-thread bases: every element this thread touches is base + a compile-time offset (c, pp)
   const int p0 = grp * 4;
-  float* const stash_t = fa.stash + (size_t)blockIdx.x * (L - 1) * C * kP * 128 + p0 * 128 + j;  // + ((l-2)*C + c)*kP*128 + pp*128
+  // stash [(l-2)][c][point group][unit j][4 points]: the four points of a thread are one 128-bit access per channel
+  float* const stash_t = fa.stash + (size_t)blockIdx.x * (L - 1) * C * kP * 128 + (grp * 128 + j) * 4;  // + ((l-2)*C + c)*kP*128
   float* const sx_t = sX + ((j >> 2) * (N + 1) + p0) * 4 + (j & 3);                              // + (c*kP + pp)*4
   float* const szt_t = sZt + (grp * 129 + j) * 4;                                                // + c*G*129*4   (float4 = 4 points)
   const int sht_off = (grp * (N2 + 1) + j) * 4;                                                  // + c*G*(N2+1)*4 (float4 = 4 points)
@@ -207,14 +208,23 @@ __global__ void __launch_bounds__(KP * 32, 1) wide_fused_kernel(WNet net, const 
 #pragma unroll
     for (int s = 0; s < NS; ++s) z[1 + NF + s] = 0.f;
   };
-  // z_m of this thread's point pp: from the stash (m >= 2) or recomputed (m == 1)
-  auto load_z = [&](int m, int pp, float (&z)[C]) {
+  // z_m of this thread's four points: from the stash (m >= 2) or recomputed (m == 1)
+  auto load_z4 = [&](int m, float (&z4)[C][4]) {
     if (m >= 2) {
-      const float* sp = stash_t + (size_t)(m - 2) * C * kP * 128 + pp * 128;
+      const float* sp = stash_t + (size_t)(m - 2) * C * kP * 128;
 #pragma unroll
-      for (int c = 0; c < C; ++c) z[c] = sp[c * kP * 128];
+      for (int c = 0; c < C; ++c) {
+        const float4 v = *reinterpret_cast<const float4*>(sp + c * kP * 128);
+        z4[c][0] = v.x; z4[c][1] = v.y; z4[c][2] = v.z; z4[c][3] = v.w;
+      }
     } else {
-      layer1(p0 + pp, z);
+#pragma unroll
+      for (int pp = 0; pp < 4; ++pp) {
+        float z[C];
+        layer1(p0 + pp, z);
+#pragma unroll
+        for (int c = 0; c < C; ++c) z4[c][pp] = z[c];
+      }
     }
   };
   // h_m (TF32) of this thread's four points -> the K = (channel, point) operand buffer `dst` (one 128-bit store per channel)
@@ -339,8 +349,7 @@ __global__ void __launch_bounds__(KP * 32, 1) wide_fused_kernel(WNet net, const 
         float* sp = stash_t + (size_t)(l - 3) * C * kP * 128;
 #pragma unroll
         for (int c = 0; c < C; ++c)
-#pragma unroll
-          for (int pp = 0; pp < 4; ++pp) sp[c * kP * 128 + pp * 128] = zk[c][pp];
+          *reinterpret_cast<float4*>(sp + c * kP * 128) = make_float4(zk[c][0], zk[c][1], zk[c][2], zk[c][3]);
       }
       wait_mma();
 #pragma unroll
@@ -371,8 +380,7 @@ __global__ void __launch_bounds__(KP * 32, 1) wide_fused_kernel(WNet net, const 
       float* sp = stash_t + (size_t)(L - 2) * C * kP * 128;
 #pragma unroll
       for (int c = 0; c < C; ++c)
-#pragma unroll
-        for (int pp = 0; pp < 4; ++pp) sp[c * kP * 128 + pp * 128] = zk[c][pp];
+        *reinterpret_cast<float4*>(sp + c * kP * 128) = make_float4(zk[c][0], zk[c][1], zk[c][2], zk[c][3]);
     }
     __syncthreads();
     // ---- output layer (FP32 SIMT, h_L in FP32): partial sums over kSl slices of the units, then a short reduction ----
@@ -502,13 +510,7 @@ __global__ void __launch_bounds__(KP * 32, 1) wide_fused_kernel(WNet net, const 
     int buf = 0;
     for (int l = L; l >= 1; --l) {
       float zl[C][4];  // z_l of the four points (stash reads do not depend on the tensor cores: issued before the wait)
-#pragma unroll
-      for (int pp = 0; pp < 4; ++pp) {
-        float z[C];
-        load_z(l, pp, z);
-#pragma unroll
-        for (int c = 0; c < C; ++c) zl[c][pp] = z[c];
-      }
+      load_z4(l, zl);
       float wo[4];
       if (l == L) {
         const float4 w = *reinterpret_cast<const float4*>(sWo + j * 4);
@@ -578,11 +580,13 @@ __global__ void __launch_bounds__(KP * 32, 1) wide_fused_kernel(WNet net, const 
           }
         }
         if (!fa.dbl && l < L) {  // single sHt buffer: h_{l-1} now (the GEMMs of step l + 1 have completed)
-          float hq[C][4];
+          float hq[C][4], z4[C][4];
+          load_z4(l - 1, z4);
 #pragma unroll
           for (int pp = 0; pp < 4; ++pp) {
             float z[C], h[C];
-            load_z(l - 1, pp, z);
+#pragma unroll
+            for (int c = 0; c < C; ++c) z[c] = z4[c][pp];
             jet_fwd_t<ACT, NF, NS, !X3>(z, h);
 #pragma unroll
             for (int c = 0; c < C; ++c) hq[c][pp] = X3 ? h[c] : tf32r(h[c]);
@@ -592,11 +596,13 @@ __global__ void __launch_bounds__(KP * 32, 1) wide_fused_kernel(WNet net, const 
         tc::tc_fence_before();
         issue_mma(true, l, sm + (buf ? lay.sHt2 : lay.sHt));
         if (fa.dbl && l >= 3) {  // h_{l-2}, the dW operand of the NEXT step, in the shadow of this step's GEMMs
-          float hq[C][4];
+          float hq[C][4], z4[C][4];
+          load_z4(l - 2, z4);
 #pragma unroll
           for (int pp = 0; pp < 4; ++pp) {
             float z[C], h[C];
-            load_z(l - 2, pp, z);
+#pragma unroll
+            for (int c = 0; c < C; ++c) z[c] = z4[c][pp];
             jet_fwd_t<ACT, NF, NS, !X3>(z, h);
 #pragma unroll
             for (int c = 0; c < C; ++c) hq[c][pp] = X3 ? h[c] : tf32r(h[c]);
