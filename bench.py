@@ -569,6 +569,11 @@ def run_ours(args):
     roof = roofline_of(run, kern_ms, fp32_peak, tf32_peak, pk["hbm_gbs"], pk_src)
     head_sizes, head_rot, head_bytes, head_fused = run.sizes, run.n_rotate, run.batch_bytes, run.fused_domains
     head_pts = run.points_per_step
+    head_allreduce = None
+    if world > 1:
+        fused_in_finalize = all(getattr(e, "_peers", None) is not None for e in run.solver._engines.values())
+        head_allreduce = ("summed over the ranks' symmetric memory inside the finalize kernel (pinn_step_finalize_allreduce)"
+                          if fused_in_finalize and run.solver._engines else "NCCL all_reduce after finalize")
     run.close()
 
     # ---- the other BASELINE configurations at their stated sizes -------------------------------------------
@@ -630,7 +635,7 @@ def run_ours(args):
                        "net": f"{cfg['net_desc']}, Adam 1e-3 + ExponentialLR",
                        "api": "idrlnet_b200.Solver.train_pipe() (post_step_loss=False: one evaluation per step, the strict step "
                               "of idrlnet/solver.py:329-339)", "fused_domains": head_fused,
-                       "points_per_step_per_gpu": head_pts, "parallelism": f"dp{world} (points sharded, 1 all-reduce)",
+                       "points_per_step_per_gpu": head_pts, "parallelism": f"dp{world} (points sharded, 1 all-reduce)", "allreduce": head_allreduce,
                        "l2": f"{head_rot} rotating point batches ({head_rot * head_bytes / 1e6:.0f} MB > 126 MB L2)"},
             "roofline": roof, "cpu_baseline": cpu,
             "e2e": {"value": e2e_value, "unit": "points/s", "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 4},

@@ -178,6 +178,76 @@ __global__ void finalize_kernel(const float* gpart, const float* lpart, int max_
   }
 }
 
+// finalize_kernel fused with a one-shot all-reduce over the peers' symmetric regions (include/pinn_b200.h).
+// Region layout (floats): data[2 sets][world][n_total_pad], then flags (uint32) [2 sets][world][n_blocks].
+struct PeerTable {
+  float* base[PINN_MAX_RANKS];
+  int rank, world;
+  uint32_t epoch;
+  int n_total_pad, n_blocks;
+};
+__host__ __device__ inline int64_t peer_flags_off(int world, int n_total_pad) { return (int64_t)2 * world * n_total_pad; }
+
+__global__ void finalize_allreduce_kernel(const float* gpart, const float* lpart, int max_cta, int PP, int n_in, int n_out,
+                                          int Hreal, int Hp, int L, int64_t n_params, int n_dom, PeerTable pt, float* out) {
+  __shared__ float red[8][33];
+  const int il = threadIdx.x & 31, cg = threadIdx.x >> 5;
+  const int64_t i = (int64_t)blockIdx.x * 32 + il;
+  float s = 0.f;
+  if (i < n_params) {
+    const Layout lay(Hp, L);
+    const int idx = flat_to_layout(n_in, n_out, Hreal, lay, i);
+    for (int c = cg; c < max_cta; c += 8) s += gpart[(size_t)c * PP + idx];
+  }
+  red[cg][il] = s;
+  __syncthreads();
+  const int set = (int)(pt.epoch & 1u);
+  const size_t slot_mine = ((size_t)set * pt.world + pt.rank) * pt.n_total_pad;
+  if (cg == 0 && i < n_params) {
+    float t = 0.f;
+#pragma unroll
+    for (int g = 0; g < 8; ++g) t += red[g][il];
+    for (int r = 0; r < pt.world; ++r) pt.base[r][slot_mine + i] = t;  // 128-byte row segments into every peer (and self)
+  }
+  if (blockIdx.x == 0 && cg == 1 && il < n_dom) {  // (a second warp: the losses ride in the same buffer, after the gradient)
+    float t = 0.f;
+    for (int c = 0; c < max_cta; ++c) t += lpart[(size_t)il * max_cta + c];
+    for (int r = 0; r < pt.world; ++r) pt.base[r][slot_mine + n_params + il] = t;
+  }
+  __threadfence_system();
+  __syncthreads();
+  const int64_t foff = peer_flags_off(pt.world, pt.n_total_pad);
+  if (threadIdx.x < pt.world) {
+    const int r = threadIdx.x;
+    // publish: "block b of rank `rank` has written its values into your region"
+    uint32_t* theirs = reinterpret_cast<uint32_t*>(pt.base[r] + foff) + ((size_t)set * pt.world + pt.rank) * pt.n_blocks + blockIdx.x;
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(theirs), "r"(pt.epoch) : "memory");
+    // wait for the same block of rank r
+    const uint32_t* mine = reinterpret_cast<const uint32_t*>(pt.base[pt.rank] + foff) + ((size_t)set * pt.world + r) * pt.n_blocks + blockIdx.x;
+    const long long t0 = clock64();
+    uint32_t v;
+    do {
+      asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(mine) : "memory");
+      if (v != pt.epoch) {
+        if (clock64() - t0 > 120000000000ll) __trap();  // ~60 s: a rank is missing; fail instead of hanging
+        if (clock64() - t0 > 200000ll) __nanosleep(200);  // a late peer (host-side skew): stop hammering the link
+      }
+    } while (v != pt.epoch);
+  }
+  __syncthreads();
+  const float* local = pt.base[pt.rank] + (size_t)set * pt.world * pt.n_total_pad;
+  if (cg == 0 && i < n_params) {
+    float t = 0.f;
+    for (int r = 0; r < pt.world; ++r) t += __ldcg(local + (size_t)r * pt.n_total_pad + i);  // rank order: the same sum everywhere
+    out[i] = t;
+  }
+  if (blockIdx.x == 0 && cg == 1 && il < n_dom) {
+    float t = 0.f;
+    for (int r = 0; r < pt.world; ++r) t += __ldcg(local + (size_t)r * pt.n_total_pad + n_params + il);
+    out[n_params + il] = t;
+  }
+}
+
 static int launch_narrow(const pinn_mlp* m, const pinn_jets* j, NarrowParams& p, const NarrowPlan& pl, cudaStream_t st) {
   static std::mutex mu;
   {
@@ -342,6 +412,54 @@ int pinn_step_finalize(const pinn_mlp* m, const pinn_jets* j, void* ws, int64_t 
   }
   if (wide_supported(m, j)) return wide_step_finalize(m, j, ws, ws_bytes, n_domains, flat_grad, add_to_grad, losses, st);
   return fail(PINN_E_UNSUPPORTED, "no fused kernel for width %d", m->width);
+}
+
+static int peer_geometry(const pinn_mlp* m, int n_domains, int* n_total_pad, int* n_blocks) {
+  const int64_t np = pinn_param_count(m);
+  if (np + n_domains > (1 << 20)) return 0;  // small gradients only: the latency-bound case this exists for
+  *n_total_pad = (int)((np + n_domains + 31) / 32 * 32);
+  *n_blocks = (int)((np + 31) / 32);
+  return 1;
+}
+
+int64_t pinn_allreduce_region_bytes(const pinn_mlp* m, const pinn_jets* j, int32_t n_domains, int32_t world) {
+  if (!m || !j || world < 2 || world > PINN_MAX_RANKS || n_domains < 1 || n_domains > 32) return 0;
+  if (!narrow_lookup(m, j)) return 0;  // wide nets: the all-reduce is 1e-3 of their step; they keep the library collective
+  int ntp, nb;
+  if (!peer_geometry(m, n_domains, &ntp, &nb)) return 0;
+  return (peer_flags_off(world, ntp) + (int64_t)2 * world * nb) * 4;
+}
+
+int pinn_step_finalize_allreduce(const pinn_mlp* m, const pinn_jets* j, void* ws, int64_t ws_bytes, int32_t n_domains,
+                                 float* out, const pinn_peers* peers, void* stream) {
+  int rc = check_mlp(m, j);
+  if (rc) return rc;
+  if (!out || !peers) return fail(PINN_E_INVALID, "null out / peers");
+  if (peers->world < 2 || peers->world > PINN_MAX_RANKS || peers->rank < 0 || peers->rank >= peers->world || peers->epoch == 0)
+    return fail(PINN_E_INVALID, "peers: rank %d of %d, epoch %u", peers->rank, peers->world, peers->epoch);
+  if (n_domains < 1 || n_domains > 32) return fail(PINN_E_INVALID, "n_domains=%d", n_domains);
+  if (!narrow_lookup(m, j)) return fail(PINN_E_UNSUPPORTED, "finalize + all-reduce exists for narrow nets only");
+  NarrowPlan pl;
+  rc = narrow_plan(m, j, &pl, true);
+  if (rc) return rc;
+  PeerTable pt;
+  memset(&pt, 0, sizeof(pt));
+  if (!peer_geometry(m, n_domains, &pt.n_total_pad, &pt.n_blocks)) return fail(PINN_E_UNSUPPORTED, "gradient too large");
+  for (int r = 0; r < peers->world; ++r) {
+    if (!peers->base[r]) return fail(PINN_E_INVALID, "peers->base[%d] is null", r);
+    pt.base[r] = (float*)peers->base[r];
+  }
+  pt.rank = peers->rank; pt.world = peers->world; pt.epoch = peers->epoch;
+  const int64_t gbytes = (int64_t)kMaxCta * pl.PP * 4;
+  if (!ws || ws_bytes < pl.head_bytes(n_domains)) return fail(PINN_E_WORKSPACE, "workspace too small");
+  const int64_t np = pinn_param_count(m);
+  finalize_allreduce_kernel<<<pt.n_blocks, 256, 0, (cudaStream_t)stream>>>(
+      (const float*)ws, (const float*)((char*)ws + gbytes), kMaxCta, pl.PP, m->n_in, m->n_out, m->width, pl.Hp, pl.L, np,
+      n_domains, pt, out);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return cuda_fail(e, "finalize + all-reduce launch");
+  count_launch(1);
+  return 0;
 }
 
 int pinn_jet_forward(const pinn_mlp* m, const pinn_jets* j, int64_t n_points, const float* const* coords, float* out,

@@ -444,6 +444,48 @@ class StepEngine:
         self._last = self.flat
         self._sigma_vals = [d.sigma for d in self.domains]
         self.sigmas = torch.tensor(self._sigma_vals, device=pack.device, dtype=torch.float32)
+        # multi-GPU: finalize + all-reduce as ONE kernel over the ranks' symmetric memory (enable_peer_allreduce)
+        self._peers: Optional[nv.PinnPeers] = None
+        self._peer_keep = None
+        self.reduced = False  # the most recent launch already summed `flat` over the ranks
+
+    def enable_peer_allreduce(self) -> bool:
+        """Under torch.distributed (NCCL, one node): let pinn_step_finalize_allreduce produce the gradient summed over the
+        ranks -- the reduction kernel writes its values into every peer's symmetric region over NVLink, signals, waits
+        and adds in rank order -- instead of pinn_step_finalize followed by an NCCL all-reduce of 6 KB.  COLLECTIVE: every
+        rank must call it at the same point.  Returns False (and keeps the NCCL path) for wide nets, other backends or when
+        symmetric memory is unavailable on any rank."""
+        import torch.distributed as dist
+        if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() < 2 or dist.get_backend() != "nccl":
+            return False
+        world, rank = dist.get_world_size(), dist.get_rank()
+        lib = nv.lib()
+        self.pack.refresh_effective()
+        mlp = self.pack.mlp_struct()
+        nbytes = int(lib.pinn_allreduce_region_bytes(C.byref(mlp), C.byref(self.domains[0].jets), len(self.domains), world))
+        ok, region, hdl = nbytes > 0, None, None
+        if ok:
+            try:
+                import torch.distributed._symmetric_memory as symm
+                region = symm.empty(nbytes // 4, dtype=torch.float32, device=self.pack.device)
+                region.zero_()
+                hdl = symm.rendezvous(region, dist.group.WORLD)
+                ok = len(hdl.buffer_ptrs) == world and hdl.rank == rank
+            except Exception as e:  # no symmetric memory on this system: the NCCL path stays
+                import logging
+                logging.getLogger("idrlnet_b200").info("peer all-reduce unavailable (%s); using NCCL", e)
+                ok = False
+        flag = torch.tensor([1 if ok else 0], device=self.pack.device, dtype=torch.int32)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)  # all ranks or none (also: everyone's zeros are in place)
+        torch.cuda.synchronize()
+        if int(flag.item()) != 1:
+            return False
+        peers = nv.PinnPeers()
+        peers.rank, peers.world, peers.epoch = rank, world, 0
+        for r in range(world):
+            peers.base[r] = int(hdl.buffer_ptrs[r])
+        self._peers, self._peer_keep = peers, (region, hdl)
+        return True
 
     def set_domains(self, domains: Sequence[FusedDomain]) -> None:
         """Swap in another binding of the same domains (fresh points); domain weights are re-read."""
@@ -486,6 +528,13 @@ class StepEngine:
         else:
             out = self.flat
         self._last = out
+        if self._peers is not None and not loss_only:
+            self._peers.epoch += 1
+            nv.check(lib.pinn_step_finalize_allreduce(C.byref(mlp), C.byref(self.domains[0].jets), self.ws.data_ptr(),
+                                                      self.ws_bytes, len(self.domains), out.data_ptr(), C.byref(self._peers), st))
+            self.reduced = True
+            return
+        self.reduced = False
         nv.check(lib.pinn_step_finalize(C.byref(mlp), C.byref(self.domains[0].jets), self.ws.data_ptr(), self.ws_bytes,
                                         len(self.domains), out.data_ptr(), 0, out.data_ptr() + 4 * pack.n_params, st))
 

@@ -78,6 +78,15 @@ def make_jets(first_in: Sequence[int], n_second: int, n_mixed: int = 0, n_high: 
     return j
 
 
+MAX_RANKS = 16
+
+
+class PinnPeers(C.Structure):
+    """pinn_peers (include/pinn_b200.h)."""
+    _fields_ = [("rank", C.c_int32), ("world", C.c_int32), ("epoch", C.c_uint32), ("reserved", C.c_int32),
+                ("base", C.c_void_p * MAX_RANKS)]
+
+
 class PinnWnLayer(C.Structure):
     """pinn_wn_layer (include/pinn_b200.h)."""
     _fields_ = [("g", C.c_void_p), ("v", C.c_void_p), ("dW", C.c_void_p), ("W", C.c_void_p), ("dg", C.c_void_p),
@@ -124,6 +133,9 @@ _SIGNATURES = {
                                   C.c_int64, C.c_int32, C.c_int32, C.c_void_p]),
     "pinn_step_finalize": (C.c_int, [C.POINTER(PinnMlp), C.POINTER(PinnJets), C.c_void_p, C.c_int64, C.c_int32,
                                      C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]),
+    "pinn_allreduce_region_bytes": (C.c_int64, [C.POINTER(PinnMlp), C.POINTER(PinnJets), C.c_int32, C.c_int32]),
+    "pinn_step_finalize_allreduce": (C.c_int, [C.POINTER(PinnMlp), C.POINTER(PinnJets), C.c_void_p, C.c_int64, C.c_int32,
+                                               C.c_void_p, C.POINTER(PinnPeers), C.c_void_p]),
     "pinn_jet_forward": (C.c_int, [C.POINTER(PinnMlp), C.POINTER(PinnJets), C.c_int64, C.POINTER(_fp), C.c_void_p,
                                    C.c_void_p, C.c_int64, C.c_void_p]),
     "pinn_jet_backward": (C.c_int, [C.POINTER(PinnMlp), C.POINTER(PinnJets), C.c_int64, C.POINTER(_fp), C.c_void_p,

@@ -363,7 +363,7 @@ class Solver(Notifier, Optimizable):
                         break
             with _Range("fused_step"):
                 eng.launch(loss_only=not grads, timed=timed)  # the post-update re-evaluation needs no reverse pass
-            if dist is not None:
+            if dist is not None and not eng.reduced:  # (narrow nets: finalize already summed over the ranks)
                 with _Range("all_reduce"):
                     dist.all_reduce(eng.flat if grads else eng.losses)
             for fd, l in zip(eng.domains, eng.losses):
@@ -432,6 +432,8 @@ class Solver(Notifier, Optimizable):
                 eng = fused.StepEngine(self._packs[key], fds)
                 eng._sig = sig
                 self._engines[key] = eng
+                if _dist() is not None and os.environ.get("IDRLNET_B200_PEER_ALLREDUCE", "1") != "0":
+                    eng.enable_peer_allreduce()  # collective; every rank builds the same engines in the same order
             else:
                 eng.set_domains(fds)
             engines.append(eng)

@@ -188,6 +188,28 @@ PINN_API int pinn_step_finalize(const pinn_mlp* mlp, const pinn_jets* jets, void
                        int64_t workspace_bytes, int32_t n_domains, float* flat_grad,
                        int32_t add_to_grad, float* losses, void* stream);
 
+/* ---- finalize + all-reduce over peer memory (one kernel) --------------- */
+/* Multi-GPU step of a NARROW net: the deterministic reduction of pinn_step_finalize fused with the SUM over the ranks
+ * of one NVLink / NVSwitch box, so that no collective launch sits between the step kernels and the optimizer.  Replaces
+ * pinn_step_finalize followed by torch.distributed.all_reduce(flat) (idrlnet has no multi-GPU path; the all-reduce is
+ * the one SURVEY.md 8(e) prescribes).  Every rank passes the same `peers` table: base[r] is rank r's symmetric region
+ * (pinn_allreduce_region_bytes bytes, zero-initialised once, mapped into this process -- e.g. the buffer_ptrs of a
+ * torch.distributed._symmetric_memory rendezvous).  Each block of the kernel writes its 32 reduced values into slot
+ * `rank` of every peer's region, publishes a per-block flag (st.release.sys), waits for the same block of every rank
+ * (ld.acquire.sys, bounded: traps after ~60 s instead of hanging) and adds the `world` slots in rank order -- bitwise the
+ * same sum on every rank.  `epoch` must increase by one per call on every rank, starting at 1 (slots and flags are
+ * double-buffered on its parity).  out[n_params + n_domains] = all-reduced gradient, then the all-reduced losses. */
+#define PINN_MAX_RANKS 16
+typedef struct pinn_peers {
+  int32_t rank, world;
+  uint32_t epoch;
+  int32_t reserved;
+  void* base[PINN_MAX_RANKS];
+} pinn_peers;
+PINN_API int64_t pinn_allreduce_region_bytes(const pinn_mlp* mlp, const pinn_jets* jets, int32_t n_domains, int32_t world);
+PINN_API int pinn_step_finalize_allreduce(const pinn_mlp* mlp, const pinn_jets* jets, void* workspace, int64_t workspace_bytes,
+                                 int32_t n_domains, float* out, const pinn_peers* peers, void* stream);
+
 /* ---- the generic path (residual evaluated by the caller) --------------- */
 /* Jets only: out[(c*n_out + o)*N + n] = channel c of output o at point n.
  * Replaces WrapEvaluate + Variables.differentiate_ for names such as u__x__x
