@@ -34,6 +34,19 @@ __device__ __forceinline__ bool mbar_wait(uint64_t* bar, uint32_t parity) {
   return false;
 }
 
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+// 16-byte asynchronous copy global -> shared (LDGSTS, L2 only); src_bytes = 0 fills the 16 bytes with zeros (the
+// source address is not dereferenced then, but must be a valid pointer)
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, uint32_t src_bytes) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
 // 1-D bulk asynchronous copy global -> shared (TMA engine, no tensor map): `bytes` (multiple of 16)
 // land at `dst` and are accounted on `bar` (which must expect them)
 __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
@@ -43,6 +56,22 @@ __device__ __forceinline__ void bulk_copy_g2s(void* dst, const void* src, uint32
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
                "l"(src), "r"(bytes), "r"(smem_u32(bar))
                : "memory");
+}
+
+// TMA tiled tensor copies global -> shared (tensor map = a __grid_constant__ CUtensorMap kernel parameter): the box lands at
+// `dst` (1024-byte aligned for SWIZZLE_128B) and its full size is accounted on `bar`; out-of-bounds elements arrive as zeros
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const void* tmap, int c0, int c1, uint64_t* bar) {
+  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(dst),
+               "l"(tmap), "r"(c0), "r"(c1), "r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const void* tmap, int c0, int c1, int c2, uint64_t* bar) {
+  asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];" ::"r"(dst),
+               "l"(tmap), "r"(c0), "r"(c1), "r"(c2), "r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_desc(const void* tmap) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(tmap) : "memory");
 }
 
 // generic-proxy smem writes -> visible to the async proxy (tensor core reads)
@@ -113,6 +142,20 @@ __device__ __forceinline__ uint64_t smem_desc(uint32_t saddr, uint32_t lbo_bytes
   d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32;
   d |= (uint64_t)1 << 46;  // descriptor version (Blackwell)
   return d;                // base offset 0, LBO mode 0, layout type 0 (no swizzle)
+}
+
+// K-major operand in the 128-byte-swizzled layout a TMA box with a 128-byte inner extent produces (CU_TENSOR_MAP_SWIZZLE_128B):
+// row r of the tile is the 128 bytes at r * 128, its 16-byte chunks XOR-permuted by (r % 8); 8-row groups are 1024 bytes
+// apart (SBO).  One MMA consumes K = 8 TF32 = 32 bytes of every row: the K step inside the 128-byte row is selected by adding
+// ks * 32 bytes to the start address (the hardware applies the swizzle to the final address).  LBO is unused in this form.
+__device__ __forceinline__ uint64_t smem_desc_sw128(uint32_t saddr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3FFFFu) >> 4);
+  d |= (uint64_t)1 << 16;
+  d |= (uint64_t)(1024 >> 4) << 32;
+  d |= (uint64_t)1 << 46;  // descriptor version (Blackwell)
+  d |= (uint64_t)2 << 61;  // layout type: SWIZZLE_128B
+  return d;
 }
 
 // Instruction descriptor, kind::tf32, FP32 accumulate, M = 128.

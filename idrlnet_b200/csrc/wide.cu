@@ -42,6 +42,12 @@ namespace {
   } while (0)
 
 // ---- first layer ------------------------------------------------------------
+__device__ __forceinline__ float tf32_rna(float x) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+  return __uint_as_float(r);
+}
+
 struct Coords {
   const float* p[PINN_MAX_IN];
 };
@@ -60,9 +66,10 @@ __global__ void first_fwd_kernel(WNet net, Coords xs, int64_t n0, int m, int Mc,
   for (int s = 0; s < net.NS; ++s) z[1 + net.NF + s] = 0.f;
   jet_fwd<ACT>(net.NF, net.NS, z, h);
   const size_t plane = (size_t)Mc * H;
+  const bool round = net.precision == 1 && net.L >= 2;  // TF32 mode: H_1 is a tensor-core operand, stored rounded
   for (int c = 0; c < net.C; ++c) {
     Z[c * plane + (size_t)n * H + j] = z[c];
-    Hb[c * plane + (size_t)n * H + j] = h[c];
+    Hb[c * plane + (size_t)n * H + j] = round ? tf32_rna(h[c]) : h[c];
   }
 }
 
@@ -451,6 +458,7 @@ __global__ void __launch_bounds__(1024) head_bwd_kernel(WNet net, const float* _
   const int per = (m + gridDim.y - 1) / gridDim.y;
   const int nb = blockIdx.y * per, ne = (nb + per < m) ? nb + per : m;
   float gW[4] = {0.f, 0.f, 0.f, 0.f};
+  const bool round = net.precision == 1 && net.L >= 2;  // TF32 mode: zbar_L is a tensor-core operand, stored rounded
   if (j < H) {
     float wo[4];
 #pragma unroll
@@ -483,7 +491,7 @@ __global__ void __launch_bounds__(1024) head_bwd_kernel(WNet net, const float* _
         jet_bwd<ACT>(net.NF, net.NS, z[u], hb, zb);
         if (nn < ne) {
 #pragma unroll
-          for (int c = 0; c < C; ++c) ZL[c * plane + (size_t)nn * H + j] = zb[c];
+          for (int c = 0; c < C; ++c) ZL[c * plane + (size_t)nn * H + j] = round ? tf32_rna(zb[c]) : zb[c];
         }
       }
     }
@@ -506,7 +514,7 @@ __global__ void __launch_bounds__(1024) head_bwd_kernel(WNet net, const float* _
 struct WideLayout {  // workspace offsets in floats
   int64_t Z, Hb;            // L planes-sets each: [l][C][Mc][H]
   int64_t dw, db, first, head, loss_slots, acc_end, total;
-  int64_t wt, wprep, ybar, tdw;  // tdw: re-tiled operands of the pipelined TF32 dW GEMM
+  int64_t wt, wprep, wr, ybar, tdw;  // tdw: re-tiled operands of the pipelined TF32 dW GEMM; wr: tf32(W_l) (TF32 mode)
   int Mc, n_splits, fp32_splits, tiles, n_dom;
 };
 
@@ -619,6 +627,7 @@ WideLayout make_layout(const WNet& n, int n_dom) {
   // W_l^T for the streamed tensor-core reverse GEMM, then the prepared weight tiles of the on-chip kernel
   wl.wt = off; off += ((int64_t)(n.L - 1) * n.H * n.H + 3) / 4 * 4;
   wl.wprep = off; off += (n.H <= 128) ? (fused_wide_wprep_floats(n) + 3) / 4 * 4 : 0;
+  wl.wr = off; off += (n.precision == 1) ? ((int64_t)(n.L - 1) * n.H * n.H + 3) / 4 * 4 : 0;
   wl.acc_end = off;
   wl.Z = off; off += planes;
   wl.Hb = off; off += planes;
@@ -653,6 +662,9 @@ int run_chunks(const WNet& n, const WideLayout& wl, float* ws, int mode, const p
                const float* const* coords, float* jets_out, const float* jets_bar, cudaStream_t st) {
   const int H = n.H, C = n.C, L = n.L;
   const size_t planes = (size_t)C * wl.Mc * H;
+  // TF32 mode: the operands of the tensor-core GEMMs (H_1 .. H_{L-1}, zbar_L .. zbar_2, the weight copies) are stored
+  // rounded by their producers; H_L (output layer) and zbar_1 (first-layer gradient) stay FP32 (wide_tc.cu)
+  const bool tf32 = n.precision == 1;
   Coords xs;
   for (int d = 0; d < PINN_MAX_IN; ++d) xs.p[d] = d < n.n_in ? coords[d] : nullptr;
   for (int64_t n0 = 0; n0 < N; n0 += wl.Mc) {
@@ -666,8 +678,8 @@ int run_chunks(const WNet& n, const WideLayout& wl, float* ws, int mode, const p
     }
     for (int l = 2; l <= L; ++l) {
       int rc = n.precision
-                   ? tc_launch_rows<ACT, 0>(n, Hb + (l - 2) * planes, n.W[l - 1], n.b[l - 1], Z + (l - 1) * planes,
-                                            Hb + (l - 1) * planes, m, wl.Mc, st)
+                   ? tc_launch_rows<ACT, 0>(n, Hb + (l - 2) * planes, tf32 ? ws + wl.wr + (size_t)(l - 2) * H * H : n.W[l - 1],
+                                            n.b[l - 1], Z + (l - 1) * planes, Hb + (l - 1) * planes, m, wl.Mc, tf32 && l < L, st)
                    : launch_gemm_rows<ACT, true, 0>(n, Hb + (l - 2) * planes, n.W[l - 1], n.b[l - 1], Z + (l - 1) * planes,
                                                     Hb + (l - 1) * planes, m, wl.Mc, st);
       if (rc) return rc;
@@ -732,7 +744,7 @@ int run_chunks(const WNet& n, const WideLayout& wl, float* ws, int mode, const p
       }
       int rc = n.precision
                    ? tc_launch_rows<ACT, 1>(n, zb, ws + wl.wt + (size_t)(l - 2) * H * H, nullptr, Z + (l - 2) * planes, nullptr,
-                                            m, wl.Mc, st)
+                                            m, wl.Mc, tf32 && l > 2, st)
                    : launch_gemm_rows<ACT, false, 1>(n, zb, n.W[l - 1], nullptr, Z + (l - 2) * planes, nullptr, m, wl.Mc, st);
       if (rc) return rc;
     }
@@ -774,7 +786,12 @@ int run_mode(const pinn_mlp* m, const pinn_jets* j, int mode, const pinn_domain*
   const bool prep = !accumulate || !stepping;
   if (n.precision && mode != W_MODE_FWD && mode != W_MODE_LOSS && prep)
     for (int l = 2; l <= n.L; ++l) {
-      rc = tc_transpose(n.W[l - 1], w + wl.wt + (size_t)(l - 2) * n.H * n.H, n.H, st);
+      rc = tc_transpose(n.W[l - 1], w + wl.wt + (size_t)(l - 2) * n.H * n.H, n.H, n.precision == 1, st);
+      if (rc) return rc;
+    }
+  if (n.precision == 1 && prep)
+    for (int l = 2; l <= n.L; ++l) {
+      rc = tc_round_copy(n.W[l - 1], w + wl.wr + (size_t)(l - 2) * n.H * n.H, n.H * n.H, st);
       if (rc) return rc;
     }
   // (prepared whenever ANY domain of this net could take the on-chip kernel: whether one does depends on its channel

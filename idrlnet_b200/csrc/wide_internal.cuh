@@ -168,12 +168,13 @@ int fused_wide_launch(const WNet& n, const pinn_domain* dom, float* stash, const
 // tensor-core GEMMs (wide_tc.cu)
 template <int ACT, int EPI>
 int tc_launch_rows(const WNet& n, const float* Bsrc, const float* Aw, const float* bias, float* Zio, float* Hout, int m, int Mc,
-                   cudaStream_t st);
+                   bool round_out, cudaStream_t st);
 int tc_dw_splits(int H);
 int tc_rows_points(int C);  // points per tile of the row GEMMs
 int64_t tc_dw2_scratch_floats(int H, int C, int Mc, bool x3);
 int tc_launch_dw2(const float* Zb, const float* Hb, int H, int C, int m, int Mc, float* part, int n_splits, float* scratch,
                   float* db_slot, bool x3, cudaStream_t st);
-int tc_transpose(const float* W, float* WT, int H, cudaStream_t st);
+int tc_transpose(const float* W, float* WT, int H, bool round, cudaStream_t st);
+int tc_round_copy(const float* W, float* Wr, int n, cudaStream_t st);  // Wr = tf32(W)
 
 }  // namespace pinn

@@ -17,8 +17,10 @@
 // overlap each other's phases.  Inputs are FP32 in memory; only the multiplicands are rounded (10-bit
 // mantissa, or hi + lo pairs in 3xTF32 mode), sums are FP32.  Stated tolerance of the TF32 mode 1e-2
 // norm-wise (tests/test_gpu_wide_tc.py); the 3xTF32 mode is held to the FP32 bar (tests/test_gpu_wide.py).
+#include <cuda.h>
 #include <cuda_runtime.h>
 #include <stdio.h>
+#include <stdlib.h>
 
 #include "tc_common.cuh"
 #include "wide_internal.cuh"
@@ -60,10 +62,95 @@ __device__ __forceinline__ void issue_chunk(uint32_t tmem, uint32_t sA, uint32_t
   }
 }
 
+__device__ __forceinline__ void release_tmem(uint64_t* bar, int lane) {
+  tc::tc_fence_before();
+  __syncwarp();
+  if (lane == 0) tc::mbar_arrive(bar);
+}
+
+// Epilogue of one (P points, 128 units) accumulator tile: lane = hidden unit; the 16-point groups alternate between the two
+// warp quads (warp = 0..7).  round_out: the values that are operands of a later tensor-core GEMM (H_l, zbar_l) are stored
+// already rounded to TF32 (cvt.rna, the rounding the staging code applies), so that tc_rows2_kernel can copy them into shared
+// memory asynchronously without touching them.  release: mbarrier to arrive on (one lane per warp) as soon as this warp
+// has read its last accumulator columns (tc_rows2_kernel: the tensor core may overwrite the buffer).
+template <int C, int ACT, int EPI>
+__device__ __forceinline__ void rows_epilogue(const WNet& net, uint32_t tmem, int warp, int lane, int n0, int j0, int m, size_t plane,
+                                              int a_rows, const float* __restrict__ bias, float* __restrict__ Zio,
+                                              float* __restrict__ Hout, bool round_out, uint64_t* release) {
+  using T = TileCfg<C>;
+  constexpr int P = T::P;
+  const int H = net.H;
+  const int j = j0 + (warp & 3) * 32 + lane;
+  const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
+  const float bj = (EPI != 1 && j < a_rows) ? bias[j] : 0.f;
+  for (int g = warp >> 2; g < P / 16; g += 2) {
+    float v[C][16];
+#pragma unroll
+    for (int c = 0; c < C; ++c) tc::tmem_ld16(tmem + lane_base + c * P + g * 16, v[c]);
+    if (EPI == 1) {
+      // reverse layer: Z_{l-1} is fetched 4 points ahead (double-buffered registers) so the global
+      // loads of the next quad are in flight while the current quad's adjoints are computed
+      float zin[2][C][4];
+      auto fetch = [&](int quad, float (&dst)[C][4]) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int n = n0 + g * 16 + quad * 4 + i;
+#pragma unroll
+          for (int c = 0; c < C; ++c) dst[c][i] = (j < H && n < m) ? Zio[c * plane + (size_t)n * H + j] : 0.f;
+        }
+      };
+      fetch(0, zin[0]);
+      tc::tmem_ld_wait();
+      if (release != nullptr && g + 2 >= P / 16) release_tmem(release, lane);
+#pragma unroll
+      for (int quad = 0; quad < 4; ++quad) {
+        if (quad + 1 < 4) fetch(quad + 1, zin[(quad + 1) & 1]);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int n = n0 + g * 16 + quad * 4 + i;
+          float a[kMaxC] = {}, b[kMaxC] = {}, o[kMaxC] = {};
+#pragma unroll
+          for (int c = 0; c < C; ++c) {
+            a[c] = v[c][quad * 4 + i];
+            b[c] = zin[quad & 1][c][i];
+            o[c] = 0.f;
+          }
+          jet_bwd<ACT>(net.NF, net.NS, b, a, o);
+          if (j < H && n < m) {
+#pragma unroll
+            for (int c = 0; c < C; ++c) Zio[c * plane + (size_t)n * H + j] = round_out ? tc::to_tf32(o[c]) : o[c];
+          }
+        }
+      }
+    } else {
+      tc::tmem_ld_wait();
+      if (release != nullptr && g + 2 >= P / 16) release_tmem(release, lane);
+      if (j < a_rows) {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          const int n = n0 + g * 16 + i;
+          if (n < m) {
+            float a[kMaxC] = {}, o[kMaxC] = {};
+#pragma unroll
+            for (int c = 0; c < C; ++c) a[c] = v[c][i];
+            a[0] += bj;
+            jet_fwd<ACT>(net.NF, net.NS, a, o);
+#pragma unroll
+            for (int c = 0; c < C; ++c) {
+              Zio[c * plane + (size_t)n * H + j] = a[c];
+              Hout[c * plane + (size_t)n * H + j] = round_out ? tc::to_tf32(o[c]) : o[c];
+            }
+          }
+        }
+      }
+    }
+  }
+}
+
 template <int C, int ACT, int EPI, bool X3>
 __global__ void __launch_bounds__(256, 2) tc_rows_kernel(WNet net, const float* __restrict__ Bsrc, const float* __restrict__ Aw,
                                                       const float* __restrict__ bias, float* __restrict__ Zio,
-                                                      float* __restrict__ Hout, int m, int Mc, int a_rows) {
+                                                      float* __restrict__ Hout, int m, int Mc, int a_rows, int round_out) {
   using T = TileCfg<C>;
   constexpr int P = T::P, N = T::N;
   constexpr int kKT = X3 ? 32 : 64;  // K elements per smem stage
@@ -139,76 +226,139 @@ __global__ void __launch_bounds__(256, 2) tc_rows_kernel(WNet net, const float* 
   if (!ok) __trap();
   tc::tc_fence_after();
 
-  // epilogue: lane = hidden unit; 16-point groups alternate between the two warp quads
-  const int j = j0 + (warp & 3) * 32 + lane;
-  const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
-  const float bj = (EPI != 1 && j < a_rows) ? bias[j] : 0.f;
-  for (int g = warp >> 2; g < P / 16; g += 2) {
-    float v[C][16];
-#pragma unroll
-    for (int c = 0; c < C; ++c) tc::tmem_ld16(tmem + lane_base + c * P + g * 16, v[c]);
-    if (EPI == 1) {
-      // reverse layer: Z_{l-1} is fetched 4 points ahead (double-buffered registers) so the global
-      // loads of the next quad are in flight while the current quad's adjoints are computed
-      float zin[2][C][4];
-      auto fetch = [&](int quad, float (&dst)[C][4]) {
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const int n = n0 + g * 16 + quad * 4 + i;
-#pragma unroll
-          for (int c = 0; c < C; ++c) dst[c][i] = (j < H && n < m) ? Zio[c * plane + (size_t)n * H + j] : 0.f;
-        }
-      };
-      fetch(0, zin[0]);
-      tc::tmem_ld_wait();
-#pragma unroll
-      for (int quad = 0; quad < 4; ++quad) {
-        if (quad + 1 < 4) fetch(quad + 1, zin[(quad + 1) & 1]);
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const int n = n0 + g * 16 + quad * 4 + i;
-          float a[kMaxC] = {}, b[kMaxC] = {}, o[kMaxC] = {};
-#pragma unroll
-          for (int c = 0; c < C; ++c) {
-            a[c] = v[c][quad * 4 + i];
-            b[c] = zin[quad & 1][c][i];
-            o[c] = 0.f;
-          }
-          jet_bwd<ACT>(net.NF, net.NS, b, a, o);
-          if (j < H && n < m) {
-#pragma unroll
-            for (int c = 0; c < C; ++c) Zio[c * plane + (size_t)n * H + j] = o[c];
-          }
-        }
-      }
-    } else {
-      tc::tmem_ld_wait();
-      if (j < a_rows) {
-#pragma unroll
-        for (int i = 0; i < 16; ++i) {
-          const int n = n0 + g * 16 + i;
-          if (n < m) {
-            float a[kMaxC] = {}, o[kMaxC] = {};
-#pragma unroll
-            for (int c = 0; c < C; ++c) a[c] = v[c][i];
-            a[0] += bj;
-            jet_fwd<ACT>(net.NF, net.NS, a, o);
-#pragma unroll
-            for (int c = 0; c < C; ++c) {
-              Zio[c * plane + (size_t)n * H + j] = a[c];
-              Hout[c * plane + (size_t)n * H + j] = o[c];
-            }
-          }
-        }
-      }
-    }
-  }
+  rows_epilogue<C, ACT, EPI>(net, tmem, warp, lane, n0, j0, m, plane, a_rows, bias, Zio, Hout, round_out != 0, nullptr);
   tc::tc_fence_before();
   __syncthreads();
   if (warp == 0) tc::tmem_dealloc(tmem, 256);
 }
 
-__global__ void transpose_kernel(const float* __restrict__ W, float* __restrict__ WT, int H) {
+// ---- TF32 mode: persistent, warp-specialised row GEMM fed by TMA --------------------------------------------------
+// tc_rows_kernel above spends nine tenths of a CTA's life outside the tensor core (profiles/r02/ncu_tc_rows_ns_xl.txt:
+// a serial load -> convert -> store -> MMA -> wait chain per K chunk on ONE shared-memory stage, then an epilogue during
+// which nothing is loaded; only the second CTA of the SM overlaps it).  In TF32 mode every GEMM operand is stored ALREADY
+// ROUNDED by its producer (first_fwd_kernel, head_bwd_kernel, the epilogues here with round_out, the per-step weight
+// copies), so staging is a pure copy and the TMA engine can do it: one persistent CTA per SM, 10 warps --
+//   warp 8      one thread: per K chunk of 32 two tensor copies (cp.async.bulk.tensor, 128-byte-swizzled boxes: weights
+//               {32 k, 128 units} from a 2-D map, jets {32 k, P points, C channels} from a 3-D map over the [c][n][k] planes;
+//               out-of-range rows / k arrive as zeros) into a 4/5-stage ring, accounted on full[s] by expect_tx;
+//   warp 9      one thread issues tcgen05.mma on SWIZZLE_128B K-major descriptors and releases stages (tcgen05.commit ->
+//               empty[s]) and accumulators;
+//   warps 0-7   epilogue of tile i (rows_epilogue) from one of TWO accumulator buffers in TMEM (columns 0 and 256),
+//               while the copies and the tensor core already work on tile i+1.
+// Tiles (point tile, unit tile) are dealt round-robin with the unit tile fastest, so the CTAs that share a point tile's
+// B rows run at the same time (L2 hits).  Same products on the same rounded operands as tc_rows_kernel<.., false>.
+// (A first version staged with 16-byte cp.async from two loader warps: 1.26x SLOWER than tc_rows_kernel -- 22 GB/s per SM,
+// twice the L2 -> SM bytes of the tile (sector-granular 16-byte requests), experiments/tc_rows2_cpasync.cu.txt.)
+template <int C>
+struct Rows2Cfg {
+  static constexpr int N = TileCfg<C>::N;
+  static constexpr int kKT = 32;
+  static constexpr int kABytes = 128 * 128, kBBytes = N * 128, kStageBytes = kABytes + kBBytes;  // multiples of 1024
+  static constexpr int kStages = (N >= 224) ? 4 : 5;  // 4 x 48 KB (N = 256) / 5 x 40 KB (N = 192)
+  static constexpr int kSmemBytes = kStages * kStageBytes + 1024;  // + alignment slack
+};
+
+template <int C, int ACT, int EPI>
+__global__ void __launch_bounds__(320, 1) tc_rows2_kernel(WNet net, const __grid_constant__ CUtensorMap tmA,
+                                                          const __grid_constant__ CUtensorMap tmB, const float* __restrict__ bias,
+                                                          float* __restrict__ Zio, float* __restrict__ Hout, int m, int Mc, int a_rows,
+                                                          int tiles_j, int n_tiles, int round_out, int dbg) {
+  using T = TileCfg<C>;
+  using R = Rows2Cfg<C>;
+  constexpr int P = T::P, N = T::N, S = R::kStages, KT = R::kKT;
+  const int H = net.H;
+  extern __shared__ __align__(1024) uint8_t sm_raw[];
+  __shared__ uint64_t full[S], empty[S], acc_full[2], acc_empty[2];
+  __shared__ uint32_t tmem_slot;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const size_t plane = (size_t)Mc * H;
+  const int nch = (H + KT - 1) / KT;
+  const uint32_t ring = (tc::smem_u32(sm_raw) + 1023u) & ~1023u;
+  if (tid == 0) {
+    for (int s = 0; s < S; ++s) {
+      tc::mbar_init(&full[s], 1);
+      tc::mbar_init(&empty[s], 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      tc::mbar_init(&acc_full[a], 1);
+      tc::mbar_init(&acc_empty[a], 8);
+    }
+    tc::fence_mbar_init();
+  }
+  if (warp == 9) tc::tmem_alloc(&tmem_slot, 512);
+  tc::tc_fence_before();
+  __syncthreads();
+  tc::tc_fence_after();
+  const uint32_t tmem = tmem_slot;
+  if (warp < 8) {  // ---- epilogue warps
+    int ti = 0;
+    for (int t = blockIdx.x; t < n_tiles; t += gridDim.x, ++ti) {
+      const int a = ti & 1;
+      if (!tc::mbar_wait(&acc_full[a], (ti >> 1) & 1)) __trap();
+      tc::tc_fence_after();
+      if (dbg & 4) {
+        release_tmem(&acc_empty[a], lane);
+        continue;
+      }
+      rows_epilogue<C, ACT, EPI>(net, tmem + a * 256, warp, lane, (t / tiles_j) * P, (t % tiles_j) * 128, m, plane, a_rows, bias,
+                                 Zio, Hout, round_out != 0, &acc_empty[a]);
+    }
+  } else if (warp == 8) {  // ---- TMA producer
+    if (lane == 0) {
+      tc::tma_prefetch_desc(&tmA);
+      tc::tma_prefetch_desc(&tmB);
+      int it = 0;
+      for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+        const int n0 = (t / tiles_j) * P, j0 = (t % tiles_j) * 128;
+        for (int ch = 0; ch < nch; ++ch, ++it) {
+          const int s = it % S;
+          if (it >= S && !tc::mbar_wait(&empty[s], ((it / S) - 1) & 1)) __trap();
+          const uint32_t sA = ring + (uint32_t)s * R::kStageBytes, sB = sA + R::kABytes;
+          tc::mbar_expect_tx(&full[s], (uint32_t)R::kStageBytes);
+          if (dbg & 2) {  // (timing experiment: no copies)
+            asm volatile("mbarrier.complete_tx.shared::cta.b64 [%0], %1;" ::"r"(tc::smem_u32(&full[s])), "r"((uint32_t)R::kStageBytes) : "memory");
+            continue;
+          }
+          tc::tma_load_2d(sA, &tmA, ch * KT, j0, &full[s]);
+          tc::tma_load_3d(sB, &tmB, ch * KT, n0, 0, &full[s]);
+        }
+      }
+    }
+  } else if (lane == 0) {  // ---- tensor-core issuer (warp 9)
+    const uint32_t idesc = tc::idesc_tf32(N, 0, 0);
+    int it = 0, ti = 0;
+    for (int t = blockIdx.x; t < n_tiles; t += gridDim.x, ++ti) {
+      const int a = ti & 1;
+      if (ti >= 2 && !tc::mbar_wait(&acc_empty[a], ((ti >> 1) - 1) & 1)) __trap();
+      tc::tc_fence_after();
+      for (int ch = 0; ch < nch; ++ch, ++it) {
+        const int s = it % S;
+        if (!tc::mbar_wait(&full[s], (it / S) & 1)) __trap();
+        tc::tc_fence_after();
+        const uint32_t sA = ring + (uint32_t)s * R::kStageBytes, sB = sA + R::kABytes;
+        if (!(dbg & 1)) {
+#pragma unroll
+          for (int ks = 0; ks < KT / 8; ++ks)
+            tc::mma_tf32(tmem + a * 256, tc::smem_desc_sw128(sA + ks * 32), tc::smem_desc_sw128(sB + ks * 32), idesc,
+                         (ch == 0 && ks == 0) ? 0u : 1u);
+        }
+        tc::mma_commit(&empty[s]);
+      }
+      tc::mma_commit(&acc_full[a]);
+    }
+  }
+  tc::tc_fence_before();
+  __syncthreads();
+  if (warp == 9) tc::tmem_dealloc(tmem, 512);
+}
+
+// elementwise TF32 rounding of a weight matrix (the per-step copy the forward row GEMMs of the TF32 mode read)
+__global__ void round_copy_kernel(const float* __restrict__ W, float* __restrict__ Wr, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) Wr[i] = tc::to_tf32(W[i]);
+}
+
+__global__ void transpose_kernel(const float* __restrict__ W, float* __restrict__ WT, int H, int round) {
   __shared__ float t[32][33];
   const int x = blockIdx.x * 32 + threadIdx.x, y0 = blockIdx.y * 32;
   for (int r = threadIdx.y; r < 32; r += blockDim.y)
@@ -216,13 +366,74 @@ __global__ void transpose_kernel(const float* __restrict__ W, float* __restrict_
   __syncthreads();
   const int xo = blockIdx.y * 32 + threadIdx.x, yo0 = blockIdx.x * 32;
   for (int r = threadIdx.y; r < 32; r += blockDim.y)
-    if (xo < H && yo0 + r < H) WT[(size_t)(yo0 + r) * H + xo] = t[threadIdx.x][r];
+    if (xo < H && yo0 + r < H) WT[(size_t)(yo0 + r) * H + xo] = round ? tc::to_tf32(t[threadIdx.x][r]) : t[threadIdx.x][r];
+}
+
+// PINN_TC_ROWS_LEGACY=1: the TF32 mode keeps the round-1 kernel (A/B measurements; same numbers, the operands are rounded twice)
+bool rows_legacy() {
+  static const bool v = [] { const char* e = getenv("PINN_TC_ROWS_LEGACY"); return e && e[0] == '1'; }();
+  return v;
+}
+
+// cuTensorMapEncodeTiled through the runtime's driver entry point (no link-time dependency on libcuda)
+bool encode_tiled(CUtensorMap* tm, int rank, const void* base, const cuuint64_t* gdim, const cuuint64_t* gstr, const cuuint32_t* box,
+                  const cuuint32_t* est) {
+  typedef CUresult (*Fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                         const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+  static const Fn fn = [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess)
+      p = nullptr;
+    return (Fn)p;
+  }();
+  if (!fn) return false;
+  return fn(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, (cuuint32_t)rank, const_cast<void*>(base), gdim, gstr, box, est,
+            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+int rows2_dbg() {  // timing experiments only (PINN_ROWS2_DBG: 1 no MMAs, 2 no loads, 4 no epilogue): results are garbage
+  static const int v = [] { const char* e = getenv("PINN_ROWS2_DBG"); return e ? atoi(e) : 0; }();
+  return v;
 }
 
 template <int C, int ACT, int EPI, bool X3>
 int launch_rows_c(const WNet& n, const float* Bsrc, const float* Aw, const float* bias, float* Zio, float* Hout, int m, int Mc,
-                  int a_rows, cudaStream_t st) {
+                  int a_rows, bool round_out, cudaStream_t st) {
   using T = TileCfg<C>;
+  if (!X3 && !rows_legacy()) {  // TF32 mode: operands are already rounded (tc_rows2_kernel, TMA-fed)
+    using R = Rows2Cfg<C>;
+    static bool attr_set2 = false;
+    static int n_sm = 0;
+    if (!attr_set2) {
+      cudaError_t e = cudaFuncSetAttribute((const void*)tc_rows2_kernel<C, ACT, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, R::kSmemBytes);
+      if (e != cudaSuccess) return (int)e;
+      int dev = 0;
+      if ((e = cudaGetDevice(&dev)) != cudaSuccess) return (int)e;
+      if ((e = cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev)) != cudaSuccess) return (int)e;
+      attr_set2 = true;
+    }
+    CUtensorMap tmA, tmB;
+    {
+      // weights [a_rows][H] row-major: dims innermost first {k, unit}
+      const cuuint64_t gdim[2] = {(cuuint64_t)n.H, (cuuint64_t)a_rows}, gstr[1] = {(cuuint64_t)n.H * 4};
+      const cuuint32_t box[2] = {32, 128}, est[2] = {1, 1};
+      if (!encode_tiled(&tmA, 2, Aw, gdim, gstr, box, est)) return PINN_E_UNSUPPORTED;
+    }
+    {
+      // jet planes [C][Mc][H]: dims {k, point, channel}; only the m valid points are in bounds (the rest arrive as zeros)
+      const cuuint64_t gdim[3] = {(cuuint64_t)n.H, (cuuint64_t)m, (cuuint64_t)C}, gstr[2] = {(cuuint64_t)n.H * 4, (cuuint64_t)Mc * n.H * 4};
+      const cuuint32_t box[3] = {32, (cuuint32_t)T::P, (cuuint32_t)C}, est[3] = {1, 1, 1};
+      if (!encode_tiled(&tmB, 3, Bsrc, gdim, gstr, box, est)) return PINN_E_UNSUPPORTED;
+    }
+    const int tiles_j = (a_rows + 127) / 128, n_tiles = ((m + T::P - 1) / T::P) * tiles_j;
+    const int grid = n_tiles < n_sm ? n_tiles : n_sm;
+    tc_rows2_kernel<C, ACT, EPI><<<grid, 320, R::kSmemBytes, st>>>(n, tmA, tmB, bias, Zio, Hout, m, Mc, a_rows, tiles_j, n_tiles,
+                                                                   round_out ? 1 : 0, rows2_dbg());
+    count_launch(1);
+    return (int)cudaGetLastError();
+  }
   constexpr int KT = X3 ? 32 : 64;
   const size_t smem = (size_t)(X3 ? 2 : 1) * (KT / 4) * (129 + T::N + 1) * 4 * sizeof(float);
   static bool attr_set = false;
@@ -232,7 +443,7 @@ int launch_rows_c(const WNet& n, const float* Bsrc, const float* Aw, const float
     attr_set = true;
   }
   dim3 grid((m + T::P - 1) / T::P, (a_rows + 127) / 128);
-  tc_rows_kernel<C, ACT, EPI, X3><<<grid, 256, smem, st>>>(n, Bsrc, Aw, bias, Zio, Hout, m, Mc, a_rows);
+  tc_rows_kernel<C, ACT, EPI, X3><<<grid, 256, smem, st>>>(n, Bsrc, Aw, bias, Zio, Hout, m, Mc, a_rows, round_out ? 1 : 0);
   count_launch(1);
   return (int)cudaGetLastError();
 }
@@ -241,13 +452,13 @@ int launch_rows_c(const WNet& n, const float* Bsrc, const float* Aw, const float
 
 template <int ACT, int EPI>
 int tc_launch_rows(const WNet& n, const float* Bsrc, const float* Aw, const float* bias, float* Zio, float* Hout, int m, int Mc,
-                   cudaStream_t st) {
+                   bool round_out, cudaStream_t st) {
   const int a_rows = n.H;
   switch (n.C) {
 #define CASE(Cc)                                                                                              \
   case Cc:                                                                                                    \
-    return n.precision == 2 ? launch_rows_c<Cc, ACT, EPI, true>(n, Bsrc, Aw, bias, Zio, Hout, m, Mc, a_rows, st) \
-                            : launch_rows_c<Cc, ACT, EPI, false>(n, Bsrc, Aw, bias, Zio, Hout, m, Mc, a_rows, st);
+    return n.precision == 2 ? launch_rows_c<Cc, ACT, EPI, true>(n, Bsrc, Aw, bias, Zio, Hout, m, Mc, a_rows, false, st) \
+                            : launch_rows_c<Cc, ACT, EPI, false>(n, Bsrc, Aw, bias, Zio, Hout, m, Mc, a_rows, round_out, st);
     CASE(1) CASE(2) CASE(3) CASE(4) CASE(5) CASE(6) CASE(7)
 #undef CASE
   }
@@ -255,8 +466,8 @@ int tc_launch_rows(const WNet& n, const float* Bsrc, const float* Aw, const floa
 }
 
 #define INST(A)                                                                                                              \
-  template int tc_launch_rows<A, 0>(const WNet&, const float*, const float*, const float*, float*, float*, int, int, cudaStream_t); \
-  template int tc_launch_rows<A, 1>(const WNet&, const float*, const float*, const float*, float*, float*, int, int, cudaStream_t);
+  template int tc_launch_rows<A, 0>(const WNet&, const float*, const float*, const float*, float*, float*, int, int, bool, cudaStream_t); \
+  template int tc_launch_rows<A, 1>(const WNet&, const float*, const float*, const float*, float*, float*, int, int, bool, cudaStream_t);
 INST(PINN_ACT_TANH)
 INST(PINN_ACT_SILU)
 INST(PINN_ACT_SIN)
@@ -272,9 +483,15 @@ int tc_dw_splits(int H) {
   return ns < 1 ? 1 : ns;
 }
 
-int tc_transpose(const float* W, float* WT, int H, cudaStream_t st) {
+int tc_transpose(const float* W, float* WT, int H, bool round, cudaStream_t st) {
   dim3 grid((H + 31) / 32, (H + 31) / 32), block(32, 8);
-  transpose_kernel<<<grid, block, 0, st>>>(W, WT, H);
+  transpose_kernel<<<grid, block, 0, st>>>(W, WT, H, round ? 1 : 0);
+  count_launch(1);
+  return (int)cudaGetLastError();
+}
+
+int tc_round_copy(const float* W, float* Wr, int n, cudaStream_t st) {
+  round_copy_kernel<<<(n + 255) / 256, 256, 0, st>>>(W, Wr, n);
   count_launch(1);
   return (int)cudaGetLastError();
 }

@@ -1,12 +1,13 @@
 """Per-CUDA-source-line executed instructions and stall samples of one kernel in an .ncu-rep
-(ncu --import-source on, compiled with -lineinfo).   python tools/ncu_lines.py rep.ncu-rep [top N]"""
+(ncu --import-source on, compiled with -lineinfo).   python tools/ncu_lines.py rep.ncu-rep [top N] [launches to skip]"""
 import csv
 import subprocess
 import sys
 
 rep = sys.argv[1]
 top = int(sys.argv[2]) if len(sys.argv) > 2 else 40
-out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--print-source", "cuda,sass"], capture_output=True, text=True).stdout
+skip = ["--launch-skip", sys.argv[3], "--launch-count", "1"] if len(sys.argv) > 3 else []
+out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--print-source", "cuda,sass"] + skip, capture_output=True, text=True).stdout
 rows = list(csv.reader(out.splitlines()))
 hdr, fname, agg = None, None, []
 for r in rows:
