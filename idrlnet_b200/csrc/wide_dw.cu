@@ -13,6 +13,7 @@
 // exhausted, then 128 threads add it into the split's partial slot.
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdlib.h>
 
 #include "tc_common.cuh"
 #include "wide_internal.cuh"
@@ -64,7 +65,7 @@ __global__ void __launch_bounds__(256) retile_kernel(const float* __restrict__ s
 // grid (tiles_j * tiles_k, splits); 128 threads.  tz: A tiles (R = 128), th: B tiles (R = NB).
 template <int NB, bool X3>
 __global__ void __launch_bounds__(128, 1) tc_dw2_kernel(const float* __restrict__ tz, const float* __restrict__ th, int H, int kblocks,
-                                                        int UBA, int UBB, int tiles_k, float* __restrict__ part) {
+                                                        int UBA, int UBB, int tiles_k, float* __restrict__ part, int dbg) {
   extern __shared__ __align__(128) float sm[];
   __shared__ uint64_t full[kStages], empty[kStages], done;  // the first kS of each are used
   __shared__ uint32_t tmem_slot;
@@ -96,6 +97,10 @@ __global__ void __launch_bounds__(128, 1) tc_dw2_kernel(const float* __restrict_
         float* sA = sm + (size_t)s * kStageFloats;
         const size_t kb = (size_t)(kb0 + it);
         tc::mbar_expect_tx(&full[s], (uint32_t)(kStageFloats * sizeof(float)));
+        if (dbg & 2) {
+          asm volatile("mbarrier.complete_tx.shared::cta.b64 [%0], %1;" ::"r"(tc::smem_u32(&full[s])), "r"((uint32_t)(kStageFloats * sizeof(float))) : "memory");
+          continue;
+        }
         tc::bulk_copy_g2s(sA, tz + (kb * UBA + tj) * kAFloats, kAFloats * sizeof(float), &full[s]);
         tc::bulk_copy_g2s(sA + kAFloats, th + (kb * UBB + tk) * kBFloats, kBFloats * sizeof(float), &full[s]);
       }
@@ -108,6 +113,7 @@ __global__ void __launch_bounds__(128, 1) tc_dw2_kernel(const float* __restrict_
         const uint32_t a0 = tc::smem_u32(sm + (size_t)s * kStageFloats), b0 = a0 + kAFloats * sizeof(float);
 #pragma unroll
         for (int ks = 0; ks < kKB / 8; ++ks) {
+          if (dbg & 1) break;
           const uint64_t da = tc::smem_desc(a0 + ks * 2 * (128 * 16), 128 * 16, 128);
           const uint64_t db = tc::smem_desc(b0 + ks * 2 * (NB * 16), NB * 16, 128);
           if (X3) {  // lo*hi + hi*lo + hi*hi
@@ -130,15 +136,23 @@ __global__ void __launch_bounds__(128, 1) tc_dw2_kernel(const float* __restrict_
     const int j = tj * 128 + tid;
     const uint32_t lane_base = (uint32_t)(warp * 32) << 16;
     float* out = part + (size_t)blockIdx.y * H * H;
+    // flush: the split's slot is touched by this CTA only, once per launch, so `+=` is done as fire-and-forget vector
+    // reductions (red.global.add.v4.f32: one add per address per launch, launches in stream order -> the same sums as a
+    // read-modify-write, without its 16 serial round trips to a slot that is in DRAM by now: that chain was 54 of the 70 ms
+    // this kernel took per mlp_xl step)
     for (int g = 0; g < NB / 16; ++g) {
+      if (dbg & 4) break;
       float v[16];
       tc::tmem_ld16(tmem + lane_base + g * 16, v);
       tc::tmem_ld_wait();
       if (j < H) {
 #pragma unroll
-        for (int i = 0; i < 16; ++i) {
+        for (int i = 0; i < 16; i += 4) {
           const int k = tk * NB + g * 16 + i;
-          if (k < H) out[(size_t)j * H + k] += v[i];
+          if (k < H)  // H % 4 == 0: a quad is inside or outside as a whole
+            asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(out + (size_t)j * H + k), "f"(v[i]), "f"(v[i + 1]),
+                         "f"(v[i + 2]), "f"(v[i + 3])
+                         : "memory");
         }
       }
     }
@@ -148,13 +162,29 @@ __global__ void __launch_bounds__(128, 1) tc_dw2_kernel(const float* __restrict_
   if (warp == 0) tc::tmem_dealloc(tmem, NB);
 }
 
-// db slot (block 0, row 0 of the [kBlocks][8][H] partials) += sum over point blocks, in index order
-__global__ void colsum_finish_kernel(const float* __restrict__ colsum, int nblk, int H, float* __restrict__ db_slot) {
-  const int j = blockIdx.x * blockDim.x + threadIdx.x;
-  if (j >= H) return;
+// db slot (block 0, row 0 of the [kBlocks][8][H] partials) += sum over point blocks: eight segments of the block range in
+// index order each, combined in segment order (fixed order; 1024 threads instead of one serial chain of `nblk` loads per unit)
+__global__ void __launch_bounds__(1024) colsum_finish_kernel(const float* __restrict__ colsum, int nblk, int H, float* __restrict__ db_slot) {
+  __shared__ float red[8][128];
+  const int jl = threadIdx.x & 127, seg = threadIdx.x >> 7;
+  const int j = blockIdx.x * 128 + jl;
+  const int per = (nblk + 7) / 8, nb0 = seg * per, nb1 = (nb0 + per < nblk) ? nb0 + per : nblk;
   float s = 0.f;
-  for (int nb = 0; nb < nblk; ++nb) s += colsum[(size_t)nb * H + j];
-  db_slot[j] += s;
+  if (j < H)
+    for (int nb = nb0; nb < nb1; ++nb) s += colsum[(size_t)nb * H + j];
+  red[seg][jl] = s;
+  __syncthreads();
+  if (seg == 0 && j < H) {
+    float t = 0.f;
+#pragma unroll
+    for (int g = 0; g < 8; ++g) t += red[g][jl];
+    db_slot[j] += t;
+  }
+}
+
+int dw2_dbg() {  // timing experiments only (PINN_DW2_DBG: 1 no MMAs, 2 no copies, 4 no flush): results are garbage
+  static const int v = [] { const char* e = getenv("PINN_DW2_DBG"); return e ? atoi(e) : 0; }();
+  return v;
 }
 
 int rows_b(int H) { return H > 128 ? 256 : 128; }
@@ -170,7 +200,7 @@ int launch_dw2(const float* Zb, const float* Hb, int H, int C, int m, int Mc, fl
   float* th = tz + (size_t)F * C * nblk_alloc * UBA * (kKB * 128);
   float* colsum = th + (size_t)F * C * nblk_alloc * UBB * (kKB * R);
   retile_kernel<128, X3><<<dim3(nblk, UBA, C), 256, 0, st>>>(Zb, tz, H, m, Mc, nblk, UBA, colsum);
-  colsum_finish_kernel<<<(H + 127) / 128, 128, 0, st>>>(colsum, nblk, H, db_slot);
+  colsum_finish_kernel<<<(H + 127) / 128, 1024, 0, st>>>(colsum, nblk, H, db_slot);
   retile_kernel<R, X3><<<dim3(nblk, UBB, C), 256, 0, st>>>(Hb, th, H, m, Mc, nblk, UBB, nullptr);
   const int tiles = UBA * UBB, kblocks = C * nblk;
   int splits = kBlocks / tiles;
@@ -184,7 +214,7 @@ int launch_dw2(const float* Zb, const float* Hb, int H, int C, int m, int Mc, fl
     if (e != cudaSuccess) return (int)e;
     set = true;
   }
-  tc_dw2_kernel<R, X3><<<dim3(tiles, splits), 128, smem, st>>>(tz, th, H, kblocks, UBA, UBB, UBB, part);
+  tc_dw2_kernel<R, X3><<<dim3(tiles, splits), 128, smem, st>>>(tz, th, H, kblocks, UBA, UBB, UBB, part, dw2_dbg());
   count_launch(4);
   return (int)cudaGetLastError();
 }
