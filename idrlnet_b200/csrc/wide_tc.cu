@@ -69,77 +69,89 @@ __device__ __forceinline__ void release_tmem(uint64_t* bar, int lane) {
 }
 
 // Epilogue of one (P points, 128 units) accumulator tile: lane = hidden unit; the 16-point groups alternate between the two
-// warp quads (warp = 0..7).  round_out: the values that are operands of a later tensor-core GEMM (H_l, zbar_l) are stored
-// already rounded to TF32 (cvt.rna, the rounding the staging code applies), so that tc_rows2_kernel can copy them into shared
-// memory asynchronously without touching them.  release: mbarrier to arrive on (one lane per warp) as soon as this warp
-// has read its last accumulator columns (tc_rows2_kernel: the tensor core may overwrite the buffer).
-template <int C, int ACT, int EPI>
+// warp quads (warp = 0..7).  The channel structure (NF first-order, NS second-order channels) is a template parameter: with
+// run-time counts the jets were predicate chains over seven-element arrays in local memory, and the row kernels, once fed by
+// TMA, turned out to be bound by exactly this code (skipping it took the mlp_xl step from 319 to 238 ms).
+// round_out: the values that are operands of a later tensor-core GEMM (H_l, zbar_l) are stored already rounded to TF32
+// (cvt.rna, the rounding the staging code applies), so that tc_rows2_kernel can copy them into shared memory without touching
+// them.  release: mbarrier to arrive on (one lane per warp) as soon as this warp has read its last accumulator columns
+// (tc_rows2_kernel: the tensor core may overwrite the buffer).
+template <int NF, int NS, int ACT, int EPI>
 __device__ __forceinline__ void rows_epilogue(const WNet& net, uint32_t tmem, int warp, int lane, int n0, int j0, int m, size_t plane,
                                               int a_rows, const float* __restrict__ bias, float* __restrict__ Zio,
                                               float* __restrict__ Hout, bool round_out, uint64_t* release) {
+  constexpr int C = 1 + NF + NS;
   using T = TileCfg<C>;
   constexpr int P = T::P;
   const int H = net.H;
   const int j = j0 + (warp & 3) * 32 + lane;
+  const bool jok = j < a_rows;
   const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
-  const float bj = (EPI != 1 && j < a_rows) ? bias[j] : 0.f;
+  const float bj = (EPI != 1 && jok) ? bias[j] : 0.f;
   for (int g = warp >> 2; g < P / 16; g += 2) {
-    float v[C][16];
-#pragma unroll
-    for (int c = 0; c < C; ++c) tc::tmem_ld16(tmem + lane_base + c * P + g * 16, v[c]);
+    const int nb = n0 + g * 16;
+    const int left = jok ? m - nb : 0;  // points of this group that exist (>= 16: all of them)
+    float* zp = Zio + (size_t)nb * H + j;
     if (EPI == 1) {
-      // reverse layer: Z_{l-1} is fetched 4 points ahead (double-buffered registers) so the global
-      // loads of the next quad are in flight while the current quad's adjoints are computed
+      // reverse layer: Z_{l-1} is fetched 4 points ahead (double-buffered registers) so the global loads of the next quad
+      // are in flight while the current quad's adjoints are computed; the accumulator columns are read eight points at a
+      // time (all sixteen at once cost 96 registers next to the 48 of the Z buffers: 570 bytes of spills per thread)
       float zin[2][C][4];
       auto fetch = [&](int quad, float (&dst)[C][4]) {
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
-          const int n = n0 + g * 16 + quad * 4 + i;
+          const bool ok = quad * 4 + i < left;
 #pragma unroll
-          for (int c = 0; c < C; ++c) dst[c][i] = (j < H && n < m) ? Zio[c * plane + (size_t)n * H + j] : 0.f;
+          for (int c = 0; c < C; ++c) dst[c][i] = ok ? zp[c * plane + (size_t)(quad * 4 + i) * H] : 0.f;
         }
       };
       fetch(0, zin[0]);
-      tc::tmem_ld_wait();
-      if (release != nullptr && g + 2 >= P / 16) release_tmem(release, lane);
 #pragma unroll
-      for (int quad = 0; quad < 4; ++quad) {
-        if (quad + 1 < 4) fetch(quad + 1, zin[(quad + 1) & 1]);
+      for (int oct = 0; oct < 2; ++oct) {
+        float v[C][8];
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const int n = n0 + g * 16 + quad * 4 + i;
-          float a[kMaxC] = {}, b[kMaxC] = {}, o[kMaxC] = {};
+        for (int c = 0; c < C; ++c) tc::tmem_ld8(tmem + lane_base + c * P + g * 16 + oct * 8, v[c]);
+        tc::tmem_ld_wait();
+        if (release != nullptr && oct == 1 && g + 2 >= P / 16) release_tmem(release, lane);
 #pragma unroll
-          for (int c = 0; c < C; ++c) {
-            a[c] = v[c][quad * 4 + i];
-            b[c] = zin[quad & 1][c][i];
-            o[c] = 0.f;
-          }
-          jet_bwd<ACT>(net.NF, net.NS, b, a, o);
-          if (j < H && n < m) {
+        for (int q = 0; q < 2; ++q) {
+          const int quad = oct * 2 + q;
+          if (quad + 1 < 4) fetch(quad + 1, zin[(quad + 1) & 1]);
 #pragma unroll
-            for (int c = 0; c < C; ++c) Zio[c * plane + (size_t)n * H + j] = round_out ? tc::to_tf32(o[c]) : o[c];
+          for (int i = 0; i < 4; ++i) {
+            float hb[C], z[C], o[C];
+#pragma unroll
+            for (int c = 0; c < C; ++c) {
+              hb[c] = v[c][q * 4 + i];
+              z[c] = zin[quad & 1][c][i];
+            }
+            jet_bwd_t<ACT, NF, NS, false>(z, hb, o);
+            if (quad * 4 + i < left) {
+#pragma unroll
+              for (int c = 0; c < C; ++c) zp[c * plane + (size_t)(quad * 4 + i) * H] = round_out ? tc::to_tf32(o[c]) : o[c];
+            }
           }
         }
       }
     } else {
+      float v[C][16];
+#pragma unroll
+      for (int c = 0; c < C; ++c) tc::tmem_ld16(tmem + lane_base + c * P + g * 16, v[c]);
       tc::tmem_ld_wait();
       if (release != nullptr && g + 2 >= P / 16) release_tmem(release, lane);
-      if (j < a_rows) {
+      float* hp = Hout + (size_t)nb * H + j;
 #pragma unroll
-        for (int i = 0; i < 16; ++i) {
-          const int n = n0 + g * 16 + i;
-          if (n < m) {
-            float a[kMaxC] = {}, o[kMaxC] = {};
+      for (int i = 0; i < 16; ++i) {
+        if (i < left) {
+          float z[C], o[C];
 #pragma unroll
-            for (int c = 0; c < C; ++c) a[c] = v[c][i];
-            a[0] += bj;
-            jet_fwd<ACT>(net.NF, net.NS, a, o);
+          for (int c = 0; c < C; ++c) z[c] = v[c][i];
+          z[0] += bj;
+          jet_fwd_t<ACT, NF, NS, false>(z, o);
 #pragma unroll
-            for (int c = 0; c < C; ++c) {
-              Zio[c * plane + (size_t)n * H + j] = a[c];
-              Hout[c * plane + (size_t)n * H + j] = round_out ? tc::to_tf32(o[c]) : o[c];
-            }
+          for (int c = 0; c < C; ++c) {
+            zp[c * plane + (size_t)i * H] = z[c];
+            hp[c * plane + (size_t)i * H] = round_out ? tc::to_tf32(o[c]) : o[c];
           }
         }
       }
@@ -147,10 +159,11 @@ __device__ __forceinline__ void rows_epilogue(const WNet& net, uint32_t tmem, in
   }
 }
 
-template <int C, int ACT, int EPI, bool X3>
+template <int NF, int NS, int ACT, int EPI, bool X3>
 __global__ void __launch_bounds__(256, 2) tc_rows_kernel(WNet net, const float* __restrict__ Bsrc, const float* __restrict__ Aw,
                                                       const float* __restrict__ bias, float* __restrict__ Zio,
                                                       float* __restrict__ Hout, int m, int Mc, int a_rows, int round_out) {
+  constexpr int C = 1 + NF + NS;
   using T = TileCfg<C>;
   constexpr int P = T::P, N = T::N;
   constexpr int kKT = X3 ? 32 : 64;  // K elements per smem stage
@@ -226,7 +239,7 @@ __global__ void __launch_bounds__(256, 2) tc_rows_kernel(WNet net, const float* 
   if (!ok) __trap();
   tc::tc_fence_after();
 
-  rows_epilogue<C, ACT, EPI>(net, tmem, warp, lane, n0, j0, m, plane, a_rows, bias, Zio, Hout, round_out != 0, nullptr);
+  rows_epilogue<NF, NS, ACT, EPI>(net, tmem, warp, lane, n0, j0, m, plane, a_rows, bias, Zio, Hout, round_out != 0, nullptr);
   tc::tc_fence_before();
   __syncthreads();
   if (warp == 0) tc::tmem_dealloc(tmem, 256);
@@ -258,11 +271,12 @@ struct Rows2Cfg {
   static constexpr int kSmemBytes = kStages * kStageBytes + 1024;  // + alignment slack
 };
 
-template <int C, int ACT, int EPI>
+template <int NF, int NS, int ACT, int EPI>
 __global__ void __launch_bounds__(320, 1) tc_rows2_kernel(WNet net, const __grid_constant__ CUtensorMap tmA,
                                                           const __grid_constant__ CUtensorMap tmB, const float* __restrict__ bias,
                                                           float* __restrict__ Zio, float* __restrict__ Hout, int m, int Mc, int a_rows,
                                                           int tiles_j, int n_tiles, int round_out, int dbg) {
+  constexpr int C = 1 + NF + NS;
   using T = TileCfg<C>;
   using R = Rows2Cfg<C>;
   constexpr int P = T::P, N = T::N, S = R::kStages, KT = R::kKT;
@@ -300,7 +314,7 @@ __global__ void __launch_bounds__(320, 1) tc_rows2_kernel(WNet net, const __grid
         release_tmem(&acc_empty[a], lane);
         continue;
       }
-      rows_epilogue<C, ACT, EPI>(net, tmem + a * 256, warp, lane, (t / tiles_j) * P, (t % tiles_j) * 128, m, plane, a_rows, bias,
+      rows_epilogue<NF, NS, ACT, EPI>(net, tmem + a * 256, warp, lane, (t / tiles_j) * P, (t % tiles_j) * 128, m, plane, a_rows, bias,
                                  Zio, Hout, round_out != 0, &acc_empty[a]);
     }
   } else if (warp == 8) {  // ---- TMA producer
@@ -369,12 +383,6 @@ __global__ void transpose_kernel(const float* __restrict__ W, float* __restrict_
     if (xo < H && yo0 + r < H) WT[(size_t)(yo0 + r) * H + xo] = round ? tc::to_tf32(t[threadIdx.x][r]) : t[threadIdx.x][r];
 }
 
-// PINN_TC_ROWS_LEGACY=1: the TF32 mode keeps the round-1 kernel (A/B measurements; same numbers, the operands are rounded twice)
-bool rows_legacy() {
-  static const bool v = [] { const char* e = getenv("PINN_TC_ROWS_LEGACY"); return e && e[0] == '1'; }();
-  return v;
-}
-
 // cuTensorMapEncodeTiled through the runtime's driver entry point (no link-time dependency on libcuda)
 bool encode_tiled(CUtensorMap* tm, int rank, const void* base, const cuuint64_t* gdim, const cuuint64_t* gstr, const cuuint32_t* box,
                   const cuuint32_t* est) {
@@ -398,16 +406,17 @@ int rows2_dbg() {  // timing experiments only (PINN_ROWS2_DBG: 1 no MMAs, 2 no l
   return v;
 }
 
-template <int C, int ACT, int EPI, bool X3>
+template <int NF, int NS, int ACT, int EPI, bool X3>
 int launch_rows_c(const WNet& n, const float* Bsrc, const float* Aw, const float* bias, float* Zio, float* Hout, int m, int Mc,
                   int a_rows, bool round_out, cudaStream_t st) {
+  constexpr int C = 1 + NF + NS;
   using T = TileCfg<C>;
-  if (!X3 && !rows_legacy()) {  // TF32 mode: operands are already rounded (tc_rows2_kernel, TMA-fed)
+  if constexpr (!X3) {  // TF32 mode: operands are already rounded (tc_rows2_kernel, TMA-fed)
     using R = Rows2Cfg<C>;
     static bool attr_set2 = false;
     static int n_sm = 0;
     if (!attr_set2) {
-      cudaError_t e = cudaFuncSetAttribute((const void*)tc_rows2_kernel<C, ACT, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, R::kSmemBytes);
+      cudaError_t e = cudaFuncSetAttribute((const void*)tc_rows2_kernel<NF, NS, ACT, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, R::kSmemBytes);
       if (e != cudaSuccess) return (int)e;
       int dev = 0;
       if ((e = cudaGetDevice(&dev)) != cudaSuccess) return (int)e;
@@ -429,23 +438,24 @@ int launch_rows_c(const WNet& n, const float* Bsrc, const float* Aw, const float
     }
     const int tiles_j = (a_rows + 127) / 128, n_tiles = ((m + T::P - 1) / T::P) * tiles_j;
     const int grid = n_tiles < n_sm ? n_tiles : n_sm;
-    tc_rows2_kernel<C, ACT, EPI><<<grid, 320, R::kSmemBytes, st>>>(n, tmA, tmB, bias, Zio, Hout, m, Mc, a_rows, tiles_j, n_tiles,
+    tc_rows2_kernel<NF, NS, ACT, EPI><<<grid, 320, R::kSmemBytes, st>>>(n, tmA, tmB, bias, Zio, Hout, m, Mc, a_rows, tiles_j, n_tiles,
                                                                    round_out ? 1 : 0, rows2_dbg());
     count_launch(1);
     return (int)cudaGetLastError();
-  }
+  } else {
   constexpr int KT = X3 ? 32 : 64;
   const size_t smem = (size_t)(X3 ? 2 : 1) * (KT / 4) * (129 + T::N + 1) * 4 * sizeof(float);
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute((const void*)tc_rows_kernel<C, ACT, EPI, X3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute((const void*)tc_rows_kernel<NF, NS, ACT, EPI, X3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return (int)e;
     attr_set = true;
   }
   dim3 grid((m + T::P - 1) / T::P, (a_rows + 127) / 128);
-  tc_rows_kernel<C, ACT, EPI, X3><<<grid, 256, smem, st>>>(n, Bsrc, Aw, bias, Zio, Hout, m, Mc, a_rows, round_out ? 1 : 0);
+  tc_rows_kernel<NF, NS, ACT, EPI, X3><<<grid, 256, smem, st>>>(n, Bsrc, Aw, bias, Zio, Hout, m, Mc, a_rows, round_out ? 1 : 0);
   count_launch(1);
   return (int)cudaGetLastError();
+  }
 }
 
 }  // namespace
@@ -454,12 +464,12 @@ template <int ACT, int EPI>
 int tc_launch_rows(const WNet& n, const float* Bsrc, const float* Aw, const float* bias, float* Zio, float* Hout, int m, int Mc,
                    bool round_out, cudaStream_t st) {
   const int a_rows = n.H;
-  switch (n.C) {
-#define CASE(Cc)                                                                                              \
-  case Cc:                                                                                                    \
-    return n.precision == 2 ? launch_rows_c<Cc, ACT, EPI, true>(n, Bsrc, Aw, bias, Zio, Hout, m, Mc, a_rows, false, st) \
-                            : launch_rows_c<Cc, ACT, EPI, false>(n, Bsrc, Aw, bias, Zio, Hout, m, Mc, a_rows, round_out, st);
-    CASE(1) CASE(2) CASE(3) CASE(4) CASE(5) CASE(6) CASE(7)
+  switch (n.NF * 4 + n.NS) {  // NS <= NF <= 3 (make_net)
+#define CASE(F, S_)                                                                                                  \
+  case F * 4 + S_:                                                                                                   \
+    return n.precision == 2 ? launch_rows_c<F, S_, ACT, EPI, true>(n, Bsrc, Aw, bias, Zio, Hout, m, Mc, a_rows, false, st) \
+                            : launch_rows_c<F, S_, ACT, EPI, false>(n, Bsrc, Aw, bias, Zio, Hout, m, Mc, a_rows, round_out, st);
+    CASE(0, 0) CASE(1, 0) CASE(1, 1) CASE(2, 0) CASE(2, 1) CASE(2, 2) CASE(3, 0) CASE(3, 1) CASE(3, 2) CASE(3, 3)
 #undef CASE
   }
   return PINN_E_UNSUPPORTED;
