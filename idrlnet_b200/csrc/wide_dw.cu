@@ -162,13 +162,14 @@ __global__ void __launch_bounds__(128, 1) tc_dw2_kernel(const float* __restrict_
   if (warp == 0) tc::tmem_dealloc(tmem, NB);
 }
 
-// db slot (block 0, row 0 of the [kBlocks][8][H] partials) += sum over point blocks: eight segments of the block range in
-// index order each, combined in segment order (fixed order; 1024 threads instead of one serial chain of `nblk` loads per unit)
+// db slot (block 0, row 0 of the [kBlocks][8][H] partials) += sum over point blocks: 32 segments of the block range in index
+// order each, combined in segment order (a fixed order).  One CTA = 32 units x 32 segments, so H / 32 CTAs share the work (one
+// serial chain of `nblk` loads per unit took 31 us per call at 2 048 blocks; a chunk of allen_cahn has that many).
 __global__ void __launch_bounds__(1024) colsum_finish_kernel(const float* __restrict__ colsum, int nblk, int H, float* __restrict__ db_slot) {
-  __shared__ float red[8][128];
-  const int jl = threadIdx.x & 127, seg = threadIdx.x >> 7;
-  const int j = blockIdx.x * 128 + jl;
-  const int per = (nblk + 7) / 8, nb0 = seg * per, nb1 = (nb0 + per < nblk) ? nb0 + per : nblk;
+  __shared__ float red[32][33];
+  const int jl = threadIdx.x & 31, seg = threadIdx.x >> 5;
+  const int j = blockIdx.x * 32 + jl;
+  const int per = (nblk + 31) / 32, nb0 = seg * per, nb1 = (nb0 + per < nblk) ? nb0 + per : nblk;
   float s = 0.f;
   if (j < H)
     for (int nb = nb0; nb < nb1; ++nb) s += colsum[(size_t)nb * H + j];
@@ -177,7 +178,7 @@ __global__ void __launch_bounds__(1024) colsum_finish_kernel(const float* __rest
   if (seg == 0 && j < H) {
     float t = 0.f;
 #pragma unroll
-    for (int g = 0; g < 8; ++g) t += red[g][jl];
+    for (int g = 0; g < 32; ++g) t += red[g][jl];
     db_slot[j] += t;
   }
 }
@@ -200,7 +201,7 @@ int launch_dw2(const float* Zb, const float* Hb, int H, int C, int m, int Mc, fl
   float* th = tz + (size_t)F * C * nblk_alloc * UBA * (kKB * 128);
   float* colsum = th + (size_t)F * C * nblk_alloc * UBB * (kKB * R);
   retile_kernel<128, X3><<<dim3(nblk, UBA, C), 256, 0, st>>>(Zb, tz, H, m, Mc, nblk, UBA, colsum);
-  colsum_finish_kernel<<<(H + 127) / 128, 1024, 0, st>>>(colsum, nblk, H, db_slot);
+  colsum_finish_kernel<<<(H + 31) / 32, 1024, 0, st>>>(colsum, nblk, H, db_slot);
   retile_kernel<R, X3><<<dim3(nblk, UBB, C), 256, 0, st>>>(Hb, th, H, m, Mc, nblk, UBB, nullptr);
   const int tiles = UBA * UBB, kblocks = C * nblk;
   int splits = kBlocks / tiles;
