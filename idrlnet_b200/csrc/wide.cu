@@ -589,10 +589,33 @@ bool make_net(const pinn_mlp* m, const pinn_jets* j, WNet* n) {
   return true;
 }
 
+}  // namespace
+
+// Bytes of planes per chunk of the layer-streamed path: 1/24 of the device memory, between 1 and 8 GB (7.5 GB on a 180 GB
+// B200; PINN_WIDE_CHUNK_MB overrides).  It was a fixed 1 GB: 4 736 points per chunk of mlp_xl = four tiles per CTA of the
+// persistent row GEMMs, whose fill and drain (one mainloop + one epilogue not overlapped) were then a quarter of every launch,
+// and 7 800 launches per 2^20-point step.  Evaluated once: the workspace size and every step must agree on it.
+int64_t chunk_budget() {
+  static const int64_t v = [] {
+    if (const char* e = getenv("PINN_WIDE_CHUNK_MB")) {
+      const long long mb = atoll(e);
+      if (mb >= 64) return (int64_t)mb << 20;
+    }
+    size_t free_b = 0, total_b = 0;
+    int64_t b = 1ll << 30;
+    if (cudaMemGetInfo(&free_b, &total_b) == cudaSuccess) b = (int64_t)(total_b / 24);
+    if (b < (1ll << 30)) b = 1ll << 30;
+    if (b > (8ll << 30)) b = 8ll << 30;
+    return b;
+  }();
+  return v;
+}
+
+namespace {
 WideLayout make_layout(const WNet& n, int n_dom) {
   WideLayout wl;
   const int64_t per_point = (2ll * n.L + (n.precision == 2 ? 5 : n.precision ? 3 : 0)) * n.C * n.H * 4;  // planes (+ re-tiled dW operands)
-  int64_t mc = kChunkBudget / per_point;
+  int64_t mc = chunk_budget() / per_point;
   mc = mc / kBM * kBM;
   if (mc < 256) mc = 256;
   if (mc > 65536) mc = 65536;

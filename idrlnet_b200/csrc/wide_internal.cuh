@@ -12,7 +12,7 @@ constexpr int kBlocks = 148;         // partial slots of the per-block reduction
 constexpr int kBM = 32;              // points per GEMM tile
 constexpr int kBN = 128;             // output columns per GEMM tile
 constexpr int kBK = 16;
-constexpr int64_t kChunkBudget = 1ll << 30;   // bytes of Z/H planes per chunk (large chunks: many tiles in flight)
+int64_t chunk_budget();              // bytes of Z/H planes (+ re-tiled operands) per chunk (wide.cu)
 constexpr int kMaxDomains = 64;       // loss slots
 
 struct WNet {

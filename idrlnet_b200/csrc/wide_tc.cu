@@ -262,23 +262,85 @@ __global__ void __launch_bounds__(256, 2) tc_rows_kernel(WNet net, const float* 
 // B rows run at the same time (L2 hits).  Same products on the same rounded operands as tc_rows_kernel<.., false>.
 // (A first version staged with 16-byte cp.async from two loader warps: 1.26x SLOWER than tc_rows_kernel -- 22 GB/s per SM,
 // twice the L2 -> SM bytes of the tile (sector-granular 16-byte requests), experiments/tc_rows2_cpasync.cu.txt.)
-template <int C>
+template <int C, int EPI>
 struct Rows2Cfg {
   static constexpr int N = TileCfg<C>::N;
   static constexpr int kKT = 32;
   static constexpr int kABytes = 128 * 128, kBBytes = N * 128, kStageBytes = kABytes + kBBytes;  // multiples of 1024
-  static constexpr int kStages = (N >= 224) ? 4 : 5;  // 4 x 48 KB (N = 256) / 5 x 40 KB (N = 192)
-  static constexpr int kSmemBytes = kStages * kStageBytes + 1024;  // + alignment slack
+  // forward epilogue through shared memory + TMA stores: per warp quad two buffers of {Z, H} boxes [C][4 points][128 units]
+  static constexpr bool kTmaEpi = (EPI == 0) && (C <= 6);
+  static constexpr int kBoxFloats = C * 4 * 128;
+  static constexpr int kStagingBytes = kTmaEpi ? 2 * 2 * 2 * kBoxFloats * 4 : 0;  // C x 16 KB
+  static constexpr int kFit = (232448 - 2048 - kStagingBytes) / kStageBytes;
+  static constexpr int kStages = kFit > 5 ? 5 : kFit;  // 5 x 40 KB at N = 192 without staging, 3 with it
+  static_assert(kStages >= 3, "ring too shallow");
+  static constexpr int kSmemBytes = kStages * kStageBytes + kStagingBytes + 1024;  // + alignment slack
 };
+
+// Forward epilogue of one accumulator tile through shared memory (tc_rows2_kernel): the 16-point groups alternate between
+// the two warp quads as in rows_epilogue; a quad of points at a time, the 128 threads of a warp quad write Z and H into
+// boxes [C][4 points][128 units] (lanes = consecutive units: conflict-free, compile-time offsets) and one thread hands both
+// boxes to the TMA engine (cp.async.bulk.tensor store; units >= H and points >= m are clipped by the tensor map).  Two
+// buffers per warp quad: the store issued two quads ago must have been read (wait_group.read 1) before its buffer is reused.
+// Replaces 12 STG.32 + their address arithmetic per thread and point (L1TEX was the busiest unit of the forward launch, 59 %).
+template <int NF, int NS, int ACT>
+__device__ __forceinline__ void rows_epilogue_fwd_tma(uint32_t tmem, int warp, int lane, int n0, int j0, int a_rows,
+                                                      const float* __restrict__ bias, const CUtensorMap* tmZ, const CUtensorMap* tmH,
+                                                      float* stage, uint32_t& phase, bool round_out, uint64_t* release) {
+  constexpr int C = 1 + NF + NS;
+  constexpr int P = TileCfg<C>::P;
+  constexpr int kBox = C * 4 * 128;
+  const int wq = warp & 3, grp = warp >> 2;
+  const int jl = wq * 32 + lane, j = j0 + jl;
+  const bool leader = (wq == 0 && lane == 0);
+  const uint32_t lane_base = (uint32_t)(wq * 32) << 16;
+  const float bj = (j < a_rows) ? bias[j] : 0.f;
+  float* mine = stage + (size_t)grp * (4 * kBox);
+  for (int g = grp; g < P / 16; g += 2) {
+    float v[C][16];
+#pragma unroll
+    for (int c = 0; c < C; ++c) tc::tmem_ld16(tmem + lane_base + c * P + g * 16, v[c]);
+    tc::tmem_ld_wait();
+    if (g + 2 >= P / 16) release_tmem(release, lane);
+#pragma unroll
+    for (int quad = 0; quad < 4; ++quad) {
+      float* buf = mine + (phase & 1u) * (2 * kBox);
+      if (leader) tc::bulk_wait_read<1>();
+      tc::named_bar(1 + grp, 128);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        float z[C], o[C];
+#pragma unroll
+        for (int c = 0; c < C; ++c) z[c] = v[c][quad * 4 + i];
+        z[0] += bj;
+        jet_fwd_t<ACT, NF, NS, false>(z, o);
+#pragma unroll
+        for (int c = 0; c < C; ++c) {
+          buf[(c * 4 + i) * 128 + jl] = z[c];
+          buf[kBox + (c * 4 + i) * 128 + jl] = round_out ? tc::to_tf32(o[c]) : o[c];
+        }
+      }
+      tc::fence_async_smem();
+      tc::named_bar(1 + grp, 128);
+      if (leader) {
+        tc::tma_store_3d(tmZ, tc::smem_u32(buf), j0, n0 + g * 16 + quad * 4, 0);
+        tc::tma_store_3d(tmH, tc::smem_u32(buf + kBox), j0, n0 + g * 16 + quad * 4, 0);
+        tc::bulk_commit();
+      }
+      ++phase;
+    }
+  }
+}
 
 template <int NF, int NS, int ACT, int EPI>
 __global__ void __launch_bounds__(320, 1) tc_rows2_kernel(WNet net, const __grid_constant__ CUtensorMap tmA,
-                                                          const __grid_constant__ CUtensorMap tmB, const float* __restrict__ bias,
+                                                          const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmZ,
+                                                          const __grid_constant__ CUtensorMap tmH, const float* __restrict__ bias,
                                                           float* __restrict__ Zio, float* __restrict__ Hout, int m, int Mc, int a_rows,
                                                           int tiles_j, int n_tiles, int round_out, int dbg) {
   constexpr int C = 1 + NF + NS;
   using T = TileCfg<C>;
-  using R = Rows2Cfg<C>;
+  using R = Rows2Cfg<C, EPI>;
   constexpr int P = T::P, N = T::N, S = R::kStages, KT = R::kKT;
   const int H = net.H;
   extern __shared__ __align__(1024) uint8_t sm_raw[];
@@ -306,6 +368,8 @@ __global__ void __launch_bounds__(320, 1) tc_rows2_kernel(WNet net, const __grid
   const uint32_t tmem = tmem_slot;
   if (warp < 8) {  // ---- epilogue warps
     int ti = 0;
+    uint32_t st_phase = 0;
+    float* staging = reinterpret_cast<float*>(sm_raw + (ring - tc::smem_u32(sm_raw)) + S * R::kStageBytes);
     for (int t = blockIdx.x; t < n_tiles; t += gridDim.x, ++ti) {
       const int a = ti & 1;
       if (!tc::mbar_wait(&acc_full[a], (ti >> 1) & 1)) __trap();
@@ -314,8 +378,16 @@ __global__ void __launch_bounds__(320, 1) tc_rows2_kernel(WNet net, const __grid
         release_tmem(&acc_empty[a], lane);
         continue;
       }
-      rows_epilogue<NF, NS, ACT, EPI>(net, tmem + a * 256, warp, lane, (t / tiles_j) * P, (t % tiles_j) * 128, m, plane, a_rows, bias,
-                                 Zio, Hout, round_out != 0, &acc_empty[a]);
+      if constexpr (R::kTmaEpi) {
+        rows_epilogue_fwd_tma<NF, NS, ACT>(tmem + a * 256, warp, lane, (t / tiles_j) * P, (t % tiles_j) * 128, a_rows, bias, &tmZ, &tmH,
+                                           staging, st_phase, round_out != 0, &acc_empty[a]);
+      } else {
+        rows_epilogue<NF, NS, ACT, EPI>(net, tmem + a * 256, warp, lane, (t / tiles_j) * P, (t % tiles_j) * 128, m, plane, a_rows, bias,
+                                        Zio, Hout, round_out != 0, &acc_empty[a]);
+      }
+    }
+    if constexpr (R::kTmaEpi) {
+      if ((warp & 3) == 0 && lane == 0) tc::bulk_wait_read<0>();  // the boxes must outlive their stores
     }
   } else if (warp == 8) {  // ---- TMA producer
     if (lane == 0) {
@@ -385,7 +457,7 @@ __global__ void transpose_kernel(const float* __restrict__ W, float* __restrict_
 
 // cuTensorMapEncodeTiled through the runtime's driver entry point (no link-time dependency on libcuda)
 bool encode_tiled(CUtensorMap* tm, int rank, const void* base, const cuuint64_t* gdim, const cuuint64_t* gstr, const cuuint32_t* box,
-                  const cuuint32_t* est) {
+                  const cuuint32_t* est, bool swizzle128 = true) {
   typedef CUresult (*Fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
                          const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
   static const Fn fn = [] {
@@ -397,7 +469,7 @@ bool encode_tiled(CUtensorMap* tm, int rank, const void* base, const cuuint64_t*
   }();
   if (!fn) return false;
   return fn(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, (cuuint32_t)rank, const_cast<void*>(base), gdim, gstr, box, est,
-            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+            CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
@@ -412,7 +484,7 @@ int launch_rows_c(const WNet& n, const float* Bsrc, const float* Aw, const float
   constexpr int C = 1 + NF + NS;
   using T = TileCfg<C>;
   if constexpr (!X3) {  // TF32 mode: operands are already rounded (tc_rows2_kernel, TMA-fed)
-    using R = Rows2Cfg<C>;
+    using R = Rows2Cfg<C, EPI>;
     static bool attr_set2 = false;
     static int n_sm = 0;
     if (!attr_set2) {
@@ -436,9 +508,17 @@ int launch_rows_c(const WNet& n, const float* Bsrc, const float* Aw, const float
       const cuuint32_t box[3] = {32, (cuuint32_t)T::P, (cuuint32_t)C}, est[3] = {1, 1, 1};
       if (!encode_tiled(&tmB, 3, Bsrc, gdim, gstr, box, est)) return PINN_E_UNSUPPORTED;
     }
+    CUtensorMap tmZ = tmA, tmH = tmA;  // (placeholders unless the epilogue stores through TMA)
+    if (R::kTmaEpi) {
+      // output planes [C][Mc][H] as {unit, point, channel}; boxes {128 units, 4 points, C}, no swizzle; only valid elements are stored
+      const cuuint64_t gdim[3] = {(cuuint64_t)n.H, (cuuint64_t)m, (cuuint64_t)C}, gstr[2] = {(cuuint64_t)n.H * 4, (cuuint64_t)Mc * n.H * 4};
+      const cuuint32_t box[3] = {128, 4, (cuuint32_t)C}, est[3] = {1, 1, 1};
+      if (!encode_tiled(&tmZ, 3, Zio, gdim, gstr, box, est, false) || !encode_tiled(&tmH, 3, Hout, gdim, gstr, box, est, false))
+        return PINN_E_UNSUPPORTED;
+    }
     const int tiles_j = (a_rows + 127) / 128, n_tiles = ((m + T::P - 1) / T::P) * tiles_j;
     const int grid = n_tiles < n_sm ? n_tiles : n_sm;
-    tc_rows2_kernel<NF, NS, ACT, EPI><<<grid, 320, R::kSmemBytes, st>>>(n, tmA, tmB, bias, Zio, Hout, m, Mc, a_rows, tiles_j, n_tiles,
+    tc_rows2_kernel<NF, NS, ACT, EPI><<<grid, 320, R::kSmemBytes, st>>>(n, tmA, tmB, tmZ, tmH, bias, Zio, Hout, m, Mc, a_rows, tiles_j, n_tiles,
                                                                    round_out ? 1 : 0, rows2_dbg());
     count_launch(1);
     return (int)cudaGetLastError();
