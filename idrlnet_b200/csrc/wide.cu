@@ -449,8 +449,9 @@ __global__ void __launch_bounds__(256) head_point_kernel(WNet net, const __grid_
 // grid (ceil(H/128), kBlocks); block = 128 units x 4 point lanes; blockIdx.y is the partial slot.
 template <int ACT, int C>
 __global__ void __launch_bounds__(1024) head_bwd_kernel(WNet net, const float* __restrict__ Yb, float* __restrict__ ZL,
-                                                        const float* __restrict__ HL, int m, int Mc, float* __restrict__ part) {
-  __shared__ float red[8][4][129];
+                                                        const float* __restrict__ HL, int m, int Mc, float* __restrict__ part,
+                                                        float* __restrict__ dbp) {
+  __shared__ float red[8][5][129];
   const int H = net.H, O = net.n_out;
   const int jl = threadIdx.x & 127, pl = threadIdx.x >> 7;
   const int j = blockIdx.x * 128 + jl;
@@ -458,6 +459,7 @@ __global__ void __launch_bounds__(1024) head_bwd_kernel(WNet net, const float* _
   const int per = (m + gridDim.y - 1) / gridDim.y;
   const int nb = blockIdx.y * per, ne = (nb + per < m) ? nb + per : m;
   float gW[4] = {0.f, 0.f, 0.f, 0.f};
+  float dbs = 0.f;  // db_L = sum of zbar_L's (unrounded) value channel, when the caller asks for it (dbp)
   const bool round = net.precision == 1 && net.L >= 2;  // TF32 mode: zbar_L is a tensor-core operand, stored rounded
   if (j < H) {
     float wo[4];
@@ -490,6 +492,7 @@ __global__ void __launch_bounds__(1024) head_bwd_kernel(WNet net, const float* _
         }
         jet_bwd<ACT>(net.NF, net.NS, z[u], hb, zb);
         if (nn < ne) {
+          dbs += zb[0];
 #pragma unroll
           for (int c = 0; c < C; ++c) ZL[c * plane + (size_t)nn * H + j] = round ? tf32_rna(zb[c]) : zb[c];
         }
@@ -498,6 +501,7 @@ __global__ void __launch_bounds__(1024) head_bwd_kernel(WNet net, const float* _
   }
 #pragma unroll
   for (int o = 0; o < 4; ++o) red[pl][o][jl] = gW[o];
+  red[pl][4][jl] = dbs;
   __syncthreads();
   if (pl == 0 && j < H) {
     const int hstride = O * H + O + 1;
@@ -506,6 +510,12 @@ __global__ void __launch_bounds__(1024) head_bwd_kernel(WNet net, const float* _
 #pragma unroll
       for (int g = 0; g < 8; ++g) sum += red[g][o][jl];
       part[(size_t)blockIdx.y * hstride + o * H + j] += sum;
+    }
+    if (dbp != nullptr) {  // this block's slot of the [kBlocks][8][H] partials, row 0
+      float sum = 0.f;
+#pragma unroll
+      for (int g = 0; g < 8; ++g) sum += red[g][4][jl];
+      dbp[(size_t)blockIdx.y * 8 * H + j] += sum;
     }
   }
 }
@@ -688,6 +698,7 @@ int run_chunks(const WNet& n, const WideLayout& wl, float* ws, int mode, const p
   // TF32 mode: the operands of the tensor-core GEMMs (H_1 .. H_{L-1}, zbar_L .. zbar_2, the weight copies) are stored
   // rounded by their producers; H_L (output layer) and zbar_1 (first-layer gradient) stay FP32 (wide_tc.cu)
   const bool tf32 = n.precision == 1;
+  const bool direct = tf32 && tc_dw_direct();  // dW operands by TMA straight from the planes; db from the producers of zbar
   Coords xs;
   for (int d = 0; d < PINN_MAX_IN; ++d) xs.p[d] = d < n.n_in ? coords[d] : nullptr;
   for (int64_t n0 = 0; n0 < N; n0 += wl.Mc) {
@@ -702,7 +713,7 @@ int run_chunks(const WNet& n, const WideLayout& wl, float* ws, int mode, const p
     for (int l = 2; l <= L; ++l) {
       int rc = n.precision
                    ? tc_launch_rows<ACT, 0>(n, Hb + (l - 2) * planes, tf32 ? ws + wl.wr + (size_t)(l - 2) * H * H : n.W[l - 1],
-                                            n.b[l - 1], Z + (l - 1) * planes, Hb + (l - 1) * planes, m, wl.Mc, tf32 && l < L, st)
+                                            n.b[l - 1], Z + (l - 1) * planes, Hb + (l - 1) * planes, m, wl.Mc, tf32 && l < L, nullptr, st)
                    : launch_gemm_rows<ACT, true, 0>(n, Hb + (l - 2) * planes, n.W[l - 1], n.b[l - 1], Z + (l - 1) * planes,
                                                     Hb + (l - 1) * planes, m, wl.Mc, st);
       if (rc) return rc;
@@ -732,7 +743,8 @@ int run_chunks(const WNet& n, const WideLayout& wl, float* ws, int mode, const p
     head_point_kernel<C_><<<pb, 256, 0, st>>>(n, ha, yb, m);                                                \
     count_launch(1);                                                                                        \
     if (mode != W_MODE_FWD && mode != W_MODE_LOSS) {                                                                 \
-      head_bwd_kernel<ACT, C_><<<bgrid, 1024, 0, st>>>(n, yb, zl, hl, m, wl.Mc, ws + wl.head);               \
+      head_bwd_kernel<ACT, C_><<<bgrid, 1024, 0, st>>>(n, yb, zl, hl, m, wl.Mc, ws + wl.head,                \
+                                                        (direct && L >= 2) ? ws + wl.db + (size_t)(L - 2) * kBlocks * 8 * H : nullptr); \
       count_launch(1);                                                                                      \
     }                                                                                                       \
   } break;
@@ -752,7 +764,15 @@ int run_chunks(const WNet& n, const WideLayout& wl, float* ws, int mode, const p
       {
         float* dwp = ws + wl.dw + (size_t)(l - 2) * wl.n_splits * H * H;
         float* dbp = ws + wl.db + (size_t)(l - 2) * kBlocks * 8 * H;
-        if (n.precision) {  // db_l rides along with the re-tiling of zbar_l
+        if (direct) {
+          // zbar_L's column sums were added by head_bwd_kernel; zbar_l (l < L) left its per-group sums in the scratch
+          if (l < L) {
+            int rc = tc_colsum_finish(ws + wl.tdw, (m + 15) / 16, H, dbp, st);
+            if (rc) return rc;
+          }
+          int rc = tc_launch_dw3(zb, hprev, H, C, m, wl.Mc, dwp, wl.n_splits, st);
+          if (rc) return rc;
+        } else if (n.precision) {  // db_l rides along with the re-tiling of zbar_l
           int rc = tc_launch_dw2(zb, hprev, H, C, m, wl.Mc, dwp, wl.n_splits, ws + wl.tdw, dbp, n.precision == 2, st);
           if (rc) return rc;
         } else {
@@ -767,7 +787,7 @@ int run_chunks(const WNet& n, const WideLayout& wl, float* ws, int mode, const p
       }
       int rc = n.precision
                    ? tc_launch_rows<ACT, 1>(n, zb, ws + wl.wt + (size_t)(l - 2) * H * H, nullptr, Z + (l - 2) * planes, nullptr,
-                                            m, wl.Mc, tf32 && l > 2, st)
+                                            m, wl.Mc, tf32 && l > 2, (direct && l > 2) ? ws + wl.tdw : nullptr, st)
                    : launch_gemm_rows<ACT, false, 1>(n, zb, n.W[l - 1], nullptr, Z + (l - 2) * planes, nullptr, m, wl.Mc, st);
       if (rc) return rc;
     }

@@ -183,6 +183,119 @@ __global__ void __launch_bounds__(1024) colsum_finish_kernel(const float* __rest
   }
 }
 
+// ---- TF32 mode: dW operands straight from the planes -------------------------------------------------------------------
+// dW_l[j][k] += sum over (c, n) of zbar_l[c][n][j] * h_{l-1}[c][n][k]: both operands are wanted with the point index as K, and the
+// planes [c][n][unit] have the UNIT index contiguous -- "MN-major" operands.  For 32-bit elements tcgen05 reads those in the
+// 128-byte swizzle with 32-byte atoms (descriptor layout type 1; TMA CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B): groups of 4 K-rows x
+// 128 bytes (32 units), SBO = 512 bytes between the two 4-row groups of one K = 8 MMA, LBO between 32-unit groups -- what a TMA
+// box {32 units, KB points, 1 channel} leaves in shared memory with LBO = KB * 128.  The form was found by exhaustive search on the
+// hardware (experiments/mn_major_probe.cu, profiles/r02/mn_major_probe.txt): the plain SWIZZLE_128B (16-byte atoms) matches no
+// descriptor form for TF32.  So the re-tiling pass (retile_kernel: read + write of both operands, 26 % of an mlp_xl TF32 step)
+// disappears: one thread issues 4 + NB / 32 boxes per 32-point K block into a 4-stage ring, one thread issues 4 MMAs (K = 8
+// points each: start address + ks * 1024 bytes) per block.
+// In TF32 mode the planes already hold TF32-rounded values (wide_tc.cu); rows >= m arrive as zeros, units >= H as zeros.
+// db_l comes from the producers of zbar_l (head_bwd_kernel, rows_epilogue) instead of the re-tiling pass.
+__device__ __forceinline__ uint64_t smem_desc_mn_sw128(uint32_t saddr, uint32_t lbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3FFFFu) >> 4);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16;
+  d |= (uint64_t)(512 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)1 << 61;  // 128-byte swizzle, 32-byte atoms
+  return d;
+}
+
+template <int NB>
+__global__ void __launch_bounds__(128, 1) tc_dw3_kernel(const __grid_constant__ CUtensorMap tmZ, const __grid_constant__ CUtensorMap tmH,
+                                                        int H, int nblk, int kblocks, int tiles_k, float* __restrict__ part, int dbg) {
+  extern __shared__ __align__(1024) uint8_t sm_raw[];
+  __shared__ uint64_t full[kStages], empty[kStages], done;
+  __shared__ uint32_t tmem_slot;
+  constexpr int kABytes = 4 * kKB * 128, kBBytes = (NB / 32) * kKB * 128, kStageBytes = kABytes + kBBytes;  // 16 KB + 32 KB
+  constexpr uint32_t kLBO = kKB * 128;  // bytes between 32-unit groups
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int tj = blockIdx.x / tiles_k, tk = blockIdx.x % tiles_k;
+  const int per = (kblocks + gridDim.y - 1) / gridDim.y;
+  const int kb0 = blockIdx.y * per, kb1 = (kb0 + per < kblocks) ? kb0 + per : kblocks;
+  const int nit = kb1 - kb0;
+  const uint32_t ring = (tc::smem_u32(sm_raw) + 1023u) & ~1023u;
+  if (tid == 0) {
+    for (int s = 0; s < kStages; ++s) {
+      tc::mbar_init(&full[s], 1);
+      tc::mbar_init(&empty[s], 1);
+    }
+    tc::mbar_init(&done, 1);
+    tc::fence_mbar_init();
+  }
+  if (warp == 0) tc::tmem_alloc(&tmem_slot, NB);
+  tc::tc_fence_before();
+  __syncthreads();
+  tc::tc_fence_after();
+  const uint32_t tmem = tmem_slot;
+  if (nit > 0) {
+    if (warp == 0 && lane == 0) {  // producer
+      tc::tma_prefetch_desc(&tmZ);
+      tc::tma_prefetch_desc(&tmH);
+      for (int it = 0; it < nit; ++it) {
+        const int s = it % kStages;
+        if (it >= kStages && !tc::mbar_wait(&empty[s], ((it / kStages) - 1) & 1)) __trap();
+        const int kb = kb0 + it, c = kb / nblk, n0 = (kb - c * nblk) * kKB;
+        const uint32_t sA = ring + (uint32_t)s * kStageBytes, sB = sA + kABytes;
+        tc::mbar_expect_tx(&full[s], (uint32_t)kStageBytes);
+        if (dbg & 2) {
+          asm volatile("mbarrier.complete_tx.shared::cta.b64 [%0], %1;" ::"r"(tc::smem_u32(&full[s])), "r"((uint32_t)kStageBytes) : "memory");
+          continue;
+        }
+#pragma unroll
+        for (int g = 0; g < 4; ++g) tc::tma_load_3d(sA + g * kLBO, &tmZ, tj * 128 + g * 32, n0, c, &full[s]);
+#pragma unroll
+        for (int g = 0; g < NB / 32; ++g) tc::tma_load_3d(sB + g * kLBO, &tmH, tk * NB + g * 32, n0, c, &full[s]);
+      }
+    } else if (warp == 1 && lane == 0) {  // tensor-core issuer
+      const uint32_t idesc = tc::idesc_tf32(NB, 1, 1);  // both operands MN-major
+      for (int it = 0; it < nit; ++it) {
+        const int s = it % kStages;
+        if (!tc::mbar_wait(&full[s], (it / kStages) & 1)) __trap();
+        tc::tc_fence_after();
+        const uint32_t sA = ring + (uint32_t)s * kStageBytes, sB = sA + kABytes;
+#pragma unroll
+        for (int ks = 0; ks < kKB / 8; ++ks) {
+          if (dbg & 1) break;
+          tc::mma_tf32(tmem, smem_desc_mn_sw128(sA + ks * 1024, kLBO), smem_desc_mn_sw128(sB + ks * 1024, kLBO), idesc,
+                       (it > 0 || ks > 0) ? 1u : 0u);
+        }
+        tc::mma_commit(&empty[s]);
+      }
+      tc::mma_commit(&done);
+    }
+    __syncwarp();
+    if (!tc::mbar_wait(&done, 0)) __trap();
+    tc::tc_fence_after();
+    const int j = tj * 128 + tid;
+    const uint32_t lane_base = (uint32_t)(warp * 32) << 16;
+    float* out = part + (size_t)blockIdx.y * H * H;
+    for (int g = 0; g < NB / 16; ++g) {  // flush by vector reductions (see tc_dw2_kernel)
+      if (dbg & 4) break;
+      float v[16];
+      tc::tmem_ld16(tmem + lane_base + g * 16, v);
+      tc::tmem_ld_wait();
+      if (j < H) {
+#pragma unroll
+        for (int i = 0; i < 16; i += 4) {
+          const int k = tk * NB + g * 16 + i;
+          if (k < H)
+            asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(out + (size_t)j * H + k), "f"(v[i]), "f"(v[i + 1]),
+                         "f"(v[i + 2]), "f"(v[i + 3])
+                         : "memory");
+        }
+      }
+    }
+  }
+  tc::tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tc::tmem_dealloc(tmem, NB);
+}
+
 int dw2_dbg() {  // timing experiments only (PINN_DW2_DBG: 1 no MMAs, 2 no copies, 4 no flush): results are garbage
   static const int v = [] { const char* e = getenv("PINN_DW2_DBG"); return e ? atoi(e) : 0; }();
   return v;
@@ -220,6 +333,32 @@ int launch_dw2(const float* Zb, const float* Hb, int H, int C, int m, int Mc, fl
   return (int)cudaGetLastError();
 }
 
+template <int NB>
+int launch_dw3(const float* Zb, const float* Hb, int H, int C, int m, int Mc, float* part, int n_splits, cudaStream_t st) {
+  const int nblk = (m + kKB - 1) / kKB;
+  const int UBA = (H + 127) / 128, UBB = (H + NB - 1) / NB;
+  CUtensorMap tmZ, tmH;
+  const cuuint64_t gdim[3] = {(cuuint64_t)H, (cuuint64_t)m, (cuuint64_t)C}, gstr[2] = {(cuuint64_t)H * 4, (cuuint64_t)Mc * H * 4};
+  const cuuint32_t box[3] = {32, (cuuint32_t)kKB, 1}, est[3] = {1, 1, 1};
+  if (!tc_encode_tiled(&tmZ, 3, Zb, gdim, gstr, box, est, 2) || !tc_encode_tiled(&tmH, 3, Hb, gdim, gstr, box, est, 2))
+    return PINN_E_UNSUPPORTED;
+  const int tiles = UBA * UBB, kblocks = C * nblk;
+  int splits = kBlocks / tiles;
+  if (splits < 1) splits = 1;
+  if (splits > n_splits) splits = n_splits;
+  if (splits > kblocks) splits = kblocks;
+  const int smem = kStages * (4 + NB / 32) * kKB * 128 + 1024;
+  static bool set = false;
+  if (!set) {
+    cudaError_t e = cudaFuncSetAttribute((const void*)tc_dw3_kernel<NB>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) return (int)e;
+    set = true;
+  }
+  tc_dw3_kernel<NB><<<dim3(tiles, splits), 128, smem, st>>>(tmZ, tmH, H, nblk, kblocks, UBB, part, dw2_dbg());
+  count_launch(1);
+  return (int)cudaGetLastError();
+}
+
 }  // namespace
 
 // floats of scratch for the two re-tiled operands of one layer (+ the per-block column sums)
@@ -236,6 +375,22 @@ int tc_launch_dw2(const float* Zb, const float* Hb, int H, int C, int m, int Mc,
               : launch_dw2<256, false>(Zb, Hb, H, C, m, Mc, part, n_splits, scratch, db_slot, st);
   return x3 ? launch_dw2<128, true>(Zb, Hb, H, C, m, Mc, part, n_splits, scratch, db_slot, st)
             : launch_dw2<128, false>(Zb, Hb, H, C, m, Mc, part, n_splits, scratch, db_slot, st);
+}
+
+int tc_launch_dw3(const float* Zb, const float* Hb, int H, int C, int m, int Mc, float* part, int n_splits, cudaStream_t st) {
+  return rows_b(H) == 256 ? launch_dw3<256>(Zb, Hb, H, C, m, Mc, part, n_splits, st) : launch_dw3<128>(Zb, Hb, H, C, m, Mc, part, n_splits, st);
+}
+
+int tc_colsum_finish(const float* colsum, int nrows, int H, float* db_slot, cudaStream_t st) {
+  colsum_finish_kernel<<<(H + 31) / 32, 1024, 0, st>>>(colsum, nrows, H, db_slot);
+  count_launch(1);
+  return (int)cudaGetLastError();
+}
+
+// PINN_DW_DIRECT=0 keeps the re-tiling pass in TF32 mode (A/B measurements)
+bool tc_dw_direct() {
+  static const bool v = [] { const char* e = getenv("PINN_DW_DIRECT"); return !(e && e[0] == '0'); }();
+  return v;
 }
 
 }  // namespace pinn

@@ -1,5 +1,6 @@
 // Pieces shared by the wide-path translation units (wide.cu, wide_tc.cu).
 #pragma once
+#include <cuda.h>
 #include <cuda_runtime.h>
 
 #include "pinn_common.h"
@@ -168,7 +169,12 @@ int fused_wide_launch(const WNet& n, const pinn_domain* dom, float* stash, const
 // tensor-core GEMMs (wide_tc.cu)
 template <int ACT, int EPI>
 int tc_launch_rows(const WNet& n, const float* Bsrc, const float* Aw, const float* bias, float* Zio, float* Hout, int m, int Mc,
-                   bool round_out, cudaStream_t st);
+                   bool round_out, float* colsum, cudaStream_t st);  // colsum (reverse, TF32 mode): [ceil(m/16)][H] sums of zbar's value channel
+bool tc_encode_tiled(CUtensorMap* tm, int rank, const void* base, const cuuint64_t* gdim, const cuuint64_t* gstr, const cuuint32_t* box,
+                     const cuuint32_t* est, int swizzle);  // 0 none, 1 SWIZZLE_128B, 2 SWIZZLE_128B_ATOM_32B
+bool tc_dw_direct();  // TF32 mode: dW operands straight from the planes (tc_launch_dw3) instead of re-tiled copies
+int tc_launch_dw3(const float* Zb, const float* Hb, int H, int C, int m, int Mc, float* part, int n_splits, cudaStream_t st);
+int tc_colsum_finish(const float* colsum, int nrows, int H, float* db_slot, cudaStream_t st);
 int tc_dw_splits(int H);
 int tc_rows_points(int C);  // points per tile of the row GEMMs
 int64_t tc_dw2_scratch_floats(int H, int C, int Mc, bool x3);

@@ -79,7 +79,7 @@ __device__ __forceinline__ void release_tmem(uint64_t* bar, int lane) {
 template <int NF, int NS, int ACT, int EPI>
 __device__ __forceinline__ void rows_epilogue(const WNet& net, uint32_t tmem, int warp, int lane, int n0, int j0, int m, size_t plane,
                                               int a_rows, const float* __restrict__ bias, float* __restrict__ Zio,
-                                              float* __restrict__ Hout, bool round_out, uint64_t* release) {
+                                              float* __restrict__ Hout, bool round_out, uint64_t* release, int dbg = 0, float* __restrict__ colsum = nullptr) {
   constexpr int C = 1 + NF + NS;
   using T = TileCfg<C>;
   constexpr int P = T::P;
@@ -100,12 +100,13 @@ __device__ __forceinline__ void rows_epilogue(const WNet& net, uint32_t tmem, in
       auto fetch = [&](int quad, float (&dst)[C][4]) {
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
-          const bool ok = quad * 4 + i < left;
+          const bool ok = quad * 4 + i < left && !(dbg & 16);
 #pragma unroll
           for (int c = 0; c < C; ++c) dst[c][i] = ok ? zp[c * plane + (size_t)(quad * 4 + i) * H] : 0.f;
         }
       };
       fetch(0, zin[0]);
+      float dbsum = 0.f;  // db_{l-1} rides along: the group's sum of the unrounded value channel
 #pragma unroll
       for (int oct = 0; oct < 2; ++oct) {
         float v[C][8];
@@ -126,13 +127,15 @@ __device__ __forceinline__ void rows_epilogue(const WNet& net, uint32_t tmem, in
               z[c] = zin[quad & 1][c][i];
             }
             jet_bwd_t<ACT, NF, NS, false>(z, hb, o);
-            if (quad * 4 + i < left) {
+            if (quad * 4 + i < left && !(dbg & 8)) {
+              dbsum += o[0];
 #pragma unroll
               for (int c = 0; c < C; ++c) zp[c * plane + (size_t)(quad * 4 + i) * H] = round_out ? tc::to_tf32(o[c]) : o[c];
             }
           }
         }
       }
+      if (colsum != nullptr && jok) colsum[(size_t)(nb >> 4) * H + j] = dbsum;
     } else {
       float v[C][16];
 #pragma unroll
@@ -142,7 +145,7 @@ __device__ __forceinline__ void rows_epilogue(const WNet& net, uint32_t tmem, in
       float* hp = Hout + (size_t)nb * H + j;
 #pragma unroll
       for (int i = 0; i < 16; ++i) {
-        if (i < left) {
+        if (i < left && !(dbg & 8)) {
           float z[C], o[C];
 #pragma unroll
           for (int c = 0; c < C; ++c) z[c] = v[c][i];
@@ -337,7 +340,7 @@ __global__ void __launch_bounds__(320, 1) tc_rows2_kernel(WNet net, const __grid
                                                           const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmZ,
                                                           const __grid_constant__ CUtensorMap tmH, const float* __restrict__ bias,
                                                           float* __restrict__ Zio, float* __restrict__ Hout, int m, int Mc, int a_rows,
-                                                          int tiles_j, int n_tiles, int round_out, int dbg) {
+                                                          int tiles_j, int n_tiles, int round_out, int dbg, float* __restrict__ colsum) {
   constexpr int C = 1 + NF + NS;
   using T = TileCfg<C>;
   using R = Rows2Cfg<C, EPI>;
@@ -383,7 +386,7 @@ __global__ void __launch_bounds__(320, 1) tc_rows2_kernel(WNet net, const __grid
                                            staging, st_phase, round_out != 0, &acc_empty[a]);
       } else {
         rows_epilogue<NF, NS, ACT, EPI>(net, tmem + a * 256, warp, lane, (t / tiles_j) * P, (t % tiles_j) * 128, m, plane, a_rows, bias,
-                                        Zio, Hout, round_out != 0, &acc_empty[a]);
+                                        Zio, Hout, round_out != 0, &acc_empty[a], dbg, colsum);
       }
     }
     if constexpr (R::kTmaEpi) {
@@ -457,7 +460,7 @@ __global__ void transpose_kernel(const float* __restrict__ W, float* __restrict_
 
 // cuTensorMapEncodeTiled through the runtime's driver entry point (no link-time dependency on libcuda)
 bool encode_tiled(CUtensorMap* tm, int rank, const void* base, const cuuint64_t* gdim, const cuuint64_t* gstr, const cuuint32_t* box,
-                  const cuuint32_t* est, bool swizzle128 = true) {
+                  const cuuint32_t* est, int swizzle = 1) {  // 0 none, 1 SWIZZLE_128B, 2 SWIZZLE_128B_ATOM_32B
   typedef CUresult (*Fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
                          const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
   static const Fn fn = [] {
@@ -469,7 +472,9 @@ bool encode_tiled(CUtensorMap* tm, int rank, const void* base, const cuuint64_t*
   }();
   if (!fn) return false;
   return fn(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, (cuuint32_t)rank, const_cast<void*>(base), gdim, gstr, box, est,
-            CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+            CU_TENSOR_MAP_INTERLEAVE_NONE,
+            swizzle == 2 ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : swizzle == 1 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE,
+            CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
@@ -480,7 +485,7 @@ int rows2_dbg() {  // timing experiments only (PINN_ROWS2_DBG: 1 no MMAs, 2 no l
 
 template <int NF, int NS, int ACT, int EPI, bool X3>
 int launch_rows_c(const WNet& n, const float* Bsrc, const float* Aw, const float* bias, float* Zio, float* Hout, int m, int Mc,
-                  int a_rows, bool round_out, cudaStream_t st) {
+                  int a_rows, bool round_out, float* colsum, cudaStream_t st) {
   constexpr int C = 1 + NF + NS;
   using T = TileCfg<C>;
   if constexpr (!X3) {  // TF32 mode: operands are already rounded (tc_rows2_kernel, TMA-fed)
@@ -513,13 +518,13 @@ int launch_rows_c(const WNet& n, const float* Bsrc, const float* Aw, const float
       // output planes [C][Mc][H] as {unit, point, channel}; boxes {128 units, 4 points, C}, no swizzle; only valid elements are stored
       const cuuint64_t gdim[3] = {(cuuint64_t)n.H, (cuuint64_t)m, (cuuint64_t)C}, gstr[2] = {(cuuint64_t)n.H * 4, (cuuint64_t)Mc * n.H * 4};
       const cuuint32_t box[3] = {128, 4, (cuuint32_t)C}, est[3] = {1, 1, 1};
-      if (!encode_tiled(&tmZ, 3, Zio, gdim, gstr, box, est, false) || !encode_tiled(&tmH, 3, Hout, gdim, gstr, box, est, false))
+      if (!encode_tiled(&tmZ, 3, Zio, gdim, gstr, box, est, 0) || !encode_tiled(&tmH, 3, Hout, gdim, gstr, box, est, 0))
         return PINN_E_UNSUPPORTED;
     }
     const int tiles_j = (a_rows + 127) / 128, n_tiles = ((m + T::P - 1) / T::P) * tiles_j;
     const int grid = n_tiles < n_sm ? n_tiles : n_sm;
     tc_rows2_kernel<NF, NS, ACT, EPI><<<grid, 320, R::kSmemBytes, st>>>(n, tmA, tmB, tmZ, tmH, bias, Zio, Hout, m, Mc, a_rows, tiles_j, n_tiles,
-                                                                   round_out ? 1 : 0, rows2_dbg());
+                                                                   round_out ? 1 : 0, rows2_dbg(), colsum);
     count_launch(1);
     return (int)cudaGetLastError();
   } else {
@@ -540,15 +545,20 @@ int launch_rows_c(const WNet& n, const float* Bsrc, const float* Aw, const float
 
 }  // namespace
 
+bool tc_encode_tiled(CUtensorMap* tm, int rank, const void* base, const cuuint64_t* gdim, const cuuint64_t* gstr, const cuuint32_t* box,
+                     const cuuint32_t* est, int swizzle) {
+  return encode_tiled(tm, rank, base, gdim, gstr, box, est, swizzle);
+}
+
 template <int ACT, int EPI>
 int tc_launch_rows(const WNet& n, const float* Bsrc, const float* Aw, const float* bias, float* Zio, float* Hout, int m, int Mc,
-                   bool round_out, cudaStream_t st) {
+                   bool round_out, float* colsum, cudaStream_t st) {
   const int a_rows = n.H;
   switch (n.NF * 4 + n.NS) {  // NS <= NF <= 3 (make_net)
 #define CASE(F, S_)                                                                                                  \
   case F * 4 + S_:                                                                                                   \
-    return n.precision == 2 ? launch_rows_c<F, S_, ACT, EPI, true>(n, Bsrc, Aw, bias, Zio, Hout, m, Mc, a_rows, false, st) \
-                            : launch_rows_c<F, S_, ACT, EPI, false>(n, Bsrc, Aw, bias, Zio, Hout, m, Mc, a_rows, round_out, st);
+    return n.precision == 2 ? launch_rows_c<F, S_, ACT, EPI, true>(n, Bsrc, Aw, bias, Zio, Hout, m, Mc, a_rows, false, nullptr, st) \
+                            : launch_rows_c<F, S_, ACT, EPI, false>(n, Bsrc, Aw, bias, Zio, Hout, m, Mc, a_rows, round_out, colsum, st);
     CASE(0, 0) CASE(1, 0) CASE(1, 1) CASE(2, 0) CASE(2, 1) CASE(2, 2) CASE(3, 0) CASE(3, 1) CASE(3, 2) CASE(3, 3)
 #undef CASE
   }
@@ -556,8 +566,8 @@ int tc_launch_rows(const WNet& n, const float* Bsrc, const float* Aw, const floa
 }
 
 #define INST(A)                                                                                                              \
-  template int tc_launch_rows<A, 0>(const WNet&, const float*, const float*, const float*, float*, float*, int, int, bool, cudaStream_t); \
-  template int tc_launch_rows<A, 1>(const WNet&, const float*, const float*, const float*, float*, float*, int, int, bool, cudaStream_t);
+  template int tc_launch_rows<A, 0>(const WNet&, const float*, const float*, const float*, float*, float*, int, int, bool, float*, cudaStream_t); \
+  template int tc_launch_rows<A, 1>(const WNet&, const float*, const float*, const float*, float*, float*, int, int, bool, float*, cudaStream_t);
 INST(PINN_ACT_TANH)
 INST(PINN_ACT_SILU)
 INST(PINN_ACT_SIN)
