@@ -698,7 +698,7 @@ int run_chunks(const WNet& n, const WideLayout& wl, float* ws, int mode, const p
   // TF32 mode: the operands of the tensor-core GEMMs (H_1 .. H_{L-1}, zbar_L .. zbar_2, the weight copies) are stored
   // rounded by their producers; H_L (output layer) and zbar_1 (first-layer gradient) stay FP32 (wide_tc.cu)
   const bool tf32 = n.precision == 1;
-  const bool direct = tf32 && tc_dw_direct();  // dW operands by TMA straight from the planes; db from the producers of zbar
+  const bool direct = n.precision != 0 && tc_dw_direct();  // dW operands by TMA straight from the planes; db from the producers of zbar
   Coords xs;
   for (int d = 0; d < PINN_MAX_IN; ++d) xs.p[d] = d < n.n_in ? coords[d] : nullptr;
   for (int64_t n0 = 0; n0 < N; n0 += wl.Mc) {
@@ -770,7 +770,7 @@ int run_chunks(const WNet& n, const WideLayout& wl, float* ws, int mode, const p
             int rc = tc_colsum_finish(ws + wl.tdw, (m + 15) / 16, H, dbp, st);
             if (rc) return rc;
           }
-          int rc = tc_launch_dw3(zb, hprev, H, C, m, wl.Mc, dwp, wl.n_splits, st);
+          int rc = tc_launch_dw3(zb, hprev, H, C, m, wl.Mc, dwp, wl.n_splits, n.precision == 2, st);
           if (rc) return rc;
         } else if (n.precision) {  // db_l rides along with the re-tiling of zbar_l
           int rc = tc_launch_dw2(zb, hprev, H, C, m, wl.Mc, dwp, wl.n_splits, ws + wl.tdw, dbp, n.precision == 2, st);

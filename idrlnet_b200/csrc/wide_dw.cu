@@ -296,6 +296,129 @@ __global__ void __launch_bounds__(128, 1) tc_dw3_kernel(const __grid_constant__ 
   if (warp == 0) tc::tmem_dealloc(tmem, NB);
 }
 
+// FP32-grade (3xTF32) mode, same idea: the planes hold FP32 values, so the split into hi = tf32(x) and lo = tf32(x - hi) happens
+// in shared memory.  TMA delivers the raw boxes (full[s]); four converter warps rewrite them in place as hi and write lo into the
+// second half of the stage -- elementwise, so the swizzled layout is simply carried over -- then publish the stage to the MMA
+// thread (conv[s], one arrival per warp after fence.proxy.async); 12 MMAs per K block (lo*hi + hi*lo + hi*hi, the order of
+// tc_dw2_kernel<., true>).  Per stage the converters move 96 KB through shared memory (~770 cycles at 128 B/clk) next to ~840
+// cycles of MMAs at NB = 128: the pass hides behind the tensor pipe, and the re-tiled hi / lo copies (HBM write + read of twice
+// the operands) are gone.  Stage = [A hi | B hi | A lo | B lo] = 64 KB, three stages.
+constexpr int kStagesX3 = 3;
+
+template <int NB>
+__global__ void __launch_bounds__(192, 1) tc_dw3x_kernel(const __grid_constant__ CUtensorMap tmZ, const __grid_constant__ CUtensorMap tmH,
+                                                         int H, int nblk, int kblocks, int tiles_k, float* __restrict__ part) {
+  extern __shared__ __align__(1024) uint8_t sm_raw[];
+  __shared__ uint64_t full[kStagesX3], conv[kStagesX3], empty[kStagesX3], done;
+  __shared__ uint32_t tmem_slot;
+  constexpr int kABytes = 4 * kKB * 128, kBBytes = (NB / 32) * kKB * 128, kRawBytes = kABytes + kBBytes, kStageBytes = 2 * kRawBytes;
+  constexpr uint32_t kLBO = kKB * 128;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int tj = blockIdx.x / tiles_k, tk = blockIdx.x % tiles_k;
+  const int per = (kblocks + gridDim.y - 1) / gridDim.y;
+  const int kb0 = blockIdx.y * per, kb1 = (kb0 + per < kblocks) ? kb0 + per : kblocks;
+  const int nit = kb1 - kb0;
+  const uint32_t ring = (tc::smem_u32(sm_raw) + 1023u) & ~1023u;
+  if (tid == 0) {
+    for (int s = 0; s < kStagesX3; ++s) {
+      tc::mbar_init(&full[s], 1);
+      tc::mbar_init(&conv[s], 4);
+      tc::mbar_init(&empty[s], 1);
+    }
+    tc::mbar_init(&done, 1);
+    tc::fence_mbar_init();
+  }
+  if (warp == 0) tc::tmem_alloc(&tmem_slot, NB);
+  tc::tc_fence_before();
+  __syncthreads();
+  tc::tc_fence_after();
+  const uint32_t tmem = tmem_slot;
+  if (nit > 0) {
+    if (warp == 0) {
+      if (lane == 0) {  // producer
+        tc::tma_prefetch_desc(&tmZ);
+        tc::tma_prefetch_desc(&tmH);
+        for (int it = 0; it < nit; ++it) {
+          const int s = it % kStagesX3;
+          if (it >= kStagesX3 && !tc::mbar_wait(&empty[s], ((it / kStagesX3) - 1) & 1)) __trap();
+          const int kb = kb0 + it, c = kb / nblk, n0 = (kb - c * nblk) * kKB;
+          const uint32_t sA = ring + (uint32_t)s * kStageBytes, sB = sA + kABytes;
+          tc::mbar_expect_tx(&full[s], (uint32_t)kRawBytes);
+#pragma unroll
+          for (int g = 0; g < 4; ++g) tc::tma_load_3d(sA + g * kLBO, &tmZ, tj * 128 + g * 32, n0, c, &full[s]);
+#pragma unroll
+          for (int g = 0; g < NB / 32; ++g) tc::tma_load_3d(sB + g * kLBO, &tmH, tk * NB + g * 32, n0, c, &full[s]);
+        }
+      }
+    } else if (warp == 1) {
+      if (lane == 0) {  // tensor-core issuer
+        const uint32_t idesc = tc::idesc_tf32(NB, 1, 1);
+        for (int it = 0; it < nit; ++it) {
+          const int s = it % kStagesX3;
+          if (!tc::mbar_wait(&conv[s], (it / kStagesX3) & 1)) __trap();
+          tc::tc_fence_after();
+          const uint32_t sA = ring + (uint32_t)s * kStageBytes, sB = sA + kABytes;
+#pragma unroll
+          for (int ks = 0; ks < kKB / 8; ++ks) {
+            const uint64_t da = smem_desc_mn_sw128(sA + ks * 1024, kLBO), db = smem_desc_mn_sw128(sB + ks * 1024, kLBO);
+            const uint64_t dal = smem_desc_mn_sw128(sA + kRawBytes + ks * 1024, kLBO), dbl = smem_desc_mn_sw128(sB + kRawBytes + ks * 1024, kLBO);
+            tc::mma_tf32(tmem, dal, db, idesc, (it > 0 || ks > 0) ? 1u : 0u);
+            tc::mma_tf32(tmem, da, dbl, idesc, 1u);
+            tc::mma_tf32(tmem, da, db, idesc, 1u);
+          }
+          tc::mma_commit(&empty[s]);
+        }
+        tc::mma_commit(&done);
+      }
+    } else {  // converter warps 2 .. 5, then the flush (TMEM lane quarter = warp & 3)
+      const int ct = tid - 64;
+      for (int it = 0; it < nit; ++it) {
+        const int s = it % kStagesX3;
+        if (!tc::mbar_wait(&full[s], (it / kStagesX3) & 1)) __trap();
+        const uint32_t base = ring + (uint32_t)s * kStageBytes + (uint32_t)ct * 16;
+#pragma unroll 4
+        for (int i = 0; i < kRawBytes / (128 * 16); ++i) {
+          const uint32_t a = base + (uint32_t)i * (128 * 16);
+          float4 x;
+          asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(x.x), "=f"(x.y), "=f"(x.z), "=f"(x.w) : "r"(a) : "memory");
+          const float4 hi = tc::to_tf32(x);
+          const float4 lo = tc::to_tf32(make_float4(x.x - hi.x, x.y - hi.y, x.z - hi.z, x.w - hi.w));
+          asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(a), "f"(hi.x), "f"(hi.y), "f"(hi.z), "f"(hi.w) : "memory");
+          asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(a + (uint32_t)kRawBytes), "f"(lo.x), "f"(lo.y), "f"(lo.z), "f"(lo.w)
+                       : "memory");
+        }
+        tc::fence_async_smem();
+        __syncwarp();
+        if (lane == 0) tc::mbar_arrive(&conv[s]);
+      }
+      if (!tc::mbar_wait(&done, 0)) __trap();
+      tc::tc_fence_after();
+      const int q = warp & 3;
+      const int j = tj * 128 + q * 32 + lane;
+      const uint32_t lane_base = (uint32_t)(q * 32) << 16;
+      float* out = part + (size_t)blockIdx.y * H * H;
+      for (int g = 0; g < NB / 16; ++g) {  // flush by vector reductions (see tc_dw2_kernel)
+        float v[16];
+        tc::tmem_ld16(tmem + lane_base + g * 16, v);
+        tc::tmem_ld_wait();
+        if (j < H) {
+#pragma unroll
+          for (int i = 0; i < 16; i += 4) {
+            const int k = tk * NB + g * 16 + i;
+            if (k < H)
+              asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(out + (size_t)j * H + k), "f"(v[i]), "f"(v[i + 1]),
+                           "f"(v[i + 2]), "f"(v[i + 3])
+                           : "memory");
+          }
+        }
+      }
+    }
+  }
+  tc::tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tc::tmem_dealloc(tmem, NB);
+}
+
 int dw2_dbg() {  // timing experiments only (PINN_DW2_DBG: 1 no MMAs, 2 no copies, 4 no flush): results are garbage
   static const int v = [] { const char* e = getenv("PINN_DW2_DBG"); return e ? atoi(e) : 0; }();
   return v;
@@ -359,6 +482,32 @@ int launch_dw3(const float* Zb, const float* Hb, int H, int C, int m, int Mc, fl
   return (int)cudaGetLastError();
 }
 
+int launch_dw3x(const float* Zb, const float* Hb, int H, int C, int m, int Mc, float* part, int n_splits, cudaStream_t st) {
+  constexpr int NB = 128;
+  const int nblk = (m + kKB - 1) / kKB;
+  const int UBA = (H + 127) / 128, UBB = (H + NB - 1) / NB;
+  CUtensorMap tmZ, tmH;
+  const cuuint64_t gdim[3] = {(cuuint64_t)H, (cuuint64_t)m, (cuuint64_t)C}, gstr[2] = {(cuuint64_t)H * 4, (cuuint64_t)Mc * H * 4};
+  const cuuint32_t box[3] = {32, (cuuint32_t)kKB, 1}, est[3] = {1, 1, 1};
+  if (!tc_encode_tiled(&tmZ, 3, Zb, gdim, gstr, box, est, 2) || !tc_encode_tiled(&tmH, 3, Hb, gdim, gstr, box, est, 2))
+    return PINN_E_UNSUPPORTED;
+  const int tiles = UBA * UBB, kblocks = C * nblk;
+  int splits = kBlocks / tiles;
+  if (splits < 1) splits = 1;
+  if (splits > n_splits) splits = n_splits;
+  if (splits > kblocks) splits = kblocks;
+  const int smem = kStagesX3 * 2 * (4 + NB / 32) * kKB * 128 + 1024;
+  static bool set = false;
+  if (!set) {
+    cudaError_t e = cudaFuncSetAttribute((const void*)tc_dw3x_kernel<NB>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) return (int)e;
+    set = true;
+  }
+  tc_dw3x_kernel<NB><<<dim3(tiles, splits), 192, smem, st>>>(tmZ, tmH, H, nblk, kblocks, UBB, part);
+  count_launch(1);
+  return (int)cudaGetLastError();
+}
+
 }  // namespace
 
 // floats of scratch for the two re-tiled operands of one layer (+ the per-block column sums)
@@ -377,7 +526,8 @@ int tc_launch_dw2(const float* Zb, const float* Hb, int H, int C, int m, int Mc,
             : launch_dw2<128, false>(Zb, Hb, H, C, m, Mc, part, n_splits, scratch, db_slot, st);
 }
 
-int tc_launch_dw3(const float* Zb, const float* Hb, int H, int C, int m, int Mc, float* part, int n_splits, cudaStream_t st) {
+int tc_launch_dw3(const float* Zb, const float* Hb, int H, int C, int m, int Mc, float* part, int n_splits, bool x3, cudaStream_t st) {
+  if (x3) return launch_dw3x(Zb, Hb, H, C, m, Mc, part, n_splits, st);
   return rows_b(H) == 256 ? launch_dw3<256>(Zb, Hb, H, C, m, Mc, part, n_splits, st) : launch_dw3<128>(Zb, Hb, H, C, m, Mc, part, n_splits, st);
 }
 
@@ -387,7 +537,7 @@ int tc_colsum_finish(const float* colsum, int nrows, int H, float* db_slot, cuda
   return (int)cudaGetLastError();
 }
 
-// PINN_DW_DIRECT=0 keeps the re-tiling pass in TF32 mode (A/B measurements)
+// PINN_DW_DIRECT=0 keeps the re-tiling pass of the tensor modes (A/B measurements)
 bool tc_dw_direct() {
   static const bool v = [] { const char* e = getenv("PINN_DW_DIRECT"); return !(e && e[0] == '0'); }();
   return v;

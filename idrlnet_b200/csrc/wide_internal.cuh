@@ -172,8 +172,8 @@ int tc_launch_rows(const WNet& n, const float* Bsrc, const float* Aw, const floa
                    bool round_out, float* colsum, cudaStream_t st);  // colsum (reverse, TF32 mode): [ceil(m/16)][H] sums of zbar's value channel
 bool tc_encode_tiled(CUtensorMap* tm, int rank, const void* base, const cuuint64_t* gdim, const cuuint64_t* gstr, const cuuint32_t* box,
                      const cuuint32_t* est, int swizzle);  // 0 none, 1 SWIZZLE_128B, 2 SWIZZLE_128B_ATOM_32B
-bool tc_dw_direct();  // TF32 mode: dW operands straight from the planes (tc_launch_dw3) instead of re-tiled copies
-int tc_launch_dw3(const float* Zb, const float* Hb, int H, int C, int m, int Mc, float* part, int n_splits, cudaStream_t st);
+bool tc_dw_direct();  // tensor modes: dW operands straight from the planes (tc_launch_dw3) instead of re-tiled copies
+int tc_launch_dw3(const float* Zb, const float* Hb, int H, int C, int m, int Mc, float* part, int n_splits, bool x3, cudaStream_t st);
 int tc_colsum_finish(const float* colsum, int nrows, int H, float* db_slot, cudaStream_t st);
 int tc_dw_splits(int H);
 int tc_rows_points(int C);  // points per tile of the row GEMMs

@@ -165,7 +165,7 @@ __device__ __forceinline__ void rows_epilogue(const WNet& net, uint32_t tmem, in
 template <int NF, int NS, int ACT, int EPI, bool X3>
 __global__ void __launch_bounds__(256, 2) tc_rows_kernel(WNet net, const float* __restrict__ Bsrc, const float* __restrict__ Aw,
                                                       const float* __restrict__ bias, float* __restrict__ Zio,
-                                                      float* __restrict__ Hout, int m, int Mc, int a_rows, int round_out) {
+                                                      float* __restrict__ Hout, int m, int Mc, int a_rows, int round_out, float* __restrict__ colsum) {
   constexpr int C = 1 + NF + NS;
   using T = TileCfg<C>;
   constexpr int P = T::P, N = T::N;
@@ -242,7 +242,7 @@ __global__ void __launch_bounds__(256, 2) tc_rows_kernel(WNet net, const float* 
   if (!ok) __trap();
   tc::tc_fence_after();
 
-  rows_epilogue<NF, NS, ACT, EPI>(net, tmem, warp, lane, n0, j0, m, plane, a_rows, bias, Zio, Hout, round_out != 0, nullptr);
+  rows_epilogue<NF, NS, ACT, EPI>(net, tmem, warp, lane, n0, j0, m, plane, a_rows, bias, Zio, Hout, round_out != 0, nullptr, 0, colsum);
   tc::tc_fence_before();
   __syncthreads();
   if (warp == 0) tc::tmem_dealloc(tmem, 256);
@@ -537,7 +537,7 @@ int launch_rows_c(const WNet& n, const float* Bsrc, const float* Aw, const float
     attr_set = true;
   }
   dim3 grid((m + T::P - 1) / T::P, (a_rows + 127) / 128);
-  tc_rows_kernel<NF, NS, ACT, EPI, X3><<<grid, 256, smem, st>>>(n, Bsrc, Aw, bias, Zio, Hout, m, Mc, a_rows, round_out ? 1 : 0);
+  tc_rows_kernel<NF, NS, ACT, EPI, X3><<<grid, 256, smem, st>>>(n, Bsrc, Aw, bias, Zio, Hout, m, Mc, a_rows, round_out ? 1 : 0, colsum);
   count_launch(1);
   return (int)cudaGetLastError();
   }
@@ -557,7 +557,7 @@ int tc_launch_rows(const WNet& n, const float* Bsrc, const float* Aw, const floa
   switch (n.NF * 4 + n.NS) {  // NS <= NF <= 3 (make_net)
 #define CASE(F, S_)                                                                                                  \
   case F * 4 + S_:                                                                                                   \
-    return n.precision == 2 ? launch_rows_c<F, S_, ACT, EPI, true>(n, Bsrc, Aw, bias, Zio, Hout, m, Mc, a_rows, false, nullptr, st) \
+    return n.precision == 2 ? launch_rows_c<F, S_, ACT, EPI, true>(n, Bsrc, Aw, bias, Zio, Hout, m, Mc, a_rows, false, colsum, st) \
                             : launch_rows_c<F, S_, ACT, EPI, false>(n, Bsrc, Aw, bias, Zio, Hout, m, Mc, a_rows, round_out, colsum, st);
     CASE(0, 0) CASE(1, 0) CASE(1, 1) CASE(2, 0) CASE(2, 1) CASE(2, 2) CASE(3, 0) CASE(3, 1) CASE(3, 2) CASE(3, 3)
 #undef CASE
