@@ -478,7 +478,7 @@ bool encode_tiled(CUtensorMap* tm, int rank, const void* base, const cuuint64_t*
             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
-int rows2_dbg() {  // timing experiments only (PINN_ROWS2_DBG: 1 no MMAs, 2 no loads, 4 no epilogue): results are garbage
+int rows2_dbg() {  // timing experiments only (PINN_ROWS2_DBG: 1 no MMAs, 2 no loads, 4 no epilogue, 8 no epilogue stores, 16 no reverse Z loads): results are garbage
   static const int v = [] { const char* e = getenv("PINN_ROWS2_DBG"); return e ? atoi(e) : 0; }();
   return v;
 }
