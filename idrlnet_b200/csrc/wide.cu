@@ -52,24 +52,49 @@ struct Coords {
   const float* p[PINN_MAX_IN];
 };
 
-template <int ACT>
-__global__ void first_fwd_kernel(WNet net, Coords xs, int64_t n0, int m, int Mc, float* __restrict__ Z, float* __restrict__ Hb) {
+constexpr int kFirstPPT = 8;  // points per thread of first_fwd_kernel
+// thread = (group of kFirstPPT consecutive points, unit j): the unit's first-layer row and the derivative channels of Z_1 (the
+// weights themselves) stay in registers over the group; compile-time channel structure (the runtime-indexed version kept its jets
+// in local memory: 2.1 TB/s of plane stores)
+template <int ACT, int NF, int NS>
+__global__ void __launch_bounds__(256) first_fwd_kernel(WNet net, Coords xs, int64_t n0, int m, int Mc, float* __restrict__ Z,
+                                                        float* __restrict__ Hb) {
+  constexpr int C = 1 + NF + NS;
   const int H = net.H;
   const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= (int64_t)m * H) return;
-  const int n = (int)(idx / H), j = (int)(idx % H);
-  float z[kMaxC] = {}, h[kMaxC] = {};
-  float v = net.b[0][j];
-  for (int d = 0; d < net.n_in; ++d) v += net.W[0][j * net.n_in + d] * xs.p[d][n0 + n];
-  z[0] = v;
-  for (int i = 0; i < net.NF; ++i) z[1 + i] = net.W[0][j * net.n_in + net.first_in[i]];
-  for (int s = 0; s < net.NS; ++s) z[1 + net.NF + s] = 0.f;
-  jet_fwd<ACT>(net.NF, net.NS, z, h);
+  const int groups = (m + kFirstPPT - 1) / kFirstPPT;
+  if (idx >= (int64_t)groups * H) return;
+  const int g = (int)(idx / H), j = (int)(idx - (int64_t)g * H);
+  float w[PINN_MAX_IN];
+#pragma unroll
+  for (int d = 0; d < PINN_MAX_IN; ++d) w[d] = d < net.n_in ? net.W[0][j * net.n_in + d] : 0.f;
+  float z[C], h[C];
+#pragma unroll
+  for (int i = 0; i < NF; ++i) {
+    const int fi = net.first_in[i];
+    float wf = w[0];
+#pragma unroll
+    for (int d = 1; d < PINN_MAX_IN; ++d) wf = (fi == d) ? w[d] : wf;
+    z[1 + i] = wf;
+  }
+#pragma unroll
+  for (int s = 0; s < NS; ++s) z[1 + NF + s] = 0.f;
+  const float bj = net.b[0][j];
   const size_t plane = (size_t)Mc * H;
   const bool round = net.precision == 1 && net.L >= 2;  // TF32 mode: H_1 is a tensor-core operand, stored rounded
-  for (int c = 0; c < net.C; ++c) {
-    Z[c * plane + (size_t)n * H + j] = z[c];
-    Hb[c * plane + (size_t)n * H + j] = round ? tf32_rna(h[c]) : h[c];
+  const int nb = g * kFirstPPT, ne = (nb + kFirstPPT < m) ? nb + kFirstPPT : m;
+  for (int n = nb; n < ne; ++n) {
+    float v = bj;
+#pragma unroll
+    for (int d = 0; d < PINN_MAX_IN; ++d)
+      if (d < net.n_in) v += w[d] * xs.p[d][n0 + n];
+    z[0] = v;
+    jet_fwd_t<ACT, NF, NS, false>(z, h);
+#pragma unroll
+    for (int c = 0; c < C; ++c) {
+      Z[c * plane + (size_t)n * H + j] = z[c];
+      Hb[c * plane + (size_t)n * H + j] = round ? tf32_rna(h[c]) : h[c];
+    }
   }
 }
 
@@ -447,10 +472,11 @@ __global__ void __launch_bounds__(256) head_point_kernel(WNet net, const __grid_
 
 // head_bwd: streaming over (point, unit): zbar_L = act'(Z_L; Wout^T ybar) in place, dWout += ybar^T h_L.
 // grid (ceil(H/128), kBlocks); block = 128 units x 4 point lanes; blockIdx.y is the partial slot.
-template <int ACT, int C>
+template <int ACT, int NF, int NS>
 __global__ void __launch_bounds__(1024) head_bwd_kernel(WNet net, const float* __restrict__ Yb, float* __restrict__ ZL,
                                                         const float* __restrict__ HL, int m, int Mc, float* __restrict__ part,
                                                         float* __restrict__ dbp) {
+  constexpr int C = 1 + NF + NS;  // compile-time channel structure: the jets stay in registers
   __shared__ float red[8][5][129];
   const int H = net.H, O = net.n_out;
   const int jl = threadIdx.x & 127, pl = threadIdx.x >> 7;
@@ -466,8 +492,7 @@ __global__ void __launch_bounds__(1024) head_bwd_kernel(WNet net, const float* _
 #pragma unroll
     for (int o = 0; o < 4; ++o) wo[o] = (o < O) ? net.W[net.L][o * H + j] : 0.f;
     for (int n = nb + pl; n < ne; n += 16) {  // two points (n, n + 8) in flight
-      float z[2][kMaxC] = {}, h[2][C];
-      float4 yb[2][C];
+      float z[2][C], h[2][C];
 #pragma unroll
       for (int u = 0; u < 2; ++u) {
         const int nn = n + 8 * u;
@@ -476,21 +501,20 @@ __global__ void __launch_bounds__(1024) head_bwd_kernel(WNet net, const float* _
           const bool ok = nn < ne;
           z[u][c] = ok ? ZL[c * plane + (size_t)nn * H + j] : 0.f;
           h[u][c] = ok ? HL[c * plane + (size_t)nn * H + j] : 0.f;
-          yb[u][c] = ok ? *reinterpret_cast<const float4*>(Yb + ((size_t)nn * C + c) * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
         }
       }
 #pragma unroll
       for (int u = 0; u < 2; ++u) {
         const int nn = n + 8 * u;
-        float hb[kMaxC] = {}, zb[kMaxC] = {};
+        float hb[C], zb[C];
 #pragma unroll
         for (int c = 0; c < C; ++c) {
-          const float4 y4 = yb[u][c];
+          // ybar of the point: the same 16 bytes for the 128 units of the point lane (a broadcast hit in L1)
+          const float4 y4 = nn < ne ? *reinterpret_cast<const float4*>(Yb + ((size_t)nn * C + c) * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
           hb[c] = wo[0] * y4.x + wo[1] * y4.y + wo[2] * y4.z + wo[3] * y4.w;
           gW[0] += y4.x * h[u][c]; gW[1] += y4.y * h[u][c]; gW[2] += y4.z * h[u][c]; gW[3] += y4.w * h[u][c];
-          zb[c] = 0.f;
         }
-        jet_bwd<ACT>(net.NF, net.NS, z[u], hb, zb);
+        jet_bwd_t<ACT, NF, NS, false>(z[u], hb, zb);
         if (nn < ne) {
           dbs += zb[0];
 #pragma unroll
@@ -706,8 +730,14 @@ int run_chunks(const WNet& n, const WideLayout& wl, float* ws, int mode, const p
     float* Z = ws + wl.Z;
     float* Hb = ws + wl.Hb;
     {
-      const int64_t tot = (int64_t)m * H;
-      first_fwd_kernel<ACT><<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(n, xs, n0, m, wl.Mc, Z, Hb);
+      const int64_t tot = (int64_t)((m + kFirstPPT - 1) / kFirstPPT) * H;
+      const unsigned fgrid = (unsigned)((tot + 255) / 256);
+      switch (n.NF * 4 + n.NS) {  // NS <= NF <= 3 (make_net)
+#define FIRST(F, S_) case F * 4 + S_: first_fwd_kernel<ACT, F, S_><<<fgrid, 256, 0, st>>>(n, xs, n0, m, wl.Mc, Z, Hb); break;
+        FIRST(0, 0) FIRST(1, 0) FIRST(1, 1) FIRST(2, 0) FIRST(2, 1) FIRST(2, 2) FIRST(3, 0) FIRST(3, 1) FIRST(3, 2) FIRST(3, 3)
+#undef FIRST
+        default: return PINN_E_UNSUPPORTED;
+      }
       count_launch(1);
     }
     for (int l = 2; l <= L; ++l) {
@@ -733,6 +763,7 @@ int run_chunks(const WNet& n, const WideLayout& wl, float* ws, int mode, const p
       const float* hl = Hb + (L - 1) * planes;
       float* yb = ws + wl.ybar;
       const dim3 bgrid((H + 127) / 128, kBlocks);
+#define HBWD(F, S_) case F * 4 + S_: head_bwd_kernel<ACT, F, S_><<<bgrid, 1024, 0, st>>>(n, yb, zl, hl, m, wl.Mc, ws + wl.head, dbl); break;
 #define HEAD(KI_, C_)                                                                                       \
   case C_: {                                                                                                \
     int ob = (C * m + 31) / 32;                                                                             \
@@ -743,8 +774,11 @@ int run_chunks(const WNet& n, const WideLayout& wl, float* ws, int mode, const p
     head_point_kernel<C_><<<pb, 256, 0, st>>>(n, ha, yb, m);                                                \
     count_launch(1);                                                                                        \
     if (mode != W_MODE_FWD && mode != W_MODE_LOSS) {                                                                 \
-      head_bwd_kernel<ACT, C_><<<bgrid, 1024, 0, st>>>(n, yb, zl, hl, m, wl.Mc, ws + wl.head,                \
-                                                        (direct && L >= 2) ? ws + wl.db + (size_t)(L - 2) * kBlocks * 8 * H : nullptr); \
+      float* dbl = (direct && L >= 2) ? ws + wl.db + (size_t)(L - 2) * kBlocks * 8 * H : nullptr;         \
+      switch (n.NF * 4 + n.NS) {                                                                            \
+        HBWD(0, 0) HBWD(1, 0) HBWD(1, 1) HBWD(2, 0) HBWD(2, 1) HBWD(2, 2) HBWD(3, 0) HBWD(3, 1) HBWD(3, 2) HBWD(3, 3) \
+        default: return PINN_E_UNSUPPORTED;                                                                 \
+      }                                                                                                     \
       count_launch(1);                                                                                      \
     }                                                                                                       \
   } break;
@@ -754,6 +788,7 @@ int run_chunks(const WNet& n, const WideLayout& wl, float* ws, int mode, const p
         switch (C) { HEAD(16, 1) HEAD(16, 2) HEAD(16, 3) HEAD(16, 4) HEAD(16, 5) HEAD(16, 6) HEAD(16, 7) default: return PINN_E_UNSUPPORTED; }
       }
 #undef HEAD
+#undef HBWD
       count_launch(1);
       CK(cudaGetLastError());
     }
