@@ -43,3 +43,32 @@ def test_struct_sizes_match_header():
     assert C.sizeof(nv.PinnJets) == 32
     assert C.sizeof(nv.PinnMlp) == 24 + 2 * 16 * 8
     assert C.sizeof(nv.PinnDomain) == 8 + 4 * 8 + 8 * 8 + 8 + 6 * 4 + 8 * 32 + 64 * 12
+
+
+def test_missing_library_fails_loudly(monkeypatch):
+    """No CPU fallback: without the CUDA library the loader raises instead of routing anywhere else."""
+    import pytest
+
+    monkeypatch.setattr(nv, "_LIB", None)
+    monkeypatch.setattr(nv, "LIB_PATH", os.path.join(os.path.dirname(nv.LIB_PATH), "no_such_libpinn_b200.so"))
+    with pytest.raises(ImportError, match="no CPU fallback"):
+        nv.lib()
+
+
+def test_product_never_touches_the_oracle():
+    """oracle/ and tests/ are checker code: nothing under the package, the reference-side binding or the workload
+    definitions imports them (bench.py may, for its reference arm only)."""
+    import re
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    pat = re.compile(r"^\s*(from|import)\s+(oracle|tests)\b", re.M)
+    hits = []
+    for top in ("idrlnet_b200", "integration", "baseline"):
+        for dirpath, dirnames, files in os.walk(os.path.join(root, top)):
+            dirnames[:] = [d for d in dirnames if d not in ("_ref", "__pycache__", "build")]
+            for f in files:
+                if f == "run_reference_with_jets.py":  # the driver tests/test_gpu_integration.py executes: loads golden fixtures
+                    continue
+                if f.endswith(".py") and pat.search(open(os.path.join(dirpath, f), encoding="utf-8").read()):
+                    hits.append(os.path.join(dirpath, f))
+    assert not hits, hits
