@@ -13,7 +13,7 @@ import torch.multiprocessing as mp
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-def _worker(rank, world, port, out):
+def _worker(rank, world, port, out, shared=False):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world),
                       IDRLNET_B200_LOGLEVEL="ERROR", IDRLNET_B200_DEVICE="cpu")
     sys.path.insert(0, ROOT)
@@ -32,8 +32,17 @@ def _worker(rank, world, port, out):
     torch.manual_seed(0)
     net = sc.get_net_node(inputs=("x", "t"), outputs=("u",), name="net1", arch=sc.Arch.mlp)
     import tempfile
-    s = sc.Solver(sample_domains=(d1, d2), netnodes=[net], pdes=[sc.BurgersNode(u="u", v=0.01)],
-                  network_dir=tempfile.mkdtemp(), loading=False)
+    nets, pdes, domains = [net], [sc.BurgersNode(u="u", v=0.01)], (d1, d2)
+    if shared:
+        # periodic boundary over a weight-sharing copy of the net on the shifted input (examples/allen_cahn/allen_cahn.py:94-118):
+        # the same Parameter objects sit in two NetNodes and must be summed over the ranks ONCE
+        x_, t_ = sp.Symbol("x"), sp.Symbol("t")
+        nets.append(sc.get_shared_net_node(net, inputs=("xp", "t"), outputs=("up",), name="net2", arch="mlp"))
+        pdes += [sc.ExpressionNode(name="xp", expression=x_ + 2),
+                 sc.ExpressionNode(name="gap", expression=sp.Function("u")(x_, t_) - sp.Function("up")(x_, t_))]
+        per = {"x": np.full((29, 1), -1.0), "t": rng.uniform(0, 1, (29, 1)), "area": np.full((29, 1), 1.0 / 29)}
+        domains += (sc.get_data_node(lambda: (dict(per), {"gap": 0.0}), name="periodic"),)
+    s = sc.Solver(sample_domains=domains, netnodes=nets, pdes=pdes, network_dir=tempfile.mkdtemp(), loading=False)
     params = list(net.net.parameters())
     # sharded step: each rank sees [rank::world] of every domain, gradients all-reduced
     s.optimizers[0].zero_grad()
@@ -63,11 +72,12 @@ def _free_port():
 
 
 @pytest.mark.timeout(300)
-def test_two_ranks_equal_one():
+@pytest.mark.parametrize("shared", [False, True], ids=["one_net", "shared_net"])
+def test_two_ranks_equal_one(shared):
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = _free_port()
-    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q, shared)) for r in range(2)]
     for p in procs:
         p.start()
     res = [q.get(timeout=240) for _ in procs]
